@@ -1,0 +1,150 @@
+"""Generate golden vectors by running the UNMODIFIED reference (imported from
+$PATCHGAN_REF, default /root/reference) on CPU.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/step_<case>.npz.  The reference cannot travel to the GPU box,
+so these fixtures (plus this script) are what pins ``oracle/patchgan_oracle.py``.
+
+Initial weights and inputs are produced by numpy RNG (oracle.UNet / Discriminator
+default init, ``synthetic_batch``) and loaded into the reference modules with
+``load_state_dict``, so the fixture only needs to hold OUTPUTS: for every tensor
+its mean, std and 256 evenly spaced samples.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = os.environ.get('PATCHGAN_REF', '/root/reference')
+sys.path.insert(0, REF)
+sys.modules.setdefault('torchinfo', types.SimpleNamespace(summary=lambda *a, **k: None))
+
+import torch  # noqa: E402
+from torch import optim  # noqa: E402
+
+import patchgan  # noqa: E402  (the reference)
+import patchgan.trainer as ref_trainer  # noqa: E402
+from oracle import patchgan_oracle as orc  # noqa: E402
+
+ref_trainer.device = 'cpu'
+
+CASES = {
+    # name: (G kwargs, D kwargs, loss_type, B, steps)
+    'tversky': (dict(input_nc=3, output_nc=1, nf=8, activation='leakyrelu', final_act='sigmoid'),
+                dict(input_nc=4, ndf=8, n_layers=3, norm=False), 'tversky', 2, 2),
+    'wbce': (dict(input_nc=3, output_nc=3, nf=8, activation='relu', final_act='sigmoid'),
+             dict(input_nc=6, ndf=8, n_layers=4, norm=True), 'weighted_bce', 2, 2),
+    'mae': (dict(input_nc=3, output_nc=2, nf=8, activation='tanh', final_act='softmax'),
+            dict(input_nc=5, ndf=8, n_layers=2, norm=False), 'MAE', 2, 2),
+}
+NS = 256
+
+
+def summarize(t):
+    a = np.asarray(t, dtype=np.float64).ravel()
+    idx = np.linspace(0, a.size - 1, min(NS, a.size)).astype(np.int64)
+    return np.concatenate([[a.mean(), a.std()], a[idx]])
+
+
+def run_case(name, gk, dk, loss_type, B, steps):
+    og = orc.UNet(**gk, seed=11)
+    od = orc.Discriminator(**dk, seed=12)
+    G = patchgan.UNet(**gk)
+    D = patchgan.Discriminator(**dk)
+    G.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in og.params.items()})
+    D.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in od.params.items()})
+    import tempfile
+    tr = patchgan.Trainer(G, D, tempfile.mkdtemp(), device='cpu')
+    tr.loss_type = loss_type
+    tr.gen_optimizer = optim.Adam(G.parameters(), lr=1e-3, betas=(0.9, 0.999))    # trainer.py:169-170
+    tr.disc_optimizer = optim.Adam(D.parameters(), lr=1e-3, betas=(0.9, 0.999))  # trainer.py:171-172
+    G.train()
+    D.train()
+    out = {}
+    acts = {}
+    hooks = []
+
+    def grab(key):
+        def hook(m, a, o):
+            if key not in acts:
+                acts[key] = o.detach().numpy().copy()
+        return hook
+    for i, blk in enumerate(G.encoder):
+        hooks.append(blk.register_forward_hook(grab(f'enc{i}')))
+    for i, blk in enumerate(G.decoder):
+        hooks.append(blk.register_forward_hook(grab(f'dec{i}')))
+    ends = [j - 1 for j in od.seq_idx[1:]] + [len(D.model) - 1]
+    for li, j in enumerate(ends):
+        hooks.append(D.model[j].register_forward_hook(grab(f'd{li}')))
+    for step in range(steps):
+        x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=1234 + step)
+        losses = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=True)
+        for k, v in losses.items():
+            out[f's{step}/loss/{k}'] = np.float64(v)
+        if step == 0:
+            for k, v in acts.items():
+                out[f's0/act/{k}'] = summarize(v)
+            for h in hooks:
+                h.remove()
+        for k, p in G.named_parameters():
+            out[f's{step}/ggrad/{k}'] = summarize(p.grad.numpy())
+            out[f's{step}/gw/{k}'] = summarize(p.detach().numpy())
+        for k, p in D.named_parameters():
+            out[f's{step}/dgrad/{k}'] = summarize(p.grad.numpy())
+            out[f's{step}/dw/{k}'] = summarize(p.detach().numpy())
+    # eval-mode forward / train=False batch (trainer.py:239-259)
+    G.eval()
+    D.eval()
+    x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=99)
+    losses = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=False)
+    for k, v in losses.items():
+        out[f'eval/loss/{k}'] = np.float64(v)
+    with torch.no_grad():
+        out['eval/gen_img'] = summarize(G(torch.from_numpy(x)).numpy())
+    np.savez_compressed(os.path.join(HERE, f'step_{name}.npz'), **out)
+    print(name, {k: float(v) for k, v in out.items() if '/loss/' in k and k.startswith('s0')})
+
+
+def losses_case():
+    """Direct calls of losses.py functions (incl. tversky / batch_mean=False)."""
+    from patchgan import losses as L
+    rng = np.random.default_rng(5)
+    p = rng.random((3, 2, 16, 16), dtype=np.float32)
+    t = (rng.random((3, 2, 16, 16)) > 0.6).astype(np.float32)
+    tp, tt = torch.from_numpy(p), torch.from_numpy(t)
+    out = dict(
+        tversky=L.tversky(tt, tp, 0.7).item(),
+        tversky_nb=L.tversky(tt, tp, 0.7, batch_mean=False).numpy(),
+        fc=L.fc_tversky(tt, tp, 0.75, 0.75).item(),
+        fc_nb=L.fc_tversky(tt, tp, 0.75, 0.75, batch_mean=False).numpy(),
+        mae=L.MAE_loss(tt, tp).item(),
+        bce=L.bce_loss(tp, tt).item(),
+    )
+    np.savez_compressed(os.path.join(HERE, 'losses.npz'), **out)
+
+
+def infer_case():
+    """n_crop / build_mask (infer.py:14-68) on a small non-trivial image."""
+    from patchgan import infer as I
+    rng = np.random.default_rng(7)
+    img = rng.random((3, 300, 300), dtype=np.float32)
+    crops = I.n_crop(torch.from_numpy(img), 128, 0.9).numpy()
+    masks = rng.random((crops.shape[0], 4, 128, 128), dtype=np.float32)
+    m_arg = I.build_mask(masks, 128, (300, 300), 0.0, 0.9)
+    m_thr = I.build_mask(masks[:, :1], 128, (300, 300), 0.5, 0.9)
+    np.savez_compressed(os.path.join(HERE, 'infer.npz'), crops_sum=summarize(crops),
+                        m_arg=m_arg.astype(np.int16), m_thr=m_thr.astype(np.float32))
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    for name, (gk, dk, lt, B, steps) in CASES.items():
+        run_case(name, gk, dk, lt, B, steps)
+    losses_case()
+    infer_case()
