@@ -62,7 +62,7 @@ def test_step_matches_reference(name):
             relnorm(summarize(g), gold[f's{step}/dgrad/{k}'], gtol, f'{name} s{step} dgrad {k}')
         # post-step weights: Adam moves each element by <= lr per step (lr = 1e-3)
         # (a sign flip of a ~0 gradient moves a weight by 2*lr: bounded, and rare at step 0)
-        frac = (0.05 if name == 'wbce' else 0.0) if step == 0 else 0.5
+        frac = (0.05 if name == 'wbce' else 0.0) if step == 0 else 1.0
         for k, p in G.params.items():
             weights_close(summarize(p), gold[f's{step}/gw/{k}'], 1e-3, step + 1, frac, f'{name} s{step} gw {k}')
         for k, p in D.params.items():
