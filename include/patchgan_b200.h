@@ -1,0 +1,189 @@
+/*
+ * patchgan_b200 -- C-ABI of the B200 (sm_100a) kernels under the patchGAN hot path.
+ *
+ * The reference (ramanakumars/patchGAN) has no FFI of its own: every arithmetic call is a
+ * PyTorch operator.  Each entry point below replaces the PyTorch operator call(s) at the cited
+ * reference line(s); the Python host side (patchgan_b200/*.py) binds them with ctypes and keeps
+ * the reference's module API (UNet / Discriminator / losses / Trainer).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller owns all memory (including workspaces); nothing is allocated or freed here;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises,
+ *     and is CUDA-graph capturable;
+ *   - return value: 0 on success, non-zero PgStatus otherwise; pg_last_error() gives the text
+ *     (thread-local);
+ *   - activations are NHWC bf16 with an explicit pixel stride `ld` (elements) so that a tensor can be a
+ *     channel slice of a wider buffer (virtual concat); channel counts seen by the conv kernels are
+ *     multiples of 16 (the host zero-pads 3/4/1/7-channel tensors and the packed weights);
+ *   - packed weights are bf16 [N][16 taps][C] (tap = kh*4+kw, C = C1+C2 in concat order).
+ */
+#ifndef PATCHGAN_B200_H
+#define PATCHGAN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum PgStatus {
+  PG_OK = 0,
+  PG_ERR_INVALID = 1,     /* bad argument / unsupported shape            */
+  PG_ERR_CUDA = 2,        /* a CUDA runtime / driver call failed         */
+  PG_ERR_UNSUPPORTED = 3  /* requested implementation cannot run this op */
+} PgStatus;
+
+typedef enum PgAct {
+  PG_ACT_NONE = 0,
+  PG_ACT_RELU = 1,
+  PG_ACT_LEAKYRELU = 2,   /* slope 0.2  (unet.py:17, disc.py:20) */
+  PG_ACT_TANH = 3,
+  PG_ACT_SIGMOID = 4
+} PgAct;
+
+typedef enum PgConvMode {
+  PG_CONV = 0,            /* nn.Conv2d(k=4, stride, pad)                          */
+  PG_CONVT = 1            /* nn.ConvTranspose2d(k=4, stride=2, pad=1)             */
+} PgConvMode;
+
+typedef enum PgImpl {
+  PG_IMPL_AUTO = 0,
+  PG_IMPL_SIMT = 1,       /* CUDA-core implicit GEMM (any shape; validation path)  */
+  PG_IMPL_TCGEN05 = 2     /* TMA + tcgen05.mma + TMEM implicit GEMM               */
+} PgImpl;
+
+/* Geometry of one 4x4 convolution-shaped contraction.
+ *   PG_CONV : out[b,oy,ox,n] = sum_{kh,kw,c} in[b, oy*stride-pad+kh, ox*stride-pad+kw, c] * W[n][kh*4+kw][c]
+ *   PG_CONVT: out[b,oy,ox,n] = sum_{kh,kw,c : oy=2*iy-1+kh, ox=2*ix-1+kw} in[b,iy,ix,c] * W[n][kh*4+kw][c]
+ * `in` is the virtual concat of src1 (C1 channels, stride ld1) and src2 (C2 channels, stride ld2).
+ * The same two forms express every data-gradient:
+ *   dgrad(Conv2d s=2)        = PG_CONVT over dY with W'[ci][tap][co]
+ *   dgrad(Conv2d s=1,p=1)    = PG_CONV stride 1 pad 2 over dY with taps flipped
+ *   dgrad(ConvTranspose2d)   = PG_CONV stride 2 pad 1 over dY with W'[ci][tap][co]
+ */
+typedef struct PgConvDesc {
+  int32_t mode;      /* PgConvMode */
+  int32_t stride;    /* PG_CONV: 1 or 2; PG_CONVT: 2 */
+  int32_t pad;       /* PG_CONV: 1 or 2; PG_CONVT: 1 */
+  int32_t B, Hin, Win;
+  int32_t Hout, Wout;
+  int32_t C1, C2;    /* multiples of 16; C2 = 0 without concat */
+  int32_t ld1, ld2;
+  int32_t N;         /* output channels computed, multiple of 16 */
+  int32_t ldo;       /* output pixel stride */
+  int32_t n_valid;   /* channels >= n_valid are stored as 0 (padding must stay 0 after sigmoid) */
+  int32_t act;       /* PgAct fused into the epilogue */
+  int32_t out_f32;   /* 0: bf16 output, 1: float output */
+  int32_t has_bias;
+} PgConvDesc;
+
+const char* pg_last_error(void);
+int pg_version(void);
+/* 1 if the library was built with the tcgen05 path and the current device is sm_100. */
+int pg_tcgen05_available(void);
+
+/* ---- convolutions: replaces aten::convolution behind nn.Conv2d / nn.ConvTranspose2d
+ *      (unet.py:19, unet.py:53, disc.py:19,27,37,45) and their autograd dgrad ---- */
+int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
+                const float* bias, void* out, int impl, void* stream);
+
+/* weight gradient of PG_CONV geometry `d` (autograd wgrad of unet.py:19,53 / disc.py:19-45):
+ *   dw[n*ld_n + c*16 + tap] += sum_{b,oy,ox} g[b,oy,ox,n] * a[b, oy*s-p+kh, ox*s-p+kw, c]
+ * g: [B,Hout,Wout] x N (stride ldg), a: [B,Hin,Win] x C1 (stride ld1).  Only n < n_real, c < c_real are
+ * written.  Accumulates atomically into dw (caller zeroes).  For ConvTranspose2d swap the roles:
+ * a = dY (2H x 2W), g = layer input.  `ws` = float workspace (>= pg_conv_wgrad_ws_bytes) or NULL. */
+int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw,
+                  int32_t ld_n, int32_t n_real, int32_t c_real, int impl, void* stream);
+
+/* bias gradient: db[n] += sum_m g[m*ldg + n], n < n_real (disc.py:19,45 biases) */
+int pg_colsum(const void* g, int64_t M, int32_t ldg, int32_t n_real, float* db, void* stream);
+
+/* ---- layout ---- */
+/* NCHW float -> NHWC bf16 channel slice [c_off, c_off+C) of a buffer with pixel stride ld
+ * (trainer.py:55-60,65,96: .to(device) + torch.cat feeding the nets) */
+int pg_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t B, int32_t C, int32_t H, int32_t W,
+                                  int32_t ld, int32_t c_off, void* stream);
+/* NHWC (bf16 or f32, pixel stride ld, channel offset c_off) -> NCHW float */
+int pg_unpack_nhwc_to_nchw_f32(const void* src, int32_t src_f32, float* dst, int32_t B, int32_t C, int32_t H,
+                               int32_t W, int32_t ld, int32_t c_off, void* stream);
+/* f32 NHWC (stride lds) channels [0,C) -> bf16 NHWC (stride ldd) channels [c_off, c_off+C) */
+int pg_copy_f32_to_bf16_slice(const float* src, int32_t lds, void* dst, int32_t ldd, int32_t c_off, int32_t C,
+                              int64_t npix, void* stream);
+/* fp32 reference-layout weight -> packed bf16 [Np][16][C1p+C2p].
+ * src element (n, c, tap) is at src[n*sn + c*sc + tap]; c < C1 maps to packed channel c, C1 <= c < C1+C2 maps to
+ * C1p + (c-C1); flip != 0 reverses the taps (15 - tap); everything else is zero. */
+int pg_pack_weight(const float* src, void* dst, int32_t N, int32_t Np, int32_t C1, int32_t C1p, int32_t C2,
+                   int32_t C2p, int64_t sn, int64_t sc, int32_t flip, void* stream);
+
+/* ---- InstanceNorm2d(affine=False, eps=1e-5) + activation + Dropout(0.2)
+ *      (unet.py:20-28,55-66; disc.py:32,42) ---- */
+/* sums[(b*C + c)*2 + {0,1}] += {sum, sum of squares} over the HW pixels of image b (caller zeroes sums) */
+int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_t HW, int32_t C, int32_t ld, float* sums,
+                      void* stream);
+/* y = dropout(act((x - mean) * rstd)); mean/rstd from sums (sums == NULL: no normalisation).
+ * drop_p == 0: no dropout; else keep = uniform(mix(*seed, salt), element index) >= drop_p, scaled 1/(1-p).
+ * seed is a DEVICE counter (so a captured CUDA graph draws a fresh mask every replay), salt is per layer;
+ * the mask is regenerated in backward from (seed, salt, index) -- no mask tensor is stored. */
+int pg_norm_act_fwd(const void* x, int32_t x_f32, const float* sums, void* y, int32_t y_f32, int32_t B, int64_t HW,
+                    int32_t C, int32_t ldx, int32_t ldy, int32_t act, float drop_p, const uint64_t* seed, uint64_t salt,
+                    void* stream);
+/* backward, pass 1: with dxhat = (dy1 [+ dy2]) * mask * act'(xhat):
+ *   bsums[(b*C+c)*2 + {0,1}] += {sum dxhat, sum dxhat*xhat}   (caller zeroes) */
+int pg_norm_act_bwd_reduce(const void* x, int32_t x_f32, const float* sums, const void* dy1, int32_t ld1,
+                           const void* dy2, int32_t ld2, float* bsums, int32_t B, int64_t HW, int32_t C, int32_t ldx,
+                           int32_t act, float drop_p, const uint64_t* seed, uint64_t salt, void* stream);
+/* backward, pass 2: dx = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat*xhat))  -> bf16 (stride lddx).
+ * sums == NULL (no norm): dx = dxhat. */
+int pg_norm_act_bwd_apply(const void* x, int32_t x_f32, const float* sums, const void* dy1, int32_t ld1,
+                          const void* dy2, int32_t ld2, const float* bsums, void* dx, int32_t lddx, int32_t B,
+                          int64_t HW, int32_t C, int32_t ldx, int32_t act, float drop_p, const uint64_t* seed,
+                          uint64_t salt, void* stream);
+/* *ctr += inc on the device (advances the dropout seed once per step, graph-capturable) */
+int pg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
+/* activation backward from the saved OUTPUT y (layers without norm: unet.py:97-99,106-107; disc.py):
+ *   dx = dy * act'(y)   (relu/leakyrelu/tanh/sigmoid are all recoverable from y) */
+int pg_act_bwd_from_output(const void* y, int32_t y_f32, int32_t ldy, const void* dy, int32_t lddy, void* dx,
+                           int32_t lddx, int64_t npix, int32_t C, int32_t act, void* stream);
+/* nn.Softmax(dim=1) over the first C channels of each pixel (unet.py:47), f32 NHWC in/out */
+int pg_softmax_fwd(const float* x, float* y, int64_t npix, int32_t C, int32_t ld, void* stream);
+
+/* ---- losses (losses.py:18-39, trainer.py:71-85,101-103) ---- */
+/* Per-sample sums for fc_tversky / weighted BCE / MAE over p (f32 NHWC, stride ld, C channels) and the
+ * target t (NCHW float, as given by the user):
+ *   part[b*8 + 0..4] += { sum t*p, sum t, sum p, sum |p-t|, sum_c w_c * bce(p,t) }   (caller zeroes)
+ *   chsum[b*C + c]  : input (sum_hw t) when wbce_w != NULL semantics are needed -- see pg_target_chsum. */
+int pg_target_chsum(const float* t, float* chsum, int32_t B, int32_t C, int64_t HW, void* stream);
+int pg_seg_loss_partials(const float* p, int32_t ld, const float* t, const float* chsum, float* part, int32_t B,
+                         int32_t C, int64_t HW, int32_t loss_type, void* stream);
+/* Finalise: writes losses[slot] = seg_alpha * loss and coef[b*4..] used by pg_gen_out_bwd.
+ * loss_type: 0 fc_tversky(beta,gamma), 1 weighted_bce, 2 MAE. */
+int pg_seg_loss_finalize(const float* part, float* coef, float* losses, int32_t slot, int32_t B, int32_t C,
+                         int64_t HW, int32_t loss_type, float beta, float gamma, float seg_alpha, void* stream);
+/* d(raw) of the generator's last layer: (dseg + dD) * final_act'(p)  -> bf16 NHWC (stride lddx).
+ * dD: bf16 NHWC gradient from the discriminator's first layer at channel offset dd_off (NULL: none).
+ * final_act: PgAct or 5 = softmax.  up = upstream scale of the seg loss (1.0). */
+int pg_gen_out_bwd(const float* p, int32_t ld, const float* t, const float* chsum, const float* coef,
+                   const void* dD, int32_t lddd, int32_t dd_off, void* dx, int32_t lddx, int32_t B, int32_t C,
+                   int64_t HW, int32_t loss_type, int32_t final_act, float beta, void* stream);
+/* nn.BCELoss(p, const label) on the discriminator map p (f32, one value per pixel, stride ld):
+ *   losses[slot] += mean bce;  if dz != NULL: dz[pix*lddz + 0] = gscale * dBCE/dp * p(1-p) (bf16), other
+ *   channels of the pixel (1..lddz-1) = 0.   (trainer.py:84,101,102 + disc.py:46 sigmoid backward) */
+int pg_bce_const(const float* p, int32_t ld, float label, float gscale, float* losses, int32_t slot, void* dz,
+                 int32_t lddz, int64_t npix, void* stream);
+
+/* ---- optim.Adam (trainer.py:169-172, 90, 107), one launch for a whole flat parameter buffer.
+ * hyper (device): [0] = lr.  step (device int32): number of steps taken so far; incremented by the call. ---- */
+int pg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int32_t* step,
+                 float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ---- inference tiling (infer.py:14-68), "next" row ---- */
+int pg_ncrop(const float* image, float* crops, int32_t C, int32_t H, int32_t W, int32_t size, int32_t eff,
+             int32_t ncy, int32_t ncx, void* stream);
+int pg_build_mask(const float* masks, float* mask_out, int32_t* argmax_out, int32_t C, int32_t H, int32_t W,
+                  int32_t size, int32_t eff, int32_t ncy, int32_t ncx, float threshold, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PATCHGAN_B200_H */

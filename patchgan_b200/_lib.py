@@ -1,0 +1,95 @@
+"""ctypes binding of libpatchgan_b200.so (the C-ABI declared in include/patchgan_b200.h).
+
+There is NO fallback: if the shared library is missing or cannot be loaded, importing the kernels
+raises, and every op raises when handed a non-CUDA tensor.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libpatchgan_b200.so')
+
+PG_CONV, PG_CONVT = 0, 1
+ACT = {'none': 0, None: 0, 'relu': 1, 'leakyrelu': 2, 'tanh': 3, 'sigmoid': 4, 'softmax': 5}
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+LOSS = {'tversky': 0, 'weighted_bce': 1, 'MAE': 2, 'none': 3}
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in (
+        'mode', 'stride', 'pad', 'B', 'Hin', 'Win', 'Hout', 'Wout', 'C1', 'C2', 'ld1', 'ld2', 'N', 'ldo',
+        'n_valid', 'act', 'out_f32', 'has_bias')]
+
+
+vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
+DP = C.POINTER(ConvDesc)
+
+_SIGS = {
+    'pg_version': ([], C.c_int),
+    'pg_tcgen05_available': ([], C.c_int),
+    'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
+    'pg_conv_wgrad': ([DP, vp, vp, i32, vp, i32, i32, i32, C.c_int, vp], C.c_int),
+    'pg_colsum': ([vp, i64, i32, i32, vp, vp], C.c_int),
+    'pg_pack_nchw_f32_to_nhwc_bf16': ([vp, vp, i32, i32, i32, i32, i32, i32, vp], C.c_int),
+    'pg_unpack_nhwc_to_nchw_f32': ([vp, i32, vp, i32, i32, i32, i32, i32, i32, vp], C.c_int),
+    'pg_copy_f32_to_bf16_slice': ([vp, i32, vp, i32, i32, i32, i64, vp], C.c_int),
+    'pg_pack_weight': ([vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i32, vp], C.c_int),
+    'pg_instnorm_stats': ([vp, i32, i32, i64, i32, i32, vp, vp], C.c_int),
+    'pg_norm_act_fwd': ([vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, i32, f32, vp, u64, vp], C.c_int),
+    'pg_norm_act_bwd_reduce': ([vp, i32, vp, vp, i32, vp, i32, vp, i32, i64, i32, i32, i32, f32, vp, u64, vp], C.c_int),
+    'pg_norm_act_bwd_apply': ([vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, f32, vp, u64, vp],
+                              C.c_int),
+    'pg_act_bwd_from_output': ([vp, i32, i32, vp, i32, vp, i32, i64, i32, i32, vp], C.c_int),
+    'pg_softmax_fwd': ([vp, vp, i64, i32, i32, vp], C.c_int),
+    'pg_target_chsum': ([vp, vp, i32, i32, i64, vp], C.c_int),
+    'pg_seg_loss_partials': ([vp, i32, vp, vp, vp, i32, i32, i64, i32, vp], C.c_int),
+    'pg_seg_loss_finalize': ([vp, vp, vp, i32, i32, i32, i64, i32, f32, f32, f32, vp], C.c_int),
+    'pg_gen_out_bwd': ([vp, i32, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i64, i32, i32, f32, vp], C.c_int),
+    'pg_bce_const': ([vp, i32, f32, f32, vp, i32, vp, i32, i64, vp], C.c_int),
+    'pg_adam_step': ([vp, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, vp], C.c_int),
+    'pg_counter_add': ([vp, u64, vp], C.c_int),
+    'pg_ncrop': ([vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], C.c_int),
+    'pg_build_mask': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp], C.c_int),
+}
+
+_lib = None
+
+
+class KernelLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the shared library; raises KernelLibraryError if it is not there."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KernelLibraryError(
+                f'{LIB_PATH} is missing: build it with `python -m patchgan_b200.build` '
+                '(nvcc, sm_100a).  patchgan_b200 has no CPU or library fallback.')
+        try:
+            handle = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise KernelLibraryError(f'cannot load {LIB_PATH}: {e}') from e
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(handle, name)
+            fn.argtypes = args
+            fn.restype = res
+        handle.pg_last_error.restype = C.c_char_p
+        handle.pg_last_error.argtypes = []
+        _lib = handle
+    return _lib
+
+
+def exported_symbols():
+    return ['pg_last_error'] + list(_SIGS)
+
+
+def check(status, what=''):
+    if status != 0:
+        msg = lib().pg_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'patchgan_b200 kernel call failed ({what}, status {status}): {msg}')
+
+
+def call(name, *args):
+    check(getattr(lib(), name)(*args), name)

@@ -1,0 +1,100 @@
+// C-ABI glue: error text, argument validation, implementation dispatch.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace pg {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+    return PG_ERR_CUDA;
+  }
+  return PG_OK;
+}
+
+int conv_fwd_simt(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, cudaStream_t);
+int conv_wgrad_simt(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
+// conv_tc.cu
+int conv_fwd_tc(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, cudaStream_t);
+bool conv_fwd_tc_supported(const PgConvDesc*, const void*, const void*, const void*, const void*);
+int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
+bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int);
+bool tc_device_ok();
+
+static int validate(const PgConvDesc* d, const char* who) {
+  PG_REQUIRE(d != nullptr, "%s: desc is NULL", who);
+  PG_REQUIRE(d->mode == PG_CONV || d->mode == PG_CONVT, "%s: bad mode %d", who, d->mode);
+  PG_REQUIRE(d->B > 0 && d->Hin > 0 && d->Win > 0 && d->Hout > 0 && d->Wout > 0, "%s: empty extent", who);
+  PG_REQUIRE(d->C1 > 0 && d->C1 % 16 == 0 && d->C2 >= 0 && d->C2 % 16 == 0, "%s: C1=%d C2=%d must be multiples of 16",
+             who, d->C1, d->C2);
+  PG_REQUIRE(d->N > 0 && d->N % 16 == 0, "%s: N=%d must be a multiple of 16", who, d->N);
+  PG_REQUIRE(d->ld1 >= d->C1 && d->ld1 % 8 == 0 && (d->C2 == 0 || (d->ld2 >= d->C2 && d->ld2 % 8 == 0)),
+             "%s: bad pixel strides", who);
+  PG_REQUIRE(d->ldo >= d->N && d->ldo % 8 == 0, "%s: bad output stride %d", who, d->ldo);
+  if (d->mode == PG_CONV) {
+    PG_REQUIRE((d->stride == 1 || d->stride == 2) && (d->pad == 1 || d->pad == 2), "%s: stride/pad unsupported", who);
+    PG_REQUIRE(d->Hout == (d->Hin + 2 * d->pad - 4) / d->stride + 1 && d->Wout == (d->Win + 2 * d->pad - 4) / d->stride + 1,
+               "%s: Hout/Wout inconsistent with Hin/Win", who);
+  } else {
+    PG_REQUIRE(d->stride == 2 && d->pad == 1 && d->Hout == 2 * d->Hin && d->Wout == 2 * d->Win,
+               "%s: convT needs stride 2 pad 1 and Hout = 2 Hin", who);
+  }
+  return PG_OK;
+}
+
+}  // namespace pg
+using namespace pg;
+
+extern "C" const char* pg_last_error(void) { return g_err; }
+extern "C" int pg_version(void) { return 100; }
+extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
+
+extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
+                           const float* bias, void* out, int impl, void* stream) {
+  if (int e = validate(d, "pg_conv_fwd")) return e;
+  PG_REQUIRE(src1 && w_packed && out && (d->C2 == 0 || src2), "pg_conv_fwd: NULL pointer");
+  PG_REQUIRE(!d->has_bias || bias, "pg_conv_fwd: has_bias but bias is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (impl == PG_IMPL_SIMT) return conv_fwd_simt(d, src1, src2, w_packed, bias, out, s);
+  const bool ok = conv_fwd_tc_supported(d, src1, src2, w_packed, out);
+  if (impl == PG_IMPL_TCGEN05) {
+    if (!ok) {
+      set_error("pg_conv_fwd: tcgen05 path does not support this shape / alignment");
+      return PG_ERR_UNSUPPORTED;
+    }
+    return conv_fwd_tc(d, src1, src2, w_packed, bias, out, s);
+  }
+  if (ok) return conv_fwd_tc(d, src1, src2, w_packed, bias, out, s);
+  return conv_fwd_simt(d, src1, src2, w_packed, bias, out, s);
+}
+
+extern "C" int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw, int32_t ld_n,
+                             int32_t n_real, int32_t c_real, int impl, void* stream) {
+  if (int e = validate(d, "pg_conv_wgrad")) return e;
+  PG_REQUIRE(d->mode == PG_CONV && d->C2 == 0, "pg_conv_wgrad: geometry must be PG_CONV with one source");
+  PG_REQUIRE(a && g && dw && ldg >= d->N && ldg % 8 == 0, "pg_conv_wgrad: bad pointers / ldg");
+  PG_REQUIRE(n_real <= d->N && c_real <= d->C1, "pg_conv_wgrad: n_real / c_real exceed padded extents");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (impl == PG_IMPL_SIMT) return conv_wgrad_simt(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
+  const bool ok = conv_wgrad_tc_supported(d, a, g, ldg);
+  if (impl == PG_IMPL_TCGEN05) {
+    if (!ok) {
+      set_error("pg_conv_wgrad: tcgen05 path does not support this shape / alignment");
+      return PG_ERR_UNSUPPORTED;
+    }
+    return conv_wgrad_tc(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
+  }
+  if (ok) return conv_wgrad_tc(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
+  return conv_wgrad_simt(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
+}

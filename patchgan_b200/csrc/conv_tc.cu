@@ -1,0 +1,457 @@
+// Implicit-GEMM 4x4 convolutions on the 5th-generation tensor cores (sm_100a):
+//   TMA (cp.async.bulk.tensor, tiled mode with element strides + zero OOB fill) -> 128B-swizzled smem
+//   -> tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
+//
+// No im2col is ever materialised.  For every (tap, channel-chunk) k-step the A operand is ONE TMA box of
+// the NHWC activation tensor:
+//   PG_CONV  : box {BK ch, TW*s (step s), TH*s (step s), TB} at (c, ox0*s-pad+kw, oy0*s-pad+kh, b0)
+//   PG_CONVT : per output-parity class (py,px) a stride-1 box {BK, TW, TH, TB} at (c, x0+px-i, y0+py-j, b0)
+// padding = TMA out-of-bounds zero fill; the skip concat = a second tensor map (K loop walks src1 then src2).
+// The B operand is a 2D box {BK, BN} of the packed weights [N][16*Ctot].
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
+// warps 2..5 = epilogue (each owns the TMEM lane quarter warp_id % 4).
+// Reference ops replaced: aten::convolution under nn.Conv2d / nn.ConvTranspose2d (unet.py:19,53; disc.py:19-45)
+// and their dgrad.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace pg {
+
+// --------------------------------------------------------------------------------------------
+// PTX wrappers
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("conv_tc: mbarrier timeout (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+      "[%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address [0,14), LBO [16,30),
+// SBO [32,46), version=1 [46,48), layout type [61,64)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                      // LBO (unused for swizzled K-major)
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;       // stride between 8-row groups
+  d |= (uint64_t)1 << 46;                      // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+// --------------------------------------------------------------------------------------------
+// kernel
+// --------------------------------------------------------------------------------------------
+struct TcParams {
+  int mode, stride, pad;
+  int B, Ha, Wa, Hout, Wout;
+  int TW, TH, lgTW, lgTH, TB;
+  int nx, ny;
+  int BN, BK, nk1, nk2, ntaps, Ctot;
+  int N, ldo, n_valid, act, out_f32;
+  const float* bias;
+  void* out;
+  uint32_t idesc, sbo, layout_type;
+  int stages;
+  uint32_t a_bytes, b_bytes, tx_bytes;
+  uint32_t tmem_cols;
+};
+
+constexpr int TC_THREADS = 192;
+constexpr int MAX_STAGES = 8;
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
+               const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_sh;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // dynamic smem base rounded up to 1024 B (SWIZZLE_128B atoms)
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + p.stages * p.a_bytes;
+
+  // tile coordinates
+  const int tile = blockIdx.x;
+  const int tx_i = tile % p.nx;
+  const int ty_i = (tile / p.nx) % p.ny;
+  const int tb_i = tile / (p.nx * p.ny);
+  const int x0 = tx_i * p.TW, y0 = ty_i * p.TH, b0 = tb_i * p.TB;
+  const int n0 = blockIdx.y * p.BN;
+  const int py = blockIdx.z >> 1, px = blockIdx.z & 1;
+  const int nk = p.nk1 + p.nk2;
+  const int ksteps = p.ntaps * nk;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapA1);
+    if (p.nk2 > 0) prefetch_tmap(&mapA2);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&acc_bar), 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_sh), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_sh;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = 0; t < p.ntaps; ++t) {
+        int cx, cy, wtap;
+        if (p.mode == PG_CONVT) {
+          const int j = t >> 1, i = t & 1;
+          wtap = ((1 - py) + 2 * j) * 4 + (1 - px) + 2 * i;
+          cx = x0 + px - i;
+          cy = y0 + py - j;
+        } else {
+          const int kh = t >> 2, kw = t & 3;
+          wtap = t;
+          cx = x0 * p.stride - p.pad + kw;
+          cy = y0 * p.stride - p.pad + kh;
+        }
+        for (int ck = 0; ck < nk; ++ck) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, p.tx_bytes);
+          if (ck < p.nk1) tma_load_4d(a_base + stage * p.a_bytes, &mapA1, fb, ck * p.BK, cx, cy, b0);
+          else tma_load_4d(a_base + stage * p.a_bytes, &mapA2, fb, (ck - p.nk1) * p.BK, cx, cy, b0);
+          tma_load_2d(b_base + stage * p.b_bytes, &mapB, fb, wtap * p.Ctot + ck * p.BK, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int kk = p.BK >> 4;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint64_t adesc = make_smem_desc(a_base + stage * p.a_bytes, p.sbo, p.layout_type);
+        const uint64_t bdesc = make_smem_desc(b_base + stage * p.b_bytes, p.sbo, p.layout_type);
+        for (int k = 0; k < kk; ++k) {
+          // +32 bytes (16 bf16) along K inside the swizzle row: start-address field += 2
+          umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (ks | k) ? 1u : 0u);
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      umma_commit(smem_u32(&acc_bar));
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;            // accumulator row == lattice point inside the tile
+    const int xl = r & (p.TW - 1);
+    const int yl = (r >> p.lgTW) & (p.TH - 1);
+    const int bl = r >> (p.lgTW + p.lgTH);
+    const int b = b0 + bl, a = y0 + yl, bb = x0 + xl;
+    const bool valid = b < p.B && a < p.Ha && bb < p.Wa;
+    int oy = a, ox = bb;
+    if (p.mode == PG_CONVT) { oy = 2 * a + py; ox = 2 * bb + px; }
+    const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
+    mbar_wait(smem_u32(&acc_bar), 0);
+    tc_fence_after();
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      if (valid) {
+        const int n = n0 + c;
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float x = __uint_as_float(v[j]);
+          if (p.bias != nullptr && n + j < p.n_valid) x += __ldg(p.bias + n + j);
+          x = act_apply(p.act, x);
+          f[j] = (n + j < p.n_valid) ? x : 0.f;
+        }
+        if (p.out_f32) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n);
+          o[0] = pack8(f);
+          o[1] = pack8(f + 8);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, p.tmem_cols);
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// host side
+// --------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+    else
+      cudaGetLastError();
+  }
+  return fn;
+}
+
+bool tc_device_ok() {
+  static int ok = -1;
+  if (ok < 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); ok = 0; return false; }
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    ok = (major == 10 && get_encode() != nullptr) ? 1 : 0;
+  }
+  return ok == 1;
+}
+
+static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
+
+struct TcPlan {
+  TcParams p;
+  int swz;  // bytes
+  dim3 grid;
+  size_t smem;
+};
+
+static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
+  TcParams& p = pl.p;
+  memset(&p, 0, sizeof(p));
+  p.mode = d->mode; p.stride = d->stride; p.pad = d->pad; p.B = d->B;
+  if (d->mode == PG_CONVT) { p.Ha = d->Hin; p.Wa = d->Win; p.ntaps = 4; }
+  else { p.Ha = d->Hout; p.Wa = d->Wout; p.ntaps = 16; }
+  p.Hout = d->Hout; p.Wout = d->Wout;
+  p.TW = pow2_ceil(p.Wa); if (p.TW > 128) p.TW = 128;
+  p.TH = pow2_ceil(p.Ha); if (p.TH > 128 / p.TW) p.TH = 128 / p.TW;
+  p.TB = 128 / (p.TW * p.TH);
+  p.lgTW = ilog2(p.TW); p.lgTH = ilog2(p.TH);
+  p.nx = (p.Wa + p.TW - 1) / p.TW; p.ny = (p.Ha + p.TH - 1) / p.TH;
+  const int nb = (p.B + p.TB - 1) / p.TB;
+  // channel chunk: largest of 64/32/16 dividing both sources
+  int bk = 64;
+  while (bk > 16 && ((d->C1 % bk) != 0 || (d->C2 % bk) != 0)) bk >>= 1;
+  if ((d->C1 % bk) != 0 || (d->C2 % bk) != 0) return false;
+  p.BK = bk; p.nk1 = d->C1 / bk; p.nk2 = d->C2 / bk; p.Ctot = d->C1 + d->C2;
+  int bn = 256;
+  while (bn > 16 && (d->N % bn) != 0) bn >>= 1;
+  if ((d->N % bn) != 0) return false;
+  p.BN = bn;
+  p.N = d->N; p.ldo = d->ldo; p.n_valid = d->n_valid; p.act = d->act; p.out_f32 = d->out_f32;
+  pl.swz = bk * 2;
+  p.layout_type = pl.swz == 128 ? 2u : (pl.swz == 64 ? 4u : 6u);
+  p.sbo = 8u * pl.swz;
+  // instruction descriptor: c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), K-major both, N>>3 at 17, M>>4 at 24
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.a_bytes = 128u * pl.swz;
+  p.b_bytes = ((uint32_t)bn * pl.swz + 1023u) & ~1023u;
+  p.tx_bytes = 128u * pl.swz + (uint32_t)bn * pl.swz;
+  const uint32_t per_stage = p.a_bytes + p.b_bytes;
+  int stages = (int)((200u * 1024u) / per_stage);
+  if (stages > MAX_STAGES) stages = MAX_STAGES;
+  const int ksteps = p.ntaps * (p.nk1 + p.nk2);
+  if (stages > ksteps) stages = ksteps;
+  if (stages < 1) return false;
+  p.stages = stages;
+  p.tmem_cols = bn < 32 ? 32u : (uint32_t)bn;
+  pl.smem = (size_t)stages * per_stage + 1024;
+  pl.grid = dim3((unsigned)(p.nx * p.ny * nb), (unsigned)(d->N / bn), d->mode == PG_CONVT ? 4 : 1);
+  // TMA box limits
+  const int es = d->mode == PG_CONV ? d->stride : 1;
+  if (p.TW * es > 256 || p.TH * es > 256 || p.TB > 256) return false;
+  return true;
+}
+
+bool conv_fwd_tc_supported(const PgConvDesc* d, const void* src1, const void* src2, const void* w, const void* out) {
+  if (!tc_device_ok()) return false;
+  if ((((uintptr_t)src1 | (uintptr_t)src2 | (uintptr_t)w | (uintptr_t)out) & 15) != 0) return false;
+  TcPlan pl;
+  return make_plan(d, pl);
+}
+
+static int encode_act_map(CUtensorMap* m, const void* base, int C, int ld, int B, int H, int W, int bk, int tw, int th,
+                          int tb, int es, int swz) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(tw * es), (cuuint32_t)(th * es), (cuuint32_t)tb};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                     : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(activation C=%d ld=%d B=%d H=%d W=%d box=%d,%d,%d,%d es=%d) failed: %d", C, ld, B,
+              H, W, bk, tw * es, th * es, tb, es, (int)r);
+    return PG_ERR_CUDA;
+  }
+  return PG_OK;
+}
+
+int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const void* w, const float* bias, void* out,
+                cudaStream_t stream) {
+  TcPlan pl;
+  if (!make_plan(d, pl)) {
+    set_error("conv_fwd_tc: unsupported shape");
+    return PG_ERR_UNSUPPORTED;
+  }
+  TcParams& p = pl.p;
+  p.bias = d->has_bias ? bias : nullptr;
+  p.out = out;
+  const int es = d->mode == PG_CONV ? d->stride : 1;
+  CUtensorMap mA1, mA2, mB;
+  if (int e = encode_act_map(&mA1, src1, d->C1, d->ld1, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB, es, pl.swz))
+    return e;
+  if (d->C2 > 0) {
+    if (int e = encode_act_map(&mA2, src2, d->C2, d->ld2, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB, es, pl.swz))
+      return e;
+  } else {
+    mA2 = mA1;
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)16 * p.Ctot, (cuuint64_t)d->N};
+    cuuint64_t strides[1] = {(cuuint64_t)16 * p.Ctot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)p.BN};
+    cuuint32_t estr[2] = {1, 1};
+    CUtensorMapSwizzle sw = pl.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                          : (pl.swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    CUresult r = get_encode()(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(weights K=%d N=%d) failed: %d", 16 * p.Ctot, d->N, (int)r);
+      return PG_ERR_CUDA;
+    }
+  }
+  static size_t smem_set = 0;
+  if (pl.smem > smem_set) {
+    PG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    smem_set = 227 * 1024;
+  }
+  conv_tc_kernel<<<pl.grid, TC_THREADS, pl.smem, stream>>>(mA1, mA2, mB, p);
+  return check_launch("conv_tc_kernel");
+}
+
+// tensor-core wgrad: not in this revision (the SIMT kernel serves it)
+bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int) { return false; }
+int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t) {
+  set_error("conv_wgrad_tc: not implemented");
+  return PG_ERR_UNSUPPORTED;
+}
+
+}  // namespace pg

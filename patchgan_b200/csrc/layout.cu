@@ -1,0 +1,103 @@
+// Layout kernels: NCHW float <-> NHWC bf16 channel slices, weight packing.  HBM-bound byte movers.
+// Reference: trainer.py:55-66,96-99 (.to(device) + torch.cat that feed the two nets).
+#include "common.cuh"
+
+namespace pg {
+
+// one thread per pixel; reads are coalesced per channel plane, each thread writes its C channels
+__global__ void pack_nchw_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int C, long long HW, int ld,
+                                 int c_off) {
+  const int b = blockIdx.y;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    bf16* o = dst + ((long long)b * HW + p) * ld + c_off;
+    const float* s = src + (long long)b * C * HW + p;
+    for (int c = 0; c < C; ++c) o[c] = __float2bfloat16(s[(long long)c * HW]);
+  }
+}
+
+__global__ void unpack_nhwc_kernel(const void* __restrict__ src, int src_f32, float* __restrict__ dst, int C,
+                                   long long HW, int ld, int c_off) {
+  const int b = blockIdx.y;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    float* o = dst + (long long)b * C * HW + p;
+    const long long base = ((long long)b * HW + p) * ld + c_off;
+    for (int c = 0; c < C; ++c) {
+      float v = src_f32 ? reinterpret_cast<const float*>(src)[base + c]
+                        : __bfloat162float(reinterpret_cast<const bf16*>(src)[base + c]);
+      o[(long long)c * HW] = v;
+    }
+  }
+}
+
+__global__ void copy_f32_to_bf16_slice_kernel(const float* __restrict__ src, int lds, bf16* __restrict__ dst, int ldd,
+                                              int c_off, int C, long long npix) {
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
+       p += (long long)gridDim.x * blockDim.x) {
+    for (int c = 0; c < C; ++c) dst[p * ldd + c_off + c] = __float2bfloat16(src[p * lds + c]);
+  }
+}
+
+// dst[n][t][cp] over the padded extents; gathers from the fp32 reference layout
+__global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N, int Np, int C1,
+                                   int C1p, int C2, int C2p, long long sn, long long sc, int flip) {
+  const int Cp = C1p + C2p;
+  const long long total = (long long)Np * 16 * Cp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int cp = (int)(i % Cp);
+    const int t = (int)((i / Cp) % 16);
+    const int n = (int)(i / ((long long)Cp * 16));
+    int c = -1;
+    if (cp < C1p) { if (cp < C1) c = cp; }
+    else { if (cp - C1p < C2) c = C1 + (cp - C1p); }
+    float v = 0.f;
+    if (n < N && c >= 0) v = src[n * sn + c * sc + (flip ? 15 - t : t)];
+    dst[i] = __float2bfloat16(v);
+  }
+}
+
+static unsigned grid1d(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = 16LL * num_sms();
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (unsigned)b;
+}
+
+}  // namespace pg
+using namespace pg;
+
+extern "C" int pg_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t B, int32_t C, int32_t H, int32_t W,
+                                             int32_t ld, int32_t c_off, void* stream) {
+  PG_REQUIRE(B > 0 && C > 0 && c_off >= 0 && c_off + C <= ld, "pg_pack_nchw: bad C=%d c_off=%d ld=%d", C, c_off, ld);
+  const long long HW = (long long)H * W;
+  dim3 grid(grid1d(HW, 256), B);
+  pack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, C, HW, ld, c_off);
+  return check_launch("pack_nchw_kernel");
+}
+
+extern "C" int pg_unpack_nhwc_to_nchw_f32(const void* src, int32_t src_f32, float* dst, int32_t B, int32_t C,
+                                          int32_t H, int32_t W, int32_t ld, int32_t c_off, void* stream) {
+  PG_REQUIRE(B > 0 && C > 0 && c_off >= 0 && c_off + C <= ld, "pg_unpack_nhwc: bad C=%d c_off=%d ld=%d", C, c_off, ld);
+  const long long HW = (long long)H * W;
+  dim3 grid(grid1d(HW, 256), B);
+  unpack_nhwc_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, src_f32, dst, C, HW, ld, c_off);
+  return check_launch("unpack_nhwc_kernel");
+}
+
+extern "C" int pg_copy_f32_to_bf16_slice(const float* src, int32_t lds, void* dst, int32_t ldd, int32_t c_off,
+                                         int32_t C, int64_t npix, void* stream) {
+  PG_REQUIRE(C > 0 && C <= lds && c_off + C <= ldd, "pg_copy_f32_to_bf16_slice: bad C=%d", C);
+  copy_f32_to_bf16_slice_kernel<<<grid1d(npix, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (bf16*)dst, ldd, c_off,
+                                                                                    C, npix);
+  return check_launch("copy_f32_to_bf16_slice_kernel");
+}
+
+extern "C" int pg_pack_weight(const float* src, void* dst, int32_t N, int32_t Np, int32_t C1, int32_t C1p, int32_t C2,
+                              int32_t C2p, int64_t sn, int64_t sc, int32_t flip, void* stream) {
+  PG_REQUIRE(N <= Np && C1 <= C1p && C2 <= C2p, "pg_pack_weight: padded extents smaller than real ones");
+  const long long total = (long long)Np * 16 * (C1p + C2p);
+  pack_weight_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, N, Np, C1, C1p, C2, C2p, sn,
+                                                                          sc, flip);
+  return check_launch("pack_weight_kernel");
+}

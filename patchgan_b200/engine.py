@@ -1,0 +1,450 @@
+"""Host-side schedule of the sm_100a kernels for the U-Net generator and the PatchGAN discriminator.
+
+This is the layer between the reference-shaped ``nn.Module`` API (unet.py / disc.py / trainer.py in this
+package) and the C-ABI library: it owns the packed bf16 weights, allocates NHWC activations with torch,
+and issues forward / data-gradient / weight-gradient launches on the current CUDA stream.  torch is used
+for memory and streams only; no torch operator does arithmetic on this path.
+
+Layer semantics follow the reference: ``DownSampleBlock`` (/root/reference/patchgan/unet.py:8-35),
+``UpSampleBlock`` (unet.py:38-72), ``UNet.forward`` (unet.py:112-134), ``Discriminator`` (disc.py:8-51).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import torch
+
+from . import _lib as L
+
+DROP_P = 0.2  # nn.Dropout(0.2), unet.py:28,65
+
+
+def rup16(c):
+    return (c + 15) // 16 * 16
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(t, what):
+    if not (isinstance(t, torch.Tensor) and t.is_cuda):
+        raise RuntimeError(f'patchgan_b200: {what} must be a CUDA tensor -- this package runs on sm_100a '
+                           'kernels only and has no CPU path')
+
+
+class Act:
+    """A (possibly channel-sliced) NHWC activation: keeps its storage alive, carries ptr / C / pixel stride."""
+    __slots__ = ('t', 'ptr', 'C', 'ld', 'B', 'H', 'W', 'f32')
+
+    def __init__(self, t, B, H, W, C, ld=None, off=0, f32=False):
+        self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
+        self.ld = ld if ld is not None else C
+        self.f32 = f32
+        self.ptr = t.data_ptr() + off * (4 if f32 else 2)
+
+    def slice(self, c0, C):
+        return Act(self.t, self.B, self.H, self.W, C, self.ld, (self.ptr - self.t.data_ptr()) // (4 if self.f32 else 2) + c0,
+                   self.f32)
+
+    def first(self, nb):
+        """The first nb images of the batch (same storage)."""
+        a = Act(self.t, nb, self.H, self.W, self.C, self.ld, 0, self.f32)
+        a.ptr = self.ptr
+        return a
+
+
+def new_act(B, H, W, C, device, f32=False, zero=False):
+    fn = torch.zeros if zero else torch.empty
+    t = fn((B, H, W, C), device=device, dtype=torch.float32 if f32 else torch.bfloat16)
+    return Act(t, B, H, W, C, f32=f32)
+
+
+def conv_desc(mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo, n_valid=None, act=0, out_f32=0,
+              has_bias=0):
+    return L.ConvDesc(mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo,
+                      N if n_valid is None else n_valid, act, out_f32, has_bias)
+
+
+class Config:
+    """Process-wide switches (tests flip `impl` to compare the tcgen05 path with the SIMT path).
+    PATCHGAN_B200_IMPL = auto | simt | tcgen05 selects the convolution implementation."""
+    impl = {'auto': L.IMPL_AUTO, 'simt': L.IMPL_SIMT, 'tcgen05': L.IMPL_TCGEN05}[
+        os.environ.get('PATCHGAN_B200_IMPL', 'auto')]
+
+
+def run_conv(desc, src1, src2, w, bias, out):
+    L.call('pg_conv_fwd', ctypes.byref(desc), src1.ptr, src2.ptr if src2 is not None else None, w.data_ptr(),
+           bias.data_ptr() if bias is not None else None, out.ptr, Config.impl, _stream())
+
+
+def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real):
+    L.call('pg_conv_wgrad', ctypes.byref(desc), a.ptr, g.ptr, g.ld, dw_ptr, ld_n, n_real, c_real, Config.impl, _stream())
+
+
+class LayerSpec:
+    """One 4x4 convolution layer of either network."""
+
+    def __init__(self, kind, stride, c1, c2, cout, bias, act, norm, dropout, wname, bname=None, norm_after_act=False):
+        self.kind, self.stride, self.c1, self.c2, self.cout = kind, stride, c1, c2, cout
+        self.bias, self.act, self.norm, self.dropout = bias, act, norm, dropout
+        self.wname, self.bname, self.norm_after_act = wname, bname, norm_after_act
+        self.c1p, self.c2p, self.np = rup16(c1), (rup16(c2) if c2 else 0), rup16(cout)
+        self.cin, self.cinp = c1 + c2, self.c1p + self.c2p
+
+
+class PackedWeights:
+    """bf16 operand copies of one layer's fp32 weight: forward form [Np][16][Cinp], dgrad form [Cinp][16][Np]."""
+
+    def __init__(self, spec, device):
+        self.spec = spec
+        self.fwd = torch.empty((spec.np, 16, spec.cinp), device=device, dtype=torch.bfloat16)
+        self.bwd = torch.empty((spec.cinp, 16, spec.np), device=device, dtype=torch.bfloat16)
+
+    def pack(self, w):
+        s, st = self.spec, _stream()
+        wp = w.data_ptr()
+        if s.kind == 'conv':      # w: (cout, cin, 4, 4)
+            L.call('pg_pack_weight', wp, self.fwd.data_ptr(), s.cout, s.np, s.c1, s.c1p, 0, 0, s.cin * 16, 16, 0, st)
+            # dgrad operand W'[ci][tap][co]; stride-1 layers run dgrad as a flipped stride-1 conv
+            L.call('pg_pack_weight', wp, self.bwd.data_ptr(), s.cin, s.cinp, s.cout, s.np, 0, 0, 16, s.cin * 16,
+                   1 if s.stride == 1 else 0, st)
+        else:                     # convT, w: (cin_total, cout, 4, 4)
+            L.call('pg_pack_weight', wp, self.fwd.data_ptr(), s.cout, s.np, s.c1, s.c1p, s.c2, s.c2p, 16, s.cout * 16, 0,
+                   st)
+            # rows of the dgrad operand live in the padded-concat channel space
+            L.call('pg_pack_weight', wp, self.bwd.data_ptr(), s.c1, s.c1p, s.cout, s.np, 0, 0, s.cout * 16, 16, 0, st)
+            if s.c2:
+                L.call('pg_pack_weight', wp + s.c1 * s.cout * 16 * 4, self.bwd.data_ptr() + s.c1p * 16 * s.np * 2, s.c2,
+                       s.c2p, s.cout, s.np, 0, 0, s.cout * 16, 16, 0, st)
+
+
+class NetEngine:
+    """Common machinery: parameter lookup, weight packing with change detection."""
+
+    def __init__(self, module, specs):
+        self.module = module
+        self.specs = specs
+        self.packed = None
+        self._stamp = None
+        self.seed = None   # device uint64 dropout counter
+
+    def params(self):
+        return dict(self.module.named_parameters())
+
+    def device(self):
+        return next(self.module.parameters()).device
+
+    def mark_dirty(self):
+        self._stamp = None
+
+    def ensure_packed(self):
+        ps = self.params()
+        dev = self.device()
+        if dev.type != 'cuda':
+            raise RuntimeError('patchgan_b200: module parameters must live on a CUDA device (no CPU path)')
+        stamp = tuple((ps[s.wname].data_ptr(), ps[s.wname]._version) for s in self.specs)
+        if self.packed is None or self.packed[0].fwd.device != dev:
+            self.packed = [PackedWeights(s, dev) for s in self.specs]
+            self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
+            self._stamp = None
+        if stamp != self._stamp:
+            for pw in self.packed:
+                w = ps[pw.spec.wname].detach()
+                if w.dtype != torch.float32 or not w.is_contiguous():
+                    raise RuntimeError(f'{pw.spec.wname}: weights must be contiguous float32')
+                pw.pack(w)
+            self._stamp = stamp
+
+    def repack(self):
+        """Unconditional repack (used inside captured graphs right after the optimizer step)."""
+        self._stamp = None
+        self.ensure_packed()
+
+    def bump_seed(self):
+        L.call('pg_counter_add', self.seed.data_ptr(), 1, _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# shared per-layer helpers
+# ------------------------------------------------------------------------------------------------
+
+def norm_fwd(x, sums, out, act, drop_p, seed, salt):
+    HW = x.H * x.W
+    L.call('pg_norm_act_fwd', x.ptr, int(x.f32), sums.data_ptr() if sums is not None else None, out.ptr, int(out.f32),
+           x.B, HW, x.C, x.ld, out.ld, act, drop_p, seed.data_ptr() if seed is not None else None, salt, _stream())
+
+
+def instnorm_stats(x):
+    sums = torch.zeros((x.B, x.C, 2), device=x.t.device, dtype=torch.float32)
+    L.call('pg_instnorm_stats', x.ptr, int(x.f32), x.B, x.H * x.W, x.C, x.ld, sums.data_ptr(), _stream())
+    return sums
+
+
+def norm_bwd(x, sums, dy1, dy2, act, drop_p, seed, salt):
+    """Backward through dropout/act/InstanceNorm: returns d(raw) as a new bf16 Act."""
+    dev = x.t.device
+    HW = x.H * x.W
+    dx = new_act(x.B, x.H, x.W, x.C, dev)
+    bsums = torch.zeros((x.B, x.C, 2), device=dev, dtype=torch.float32)
+    sp = seed.data_ptr() if seed is not None else None
+    p2, l2 = (dy2.ptr, dy2.ld) if dy2 is not None else (None, 0)
+    st = _stream()
+    L.call('pg_norm_act_bwd_reduce', x.ptr, int(x.f32), sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), x.B,
+           HW, x.C, x.ld, act, drop_p, sp, salt, st)
+    L.call('pg_norm_act_bwd_apply', x.ptr, int(x.f32), sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(),
+           dx.ptr, dx.ld, x.B, HW, x.C, x.ld, act, drop_p, sp, salt, st)
+    return dx
+
+
+def act_bwd_out(y, dy, act):
+    dx = new_act(y.B, y.H, y.W, y.C, y.t.device)
+    L.call('pg_act_bwd_from_output', y.ptr, int(y.f32), y.ld, dy.ptr, dy.ld, dx.ptr, dx.ld, y.B * y.H * y.W, y.C, act,
+           _stream())
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# Generator
+# ------------------------------------------------------------------------------------------------
+
+class GeneratorEngine(NetEngine):
+    def __init__(self, module):
+        nf, inc, outc = module.nf, module.input_nc, module.output_nc
+        filts = [nf, nf * 2, nf * 4, nf * 8, nf * 8, nf * 8, nf * 8]
+        specs, prev = [], inc
+        for i, f in enumerate(filts):
+            specs.append(LayerSpec('conv', 2, prev, 0, f, False, module.activation, True, module.use_dropout,
+                                   f'encoder.{i}.model.DownConv{i}.weight'))
+            prev = f
+        enc_out = filts
+        for i, f in enumerate(filts[:-1][::-1]):
+            if i == 0:
+                specs.append(LayerSpec('convT', 2, prev, 0, f, False, module.activation, False, False,
+                                       f'decoder.{i}.model.UpConv{i}.weight'))
+            else:
+                specs.append(LayerSpec('convT', 2, prev, enc_out[6 - i], f, False, module.activation, True,
+                                       module.use_dropout, f'decoder.{i}.model.UpConv{i}.weight'))
+            prev = f
+        specs.append(LayerSpec('convT', 2, prev, enc_out[0], outc, False, module.final_act, False, False,
+                               'decoder.6.model.UpConv6.weight'))
+        super().__init__(module, specs)
+        self.enc, self.dec = specs[:7], specs[7:]
+        self.in_cp = rup16(inc)
+        self.out_cp = rup16(outc)
+
+    def pack_input(self, x):
+        """NCHW float -> NHWC bf16 with channels zero-padded to 16."""
+        B, C, H, W = x.shape
+        a = new_act(B, H, W, self.in_cp, x.device, zero=True)
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), a.ptr, B, C, H, W, a.ld, 0, _stream())
+        return a
+
+    def forward(self, xin, training, save=True):
+        """xin: Act (B,H,W,in_cp) bf16.  Returns (p: f32 Act (B,H,W,out_cp), ctx)."""
+        self.ensure_packed()
+        dev = xin.t.device
+        B = xin.B
+        ctx = {'enc': [], 'dec': [], 'training': training}
+        h = xin
+        enc_outs = []
+        for i, s in enumerate(self.enc):
+            Ho, Wo = h.H // 2, h.W // 2
+            if Ho * Wo <= 1 and training:
+                # aten::instance_norm raises for a single spatial element in training mode
+                raise ValueError('Expected more than 1 spatial element when training (input too small for 7 '
+                                 'stride-2 stages)')
+            raw = new_act(B, Ho, Wo, s.np, dev, f32=True)
+            run_conv(conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, raw.ld, out_f32=1), h, None,
+                     self.packed[i].fwd, None, raw)
+            sums = instnorm_stats(raw)
+            out = new_act(B, Ho, Wo, s.np, dev)
+            dp = DROP_P if (training and s.dropout) else 0.0
+            norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, i)
+            ctx['enc'].append((h, raw, sums, out, dp) if save else None)
+            enc_outs.append(out)
+            h = out
+        for i, s in enumerate(self.dec):
+            src1 = h
+            src2 = enc_outs[6 - i] if i > 0 else None
+            Ho, Wo = src1.H * 2, src1.W * 2
+            pw = self.packed[7 + i]
+            c2, ld2 = (src2.C, src2.ld) if src2 is not None else (0, 0)
+            if s.norm:
+                raw = new_act(B, Ho, Wo, s.np, dev, f32=True)
+                run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, raw.ld,
+                                   out_f32=1), src1, src2, pw.fwd, None, raw)
+                sums = instnorm_stats(raw)
+                out = new_act(B, Ho, Wo, s.np, dev)
+                dp = DROP_P if (training and s.dropout) else 0.0
+                norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, 16 + i)
+                ctx['dec'].append((src1, src2, raw, sums, out, dp) if save else None)
+            elif i < 6:
+                out = new_act(B, Ho, Wo, s.np, dev)
+                run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, out.ld,
+                                   act=L.ACT[s.act]), src1, src2, pw.fwd, None, out)
+                ctx['dec'].append((src1, src2, None, None, out, 0.0) if save else None)
+            else:
+                out = new_act(B, Ho, Wo, s.np, dev, f32=True)
+                fused = 0 if s.act == 'softmax' else L.ACT[s.act]
+                run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, out.ld,
+                                   n_valid=s.cout, act=fused, out_f32=1), src1, src2, pw.fwd, None, out)
+                if s.act == 'softmax':
+                    L.call('pg_softmax_fwd', out.ptr, out.ptr, B * Ho * Wo, s.cout, out.ld, _stream())
+                ctx['dec'].append((src1, src2, None, None, out, 0.0) if save else None)
+            h = out
+        return h, ctx
+
+    def backward(self, ctx, d_raw, grads, need_dx=False):
+        """d_raw: bf16 Act, gradient wrt the last ConvTranspose2d's output (pre final activation).
+        grads: dict name -> zero-initialised float32 tensor in the reference layout (accumulated into)."""
+        dev = d_raw.t.device
+        B = d_raw.B
+        dskip = [None] * 7
+        d_enc6 = None
+        for i in range(6, -1, -1):
+            s = self.dec[i]
+            src1, src2, raw, sums, out, dp = ctx['dec'][i]
+            pw = self.packed[7 + i]
+            g = grads[s.wname]
+            # weight gradient: dW[ci][co][tap] = sum x[ci] * dY[co] -- PG_CONV geometry with A = dY, G = layer input
+            wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C, src1.C)
+            run_wgrad(wd, d_raw, src1, g.data_ptr(), s.cout * 16, s.c1, s.cout)
+            if src2 is not None:
+                wd2 = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src2.H, src2.W, d_raw.C, 0, d_raw.ld, 0, src2.C,
+                                src2.C)
+                run_wgrad(wd2, d_raw, src2, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout)
+            # data gradient: stride-2 conv of dY with W'[ci][tap][co]
+            din = new_act(B, src1.H, src1.W, s.cinp, dev)
+            run_conv(conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
+                               din.ld), d_raw, None, pw.bwd, None, din)
+            if i >= 1:
+                d_prev = din.slice(0, s.c1p)
+                dskip[6 - i] = din.slice(s.c1p, s.c2p)
+                ps = self.dec[i - 1]
+                _, _, praw, psums, pout, pdp = ctx['dec'][i - 1]
+                if ps.norm:
+                    d_raw = norm_bwd(praw, psums, d_prev, None, L.ACT[ps.act], pdp, self.seed, 16 + i - 1)
+                else:
+                    d_raw = act_bwd_out(pout, d_prev, L.ACT[ps.act])
+            else:
+                d_enc6 = din
+        dy1 = d_enc6
+        dx = None
+        for i in range(6, -1, -1):
+            s = self.enc[i]
+            h, raw, sums, out, dp = ctx['enc'][i]
+            d_raw = norm_bwd(raw, sums, dy1, dskip[i] if i < 6 else None, L.ACT[s.act], dp, self.seed, i)
+            wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np)
+            run_wgrad(wd, h, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
+            if i > 0 or need_dx:
+                din = new_act(B, h.H, h.W, s.cinp, dev)
+                run_conv(conv_desc(L.PG_CONVT, 2, 1, B, raw.H, raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp, din.ld),
+                         d_raw, None, self.packed[i].bwd, None, din)
+                dy1 = din
+                dx = din
+        return dx if need_dx else None
+
+
+# ------------------------------------------------------------------------------------------------
+# Discriminator
+# ------------------------------------------------------------------------------------------------
+
+class DiscriminatorEngine(NetEngine):
+    def __init__(self, module):
+        inc, ndf, nl, norm = module.input_nc, module.ndf, module.n_layers, module.norm
+        idx = 0
+        specs = [LayerSpec('conv', 2, inc, 0, ndf, True, 'leakyrelu', False, False, 'model.0.weight', 'model.0.bias')]
+        idx += 2
+        mult = 1
+        for n in range(1, nl):
+            prev, mult = mult, min(2 ** n, 8)
+            specs.append(LayerSpec('conv', 2, ndf * prev, 0, ndf * mult, False, 'tanh', norm, False,
+                                   f'model.{idx}.weight', norm_after_act=True))
+            idx += 3 if norm else 2
+        prev, mult = mult, min(2 ** nl, 8)
+        specs.append(LayerSpec('conv', 1, ndf * prev, 0, ndf * mult, False, 'tanh', norm, False, f'model.{idx}.weight',
+                               norm_after_act=True))
+        idx += 3 if norm else 2
+        specs.append(LayerSpec('conv', 1, ndf * mult, 0, 1, True, 'sigmoid', False, False, f'model.{idx}.weight',
+                               f'model.{idx}.bias'))
+        super().__init__(module, specs)
+        self.in_cp = rup16(inc)
+
+    def new_input(self, B, H, W, device):
+        return new_act(B, H, W, self.in_cp, device, zero=True)
+
+    def forward(self, xin, save=True):
+        """xin: Act (B,H,W,in_cp) bf16 -> (p: f32 Act (B,Ho,Wo,16) with the patch probabilities in channel 0, ctx)."""
+        self.ensure_packed()
+        ps = self.params()
+        dev = xin.t.device
+        B = xin.B
+        ctx = []
+        h = xin
+        last = len(self.specs) - 1
+        for li, s in enumerate(self.specs):
+            Ho = (h.H + 2 - 4) // s.stride + 1
+            Wo = (h.W + 2 - 4) // s.stride + 1
+            if Ho < 1 or Wo < 1:
+                raise RuntimeError(f'Discriminator: input too small at layer {li} ({h.H}x{h.W})')
+            bias = ps[s.bname].detach() if s.bias else None
+            if li == last:
+                out = new_act(B, Ho, Wo, s.np, dev, f32=True)
+                run_conv(conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, out.ld,
+                                   n_valid=s.cout, act=L.ACT[s.act], out_f32=1, has_bias=1), h, None, self.packed[li].fwd,
+                         bias, out)
+                ctx.append((h, None, None, out) if save else None)
+            else:
+                t = new_act(B, Ho, Wo, s.np, dev)
+                run_conv(conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, t.ld,
+                                   n_valid=s.cout, act=L.ACT[s.act], has_bias=int(s.bias)), h, None, self.packed[li].fwd,
+                         bias, t)
+                if s.norm:
+                    sums = instnorm_stats(t)
+                    out = new_act(B, Ho, Wo, s.np, dev)
+                    norm_fwd(t, sums, out, 0, 0.0, None, 0)
+                    ctx.append((h, t, sums, out) if save else None)
+                else:
+                    out = t
+                    ctx.append((h, t, None, out) if save else None)
+            h = out
+        return h, ctx
+
+    def backward(self, ctx, d_raw, grads, need_dx, nb=None):
+        """d_raw: bf16 Act (nb,Ho,Wo,16): gradient wrt the last conv's pre-sigmoid output.
+        grads: dict of zero-initialised fp32 tensors to accumulate into, or None to skip weight gradients.
+        nb: process only the first nb images of the saved batch."""
+        dev = d_raw.t.device
+        B = d_raw.B if nb is None else nb
+        din = None
+        for li in range(len(self.specs) - 1, -1, -1):
+            s = self.specs[li]
+            h, t, sums, out = ctx[li]
+            h = h.first(B)
+            if grads is not None:
+                wd = conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, d_raw.H, d_raw.W, h.C, 0, h.ld, 0, s.np, s.np)
+                run_wgrad(wd, h, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
+                if s.bias:
+                    L.call('pg_colsum', d_raw.ptr, B * d_raw.H * d_raw.W, d_raw.ld, s.cout, grads[s.bname].data_ptr(),
+                           _stream())
+            if li > 0 or need_dx:
+                din = new_act(B, h.H, h.W, s.cinp, dev)
+                if s.stride == 2:
+                    dd = conv_desc(L.PG_CONVT, 2, 1, B, d_raw.H, d_raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
+                                   din.ld)
+                else:
+                    dd = conv_desc(L.PG_CONV, 1, 2, B, d_raw.H, d_raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
+                                   din.ld)
+                run_conv(dd, d_raw, None, self.packed[li].bwd, None, din)
+            if li > 0:
+                ps = self.specs[li - 1]
+                _, pt, psums, pout = ctx[li - 1]
+                pt = pt.first(B)
+                if ps.norm:
+                    dt = norm_bwd(pt, psums, din, None, 0, 0.0, None, 0)
+                    d_raw = act_bwd_out(pt, dt, L.ACT[ps.act])
+                else:
+                    d_raw = act_bwd_out(pt, din, L.ACT[ps.act])
+        return din if need_dx else None

@@ -1,0 +1,330 @@
+"""Trainer with the reference's API (/root/reference/patchgan/trainer.py:16-321) and a fused G+D step.
+
+``Trainer.batch`` computes exactly what the reference's ``batch`` computes (trainer.py:50-115) -- generator
+forward, D(fake), segmentation + adversarial generator loss, generator Adam step, D(real), discriminator loss,
+discriminator Adam step, the six-entry loss dict -- but schedules it as explicit kernel launches instead of
+three autograd graphs:
+
+  * D(fake) and D(real) run as ONE batched discriminator forward over 2B images (InstanceNorm is per-sample, so
+    batching cannot change results); the reference's second D(fake) forward (trainer.py:98-99) is bit-identical
+    to the first and is not repeated;
+  * the generator's backward goes through the discriminator with data-gradients only -- the reference computes
+    and then zeroes the discriminator weight-gradients there (trainer.py:89,94);
+  * the six ``.item()`` syncs (trainer.py:110-111) become one 4-float device->host copy;
+  * with ``torch.distributed`` initialised, each rank steps its own shard and the flat gradient buffers are
+    all-reduced over NCCL (generator all-reduce overlapped with the discriminator backward).
+"""
+import glob
+import os
+from collections import defaultdict
+
+import numpy as np
+import torch
+import tqdm
+from torch.optim.lr_scheduler import ExponentialLR, ReduceLROnPlateau
+
+from . import _lib as L
+from . import dp
+from .engine import _stream, new_act
+from .optim import FusedAdam
+
+LOSS_KEYS = ['gen', 'gen_loss', 'gdisc', 'discr', 'discf', 'disc']
+
+
+def weights_init(net, init_type='normal', scaling=0.02):
+    """The reference's ``weights_init`` (trainer.py:327-343) defines an inner function and never applies it, so
+    ``module.apply(weights_init)`` leaves the default PyTorch initialisation untouched.  Reproduced as a no-op."""
+    return None
+
+
+class Trainer:
+    '''
+        Drives training of a UNet generator against a PatchGAN discriminator
+        (same attributes and methods as the reference Trainer).
+    '''
+
+    seg_alpha = 200
+    loss_type = 'tversky'
+    tversky_beta = 0.75
+    tversky_gamma = 0.75
+
+    neptune_config = None
+
+    def __init__(self, generator, discriminator, savefolder, device='cuda'):
+        generator.apply(weights_init)
+        discriminator.apply(weights_init)
+        self.generator = generator
+        self.discriminator = discriminator
+        self.device = device
+        if savefolder[-1] != '/':
+            savefolder += '/'
+        self.savefolder = savefolder
+        if not os.path.exists(savefolder):
+            os.mkdir(savefolder)
+        self.start = 1
+        self._host_losses = None
+
+    # ------------------------------------------------------------------------------------------
+    # one G+D step
+    # ------------------------------------------------------------------------------------------
+    def make_optimizers(self, gen_lr=1e-3, dsc_lr=1e-3):
+        """Adam for both nets exactly as trainer.py:169-172 (lr, betas=(0.9, 0.999))."""
+        self.gen_optimizer = FusedAdam(self.generator.parameters(), lr=gen_lr, betas=(0.9, 0.999),
+                                       on_step=self.generator._engine().mark_dirty)
+        self.disc_optimizer = FusedAdam(self.discriminator.parameters(), lr=dsc_lr, betas=(0.9, 0.999),
+                                        on_step=self.discriminator._engine().mark_dirty)
+
+    def _to_device(self, a):
+        if not isinstance(a, torch.Tensor):
+            return torch.as_tensor(a, dtype=torch.float).to(self.device)
+        return a.to(self.device, non_blocking=True)
+
+    def step_device(self, x, y, train):
+        """Issue the whole step on the current stream.  x, y: CUDA float NCHW.  Returns the device tensor
+        [seg*alpha, gdisc, discr, discf] (no host sync)."""
+        G, D = self.generator._engine(), self.discriminator._engine()
+        gm, dm = self.generator, self.discriminator
+        if self.loss_type not in ('tversky', 'weighted_bce', 'MAE'):
+            raise ValueError(f'unknown loss_type {self.loss_type!r}')
+        B, cin, H, W = x.shape
+        cout = gm.output_nc
+        if cin != gm.input_nc or y.shape != (B, cout, H, W):
+            raise RuntimeError(f'batch: expected x (B,{gm.input_nc},H,W) and y (B,{cout},H,W), got {tuple(x.shape)} '
+                               f'and {tuple(y.shape)}')
+        if dm.input_nc != cin + cout:
+            raise RuntimeError(f'Discriminator.input_nc={dm.input_nc} != {cin}+{cout}')
+        dev = x.device
+        st = _stream()
+        lt = L.LOSS[self.loss_type]
+        losses = torch.zeros(8, device=dev, dtype=torch.float32)
+        world = dp.world_size()
+
+        # ---- inputs: NCHW float -> NHWC bf16; D input = [fake batch ; real batch] with x in channels 0..cin-1
+        xin = G.pack_input(x)
+        dboth = D.new_input(2 * B, H, W, dev)
+        half = B * H * W * dboth.ld * 2
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), dboth.ptr, B, cin, H, W, dboth.ld, 0, st)
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), dboth.ptr + half, B, cin, H, W, dboth.ld, 0, st)
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', y.data_ptr(), dboth.ptr + half, B, cout, H, W, dboth.ld, cin, st)
+
+        # ---- generator forward (trainer.py:63), D(cat(x, G(x))) and D(cat(x, y)) (trainer.py:65-66, 96-97)
+        if gm.training and gm.use_dropout:
+            G.ensure_packed()
+            G.bump_seed()
+        p, gctx = G.forward(xin, gm.training, save=train)
+        L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.ptr, dboth.ld, cin, cout, B * H * W, st)
+        pd, dctx = D.forward(dboth, save=train)
+        npatch = B * pd.H * pd.W
+        pd_real_ptr = pd.ptr + npatch * pd.ld * 4
+
+        # ---- segmentation loss (trainer.py:71-82)
+        part = torch.zeros((B, 8), device=dev, dtype=torch.float32)
+        coef = torch.zeros((B, 4), device=dev, dtype=torch.float32)
+        chsum = None
+        if lt == L.LOSS['weighted_bce']:
+            chsum = torch.zeros((B, cout), device=dev, dtype=torch.float32)
+            L.call('pg_target_chsum', y.data_ptr(), chsum.data_ptr(), B, cout, H * W, st)
+        chp = chsum.data_ptr() if chsum is not None else None
+        L.call('pg_seg_loss_partials', p.ptr, p.ld, y.data_ptr(), chp, part.data_ptr(), B, cout, H * W, lt, st)
+        L.call('pg_seg_loss_finalize', part.data_ptr(), coef.data_ptr(), losses.data_ptr(), 0, B, cout, H * W, lt,
+               float(self.tversky_beta), float(self.tversky_gamma), float(self.seg_alpha), st)
+
+        # ---- generator adversarial loss bce(D(fake), 1) (trainer.py:84) and generator update (:87-90)
+        dz_g = new_act(B, pd.H, pd.W, pd.ld, dev) if train else None
+        L.call('pg_bce_const', pd.ptr, pd.ld, 1.0, 1.0, losses.data_ptr(), 1, dz_g.ptr if train else None, pd.ld,
+               npatch, st)
+        g_work = None
+        if train:
+            gopt, dopt = self.gen_optimizer, self.disc_optimizer
+            gflat = gopt.flat()
+            gflat['g'].zero_()
+            d_dinp = D.backward(dctx, dz_g, None, need_dx=True, nb=B)
+            d_raw = new_act(B, H, W, p.ld, dev)
+            L.call('pg_gen_out_bwd', p.ptr, p.ld, y.data_ptr(), chp, coef.data_ptr(), d_dinp.ptr, d_dinp.ld, cin,
+                   d_raw.ptr, d_raw.ld, B, cout, H * W, lt, L.ACT[gm.final_act], float(self.tversky_beta), st)
+            ggrads = {n: q.grad for n, q in gm.named_parameters()}
+            G.backward(gctx, d_raw, ggrads)
+            if world > 1:
+                g_work = dp.all_reduce_sum_async(gflat['g'])
+                gopt.grad_scale = 1.0 / world
+            else:
+                gopt.step(sync_lr=False)
+
+        # ---- discriminator losses (trainer.py:101-103) and update (:105-107)
+        dz = new_act(2 * B, pd.H, pd.W, pd.ld, dev) if train else None
+        L.call('pg_bce_const', pd.ptr, pd.ld, 0.0, 0.5, losses.data_ptr(), 3, dz.ptr if train else None, pd.ld, npatch,
+               st)
+        L.call('pg_bce_const', pd_real_ptr, pd.ld, 1.0, 0.5, losses.data_ptr(), 2,
+               dz.ptr + npatch * pd.ld * 2 if train else None, pd.ld, npatch, st)
+        if train:
+            dflat = dopt.flat()
+            dflat['g'].zero_()
+            dgrads = {n: q.grad for n, q in dm.named_parameters()}
+            D.backward(dctx, dz, dgrads, need_dx=False)
+            if world > 1:
+                d_work = dp.all_reduce_sum_async(dflat['g'])
+                dopt.grad_scale = 1.0 / world
+                g_work.wait()
+                gopt.step(sync_lr=False)
+                d_work.wait()
+            dopt.step(sync_lr=False)
+        return losses
+
+    def batch(self, x, y, train=False):
+        '''
+            Train the generator and discriminator on a single batch
+        '''
+        input_tensor = self._to_device(x)
+        target_tensor = self._to_device(y)
+        if input_tensor.device.type != 'cuda':
+            raise RuntimeError('patchgan_b200.Trainer runs on CUDA (sm_100a) only; there is no CPU path')
+        input_tensor = input_tensor.float().contiguous()
+        target_tensor = target_tensor.float().contiguous()
+        if train:
+            if not hasattr(self, 'gen_optimizer'):
+                raise AttributeError("'Trainer' object has no attribute 'gen_optimizer' (call train() or "
+                                     "make_optimizers() first)")
+            self.gen_optimizer.sync_lr()
+            self.disc_optimizer.sync_lr()
+        losses = self.step_device(input_tensor, target_tensor, train)
+        # one device->host copy instead of six .item() calls (trainer.py:110-111)
+        if self._host_losses is None:
+            self._host_losses = torch.empty(8, dtype=torch.float32, pin_memory=True)
+        self._host_losses.copy_(losses, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        seg, gdisc, discr, discf = (float(v) for v in self._host_losses[:4])
+        gen_loss = float(np.float32(seg) + np.float32(gdisc))
+        disc_loss = float((np.float32(discf) + np.float32(discr)) / np.float32(2.))
+        return dict(zip(LOSS_KEYS, [gen_loss, gen_loss, gdisc, discr, discf, disc_loss]))
+
+    # ------------------------------------------------------------------------------------------
+    # epoch driver (trainer.py:117-279)
+    # ------------------------------------------------------------------------------------------
+    def _run_epoch(self, data, train, desc):
+        pbar = tqdm.tqdm(data, desc=desc, dynamic_ncols=True)
+        if hasattr(data, 'shuffle'):
+            data.shuffle()
+        sums = defaultdict(float)
+        loss_mean = {}
+        for i, (input_img, target_mask) in enumerate(pbar):
+            batch_loss = self.batch(input_img, target_mask, train=train)
+            for key, value in batch_loss.items():
+                sums[key] += value           # O(1) running mean (the reference re-averages a growing list)
+                loss_mean[key] = sums[key] / (i + 1)
+            pbar.set_postfix_str(" ".join(f"{key}: {value:.2e}" for key, value in loss_mean.items()))
+        return loss_mean
+
+    def train(self, train_data, val_data, epochs, dsc_learning_rate=1.e-3,
+              gen_learning_rate=1.e-3, save_freq=10, lr_decay=None, decay_freq=5,
+              reduce_on_plateau=False):
+        '''
+            Training driver: builds the two Adam optimizers, runs `epochs` epochs of `batch(..., train=True)`
+            over train_data and `batch(..., train=False)` over val_data, applies LR decay and saves checkpoints.
+            Arguments and return value (G_loss_ep, D_loss_ep) are the reference's (trainer.py:117-279).
+        '''
+        if (lr_decay is not None) and not reduce_on_plateau:
+            gen_lr = gen_learning_rate * (lr_decay)**((self.start - 1) / (decay_freq))
+            dsc_lr = dsc_learning_rate * (lr_decay)**((self.start - 1) / (decay_freq))
+        else:
+            gen_lr, dsc_lr = gen_learning_rate, dsc_learning_rate
+
+        cfg = self.neptune_config
+        if cfg is not None:
+            cfg['model/parameters/gen_learning_rate'] = gen_lr
+            cfg['model/parameters/dsc_learning_rate'] = dsc_lr
+            cfg['model/parameters/start'] = self.start
+            cfg['model/parameters/n_epochs'] = epochs
+
+        self.make_optimizers(gen_lr, dsc_lr)
+
+        if reduce_on_plateau:
+            # the reference passes verbose=True, which newer torch rejects, and dereferences neptune_config
+            # unconditionally (trainer.py:176-178); both are tolerated here
+            gen_scheduler = ReduceLROnPlateau(self.gen_optimizer)
+            dsc_scheduler = ReduceLROnPlateau(self.disc_optimizer)
+            if cfg is not None:
+                cfg['model/parameters/scheduler'] = 'ReduceLROnPlateau'
+        elif lr_decay is not None:
+            gen_scheduler = ExponentialLR(self.gen_optimizer, gamma=lr_decay)
+            dsc_scheduler = ExponentialLR(self.disc_optimizer, gamma=lr_decay)
+            if cfg is not None:
+                cfg['model/parameters/scheduler'] = 'ExponentialLR'
+                cfg['model/parameters/decay_freq'] = decay_freq
+                cfg['model/parameters/lr_decay'] = lr_decay
+        else:
+            gen_scheduler = dsc_scheduler = None
+
+        D_loss_ep, G_loss_ep = [], []
+        for epoch in range(self.start, epochs + 1):
+            if isinstance(gen_scheduler, ExponentialLR):
+                gen_lr = gen_scheduler.get_last_lr()[0]
+                dsc_lr = dsc_scheduler.get_last_lr()[0]
+            else:
+                gen_lr, dsc_lr = gen_learning_rate, dsc_learning_rate
+            print(f"Epoch {epoch} -- lr: {gen_lr:5.3e}, {dsc_lr:5.3e}")
+            print("-------------------------------------------------------")
+
+            self.generator.train()
+            self.discriminator.train()
+            loss_mean = self._run_epoch(train_data, True, 'Training: ')
+            D_loss_ep.append(loss_mean['disc'])
+            G_loss_ep.append(loss_mean['gen'])
+            if cfg is not None:
+                cfg['train/gen_loss'].append(loss_mean['gen'])
+                cfg['train/disc_loss'].append(loss_mean['disc'])
+
+            self.discriminator.eval()
+            self.generator.eval()
+            loss_mean = self._run_epoch(val_data, False, 'Validation: ')
+            if cfg is not None:
+                cfg['eval/gen_loss'].append(loss_mean['gen'])
+                cfg['eval/disc_loss'].append(loss_mean['disc'])
+
+            if (gen_scheduler is not None) and (dsc_scheduler is not None):
+                if isinstance(gen_scheduler, ExponentialLR):
+                    if epoch % decay_freq == 0:
+                        gen_scheduler.step()
+                        dsc_scheduler.step()
+                else:
+                    gen_scheduler.step(loss_mean['gen'])
+                    dsc_scheduler.step(loss_mean['disc'])
+
+            if epoch % save_freq == 0:
+                self.save(epoch)
+
+        return G_loss_ep, D_loss_ep
+
+    # ------------------------------------------------------------------------------------------
+    # checkpoints (trainer.py:281-321): same file names, fp32 state_dicts in the reference layout
+    # ------------------------------------------------------------------------------------------
+    def save(self, epoch):
+        gen_savefile = f'{self.savefolder}/generator_ep_{epoch:03d}.pth'
+        disc_savefile = f'{self.savefolder}/discriminator_ep_{epoch:03d}.pth'
+        print(f"Saving to {gen_savefile} and {disc_savefile}")
+        if dp.rank() == 0:
+            torch.save({k: v.detach().clone() for k, v in self.generator.state_dict().items()}, gen_savefile)
+            torch.save({k: v.detach().clone() for k, v in self.discriminator.state_dict().items()}, disc_savefile)
+
+    def load_last_checkpoint(self):
+        def epochs_of(prefix):
+            files = glob.glob(self.savefolder + f"{prefix}_ep*.pth")
+            return {int(os.path.basename(f).replace(f'{prefix}_ep_', '')[:-4]) for f in files}
+        gen_epochs, dsc_epochs = epochs_of('generator'), epochs_of('discriminator')
+        try:
+            assert len(gen_epochs) > 0, "No checkpoints found!"
+            start = max(gen_epochs.union(dsc_epochs))
+            self.load(f"{self.savefolder}/generator_ep_{start:03d}.pth",
+                      f"{self.savefolder}/discriminator_ep_{start:03d}.pth")
+            self.start = start + 1
+        except Exception as e:
+            print(e)
+            print("Checkpoints not loaded")
+
+    def load(self, generator_save, discriminator_save):
+        print(generator_save, discriminator_save)
+        dev = next(self.generator.parameters()).device
+        self.generator.load_state_dict(torch.load(generator_save, map_location=dev))
+        self.discriminator.load_state_dict(torch.load(discriminator_save, map_location=dev))
+        gfname = generator_save.split('/')[-1]
+        dfname = discriminator_save.split('/')[-1]
+        print(f"Loaded checkpoints from {gfname} and {dfname}")

@@ -1,0 +1,160 @@
+"""U-Net generator with the reference's constructor, parameter names/shapes and call signature
+(/root/reference/patchgan/unet.py:75-134), executed by the sm_100a kernels in ``engine.py``.
+
+The module keeps the reference's sub-module tree (``encoder.{i}.model.DownConv{i}`` /
+``decoder.{i}.model.UpConv{i}``) so ``state_dict`` files interchange both ways, but the sub-modules are
+parameter holders only: ``forward`` runs the whole network as ONE autograd node (``_UNetFunction``) whose
+forward/backward issue the fused kernels.  Tensors must be CUDA tensors; there is no CPU path.
+"""
+from collections import OrderedDict
+
+import torch
+from torch import nn
+
+from . import _lib as L
+from .engine import Act, GeneratorEngine, _stream, new_act, require_cuda
+from .transfer import Transferable
+
+_ACTS = ('tanh', 'relu', 'leakyrelu', 'softmax', 'sigmoid')
+
+
+class _Holder(nn.Module):
+    """Parameter holder reproducing nn.Conv2d / nn.ConvTranspose2d default init (kaiming_uniform(a=sqrt(5)))."""
+
+    def __init__(self, shape, fan_in, bias_n=0):
+        super().__init__()
+        bound = 1.0 / fan_in ** 0.5
+        self.weight = nn.Parameter(torch.empty(shape).uniform_(-bound, bound))
+        if bias_n:
+            self.bias = nn.Parameter(torch.empty(bias_n).uniform_(-bound, bound))
+
+
+class DownSampleBlock(nn.Module):
+    """unet.py:8-35: Conv2d(k4,s2,p1,bias=False) -> InstanceNorm2d -> act -> [Dropout(0.2)]."""
+
+    def __init__(self, input_filt, output_filt, activation, norm_layer, layer, use_dropout=False, **kwargs):
+        super().__init__()
+        self.model = nn.Sequential(OrderedDict([
+            (f'DownConv{layer}', _Holder((output_filt, input_filt, 4, 4), input_filt * 16))]))
+
+
+class UpSampleBlock(nn.Module):
+    """unet.py:38-72: ConvTranspose2d(k4,s2,p1,bias=False) -> [InstanceNorm2d] -> act -> [Dropout(0.2)]."""
+
+    def __init__(self, input_filt, output_filt, activation, norm_layer, layer, batch_norm=True, use_dropout=False,
+                 **kwargs):
+        super().__init__()
+        # torch computes fan_in of a ConvTranspose2d weight (Cin, Cout, 4, 4) from dim 1
+        self.model = nn.Sequential(OrderedDict([
+            (f'UpConv{layer}', _Holder((input_filt, output_filt, 4, 4), output_filt * 16))]))
+
+
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *weights):
+        eng = module._engine()
+        B, C, H, W = x.shape
+        xin = eng.pack_input(x.contiguous().float())
+        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights))
+        if module.training and module.use_dropout:
+            eng.ensure_packed()
+            eng.bump_seed()
+        p, saved = eng.forward(xin, module.training, save=need_grad)
+        out = torch.empty((B, module.output_nc, H, W), device=x.device, dtype=torch.float32)
+        L.call('pg_unpack_nhwc_to_nchw_f32', p.ptr, 1, out.data_ptr(), B, module.output_nc, H, W, p.ld, 0, _stream())
+        ctx.module, ctx.saved, ctx.p = module, saved, p
+        ctx.x_needs_grad = x.requires_grad
+        ctx.shape = (B, C, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        module, eng = ctx.module, ctx.module._engine()
+        B, C, H, W = ctx.shape
+        p = ctx.p
+        dev = dout.device
+        # dOut (NCHW float) -> NHWC bf16, then through the final activation
+        dpk = new_act(B, H, W, p.ld, dev, zero=True)
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', dout.contiguous().data_ptr(), dpk.ptr, B, module.output_nc, H, W, dpk.ld,
+               0, _stream())
+        d_raw = new_act(B, H, W, p.ld, dev)
+        L.call('pg_gen_out_bwd', p.ptr, p.ld, None, None, None, dpk.ptr, dpk.ld, 0, d_raw.ptr, d_raw.ld, B,
+               module.output_nc, H * W, L.LOSS['none'], L.ACT[module.final_act], 0.0, _stream())
+        names = [s.wname for s in eng.specs]
+        params = eng.params()
+        grads = {n: torch.zeros_like(params[n], dtype=torch.float32) for n in names}
+        dx = eng.backward(ctx.saved, d_raw, grads, need_dx=ctx.x_needs_grad)
+        gx = None
+        if ctx.x_needs_grad:
+            gx = torch.empty((B, C, H, W), device=dev, dtype=torch.float32)
+            L.call('pg_unpack_nhwc_to_nchw_f32', dx.ptr, 0, gx.data_ptr(), B, C, H, W, dx.ld, 0, _stream())
+        return (None, gx) + tuple(grads[n] for n in names)
+
+
+class UNet(nn.Module, Transferable):
+    def __init__(self, input_nc, output_nc, nf=64, norm_layer=nn.InstanceNorm2d, use_dropout=False,
+                 activation='tanh', final_act='softmax'):
+        super(UNet, self).__init__()
+        if norm_layer is not nn.InstanceNorm2d:
+            raise NotImplementedError('patchgan_b200.UNet implements the reference default norm_layer=nn.InstanceNorm2d '
+                                      '(affine=False) only')
+        if activation not in ('tanh', 'relu', 'leakyrelu'):
+            raise ValueError(f'activation must be tanh / relu / leakyrelu, got {activation!r}')
+        if final_act not in _ACTS:
+            raise ValueError(f'final_act must be one of {_ACTS}, got {final_act!r}')
+        if output_nc > 16:
+            raise NotImplementedError('output_nc > 16 is not supported by the fused loss kernels')
+        self.input_nc, self.output_nc, self.nf = input_nc, output_nc, nf
+        self.use_dropout, self.activation, self.final_act = use_dropout, activation, final_act
+
+        conv_filts = [nf, nf * 2, nf * 4, nf * 8, nf * 8, nf * 8, nf * 8]
+        encoder_layers = []
+        prev_filt = input_nc
+        for i, filt in enumerate(conv_filts):
+            encoder_layers.append(DownSampleBlock(prev_filt, filt, activation, norm_layer, layer=i,
+                                                  use_dropout=use_dropout))
+            prev_filt = filt
+        decoder_layers = []
+        for i, filt in enumerate(conv_filts[:-1][::-1]):
+            if i == 0:
+                decoder_layers.append(UpSampleBlock(prev_filt, filt, activation, norm_layer, layer=i, batch_norm=False))
+            else:
+                decoder_layers.append(UpSampleBlock(prev_filt * 2, filt, activation, norm_layer, layer=i,
+                                                    use_dropout=use_dropout, batch_norm=True))
+            prev_filt = filt
+        decoder_layers.append(UpSampleBlock(nf * 2, output_nc, final_act, norm_layer, layer=i + 1, batch_norm=False))
+        self.encoder = nn.ModuleList(encoder_layers)
+        self.decoder = nn.ModuleList(decoder_layers)
+        self.__dict__['_eng'] = None
+
+    def _engine(self):
+        if self.__dict__.get('_eng') is None:
+            self.__dict__['_eng'] = GeneratorEngine(self)
+        return self.__dict__['_eng']
+
+    def _weights(self):
+        ps = dict(self.named_parameters())
+        return [ps[s.wname] for s in self._engine().specs]
+
+    def forward(self, x, return_hidden=False):
+        require_cuda(x, 'UNet input')
+        if x.dim() != 4 or x.shape[1] != self.input_nc:
+            raise RuntimeError(f'UNet expects (B, {self.input_nc}, H, W), got {tuple(x.shape)}')
+        out = _UNetFunction.apply(self, x, *self._weights())
+        if return_hidden:
+            return out, self._hidden(x)
+        return out
+
+    def _hidden(self, x):
+        """(B, 8nf, H/128, W/128) encoder bottleneck as NCHW float (unet.py:119,131-132; not differentiable here)."""
+        eng = self._engine()
+        with torch.no_grad():
+            xin = eng.pack_input(x.contiguous().float())
+            # re-run the network so that `forward` does not have to keep the bottleneck alive
+            p, saved = eng.forward(xin, self.training, save=True)
+            h6 = saved['enc'][6][3]
+            B = x.shape[0]
+            out = torch.empty((B, self.nf * 8, h6.H, h6.W), device=x.device, dtype=torch.float32)
+            L.call('pg_unpack_nhwc_to_nchw_f32', h6.ptr, 0, out.data_ptr(), B, self.nf * 8, h6.H, h6.W, h6.ld, 0,
+                   _stream())
+        return out

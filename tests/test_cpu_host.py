@@ -1,0 +1,77 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol, the modules keep
+the reference's constructor / state_dict contract, and the product fails loudly without CUDA (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from patchgan_b200 import _lib as L
+    from patchgan_b200.build import build
+    build()
+    header = open(os.path.join(ROOT, 'include', 'patchgan_b200.h')).read()
+    declared = set(re.findall(r'\b(pg_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 24
+    lib = ctypes.CDLL(L.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/patchgan_b200.h but not exported'
+    assert declared == set(L.exported_symbols()), declared ^ set(L.exported_symbols())
+    assert L.lib().pg_version() == 100
+
+
+def test_no_cpu_fallback():
+    import patchgan_b200 as P
+    G = P.UNet(3, 1, 8, activation='leakyrelu', final_act='sigmoid')
+    with pytest.raises(RuntimeError, match='CUDA'):
+        G(torch.zeros(1, 3, 256, 256))
+    D = P.Discriminator(4, 8)
+    with pytest.raises(RuntimeError, match='CUDA'):
+        D(torch.zeros(1, 4, 256, 256))
+    from patchgan_b200.losses import fc_tversky
+    with pytest.raises(RuntimeError, match='CUDA'):
+        fc_tversky(torch.zeros(1, 1, 4, 4), torch.zeros(1, 1, 4, 4), 0.75)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'patchgan_b200')
+    for fn in os.listdir(pkg):
+        if fn.endswith('.py'):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), fn
+
+
+def test_state_dict_contract_matches_reference_layout():
+    import patchgan_b200 as P
+    from oracle import patchgan_oracle as orc
+    for gk in (dict(input_nc=3, output_nc=1, nf=32), dict(input_nc=4, output_nc=7, nf=8)):
+        G = P.UNet(**gk)
+        og = orc.UNet(**gk)
+        sd = G.state_dict()
+        assert list(sd) == og.enc_names + og.dec_names
+        for k in sd:
+            assert tuple(sd[k].shape) == og.params[k].shape and sd[k].dtype == torch.float32
+    for dk in (dict(input_nc=4, ndf=64, n_layers=3), dict(input_nc=10, ndf=16, n_layers=5, norm=True)):
+        D = P.Discriminator(**dk)
+        od = orc.Discriminator(**dk)
+        assert list(D.state_dict()) == list(od.params)
+        for k, v in D.state_dict().items():
+            assert tuple(v.shape) == od.params[k].shape
+    # default init is U(+-1/sqrt(fan_in)) like nn.Conv2d (trainer.py:327-343 weights_init is a no-op)
+    w = P.UNet(3, 1, 32).state_dict()['encoder.1.model.DownConv1.weight']
+    assert float(w.abs().max()) <= 1 / (32 * 16) ** 0.5 + 1e-7 and float(w.abs().max()) > 0.9 / (32 * 16) ** 0.5
+
+
+def test_transfer_learning_partial_load():
+    import patchgan_b200 as P
+    from patchgan_b200.transfer import InvalidCheckpointError
+    a, b = P.UNet(3, 1, 8), P.UNet(3, 2, 8)
+    b.load_transfer_data(a.state_dict())            # all but the last layer match
+    assert torch.equal(a.state_dict()['encoder.0.model.DownConv0.weight'],
+                       b.state_dict()['encoder.0.model.DownConv0.weight'])
+    with pytest.raises(InvalidCheckpointError):
+        P.UNet(3, 1, 16).load_transfer_data({'encoder.0.model.DownConv0.weight': torch.zeros(1)})
