@@ -13,7 +13,7 @@
  *     and is CUDA-graph capturable;
  *   - return value: 0 on success, non-zero PgStatus otherwise; pg_last_error() gives the text
  *     (thread-local);
- *   - activations are NHWC bf16 with an explicit pixel stride `ld` (elements) so that a tensor can be a
+ *   - activations are NHWC 16-bit (bf16 or f16, see PgDType) with an explicit pixel stride `ld` (elements) so that a tensor can be a
  *     channel slice of a wider buffer (virtual concat); channel counts seen by the conv kernels are
  *     multiples of 16 (the host zero-pads 3/4/1/7-channel tensors and the packed weights);
  *   - packed weights are bf16 [N][16 taps][C] (tap = kh*4+kw, C = C1+C2 in concat order).
@@ -41,6 +41,14 @@ typedef enum PgAct {
   PG_ACT_TANH = 3,
   PG_ACT_SIGMOID = 4
 } PgAct;
+
+/* element types of activation / gradient tensors.  Forward operands may be bf16 or f16 (same tensor-core
+ * rate; f16 carries 3 more mantissa bits and post-InstanceNorm activations are O(1)); gradients are bf16. */
+typedef enum PgDType {
+  PG_BF16 = 0,
+  PG_F32 = 1,
+  PG_F16 = 2
+} PgDType;
 
 typedef enum PgConvMode {
   PG_CONV = 0,            /* nn.Conv2d(k=4, stride, pad)                          */
@@ -74,8 +82,9 @@ typedef struct PgConvDesc {
   int32_t ldo;       /* output pixel stride */
   int32_t n_valid;   /* channels >= n_valid are stored as 0 (padding must stay 0 after sigmoid) */
   int32_t act;       /* PgAct fused into the epilogue */
-  int32_t out_f32;   /* 0: bf16 output, 1: float output */
+  int32_t out_f32;   /* PgDType of the output: PG_BF16, PG_F32 or PG_F16 */
   int32_t has_bias;
+  int32_t in_dtype;  /* PgDType of src1/src2 and of the packed weights: PG_BF16 or PG_F16 */
 } PgConvDesc;
 
 const char* pg_last_error(void);
@@ -95,6 +104,7 @@ int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const v
  * a = dY (2H x 2W), g = layer input.  `ws` = float workspace (>= pg_conv_wgrad_ws_bytes) or NULL. */
 int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw,
                   int32_t ld_n, int32_t n_real, int32_t c_real, int impl, void* stream);
+/* (d->in_dtype is the type of `a`; d->out_f32 is reused as the PgDType of `g`: PG_BF16 or PG_F16) */
 
 /* bias gradient: db[n] += sum_m g[m*ldg + n], n < n_real (disc.py:19,45 biases) */
 int pg_colsum(const void* g, int64_t M, int32_t ldg, int32_t n_real, float* db, void* stream);
@@ -103,21 +113,22 @@ int pg_colsum(const void* g, int64_t M, int32_t ldg, int32_t n_real, float* db, 
 /* NCHW float -> NHWC bf16 channel slice [c_off, c_off+C) of a buffer with pixel stride ld
  * (trainer.py:55-60,65,96: .to(device) + torch.cat feeding the nets) */
 int pg_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t B, int32_t C, int32_t H, int32_t W,
-                                  int32_t ld, int32_t c_off, void* stream);
-/* NHWC (bf16 or f32, pixel stride ld, channel offset c_off) -> NCHW float */
+                                  int32_t ld, int32_t c_off, int32_t dst_dtype, void* stream);
+/* NHWC (src_f32 = PgDType of src, pixel stride ld, channel offset c_off) -> NCHW float */
 int pg_unpack_nhwc_to_nchw_f32(const void* src, int32_t src_f32, float* dst, int32_t B, int32_t C, int32_t H,
                                int32_t W, int32_t ld, int32_t c_off, void* stream);
 /* f32 NHWC (stride lds) channels [0,C) -> bf16 NHWC (stride ldd) channels [c_off, c_off+C) */
 int pg_copy_f32_to_bf16_slice(const float* src, int32_t lds, void* dst, int32_t ldd, int32_t c_off, int32_t C,
-                              int64_t npix, void* stream);
+                              int64_t npix, int32_t dst_dtype, void* stream);
 /* fp32 reference-layout weight -> packed bf16 [Np][16][C1p+C2p].
  * src element (n, c, tap) is at src[n*sn + c*sc + tap]; c < C1 maps to packed channel c, C1 <= c < C1+C2 maps to
  * C1p + (c-C1); flip != 0 reverses the taps (15 - tap); everything else is zero. */
 int pg_pack_weight(const float* src, void* dst, int32_t N, int32_t Np, int32_t C1, int32_t C1p, int32_t C2,
-                   int32_t C2p, int64_t sn, int64_t sc, int32_t flip, void* stream);
+                   int32_t C2p, int64_t sn, int64_t sc, int32_t flip, int32_t dst_dtype, void* stream);
 
 /* ---- InstanceNorm2d(affine=False, eps=1e-5) + activation + Dropout(0.2)
  *      (unet.py:20-28,55-66; disc.py:32,42) ---- */
+/* In this group x_f32 / y_f32 are PgDType values (PG_BF16, PG_F32, PG_F16); dy / dx gradients are bf16. */
 /* sums[(b*C + c)*2 + {0,1}] += {sum, sum of squares} over the HW pixels of image b (caller zeroes sums) */
 int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_t HW, int32_t C, int32_t ld, float* sums,
                       void* stream);

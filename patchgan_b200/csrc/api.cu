@@ -42,6 +42,8 @@ static int validate(const PgConvDesc* d, const char* who) {
   PG_REQUIRE(d->ld1 >= d->C1 && d->ld1 % 8 == 0 && (d->C2 == 0 || (d->ld2 >= d->C2 && d->ld2 % 8 == 0)),
              "%s: bad pixel strides", who);
   PG_REQUIRE(d->ldo >= d->N && d->ldo % 8 == 0, "%s: bad output stride %d", who, d->ldo);
+  PG_REQUIRE(d->in_dtype == PG_BF16 || d->in_dtype == PG_F16, "%s: in_dtype must be PG_BF16 or PG_F16", who);
+  PG_REQUIRE(d->out_f32 >= PG_BF16 && d->out_f32 <= PG_F16, "%s: bad output dtype %d", who, d->out_f32);
   if (d->mode == PG_CONV) {
     PG_REQUIRE((d->stride == 1 || d->stride == 2) && (d->pad == 1 || d->pad == 2), "%s: stride/pad unsupported", who);
     PG_REQUIRE(d->Hout == (d->Hin + 2 * d->pad - 4) / d->stride + 1 && d->Wout == (d->Win + 2 * d->pad - 4) / d->stride + 1,

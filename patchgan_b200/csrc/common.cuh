@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -28,6 +29,7 @@ int check_launch(const char* what);
   do {                                                                             \
     cudaError_t e__ = (call);                                                      \
     if (e__ != cudaSuccess) {                                                      \
+      cudaGetLastError(); /* clear the sticky-until-read error */                  \
       pg::set_error("%s failed: %s", #call, cudaGetErrorString(e__));              \
       return PG_ERR_CUDA;                                                          \
     }                                                                              \
@@ -71,6 +73,23 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// 8 x 16-bit (bf16 or fp16, selected by PgDType) <-> 8 float through one 16-byte vector
+__device__ __forceinline__ void unpack8h(const uint4& v, float* f) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __half22float2(h[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 pack8h(const float* f) {
+  uint4 v;
+  __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
 // 8 bf16 <-> 8 float through one 16-byte vector
 __device__ __forceinline__ void unpack8(const uint4& v, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
@@ -87,6 +106,19 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   return v;
+}
+
+__device__ __forceinline__ void unpack8dt(const uint4& v, int dt, float* f) {
+  if (dt == PG_F16) unpack8h(v, f); else unpack8(v, f);
+}
+__device__ __forceinline__ uint4 pack8dt(const float* f, int dt) { return dt == PG_F16 ? pack8h(f) : pack8(f); }
+__device__ __forceinline__ unsigned short to16(float x, int dt) {
+  if (dt == PG_F16) return __half_as_ushort(__float2half_rn(x));
+  return __bfloat16_as_ushort(__float2bfloat16(x));
+}
+__device__ __forceinline__ float from16(unsigned short u, int dt) {
+  if (dt == PG_F16) return __half2float(__ushort_as_half(u));
+  return __bfloat162float(__ushort_as_bfloat16(u));
 }
 
 // Counter-based RNG for dropout: one 32-bit draw per element index, reproducible in backward

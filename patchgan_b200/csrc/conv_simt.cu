@@ -10,7 +10,7 @@ struct ConvK {
   const bf16* w;
   const float* bias;
   void* out;
-  int mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo, n_valid, act, out_f32;
+  int mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo, n_valid, act, out_f32, in_dt;
   int Ha, Wa;  // lattice the tiles walk: PG_CONV -> (Hout, Wout); PG_CONVT -> (Hin, Win) per parity class
   long long M;
 };
@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvK p) {
       if (n0 + lrow < p.N && c < Ctot)
         wv = *reinterpret_cast<const uint4*>(p.w + ((long long)(n0 + lrow) * 16 + wtap) * Ctot + c);
       float af[8], wf[8];
-      unpack8(av, af);
-      unpack8(wv, wf);
+      unpack8dt(av, p.in_dt, af);
+      unpack8dt(wv, p.in_dt, wf);
       __syncthreads();
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -117,15 +117,13 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvK p) {
       x = act_apply(p.act, x);
       v[j] = (n + j < p.n_valid) ? x : 0.f;
     }
-    if (p.out_f32) {
+    if (p.out_f32 == PG_F32) {
       *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n) =
           make_float4(v[0], v[1], v[2], v[3]);
     } else {
-      __nv_bfloat162 h0 = __floats2bfloat162_rn(v[0], v[1]);
-      __nv_bfloat162 h1 = __floats2bfloat162_rn(v[2], v[3]);
       uint2 u;
-      u.x = *reinterpret_cast<uint32_t*>(&h0);
-      u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.x = (uint32_t)to16(v[0], p.out_f32) | ((uint32_t)to16(v[1], p.out_f32) << 16);
+      u.y = (uint32_t)to16(v[2], p.out_f32) | ((uint32_t)to16(v[3], p.out_f32) << 16);
       *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n) = u;
     }
   }
@@ -142,6 +140,7 @@ int conv_fwd_simt(const PgConvDesc* d, const void* src1, const void* src2, const
   p.mode = d->mode; p.stride = d->stride; p.pad = d->pad; p.B = d->B; p.Hin = d->Hin; p.Win = d->Win;
   p.Hout = d->Hout; p.Wout = d->Wout; p.C1 = d->C1; p.C2 = d->C2; p.ld1 = d->ld1; p.ld2 = d->ld2;
   p.N = d->N; p.ldo = d->ldo; p.n_valid = d->n_valid; p.act = d->act; p.out_f32 = d->out_f32;
+  p.in_dt = d->in_dtype;
   if (d->mode == PG_CONVT) { p.Ha = d->Hin; p.Wa = d->Win; } else { p.Ha = d->Hout; p.Wa = d->Wout; }
   p.M = (long long)d->B * p.Ha * p.Wa;
   dim3 grid((unsigned)((p.M + TM - 1) / TM), (unsigned)((d->N + TN - 1) / TN), d->mode == PG_CONVT ? 4 : 1);
@@ -156,7 +155,7 @@ struct WgradK {
   const bf16* a;
   const bf16* g;
   float* dw;
-  int stride, pad, B, Hin, Win, Hout, Wout, C, lda, N, ldg, ld_n, n_real, c_real;
+  int stride, pad, B, Hin, Win, Hout, Wout, C, lda, N, ldg, ld_n, n_real, c_real, a_dt, g_dt;
   long long M;
   int chunk;  // pixels per split
   int ctiles;
@@ -199,8 +198,8 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradK p) {
         av = *reinterpret_cast<const uint4*>(p.a + (((long long)b * p.Hin + iy) * p.Win + ix) * p.lda + c);
     }
     float gf[8], af[8];
-    unpack8(gv, gf);
-    unpack8(av, af);
+    unpack8dt(gv, p.g_dt, gf);
+    unpack8dt(av, p.a_dt, af);
     __syncthreads();
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -240,6 +239,7 @@ int conv_wgrad_simt(const PgConvDesc* d, const void* a, const void* g, int ldg, 
   p.stride = d->stride; p.pad = d->pad; p.B = d->B; p.Hin = d->Hin; p.Win = d->Win; p.Hout = d->Hout;
   p.Wout = d->Wout; p.C = d->C1; p.lda = d->ld1; p.N = d->N; p.ldg = ldg; p.ld_n = ld_n;
   p.n_real = n_real; p.c_real = c_real;
+  p.a_dt = d->in_dtype; p.g_dt = d->out_f32;
   p.M = (long long)d->B * d->Hout * d->Wout;
   const int ntiles = (d->N + 63) / 64;
   p.ctiles = (d->C1 + 63) / 64;

@@ -144,6 +144,7 @@ struct TcParams {
 
 constexpr int TC_THREADS = 192;
 constexpr int MAX_STAGES = 8;
+constexpr int TC_MAX_DYN_SMEM = 224 * 1024;
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
@@ -266,14 +267,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           x = act_apply(p.act, x);
           f[j] = (n + j < p.n_valid) ? x : 0.f;
         }
-        if (p.out_f32) {
+        if (p.out_f32 == PG_F32) {
           float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n);
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         } else {
           uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n);
-          o[0] = pack8(f);
-          o[1] = pack8(f + 8);
+          o[0] = pack8dt(f, p.out_f32);
+          o[1] = pack8dt(f + 8, p.out_f32);
         }
       }
     }
@@ -357,12 +358,13 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
   p.layout_type = pl.swz == 128 ? 2u : (pl.swz == 64 ? 4u : 6u);
   p.sbo = 8u * pl.swz;
   // instruction descriptor: c=f32 (1<<4), a=bf16 (1<<7), b=bf16 (1<<10), K-major both, N>>3 at 17, M>>4 at 24
-  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const uint32_t fmt = d->in_dtype == PG_F16 ? 0u : 1u;   // F16F32Format: F16 = 0, BF16 = 1
+  p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   p.a_bytes = 128u * pl.swz;
   p.b_bytes = ((uint32_t)bn * pl.swz + 1023u) & ~1023u;
   p.tx_bytes = 128u * pl.swz + (uint32_t)bn * pl.swz;
   const uint32_t per_stage = p.a_bytes + p.b_bytes;
-  int stages = (int)((200u * 1024u) / per_stage);
+  int stages = (int)(((uint32_t)TC_MAX_DYN_SMEM - 2048u) / per_stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int ksteps = p.ntaps * (p.nk1 + p.nk2);
   if (stages > ksteps) stages = ksteps;
@@ -385,14 +387,14 @@ bool conv_fwd_tc_supported(const PgConvDesc* d, const void* src1, const void* sr
 }
 
 static int encode_act_map(CUtensorMap* m, const void* base, int C, int ld, int B, int H, int W, int bk, int tw, int th,
-                          int tb, int es, int swz) {
+                          int tb, int es, int swz, int dt) {
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
   cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(tw * es), (cuuint32_t)(th * es), (cuuint32_t)tb};
   cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
   CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                      : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = get_encode()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = get_encode()(m, dt == PG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -415,10 +417,10 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   p.out = out;
   const int es = d->mode == PG_CONV ? d->stride : 1;
   CUtensorMap mA1, mA2, mB;
-  if (int e = encode_act_map(&mA1, src1, d->C1, d->ld1, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB, es, pl.swz))
+  if (int e = encode_act_map(&mA1, src1, d->C1, d->ld1, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB, es, pl.swz, d->in_dtype))
     return e;
   if (d->C2 > 0) {
-    if (int e = encode_act_map(&mA2, src2, d->C2, d->ld2, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB, es, pl.swz))
+    if (int e = encode_act_map(&mA2, src2, d->C2, d->ld2, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB, es, pl.swz, d->in_dtype))
       return e;
   } else {
     mA2 = mA1;
@@ -430,7 +432,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     cuuint32_t estr[2] = {1, 1};
     CUtensorMapSwizzle sw = pl.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                           : (pl.swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-    CUresult r = get_encode()(&mB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
+    CUresult r = get_encode()(&mB, d->in_dtype == PG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides, box, estr,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -438,10 +440,11 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
       return PG_ERR_CUDA;
     }
   }
-  static size_t smem_set = 0;
-  if (pl.smem > smem_set) {
-    PG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    smem_set = 227 * 1024;
+  static bool smem_set = false;
+  if (!smem_set) {
+    // 227 KB opt-in limit per block minus this kernel's static shared memory (barriers, 1 KB with alignment)
+    PG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
+    smem_set = true;
   }
   conv_tc_kernel<<<pl.grid, TC_THREADS, pl.smem, stream>>>(mA1, mA2, mB, p);
   return check_launch("conv_tc_kernel");

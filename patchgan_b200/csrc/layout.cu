@@ -5,13 +5,13 @@
 namespace pg {
 
 // one thread per pixel; reads are coalesced per channel plane, each thread writes its C channels
-__global__ void pack_nchw_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int C, long long HW, int ld,
-                                 int c_off) {
+__global__ void pack_nchw_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int C, long long HW,
+                                 int ld, int c_off, int dt) {
   const int b = blockIdx.y;
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
-    bf16* o = dst + ((long long)b * HW + p) * ld + c_off;
+    unsigned short* o = dst + ((long long)b * HW + p) * ld + c_off;
     const float* s = src + (long long)b * C * HW + p;
-    for (int c = 0; c < C; ++c) o[c] = __float2bfloat16(s[(long long)c * HW]);
+    for (int c = 0; c < C; ++c) o[c] = to16(s[(long long)c * HW], dt);
   }
 }
 
@@ -22,24 +22,24 @@ __global__ void unpack_nhwc_kernel(const void* __restrict__ src, int src_f32, fl
     float* o = dst + (long long)b * C * HW + p;
     const long long base = ((long long)b * HW + p) * ld + c_off;
     for (int c = 0; c < C; ++c) {
-      float v = src_f32 ? reinterpret_cast<const float*>(src)[base + c]
-                        : __bfloat162float(reinterpret_cast<const bf16*>(src)[base + c]);
+      float v = src_f32 == PG_F32 ? reinterpret_cast<const float*>(src)[base + c]
+                                  : from16(reinterpret_cast<const unsigned short*>(src)[base + c], src_f32);
       o[(long long)c * HW] = v;
     }
   }
 }
 
-__global__ void copy_f32_to_bf16_slice_kernel(const float* __restrict__ src, int lds, bf16* __restrict__ dst, int ldd,
-                                              int c_off, int C, long long npix) {
+__global__ void copy_f32_to_bf16_slice_kernel(const float* __restrict__ src, int lds, unsigned short* __restrict__ dst,
+                                              int ldd, int c_off, int C, long long npix, int dt) {
   for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npix;
        p += (long long)gridDim.x * blockDim.x) {
-    for (int c = 0; c < C; ++c) dst[p * ldd + c_off + c] = __float2bfloat16(src[p * lds + c]);
+    for (int c = 0; c < C; ++c) dst[p * ldd + c_off + c] = to16(src[p * lds + c], dt);
   }
 }
 
 // dst[n][t][cp] over the padded extents; gathers from the fp32 reference layout
-__global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restrict__ dst, int N, int Np, int C1,
-                                   int C1p, int C2, int C2p, long long sn, long long sc, int flip) {
+__global__ void pack_weight_kernel(const float* __restrict__ src, unsigned short* __restrict__ dst, int N, int Np, int C1,
+                                   int C1p, int C2, int C2p, long long sn, long long sc, int flip, int dt) {
   const int Cp = C1p + C2p;
   const long long total = (long long)Np * 16 * Cp;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -52,7 +52,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, bf16* __restri
     else { if (cp - C1p < C2) c = C1 + (cp - C1p); }
     float v = 0.f;
     if (n < N && c >= 0) v = src[n * sn + c * sc + (flip ? 15 - t : t)];
-    dst[i] = __float2bfloat16(v);
+    dst[i] = to16(v, dt);
   }
 }
 
@@ -68,11 +68,12 @@ static unsigned grid1d(long long work, int threads) {
 using namespace pg;
 
 extern "C" int pg_pack_nchw_f32_to_nhwc_bf16(const float* src, void* dst, int32_t B, int32_t C, int32_t H, int32_t W,
-                                             int32_t ld, int32_t c_off, void* stream) {
+                                             int32_t ld, int32_t c_off, int32_t dst_dtype, void* stream) {
+  PG_REQUIRE(dst_dtype == PG_BF16 || dst_dtype == PG_F16, "pg_pack_nchw: dst_dtype must be 16-bit");
   PG_REQUIRE(B > 0 && C > 0 && c_off >= 0 && c_off + C <= ld, "pg_pack_nchw: bad C=%d c_off=%d ld=%d", C, c_off, ld);
   const long long HW = (long long)H * W;
   dim3 grid(grid1d(HW, 256), B);
-  pack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, C, HW, ld, c_off);
+  pack_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (unsigned short*)dst, C, HW, ld, c_off, dst_dtype);
   return check_launch("pack_nchw_kernel");
 }
 
@@ -86,18 +87,18 @@ extern "C" int pg_unpack_nhwc_to_nchw_f32(const void* src, int32_t src_f32, floa
 }
 
 extern "C" int pg_copy_f32_to_bf16_slice(const float* src, int32_t lds, void* dst, int32_t ldd, int32_t c_off,
-                                         int32_t C, int64_t npix, void* stream) {
+                                         int32_t C, int64_t npix, int32_t dst_dtype, void* stream) {
   PG_REQUIRE(C > 0 && C <= lds && c_off + C <= ldd, "pg_copy_f32_to_bf16_slice: bad C=%d", C);
-  copy_f32_to_bf16_slice_kernel<<<grid1d(npix, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (bf16*)dst, ldd, c_off,
-                                                                                    C, npix);
+  copy_f32_to_bf16_slice_kernel<<<grid1d(npix, 256), 256, 0, (cudaStream_t)stream>>>(src, lds, (unsigned short*)dst, ldd,
+                                                                                    c_off, C, npix, dst_dtype);
   return check_launch("copy_f32_to_bf16_slice_kernel");
 }
 
 extern "C" int pg_pack_weight(const float* src, void* dst, int32_t N, int32_t Np, int32_t C1, int32_t C1p, int32_t C2,
-                              int32_t C2p, int64_t sn, int64_t sc, int32_t flip, void* stream) {
+                              int32_t C2p, int64_t sn, int64_t sc, int32_t flip, int32_t dst_dtype, void* stream) {
   PG_REQUIRE(N <= Np && C1 <= C1p && C2 <= C2p, "pg_pack_weight: padded extents smaller than real ones");
   const long long total = (long long)Np * 16 * (C1p + C2p);
-  pack_weight_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (bf16*)dst, N, Np, C1, C1p, C2, C2p, sn,
-                                                                          sc, flip);
+  pack_weight_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned short*)dst, N, Np, C1, C1p, C2,
+                                                                          C2p, sn, sc, flip, dst_dtype);
   return check_launch("pack_weight_kernel");
 }

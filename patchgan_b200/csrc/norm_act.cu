@@ -13,23 +13,24 @@ __device__ __forceinline__ unsigned long long mix_seed(unsigned long long s, uns
   return s ^ (salt * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull);
 }
 
+// is_f32 is a PgDType: PG_BF16 (0), PG_F32 (1) or PG_F16 (2)
 __device__ __forceinline__ void load8(const void* base, int is_f32, long long off, float* f) {
-  if (is_f32) {
+  if (is_f32 == PG_F32) {
     const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + off);
     float4 a = p[0], b = p[1];
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
   } else {
     uint4 v = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + off);
-    unpack8(v, f);
+    unpack8dt(v, is_f32, f);
   }
 }
 __device__ __forceinline__ void store8(void* base, int is_f32, long long off, const float* f) {
-  if (is_f32) {
+  if (is_f32 == PG_F32) {
     float4* p = reinterpret_cast<float4*>(reinterpret_cast<float*>(base) + off);
     p[0] = make_float4(f[0], f[1], f[2], f[3]);
     p[1] = make_float4(f[4], f[5], f[6], f[7]);
   } else {
-    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + off) = pack8(f);
+    *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(base) + off) = pack8dt(f, is_f32);
   }
 }
 

@@ -31,9 +31,9 @@ class _DiscFunction(torch.autograd.Function):
         eng = module._engine()
         B, C, H, W = x.shape
         xin = eng.new_input(B, H, W, x.device)
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.contiguous().float().data_ptr(), xin.ptr, B, C, H, W, xin.ld, 0,
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.contiguous().float().data_ptr(), xin.ptr, B, C, H, W, xin.ld, 0, xin.dt,
                _stream())
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in params))
+        need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
         p, saved = eng.forward(xin, save=need_grad)
         out = torch.empty((B, 1, p.H, p.W), device=x.device, dtype=torch.float32)
         L.call('pg_unpack_nhwc_to_nchw_f32', p.ptr, 1, out.data_ptr(), B, 1, p.H, p.W, p.ld, 0, _stream())
@@ -49,7 +49,7 @@ class _DiscFunction(torch.autograd.Function):
         p = ctx.p
         dev = dout.device
         dpk = new_act(B, p.H, p.W, p.ld, dev, zero=True)
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', dout.contiguous().data_ptr(), dpk.ptr, B, 1, p.H, p.W, dpk.ld, 0,
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', dout.contiguous().data_ptr(), dpk.ptr, B, 1, p.H, p.W, dpk.ld, 0, dpk.dt,
                _stream())
         d_raw = new_act(B, p.H, p.W, p.ld, dev)
         L.call('pg_act_bwd_from_output', p.ptr, 1, p.ld, dpk.ptr, dpk.ld, d_raw.ptr, d_raw.ld, B * p.H * p.W, p.ld,
@@ -65,7 +65,7 @@ class _DiscFunction(torch.autograd.Function):
         gx = None
         if ctx.x_needs_grad:
             gx = torch.empty((B, C, H, W), device=dev, dtype=torch.float32)
-            L.call('pg_unpack_nhwc_to_nchw_f32', dx.ptr, 0, gx.data_ptr(), B, C, H, W, dx.ld, 0, _stream())
+            L.call('pg_unpack_nhwc_to_nchw_f32', dx.ptr, dx.dt, gx.data_ptr(), B, C, H, W, dx.ld, 0, _stream())
         return (None, gx) + tuple(grads[n] for n in names)
 
 

@@ -34,37 +34,44 @@ def require_cuda(t, what):
                            'kernels only and has no CPU path')
 
 
-class Act:
-    """A (possibly channel-sliced) NHWC activation: keeps its storage alive, carries ptr / C / pixel stride."""
-    __slots__ = ('t', 'ptr', 'C', 'ld', 'B', 'H', 'W', 'f32')
+BF16, F32, F16 = L.DT_BF16, L.DT_F32, L.DT_F16
+TORCH_DT = {BF16: torch.bfloat16, F32: torch.float32, F16: torch.float16}
 
-    def __init__(self, t, B, H, W, C, ld=None, off=0, f32=False):
+
+class Act:
+    """A (possibly channel-sliced) NHWC activation: keeps its storage alive, carries ptr / C / pixel stride / dtype."""
+    __slots__ = ('t', 'ptr', 'C', 'ld', 'B', 'H', 'W', 'dt')
+
+    def __init__(self, t, B, H, W, C, ld=None, off=0, dt=BF16):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
         self.ld = ld if ld is not None else C
-        self.f32 = f32
-        self.ptr = t.data_ptr() + off * (4 if f32 else 2)
+        self.dt = dt
+        self.ptr = t.data_ptr() + off * self.esize
+
+    @property
+    def esize(self):
+        return 4 if self.dt == F32 else 2
 
     def slice(self, c0, C):
-        return Act(self.t, self.B, self.H, self.W, C, self.ld, (self.ptr - self.t.data_ptr()) // (4 if self.f32 else 2) + c0,
-                   self.f32)
+        return Act(self.t, self.B, self.H, self.W, C, self.ld, (self.ptr - self.t.data_ptr()) // self.esize + c0, self.dt)
 
     def first(self, nb):
         """The first nb images of the batch (same storage)."""
-        a = Act(self.t, nb, self.H, self.W, self.C, self.ld, 0, self.f32)
+        a = Act(self.t, nb, self.H, self.W, self.C, self.ld, 0, self.dt)
         a.ptr = self.ptr
         return a
 
 
-def new_act(B, H, W, C, device, f32=False, zero=False):
+def new_act(B, H, W, C, device, dt=BF16, zero=False):
     fn = torch.zeros if zero else torch.empty
-    t = fn((B, H, W, C), device=device, dtype=torch.float32 if f32 else torch.bfloat16)
-    return Act(t, B, H, W, C, f32=f32)
+    t = fn((B, H, W, C), device=device, dtype=TORCH_DT[dt])
+    return Act(t, B, H, W, C, dt=dt)
 
 
-def conv_desc(mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo, n_valid=None, act=0, out_f32=0,
-              has_bias=0):
+def conv_desc(mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo, n_valid=None, act=0, out_dt=BF16,
+              has_bias=0, in_dt=BF16):
     return L.ConvDesc(mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo,
-                      N if n_valid is None else n_valid, act, out_f32, has_bias)
+                      N if n_valid is None else n_valid, act, out_dt, has_bias, in_dt)
 
 
 class Config:
@@ -72,6 +79,10 @@ class Config:
     PATCHGAN_B200_IMPL = auto | simt | tcgen05 selects the convolution implementation."""
     impl = {'auto': L.IMPL_AUTO, 'simt': L.IMPL_SIMT, 'tcgen05': L.IMPL_TCGEN05}[
         os.environ.get('PATCHGAN_B200_IMPL', 'auto')]
+    # 16-bit type of the FORWARD tensor-core operands (activations + weights).  fp16 and bf16 run at the same
+    # tcgen05 rate; fp16's 3 extra mantissa bits keep every layer within the 1e-2 activation tolerance (bf16
+    # reaches 1.3-2e-2 at the 2x2 bottleneck, see DESIGN.md).  Gradient tensors are always bf16 (range).
+    fwd_dt = {'fp16': L.DT_F16, 'bf16': L.DT_BF16}[os.environ.get('PATCHGAN_B200_FWD_DTYPE', 'fp16')]
 
 
 def run_conv(desc, src1, src2, w, bias, out):
@@ -99,25 +110,26 @@ class PackedWeights:
 
     def __init__(self, spec, device):
         self.spec = spec
-        self.fwd = torch.empty((spec.np, 16, spec.cinp), device=device, dtype=torch.bfloat16)
+        self.fwd_dt = Config.fwd_dt
+        self.fwd = torch.empty((spec.np, 16, spec.cinp), device=device, dtype=TORCH_DT[self.fwd_dt])
         self.bwd = torch.empty((spec.cinp, 16, spec.np), device=device, dtype=torch.bfloat16)
 
     def pack(self, w):
         s, st = self.spec, _stream()
         wp = w.data_ptr()
         if s.kind == 'conv':      # w: (cout, cin, 4, 4)
-            L.call('pg_pack_weight', wp, self.fwd.data_ptr(), s.cout, s.np, s.c1, s.c1p, 0, 0, s.cin * 16, 16, 0, st)
+            L.call('pg_pack_weight', wp, self.fwd.data_ptr(), s.cout, s.np, s.c1, s.c1p, 0, 0, s.cin * 16, 16, 0, self.fwd_dt, st)
             # dgrad operand W'[ci][tap][co]; stride-1 layers run dgrad as a flipped stride-1 conv
             L.call('pg_pack_weight', wp, self.bwd.data_ptr(), s.cin, s.cinp, s.cout, s.np, 0, 0, 16, s.cin * 16,
-                   1 if s.stride == 1 else 0, st)
+                   1 if s.stride == 1 else 0, BF16, st)
         else:                     # convT, w: (cin_total, cout, 4, 4)
             L.call('pg_pack_weight', wp, self.fwd.data_ptr(), s.cout, s.np, s.c1, s.c1p, s.c2, s.c2p, 16, s.cout * 16, 0,
-                   st)
+                   self.fwd_dt, st)
             # rows of the dgrad operand live in the padded-concat channel space
-            L.call('pg_pack_weight', wp, self.bwd.data_ptr(), s.c1, s.c1p, s.cout, s.np, 0, 0, s.cout * 16, 16, 0, st)
+            L.call('pg_pack_weight', wp, self.bwd.data_ptr(), s.c1, s.c1p, s.cout, s.np, 0, 0, s.cout * 16, 16, 0, BF16, st)
             if s.c2:
                 L.call('pg_pack_weight', wp + s.c1 * s.cout * 16 * 4, self.bwd.data_ptr() + s.c1p * 16 * s.np * 2, s.c2,
-                       s.c2p, s.cout, s.np, 0, 0, s.cout * 16, 16, 0, st)
+                       s.c2p, s.cout, s.np, 0, 0, s.cout * 16, 16, 0, BF16, st)
 
 
 class NetEngine:
@@ -145,7 +157,7 @@ class NetEngine:
         if dev.type != 'cuda':
             raise RuntimeError('patchgan_b200: module parameters must live on a CUDA device (no CPU path)')
         stamp = tuple((ps[s.wname].data_ptr(), ps[s.wname]._version) for s in self.specs)
-        if self.packed is None or self.packed[0].fwd.device != dev:
+        if self.packed is None or self.packed[0].fwd.device != dev or self.packed[0].fwd_dt != Config.fwd_dt:
             self.packed = [PackedWeights(s, dev) for s in self.specs]
             self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
             self._stamp = None
@@ -172,13 +184,13 @@ class NetEngine:
 
 def norm_fwd(x, sums, out, act, drop_p, seed, salt):
     HW = x.H * x.W
-    L.call('pg_norm_act_fwd', x.ptr, int(x.f32), sums.data_ptr() if sums is not None else None, out.ptr, int(out.f32),
+    L.call('pg_norm_act_fwd', x.ptr, x.dt, sums.data_ptr() if sums is not None else None, out.ptr, out.dt,
            x.B, HW, x.C, x.ld, out.ld, act, drop_p, seed.data_ptr() if seed is not None else None, salt, _stream())
 
 
 def instnorm_stats(x):
     sums = torch.zeros((x.B, x.C, 2), device=x.t.device, dtype=torch.float32)
-    L.call('pg_instnorm_stats', x.ptr, int(x.f32), x.B, x.H * x.W, x.C, x.ld, sums.data_ptr(), _stream())
+    L.call('pg_instnorm_stats', x.ptr, x.dt, x.B, x.H * x.W, x.C, x.ld, sums.data_ptr(), _stream())
     return sums
 
 
@@ -191,16 +203,16 @@ def norm_bwd(x, sums, dy1, dy2, act, drop_p, seed, salt):
     sp = seed.data_ptr() if seed is not None else None
     p2, l2 = (dy2.ptr, dy2.ld) if dy2 is not None else (None, 0)
     st = _stream()
-    L.call('pg_norm_act_bwd_reduce', x.ptr, int(x.f32), sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), x.B,
+    L.call('pg_norm_act_bwd_reduce', x.ptr, x.dt, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), x.B,
            HW, x.C, x.ld, act, drop_p, sp, salt, st)
-    L.call('pg_norm_act_bwd_apply', x.ptr, int(x.f32), sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(),
+    L.call('pg_norm_act_bwd_apply', x.ptr, x.dt, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(),
            dx.ptr, dx.ld, x.B, HW, x.C, x.ld, act, drop_p, sp, salt, st)
     return dx
 
 
 def act_bwd_out(y, dy, act):
     dx = new_act(y.B, y.H, y.W, y.C, y.t.device)
-    L.call('pg_act_bwd_from_output', y.ptr, int(y.f32), y.ld, dy.ptr, dy.ld, dx.ptr, dx.ld, y.B * y.H * y.W, y.C, act,
+    L.call('pg_act_bwd_from_output', y.ptr, y.dt, y.ld, dy.ptr, dy.ld, dx.ptr, dx.ld, y.B * y.H * y.W, y.C, act,
            _stream())
     return dx
 
@@ -237,8 +249,8 @@ class GeneratorEngine(NetEngine):
     def pack_input(self, x):
         """NCHW float -> NHWC bf16 with channels zero-padded to 16."""
         B, C, H, W = x.shape
-        a = new_act(B, H, W, self.in_cp, x.device, zero=True)
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), a.ptr, B, C, H, W, a.ld, 0, _stream())
+        a = new_act(B, H, W, self.in_cp, x.device, dt=Config.fwd_dt, zero=True)
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), a.ptr, B, C, H, W, a.ld, 0, a.dt, _stream())
         return a
 
     def forward(self, xin, training, save=True):
@@ -255,11 +267,11 @@ class GeneratorEngine(NetEngine):
                 # aten::instance_norm raises for a single spatial element in training mode
                 raise ValueError('Expected more than 1 spatial element when training (input too small for 7 '
                                  'stride-2 stages)')
-            raw = new_act(B, Ho, Wo, s.np, dev, f32=True)
-            run_conv(conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, raw.ld, out_f32=1), h, None,
-                     self.packed[i].fwd, None, raw)
+            raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
+            run_conv(conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, raw.ld, out_dt=F32,
+                               in_dt=h.dt), h, None, self.packed[i].fwd, None, raw)
             sums = instnorm_stats(raw)
-            out = new_act(B, Ho, Wo, s.np, dev)
+            out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt)
             dp = DROP_P if (training and s.dropout) else 0.0
             norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, i)
             ctx['enc'].append((h, raw, sums, out, dp) if save else None)
@@ -272,24 +284,24 @@ class GeneratorEngine(NetEngine):
             pw = self.packed[7 + i]
             c2, ld2 = (src2.C, src2.ld) if src2 is not None else (0, 0)
             if s.norm:
-                raw = new_act(B, Ho, Wo, s.np, dev, f32=True)
+                raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, raw.ld,
-                                   out_f32=1), src1, src2, pw.fwd, None, raw)
+                                   out_dt=F32, in_dt=src1.dt), src1, src2, pw.fwd, None, raw)
                 sums = instnorm_stats(raw)
-                out = new_act(B, Ho, Wo, s.np, dev)
+                out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt)
                 dp = DROP_P if (training and s.dropout) else 0.0
                 norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, 16 + i)
                 ctx['dec'].append((src1, src2, raw, sums, out, dp) if save else None)
             elif i < 6:
-                out = new_act(B, Ho, Wo, s.np, dev)
+                out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt)
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, out.ld,
-                                   act=L.ACT[s.act]), src1, src2, pw.fwd, None, out)
+                                   act=L.ACT[s.act], out_dt=out.dt, in_dt=src1.dt), src1, src2, pw.fwd, None, out)
                 ctx['dec'].append((src1, src2, None, None, out, 0.0) if save else None)
             else:
-                out = new_act(B, Ho, Wo, s.np, dev, f32=True)
+                out = new_act(B, Ho, Wo, s.np, dev, dt=F32)
                 fused = 0 if s.act == 'softmax' else L.ACT[s.act]
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, out.ld,
-                                   n_valid=s.cout, act=fused, out_f32=1), src1, src2, pw.fwd, None, out)
+                                   n_valid=s.cout, act=fused, out_dt=F32, in_dt=src1.dt), src1, src2, pw.fwd, None, out)
                 if s.act == 'softmax':
                     L.call('pg_softmax_fwd', out.ptr, out.ptr, B * Ho * Wo, s.cout, out.ld, _stream())
                 ctx['dec'].append((src1, src2, None, None, out, 0.0) if save else None)
@@ -309,11 +321,12 @@ class GeneratorEngine(NetEngine):
             pw = self.packed[7 + i]
             g = grads[s.wname]
             # weight gradient: dW[ci][co][tap] = sum x[ci] * dY[co] -- PG_CONV geometry with A = dY, G = layer input
-            wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C, src1.C)
+            wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C, src1.C,
+                           out_dt=src1.dt, in_dt=BF16)
             run_wgrad(wd, d_raw, src1, g.data_ptr(), s.cout * 16, s.c1, s.cout)
             if src2 is not None:
                 wd2 = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src2.H, src2.W, d_raw.C, 0, d_raw.ld, 0, src2.C,
-                                src2.C)
+                                src2.C, out_dt=src2.dt, in_dt=BF16)
                 run_wgrad(wd2, d_raw, src2, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout)
             # data gradient: stride-2 conv of dY with W'[ci][tap][co]
             din = new_act(B, src1.H, src1.W, s.cinp, dev)
@@ -336,7 +349,7 @@ class GeneratorEngine(NetEngine):
             s = self.enc[i]
             h, raw, sums, out, dp = ctx['enc'][i]
             d_raw = norm_bwd(raw, sums, dy1, dskip[i] if i < 6 else None, L.ACT[s.act], dp, self.seed, i)
-            wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np)
+            wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16, in_dt=h.dt)
             run_wgrad(wd, h, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
             if i > 0 or need_dx:
                 din = new_act(B, h.H, h.W, s.cinp, dev)
@@ -373,7 +386,7 @@ class DiscriminatorEngine(NetEngine):
         self.in_cp = rup16(inc)
 
     def new_input(self, B, H, W, device):
-        return new_act(B, H, W, self.in_cp, device, zero=True)
+        return new_act(B, H, W, self.in_cp, device, dt=Config.fwd_dt, zero=True)
 
     def forward(self, xin, save=True):
         """xin: Act (B,H,W,in_cp) bf16 -> (p: f32 Act (B,Ho,Wo,16) with the patch probabilities in channel 0, ctx)."""
@@ -391,19 +404,19 @@ class DiscriminatorEngine(NetEngine):
                 raise RuntimeError(f'Discriminator: input too small at layer {li} ({h.H}x{h.W})')
             bias = ps[s.bname].detach() if s.bias else None
             if li == last:
-                out = new_act(B, Ho, Wo, s.np, dev, f32=True)
+                out = new_act(B, Ho, Wo, s.np, dev, dt=F32)
                 run_conv(conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, out.ld,
-                                   n_valid=s.cout, act=L.ACT[s.act], out_f32=1, has_bias=1), h, None, self.packed[li].fwd,
-                         bias, out)
+                                   n_valid=s.cout, act=L.ACT[s.act], out_dt=F32, has_bias=1, in_dt=h.dt), h, None,
+                         self.packed[li].fwd, bias, out)
                 ctx.append((h, None, None, out) if save else None)
             else:
-                t = new_act(B, Ho, Wo, s.np, dev)
+                t = new_act(B, Ho, Wo, s.np, dev, dt=h.dt)
                 run_conv(conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, t.ld,
-                                   n_valid=s.cout, act=L.ACT[s.act], has_bias=int(s.bias)), h, None, self.packed[li].fwd,
-                         bias, t)
+                                   n_valid=s.cout, act=L.ACT[s.act], out_dt=t.dt, has_bias=int(s.bias), in_dt=h.dt), h,
+                         None, self.packed[li].fwd, bias, t)
                 if s.norm:
                     sums = instnorm_stats(t)
-                    out = new_act(B, Ho, Wo, s.np, dev)
+                    out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt)
                     norm_fwd(t, sums, out, 0, 0.0, None, 0)
                     ctx.append((h, t, sums, out) if save else None)
                 else:
@@ -424,7 +437,8 @@ class DiscriminatorEngine(NetEngine):
             h, t, sums, out = ctx[li]
             h = h.first(B)
             if grads is not None:
-                wd = conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, d_raw.H, d_raw.W, h.C, 0, h.ld, 0, s.np, s.np)
+                wd = conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, d_raw.H, d_raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
+                               in_dt=h.dt)
                 run_wgrad(wd, h, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
                 if s.bias:
                     L.call('pg_colsum', d_raw.ptr, B * d_raw.H * d_raw.W, d_raw.ld, s.cout, grads[s.bname].data_ptr(),

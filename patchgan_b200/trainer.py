@@ -103,16 +103,16 @@ class Trainer:
         xin = G.pack_input(x)
         dboth = D.new_input(2 * B, H, W, dev)
         half = B * H * W * dboth.ld * 2
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), dboth.ptr, B, cin, H, W, dboth.ld, 0, st)
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), dboth.ptr + half, B, cin, H, W, dboth.ld, 0, st)
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', y.data_ptr(), dboth.ptr + half, B, cout, H, W, dboth.ld, cin, st)
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), dboth.ptr, B, cin, H, W, dboth.ld, 0, dboth.dt, st)
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), dboth.ptr + half, B, cin, H, W, dboth.ld, 0, dboth.dt, st)
+        L.call('pg_pack_nchw_f32_to_nhwc_bf16', y.data_ptr(), dboth.ptr + half, B, cout, H, W, dboth.ld, cin, dboth.dt, st)
 
         # ---- generator forward (trainer.py:63), D(cat(x, G(x))) and D(cat(x, y)) (trainer.py:65-66, 96-97)
         if gm.training and gm.use_dropout:
             G.ensure_packed()
             G.bump_seed()
         p, gctx = G.forward(xin, gm.training, save=train)
-        L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.ptr, dboth.ld, cin, cout, B * H * W, st)
+        L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.ptr, dboth.ld, cin, cout, B * H * W, dboth.dt, st)
         pd, dctx = D.forward(dboth, save=train)
         npatch = B * pd.H * pd.W
         pd_real_ptr = pd.ptr + npatch * pd.ld * 4

@@ -55,7 +55,7 @@ class _UNetFunction(torch.autograd.Function):
         eng = module._engine()
         B, C, H, W = x.shape
         xin = eng.pack_input(x.contiguous().float())
-        need_grad = torch.is_grad_enabled() and (x.requires_grad or any(w.requires_grad for w in weights))
+        need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
         if module.training and module.use_dropout:
             eng.ensure_packed()
             eng.bump_seed()
@@ -76,7 +76,7 @@ class _UNetFunction(torch.autograd.Function):
         # dOut (NCHW float) -> NHWC bf16, then through the final activation
         dpk = new_act(B, H, W, p.ld, dev, zero=True)
         L.call('pg_pack_nchw_f32_to_nhwc_bf16', dout.contiguous().data_ptr(), dpk.ptr, B, module.output_nc, H, W, dpk.ld,
-               0, _stream())
+               0, dpk.dt, _stream())
         d_raw = new_act(B, H, W, p.ld, dev)
         L.call('pg_gen_out_bwd', p.ptr, p.ld, None, None, None, dpk.ptr, dpk.ld, 0, d_raw.ptr, d_raw.ld, B,
                module.output_nc, H * W, L.LOSS['none'], L.ACT[module.final_act], 0.0, _stream())
@@ -87,7 +87,7 @@ class _UNetFunction(torch.autograd.Function):
         gx = None
         if ctx.x_needs_grad:
             gx = torch.empty((B, C, H, W), device=dev, dtype=torch.float32)
-            L.call('pg_unpack_nhwc_to_nchw_f32', dx.ptr, 0, gx.data_ptr(), B, C, H, W, dx.ld, 0, _stream())
+            L.call('pg_unpack_nhwc_to_nchw_f32', dx.ptr, dx.dt, gx.data_ptr(), B, C, H, W, dx.ld, 0, _stream())
         return (None, gx) + tuple(grads[n] for n in names)
 
 
@@ -155,6 +155,6 @@ class UNet(nn.Module, Transferable):
             h6 = saved['enc'][6][3]
             B = x.shape[0]
             out = torch.empty((B, self.nf * 8, h6.H, h6.W), device=x.device, dtype=torch.float32)
-            L.call('pg_unpack_nhwc_to_nchw_f32', h6.ptr, 0, out.data_ptr(), B, self.nf * 8, h6.H, h6.W, h6.ld, 0,
+            L.call('pg_unpack_nhwc_to_nchw_f32', h6.ptr, h6.dt, out.data_ptr(), B, self.nf * 8, h6.H, h6.W, h6.ld, 0,
                    _stream())
         return out

@@ -1,0 +1,22 @@
+"""Configurations and the summary statistic shared by make_golden.py (which needs the reference) and the tests
+(which must not)."""
+import numpy as np
+
+CASES = {
+    # name: (G kwargs, D kwargs, loss_type, B, steps)
+    'tversky': (dict(input_nc=3, output_nc=1, nf=8, activation='leakyrelu', final_act='sigmoid'),
+                dict(input_nc=4, ndf=8, n_layers=3, norm=False), 'tversky', 2, 2),
+    'wbce': (dict(input_nc=3, output_nc=3, nf=8, activation='relu', final_act='sigmoid'),
+             dict(input_nc=6, ndf=8, n_layers=4, norm=True), 'weighted_bce', 2, 2),
+    'mae': (dict(input_nc=3, output_nc=2, nf=8, activation='tanh', final_act='softmax'),
+            dict(input_nc=5, ndf=8, n_layers=2, norm=False), 'MAE', 2, 2),
+}
+NS = 256
+
+
+def summarize(t):
+    a = np.asarray(t, dtype=np.float64).ravel()
+    idx = np.linspace(0, a.size - 1, min(NS, a.size)).astype(np.int64)
+    return np.concatenate([[a.mean(), a.std()], a[idx]])
+
+

@@ -24,9 +24,11 @@ def rng(seed=0):
     return np.random.default_rng(seed)
 
 
-def run_conv(desc, src1, src2, w, bias, out_f32, impl, Hout, Wout, N):
+def run_conv(desc, src1, src2, w, bias, out_dt, impl, Hout, Wout, N):
+    from patchgan_b200.engine import TORCH_DT
     B = desc.B
-    out = torch.full((B, Hout, Wout, desc.ldo), 7.0, device='cuda', dtype=torch.float32 if out_f32 else torch.bfloat16)
+    out_dt = L.DT_F32 if out_dt is True else (L.DT_BF16 if out_dt is False else out_dt)
+    out = torch.full((B, Hout, Wout, desc.ldo), 7.0, device='cuda', dtype=TORCH_DT[out_dt])
     L.call('pg_conv_fwd', ctypes.byref(desc), src1.data_ptr(), src2.data_ptr() if src2 is not None else None,
            w.data_ptr(), bias.data_ptr() if bias is not None else None, out.data_ptr(), impl, stream())
     torch.cuda.synchronize()
@@ -41,23 +43,28 @@ CONV_CASES = [
 ]
 
 
+DTS = [L.DT_BF16, L.DT_F16]
+DT_IDS = ['bf16', 'f16']
+
+
+@pytest.mark.parametrize('dt', DTS, ids=DT_IDS)
 @pytest.mark.parametrize('impl', IMPLS, ids=IMPL_IDS)
 @pytest.mark.parametrize('case', CONV_CASES, ids=[str(c) for c in CONV_CASES])
-def test_conv2d_forward(case, impl):
+def test_conv2d_forward(case, impl, dt):
     B, Ci, Co, H, s = case
     r = rng(1)
-    x = bf16_round(r.standard_normal((B, Ci, H, H)))
-    w = bf16_round(r.standard_normal((Co, Ci, 4, 4)) / np.sqrt(Ci * 16))
+    x = bf16_round(r.standard_normal((B, Ci, H, H)), dt)
+    w = bf16_round(r.standard_normal((Co, Ci, 4, 4)) / np.sqrt(Ci * 16), dt)
     b = r.standard_normal(Co).astype(np.float32)
     ref = orc.act_fwd('leakyrelu', orc.conv2d_fwd(x, w, b, s))
     Ho = ref.shape[2]
     Cip, Cop = rup16(Ci), rup16(Co)
-    xd = to_nhwc(x)
-    wd = pack_weight(w, Co, Cop, Ci, Cip, 0, 0, Ci * 16, 16)
+    xd = to_nhwc(x, dt=dt)
+    wd = pack_weight(w, Co, Cop, Ci, Cip, 0, 0, Ci * 16, 16, dt=dt)
     bd = torch.zeros(Cop, device='cuda')
     bd[:Co] = torch.from_numpy(b).cuda()
     d = conv_desc(L.PG_CONV, s, 1, B, H, H, Ho, Ho, Cip, 0, Cip, 0, Cop, Cop, n_valid=Co, act=L.ACT['leakyrelu'],
-                  out_f32=1, has_bias=1)
+                  out_dt=L.DT_F32, has_bias=1, in_dt=dt)
     out = run_conv(d, xd, None, wd, bd, True, impl, Ho, Ho, Cop)
     assert relerr(from_nhwc(out, Co), ref) < TOL
     if Cop > Co:
@@ -68,25 +75,26 @@ CONVT_CASES = [(2, 256, 0, 256, 2), (2, 256, 256, 256, 4), (1, 64, 64, 32, 16), 
                (3, 128, 128, 64, 8), (2, 64, 0, 64, 5)]
 
 
+@pytest.mark.parametrize('dt', DTS, ids=DT_IDS)
 @pytest.mark.parametrize('impl', IMPLS, ids=IMPL_IDS)
 @pytest.mark.parametrize('case', CONVT_CASES, ids=[str(c) for c in CONVT_CASES])
-def test_conv_transpose_forward_with_virtual_concat(case, impl):
+def test_conv_transpose_forward_with_virtual_concat(case, impl, dt):
     B, C1, C2, Co, H = case
     r = rng(2)
-    x1 = bf16_round(r.standard_normal((B, C1, H, H)))
-    x2 = bf16_round(r.standard_normal((B, C2, H, H))) if C2 else None
+    x1 = bf16_round(r.standard_normal((B, C1, H, H)), dt)
+    x2 = bf16_round(r.standard_normal((B, C2, H, H)), dt) if C2 else None
     Ci = C1 + C2
-    w = bf16_round(r.standard_normal((Ci, Co, 4, 4)) / np.sqrt(Ci * 4))
+    w = bf16_round(r.standard_normal((Ci, Co, 4, 4)) / np.sqrt(Ci * 4), dt)
     xin = x1 if x2 is None else np.concatenate([x1, x2], axis=1)
     ref = orc.act_fwd('sigmoid', orc.convT_fwd(xin, w))
     Cop = rup16(Co)
-    wd = pack_weight(w, Co, Cop, C1, rup16(C1), C2, rup16(C2) if C2 else 0, 16, Co * 16)
-    x1d = to_nhwc(x1)
-    x2d = to_nhwc(x2) if C2 else None
+    wd = pack_weight(w, Co, Cop, C1, rup16(C1), C2, rup16(C2) if C2 else 0, 16, Co * 16, dt=dt)
+    x1d = to_nhwc(x1, dt=dt)
+    x2d = to_nhwc(x2, dt=dt) if C2 else None
     d = conv_desc(L.PG_CONVT, 2, 1, B, H, H, 2 * H, 2 * H, rup16(C1), rup16(C2) if C2 else 0, rup16(C1),
-                  rup16(C2) if C2 else 0, Cop, Cop, n_valid=Co, act=L.ACT['sigmoid'], out_f32=0)
-    out = run_conv(d, x1d, x2d, wd, None, False, impl, 2 * H, 2 * H, Cop)
-    assert relerr(from_nhwc(out, Co), ref) < 5e-3     # bf16 output
+                  rup16(C2) if C2 else 0, Cop, Cop, n_valid=Co, act=L.ACT['sigmoid'], out_dt=dt, in_dt=dt)
+    out = run_conv(d, x1d, x2d, wd, None, dt, impl, 2 * H, 2 * H, Cop)
+    assert relerr(from_nhwc(out, Co), ref) < 5e-3     # 16-bit output
     if Cop > Co:
         assert float(out[..., Co:].float().abs().max()) == 0.0
 
@@ -109,9 +117,9 @@ def test_conv2d_data_gradient(case, impl):
     wd = pack_weight(w, Ci, Cip, Co, Cop, 0, 0, 16, Ci * 16, flip=1 if s == 1 else 0)
     dyd = to_nhwc(dy)
     if s == 2:
-        d = conv_desc(L.PG_CONVT, 2, 1, B, Ho, Ho, H, H, Cop, 0, Cop, 0, Cip, Cip, out_f32=1)
+        d = conv_desc(L.PG_CONVT, 2, 1, B, Ho, Ho, H, H, Cop, 0, Cop, 0, Cip, Cip, out_dt=L.DT_F32)
     else:
-        d = conv_desc(L.PG_CONV, 1, 2, B, Ho, Ho, H, H, Cop, 0, Cop, 0, Cip, Cip, out_f32=1)
+        d = conv_desc(L.PG_CONV, 1, 2, B, Ho, Ho, H, H, Cop, 0, Cop, 0, Cip, Cip, out_dt=L.DT_F32)
     out = run_conv(d, dyd, None, wd, None, True, impl, H, H, Cip)
     assert relerr(from_nhwc(out, Ci), ref) < TOL
 
@@ -126,7 +134,7 @@ def test_conv_transpose_data_gradient(impl):
     ref, _ = orc.convT_bwd(x, w, dy)
     Cip, Cop = rup16(Ci), rup16(Co)
     wd = pack_weight(w, Ci, Cip, Co, Cop, 0, 0, Co * 16, 16)
-    d = conv_desc(L.PG_CONV, 2, 1, B, 2 * H, 2 * H, H, H, Cop, 0, Cop, 0, Cip, Cip, out_f32=1)
+    d = conv_desc(L.PG_CONV, 2, 1, B, 2 * H, 2 * H, H, H, Cop, 0, Cop, 0, Cip, Cip, out_dt=L.DT_F32)
     out = run_conv(d, to_nhwc(dy), None, wd, None, True, impl, H, H, Cip)
     assert relerr(from_nhwc(out, Ci), ref) < TOL
 
@@ -134,19 +142,20 @@ def test_conv_transpose_data_gradient(impl):
 WGRAD_CASES = [(2, 3, 32, 64, 2), (2, 32, 64, 32, 2), (2, 256, 512, 16, 1), (2, 512, 1, 15, 1), (3, 64, 64, 4, 2)]
 
 
+@pytest.mark.parametrize('dt', DTS, ids=DT_IDS)
 @pytest.mark.parametrize('case', WGRAD_CASES, ids=[str(c) for c in WGRAD_CASES])
-def test_conv2d_weight_gradient(case):
+def test_conv2d_weight_gradient(case, dt):
     B, Ci, Co, H, s = case
     r = rng(5)
-    x = bf16_round(r.standard_normal((B, Ci, H, H)))
+    x = bf16_round(r.standard_normal((B, Ci, H, H)), dt)
     w = r.standard_normal((Co, Ci, 4, 4)).astype(np.float32)
     Ho = (H + 2 - 4) // s + 1
     dy = bf16_round(r.standard_normal((B, Co, Ho, Ho)))
     _, ref, refb = orc.conv2d_bwd(x, w, dy, s, has_bias=True, need_dx=False)
     Cip, Cop = rup16(Ci), rup16(Co)
     dw = torch.zeros((Co, Ci, 4, 4), device='cuda')
-    d = conv_desc(L.PG_CONV, s, 1, B, H, H, Ho, Ho, Cip, 0, Cip, 0, Cop, Cop)
-    xd, dyd = to_nhwc(x), to_nhwc(dy)
+    d = conv_desc(L.PG_CONV, s, 1, B, H, H, Ho, Ho, Cip, 0, Cip, 0, Cop, Cop, out_dt=L.DT_BF16, in_dt=dt)
+    xd, dyd = to_nhwc(x, dt=dt), to_nhwc(dy)
     L.call('pg_conv_wgrad', ctypes.byref(d), xd.data_ptr(), dyd.data_ptr(), Cop, dw.data_ptr(), Ci * 16, Co, Ci,
            L.IMPL_AUTO, stream())
     db = torch.zeros(Co, device='cuda')
@@ -159,16 +168,17 @@ def test_conv2d_weight_gradient(case):
 def test_conv_transpose_weight_gradient_two_sources():
     B, C1, C2, Co, H = 2, 32, 48, 16, 8
     r = rng(6)
-    x1 = bf16_round(r.standard_normal((B, C1, H, H)))
-    x2 = bf16_round(r.standard_normal((B, C2, H, H)))
+    x1 = bf16_round(r.standard_normal((B, C1, H, H)), L.DT_F16)
+    x2 = bf16_round(r.standard_normal((B, C2, H, H)), L.DT_F16)
     w = r.standard_normal((C1 + C2, Co, 4, 4)).astype(np.float32)
     dy = bf16_round(r.standard_normal((B, Co, 2 * H, 2 * H)))
     _, ref = orc.convT_bwd(np.concatenate([x1, x2], axis=1), w, dy, need_dx=False)
     dw = torch.zeros((C1 + C2, Co, 4, 4), device='cuda')
     dyd = to_nhwc(dy)
     for (xs, C, off) in ((x1, C1, 0), (x2, C2, C1)):
-        xd = to_nhwc(xs)
-        d = conv_desc(L.PG_CONV, 2, 1, B, 2 * H, 2 * H, H, H, rup16(Co), 0, rup16(Co), 0, rup16(C), rup16(C))
+        xd = to_nhwc(xs, dt=L.DT_F16)
+        d = conv_desc(L.PG_CONV, 2, 1, B, 2 * H, 2 * H, H, H, rup16(Co), 0, rup16(Co), 0, rup16(C), rup16(C),
+                      out_dt=L.DT_F16, in_dt=L.DT_BF16)
         L.call('pg_conv_wgrad', ctypes.byref(d), dyd.data_ptr(), xd.data_ptr(), rup16(C),
                dw.data_ptr() + off * Co * 16 * 4, Co * 16, C, Co, L.IMPL_AUTO, stream())
     torch.cuda.synchronize()
@@ -297,7 +307,7 @@ def test_fused_adam_matches_oracle():
     hyper = torch.tensor([1e-3, 0, 0, 0], device='cuda')
     step = torch.zeros(1, device='cuda', dtype=torch.int32)
     for it in range(3):
-        g = r.standard_normal(n).astype(np.float32) * (10.0 ** r.integers(-6, 2))
+        g = (r.standard_normal(n) * (10.0 ** r.integers(-6, 2))).astype(np.float32)
         opt.step({'w': g})
         gd = torch.from_numpy(g).cuda()
         L.call('pg_adam_step', pbuf.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), n, hyper.data_ptr(),
@@ -312,7 +322,7 @@ def test_layout_roundtrip_and_softmax():
     x = r.standard_normal((2, 5, 9, 7)).astype(np.float32)
     xd = torch.from_numpy(x).cuda()
     buf = torch.zeros((2, 9, 7, 16), device='cuda', dtype=torch.bfloat16)
-    L.call('pg_pack_nchw_f32_to_nhwc_bf16', xd.data_ptr(), buf.data_ptr(), 2, 5, 9, 7, 16, 3, stream())
+    L.call('pg_pack_nchw_f32_to_nhwc_bf16', xd.data_ptr(), buf.data_ptr(), 2, 5, 9, 7, 16, 3, L.DT_BF16, stream())
     back = torch.empty((2, 5, 9, 7), device='cuda')
     L.call('pg_unpack_nhwc_to_nchw_f32', buf.data_ptr(), 0, back.data_ptr(), 2, 5, 9, 7, 16, 3, stream())
     torch.cuda.synchronize()
@@ -344,7 +354,8 @@ def test_inference_tiling_bit_exact():
         L.call('pg_build_mask', md.data_ptr(), mo.data_ptr(), am.data_ptr(), 4, Hh, Ww, size, eff, ncy, ncx, 0.0, stream())
         torch.cuda.synchronize()
         assert np.array_equal(am.cpu().numpy(), orc.build_mask(masks, size, (Hh, Ww), 0.0, overlap))
-        L.call('pg_build_mask', md.data_ptr(), mo.data_ptr(), None, 1, Hh, Ww, size, eff, ncy, ncx, 0.5, stream())
+        m1 = md[:, :1].contiguous()
+        L.call('pg_build_mask', m1.data_ptr(), mo.data_ptr(), None, 1, Hh, Ww, size, eff, ncy, ncx, 0.5, stream())
         torch.cuda.synchronize()
         assert np.array_equal(mo[0].cpu().numpy(), orc.build_mask(masks[:, :1], size, (Hh, Ww), 0.5, overlap)
                               .astype(np.float32))

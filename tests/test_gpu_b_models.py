@@ -10,9 +10,15 @@ from oracle import patchgan_oracle as orc
 from patchgan_b200 import _lib as L
 from tests.gpu_util import from_nhwc, relerr
 
+from patchgan_b200.engine import Config
+
 pytestmark = pytest.mark.gpu
-ACT_TOL = 1e-2
-GRAD_TOL = 3e-2
+ACT_TOL = 1e-2          # north_star: rel err <= 1e-2 on activations (norm-wise, per layer, vs the fp32 oracle)
+GRAD_TOL = 2e-2         # gradients vs the oracle with the CUDA path's storage rounding (see test_gpu_c_step.py)
+
+
+def quant_kwargs():
+    return dict(fwd=orc.round_f16 if Config.fwd_dt == L.DT_F16 else orc.round_bf16, grad=orc.round_bf16)
 
 
 def load(module, oparams):
@@ -72,7 +78,7 @@ def test_discriminator_forward(name):
     xin = eng.new_input(2, 256, 256, 'cuda')
     import ctypes
     xt = torch.from_numpy(x).cuda()
-    L.call('pg_pack_nchw_f32_to_nhwc_bf16', xt.data_ptr(), xin.ptr, 2, dk['input_nc'], 256, 256, xin.ld, 0,
+    L.call('pg_pack_nchw_f32_to_nhwc_bf16', xt.data_ptr(), xin.ptr, 2, dk['input_nc'], 256, 256, xin.ld, 0, xin.dt,
            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     p, ctx = eng.forward(xin, save=True)
     with torch.no_grad():
@@ -93,8 +99,12 @@ def test_unet_autograd_gradients(name):
     G = load(P.UNet(**gk), og.params).train()
     x, _ = orc.synthetic_batch(2, gk['output_nc'], 256, seed=5)
     m = np.random.default_rng(8).standard_normal((2, gk['output_nc'], 256, 256)).astype(np.float32)
-    og.forward(x, keep=True)
-    ref = og.backward(m)
+    orc.set_quant(**quant_kwargs())
+    try:
+        og.forward(x, keep=True)
+        ref = og.backward(m)
+    finally:
+        orc.set_quant()
     out = G(torch.from_numpy(x).cuda())
     (out * torch.from_numpy(m).cuda()).sum().backward()
     torch.cuda.synchronize()
@@ -111,9 +121,13 @@ def test_discriminator_autograd_gradients(name):
     od = orc.Discriminator(**dk, seed=4)
     D = load(P.Discriminator(**dk), od.params)
     x = np.random.default_rng(6).random((2, dk['input_nc'], 256, 256), dtype=np.float32)
-    out_ref = od.forward(x, keep=True)
-    m = np.random.default_rng(9).standard_normal(out_ref.shape).astype(np.float32)
-    dx_ref, ref = od.backward(m, need_dx=True)
+    orc.set_quant(**quant_kwargs())
+    try:
+        out_ref = od.forward(x, keep=True)
+        m = np.random.default_rng(9).standard_normal(out_ref.shape).astype(np.float32)
+        dx_ref, ref = od.backward(m, need_dx=True)
+    finally:
+        orc.set_quant()
     xt = torch.from_numpy(x).cuda().requires_grad_(True)
     out = D(xt)
     (out * torch.from_numpy(m).cuda()).sum().backward()

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import patchgan_oracle as orc
-from tests.golden.make_golden import CASES, summarize  # noqa: F401  (imports torch lazily ok)
+from tests.golden.cases import CASES, summarize
 
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
