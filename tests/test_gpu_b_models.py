@@ -14,7 +14,8 @@ from patchgan_b200.engine import Config
 
 pytestmark = pytest.mark.gpu
 ACT_TOL = 1e-2          # north_star: rel err <= 1e-2 on activations (norm-wise, per layer, vs the fp32 oracle)
-GRAD_TOL = 2e-2         # gradients vs the oracle with the CUDA path's storage rounding (see test_gpu_c_step.py)
+GRAD_TOL = 2e-2         # gradients vs the oracle with the CUDA path's storage rounding, smooth activations
+GRAD_TOL_GATED = 8e-2   # same, LeakyReLU / ReLU generators (gate flips; reasoning in tests/test_gpu_c_step.py)
 
 
 def quant_kwargs():
@@ -92,7 +93,7 @@ def test_discriminator_forward(name):
     assert max(errs.values()) < ACT_TOL, errs
 
 
-@pytest.mark.parametrize('name', ['nf8-leaky-sigmoid', 'nf16-relu-softmax'])
+@pytest.mark.parametrize('name', ['nf8-leaky-sigmoid', 'nf16-relu-softmax', 'nf32-tanh-tanh'])
 def test_unet_autograd_gradients(name):
     gk = G_CASES[name]
     og = orc.UNet(**gk, seed=3)
@@ -110,9 +111,7 @@ def test_unet_autograd_gradients(name):
     torch.cuda.synchronize()
     errs = {k: relerr(p.grad.cpu().numpy(), ref[k]) for k, p in G.named_parameters()}
     print(name, {k.split('.')[-2]: f'{v:.2e}' for k, v in errs.items()})
-    # ReLU is discontinuous (see tests/test_oracle_golden.py): a handful of flipped gates cost ~1e-2 norm-wise
-    tol = 6e-2 if gk['activation'] == 'relu' else GRAD_TOL
-    assert max(errs.values()) < tol, errs
+    assert max(errs.values()) < (GRAD_TOL if gk['activation'] == 'tanh' else GRAD_TOL_GATED), errs
 
 
 @pytest.mark.parametrize('name', ['L3', 'L4-norm'])
