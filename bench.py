@@ -1,0 +1,309 @@
+#!/usr/bin/env python
+"""Benchmark of the patchGAN hot path on B200 (contract: see DESIGN.md "Measurement").
+
+    python bench.py --gpus 1 --steps 20 --warmup 5                 # our CUDA path, one JSON line
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1 # CPU arm (oracle port), one JSON line
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W                       # data-parallel, weak scaling
+
+A "step" is one full G+D training step (Trainer.batch semantics, trainer.py:50-115) on a synthetic batch of the
+BASELINE cfg 3 shape: UNet(3->1, nf=32, leakyrelu, sigmoid) + 3-layer PatchGAN(ndf=64), 256x256, batch 16 per GPU.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# algorithmic minimum GFLOP per image of one G+D step (BASELINE.md / SURVEY.md section 8d)
+CONFIGS = {
+    'cfg3': dict(workload='cfg3: UNet(3->1,nf=32,leakyrelu,sigmoid)+PatchGAN(ndf=64,L=3) full G+D train step, '
+                          '256x256, batch 16/GPU',
+                 G=dict(input_nc=3, output_nc=1, nf=32, activation='leakyrelu', final_act='sigmoid', use_dropout=False),
+                 D=dict(input_nc=4, ndf=64, n_layers=3), loss_type='tversky', B=16, S=256, gflop_per_img=53.03),
+    'cfg4': dict(workload='cfg4: train_coco-shaped UNet(3->7,nf=32,relu,dropout)+PatchGAN(ndf=16,L=5), weighted_bce, '
+                          '256x256, batch 16/GPU',
+                 G=dict(input_nc=3, output_nc=7, nf=32, activation='relu', final_act='sigmoid', use_dropout=True),
+                 D=dict(input_nc=10, ndf=16, n_layers=5), loss_type='weighted_bce', B=16, S=256, gflop_per_img=11.86),
+    'cfg5': dict(workload='cfg5: UNet(3->1,nf=64)+PatchGAN(ndf=64,L=4), 1024x1024, batch 4/GPU',
+                 G=dict(input_nc=3, output_nc=1, nf=64, activation='leakyrelu', final_act='sigmoid', use_dropout=False),
+                 D=dict(input_nc=4, ndf=64, n_layers=4), loss_type='tversky', B=4, S=1024, gflop_per_img=1175.2),
+}
+CLOCK_QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+               'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+               'clocks_event_reasons.sw_power_cap')
+
+
+def peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(src='measured', hbm=p['hbm_gbs'], tf_burst=p['bf16_tflops'], tf_sustained=p['bf16_tflops_sustained'])
+    return dict(src='fallback', hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference step, all host threads, bounded sample
+# ----------------------------------------------------------------------------------------------------------------
+CPU_SAMPLE = ("oracle/torch_port.py: the reference step (trainer.py:50-115, unet.py, disc.py, optim.Adam) restated on "
+              "torch CPU operators -- the reference's own arithmetic library -- all host threads, fp32")
+
+
+def cpu_step_rate(cfg, steps, warmup, batch=4):
+    import numpy as np
+    import torch
+    from oracle import patchgan_oracle as orc
+    from oracle import torch_port as tp
+    torch.set_num_threads(os.cpu_count())
+    gk = cfg['G']
+    og = orc.UNet(gk['input_nc'], gk['output_nc'], gk['nf'], use_dropout=False, activation=gk['activation'],
+                  final_act=gk['final_act'], seed=0)
+    od = orc.Discriminator(cfg['D']['input_nc'], cfg['D']['ndf'], cfg['D']['n_layers'], seed=1)
+    st = tp.Step(og.params, od.params, gk, cfg['D'], cfg['loss_type'])
+    x, y = orc.synthetic_batch(batch, gk['output_nc'], cfg['S'], seed=1234)
+    x, y = torch.from_numpy(x), torch.from_numpy(y)
+    for _ in range(warmup):
+        st.batch(x, y, train=True)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        st.batch(x, y, train=True)
+        ts.append(time.perf_counter() - t0)
+    sec = float(np.median(ts))
+    return batch / sec, sec
+
+
+def run_reference(args, cfg):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
+    batch = 4 if cfg['S'] <= 256 else 1
+    rate, sec = cpu_step_rate(cfg, steps, warmup, batch)
+    cores = os.cpu_count()
+    sample = f'{CPU_SAMPLE}; {warmup} warm-up + {steps} timed step(s) of batch {batch} at {cfg["S"]}x{cfg["S"]}, median'
+    line = dict(metric='train_img_per_s', value=round(rate, 3), unit='img/s', n_gpus=args.gpus, steps=steps, warmup=warmup,
+                ms_per_step=round(sec * 1e3, 2), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
+                data='synthetic', impl='reference', config=dict(workload=cfg['workload'], cpu_batch=batch),
+                cpu_baseline=dict(value=round(rate, 3), unit='img/s', cores=cores, kind='port', sample=sample),
+                e2e=dict(value=round(rate, 3), unit='img/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------------
+class CallProfiler:
+    """Times every C-ABI call with CUDA events on the launching stream (used in a separate pass after the timed
+    region so the headline number is not perturbed)."""
+
+    def __init__(self, torch, lib):
+        self.torch, self.lib, self.rec, self._flops = torch, lib, [], 0.0
+
+    def note(self, flops):
+        self._flops = flops
+
+    def begin(self, name):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        fl, self._flops = self._flops, 0.0
+        return (name, fl, e)
+
+    def end(self, tok):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        name = tok[0]
+        if name in ('pg_conv_fwd', 'pg_conv_wgrad'):
+            name += ':tcgen05' if self.lib.pg_last_conv_impl() == 2 else ':simt'
+        self.rec.append((name, tok[1], tok[2], e))
+
+    def summary(self):
+        self.torch.cuda.synchronize()
+        agg = {}
+        for name, fl, e0, e1 in self.rec:
+            a = agg.setdefault(name, [0, 0.0, 0.0])
+            a[0] += 1
+            a[1] += e0.elapsed_time(e1)
+            a[2] += fl
+        return agg
+
+
+def sample_clocks(dev_index):
+    try:
+        return subprocess.Popen(['nvidia-smi', f'--id={dev_index}', f'--query-gpu={CLOCK_QUERY}', '--format=csv,noheader,nounits',
+                                 '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    except Exception:
+        return None
+
+
+def finish_clocks(proc):
+    if proc is None:
+        return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+    proc.terminate()
+    try:
+        out, _ = proc.communicate(timeout=5)
+    except Exception:
+        proc.kill()
+        out = ''
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for ln in out.strip().splitlines():
+        f = [t.strip() for t in ln.split(',')]
+        if len(f) < 9:
+            continue
+        try:
+            sm.append(float(f[1]))
+            mx.append(float(f[2]))
+        except ValueError:
+            continue
+        for n, v in zip(names, f[5:9]):
+            if v.lower().startswith('active'):
+                reasons.add(n)
+    sm.sort()
+    return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
+                samples=len(sm))
+
+
+def run_ours(args, cfg):
+    import torch
+    import patchgan_b200 as P
+    from patchgan_b200 import _lib as L
+    from patchgan_b200 import dp
+    from patchgan_b200.engine import Config
+
+    rank, world, local = dp.init_from_env('nccl')
+    if world != args.gpus and world > 1:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    lib = L.lib()
+    B, S = cfg['B'], cfg['S']
+
+    torch.manual_seed(0)
+    G = P.UNet(**cfg['G']).to(dev).train()
+    D = P.Discriminator(**cfg['D']).to(dev).train()
+    dp.broadcast_parameters(G)
+    dp.broadcast_parameters(D)
+    tr = P.Trainer(G, D, tempfile.mkdtemp(prefix='pgbench'), device=str(dev))
+    tr.loss_type = cfg['loss_type']
+    tr.make_optimizers(1e-3, 1e-3)
+
+    gen = torch.Generator().manual_seed(dp.shard_seed(1234))
+    cout = cfg['G']['output_nc']
+    x_host = torch.rand((B, 3, S, S), generator=gen).pin_memory()
+    if cout == 1:
+        y_host = (torch.rand((B, 1, S, S), generator=gen) > 0.5).float().pin_memory()
+    else:
+        lab = torch.randint(0, cout + 1, (B, S, S), generator=gen)
+        y_host = torch.stack([(lab == i + 1) for i in range(cout)], 1).float().pin_memory()
+    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    tr.gen_optimizer.sync_lr()
+    tr.disc_optimizer.sync_lr()
+    for _ in range(max(args.warmup, 3)):
+        tr.step_device(x_dev, y_dev, True)
+    barrier()
+
+    clocks = sample_clocks(local) if rank == 0 else None
+    # ---- device-timed region: inputs resident in HBM, CUDA events on the launching stream, L2 flushed between steps
+    evs = []
+    n0 = lib.pg_launch_count()
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        tr.step_device(x_dev, y_dev, True)
+        e1.record()
+        evs.append((e0, e1))
+    barrier()
+    launches = (lib.pg_launch_count() - n0) // args.steps
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    dev_ms = dp.max_over_ranks(dev_ms, dev)
+
+    # ---- end to end through the public API: pinned host inputs -> Trainer.batch -> loss dict on the host
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        losses = tr.batch(x_host, y_host, train=True)
+    torch.cuda.synchronize()
+    e2e_s = dp.max_over_ranks(time.perf_counter() - t0, dev)
+    clock_info = finish_clocks(clocks) if rank == 0 else None
+
+    # ---- per-kernel pass (separate from the timed region): CUDA events around every C-ABI call
+    prof = CallProfiler(torch, lib)
+    L.PROFILER = prof
+    nprof = 2
+    for _ in range(nprof):
+        tr.step_device(x_dev, y_dev, True)
+    L.PROFILER = None
+    agg = prof.summary()
+    if rank != 0:
+        return
+    pk = peaks()
+    total_prof_ms = sum(a[1] for a in agg.values())
+    top = sorted(agg.items(), key=lambda kv: -kv[1][1])
+    shares = {k: round(v[1] / total_prof_ms, 4) for k, v in top[:8]}
+    conv = [(k, v) for k, v in top if v[2] > 0]
+    kname, (cnt, ms, fl) = conv[0]
+    achieved_tf = fl / (ms * 1e-3) / 1e12
+    roof = dict(bound='tensor', kernel=kname, achieved=round(achieved_tf, 2), peak=pk['tf_sustained'],
+                peak_src=pk['src'] + ' (sustained cuBLAS bf16)', unit='TFLOP/s', frac=round(achieved_tf / pk['tf_sustained'], 4),
+                traffic=None, launches_per_step=cnt // nprof, ms_per_step=round(ms / nprof, 4),
+                flops_per_step=fl / nprof)
+    img_s = world * B * args.steps / (dev_ms * 1e-3)
+    step_tf = img_s * cfg['gflop_per_img'] / 1e3
+    line = dict(metric='train_img_per_s', value=round(img_s, 2), unit='img/s', n_gpus=world, steps=args.steps,
+                warmup=max(args.warmup, 3), ms_per_step=round(dev_ms / args.steps, 4), higher_is_better=True,
+                scaling='weak', vs_baseline=None,
+                dtype=('f16' if Config.fwd_dt == L.DT_F16 else 'bf16') + ' forward operands, bf16 gradients, f32 accumulate',
+                data='synthetic',
+                config=dict(workload=cfg['workload'], global_batch=world * B, per_gpu_batch=B, image=S,
+                            parallelism=f'dp{world}', l2='flushed (256 MB write) between timed steps',
+                            conv_impl={0: 'auto', 1: 'simt', 2: 'tcgen05'}[Config.impl]),
+                clocks=clock_info,
+                e2e=dict(value=round(world * B * args.steps / e2e_s, 2), unit='img/s',
+                         h2d_bytes_per_step=int(x_host.numel() * 4 + y_host.numel() * 4), d2h_bytes_per_step=32,
+                         ms_per_step=round(e2e_s / args.steps * 1e3, 4)),
+                gpu_launches=int(launches), roofline=roof,
+                step_tensor=dict(algorithmic_gflop_per_img=cfg['gflop_per_img'], achieved_tflops=round(step_tf, 2),
+                                 frac_of_peak=round(step_tf / pk['tf_sustained'], 4)),
+                kernel_time_shares=shares, last_losses={k: round(v, 5) for k, v in losses.items()})
+    if world == 1 and not args.no_cpu_baseline:
+        cb = 4 if S <= 256 else 1
+        rate, sec = cpu_step_rate(cfg, 5, 2, cb)
+        line['cpu_baseline'] = dict(value=round(rate, 3), unit='img/s', cores=os.cpu_count(), kind='port',
+                                    sample=f'{CPU_SAMPLE}; 2 warm-up + 5 timed steps of batch {cb}, median')
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--config', default='cfg3', choices=list(CONFIGS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == 'reference':
+        run_reference(args, cfg)
+    else:
+        run_ours(args, cfg)
+
+
+if __name__ == '__main__':
+    main()

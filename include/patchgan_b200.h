@@ -89,6 +89,10 @@ typedef struct PgConvDesc {
 
 const char* pg_last_error(void);
 int pg_version(void);
+/* number of kernels this library has launched in this process (bench.py reports the per-step delta) */
+int64_t pg_launch_count(void);
+/* PgImpl the last pg_conv_fwd / pg_conv_wgrad of this thread dispatched to (profiling aid) */
+int pg_last_conv_impl(void);
 /* 1 if the library was built with the tcgen05 path and the current device is sm_100. */
 int pg_tcgen05_available(void);
 

@@ -28,6 +28,8 @@ DP = C.POINTER(ConvDesc)
 _SIGS = {
     'pg_version': ([], C.c_int),
     'pg_tcgen05_available': ([], C.c_int),
+    'pg_launch_count': ([], C.c_int64),
+    'pg_last_conv_impl': ([], C.c_int),
     'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_wgrad': ([DP, vp, vp, i32, vp, i32, i32, i32, C.c_int, vp], C.c_int),
     'pg_colsum': ([vp, i64, i32, i32, vp, vp], C.c_int),
@@ -92,5 +94,13 @@ def check(status, what=''):
         raise RuntimeError(f'patchgan_b200 kernel call failed ({what}, status {status}): {msg}')
 
 
+PROFILER = None      # set to an object with begin(name)/end(token) to time every C-ABI call (bench.py)
+
+
 def call(name, *args):
-    check(getattr(lib(), name)(*args), name)
+    if PROFILER is None:
+        check(getattr(lib(), name)(*args), name)
+    else:
+        tok = PROFILER.begin(name)
+        check(getattr(lib(), name)(*args), name)
+        PROFILER.end(tok)

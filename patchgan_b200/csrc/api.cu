@@ -14,7 +14,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+static thread_local int g_last_impl = 0;
+
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
@@ -60,6 +64,8 @@ using namespace pg;
 
 extern "C" const char* pg_last_error(void) { return g_err; }
 extern "C" int pg_version(void) { return 100; }
+extern "C" int64_t pg_launch_count(void) { return (int64_t)g_launches; }
+extern "C" int pg_last_conv_impl(void) { return g_last_impl; }
 extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
 
 extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
@@ -68,8 +74,10 @@ extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* sr
   PG_REQUIRE(src1 && w_packed && out && (d->C2 == 0 || src2), "pg_conv_fwd: NULL pointer");
   PG_REQUIRE(!d->has_bias || bias, "pg_conv_fwd: has_bias but bias is NULL");
   cudaStream_t s = (cudaStream_t)stream;
+  g_last_impl = PG_IMPL_SIMT;
   if (impl == PG_IMPL_SIMT) return conv_fwd_simt(d, src1, src2, w_packed, bias, out, s);
   const bool ok = conv_fwd_tc_supported(d, src1, src2, w_packed, out);
+  if (ok) g_last_impl = PG_IMPL_TCGEN05;
   if (impl == PG_IMPL_TCGEN05) {
     if (!ok) {
       set_error("pg_conv_fwd: tcgen05 path does not support this shape / alignment");
@@ -88,8 +96,10 @@ extern "C" int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, 
   PG_REQUIRE(a && g && dw && ldg >= d->N && ldg % 8 == 0, "pg_conv_wgrad: bad pointers / ldg");
   PG_REQUIRE(n_real <= d->N && c_real <= d->C1, "pg_conv_wgrad: n_real / c_real exceed padded extents");
   cudaStream_t s = (cudaStream_t)stream;
+  g_last_impl = PG_IMPL_SIMT;
   if (impl == PG_IMPL_SIMT) return conv_wgrad_simt(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
   const bool ok = conv_wgrad_tc_supported(d, a, g, ldg);
+  if (ok) g_last_impl = PG_IMPL_TCGEN05;
   if (impl == PG_IMPL_TCGEN05) {
     if (!ok) {
       set_error("pg_conv_wgrad: tcgen05 path does not support this shape / alignment");

@@ -85,12 +85,24 @@ class Config:
     fwd_dt = {'fp16': L.DT_F16, 'bf16': L.DT_BF16}[os.environ.get('PATCHGAN_B200_FWD_DTYPE', 'fp16')]
 
 
+def conv_flops(desc):
+    """2*MACs of the contraction as launched (padded channel counts)."""
+    c = desc.C1 + desc.C2
+    if desc.mode == L.PG_CONVT:
+        return 2.0 * desc.B * desc.Hin * desc.Win * c * desc.N * 16
+    return 2.0 * desc.B * desc.Hout * desc.Wout * c * desc.N * 16
+
+
 def run_conv(desc, src1, src2, w, bias, out):
+    if L.PROFILER is not None:
+        L.PROFILER.note(conv_flops(desc))
     L.call('pg_conv_fwd', ctypes.byref(desc), src1.ptr, src2.ptr if src2 is not None else None, w.data_ptr(),
            bias.data_ptr() if bias is not None else None, out.ptr, Config.impl, _stream())
 
 
 def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real):
+    if L.PROFILER is not None:
+        L.PROFILER.note(conv_flops(desc))
     L.call('pg_conv_wgrad', ctypes.byref(desc), a.ptr, g.ptr, g.ld, dw_ptr, ld_n, n_real, c_real, Config.impl, _stream())
 
 

@@ -127,3 +127,26 @@ def test_infer_tiling_matches_reference():
     masks = rng.random((crops.shape[0], 4, 128, 128), dtype=np.float32)
     assert np.array_equal(orc.build_mask(masks, 128, (300, 300), 0.0, 0.9), gold['m_arg'])
     assert np.array_equal(orc.build_mask(masks[:, :1], 128, (300, 300), 0.5, 0.9).astype(np.float32), gold['m_thr'])
+
+
+@pytest.mark.parametrize('name', ['tversky', 'wbce', 'mae'])
+def test_torch_port_matches_reference(name):
+    """oracle/torch_port.py (the CPU-baseline port on torch CPU ops) against the live reference's goldens."""
+    import torch
+    from oracle import torch_port as tp
+    gk, dk, loss_type, B, steps = CASES[name]
+    gold = np.load(os.path.join(GOLD, f'step_{name}.npz'))
+    og = orc.UNet(**gk, seed=11)
+    od = orc.Discriminator(**dk, seed=12)
+    st = tp.Step(og.params, od.params, gk, dk, loss_type)
+    for step in range(steps):
+        x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=1234 + step)
+        losses = st.batch(torch.from_numpy(x), torch.from_numpy(y), train=True)
+        for k, v in losses.items():
+            close(v, gold[f's{step}/loss/{k}'], 1e-5 if step == 0 else 2e-3, 1e-6, f'{name} s{step} loss {k}')
+        if step == 0:
+            for k, p in st.g.items():
+                relnorm(summarize(p.grad.numpy()), gold[f's0/ggrad/{k}'], 1e-2 if name == 'wbce' else 1e-4, k)
+                weights_close(summarize(p.detach().numpy()), gold[f's0/gw/{k}'], 1e-3, 1, 0.05 if name == 'wbce' else 0.0, k)
+            for k, p in st.d.items():
+                relnorm(summarize(p.grad.numpy()), gold[f's0/dgrad/{k}'], 1e-4, k)
