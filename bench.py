@@ -104,16 +104,18 @@ class CallProfiler:
     region so the headline number is not perturbed)."""
 
     def __init__(self, torch, lib):
-        self.torch, self.lib, self.rec, self._flops = torch, lib, [], 0.0
+        self.torch, self.lib, self.rec, self._flops, self._tag = torch, lib, [], 0.0, ''
 
-    def note(self, flops):
+    def note(self, flops, tag=''):
         self._flops = flops
+        self._tag = tag
 
     def begin(self, name):
         e = self.torch.cuda.Event(enable_timing=True)
         e.record()
         fl, self._flops = self._flops, 0.0
-        return (name, fl, e)
+        tag, self._tag = self._tag, ''
+        return (name, fl, e, tag)
 
     def end(self, tok):
         e = self.torch.cuda.Event(enable_timing=True)
@@ -121,16 +123,19 @@ class CallProfiler:
         name = tok[0]
         if name in ('pg_conv_fwd', 'pg_conv_wgrad'):
             name += ':tcgen05' if self.lib.pg_last_conv_impl() == 2 else ':simt'
-        self.rec.append((name, tok[1], tok[2], e))
+        self.rec.append((name, tok[1], tok[2], e, tok[3]))
 
     def summary(self):
         self.torch.cuda.synchronize()
         agg = {}
-        for name, fl, e0, e1 in self.rec:
+        self.detail = []
+        for name, fl, e0, e1, tag in self.rec:
+            ms = e0.elapsed_time(e1)
             a = agg.setdefault(name, [0, 0.0, 0.0])
             a[0] += 1
-            a[1] += e0.elapsed_time(e1)
+            a[1] += ms
             a[2] += fl
+            self.detail.append(dict(call=name, shape=tag, ms=round(ms, 4), tflops=round(fl / ms / 1e9, 1) if fl else None))
         return agg
 
 
@@ -252,6 +257,9 @@ def run_ours(args, cfg):
     agg = prof.summary()
     if rank != 0:
         return
+    if args.detail:
+        with open(args.detail, 'w') as f:
+            json.dump(prof.detail[len(prof.detail) // nprof:], f, indent=0)
     pk = peaks()
     total_prof_ms = sum(a[1] for a in agg.values())
     top = sorted(agg.items(), key=lambda kv: -kv[1][1])
@@ -297,6 +305,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg3', choices=list(CONFIGS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--detail', default=None, help='write the per-launch timing of one profiled step to this JSON file')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == 'reference':

@@ -93,16 +93,21 @@ def conv_flops(desc):
     return 2.0 * desc.B * desc.Hout * desc.Wout * c * desc.N * 16
 
 
+def desc_tag(d):
+    return (f"{'convT' if d.mode else 'conv'} s{d.stride}p{d.pad} B{d.B} {d.Hin}x{d.Win}->{d.Hout}x{d.Wout} "
+            f"C{d.C1}+{d.C2} N{d.N}")
+
+
 def run_conv(desc, src1, src2, w, bias, out):
     if L.PROFILER is not None:
-        L.PROFILER.note(conv_flops(desc))
+        L.PROFILER.note(conv_flops(desc), desc_tag(desc))
     L.call('pg_conv_fwd', ctypes.byref(desc), src1.ptr, src2.ptr if src2 is not None else None, w.data_ptr(),
            bias.data_ptr() if bias is not None else None, out.ptr, Config.impl, _stream())
 
 
 def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real):
     if L.PROFILER is not None:
-        L.PROFILER.note(conv_flops(desc))
+        L.PROFILER.note(conv_flops(desc), desc_tag(desc))
     L.call('pg_conv_wgrad', ctypes.byref(desc), a.ptr, g.ptr, g.ld, dw_ptr, ld_n, n_real, c_real, Config.impl, _stream())
 
 
