@@ -450,11 +450,257 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   return check_launch("conv_tc_kernel");
 }
 
-// tensor-core wgrad: not in this revision (the SIMT kernel serves it)
-bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int) { return false; }
-int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t) {
-  set_error("conv_wgrad_tc: not implemented");
-  return PG_ERR_UNSUPPORTED;
+// --------------------------------------------------------------------------------------------
+// weight gradient on tcgen05:  dW[n][c][tap] += sum_pix G[pix][n] * A[pix(tap)][c]
+//
+// Per tap this is a GEMM D[n][c] with the reduction over PIXELS.  Both operands are stored pixel-major with
+// channels contiguous (NHWC), i.e. MN-major for the tensor core: a TMA box {channels, TW, TH, TB} lands in smem
+// as KP=64 rows (pixels) of one swizzle-width of channels, which is exactly the canonical MN-major layout
+// ((atom, n), (8, k)) with SBO = 8 rows and LBO = one box.  The G tile (dY, or the layer input for
+// ConvTranspose2d) is loaded once per pixel tile and reused by the T taps whose accumulators [128 x ct] share
+// the 512 TMEM columns; the A tile of every tap is the same strided/zero-filled box the forward kernel loads.
+// Split-K over pixel tiles; the epilogue adds fp32 partials into dW with red.global.add.v4.f32 (4 taps of one
+// (n, c) are contiguous in the reference weight layout).
+// --------------------------------------------------------------------------------------------
+struct WgParams {
+  int stride, pad;
+  int B, Hout, Wout;
+  int TW, TH, TB;
+  int nx, ny, total_tiles, tiles_per_split;
+  int g_box, n_atoms, a_box, c_atoms, ct, T, ctiles;
+  uint32_t idesc;
+  uint32_t g_rowbytes, a_rowbytes, g_layout, a_layout, g_boxbytes, a_boxbytes;
+  uint32_t g_stage_bytes, a_stage_bytes;
+  int g_stages, a_stages;
+  uint32_t tmem_cols;
+  float* dw;
+  int ld_n, n_real, c_real;
+};
+
+constexpr int WG_KP = 64;
+constexpr int WG_MAX_G = 4, WG_MAX_A = 12;
+
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                      uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;   // stride between MN atoms (one TMA box)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // stride between groups of 8 k-rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapA, const WgParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t gfull[WG_MAX_G], gempty[WG_MAX_G], afull[WG_MAX_A], aempty[WG_MAX_A];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_sh;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t g_base = smem_base;
+  const uint32_t a_base = smem_base + p.g_stages * p.g_stage_bytes;
+
+  const int n0 = blockIdx.x * 128;
+  const int ctile = blockIdx.y % p.ctiles;
+  const int tgrp = blockIdx.y / p.ctiles;
+  const int c0 = ctile * p.ct;
+  const int t0 = tgrp * p.T;
+  const int tile_beg = blockIdx.z * p.tiles_per_split;
+  int tile_end = tile_beg + p.tiles_per_split;
+  if (tile_end > p.total_tiles) tile_end = p.total_tiles;
+  const int ntiles = tile_end > tile_beg ? tile_end - tile_beg : 0;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapG);
+    prefetch_tmap(&mapA);
+    for (int s = 0; s < p.g_stages; ++s) { mbar_init(smem_u32(&gfull[s]), 1); mbar_init(smem_u32(&gempty[s]), 1); }
+    for (int s = 0; s < p.a_stages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), 1); }
+    mbar_init(smem_u32(&acc_bar), 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_sh), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_acc = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0 && ntiles > 0) {
+      int gs = 0, as = 0;
+      uint32_t gph = 0, aph = 0;
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        const int x0 = (tile % p.nx) * p.TW;
+        const int y0 = ((tile / p.nx) % p.ny) * p.TH;
+        const int b0 = (tile / (p.nx * p.ny)) * p.TB;
+        mbar_wait(smem_u32(&gempty[gs]), gph ^ 1);
+        const uint32_t gb = smem_u32(&gfull[gs]);
+        mbar_expect_tx(gb, p.n_atoms * p.g_boxbytes);
+        for (int a = 0; a < p.n_atoms; ++a)
+          tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, &mapG, gb, n0 + a * p.g_box, x0, y0, b0);
+        if (++gs == p.g_stages) { gs = 0; gph ^= 1; }
+        for (int tl = 0; tl < p.T; ++tl) {
+          const int t = t0 + tl, kh = t >> 2, kw = t & 3;
+          mbar_wait(smem_u32(&aempty[as]), aph ^ 1);
+          const uint32_t ab = smem_u32(&afull[as]);
+          mbar_expect_tx(ab, p.c_atoms * p.a_boxbytes);
+          for (int a = 0; a < p.c_atoms; ++a)
+            tma_load_4d(a_base + as * p.a_stage_bytes + a * p.a_boxbytes, &mapA, ab, c0 + a * p.a_box,
+                        x0 * p.stride - p.pad + kw, y0 * p.stride - p.pad + kh, b0);
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && ntiles > 0) {
+      int gs = 0, as = 0;
+      uint32_t gph = 0, aph = 0;
+      for (int it = 0; it < ntiles; ++it) {
+        mbar_wait(smem_u32(&gfull[gs]), gph);
+        tc_fence_after();
+        const uint64_t gdesc = make_smem_desc_mn(g_base + gs * p.g_stage_bytes, p.g_boxbytes, 8 * p.g_rowbytes, p.g_layout);
+        for (int tl = 0; tl < p.T; ++tl) {
+          mbar_wait(smem_u32(&afull[as]), aph);
+          tc_fence_after();
+          const uint64_t adesc =
+              make_smem_desc_mn(a_base + as * p.a_stage_bytes, p.a_boxbytes, 8 * p.a_rowbytes, p.a_layout);
+#pragma unroll
+          for (int k = 0; k < WG_KP / 16; ++k) {
+            // 16 pixels (rows) further along K: 16 * rowbytes
+            umma_bf16(tmem_acc + (uint32_t)(tl * p.ct), gdesc + (uint64_t)((k * 16 * p.g_rowbytes) >> 4),
+                      adesc + (uint64_t)((k * 16 * p.a_rowbytes) >> 4), p.idesc, (it | k) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&aempty[as]));
+          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+        }
+        umma_commit(smem_u32(&gempty[gs]));
+        if (++gs == p.g_stages) { gs = 0; gph ^= 1; }
+      }
+      umma_commit(smem_u32(&acc_bar));
+    }
+  } else if (ntiles > 0) {
+    const int q = warp & 3;
+    const int n = n0 + q * 32 + lane;
+    mbar_wait(smem_u32(&acc_bar), 0);
+    tc_fence_after();
+    for (int c16 = 0; c16 < p.ct; c16 += 16) {
+      for (int tq = 0; tq < p.T; tq += 4) {
+        uint32_t v[4][16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)((tq + j) * p.ct + c16), v[j]);
+        tmem_ld_wait();
+        if (n < p.n_real) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + c16 + i;
+            if (c < p.c_real)
+              red_add_v4(p.dw + (long long)n * p.ld_n + (long long)c * 16 + t0 + tq, __uint_as_float(v[0][i]),
+                         __uint_as_float(v[1][i]), __uint_as_float(v[2][i]), __uint_as_float(v[3][i]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_acc, p.tmem_cols);
+  }
+}
+
+static int box_of(int ch) { return ch >= 64 ? 64 : (ch >= 32 ? 32 : 16); }
+static uint32_t layout_of(int rowbytes) { return rowbytes == 128 ? 2u : (rowbytes == 64 ? 4u : 6u); }
+
+static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& smem) {
+  memset(&p, 0, sizeof(p));
+  if (d->mode != PG_CONV || d->C2 != 0) return false;
+  p.stride = d->stride; p.pad = d->pad; p.B = d->B; p.Hout = d->Hout; p.Wout = d->Wout;
+  p.TW = pow2_ceil(d->Wout); if (p.TW > WG_KP) p.TW = WG_KP;
+  p.TH = pow2_ceil(d->Hout); if (p.TH > WG_KP / p.TW) p.TH = WG_KP / p.TW;
+  p.TB = WG_KP / (p.TW * p.TH);
+  p.nx = (d->Wout + p.TW - 1) / p.TW; p.ny = (d->Hout + p.TH - 1) / p.TH;
+  const int nb = (d->B + p.TB - 1) / p.TB;
+  p.total_tiles = p.nx * p.ny * nb;
+  if (p.TW * d->stride > 256 || p.TH * d->stride > 256) return false;
+  const int N = d->N, C = d->C1;
+  p.g_box = box_of(N); p.n_atoms = 128 / p.g_box;
+  p.a_box = box_of(C);
+  if (C >= 128) { p.ct = 128; p.T = 4; }
+  else if (C >= 64) { p.ct = 64; p.T = 8; }
+  else if (C >= 32) { p.ct = 32; p.T = 16; }
+  else { p.ct = 16; p.T = 16; }
+  p.c_atoms = p.ct / p.a_box;
+  p.ctiles = (C + p.ct - 1) / p.ct;
+  p.g_rowbytes = p.g_box * 2; p.a_rowbytes = p.a_box * 2;
+  p.g_layout = layout_of(p.g_rowbytes); p.a_layout = layout_of(p.a_rowbytes);
+  p.g_boxbytes = WG_KP * p.g_rowbytes; p.a_boxbytes = WG_KP * p.a_rowbytes;
+  p.g_stage_bytes = (p.n_atoms * p.g_boxbytes + 1023u) & ~1023u;
+  p.a_stage_bytes = (p.c_atoms * p.a_boxbytes + 1023u) & ~1023u;
+  p.g_stages = 3;
+  int as = (int)(((uint32_t)TC_MAX_DYN_SMEM - 2048u - p.g_stages * p.g_stage_bytes) / p.a_stage_bytes);
+  if (as > WG_MAX_A) as = WG_MAX_A;
+  if (as < 2) return false;
+  p.a_stages = as;
+  const int cols = p.T * p.ct;
+  p.tmem_cols = cols <= 32 ? 32u : (cols <= 64 ? 64u : (cols <= 128 ? 128u : (cols <= 256 ? 256u : 512u)));
+  // A operand = G (grad side, d->out_f32 holds its dtype), B operand = activations (d->in_dtype); both MN-major
+  const uint32_t afmt = d->out_f32 == PG_F16 ? 0u : 1u, bfmt = d->in_dtype == PG_F16 ? 0u : 1u;
+  p.idesc = (1u << 4) | (afmt << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.ct >> 3) << 17) |
+            ((uint32_t)(128 >> 4) << 24);
+  const int gx = (N + 127) / 128, gy = p.ctiles * (16 / p.T);
+  int splits = (2 * num_sms() + gx * gy - 1) / (gx * gy);
+  if (splits > p.total_tiles) splits = p.total_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
+  splits = (p.total_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  grid = dim3((unsigned)gx, (unsigned)gy, (unsigned)splits);
+  smem = (size_t)p.g_stages * p.g_stage_bytes + (size_t)p.a_stages * p.a_stage_bytes + 1024;
+  return true;
+}
+
+bool conv_wgrad_tc_supported(const PgConvDesc* d, const void* a, const void* g, int ldg) {
+  if (!tc_device_ok()) return false;
+  if ((((uintptr_t)a | (uintptr_t)g) & 15) != 0 || (ldg % 8) != 0) return false;
+  if (d->out_f32 != PG_BF16 && d->out_f32 != PG_F16) return false;
+  WgParams p; dim3 grid; size_t smem;
+  return make_wg_plan(d, p, grid, smem);
+}
+
+int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, float* dw, int ld_n, int n_real,
+                  int c_real, cudaStream_t stream) {
+  WgParams p; dim3 grid; size_t smem;
+  if (!make_wg_plan(d, p, grid, smem)) {
+    set_error("conv_wgrad_tc: unsupported shape");
+    return PG_ERR_UNSUPPORTED;
+  }
+  if ((((uintptr_t)dw) & 15) != 0 || (ld_n % 4) != 0) {
+    set_error("conv_wgrad_tc: dw must be 16-byte aligned with ld_n %% 4 == 0");
+    return PG_ERR_UNSUPPORTED;
+  }
+  p.dw = dw; p.ld_n = ld_n; p.n_real = n_real; p.c_real = c_real;
+  CUtensorMap mG, mA;
+  if (int e = encode_act_map(&mG, g, d->N, ldg, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, 1, p.g_rowbytes,
+                             d->out_f32))
+    return e;
+  if (int e = encode_act_map(&mA, a, d->C1, d->ld1, d->B, d->Hin, d->Win, p.a_box, p.TW, p.TH, p.TB, d->stride,
+                             p.a_rowbytes, d->in_dtype))
+    return e;
+  static bool smem_set = false;
+  if (!smem_set) {
+    PG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
+    smem_set = true;
+  }
+  wgrad_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mG, mA, p);
+  return check_launch("wgrad_tc_kernel");
 }
 
 }  // namespace pg

@@ -139,12 +139,14 @@ def test_conv_transpose_data_gradient(impl):
     assert relerr(from_nhwc(out, Ci), ref) < TOL
 
 
-WGRAD_CASES = [(2, 3, 32, 64, 2), (2, 32, 64, 32, 2), (2, 256, 512, 16, 1), (2, 512, 1, 15, 1), (3, 64, 64, 4, 2)]
+WGRAD_CASES = [(2, 3, 32, 64, 2), (2, 32, 64, 32, 2), (2, 256, 512, 16, 1), (2, 512, 1, 15, 1), (3, 64, 64, 4, 2),
+               (2, 128, 256, 32, 2), (1, 64, 128, 31, 1), (2, 48, 96, 20, 2)]
 
 
+@pytest.mark.parametrize('impl', IMPLS, ids=IMPL_IDS)
 @pytest.mark.parametrize('dt', DTS, ids=DT_IDS)
 @pytest.mark.parametrize('case', WGRAD_CASES, ids=[str(c) for c in WGRAD_CASES])
-def test_conv2d_weight_gradient(case, dt):
+def test_conv2d_weight_gradient(case, dt, impl):
     B, Ci, Co, H, s = case
     r = rng(5)
     x = bf16_round(r.standard_normal((B, Ci, H, H)), dt)
@@ -157,7 +159,7 @@ def test_conv2d_weight_gradient(case, dt):
     d = conv_desc(L.PG_CONV, s, 1, B, H, H, Ho, Ho, Cip, 0, Cip, 0, Cop, Cop, out_dt=L.DT_BF16, in_dt=dt)
     xd, dyd = to_nhwc(x, dt=dt), to_nhwc(dy)
     L.call('pg_conv_wgrad', ctypes.byref(d), xd.data_ptr(), dyd.data_ptr(), Cop, dw.data_ptr(), Ci * 16, Co, Ci,
-           L.IMPL_AUTO, stream())
+           impl, stream())
     db = torch.zeros(Co, device='cuda')
     L.call('pg_colsum', dyd.data_ptr(), B * Ho * Ho, Cop, Co, db.data_ptr(), stream())
     torch.cuda.synchronize()
@@ -165,7 +167,8 @@ def test_conv2d_weight_gradient(case, dt):
     assert relerr(db.cpu().numpy(), refb) < 1e-4
 
 
-def test_conv_transpose_weight_gradient_two_sources():
+@pytest.mark.parametrize('impl', IMPLS, ids=IMPL_IDS)
+def test_conv_transpose_weight_gradient_two_sources(impl):
     B, C1, C2, Co, H = 2, 32, 48, 16, 8
     r = rng(6)
     x1 = bf16_round(r.standard_normal((B, C1, H, H)), L.DT_F16)
@@ -180,7 +183,7 @@ def test_conv_transpose_weight_gradient_two_sources():
         d = conv_desc(L.PG_CONV, 2, 1, B, 2 * H, 2 * H, H, H, rup16(Co), 0, rup16(Co), 0, rup16(C), rup16(C),
                       out_dt=L.DT_F16, in_dt=L.DT_BF16)
         L.call('pg_conv_wgrad', ctypes.byref(d), dyd.data_ptr(), xd.data_ptr(), rup16(C),
-               dw.data_ptr() + off * Co * 16 * 4, Co * 16, C, Co, L.IMPL_AUTO, stream())
+               dw.data_ptr() + off * Co * 16 * 4, Co * 16, C, Co, impl, stream())
     torch.cuda.synchronize()
     assert relerr(dw.cpu().numpy(), ref) < 1e-4
 
