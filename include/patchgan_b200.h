@@ -98,8 +98,11 @@ int pg_tcgen05_available(void);
 
 /* ---- convolutions: replaces aten::convolution behind nn.Conv2d / nn.ConvTranspose2d
  *      (unet.py:19, unet.py:53, disc.py:19,27,37,45) and their autograd dgrad ---- */
+/* out2 (nullable): a second, bf16 copy of the output with the same pixel stride.  tcgen05 kind::f16 needs both
+ * MMA operands in ONE 16-bit format, so when forward tensors are f16 the weight-gradient GEMMs (whose other
+ * operand is a bf16 gradient) read this bf16 twin. */
 int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
-                const float* bias, void* out, int impl, void* stream);
+                const float* bias, void* out, void* out2, int impl, void* stream);
 
 /* weight gradient of PG_CONV geometry `d` (autograd wgrad of unet.py:19,53 / disc.py:19-45):
  *   dw[n*ld_n + c*16 + tap] += sum_{b,oy,ox} g[b,oy,ox,n] * a[b, oy*s-p+kh, ox*s-p+kw, c]
@@ -108,7 +111,8 @@ int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const v
  * a = dY (2H x 2W), g = layer input.  `ws` = float workspace (>= pg_conv_wgrad_ws_bytes) or NULL. */
 int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw,
                   int32_t ld_n, int32_t n_real, int32_t c_real, int impl, void* stream);
-/* (d->in_dtype is the type of `a`; d->out_f32 is reused as the PgDType of `g`: PG_BF16 or PG_F16) */
+/* (d->in_dtype is the type of `a`; d->out_f32 is reused as the PgDType of `g`: PG_BF16 or PG_F16; the tcgen05
+ * implementation needs both to be the same type) */
 
 /* bias gradient: db[n] += sum_m g[m*ldg + n], n < n_real (disc.py:19,45 biases) */
 int pg_colsum(const void* g, int64_t M, int32_t ldg, int32_t n_real, float* db, void* stream);
@@ -140,7 +144,8 @@ int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_t HW, int32
  * drop_p == 0: no dropout; else keep = uniform(mix(*seed, salt), element index) >= drop_p, scaled 1/(1-p).
  * seed is a DEVICE counter (so a captured CUDA graph draws a fresh mask every replay), salt is per layer;
  * the mask is regenerated in backward from (seed, salt, index) -- no mask tensor is stored. */
-int pg_norm_act_fwd(const void* x, int32_t x_f32, const float* sums, void* y, int32_t y_f32, int32_t B, int64_t HW,
+/* y2 (nullable): bf16 twin of y, same stride (see pg_conv_fwd). */
+int pg_norm_act_fwd(const void* x, int32_t x_f32, const float* sums, void* y, int32_t y_f32, void* y2, int32_t B, int64_t HW,
                     int32_t C, int32_t ldx, int32_t ldy, int32_t act, float drop_p, const uint64_t* seed, uint64_t salt,
                     void* stream);
 /* backward, pass 1: with dxhat = (dy1 [+ dy2]) * mask * act'(xhat):

@@ -30,7 +30,7 @@ _SIGS = {
     'pg_tcgen05_available': ([], C.c_int),
     'pg_launch_count': ([], C.c_int64),
     'pg_last_conv_impl': ([], C.c_int),
-    'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
+    'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_wgrad': ([DP, vp, vp, i32, vp, i32, i32, i32, C.c_int, vp], C.c_int),
     'pg_colsum': ([vp, i64, i32, i32, vp, vp], C.c_int),
     'pg_pack_nchw_f32_to_nhwc_bf16': ([vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], C.c_int),
@@ -38,7 +38,7 @@ _SIGS = {
     'pg_copy_f32_to_bf16_slice': ([vp, i32, vp, i32, i32, i32, i64, i32, vp], C.c_int),
     'pg_pack_weight': ([vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i32, i32, vp], C.c_int),
     'pg_instnorm_stats': ([vp, i32, i32, i64, i32, i32, vp, vp], C.c_int),
-    'pg_norm_act_fwd': ([vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, i32, f32, vp, u64, vp], C.c_int),
+    'pg_norm_act_fwd': ([vp, i32, vp, vp, i32, vp, i32, i64, i32, i32, i32, i32, f32, vp, u64, vp], C.c_int),
     'pg_norm_act_bwd_reduce': ([vp, i32, vp, vp, i32, vp, i32, vp, i32, i64, i32, i32, i32, f32, vp, u64, vp], C.c_int),
     'pg_norm_act_bwd_apply': ([vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, f32, vp, u64, vp],
                               C.c_int),

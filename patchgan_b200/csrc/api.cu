@@ -27,10 +27,10 @@ int check_launch(const char* what) {
   return PG_OK;
 }
 
-int conv_fwd_simt(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, cudaStream_t);
+int conv_fwd_simt(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, cudaStream_t);
 int conv_wgrad_simt(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
 // conv_tc.cu
-int conv_fwd_tc(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, cudaStream_t);
+int conv_fwd_tc(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, cudaStream_t);
 bool conv_fwd_tc_supported(const PgConvDesc*, const void*, const void*, const void*, const void*);
 int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
 bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int);
@@ -69,13 +69,14 @@ extern "C" int pg_last_conv_impl(void) { return g_last_impl; }
 extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
 
 extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
-                           const float* bias, void* out, int impl, void* stream) {
+                           const float* bias, void* out, void* out2, int impl, void* stream) {
   if (int e = validate(d, "pg_conv_fwd")) return e;
   PG_REQUIRE(src1 && w_packed && out && (d->C2 == 0 || src2), "pg_conv_fwd: NULL pointer");
   PG_REQUIRE(!d->has_bias || bias, "pg_conv_fwd: has_bias but bias is NULL");
   cudaStream_t s = (cudaStream_t)stream;
   g_last_impl = PG_IMPL_SIMT;
-  if (impl == PG_IMPL_SIMT) return conv_fwd_simt(d, src1, src2, w_packed, bias, out, s);
+  PG_REQUIRE(out2 == nullptr || d->out_f32 != PG_F32, "pg_conv_fwd: out2 (bf16 twin) needs a 16-bit primary output");
+  if (impl == PG_IMPL_SIMT) return conv_fwd_simt(d, src1, src2, w_packed, bias, out, out2, s);
   const bool ok = conv_fwd_tc_supported(d, src1, src2, w_packed, out);
   if (ok) g_last_impl = PG_IMPL_TCGEN05;
   if (impl == PG_IMPL_TCGEN05) {
@@ -83,10 +84,10 @@ extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* sr
       set_error("pg_conv_fwd: tcgen05 path does not support this shape / alignment");
       return PG_ERR_UNSUPPORTED;
     }
-    return conv_fwd_tc(d, src1, src2, w_packed, bias, out, s);
+    return conv_fwd_tc(d, src1, src2, w_packed, bias, out, out2, s);
   }
-  if (ok) return conv_fwd_tc(d, src1, src2, w_packed, bias, out, s);
-  return conv_fwd_simt(d, src1, src2, w_packed, bias, out, s);
+  if (ok) return conv_fwd_tc(d, src1, src2, w_packed, bias, out, out2, s);
+  return conv_fwd_simt(d, src1, src2, w_packed, bias, out, out2, s);
 }
 
 extern "C" int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw, int32_t ld_n,

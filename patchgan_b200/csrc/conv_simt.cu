@@ -10,6 +10,7 @@ struct ConvK {
   const bf16* w;
   const float* bias;
   void* out;
+  void* out2;
   int mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo, n_valid, act, out_f32, in_dt;
   int Ha, Wa;  // lattice the tiles walk: PG_CONV -> (Hout, Wout); PG_CONVT -> (Hin, Win) per parity class
   long long M;
@@ -125,18 +126,24 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvK p) {
       u.x = (uint32_t)to16(v[0], p.out_f32) | ((uint32_t)to16(v[1], p.out_f32) << 16);
       u.y = (uint32_t)to16(v[2], p.out_f32) | ((uint32_t)to16(v[3], p.out_f32) << 16);
       *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n) = u;
+      if (p.out2 != nullptr) {
+        u.x = (uint32_t)to16(v[0], PG_BF16) | ((uint32_t)to16(v[1], PG_BF16) << 16);
+        u.y = (uint32_t)to16(v[2], PG_BF16) | ((uint32_t)to16(v[3], PG_BF16) << 16);
+        *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(p.out2) + opix * p.ldo + n) = u;
+      }
     }
   }
 }
 
 int conv_fwd_simt(const PgConvDesc* d, const void* src1, const void* src2, const void* w, const float* bias,
-                  void* out, cudaStream_t stream) {
+                  void* out, void* out2, cudaStream_t stream) {
   ConvK p;
   p.src1 = (const bf16*)src1;
   p.src2 = (const bf16*)src2;
   p.w = (const bf16*)w;
   p.bias = d->has_bias ? bias : nullptr;
   p.out = out;
+  p.out2 = out2;
   p.mode = d->mode; p.stride = d->stride; p.pad = d->pad; p.B = d->B; p.Hin = d->Hin; p.Win = d->Win;
   p.Hout = d->Hout; p.Wout = d->Wout; p.C1 = d->C1; p.C2 = d->C2; p.ld1 = d->ld1; p.ld2 = d->ld2;
   p.N = d->N; p.ldo = d->ldo; p.n_valid = d->n_valid; p.act = d->act; p.out_f32 = d->out_f32;

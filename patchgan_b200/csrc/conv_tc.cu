@@ -136,6 +136,7 @@ struct TcParams {
   int N, ldo, n_valid, act, out_f32;
   const float* bias;
   void* out;
+  void* out2;
   uint32_t idesc, sbo, layout_type;
   int stages;
   uint32_t a_bytes, b_bytes, tx_bytes;
@@ -275,6 +276,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n);
           o[0] = pack8dt(f, p.out_f32);
           o[1] = pack8dt(f + 8, p.out_f32);
+          if (p.out2 != nullptr) {
+            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + opix * p.ldo + n);
+            o2[0] = pack8(f);
+            o2[1] = pack8(f + 8);
+          }
         }
       }
     }
@@ -406,7 +412,7 @@ static int encode_act_map(CUtensorMap* m, const void* base, int C, int ld, int B
 }
 
 int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const void* w, const float* bias, void* out,
-                cudaStream_t stream) {
+                void* out2, cudaStream_t stream) {
   TcPlan pl;
   if (!make_plan(d, pl)) {
     set_error("conv_fwd_tc: unsupported shape");
@@ -415,6 +421,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   TcParams& p = pl.p;
   p.bias = d->has_bias ? bias : nullptr;
   p.out = out;
+  p.out2 = out2;
   const int es = d->mode == PG_CONV ? d->stride : 1;
   CUtensorMap mA1, mA2, mB;
   if (int e = encode_act_map(&mA1, src1, d->C1, d->ld1, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB, es, pl.swz, d->in_dtype))
@@ -671,6 +678,7 @@ bool conv_wgrad_tc_supported(const PgConvDesc* d, const void* a, const void* g, 
   if (!tc_device_ok()) return false;
   if ((((uintptr_t)a | (uintptr_t)g) & 15) != 0 || (ldg % 8) != 0) return false;
   if (d->out_f32 != PG_BF16 && d->out_f32 != PG_F16) return false;
+  if (d->out_f32 != d->in_dtype) return false;   // kind::f16 needs one operand format (mixed = illegal instruction)
   WgParams p; dim3 grid; size_t smem;
   return make_wg_plan(d, p, grid, smem);
 }

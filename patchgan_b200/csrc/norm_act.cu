@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(NT) instnorm_stats_kernel(const void* x, int x
 
 // ------------------------------------------------------------------ forward apply
 __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f32, const float* sums, void* y,
-                                                          int y_f32, long long HW, int C, int ldx, int ldy, int act,
+                                                          int y_f32, void* y2, long long HW, int C, int ldx, int ldy, int act,
                                                           float drop_p, const unsigned long long* seed_ptr, unsigned long long salt,
                                                           long long ppb) {
   const int b = blockIdx.y;
@@ -124,6 +124,7 @@ __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f
       f[j] = v;
     }
     store8(y, y_f32, pix * ldy + s.my_cg * 8, f);
+    if (y2 != nullptr) store8(y2, PG_BF16, pix * ldy + s.my_cg * 8, f);
   }
 }
 
@@ -286,13 +287,13 @@ extern "C" int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_
   return check_launch("instnorm_stats_kernel");
 }
 
-extern "C" int pg_norm_act_fwd(const void* x, int32_t x_f32, const float* sums, void* y, int32_t y_f32, int32_t B,
+extern "C" int pg_norm_act_fwd(const void* x, int32_t x_f32, const float* sums, void* y, int32_t y_f32, void* y2, int32_t B,
                                int64_t HW, int32_t C, int32_t ldx, int32_t ldy, int32_t act, float drop_p,
                                const uint64_t* seed, uint64_t salt, void* stream) {
   if (int e = check_c("pg_norm_act_fwd", C)) return e;
   dim3 grid; long long ppb;
   span_grid(B, HW, C, grid, ppb);
-  norm_act_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x, x_f32, sums, y, y_f32, HW, C, ldx, ldy, act, drop_p,
+  norm_act_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x, x_f32, sums, y, y_f32, y2, HW, C, ldx, ldy, act, drop_p,
                                                             (const unsigned long long*)seed, salt, ppb);
   return check_launch("norm_act_fwd_kernel");
 }

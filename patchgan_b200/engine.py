@@ -40,32 +40,54 @@ TORCH_DT = {BF16: torch.bfloat16, F32: torch.float32, F16: torch.float16}
 
 class Act:
     """A (possibly channel-sliced) NHWC activation: keeps its storage alive, carries ptr / C / pixel stride / dtype."""
-    __slots__ = ('t', 'ptr', 'C', 'ld', 'B', 'H', 'W', 'dt')
+    __slots__ = ('t', 'ptr', 'C', 'ld', 'B', 'H', 'W', 'dt', 'tw')
 
     def __init__(self, t, B, H, W, C, ld=None, off=0, dt=BF16):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
         self.ld = ld if ld is not None else C
         self.dt = dt
         self.ptr = t.data_ptr() + off * self.esize
+        self.tw = None      # bf16 twin of an f16 activation (same shape / stride), read by the wgrad GEMMs
+
+    @property
+    def b16(self):
+        """The bf16 version of this activation (itself if it already is bf16)."""
+        if self.dt == BF16:
+            return self
+        if self.tw is None:
+            raise RuntimeError('activation has no bf16 twin (forward ran without save=True)')
+        return self.tw
+
+    @property
+    def twptr(self):
+        return self.tw.ptr if self.tw is not None else None
 
     @property
     def esize(self):
         return 4 if self.dt == F32 else 2
 
     def slice(self, c0, C):
-        return Act(self.t, self.B, self.H, self.W, C, self.ld, (self.ptr - self.t.data_ptr()) // self.esize + c0, self.dt)
+        a = Act(self.t, self.B, self.H, self.W, C, self.ld, (self.ptr - self.t.data_ptr()) // self.esize + c0, self.dt)
+        if self.tw is not None:
+            a.tw = self.tw.slice(c0, C)
+        return a
 
     def first(self, nb):
         """The first nb images of the batch (same storage)."""
         a = Act(self.t, nb, self.H, self.W, self.C, self.ld, 0, self.dt)
         a.ptr = self.ptr
+        if self.tw is not None:
+            a.tw = self.tw.first(nb)
         return a
 
 
-def new_act(B, H, W, C, device, dt=BF16, zero=False):
+def new_act(B, H, W, C, device, dt=BF16, zero=False, twin=False):
     fn = torch.zeros if zero else torch.empty
     t = fn((B, H, W, C), device=device, dtype=TORCH_DT[dt])
-    return Act(t, B, H, W, C, dt=dt)
+    a = Act(t, B, H, W, C, dt=dt)
+    if twin and dt == F16:
+        a.tw = Act(fn((B, H, W, C), device=device, dtype=torch.bfloat16), B, H, W, C, dt=BF16)
+    return a
 
 
 def conv_desc(mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo, n_valid=None, act=0, out_dt=BF16,
@@ -102,7 +124,7 @@ def run_conv(desc, src1, src2, w, bias, out):
     if L.PROFILER is not None:
         L.PROFILER.note(conv_flops(desc), desc_tag(desc))
     L.call('pg_conv_fwd', ctypes.byref(desc), src1.ptr, src2.ptr if src2 is not None else None, w.data_ptr(),
-           bias.data_ptr() if bias is not None else None, out.ptr, Config.impl, _stream())
+           bias.data_ptr() if bias is not None else None, out.ptr, out.twptr, Config.impl, _stream())
 
 
 def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real):
@@ -201,7 +223,7 @@ class NetEngine:
 
 def norm_fwd(x, sums, out, act, drop_p, seed, salt):
     HW = x.H * x.W
-    L.call('pg_norm_act_fwd', x.ptr, x.dt, sums.data_ptr() if sums is not None else None, out.ptr, out.dt,
+    L.call('pg_norm_act_fwd', x.ptr, x.dt, sums.data_ptr() if sums is not None else None, out.ptr, out.dt, out.twptr,
            x.B, HW, x.C, x.ld, out.ld, act, drop_p, seed.data_ptr() if seed is not None else None, salt, _stream())
 
 
@@ -263,11 +285,13 @@ class GeneratorEngine(NetEngine):
         self.in_cp = rup16(inc)
         self.out_cp = rup16(outc)
 
-    def pack_input(self, x):
+    def pack_input(self, x, twin=False):
         """NCHW float -> NHWC bf16 with channels zero-padded to 16."""
         B, C, H, W = x.shape
-        a = new_act(B, H, W, self.in_cp, x.device, dt=Config.fwd_dt, zero=True)
+        a = new_act(B, H, W, self.in_cp, x.device, dt=Config.fwd_dt, zero=True, twin=twin)
         L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), a.ptr, B, C, H, W, a.ld, 0, a.dt, _stream())
+        if a.tw is not None:
+            L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), a.tw.ptr, B, C, H, W, a.ld, 0, BF16, _stream())
         return a
 
     def forward(self, xin, training, save=True):
@@ -288,7 +312,7 @@ class GeneratorEngine(NetEngine):
             run_conv(conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, raw.ld, out_dt=F32,
                                in_dt=h.dt), h, None, self.packed[i].fwd, None, raw)
             sums = instnorm_stats(raw)
-            out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt)
+            out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt, twin=save)
             dp = DROP_P if (training and s.dropout) else 0.0
             norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, i)
             ctx['enc'].append((h, raw, sums, out, dp) if save else None)
@@ -305,12 +329,12 @@ class GeneratorEngine(NetEngine):
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, raw.ld,
                                    out_dt=F32, in_dt=src1.dt), src1, src2, pw.fwd, None, raw)
                 sums = instnorm_stats(raw)
-                out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt)
+                out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt, twin=save)
                 dp = DROP_P if (training and s.dropout) else 0.0
                 norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, 16 + i)
                 ctx['dec'].append((src1, src2, raw, sums, out, dp) if save else None)
             elif i < 6:
-                out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt)
+                out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt, twin=save)
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, out.ld,
                                    act=L.ACT[s.act], out_dt=out.dt, in_dt=src1.dt), src1, src2, pw.fwd, None, out)
                 ctx['dec'].append((src1, src2, None, None, out, 0.0) if save else None)
@@ -339,12 +363,12 @@ class GeneratorEngine(NetEngine):
             g = grads[s.wname]
             # weight gradient: dW[ci][co][tap] = sum x[ci] * dY[co] -- PG_CONV geometry with A = dY, G = layer input
             wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C, src1.C,
-                           out_dt=src1.dt, in_dt=BF16)
-            run_wgrad(wd, d_raw, src1, g.data_ptr(), s.cout * 16, s.c1, s.cout)
+                           out_dt=BF16, in_dt=BF16)
+            run_wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.c1, s.cout)
             if src2 is not None:
                 wd2 = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src2.H, src2.W, d_raw.C, 0, d_raw.ld, 0, src2.C,
-                                src2.C, out_dt=src2.dt, in_dt=BF16)
-                run_wgrad(wd2, d_raw, src2, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout)
+                                src2.C, out_dt=BF16, in_dt=BF16)
+                run_wgrad(wd2, d_raw, src2.b16, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout)
             # data gradient: stride-2 conv of dY with W'[ci][tap][co]
             din = new_act(B, src1.H, src1.W, s.cinp, dev)
             run_conv(conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
@@ -366,8 +390,8 @@ class GeneratorEngine(NetEngine):
             s = self.enc[i]
             h, raw, sums, out, dp = ctx['enc'][i]
             d_raw = norm_bwd(raw, sums, dy1, dskip[i] if i < 6 else None, L.ACT[s.act], dp, self.seed, i)
-            wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16, in_dt=h.dt)
-            run_wgrad(wd, h, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
+            wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16, in_dt=BF16)
+            run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
             if i > 0 or need_dx:
                 din = new_act(B, h.H, h.W, s.cinp, dev)
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, raw.H, raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp, din.ld),
@@ -402,8 +426,8 @@ class DiscriminatorEngine(NetEngine):
         super().__init__(module, specs)
         self.in_cp = rup16(inc)
 
-    def new_input(self, B, H, W, device):
-        return new_act(B, H, W, self.in_cp, device, dt=Config.fwd_dt, zero=True)
+    def new_input(self, B, H, W, device, twin=False):
+        return new_act(B, H, W, self.in_cp, device, dt=Config.fwd_dt, zero=True, twin=twin)
 
     def forward(self, xin, save=True):
         """xin: Act (B,H,W,in_cp) bf16 -> (p: f32 Act (B,Ho,Wo,16) with the patch probabilities in channel 0, ctx)."""
@@ -427,13 +451,13 @@ class DiscriminatorEngine(NetEngine):
                          self.packed[li].fwd, bias, out)
                 ctx.append((h, None, None, out) if save else None)
             else:
-                t = new_act(B, Ho, Wo, s.np, dev, dt=h.dt)
+                t = new_act(B, Ho, Wo, s.np, dev, dt=h.dt, twin=save)
                 run_conv(conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, t.ld,
                                    n_valid=s.cout, act=L.ACT[s.act], out_dt=t.dt, has_bias=int(s.bias), in_dt=h.dt), h,
                          None, self.packed[li].fwd, bias, t)
                 if s.norm:
                     sums = instnorm_stats(t)
-                    out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt)
+                    out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt, twin=save)
                     norm_fwd(t, sums, out, 0, 0.0, None, 0)
                     ctx.append((h, t, sums, out) if save else None)
                 else:
@@ -455,8 +479,8 @@ class DiscriminatorEngine(NetEngine):
             h = h.first(B)
             if grads is not None:
                 wd = conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, d_raw.H, d_raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
-                               in_dt=h.dt)
-                run_wgrad(wd, h, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
+                               in_dt=BF16)
+                run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
                 if s.bias:
                     L.call('pg_colsum', d_raw.ptr, B * d_raw.H * d_raw.W, d_raw.ld, s.cout, grads[s.bname].data_ptr(),
                            _stream())

@@ -100,12 +100,13 @@ class Trainer:
         world = dp.world_size()
 
         # ---- inputs: NCHW float -> NHWC bf16; D input = [fake batch ; real batch] with x in channels 0..cin-1
-        xin = G.pack_input(x)
-        dboth = D.new_input(2 * B, H, W, dev)
+        xin = G.pack_input(x, twin=train)
+        dboth = D.new_input(2 * B, H, W, dev, twin=train)
         half = B * H * W * dboth.ld * 2
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), dboth.ptr, B, cin, H, W, dboth.ld, 0, dboth.dt, st)
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), dboth.ptr + half, B, cin, H, W, dboth.ld, 0, dboth.dt, st)
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', y.data_ptr(), dboth.ptr + half, B, cout, H, W, dboth.ld, cin, dboth.dt, st)
+        for buf in ((dboth, dboth.tw) if dboth.tw is not None else (dboth,)):
+            L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), buf.ptr, B, cin, H, W, buf.ld, 0, buf.dt, st)
+            L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), buf.ptr + half, B, cin, H, W, buf.ld, 0, buf.dt, st)
+            L.call('pg_pack_nchw_f32_to_nhwc_bf16', y.data_ptr(), buf.ptr + half, B, cout, H, W, buf.ld, cin, buf.dt, st)
 
         # ---- generator forward (trainer.py:63), D(cat(x, G(x))) and D(cat(x, y)) (trainer.py:65-66, 96-97)
         if gm.training and gm.use_dropout:
@@ -113,6 +114,8 @@ class Trainer:
             G.bump_seed()
         p, gctx = G.forward(xin, gm.training, save=train)
         L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.ptr, dboth.ld, cin, cout, B * H * W, dboth.dt, st)
+        if dboth.tw is not None:
+            L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.tw.ptr, dboth.ld, cin, cout, B * H * W, 0, st)
         pd, dctx = D.forward(dboth, save=train)
         npatch = B * pd.H * pd.W
         pd_real_ptr = pd.ptr + npatch * pd.ld * 4

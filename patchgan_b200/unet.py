@@ -54,8 +54,8 @@ class _UNetFunction(torch.autograd.Function):
     def forward(ctx, module, x, *weights):
         eng = module._engine()
         B, C, H, W = x.shape
-        xin = eng.pack_input(x.contiguous().float())
         need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
+        xin = eng.pack_input(x.contiguous().float(), twin=need_grad)
         if module.training and module.use_dropout:
             eng.ensure_packed()
             eng.bump_seed()
