@@ -45,7 +45,9 @@ static int validate(const PgConvDesc* d, const char* who) {
   PG_REQUIRE(d->N > 0 && d->N % 16 == 0, "%s: N=%d must be a multiple of 16", who, d->N);
   PG_REQUIRE(d->ld1 >= d->C1 && d->ld1 % 8 == 0 && (d->C2 == 0 || (d->ld2 >= d->C2 && d->ld2 % 8 == 0)),
              "%s: bad pixel strides", who);
-  PG_REQUIRE(d->ldo >= d->N && d->ldo % 8 == 0, "%s: bad output stride %d", who, d->ldo);
+  // ldo may be smaller than N when only the first n_valid (<= ldo) channels are wanted: the rest is not stored
+  PG_REQUIRE((d->ldo >= d->N || d->ldo >= d->n_valid) && d->ldo % (d->out_f32 == PG_F32 ? 4 : 8) == 0,
+             "%s: bad output stride %d", who, d->ldo);
   PG_REQUIRE(d->in_dtype == PG_BF16 || d->in_dtype == PG_F16, "%s: in_dtype must be PG_BF16 or PG_F16", who);
   PG_REQUIRE(d->out_f32 >= PG_BF16 && d->out_f32 <= PG_F16, "%s: bad output dtype %d", who, d->out_f32);
   if (d->mode == PG_CONV) {

@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvK p) {
     }
     const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
     const int n = n0 + tx * 4;
-    if (n >= p.N) continue;
+    if (n >= p.N || n >= p.ldo) continue;
     float v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

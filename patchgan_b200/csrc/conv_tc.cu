@@ -268,18 +268,21 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
           x = act_apply(p.act, x);
           f[j] = (n + j < p.n_valid) ? x : 0.f;
         }
-        if (p.out_f32 == PG_F32) {
+        const int keep = p.ldo - n;     // channels of this 16-chunk that exist in the (possibly trimmed) output row
+        if (keep <= 0) {
+        } else if (p.out_f32 == PG_F32) {
           float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          for (int j = 0; j < 4; ++j)
+            if (4 * j < keep) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
         } else {
           uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n);
           o[0] = pack8dt(f, p.out_f32);
-          o[1] = pack8dt(f + 8, p.out_f32);
+          if (keep > 8) o[1] = pack8dt(f + 8, p.out_f32);
           if (p.out2 != nullptr) {
             uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + opix * p.ldo + n);
             o2[0] = pack8(f);
-            o2[1] = pack8(f + 8);
+            if (keep > 8) o2[1] = pack8(f + 8);
           }
         }
       }
@@ -358,6 +361,12 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
   int bn = 256;
   while (bn > 16 && (d->N % bn) != 0) bn >>= 1;
   if ((d->N % bn) != 0) return false;
+  // Small M grids (the 2x2 .. 16x16 bottleneck layers) would otherwise run on a handful of SMs, each pulling the
+  // whole weight matrix through its own ~80 GB/s L2 port: split N further so the weights stream on more SMs.
+  {
+    const long long mtiles = (long long)p.nx * p.ny * nb * (d->mode == PG_CONVT ? 4 : 1);
+    while (bn > 16 && mtiles * (d->N / bn) < num_sms()) bn >>= 1;
+  }
   p.BN = bn;
   p.N = d->N; p.ldo = d->ldo; p.n_valid = d->n_valid; p.act = d->act; p.out_f32 = d->out_f32;
   pl.swz = bk * 2;

@@ -56,6 +56,38 @@ __global__ void pack_weight_kernel(const float* __restrict__ src, unsigned short
   }
 }
 
+// Tiled version: one block moves an 8 (n) x 32 (c) x 16 (tap) brick.  Reads follow the source's contiguous axis
+// (the 16 taps of one (n, c) are always contiguous; the next-fastest source axis is n when sn == 16, else c),
+// writes are 32 consecutive packed channels (64 B) per (n, tap).
+__global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const float* __restrict__ src,
+                                                               unsigned short* __restrict__ dst, int N, int Np, int C1,
+                                                               int C1p, int C2, int C2p, long long sn, long long sc,
+                                                               int flip, int dt) {
+  __shared__ float tile[8][32][17];
+  const int Cp = C1p + C2p;
+  const int n0 = blockIdx.y * 8, cp0 = blockIdx.x * 32;
+  // ---- load: thread -> (t fastest, then the source-contiguous one of (n, c))
+  for (int e = threadIdx.x; e < 8 * 32 * 16; e += 256) {
+    const int t = e & 15;
+    int nl, cl;
+    if (sn == 16) { nl = (e >> 4) & 7; cl = e >> 7; } else { cl = (e >> 4) & 31; nl = e >> 9; }
+    const int n = n0 + nl, cp = cp0 + cl;
+    int c = -1;
+    if (cp < C1p) { if (cp < C1) c = cp; }
+    else if (cp < Cp) { if (cp - C1p < C2) c = C1 + (cp - C1p); }
+    float v = 0.f;
+    if (n < N && c >= 0) v = src[n * sn + c * sc + t];
+    tile[nl][cl][t] = v;
+  }
+  __syncthreads();
+  // ---- store: 32 consecutive packed channels per (n, tap)
+  for (int e = threadIdx.x; e < 8 * 32 * 16; e += 256) {
+    const int cl = e & 31, t = (e >> 5) & 15, nl = e >> 9;
+    const int n = n0 + nl, cp = cp0 + cl;
+    if (n < Np && cp < Cp) dst[((long long)n * 16 + t) * Cp + cp] = to16(tile[nl][cl][flip ? 15 - t : t], dt);
+  }
+}
+
 static unsigned grid1d(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
   const long long cap = 16LL * num_sms();
@@ -97,6 +129,12 @@ extern "C" int pg_copy_f32_to_bf16_slice(const float* src, int32_t lds, void* ds
 extern "C" int pg_pack_weight(const float* src, void* dst, int32_t N, int32_t Np, int32_t C1, int32_t C1p, int32_t C2,
                               int32_t C2p, int64_t sn, int64_t sc, int32_t flip, int32_t dst_dtype, void* stream) {
   PG_REQUIRE(N <= Np && C1 <= C1p && C2 <= C2p, "pg_pack_weight: padded extents smaller than real ones");
+  if (sn == 16 || sc == 16) {
+    dim3 grid((unsigned)((C1p + C2p + 31) / 32), (unsigned)((Np + 7) / 8));
+    pack_weight_tiled_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, (unsigned short*)dst, N, Np, C1, C1p, C2, C2p,
+                                                                     sn, sc, flip, dst_dtype);
+    return check_launch("pack_weight_tiled_kernel");
+  }
   const long long total = (long long)Np * 16 * (C1p + C2p);
   pack_weight_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned short*)dst, N, Np, C1, C1p, C2,
                                                                           C2p, sn, sc, flip, dst_dtype);

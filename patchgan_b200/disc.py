@@ -50,12 +50,13 @@ class _DiscFunction(torch.autograd.Function):
         B, C, H, W = ctx.shape
         p = ctx.p
         dev = dout.device
-        dpk = new_act(B, p.H, p.W, p.ld, dev, zero=True)
+        dpk = new_act(B, p.H, p.W, 16, dev, zero=True)
         L.call('pg_pack_nchw_f32_to_nhwc_bf16', dout.contiguous().data_ptr(), dpk.ptr, B, 1, p.H, p.W, dpk.ld, 0, dpk.dt,
                _stream())
-        d_raw = new_act(B, p.H, p.W, p.ld, dev)
-        L.call('pg_act_bwd_from_output', p.ptr, 1, p.ld, dpk.ptr, dpk.ld, d_raw.ptr, d_raw.ld, B * p.H * p.W, p.ld,
-               L.ACT['sigmoid'], _stream())
+        d_raw = new_act(B, p.H, p.W, 16, dev)
+        # sigmoid backward of the single real channel; channels 1..15 of d_raw are written as zeros
+        L.call('pg_gen_out_bwd', p.ptr, p.ld, None, None, None, dpk.ptr, dpk.ld, 0, d_raw.ptr, d_raw.ld, B, 1, p.H * p.W,
+               L.LOSS['none'], L.ACT['sigmoid'], 0.0, _stream())
         names = []
         for s in eng.specs:
             names.append(s.wname)

@@ -339,7 +339,7 @@ class GeneratorEngine(NetEngine):
                                    act=L.ACT[s.act], out_dt=out.dt, in_dt=src1.dt), src1, src2, pw.fwd, None, out)
                 ctx['dec'].append((src1, src2, None, None, out, 0.0) if save else None)
             else:
-                out = new_act(B, Ho, Wo, s.np, dev, dt=F32)
+                out = new_act(B, Ho, Wo, (s.cout + 3) // 4 * 4, dev, dt=F32)   # trimmed stride: real channels only
                 fused = 0 if s.act == 'softmax' else L.ACT[s.act]
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, out.ld,
                                    n_valid=s.cout, act=fused, out_dt=F32, in_dt=src1.dt), src1, src2, pw.fwd, None, out)
@@ -445,7 +445,7 @@ class DiscriminatorEngine(NetEngine):
                 raise RuntimeError(f'Discriminator: input too small at layer {li} ({h.H}x{h.W})')
             bias = ps[s.bname].detach() if s.bias else None
             if li == last:
-                out = new_act(B, Ho, Wo, s.np, dev, dt=F32)
+                out = new_act(B, Ho, Wo, 4, dev, dt=F32)                         # one real channel, stride 4
                 run_conv(conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, out.ld,
                                    n_valid=s.cout, act=L.ACT[s.act], out_dt=F32, has_bias=1, in_dt=h.dt), h, None,
                          self.packed[li].fwd, bias, out)

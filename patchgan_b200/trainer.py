@@ -133,8 +133,8 @@ class Trainer:
                float(self.tversky_beta), float(self.tversky_gamma), float(self.seg_alpha), st)
 
         # ---- generator adversarial loss bce(D(fake), 1) (trainer.py:84) and generator update (:87-90)
-        dz_g = new_act(B, pd.H, pd.W, pd.ld, dev) if train else None
-        L.call('pg_bce_const', pd.ptr, pd.ld, 1.0, 1.0, losses.data_ptr(), 1, dz_g.ptr if train else None, pd.ld,
+        dz_g = new_act(B, pd.H, pd.W, 16, dev) if train else None
+        L.call('pg_bce_const', pd.ptr, pd.ld, 1.0, 1.0, losses.data_ptr(), 1, dz_g.ptr if train else None, 16,
                npatch, st)
         g_work = None
         if train:
@@ -142,7 +142,7 @@ class Trainer:
             gflat = gopt.flat()
             gflat['g'].zero_()
             d_dinp = D.backward(dctx, dz_g, None, need_dx=True, nb=B)
-            d_raw = new_act(B, H, W, p.ld, dev)
+            d_raw = new_act(B, H, W, G.out_cp, dev)
             L.call('pg_gen_out_bwd', p.ptr, p.ld, y.data_ptr(), chp, coef.data_ptr(), d_dinp.ptr, d_dinp.ld, cin,
                    d_raw.ptr, d_raw.ld, B, cout, H * W, lt, L.ACT[gm.final_act], float(self.tversky_beta), st)
             ggrads = {n: q.grad for n, q in gm.named_parameters()}
@@ -154,11 +154,11 @@ class Trainer:
                 gopt.step(sync_lr=False)
 
         # ---- discriminator losses (trainer.py:101-103) and update (:105-107)
-        dz = new_act(2 * B, pd.H, pd.W, pd.ld, dev) if train else None
-        L.call('pg_bce_const', pd.ptr, pd.ld, 0.0, 0.5, losses.data_ptr(), 3, dz.ptr if train else None, pd.ld, npatch,
+        dz = new_act(2 * B, pd.H, pd.W, 16, dev) if train else None
+        L.call('pg_bce_const', pd.ptr, pd.ld, 0.0, 0.5, losses.data_ptr(), 3, dz.ptr if train else None, 16, npatch,
                st)
         L.call('pg_bce_const', pd_real_ptr, pd.ld, 1.0, 0.5, losses.data_ptr(), 2,
-               dz.ptr + npatch * pd.ld * 2 if train else None, pd.ld, npatch, st)
+               dz.ptr + npatch * 16 * 2 if train else None, 16, npatch, st)
         if train:
             dflat = dopt.flat()
             dflat['g'].zero_()

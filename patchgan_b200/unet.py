@@ -74,10 +74,10 @@ class _UNetFunction(torch.autograd.Function):
         p = ctx.p
         dev = dout.device
         # dOut (NCHW float) -> NHWC bf16, then through the final activation
-        dpk = new_act(B, H, W, p.ld, dev, zero=True)
+        dpk = new_act(B, H, W, eng.out_cp, dev, zero=True)
         L.call('pg_pack_nchw_f32_to_nhwc_bf16', dout.contiguous().data_ptr(), dpk.ptr, B, module.output_nc, H, W, dpk.ld,
                0, dpk.dt, _stream())
-        d_raw = new_act(B, H, W, p.ld, dev)
+        d_raw = new_act(B, H, W, eng.out_cp, dev)
         L.call('pg_gen_out_bwd', p.ptr, p.ld, None, None, None, dpk.ptr, dpk.ld, 0, d_raw.ptr, d_raw.ld, B,
                module.output_nc, H * W, L.LOSS['none'], L.ACT[module.final_act], 0.0, _stream())
         names = [s.wname for s in eng.specs]
