@@ -134,6 +134,21 @@ int pg_copy_f32_to_bf16_slice(const float* src, int32_t lds, void* dst, int32_t 
 int pg_pack_weight(const float* src, void* dst, int32_t N, int32_t Np, int32_t C1, int32_t C1p, int32_t C2,
                    int32_t C2p, int64_t sn, int64_t sc, int32_t flip, int32_t dst_dtype, void* stream);
 
+/* Two NCHW float sources -> one full NHWC row per pixel [src1 | src2 | zeros up to ld] (ld = 16 or 32), plus an optional
+ * bf16 twin dst2: the whole torch.cat((input, mask), 1) + cast + pad of trainer.py:65,96 in one pass. */
+int pg_pack2_nchw_rows(const float* src1, int32_t C1, const float* src2, int32_t C2, void* dst, void* dst2, int32_t B,
+                       int32_t H, int32_t W, int32_t ld, int32_t dst_dtype, void* stream);
+/* Every weight tensor of a network in one launch.  jobs_dev: DEVICE array; each job is one pg_pack_weight call;
+ * tile_begin = first 8x32x16 brick of the job in the launch, ctiles = ceil((C1p+C2p)/32). */
+typedef struct PgPackJob {
+  const float* src;
+  void* dst;
+  int64_t sn, sc;
+  int32_t N, Np, C1, C1p, C2, C2p, flip, dst_dtype;
+  int32_t tile_begin, ctiles;
+} PgPackJob;
+int pg_pack_weights_multi(const PgPackJob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream);
+
 /* ---- InstanceNorm2d(affine=False, eps=1e-5) + activation + Dropout(0.2)
  *      (unet.py:20-28,55-66; disc.py:32,42) ---- */
 /* In this group x_f32 / y_f32 are PgDType values (PG_BF16, PG_F32, PG_F16); dy / dx gradients are bf16. */

@@ -281,9 +281,46 @@ __global__ void colsum_kernel(const bf16* g, long long M, int ldg, int n_real, f
 
 }  // namespace pg
 
+__global__ void __launch_bounds__(256) colsum_vec_kernel(const pg::bf16* __restrict__ g, long long M, int ldg, int n_real,
+                                                        float* db, long long rows_per_block) {
+  // 8 channels per thread (16 B loads), consecutive threads on consecutive channel groups of a row
+  __shared__ float sh[1024];
+  const int cg = (n_real + 7) >> 3;
+  const int pl = 256 / cg;
+  const int my_cg = threadIdx.x % cg, my_pl = threadIdx.x / cg;
+  for (int i = threadIdx.x; i < cg * 8; i += 256) sh[i] = 0.f;
+  __syncthreads();
+  const long long beg = (long long)blockIdx.x * rows_per_block;
+  long long end = beg + rows_per_block;
+  if (end > M) end = M;
+  if (my_pl < pl) {
+    float a[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = 0.f;
+    for (long long m = beg + my_pl; m < end; m += pl) {
+      float f[8];
+      pg::unpack8(*reinterpret_cast<const uint4*>(g + m * ldg + my_cg * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(&sh[my_cg * 8 + j], a[j]);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_real; i += 256) atomicAdd(db + i, sh[i]);
+}
+
 extern "C" int pg_colsum(const void* g, int64_t M, int32_t ldg, int32_t n_real, float* db, void* stream) {
   PG_REQUIRE(n_real >= 1 && n_real <= 1024, "pg_colsum: n_real=%d out of range", n_real);
   if (M <= 0) return PG_OK;
+  if (ldg % 8 == 0 && ((n_real + 7) / 8) * 8 <= ldg && (((uintptr_t)g) & 15) == 0) {
+    long long blocks = 4LL * pg::num_sms();
+    long long rpb = (M + blocks - 1) / blocks;
+    if (rpb < 64) rpb = 64;
+    blocks = (M + rpb - 1) / rpb;
+    colsum_vec_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((const pg::bf16*)g, M, ldg, n_real, db, rpb);
+    return pg::check_launch("colsum_vec_kernel");
+  }
   long long chunk = 512;
   long long blocks = (M + chunk - 1) / chunk;
   int threads = ((n_real + 31) / 32) * 32;

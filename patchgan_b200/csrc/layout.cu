@@ -88,6 +88,76 @@ __global__ void __launch_bounds__(256) pack_weight_tiled_kernel(const float* __r
   }
 }
 
+// Two NCHW float sources -> ONE full NHWC row per pixel: [src1 channels | src2 channels | zeros up to ld], written as
+// 16-byte vectors, optionally also as a bf16 twin.  One thread per pixel (plane reads coalesced across the warp).
+template <int LD>
+__global__ void __launch_bounds__(256) pack2_rows_kernel(const float* __restrict__ s1, int C1, const float* __restrict__ s2,
+                                                        int C2, unsigned short* __restrict__ dst,
+                                                        unsigned short* __restrict__ dst2, long long HW, int dt) {
+  const int b = blockIdx.y;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < HW; p += (long long)gridDim.x * blockDim.x) {
+    float v[LD];
+#pragma unroll
+    for (int c = 0; c < LD; ++c) {
+      float x = 0.f;
+      if (c < C1) x = s1[((long long)b * C1 + c) * HW + p];
+      else if (c - C1 < C2) x = s2[((long long)b * C2 + (c - C1)) * HW + p];
+      v[c] = x;
+    }
+    const long long o = ((long long)b * HW + p) * LD;
+#pragma unroll
+    for (int c = 0; c < LD; c += 8) {
+      *reinterpret_cast<uint4*>(dst + o + c) = pack8dt(v + c, dt);
+      if (dst2 != nullptr) *reinterpret_cast<uint4*>(dst2 + o + c) = pack8(v + c);
+    }
+  }
+}
+
+// All weight tensors of a network in ONE launch: blockIdx.x walks a concatenated list of 8x32x16 bricks.
+struct PackJob {              // mirrors PgPackJob
+  const float* src;
+  unsigned short* dst;
+  long long sn, sc;
+  int N, Np, C1, C1p, C2, C2p, flip, dt;
+  int tile_begin, ctiles;
+};
+
+__global__ void __launch_bounds__(256) pack_weight_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
+  __shared__ float tile[8][32][17];
+  __shared__ PackJob job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;              // last job whose tile_begin <= blockIdx.x
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    job = jobs[lo];
+  }
+  __syncthreads();
+  const int local = blockIdx.x - job.tile_begin;
+  const int n0 = (local / job.ctiles) * 8, cp0 = (local % job.ctiles) * 32;
+  const int Cp = job.C1p + job.C2p;
+  for (int e = threadIdx.x; e < 8 * 32 * 16; e += 256) {
+    const int t = e & 15;
+    int nl, cl;
+    if (job.sn == 16) { nl = (e >> 4) & 7; cl = e >> 7; } else { cl = (e >> 4) & 31; nl = e >> 9; }
+    const int n = n0 + nl, cp = cp0 + cl;
+    int c = -1;
+    if (cp < job.C1p) { if (cp < job.C1) c = cp; }
+    else if (cp < Cp) { if (cp - job.C1p < job.C2) c = job.C1 + (cp - job.C1p); }
+    float v = 0.f;
+    if (n < job.N && c >= 0) v = job.src[n * job.sn + c * job.sc + t];
+    tile[nl][cl][t] = v;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 8 * 32 * 16; e += 256) {
+    const int cl = e & 31, t = (e >> 5) & 15, nl = e >> 9;
+    const int n = n0 + nl, cp = cp0 + cl;
+    if (n < job.Np && cp < Cp)
+      job.dst[((long long)n * 16 + t) * Cp + cp] = to16(tile[nl][cl][job.flip ? 15 - t : t], job.dt);
+  }
+}
+
 static unsigned grid1d(long long work, int threads) {
   long long b = (work + threads - 1) / threads;
   const long long cap = 16LL * num_sms();
@@ -139,4 +209,28 @@ extern "C" int pg_pack_weight(const float* src, void* dst, int32_t N, int32_t Np
   pack_weight_kernel<<<grid1d(total, 256), 256, 0, (cudaStream_t)stream>>>(src, (unsigned short*)dst, N, Np, C1, C1p, C2,
                                                                           C2p, sn, sc, flip, dst_dtype);
   return check_launch("pack_weight_kernel");
+}
+
+extern "C" int pg_pack2_nchw_rows(const float* src1, int32_t C1, const float* src2, int32_t C2, void* dst, void* dst2,
+                                  int32_t B, int32_t H, int32_t W, int32_t ld, int32_t dst_dtype, void* stream) {
+  PG_REQUIRE(dst_dtype == PG_BF16 || dst_dtype == PG_F16, "pg_pack2_nchw_rows: dst_dtype must be 16-bit");
+  PG_REQUIRE(C1 > 0 && C2 >= 0 && C1 + C2 <= ld && (ld == 16 || ld == 32), "pg_pack2_nchw_rows: C1=%d C2=%d ld=%d", C1, C2,
+             ld);
+  PG_REQUIRE(C2 == 0 || src2 != nullptr, "pg_pack2_nchw_rows: src2 is NULL");
+  const long long HW = (long long)H * W;
+  dim3 grid(grid1d(HW, 256), B);
+  if (ld == 16)
+    pack2_rows_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(src1, C1, src2, C2, (unsigned short*)dst,
+                                                                 (unsigned short*)dst2, HW, dst_dtype);
+  else
+    pack2_rows_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(src1, C1, src2, C2, (unsigned short*)dst,
+                                                                 (unsigned short*)dst2, HW, dst_dtype);
+  return check_launch("pack2_rows_kernel");
+}
+
+extern "C" int pg_pack_weights_multi(const PgPackJob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream) {
+  static_assert(sizeof(PgPackJob) == sizeof(PackJob), "PgPackJob layout");
+  PG_REQUIRE(jobs_dev != nullptr && njobs > 0 && total_tiles > 0, "pg_pack_weights_multi: empty job list");
+  pack_weight_multi_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>((const PackJob*)jobs_dev, njobs);
+  return check_launch("pack_weight_multi_kernel");
 }

@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(256) gen_out_bwd_kernel(const float* __restric
     const float* pp = p + pix * ld;
     float dp[16], pv[16];
     float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) { dp[c] = 0.f; pv[c] = 0.f; }
     for (int c = 0; c < C; ++c) {
       const float q = pp[c];
       const float tv = loss_type == LT_NONE ? 0.f : t[((long long)b * C + c) * HW + px];
@@ -159,13 +161,22 @@ __global__ void __launch_bounds__(256) gen_out_bwd_kernel(const float* __restric
       pv[c] = q;
       dot = fmaf(g, q, dot);
     }
-    for (int c = 0; c < C; ++c) {
-      float g;
-      if (final_act == FINAL_SOFTMAX) g = pv[c] * (dp[c] - dot);
-      else g = dp[c] * act_grad_from_output(final_act, pv[c]);
-      dx[pix * lddx + c] = __float2bfloat16(g);
+    float outv[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      float g = 0.f;
+      if (c < C) {
+        if (final_act == FINAL_SOFTMAX) g = pv[c] * (dp[c] - dot);
+        else g = dp[c] * act_grad_from_output(final_act, pv[c]);
+      }
+      outv[c] = g;
     }
-    for (int c = C; c < lddx; ++c) dx[pix * lddx + c] = __float2bfloat16(0.f);
+    if (lddx == 16) {          // the usual case: one 32-byte row
+      *reinterpret_cast<uint4*>(dx + pix * 16) = pack8(outv);
+      *reinterpret_cast<uint4*>(dx + pix * 16 + 8) = pack8(outv + 8);
+    } else {
+      for (int c = 0; c < lddx; ++c) dx[pix * lddx + c] = __float2bfloat16(c < 16 ? outv[c] : 0.f);
+    }
   }
 }
 

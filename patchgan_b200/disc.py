@@ -9,7 +9,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
-from .engine import DiscriminatorEngine, _stream, new_act, require_cuda
+from .engine import DiscriminatorEngine, _stream, new_act, pack_rows, require_cuda
 from .transfer import Transferable
 from .unet import _Holder
 
@@ -31,11 +31,15 @@ class _DiscFunction(torch.autograd.Function):
         eng = module._engine()
         B, C, H, W = x.shape
         need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
-        xin = eng.new_input(B, H, W, x.device, twin=need_grad)
         xs = x.contiguous().float()
-        L.call('pg_pack_nchw_f32_to_nhwc_bf16', xs.data_ptr(), xin.ptr, B, C, H, W, xin.ld, 0, xin.dt, _stream())
-        if xin.tw is not None:
-            L.call('pg_pack_nchw_f32_to_nhwc_bf16', xs.data_ptr(), xin.tw.ptr, B, C, H, W, xin.ld, 0, 0, _stream())
+        if eng.in_cp in (16, 32):
+            xin = eng.new_input(B, H, W, x.device, twin=need_grad, zero=False)
+            pack_rows(xs, None, xin, 0)
+        else:
+            xin = eng.new_input(B, H, W, x.device, twin=need_grad)
+            L.call('pg_pack_nchw_f32_to_nhwc_bf16', xs.data_ptr(), xin.ptr, B, C, H, W, xin.ld, 0, xin.dt, _stream())
+            if xin.tw is not None:
+                L.call('pg_pack_nchw_f32_to_nhwc_bf16', xs.data_ptr(), xin.tw.ptr, B, C, H, W, xin.ld, 0, 0, _stream())
         p, saved = eng.forward(xin, save=need_grad)
         out = torch.empty((B, 1, p.H, p.W), device=x.device, dtype=torch.float32)
         L.call('pg_unpack_nhwc_to_nchw_f32', p.ptr, 1, out.data_ptr(), B, 1, p.H, p.W, p.ld, 0, _stream())

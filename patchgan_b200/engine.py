@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes
 import os
 
+import numpy as np
 import torch
 
 from . import _lib as L
@@ -153,6 +154,20 @@ class PackedWeights:
         self.fwd = torch.empty((spec.np, 16, spec.cinp), device=device, dtype=TORCH_DT[self.fwd_dt])
         self.bwd = torch.empty((spec.cinp, 16, spec.np), device=device, dtype=torch.bfloat16)
 
+    def jobs(self, w):
+        """The pg_pack_weight calls of `pack` as (src, dst, N, Np, C1, C1p, C2, C2p, sn, sc, flip, dtype) tuples."""
+        s, wp = self.spec, w.data_ptr()
+        if s.kind == 'conv':
+            return [(wp, self.fwd.data_ptr(), s.cout, s.np, s.c1, s.c1p, 0, 0, s.cin * 16, 16, 0, self.fwd_dt),
+                    (wp, self.bwd.data_ptr(), s.cin, s.cinp, s.cout, s.np, 0, 0, 16, s.cin * 16,
+                     1 if s.stride == 1 else 0, BF16)]
+        out = [(wp, self.fwd.data_ptr(), s.cout, s.np, s.c1, s.c1p, s.c2, s.c2p, 16, s.cout * 16, 0, self.fwd_dt),
+               (wp, self.bwd.data_ptr(), s.c1, s.c1p, s.cout, s.np, 0, 0, s.cout * 16, 16, 0, BF16)]
+        if s.c2:
+            out.append((wp + s.c1 * s.cout * 16 * 4, self.bwd.data_ptr() + s.c1p * 16 * s.np * 2, s.c2, s.c2p, s.cout,
+                        s.np, 0, 0, s.cout * 16, 16, 0, BF16))
+        return out
+
     def pack(self, w):
         s, st = self.spec, _stream()
         wp = w.data_ptr()
@@ -179,6 +194,7 @@ class NetEngine:
         self.specs = specs
         self.packed = None
         self._stamp = None
+        self._jobs = None
         self.seed = None   # device uint64 dropout counter
 
     def params(self):
@@ -201,12 +217,31 @@ class NetEngine:
             self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
             self._stamp = None
         if stamp != self._stamp:
-            for pw in self.packed:
-                w = ps[pw.spec.wname].detach()
-                if w.dtype != torch.float32 or not w.is_contiguous():
-                    raise RuntimeError(f'{pw.spec.wname}: weights must be contiguous float32')
-                pw.pack(w)
+            ptrs = tuple(s_[0] for s_ in stamp)
+            if self._jobs is None or self._jobs[0] != ptrs:
+                self._jobs = (ptrs,) + self._build_jobs(ps, dev)
+            _, table, njobs, ntiles = self._jobs
+            L.call('pg_pack_weights_multi', table.data_ptr(), njobs, ntiles, _stream())
             self._stamp = stamp
+
+    JOB_DT = np.dtype([('src', '<u8'), ('dst', '<u8'), ('sn', '<i8'), ('sc', '<i8'), ('N', '<i4'), ('Np', '<i4'),
+                       ('C1', '<i4'), ('C1p', '<i4'), ('C2', '<i4'), ('C2p', '<i4'), ('flip', '<i4'), ('dt', '<i4'),
+                       ('tile_begin', '<i4'), ('ctiles', '<i4')])
+
+    def _build_jobs(self, ps, dev):
+        """Device table for pg_pack_weights_multi: every layer's forward + dgrad operand packs in one launch."""
+        rows, tile = [], 0
+        for pw in self.packed:
+            w = ps[pw.spec.wname].detach()
+            if w.dtype != torch.float32 or not w.is_contiguous():
+                raise RuntimeError(f'{pw.spec.wname}: weights must be contiguous float32')
+            for (src, dst, N, Np, C1, C1p, C2, C2p, sn, sc, flip, dt) in pw.jobs(w):
+                ctiles = (C1p + C2p + 31) // 32
+                rows.append((src, dst, sn, sc, N, Np, C1, C1p, C2, C2p, flip, dt, tile, ctiles))
+                tile += ctiles * ((Np + 7) // 8)
+        arr = np.array(rows, dtype=self.JOB_DT)
+        table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
+        return table, len(rows), tile
 
     def repack(self):
         """Unconditional repack (used inside captured graphs right after the optimizer step)."""
@@ -220,6 +255,16 @@ class NetEngine:
 # ------------------------------------------------------------------------------------------------
 # shared per-layer helpers
 # ------------------------------------------------------------------------------------------------
+
+def pack_rows(x1, x2, dst, first_image):
+    """NCHW float x1 [, x2] -> full NHWC rows [x1 | x2 | 0...] of `dst` (and its bf16 twin) starting at image
+    `first_image`; dst.ld must be 16 or 32 (one launch, no pre-zeroing needed)."""
+    B, C1, H, W = x1.shape
+    C2 = x2.shape[1] if x2 is not None else 0
+    off = first_image * H * W * dst.ld * 2
+    L.call('pg_pack2_nchw_rows', x1.data_ptr(), C1, x2.data_ptr() if x2 is not None else None, C2, dst.ptr + off,
+           dst.tw.ptr + off if dst.tw is not None else None, B, H, W, dst.ld, dst.dt, _stream())
+
 
 def norm_fwd(x, sums, out, act, drop_p, seed, salt):
     HW = x.H * x.W
@@ -288,6 +333,10 @@ class GeneratorEngine(NetEngine):
     def pack_input(self, x, twin=False):
         """NCHW float -> NHWC bf16 with channels zero-padded to 16."""
         B, C, H, W = x.shape
+        if self.in_cp in (16, 32):
+            a = new_act(B, H, W, self.in_cp, x.device, dt=Config.fwd_dt, twin=twin)
+            pack_rows(x, None, a, 0)
+            return a
         a = new_act(B, H, W, self.in_cp, x.device, dt=Config.fwd_dt, zero=True, twin=twin)
         L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), a.ptr, B, C, H, W, a.ld, 0, a.dt, _stream())
         if a.tw is not None:
@@ -426,8 +475,8 @@ class DiscriminatorEngine(NetEngine):
         super().__init__(module, specs)
         self.in_cp = rup16(inc)
 
-    def new_input(self, B, H, W, device, twin=False):
-        return new_act(B, H, W, self.in_cp, device, dt=Config.fwd_dt, zero=True, twin=twin)
+    def new_input(self, B, H, W, device, twin=False, zero=True):
+        return new_act(B, H, W, self.in_cp, device, dt=Config.fwd_dt, zero=zero, twin=twin)
 
     def forward(self, xin, save=True):
         """xin: Act (B,H,W,in_cp) bf16 -> (p: f32 Act (B,Ho,Wo,16) with the patch probabilities in channel 0, ctx)."""

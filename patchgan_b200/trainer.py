@@ -25,7 +25,7 @@ from torch.optim.lr_scheduler import ExponentialLR, ReduceLROnPlateau
 
 from . import _lib as L
 from . import dp
-from .engine import _stream, new_act
+from .engine import _stream, new_act, pack_rows
 from .optim import FusedAdam
 
 LOSS_KEYS = ['gen', 'gen_loss', 'gdisc', 'discr', 'discf', 'disc']
@@ -101,12 +101,18 @@ class Trainer:
 
         # ---- inputs: NCHW float -> NHWC bf16; D input = [fake batch ; real batch] with x in channels 0..cin-1
         xin = G.pack_input(x, twin=train)
-        dboth = D.new_input(2 * B, H, W, dev, twin=train)
-        half = B * H * W * dboth.ld * 2
-        for buf in ((dboth, dboth.tw) if dboth.tw is not None else (dboth,)):
-            L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), buf.ptr, B, cin, H, W, buf.ld, 0, buf.dt, st)
-            L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), buf.ptr + half, B, cin, H, W, buf.ld, 0, buf.dt, st)
-            L.call('pg_pack_nchw_f32_to_nhwc_bf16', y.data_ptr(), buf.ptr + half, B, cout, H, W, buf.ld, cin, buf.dt, st)
+        if D.in_cp in (16, 32):
+            dboth = D.new_input(2 * B, H, W, dev, twin=train, zero=False)
+            pack_rows(x, None, dboth, 0)          # fake half: [x | (G(x) copied in below) | 0]
+            pack_rows(x, y, dboth, B)             # real half: [x | y | 0]
+        else:
+            dboth = D.new_input(2 * B, H, W, dev, twin=train)
+            half = B * H * W * dboth.ld * 2
+            for buf in ((dboth, dboth.tw) if dboth.tw is not None else (dboth,)):
+                L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), buf.ptr, B, cin, H, W, buf.ld, 0, buf.dt, st)
+                L.call('pg_pack_nchw_f32_to_nhwc_bf16', x.data_ptr(), buf.ptr + half, B, cin, H, W, buf.ld, 0, buf.dt, st)
+                L.call('pg_pack_nchw_f32_to_nhwc_bf16', y.data_ptr(), buf.ptr + half, B, cout, H, W, buf.ld, cin, buf.dt,
+                       st)
 
         # ---- generator forward (trainer.py:63), D(cat(x, G(x))) and D(cat(x, y)) (trainer.py:65-66, 96-97)
         if gm.training and gm.use_dropout:

@@ -32,7 +32,8 @@ from patchgan_b200.engine import Config
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 GRAD_TOL = 2e-2          # vs storage-rounding oracle, smooth activation (tanh)
-GRAD_TOL_GATED = 8e-2    # vs storage-rounding oracle, LeakyReLU / ReLU generators (see module docstring)
+GRAD_TOL_GATED = 8e-2    # vs storage-rounding oracle, LeakyReLU generators (see module docstring)
+GRAD_TOL_RELU = 0.12     # ReLU: exact zeros make each flipped gate cost more (and the run-to-run atomics jitter)
 GRAD_TOL_FP32 = 0.35     # vs plain fp32 oracle: sanity bound only (see module docstring)
 FLIP_FRAC = 0.05
 
@@ -85,7 +86,7 @@ def check_step(tr, otr, oq, x, y, name, relu, gated=True):
         gerr32['D.' + k] = relerr(p.grad.cpu().numpy(), otr.last['disc_grads'][k])
     print(name, 'grad err vs storage-rounding oracle', short(gerr))
     print(name, 'grad err vs fp32 oracle            ', short(gerr32))
-    assert max(gerr.values()) < (GRAD_TOL_GATED if gated else GRAD_TOL), gerr
+    assert max(gerr.values()) < (GRAD_TOL_RELU if relu else (GRAD_TOL_GATED if gated else GRAD_TOL)), gerr
     assert max(gerr32.values()) < GRAD_TOL_FP32, gerr32
     lr = 1e-3
     flips = {}
