@@ -14,6 +14,7 @@
 // Reference ops replaced: aten::convolution under nn.Conv2d / nn.ConvTranspose2d (unet.py:19,53; disc.py:19-45)
 // and their dgrad.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -144,10 +145,10 @@ struct TcParams {
 };
 
 constexpr int TC_THREADS = 192;
-constexpr int MAX_STAGES = 8;
+constexpr int MAX_STAGES = 12;
 constexpr int TC_MAX_DYN_SMEM = 224 * 1024;
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 4)
 conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
                const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -379,7 +380,23 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
   p.b_bytes = ((uint32_t)bn * pl.swz + 1023u) & ~1023u;
   p.tx_bytes = 128u * pl.swz + (uint32_t)bn * pl.swz;
   const uint32_t per_stage = p.a_bytes + p.b_bytes;
-  int stages = (int)(((uint32_t)TC_MAX_DYN_SMEM - 2048u) / per_stage);
+  // Two CTAs share an SM (each with half of the smem ring and <= 256 TMEM columns) so that one CTA's prologue /
+  // epilogue overlaps the other's main loop.  PG_TC_OCC=1 restores one CTA per SM with the full ring.
+  static const int occ_env = [] { const char* e = getenv("PG_TC_OCC"); return e ? atoi(e) : 4; }();
+  int occ = occ_env < 1 ? 1 : (occ_env > 4 ? 4 : occ_env);
+  {
+    // small grids cannot fill more than one CTA per SM anyway: give them one CTA with a deep ring (latency-bound
+    // k-loops need bytes in flight), large grids get co-resident CTAs with shallow rings
+    const long long ctas = (long long)p.nx * p.ny * nb * (d->N / bn) * (d->mode == PG_CONVT ? 4 : 1);
+    const int want = (int)((ctas + num_sms() - 1) / num_sms());
+    if (occ > want) occ = want < 1 ? 1 : want;
+  }
+  const int tmem_need = bn < 32 ? 32 : bn;
+  if (occ * tmem_need > 512) occ = 512 / tmem_need;                 // co-resident CTAs share the 512 TMEM columns
+  while (occ > 1 && (220u * 1024u / occ) / per_stage < 2) --occ;    // keep at least a 2-deep ring per CTA
+  const uint32_t budget = occ >= 2 ? 220u * 1024u / occ - 1024u : (uint32_t)TC_MAX_DYN_SMEM - 2048u;
+  int stages = (int)(budget / per_stage);
+  if (stages < 1) stages = 1;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
   const int ksteps = p.ntaps * (p.nk1 + p.nk2);
   if (stages > ksteps) stages = ksteps;
@@ -507,11 +524,14 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr, uint32_t l
   return d;
 }
 
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapA, const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t gfull[WG_MAX_G], gempty[WG_MAX_G], afull[WG_MAX_A], aempty[WG_MAX_A];
@@ -606,6 +626,23 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
     const int n = n0 + q * 32 + lane;
     mbar_wait(smem_u32(&acc_bar), 0);
     tc_fence_after();
+    if (p.T == 2) {
+      for (int c16 = 0; c16 < p.ct; c16 += 16) {
+        uint32_t v[2][16];
+        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c16, v[0]);
+        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(p.ct + c16), v[1]);
+        tmem_ld_wait();
+        if (n < p.n_real) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + c16 + i;
+            if (c < p.c_real)
+              red_add_v2(p.dw + (long long)n * p.ld_n + (long long)c * 16 + t0, __uint_as_float(v[0][i]),
+                         __uint_as_float(v[1][i]));
+          }
+        }
+      }
+    } else
     for (int c16 = 0; c16 < p.ct; c16 += 16) {
       for (int tq = 0; tq < p.T; tq += 4) {
         uint32_t v[4][16];
@@ -650,9 +687,10 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   const int N = d->N, C = d->C1;
   p.g_box = box_of(N); p.n_atoms = 128 / p.g_box;
   p.a_box = box_of(C);
-  if (C >= 128) { p.ct = 128; p.T = 4; }
-  else if (C >= 64) { p.ct = 64; p.T = 8; }
-  else if (C >= 32) { p.ct = 32; p.T = 16; }
+  // T taps x ct channels = 256 accumulator columns, so two CTAs fit the 512 TMEM columns of an SM
+  if (C >= 128) { p.ct = 128; p.T = 2; }
+  else if (C >= 64) { p.ct = 64; p.T = 4; }
+  else if (C >= 32) { p.ct = 32; p.T = 8; }
   else { p.ct = 16; p.T = 16; }
   p.c_atoms = p.ct / p.a_box;
   p.ctiles = (C + p.ct - 1) / p.ct;
@@ -661,8 +699,8 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   p.g_boxbytes = WG_KP * p.g_rowbytes; p.a_boxbytes = WG_KP * p.a_rowbytes;
   p.g_stage_bytes = (p.n_atoms * p.g_boxbytes + 1023u) & ~1023u;
   p.a_stage_bytes = (p.c_atoms * p.a_boxbytes + 1023u) & ~1023u;
-  p.g_stages = 3;
-  int as = (int)(((uint32_t)TC_MAX_DYN_SMEM - 2048u - p.g_stages * p.g_stage_bytes) / p.a_stage_bytes);
+  p.g_stages = 2;
+  int as = (int)((110u * 1024u - p.g_stages * p.g_stage_bytes) / p.a_stage_bytes);
   if (as > WG_MAX_A) as = WG_MAX_A;
   if (as < 2) return false;
   p.a_stages = as;
@@ -673,7 +711,7 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   p.idesc = (1u << 4) | (afmt << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.ct >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
   const int gx = (N + 127) / 128, gy = p.ctiles * (16 / p.T);
-  int splits = (2 * num_sms() + gx * gy - 1) / (gx * gy);
+  int splits = (4 * num_sms() + gx * gy - 1) / (gx * gy);
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
