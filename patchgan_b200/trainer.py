@@ -50,6 +50,11 @@ class Trainer:
 
     neptune_config = None
 
+    # Replay the step as ONE CUDA graph once a (shape, mode) has been seen GRAPH_WARMUP times (the step is ~140 short
+    # launches; the host cannot keep a B200 fed).  PATCHGAN_B200_GRAPH=0 keeps eager launches.
+    use_cuda_graph = os.environ.get('PATCHGAN_B200_GRAPH', '1') != '0'
+    GRAPH_WARMUP = 2
+
     def __init__(self, generator, discriminator, savefolder, device='cuda'):
         generator.apply(weights_init)
         discriminator.apply(weights_init)
@@ -63,6 +68,7 @@ class Trainer:
             os.mkdir(savefolder)
         self.start = 1
         self._host_losses = None
+        self._graphs = {}
 
     # ------------------------------------------------------------------------------------------
     # one G+D step
@@ -179,6 +185,46 @@ class Trainer:
             dopt.step(sync_lr=False)
         return losses
 
+    def _graph_key(self, x, y, train):
+        return (tuple(x.shape), tuple(y.shape), bool(train), self.loss_type, float(self.seg_alpha),
+                float(self.tversky_beta), float(self.tversky_gamma), self.generator.training,
+                self.discriminator.training, x.device.index)
+
+    def step(self, x, y, train):
+        """step_device, replayed from a captured CUDA graph when possible.  x, y: CUDA float NCHW (contiguous).
+        Returns the device loss tensor of step_device (valid until the next call)."""
+        if not self.use_cuda_graph or dp.world_size() > 1 or L.PROFILER is not None:
+            return self.step_device(x, y, train)
+        key = self._graph_key(x, y, train)
+        ent = self._graphs.get(key)
+        if ent is None:
+            ent = self._graphs[key] = dict(seen=0, graph=None)
+        if ent['graph'] is None:
+            ent['seen'] += 1
+            if ent['seen'] <= self.GRAPH_WARMUP:
+                return self.step_device(x, y, train)
+            # capture: static input buffers; every weight pack must be part of the graph
+            ent['x'], ent['y'] = x.clone(), y.clone()
+            self.generator._engine().mark_dirty()
+            self.discriminator._engine().mark_dirty()
+            if train:
+                self.gen_optimizer.flat()
+                self.disc_optimizer.flat()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                ent['losses'] = self.step_device(ent['x'], ent['y'], train)
+            ent['graph'] = g
+            # the capture itself executed nothing: fall through to the first replay
+        ent['x'].copy_(x, non_blocking=True)
+        ent['y'].copy_(y, non_blocking=True)
+        ent['graph'].replay()
+        if train:
+            # the captured Adam kernels changed the weights behind torch's back
+            self.generator._engine().mark_dirty()
+            self.discriminator._engine().mark_dirty()
+        return ent['losses']
+
     def batch(self, x, y, train=False):
         '''
             Train the generator and discriminator on a single batch
@@ -195,7 +241,7 @@ class Trainer:
                                      "make_optimizers() first)")
             self.gen_optimizer.sync_lr()
             self.disc_optimizer.sync_lr()
-        losses = self.step_device(input_tensor, target_tensor, train)
+        losses = self.step(input_tensor, target_tensor, train)
         # one device->host copy instead of six .item() calls (trainer.py:110-111)
         if self._host_losses is None:
             self._host_losses = torch.empty(8, dtype=torch.float32, pin_memory=True)
