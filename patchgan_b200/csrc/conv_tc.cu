@@ -711,7 +711,11 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   p.idesc = (1u << 4) | (afmt << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.ct >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
   const int gx = (N + 127) / 128, gy = p.ctiles * (16 / p.T);
-  int splits = (4 * num_sms() + gx * gy - 1) / (gx * gy);
+  // Split-K over pixel tiles: every CTA ends with 128 x 256 fp32 atomics into dW, so a CTA should own enough pixel
+  // tiles (>= 8, ~1 us of MMA) to amortise them; beyond that, split until ~2 CTAs per SM exist.
+  int splits = (2 * num_sms() + gx * gy - 1) / (gx * gy);
+  const int max_splits = p.total_tiles / 8 > 0 ? p.total_tiles / 8 : 1;
+  if (splits > max_splits) splits = max_splits;
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.total_tiles + splits - 1) / splits;

@@ -63,35 +63,106 @@ __device__ __forceinline__ Span make_span(int C, long long HW, long long ppb) {
   return s;
 }
 
+// Per-block (mean, rstd) table in shared memory: C threads do the fp64 finish once instead of every thread 8 times.
+__device__ __forceinline__ void load_stats(const float* sums, int b, int C, long long HW, float* sh_mean, float* sh_rstd) {
+  for (int c = threadIdx.x; c < C; c += NT) {
+    if (sums != nullptr) mean_rstd(sums, b, C, c, HW, sh_mean[c], sh_rstd[c]);
+    else { sh_mean[c] = 0.f; sh_rstd[c] = 1.f; }
+  }
+  __syncthreads();
+}
+
+// Block-level reduction of per-thread (a1[8], a2[8]) channel partials into global pairs out[(b*C + c)*2 + {0,1}].
+// Threads that share a channel group sit cg lanes apart, so for power-of-two cg <= 32 a few shuffles leave one partial
+// per (warp, channel); the 8 warp partials are then summed by C threads.  (The first version let all 256 threads
+// atomicAdd into 2*C shared words: a 64-way same-address conflict that cost more than the HBM traffic.)
+__device__ __forceinline__ void reduce_channels(float* a1, float* a2, const Span& s, int C, float* sh, float* out, int b) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool pow2 = (s.cg & (s.cg - 1)) == 0 && s.cg <= 32;
+  if (pow2) {
+    if (!s.active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+    }
+    for (int off = s.cg; off < 32; off <<= 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += __shfl_xor_sync(0xffffffffu, a1[j], off);
+        a2[j] += __shfl_xor_sync(0xffffffffu, a2[j], off);
+      }
+    }
+    if (lane < s.cg) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sh[(warp * C + lane * 8 + j) * 2] = a1[j];
+        sh[(warp * C + lane * 8 + j) * 2 + 1] = a2[j];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += NT) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NT / 32; ++w) t += sh[w * C * 2 + i];
+      atomicAdd(&out[(long long)b * C * 2 + i], t);
+    }
+  } else {
+    for (int i = threadIdx.x; i < 2 * C; i += NT) sh[i] = 0.f;
+    __syncthreads();
+    if (s.active) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        atomicAdd(&sh[(s.my_cg * 8 + j) * 2], a1[j]);
+        atomicAdd(&sh[(s.my_cg * 8 + j) * 2 + 1], a2[j]);
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += NT) atomicAdd(&out[(long long)b * C * 2 + i], sh[i]);
+  }
+}
+// shared floats needed by reduce_channels
+static inline size_t reduce_smem(int C) {
+  const int cg = C >> 3;
+  const bool pow2 = (cg & (cg - 1)) == 0 && cg <= 32;
+  return (size_t)(pow2 ? (NT / 32) * C * 2 : 2 * C) * sizeof(float);
+}
+
+constexpr int UNR = 4;   // independent 16/32-byte loads in flight per thread
+
 // ------------------------------------------------------------------ statistics
 __global__ void __launch_bounds__(NT) instnorm_stats_kernel(const void* x, int x_f32, long long HW, int C, int ld,
                                                             float* sums, long long ppb) {
-  extern __shared__ float sh[];  // [2*C]
+  extern __shared__ float sh[];
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < 2 * C; i += NT) sh[i] = 0.f;
-  __syncthreads();
   Span s = make_span(C, HW, ppb);
-  if (s.active) {
-    float a1[8], a2[8];
+  float a1[8], a2[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
-    for (long long p = s.pbeg + s.my_pl; p < s.pend; p += s.pl) {
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+  if (s.active) {
+    const long long base = (long long)b * HW;
+    long long p = s.pbeg + s.my_pl;
+    for (; p + (UNR - 1) * s.pl < s.pend; p += UNR * s.pl) {
+      float f[UNR][8];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) load8(x, x_f32, (base + p + u * s.pl) * ld + s.my_cg * 8, f[u]);
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a1[j] += f[u][j];
+          a2[j] = fmaf(f[u][j], f[u][j], a2[j]);
+        }
+    }
+    for (; p < s.pend; p += s.pl) {
       float f[8];
-      load8(x, x_f32, ((long long)b * HW + p) * ld + s.my_cg * 8, f);
+      load8(x, x_f32, (base + p) * ld + s.my_cg * 8, f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a1[j] += f[j];
         a2[j] = fmaf(f[j], f[j], a2[j]);
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[(s.my_cg * 8 + j) * 2], a1[j]);
-      atomicAdd(&sh[(s.my_cg * 8 + j) * 2 + 1], a2[j]);
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += NT) atomicAdd(&sums[(long long)b * C * 2 + i], sh[i]);
+  reduce_channels(a1, a2, s, C, sh, sums, b);
 }
 
 // ------------------------------------------------------------------ forward apply
@@ -99,50 +170,48 @@ __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f
                                                           int y_f32, void* y2, long long HW, int C, int ldx, int ldy, int act,
                                                           float drop_p, const unsigned long long* seed_ptr, unsigned long long salt,
                                                           long long ppb) {
+  extern __shared__ float sh[];
+  float* sh_mean = sh;
+  float* sh_rstd = sh + C;
   const int b = blockIdx.y;
   const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
+  load_stats(sums, b, C, HW, sh_mean, sh_rstd);
   Span s = make_span(C, HW, ppb);
   if (!s.active) return;
   float mean[8], rstd[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (sums != nullptr) mean_rstd(sums, b, C, s.my_cg * 8 + j, HW, mean[j], rstd[j]);
-    else { mean[j] = 0.f; rstd[j] = 1.f; }
-  }
+  for (int j = 0; j < 8; ++j) { mean[j] = sh_mean[s.my_cg * 8 + j]; rstd[j] = sh_rstd[s.my_cg * 8 + j]; }
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  for (long long p = s.pbeg + s.my_pl; p < s.pend; p += s.pl) {
-    float f[8];
-    const long long pix = (long long)b * HW + p;
-    load8(x, x_f32, pix * ldx + s.my_cg * 8, f);
+  const long long base = (long long)b * HW;
+  for (long long p0 = s.pbeg + s.my_pl; p0 < s.pend; p0 += UNR * s.pl) {
+    float f[UNR][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float v = act_apply(act, (f[j] - mean[j]) * rstd[j]);
-      if (drop_p > 0.f) {
-        const float u = uniform01(seed, (unsigned long long)(pix * C + s.my_cg * 8 + j));
-        v = u >= drop_p ? v * keep_scale : 0.f;
+    for (int u = 0; u < UNR; ++u)
+      if (p0 + u * s.pl < s.pend) load8(x, x_f32, (base + p0 + u * s.pl) * ldx + s.my_cg * 8, f[u]);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const long long p = p0 + u * s.pl;
+      if (p >= s.pend) break;
+      const long long pix = base + p;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float v = act_apply(act, (f[u][j] - mean[j]) * rstd[j]);
+        if (drop_p > 0.f) {
+          const float r = uniform01(seed, (unsigned long long)(pix * C + s.my_cg * 8 + j));
+          v = r >= drop_p ? v * keep_scale : 0.f;
+        }
+        f[u][j] = v;
       }
-      f[j] = v;
+      store8(y, y_f32, pix * ldy + s.my_cg * 8, f[u]);
+      if (y2 != nullptr) store8(y2, PG_BF16, pix * ldy + s.my_cg * 8, f[u]);
     }
-    store8(y, y_f32, pix * ldy + s.my_cg * 8, f);
-    if (y2 != nullptr) store8(y2, PG_BF16, pix * ldy + s.my_cg * 8, f);
   }
 }
 
 // ------------------------------------------------------------------ backward
-// dxhat for 8 channels of one pixel
-__device__ __forceinline__ void dxhat8(const void* x, int x_f32, const void* dy1, int ld1, const void* dy2, int ld2,
-                                       long long pix, int C, int c0, int ldx, int act, float drop_p,
-                                       unsigned long long seed, const float* mean, const float* rstd, float* xhat,
-                                       float* dxh) {
-  float f[8], g[8];
-  load8(x, x_f32, pix * ldx + c0, f);
-  load8(dy1, 0, pix * ld1 + c0, g);
-  if (dy2 != nullptr) {
-    float g2[8];
-    load8(dy2, 0, pix * ld2 + c0, g2);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) g[j] += g2[j];
-  }
+// dxhat for 8 channels of one pixel, from already loaded x / dy values
+__device__ __forceinline__ void dxhat8(const float* f, float* g, long long pix, int C, int c0, int act, float drop_p,
+                                       unsigned long long seed, const float* mean, const float* rstd, float* xhat) {
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -153,9 +222,20 @@ __device__ __forceinline__ void dxhat8(const void* x, int x_f32, const void* dy1
       d = u >= drop_p ? d * keep_scale : 0.f;
     }
     xhat[j] = xh;
-    dxh[j] = d;
+    g[j] = d;
   }
 }
+__device__ __forceinline__ void load_dy(const void* dy1, int ld1, const void* dy2, int ld2, long long pix, int c0, float* g) {
+  load8(dy1, 0, pix * ld1 + c0, g);
+  if (dy2 != nullptr) {
+    float g2[8];
+    load8(dy2, 0, pix * ld2 + c0, g2);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] += g2[j];
+  }
+}
+
+constexpr int UNB = 2;
 
 __global__ void __launch_bounds__(NT) norm_act_bwd_reduce_kernel(const void* x, int x_f32, const float* sums,
                                                                  const void* dy1, int ld1, const void* dy2, int ld2,
@@ -165,34 +245,41 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_reduce_kernel(const void* x, 
   extern __shared__ float sh[];
   const int b = blockIdx.y;
   const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
-  for (int i = threadIdx.x; i < 2 * C; i += NT) sh[i] = 0.f;
-  __syncthreads();
+  load_stats(sums, b, C, HW, sh, sh + C);
   Span s = make_span(C, HW, ppb);
+  float a1[8], a2[8], mean[8], rstd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a1[j] = a2[j] = 0.f;
+    mean[j] = s.active ? sh[s.my_cg * 8 + j] : 0.f;
+    rstd[j] = s.active ? sh[C + s.my_cg * 8 + j] : 1.f;
+  }
+  __syncthreads();       // sh is reused by reduce_channels
   if (s.active) {
-    float mean[8], rstd[8], a1[8], a2[8];
+    const long long base = (long long)b * HW;
+    const int c0 = s.my_cg * 8;
+    for (long long p0 = s.pbeg + s.my_pl; p0 < s.pend; p0 += UNB * s.pl) {
+      float f[UNB][8], g[UNB][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      mean_rstd(sums, b, C, s.my_cg * 8 + j, HW, mean[j], rstd[j]);
-      a1[j] = a2[j] = 0.f;
-    }
-    for (long long p = s.pbeg + s.my_pl; p < s.pend; p += s.pl) {
-      float xh[8], d[8];
-      dxhat8(x, x_f32, dy1, ld1, dy2, ld2, (long long)b * HW + p, C, s.my_cg * 8, ldx, act, drop_p, seed, mean, rstd,
-             xh, d);
+      for (int u = 0; u < UNB; ++u)
+        if (p0 + u * s.pl < s.pend) {
+          load8(x, x_f32, (base + p0 + u * s.pl) * ldx + c0, f[u]);
+          load_dy(dy1, ld1, dy2, ld2, base + p0 + u * s.pl, c0, g[u]);
+        }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a1[j] += d[j];
-        a2[j] = fmaf(d[j], xh[j], a2[j]);
+      for (int u = 0; u < UNB; ++u) {
+        if (p0 + u * s.pl >= s.pend) break;
+        float xh[8];
+        dxhat8(f[u], g[u], base + p0 + u * s.pl, C, c0, act, drop_p, seed, mean, rstd, xh);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a1[j] += g[u][j];
+          a2[j] = fmaf(g[u][j], xh[j], a2[j]);
+        }
       }
     }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      atomicAdd(&sh[(s.my_cg * 8 + j) * 2], a1[j]);
-      atomicAdd(&sh[(s.my_cg * 8 + j) * 2 + 1], a2[j]);
-    }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < 2 * C; i += NT) atomicAdd(&bsums[(long long)b * C * 2 + i], sh[i]);
+  reduce_channels(a1, a2, s, C, sh, bsums, b);
 }
 
 __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, int x_f32, const float* sums,
@@ -201,29 +288,44 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
                                                                 int C, int ldx, int act, float drop_p,
                                                                 const unsigned long long* seed_ptr,
                                                                 unsigned long long salt, long long ppb) {
+  extern __shared__ float sh[];
   const int b = blockIdx.y;
   const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
+  load_stats(sums, b, C, HW, sh, sh + C);
   Span s = make_span(C, HW, ppb);
   if (!s.active) return;
   float mean[8], rstd[8], m1[8], m2[8];
+  const int c0 = s.my_cg * 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
+    mean[j] = sh[c0 + j];
+    rstd[j] = sh[C + c0 + j];
     if (sums != nullptr) {
-      const int c = s.my_cg * 8 + j;
-      mean_rstd(sums, b, C, c, HW, mean[j], rstd[j]);
-      m1[j] = bsums[((long long)b * C + c) * 2] / (float)HW;
-      m2[j] = bsums[((long long)b * C + c) * 2 + 1] / (float)HW;
+      m1[j] = bsums[((long long)b * C + c0 + j) * 2] / (float)HW;
+      m2[j] = bsums[((long long)b * C + c0 + j) * 2 + 1] / (float)HW;
     } else {
-      mean[j] = 0.f; rstd[j] = 1.f; m1[j] = 0.f; m2[j] = 0.f;
+      m1[j] = 0.f; m2[j] = 0.f;
     }
   }
-  for (long long p = s.pbeg + s.my_pl; p < s.pend; p += s.pl) {
-    float xh[8], d[8];
-    const long long pix = (long long)b * HW + p;
-    dxhat8(x, x_f32, dy1, ld1, dy2, ld2, pix, C, s.my_cg * 8, ldx, act, drop_p, seed, mean, rstd, xh, d);
+  const long long base = (long long)b * HW;
+  for (long long p0 = s.pbeg + s.my_pl; p0 < s.pend; p0 += UNB * s.pl) {
+    float f[UNB][8], g[UNB][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) d[j] = rstd[j] * (d[j] - m1[j] - xh[j] * m2[j]);
-    store8(dx, 0, pix * lddx + s.my_cg * 8, d);
+    for (int u = 0; u < UNB; ++u)
+      if (p0 + u * s.pl < s.pend) {
+        load8(x, x_f32, (base + p0 + u * s.pl) * ldx + c0, f[u]);
+        load_dy(dy1, ld1, dy2, ld2, base + p0 + u * s.pl, c0, g[u]);
+      }
+#pragma unroll
+    for (int u = 0; u < UNB; ++u) {
+      const long long pix = base + p0 + u * s.pl;
+      if (p0 + u * s.pl >= s.pend) break;
+      float xh[8];
+      dxhat8(f[u], g[u], pix, C, c0, act, drop_p, seed, mean, rstd, xh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[u][j] = rstd[j] * (g[u][j] - m1[j] - xh[j] * m2[j]);
+      store8(dx, 0, pix * lddx + c0, g[u]);
+    }
   }
 }
 
@@ -261,10 +363,10 @@ __global__ void softmax_fwd_kernel(const float* x, float* y, long long npix, int
 
 static void span_grid(int B, long long HW, int C, dim3& grid, long long& ppb) {
   const int pl = NT / (C >> 3);
-  long long per_img = (4LL * num_sms() + B - 1) / B;
+  long long per_img = (8LL * num_sms() + B - 1) / B;
   if (per_img < 1) per_img = 1;
   ppb = (HW + per_img - 1) / per_img;
-  if (ppb < 4LL * pl) ppb = 4LL * pl;
+  if (ppb < 1LL * pl) ppb = 1LL * pl;
   const long long nb = (HW + ppb - 1) / ppb;
   grid = dim3((unsigned)nb, (unsigned)B, 1);
 }
@@ -283,7 +385,7 @@ extern "C" int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_
   if (int e = check_c("pg_instnorm_stats", C)) return e;
   dim3 grid; long long ppb;
   span_grid(B, HW, C, grid, ppb);
-  instnorm_stats_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, HW, C, ld, sums, ppb);
+  instnorm_stats_kernel<<<grid, NT, reduce_smem(C), (cudaStream_t)stream>>>(x, x_f32, HW, C, ld, sums, ppb);
   return check_launch("instnorm_stats_kernel");
 }
 
@@ -293,7 +395,7 @@ extern "C" int pg_norm_act_fwd(const void* x, int32_t x_f32, const float* sums, 
   if (int e = check_c("pg_norm_act_fwd", C)) return e;
   dim3 grid; long long ppb;
   span_grid(B, HW, C, grid, ppb);
-  norm_act_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x, x_f32, sums, y, y_f32, y2, HW, C, ldx, ldy, act, drop_p,
+  norm_act_fwd_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, sums, y, y_f32, y2, HW, C, ldx, ldy, act, drop_p,
                                                             (const unsigned long long*)seed, salt, ppb);
   return check_launch("norm_act_fwd_kernel");
 }
@@ -306,7 +408,7 @@ extern "C" int pg_norm_act_bwd_reduce(const void* x, int32_t x_f32, const float*
   PG_REQUIRE(sums != nullptr, "pg_norm_act_bwd_reduce: sums is NULL");
   dim3 grid; long long ppb;
   span_grid(B, HW, C, grid, ppb);
-  norm_act_bwd_reduce_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(
+  norm_act_bwd_reduce_kernel<<<grid, NT, reduce_smem(C), (cudaStream_t)stream>>>(
       x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb);
   return check_launch("norm_act_bwd_reduce_kernel");
 }
@@ -318,7 +420,7 @@ extern "C" int pg_norm_act_bwd_apply(const void* x, int32_t x_f32, const float* 
   if (int e = check_c("pg_norm_act_bwd_apply", C)) return e;
   dim3 grid; long long ppb;
   span_grid(B, HW, C, grid, ppb);
-  norm_act_bwd_apply_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, dx,
+  norm_act_bwd_apply_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, dx,
                                                                   lddx, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb);
   return check_launch("norm_act_bwd_apply_kernel");
 }
