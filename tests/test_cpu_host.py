@@ -75,3 +75,31 @@ def test_transfer_learning_partial_load():
                        b.state_dict()['encoder.0.model.DownConv0.weight'])
     with pytest.raises(InvalidCheckpointError):
         P.UNet(3, 1, 16).load_transfer_data({'encoder.0.model.DownConv0.weight': torch.zeros(1)})
+
+
+def test_yaml_schemas_both_accepted():
+    """train.py reads the nested schema, infer.py / examples/train_coco.yaml the flat one."""
+    from patchgan_b200 import config as cfg
+    nested = {'model_params': {'generator': {'filters': 32, 'activation': 'relu'},
+                               'discriminator': {'filters': 16, 'n_layers': 5}},
+              'dataset': {'type': 'COCOStuff', 'labels': [1, 2, 3], 'train_data': {'images': 'a', 'masks': 'b'},
+                          'validation_data': {'images': 'c', 'masks': 'd'}}}
+    flat = {'model_params': {'gen_filts': 32, 'disc_filts': 16, 'activation': 'relu', 'use_dropout': True,
+                             'final_activation': 'sigmoid', 'n_disc_layers': 5},
+            'dataset': {'type': 'COCOStuff'}, 'train_data': {'images': 'a', 'masks': 'b'},
+            'validation_data': {'images': 'c', 'masks': 'd'}}
+    a, b = cfg.model_params(nested), cfg.model_params(flat)
+    assert a == b == dict(gen_filts=32, activation='relu', use_dropout=True, final_activation='sigmoid',
+                          disc_filts=16, disc_norm=False, n_disc_layers=5)
+    assert cfg.data_paths(nested)[0] == cfg.data_paths(flat)[0] == {'images': 'a', 'masks': 'b'}
+    cls, cin, cout, kw = cfg.dataset_class(nested['dataset'])
+    assert (cls.__name__, cin, cout, kw) == ('COCOStuffDataset', 3, 3, {'labels': [1, 2, 3]})
+    with pytest.raises(AttributeError):
+        cfg.data_paths({'dataset': {'type': 'COCOStuff'}})
+
+
+def test_console_entry_points_importable():
+    from patchgan_b200.infer import build_mask, n_crop, patchgan_infer  # noqa: F401
+    from patchgan_b200.train import patchgan_train  # noqa: F401
+    with pytest.raises(RuntimeError, match='CUDA'):
+        n_crop(torch.zeros(3, 300, 300), 128, 0.9)

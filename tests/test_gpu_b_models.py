@@ -150,3 +150,17 @@ def test_return_hidden_and_state_dict_roundtrip(tmp_path):
     torch.save(G.state_dict(), tmp_path / 'g.pth')
     sd = torch.load(tmp_path / 'g.pth')
     assert set(sd) == set(og.params) and all(tuple(sd[k].shape) == og.params[k].shape for k in sd)
+
+
+def test_infer_tiling_wrappers_match_reference_semantics():
+    """patchgan_b200.infer.n_crop / build_mask (device) vs the oracle's restatement of infer.py:14-68."""
+    from patchgan_b200.infer import build_mask, n_crop
+    r = np.random.default_rng(21)
+    img = r.random((3, 300, 300), dtype=np.float32)
+    crops = n_crop(torch.from_numpy(img).cuda(), 128, 0.9)
+    assert np.array_equal(crops.cpu().numpy(), orc.n_crop(img, 128, 0.9))
+    masks = r.random((crops.shape[0], 5, 128, 128), dtype=np.float32)
+    got = build_mask(torch.from_numpy(masks).cuda(), 128, (300, 300), 0.0, 0.9)
+    assert got.dtype == np.int64 and np.array_equal(got, orc.build_mask(masks, 128, (300, 300), 0.0, 0.9))
+    got1 = build_mask(torch.from_numpy(masks[:, :1].copy()).cuda(), 128, (300, 300), 0.5, 0.9)
+    assert np.array_equal(got1, orc.build_mask(masks[:, :1], 128, (300, 300), 0.5, 0.9))
