@@ -182,6 +182,10 @@ def run_ours(args, cfg):
     from patchgan_b200 import dp
     from patchgan_b200.engine import Config
 
+    # keep stdout clean for the single JSON line: libraries (NCCL banner, ...) write to fd 1 during the run
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = dp.init_from_env('nccl')
     if world != args.gpus and world > 1:
         raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}')
@@ -255,6 +259,12 @@ def run_ours(args, cfg):
     launches = (lib.pg_launch_count() - n0) // nprof      # kernels of this library per step (graph replays launch the same)
     L.PROFILER = None
     agg = prof.summary()
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank != 0:
         return
     if args.detail:
@@ -281,7 +291,7 @@ def run_ours(args, cfg):
                 config=dict(workload=cfg['workload'], global_batch=world * B, per_gpu_batch=B, image=S,
                             parallelism=f'dp{world}', l2='flushed (256 MB write) between timed steps',
                             conv_impl={0: 'auto', 1: 'simt', 2: 'tcgen05'}[Config.impl],
-                            cuda_graph=bool(tr.use_cuda_graph and world == 1)),
+                            cuda_graph=bool(tr.use_cuda_graph)),
                 clocks=clock_info,
                 e2e=dict(value=round(world * B * args.steps / e2e_s, 2), unit='img/s',
                          h2d_bytes_per_step=int(x_host.numel() * 4 + y_host.numel() * 4), d2h_bytes_per_step=32,

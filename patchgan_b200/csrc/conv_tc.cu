@@ -1,10 +1,14 @@
 // Implicit-GEMM 4x4 convolutions on the 5th-generation tensor cores (sm_100a):
-//   TMA (cp.async.bulk.tensor, tiled mode with element strides + zero OOB fill) -> 128B-swizzled smem
+//   TMA (cp.async.bulk.tensor, tiled mode, zero OOB fill; stride-2 layers through four phase-split views) -> swizzled smem
 //   -> tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
 //
 // No im2col is ever materialised.  For every (tap, channel-chunk) k-step the A operand is ONE TMA box of
 // the NHWC activation tensor:
-//   PG_CONV  : box {BK ch, TW*s (step s), TH*s (step s), TB} at (c, ox0*s-pad+kw, oy0*s-pad+kh, b0)
+//   PG_CONV  : stride 1: box {BK ch, TW, TH, TB} at (c, ox0-pad+kw, oy0-pad+kh, b0).  Stride 2: the input is viewed as
+//              four phase tensors X[b][2y'+ry][2x'+rx][c] (one tensor map each); tap (kh,kw) with u = kh-pad, v = kw-pad
+//              is the STRIDE-1 box at (c, ox0+floor(v/2), oy0+floor(u/2), b0) of phase (u&1, v&1).  (Element-strided
+//              boxes do the same job but the TMA engine walks them at ~3.7 ns per row, 35 GB/s per SM -- measured with
+//              tools/tma_probe.cu -- which made every stride-2 layer TMA-bound.)
 //   PG_CONVT : per output-parity class (py,px) a stride-1 box {BK, TW, TH, TB} at (c, x0+px-i, y0+py-j, b0)
 // padding = TMA out-of-bounds zero fill; the skip concat = a second tensor map (K loop walks src1 then src2).
 // The B operand is a 2D box {BK, BN} of the packed weights [N][16*Ctot].
@@ -148,9 +152,12 @@ constexpr int TC_THREADS = 192;
 constexpr int MAX_STAGES = 12;
 constexpr int TC_MAX_DYN_SMEM = 224 * 1024;
 
+struct ActMaps {
+  CUtensorMap m[8];   // [source (0/1)][phase ry*2+rx]; stride-1 layers use phase 0 only
+};
+
 __global__ void __launch_bounds__(TC_THREADS, 4)
-conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant__ CUtensorMap mapA2,
-               const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -175,8 +182,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
   const int ksteps = p.ntaps * nk;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&mapA1);
-    if (p.nk2 > 0) prefetch_tmap(&mapA2);
+    prefetch_tmap(&mapsA.m[0]);
+    if (p.nk2 > 0) prefetch_tmap(&mapsA.m[4]);
     prefetch_tmap(&mapB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
@@ -198,7 +205,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int t = 0; t < p.ntaps; ++t) {
-        int cx, cy, wtap;
+        int cx, cy, wtap, ph = 0;
         if (p.mode == PG_CONVT) {
           const int j = t >> 1, i = t & 1;
           wtap = ((1 - py) + 2 * j) * 4 + (1 - px) + 2 * i;
@@ -207,15 +214,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap mapA1, const __grid_constant_
         } else {
           const int kh = t >> 2, kw = t & 3;
           wtap = t;
-          cx = x0 * p.stride - p.pad + kw;
-          cy = y0 * p.stride - p.pad + kh;
+          if (p.stride == 2) {
+            const int u = kh - p.pad, v = kw - p.pad;       // input row = 2*oy + u
+            ph = (u & 1) * 2 + (v & 1);
+            cx = x0 + (v >> 1);                              // arithmetic shift = floor
+            cy = y0 + (u >> 1);
+          } else {
+            cx = x0 - p.pad + kw;
+            cy = y0 - p.pad + kh;
+          }
         }
         for (int ck = 0; ck < nk; ++ck) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, p.tx_bytes);
-          if (ck < p.nk1) tma_load_4d(a_base + stage * p.a_bytes, &mapA1, fb, ck * p.BK, cx, cy, b0);
-          else tma_load_4d(a_base + stage * p.a_bytes, &mapA2, fb, (ck - p.nk1) * p.BK, cx, cy, b0);
+          if (ck < p.nk1) tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[ph], fb, ck * p.BK, cx, cy, b0);
+          else tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[4 + ph], fb, (ck - p.nk1) * p.BK, cx, cy, b0);
           tma_load_2d(b_base + stage * p.b_bytes, &mapB, fb, wtap * p.Ctot + ck * p.BK, n0);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
@@ -406,8 +420,7 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
   pl.smem = (size_t)stages * per_stage + 1024;
   pl.grid = dim3((unsigned)(p.nx * p.ny * nb), (unsigned)(d->N / bn), d->mode == PG_CONVT ? 4 : 1);
   // TMA box limits
-  const int es = d->mode == PG_CONV ? d->stride : 1;
-  if (p.TW * es > 256 || p.TH * es > 256 || p.TB > 256) return false;
+  if (p.TW > 256 || p.TH > 256 || p.TB > 256) return false;
   return true;
 }
 
@@ -418,20 +431,29 @@ bool conv_fwd_tc_supported(const PgConvDesc* d, const void* src1, const void* sr
   return make_plan(d, pl);
 }
 
+// Tensor map over an NHWC activation.  phase < 0: the plain tensor {C, W, H, B}.  phase = ry*2+rx: the stride-2 phase
+// view X[b][2y'+ry][2x'+rx][c] with extents {C, ceil((W-rx)/2), ceil((H-ry)/2), B}.  Boxes are always unit-stride.
 static int encode_act_map(CUtensorMap* m, const void* base, int C, int ld, int B, int H, int W, int bk, int tw, int th,
-                          int tb, int es, int swz, int dt) {
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)(tw * es), (cuuint32_t)(th * es), (cuuint32_t)tb};
-  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+                          int tb, int phase, int swz, int dt) {
+  const int ry = phase < 0 ? 0 : (phase >> 1), rx = phase < 0 ? 0 : (phase & 1);
+  const int step = phase < 0 ? 1 : 2;
+  const int Wv = phase < 0 ? W : (W - rx + 1) / 2, Hv = phase < 0 ? H : (H - ry + 1) / 2;
+  if (Wv <= 0 || Hv <= 0) {            // degenerate phase (1-pixel-wide input): never addressed in bounds; map phase 0
+    return encode_act_map(m, base, C, ld, B, H, W, bk, tw, th, tb, phase < 0 ? -1 : 0, swz, dt);
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)step * ld * 2, (cuuint64_t)step * W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  const char* origin = (const char*)base + ((size_t)ry * W + rx) * ld * 2;
   CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                      : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = get_encode()(m, dt == PG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = get_encode()(m, dt == PG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
+                            const_cast<char*>(origin), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled(activation C=%d ld=%d B=%d H=%d W=%d box=%d,%d,%d,%d es=%d) failed: %d", C, ld, B,
-              H, W, bk, tw * es, th * es, tb, es, (int)r);
+    set_error("cuTensorMapEncodeTiled(activation C=%d ld=%d B=%d H=%d W=%d box=%d,%d,%d,%d phase=%d) failed: %d", C, ld, B,
+              H, W, bk, tw, th, tb, phase, (int)r);
     return PG_ERR_CUDA;
   }
   return PG_OK;
@@ -448,15 +470,17 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   p.bias = d->has_bias ? bias : nullptr;
   p.out = out;
   p.out2 = out2;
-  const int es = d->mode == PG_CONV ? d->stride : 1;
-  CUtensorMap mA1, mA2, mB;
-  if (int e = encode_act_map(&mA1, src1, d->C1, d->ld1, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB, es, pl.swz, d->in_dtype))
-    return e;
-  if (d->C2 > 0) {
-    if (int e = encode_act_map(&mA2, src2, d->C2, d->ld2, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB, es, pl.swz, d->in_dtype))
-      return e;
-  } else {
-    mA2 = mA1;
+  const bool phased = d->mode == PG_CONV && d->stride == 2;
+  ActMaps mA;
+  CUtensorMap mB;
+  memset(&mA, 0, sizeof(mA));
+  for (int src = 0; src < (d->C2 > 0 ? 2 : 1); ++src) {
+    const void* base = src ? src2 : src1;
+    const int C = src ? d->C2 : d->C1, ld = src ? d->ld2 : d->ld1;
+    for (int ph = 0; ph < (phased ? 4 : 1); ++ph)
+      if (int e = encode_act_map(&mA.m[src * 4 + ph], base, C, ld, d->B, d->Hin, d->Win, p.BK, p.TW, p.TH, p.TB,
+                                 phased ? ph : -1, pl.swz, d->in_dtype))
+        return e;
   }
   {
     cuuint64_t dims[2] = {(cuuint64_t)16 * p.Ctot, (cuuint64_t)d->N};
@@ -479,7 +503,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     PG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
     smem_set = true;
   }
-  conv_tc_kernel<<<pl.grid, TC_THREADS, pl.smem, stream>>>(mA1, mA2, mB, p);
+  conv_tc_kernel<<<pl.grid, TC_THREADS, pl.smem, stream>>>(mA, mB, p);
   return check_launch("conv_tc_kernel");
 }
 
@@ -532,7 +556,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ CUtensorMap mapA, const WgParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ ActMaps mapsA, const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t gfull[WG_MAX_G], gempty[WG_MAX_G], afull[WG_MAX_A], aempty[WG_MAX_A];
   __shared__ __align__(8) uint64_t acc_bar;
@@ -555,7 +579,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapG);
-    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapsA.m[0]);
     for (int s = 0; s < p.g_stages; ++s) { mbar_init(smem_u32(&gfull[s]), 1); mbar_init(smem_u32(&gempty[s]), 1); }
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), 1); }
     mbar_init(smem_u32(&acc_bar), 1);
@@ -587,9 +611,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
           mbar_wait(smem_u32(&aempty[as]), aph ^ 1);
           const uint32_t ab = smem_u32(&afull[as]);
           mbar_expect_tx(ab, p.c_atoms * p.a_boxbytes);
+          int ph = 0, cx = x0 - p.pad + kw, cy = y0 - p.pad + kh;
+          if (p.stride == 2) {
+            const int u = kh - p.pad, v = kw - p.pad;
+            ph = (u & 1) * 2 + (v & 1);
+            cx = x0 + (v >> 1);
+            cy = y0 + (u >> 1);
+          }
           for (int a = 0; a < p.c_atoms; ++a)
-            tma_load_4d(a_base + as * p.a_stage_bytes + a * p.a_boxbytes, &mapA, ab, c0 + a * p.a_box,
-                        x0 * p.stride - p.pad + kw, y0 * p.stride - p.pad + kh, b0);
+            tma_load_4d(a_base + as * p.a_stage_bytes + a * p.a_boxbytes, &mapsA.m[ph], ab, c0 + a * p.a_box, cx, cy, b0);
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
       }
@@ -683,7 +713,6 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   p.nx = (d->Wout + p.TW - 1) / p.TW; p.ny = (d->Hout + p.TH - 1) / p.TH;
   const int nb = (d->B + p.TB - 1) / p.TB;
   p.total_tiles = p.nx * p.ny * nb;
-  if (p.TW * d->stride > 256 || p.TH * d->stride > 256) return false;
   const int N = d->N, C = d->C1;
   p.g_box = box_of(N); p.n_atoms = 128 / p.g_box;
   p.a_box = box_of(C);
@@ -746,13 +775,16 @@ int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, fl
     return PG_ERR_UNSUPPORTED;
   }
   p.dw = dw; p.ld_n = ld_n; p.n_real = n_real; p.c_real = c_real;
-  CUtensorMap mG, mA;
-  if (int e = encode_act_map(&mG, g, d->N, ldg, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, 1, p.g_rowbytes,
+  CUtensorMap mG;
+  ActMaps mA;
+  memset(&mA, 0, sizeof(mA));
+  if (int e = encode_act_map(&mG, g, d->N, ldg, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, -1, p.g_rowbytes,
                              d->out_f32))
     return e;
-  if (int e = encode_act_map(&mA, a, d->C1, d->ld1, d->B, d->Hin, d->Win, p.a_box, p.TW, p.TH, p.TB, d->stride,
-                             p.a_rowbytes, d->in_dtype))
-    return e;
+  for (int ph = 0; ph < (d->stride == 2 ? 4 : 1); ++ph)
+    if (int e = encode_act_map(&mA.m[ph], a, d->C1, d->ld1, d->B, d->Hin, d->Win, p.a_box, p.TW, p.TH, p.TB,
+                               d->stride == 2 ? ph : -1, p.a_rowbytes, d->in_dtype))
+      return e;
   static bool smem_set = false;
   if (!smem_set) {
     PG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));

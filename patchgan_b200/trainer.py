@@ -193,7 +193,8 @@ class Trainer:
     def step(self, x, y, train):
         """step_device, replayed from a captured CUDA graph when possible.  x, y: CUDA float NCHW (contiguous).
         Returns the device loss tensor of step_device (valid until the next call)."""
-        if not self.use_cuda_graph or dp.world_size() > 1 or L.PROFILER is not None:
+        if not self.use_cuda_graph or L.PROFILER is not None or \
+                (dp.world_size() > 1 and os.environ.get('PATCHGAN_B200_GRAPH_DP', '1') == '0'):
             return self.step_device(x, y, train)
         key = self._graph_key(x, y, train)
         ent = self._graphs.get(key)
