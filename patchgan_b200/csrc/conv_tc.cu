@@ -78,6 +78,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -146,6 +158,10 @@ struct TcParams {
   int stages;
   uint32_t a_bytes, b_bytes, tx_bytes;
   uint32_t tmem_cols;
+  int nacc;   // independent TMEM accumulators the MMAs rotate over (summed in the epilogue)
+  int debug;  // timing experiments only: 1 = skip the MMAs, 2 = skip the TMA loads, 4 = skip the epilogue stores
+  // TMA-store epilogue: the tile is staged in (reused) ring smem as 128 rows x st_rowbytes, swizzled, st_cw columns at a time
+  int tma_store, st_rowbytes, st_cw, st_nbuf, st_twin;
 };
 
 constexpr int TC_THREADS = 192;
@@ -157,7 +173,8 @@ struct ActMaps {
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 4)
-conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB,
+               const __grid_constant__ ActMaps mapsO, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -227,6 +244,7 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
         for (int ck = 0; ck < nk; ++ck) {
           mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           const uint32_t fb = smem_u32(&full_bar[stage]);
+          if (p.debug & 2) { mbar_expect_tx(fb, 0); if (++stage == p.stages) { stage = 0; phase ^= 1; } continue; }
           mbar_expect_tx(fb, p.tx_bytes);
           if (ck < p.nk1) tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[ph], fb, ck * p.BK, cx, cy, b0);
           else tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[4 + ph], fb, (ck - p.nk1) * p.BK, cx, cy, b0);
@@ -247,8 +265,14 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
         const uint64_t adesc = make_smem_desc(a_base + stage * p.a_bytes, p.sbo, p.layout_type);
         const uint64_t bdesc = make_smem_desc(b_base + stage * p.b_bytes, p.sbo, p.layout_type);
         for (int k = 0; k < kk; ++k) {
-          // +32 bytes (16 bf16) along K inside the swizzle row: start-address field += 2
-          umma_bf16(tmem_acc, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc, (ks | k) ? 1u : 0u);
+          // +32 bytes (16 bf16) along K inside the swizzle row: start-address field += 2.
+          // Successive MMAs go to different accumulators: an MMA that accumulates into the tile of its predecessor
+          // waits for it (~115 ns each), which made small-N tiles latency-bound (0.46 us per k-step).
+          const int idx = ks * kk + k;
+          const int acc = idx % p.nacc;
+          if (p.debug & 1) continue;
+          umma_bf16(tmem_acc + (uint32_t)(acc * p.BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                    idx >= p.nacc ? 1u : 0u);
         }
         umma_commit(smem_u32(&empty_bar[stage]));
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -269,35 +293,97 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
     const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
     mbar_wait(smem_u32(&acc_bar), 0);
     tc_fence_after();
-    for (int c = 0; c < p.BN; c += 16) {
+    // 16 accumulator columns of this thread's row -> bias / activation / padding mask
+    auto load16 = [&](int c, float* f) {
       uint32_t v[16];
       tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
       tmem_ld_wait();
-      if (valid) {
-        const int n = n0 + c;
-        float f[16];
+      for (int a = 1; a < p.nacc; ++a) {
+        uint32_t w[16];
+        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.BN + c), w);
+        tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float x = __uint_as_float(v[j]);
-          if (p.bias != nullptr && n + j < p.n_valid) x += __ldg(p.bias + n + j);
-          x = act_apply(p.act, x);
-          f[j] = (n + j < p.n_valid) ? x : 0.f;
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
+      const int n = n0 + c;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float x = __uint_as_float(v[j]);
+        if (p.bias != nullptr && n + j < p.n_valid) x += __ldg(p.bias + n + j);
+        x = act_apply(p.act, x);
+        f[j] = (n + j < p.n_valid) ? x : 0.f;
+      }
+    };
+    if (p.tma_store) {
+      // ---- stage the tile in the (now idle) ring smem with the TMA swizzle, store it with cp.async.bulk.tensor:
+      //      full 128-byte rows instead of 32 scattered 16-byte stores per warp instruction; tails are clipped by TMA
+      const int et = threadIdx.x - 64;                     // 0..127 among the epilogue threads
+      const uint32_t bufbytes = 128u * (uint32_t)p.st_rowbytes;
+      const int sh = p.st_rowbytes == 128 ? 0 : (p.st_rowbytes == 64 ? 1 : 2);
+      const uint32_t xr = (uint32_t)(r >> sh) & (uint32_t)((p.st_rowbytes >> 4) - 1);   // swizzle XOR of this row
+      const int cls = blockIdx.z;
+      const int nch = p.BN / p.st_cw;
+      for (int ch = 0; ch < nch; ++ch) {
+        const int buf = ch % p.st_nbuf;
+        if (ch >= p.st_nbuf) {                              // the buffer's previous store must have been read
+          if (et == 0) { if (p.st_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+          epi_bar_sync();
         }
-        const int keep = p.ldo - n;     // channels of this 16-chunk that exist in the (possibly trimmed) output row
-        if (keep <= 0) {
-        } else if (p.out_f32 == PG_F32) {
-          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n);
+        const uint32_t prim = smem_base + (uint32_t)buf * bufbytes + (uint32_t)r * p.st_rowbytes;
+        const uint32_t twin = smem_base + (uint32_t)(p.st_nbuf + buf) * bufbytes + (uint32_t)r * p.st_rowbytes;
+        for (int sub = 0; sub < p.st_cw; sub += 16) {
+          float f[16];
+          load16(ch * p.st_cw + sub, f);
+          if (p.out_f32 == PG_F32) {
+            const uint32_t u0 = (uint32_t)(sub * 4) >> 4;
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            if (4 * j < keep) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-        } else {
-          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n);
-          o[0] = pack8dt(f, p.out_f32);
-          if (keep > 8) o[1] = pack8dt(f + 8, p.out_f32);
-          if (p.out2 != nullptr) {
-            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + opix * p.ldo + n);
-            o2[0] = pack8(f);
-            if (keep > 8) o2[1] = pack8(f + 8);
+            for (int j = 0; j < 4; ++j) {
+              uint4 v4 = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                    __float_as_uint(f[4 * j + 3]));
+              st_shared_v4(prim + (((u0 + j) ^ xr) << 4), v4);
+            }
+          } else {
+            const uint32_t u0 = (uint32_t)(sub * 2) >> 4;
+            st_shared_v4(prim + ((u0 ^ xr) << 4), pack8dt(f, p.out_f32));
+            st_shared_v4(prim + (((u0 + 1) ^ xr) << 4), pack8dt(f + 8, p.out_f32));
+            if (p.st_twin) {
+              st_shared_v4(twin + ((u0 ^ xr) << 4), pack8(f));
+              st_shared_v4(twin + (((u0 + 1) ^ xr) << 4), pack8(f + 8));
+            }
+          }
+        }
+        fence_proxy_async();
+        epi_bar_sync();
+        if (et == 0 && !(p.debug & 4)) {
+          tma_store_4d(&mapsO.m[cls], smem_base + (uint32_t)buf * bufbytes, n0 + ch * p.st_cw, x0, y0, b0);
+          if (p.st_twin)
+            tma_store_4d(&mapsO.m[4 + cls], smem_base + (uint32_t)(p.st_nbuf + buf) * bufbytes, n0 + ch * p.st_cw, x0, y0, b0);
+          bulk_commit();
+        }
+      }
+      if (et == 0) bulk_wait_read<0>();
+    } else {
+      for (int c = 0; c < p.BN; c += 16) {
+        float f[16];
+        load16(c, f);
+        if (valid && !(p.debug & 4)) {
+          const int n = n0 + c;
+          const int keep = p.ldo - n;     // channels of this 16-chunk that exist in the (possibly trimmed) output row
+          if (keep <= 0) {
+          } else if (p.out_f32 == PG_F32) {
+            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (4 * j < keep) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          } else {
+            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n);
+            o[0] = pack8dt(f, p.out_f32);
+            if (keep > 8) o[1] = pack8dt(f + 8, p.out_f32);
+            if (p.out2 != nullptr) {
+              uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + opix * p.ldo + n);
+              o2[0] = pack8(f);
+              if (keep > 8) o2[1] = pack8(f + 8);
+            }
           }
         }
       }
@@ -405,18 +491,29 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
     const int want = (int)((ctas + num_sms() - 1) / num_sms());
     if (occ > want) occ = want < 1 ? 1 : want;
   }
-  const int tmem_need = bn < 32 ? 32 : bn;
+  static const int nacc_env = [] { const char* e = getenv("PG_TC_NACC"); return e ? atoi(e) : 4; }();
+  {
+    const int total_mma = p.ntaps * (p.nk1 + p.nk2) * (bk / 16);
+    int nacc = bn <= 64 ? nacc_env : (bn == 128 ? (nacc_env >= 2 ? 2 : 1) : 1);
+    while (nacc > 1 && (nacc * bn > 256 || total_mma < 2 * nacc)) nacc >>= 1;
+    p.nacc = nacc < 1 ? 1 : nacc;
+  }
+  const int tmem_need = p.nacc * bn < 32 ? 32 : p.nacc * bn;        // (power of two: nacc and bn both are)
   if (occ * tmem_need > 512) occ = 512 / tmem_need;                 // co-resident CTAs share the 512 TMEM columns
   while (occ > 1 && (220u * 1024u / occ) / per_stage < 2) --occ;    // keep at least a 2-deep ring per CTA
   const uint32_t budget = occ >= 2 ? 220u * 1024u / occ - 1024u : (uint32_t)TC_MAX_DYN_SMEM - 2048u;
   int stages = (int)(budget / per_stage);
   if (stages < 1) stages = 1;
   if (stages > MAX_STAGES) stages = MAX_STAGES;
+  {
+    static const int st_env = [] { const char* e = getenv("PG_TC_STAGES"); return e ? atoi(e) : 0; }();
+    if (st_env > 0 && st_env < stages) stages = st_env;      // experiment knob
+  }
   const int ksteps = p.ntaps * (p.nk1 + p.nk2);
   if (stages > ksteps) stages = ksteps;
   if (stages < 1) return false;
   p.stages = stages;
-  p.tmem_cols = bn < 32 ? 32u : (uint32_t)bn;
+  p.tmem_cols = (uint32_t)tmem_need;
   pl.smem = (size_t)stages * per_stage + 1024;
   pl.grid = dim3((unsigned)(p.nx * p.ny * nb), (unsigned)(d->N / bn), d->mode == PG_CONVT ? 4 : 1);
   // TMA box limits
@@ -435,6 +532,7 @@ bool conv_fwd_tc_supported(const PgConvDesc* d, const void* src1, const void* sr
 // view X[b][2y'+ry][2x'+rx][c] with extents {C, ceil((W-rx)/2), ceil((H-ry)/2), B}.  Boxes are always unit-stride.
 static int encode_act_map(CUtensorMap* m, const void* base, int C, int ld, int B, int H, int W, int bk, int tw, int th,
                           int tb, int phase, int swz, int dt) {
+  const size_t es_ = dt == PG_F32 ? 4 : 2;
   const int ry = phase < 0 ? 0 : (phase >> 1), rx = phase < 0 ? 0 : (phase & 1);
   const int step = phase < 0 ? 1 : 2;
   const int Wv = phase < 0 ? W : (W - rx + 1) / 2, Hv = phase < 0 ? H : (H - ry + 1) / 2;
@@ -442,14 +540,15 @@ static int encode_act_map(CUtensorMap* m, const void* base, int C, int ld, int B
     return encode_act_map(m, base, C, ld, B, H, W, bk, tw, th, tb, phase < 0 ? -1 : 0, swz, dt);
   }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)Wv, (cuuint64_t)Hv, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)step * ld * 2, (cuuint64_t)step * W * ld * 2, (cuuint64_t)H * W * ld * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)step * ld * es_, (cuuint64_t)step * W * ld * es_, (cuuint64_t)H * W * ld * es_};
   cuuint32_t box[4] = {(cuuint32_t)bk, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  const char* origin = (const char*)base + ((size_t)ry * W + rx) * ld * 2;
+  const char* origin = (const char*)base + ((size_t)ry * W + rx) * ld * es_;
   CUtensorMapSwizzle sw = swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                      : (swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
-  CUresult r = get_encode()(m, dt == PG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
-                            const_cast<char*>(origin), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+  const CUtensorMapDataType cdt = dt == PG_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                               : (dt == PG_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+  CUresult r = get_encode()(m, cdt, 4, const_cast<char*>(origin), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(activation C=%d ld=%d B=%d H=%d W=%d box=%d,%d,%d,%d phase=%d) failed: %d", C, ld, B,
@@ -503,7 +602,43 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     PG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
     smem_set = true;
   }
-  conv_tc_kernel<<<pl.grid, TC_THREADS, pl.smem, stream>>>(mA, mB, p);
+  // ---- output path: TMA store of a smem-staged tile unless the output row is trimmed / tiny
+  ActMaps mO;
+  memset(&mO, 0, sizeof(mO));
+  {
+    static const int tma_st_env = [] { const char* e = getenv("PG_TC_TMA_STORE"); return e ? atoi(e) : 1; }();
+    const int esz = d->out_f32 == PG_F32 ? 4 : 2;
+    int rowbytes = p.BN * esz > 128 ? 128 : p.BN * esz;
+    const int twin = out2 != nullptr ? 1 : 0;
+    const uint32_t ring = (uint32_t)p.stages * (p.a_bytes + p.b_bytes);
+    const uint32_t need1 = 128u * rowbytes * (1 + twin);
+    p.tma_store = tma_st_env && d->ldo >= d->N && rowbytes >= 32 && ring >= need1 && ((uintptr_t)out & 15) == 0 &&
+                  (twin == 0 || ((uintptr_t)out2 & 15) == 0);
+    if (p.tma_store) {
+      p.st_rowbytes = rowbytes;
+      p.st_cw = rowbytes / esz;
+      p.st_nbuf = ring >= 2 * need1 ? 2 : 1;
+      p.st_twin = twin;
+      const bool cls = d->mode == PG_CONVT;
+      for (int ph = 0; ph < (cls ? 4 : 1); ++ph) {
+        if (int e = encode_act_map(&mO.m[ph], out, d->N, d->ldo, d->B, d->Hout, d->Wout, p.st_cw, p.TW, p.TH, p.TB,
+                                   cls ? ph : -1, rowbytes, d->out_f32))
+          return e;
+        if (twin)
+          if (int e = encode_act_map(&mO.m[4 + ph], out2, d->N, d->ldo, d->B, d->Hout, d->Wout, p.st_cw, p.TW, p.TH, p.TB,
+                                     cls ? ph : -1, rowbytes, PG_BF16))
+            return e;
+      }
+    }
+  }
+  static const int skip = [] { const char* e = getenv("PG_TC_SKIP"); return e ? atoi(e) : 0; }();
+  p.debug = skip;
+  static const bool dbg = getenv("PG_TC_DEBUG") != nullptr;
+  if (dbg)
+    fprintf(stderr, "conv_tc: grid (%u,%u,%u) BN %d BK %d stages %d nacc %d tmem %u smem %zu TW %d TH %d TB %d ksteps %d\n",
+            pl.grid.x, pl.grid.y, pl.grid.z, p.BN, p.BK, p.stages, p.nacc, p.tmem_cols, pl.smem, p.TW, p.TH, p.TB,
+            p.ntaps * (p.nk1 + p.nk2));
+  conv_tc_kernel<<<pl.grid, TC_THREADS, pl.smem, stream>>>(mA, mB, mO, p);
   return check_launch("conv_tc_kernel");
 }
 

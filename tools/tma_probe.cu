@@ -21,7 +21,9 @@ __device__ __forceinline__ bool mb_try(uint32_t b, uint32_t ph) {
 }
 __device__ __forceinline__ void mb_wait(uint32_t b, uint32_t ph) { while (!mb_try(b, ph)) {} }
 
-constexpr int STAGES = 6;
+#ifndef STAGES
+#define STAGES 6
+#endif
 
 // mode 0: 2D box {64 elem (128B), rows} ; mode 1: 4D box NHWC es=2 ; mode 2: 1-D bulk
 __global__ void __launch_bounds__(64, 1) probe(const __grid_constant__ CUtensorMap map, const uint8_t* base, int mode,
@@ -50,6 +52,12 @@ __global__ void __launch_bounds__(64, 1) probe(const __grid_constant__ CUtensorM
           const int r0 = (int)((id * rows) % span_rows);
           asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                        ::"r"(dst), "l"(&map), "r"(fb), "r"(0), "r"(r0) : "memory");
+        } else if (mode == 3) {
+          // 4D unit-stride box {64, tw, th, tb}: W = tw*8, H = th*8 tiles, walk them
+          const int tw = W, th = H, tb = rows / (W * H);
+          const long long t = id % 64;
+          asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                       ::"r"(dst), "l"(&map), "r"(fb), "r"(0), "r"((int)(t % 8) * tw), "r"((int)(t / 8) * th), "r"((int)((id / 64) % 4) * tb) : "memory");
         } else if (mode == 1) {
           // NHWC: box {64, TW*2 (es2), TH*2 (es2), 1}; walk tiles
           const int tw = 32, th = rows / 32;
@@ -133,6 +141,34 @@ int main(int argc, char** argv) {
           const double tot = (double)sms * ctas_per_sm * iters * chunk;
           printf("4D es=2 box C=%3d rows %3d: %7.1f GB/s total, %6.1f GB/s per SM, %5.2f ns per row per SM\n", C, rows,
                  tot / ms / 1e6, tot / ms / 1e6 / sms, ms * 1e6 / ((double)iters * rows));
+        }
+      }
+    }
+    // (b2) 4D unit-stride boxes of 128 rows with different shapes; pixel pitch = C*2 B (and 2x for the "phase view")
+    for (int step : {1, 2}) {
+      for (int shape = 0; shape < 5; ++shape) {
+        const int tws[5] = {128, 32, 8, 2, 1}, ths[5] = {1, 4, 8, 2, 1}, tbs[5] = {1, 1, 2, 32, 128};
+        const int tw = tws[shape], th = ths[shape], tb = tbs[shape];
+        const int C = 256, W = tw * 8, H = th * 8, B = tb * 4;
+        CUtensorMap m;
+        cuuint64_t dims[4] = {64, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)step * C * 2, (cuuint64_t)step * W * step * C * 2, (cuuint64_t)H * step * W * step * C * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)tw, (cuuint32_t)th, (cuuint32_t)tb};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, buf, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { printf("encode4d(b2) failed %d\n", (int)r); continue; }
+        const int rows = 128, chunk = rows * 128;
+        for (int rep = 0; rep < 2; ++rep) {
+          cudaEventRecord(e0);
+          probe<<<sms * ctas_per_sm, 64, STAGES * chunk + 1024>>>(m, buf, 3, rows, iters, 0, chunk, tw, th);
+          cudaEventRecord(e1); CK(cudaDeviceSynchronize());
+          float ms; cudaEventElapsedTime(&ms, e0, e1);
+          if (rep == 1) {
+            const double tot = (double)sms * ctas_per_sm * iters * chunk;
+            printf("4D unit box {64,%3d,%d,%3d} pitch x%d: %7.1f GB/s total, %6.1f GB/s per SM, %5.2f ns per row per SM\n", tw, th, tb,
+                   step, tot / ms / 1e6, tot / ms / 1e6 / sms, ms * 1e6 / ((double)iters * rows));
+          }
         }
       }
     }
