@@ -95,6 +95,9 @@ int64_t pg_launch_count(void);
 int pg_last_conv_impl(void);
 /* 1 if the library was built with the tcgen05 path and the current device is sm_100. */
 int pg_tcgen05_available(void);
+/* Debug hook (kernel tuning only): when buf != NULL every conv_tc CTA writes 8 uint64 (globaltimer ns at entry, after
+ * setup, first operands landed, last MMA issued, accumulator ready, epilogue done, exit; SM id) at buf[cta*8 ...]. */
+int pg_debug_set_trace(void* buf);
 
 /* ---- convolutions: replaces aten::convolution behind nn.Conv2d / nn.ConvTranspose2d
  *      (unet.py:19, unet.py:53, disc.py:19,27,37,45) and their autograd dgrad ---- */

@@ -35,6 +35,7 @@ bool conv_fwd_tc_supported(const PgConvDesc*, const void*, const void*, const vo
 int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
 bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int);
 bool tc_device_ok();
+void set_tc_trace(void*);
 
 static int validate(const PgConvDesc* d, const char* who) {
   PG_REQUIRE(d != nullptr, "%s: desc is NULL", who);
@@ -69,6 +70,7 @@ extern "C" int pg_version(void) { return 100; }
 extern "C" int64_t pg_launch_count(void) { return (int64_t)g_launches; }
 extern "C" int pg_last_conv_impl(void) { return g_last_impl; }
 extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
+extern "C" int pg_debug_set_trace(void* buf) { set_tc_trace(buf); return PG_OK; }
 
 extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
                            const float* bias, void* out, void* out2, int impl, void* stream) {

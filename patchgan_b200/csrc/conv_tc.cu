@@ -162,15 +162,189 @@ struct TcParams {
   int debug;  // timing experiments only: 1 = skip the MMAs, 2 = skip the TMA loads, 4 = skip the epilogue stores
   // TMA-store epilogue: the tile is staged in (reused) ring smem as 128 rows x st_rowbytes, swizzled, st_cw columns at a time
   int tma_store, st_rowbytes, st_cw, st_nbuf, st_twin;
+  unsigned long long* trace;   // debug: 8 timestamps per CTA (pg_debug_set_trace), else null
 };
 
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_put(const TcParams& p, int slot) {
+  if (p.trace != nullptr) {
+    const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+    p.trace[cta * 8 + slot] = gtimer();
+  }
+}
+
 constexpr int TC_THREADS = 192;
+#ifndef EPI_WIDE
+#define EPI_WIDE 0
+#endif
 constexpr int MAX_STAGES = 12;
 constexpr int TC_MAX_DYN_SMEM = 224 * 1024;
 
 struct ActMaps {
   CUtensorMap m[8];   // [source (0/1)][phase ry*2+rx]; stride-1 layers use phase 0 only
 };
+
+// --------------------------------------------------------------------------------------------
+// epilogue (warps 2..5): TMEM -> registers -> bias / activation / padding mask -> global
+// --------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+  if (ACT == PG_ACT_RELU) return fmaxf(x, 0.f);
+  if (ACT == PG_ACT_LEAKYRELU) return fmaxf(x, 0.2f * x);
+  if (ACT == PG_ACT_TANH) {
+    // 1 - 2 / (e^{2x} + 1): branch-free (ex2 + rcp), absolute error ~1e-7, saturates correctly at +-inf
+    return 1.f - __fdividef(2.f, __expf(2.f * x) + 1.f);
+  }
+  if (ACT == PG_ACT_SIGMOID) return __fdividef(1.f, 1.f + __expf(-x));
+  return x;
+}
+
+struct EpiCtx {
+  uint32_t smem_base, tmem_acc;
+  int x0, y0, b0, n0, py, px;
+};
+
+// U accumulator columns [c, c+U) of this thread's row (summed over the rotating accumulators) -> f[0..U)
+template <int ACT, int U>
+__device__ __forceinline__ void epi_load(const TcParams& p, uint32_t trow, int c, int n, float* f) {
+  uint32_t v[U];
+#pragma unroll
+  for (int i = 0; i < U; i += 16) tmem_ld16(trow + (uint32_t)(c + i), v + i);
+  tmem_ld_wait();
+  for (int a = 1; a < p.nacc; ++a) {
+#pragma unroll
+    for (int i = 0; i < U; i += 16) {
+      uint32_t w[16];
+      tmem_ld16(trow + (uint32_t)(a * p.BN + c + i), w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[i + j] = __float_as_uint(__uint_as_float(v[i + j]) + __uint_as_float(w[j]));
+    }
+  }
+  if (p.bias != nullptr) {
+    if (n + U <= p.n_valid) {
+#pragma unroll
+      for (int j = 0; j < U; j += 4) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
+        v[j] = __float_as_uint(__uint_as_float(v[j]) + b4.x);
+        v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + b4.y);
+        v[j + 2] = __float_as_uint(__uint_as_float(v[j + 2]) + b4.z);
+        v[j + 3] = __float_as_uint(__uint_as_float(v[j + 3]) + b4.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+        if (n + j < p.n_valid) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + n + j));
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < U; ++j) f[j] = act_fast<ACT>(__uint_as_float(v[j]));
+  if (n + U > p.n_valid) {       // zero the padded output channels
+#pragma unroll
+    for (int j = 0; j < U; ++j) f[j] = (n + j < p.n_valid) ? f[j] : 0.f;
+  }
+}
+
+template <int ACT, int U>
+__device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& mapsO, const EpiCtx& e) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;                 // TMEM lane quarter this warp may access
+  const int r = q * 32 + lane;            // accumulator row == lattice point inside the tile
+  const uint32_t trow = e.tmem_acc + ((uint32_t)(q * 32) << 16);
+  if (p.tma_store) {
+    // ---- stage the tile in the (now idle) ring smem with the TMA swizzle, store it with cp.async.bulk.tensor:
+    //      full 128-byte rows instead of 32 scattered 16-byte stores per warp instruction; tails are clipped by TMA
+    const int et = threadIdx.x - 64;                     // 0..127 among the epilogue threads
+    const uint32_t bufbytes = 128u * (uint32_t)p.st_rowbytes;
+    const int sh = p.st_rowbytes == 128 ? 0 : (p.st_rowbytes == 64 ? 1 : 2);
+    const uint32_t xr = (uint32_t)(r >> sh) & (uint32_t)((p.st_rowbytes >> 4) - 1);   // swizzle XOR of this row
+    const int cls = blockIdx.z;
+    const int nch = p.BN / p.st_cw;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int buf = ch % p.st_nbuf;
+      if (ch >= p.st_nbuf) {                              // the buffer's previous store must have been read
+        if (et == 0) { if (p.st_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+        epi_bar_sync();
+      }
+      const uint32_t prim = e.smem_base + (uint32_t)buf * bufbytes + (uint32_t)r * p.st_rowbytes;
+      const uint32_t twin = e.smem_base + (uint32_t)(p.st_nbuf + buf) * bufbytes + (uint32_t)r * p.st_rowbytes;
+      for (int sub = 0; sub < p.st_cw; sub += U) {
+        float f[U];
+        epi_load<ACT, U>(p, trow, ch * p.st_cw + sub, e.n0 + ch * p.st_cw + sub, f);
+        if (p.out_f32 == PG_F32) {
+          const uint32_t u0 = (uint32_t)(sub * 4) >> 4;
+#pragma unroll
+          for (int j = 0; j < U / 4; ++j) {
+            uint4 v4 = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
+                                  __float_as_uint(f[4 * j + 3]));
+            st_shared_v4(prim + (((u0 + j) ^ xr) << 4), v4);
+          }
+        } else {
+          const uint32_t u0 = (uint32_t)(sub * 2) >> 4;
+          if (p.out_f32 == PG_F16) {
+#pragma unroll
+            for (int j = 0; j < U / 8; ++j) st_shared_v4(prim + (((u0 + j) ^ xr) << 4), pack8h(f + 8 * j));
+          } else {
+#pragma unroll
+            for (int j = 0; j < U / 8; ++j) st_shared_v4(prim + (((u0 + j) ^ xr) << 4), pack8(f + 8 * j));
+          }
+          if (p.st_twin) {
+#pragma unroll
+            for (int j = 0; j < U / 8; ++j) st_shared_v4(twin + (((u0 + j) ^ xr) << 4), pack8(f + 8 * j));
+          }
+        }
+      }
+      fence_proxy_async();
+      epi_bar_sync();
+      if (et == 0 && !(p.debug & 4)) {
+        tma_store_4d(&mapsO.m[cls], e.smem_base + (uint32_t)buf * bufbytes, e.n0 + ch * p.st_cw, e.x0, e.y0, e.b0);
+        if (p.st_twin)
+          tma_store_4d(&mapsO.m[4 + cls], e.smem_base + (uint32_t)(p.st_nbuf + buf) * bufbytes, e.n0 + ch * p.st_cw, e.x0,
+                       e.y0, e.b0);
+        bulk_commit();
+      }
+    }
+    if (et == 0) bulk_wait_read<0>();
+  } else {
+    const int xl = r & (p.TW - 1);
+    const int yl = (r >> p.lgTW) & (p.TH - 1);
+    const int bl = r >> (p.lgTW + p.lgTH);
+    const int b = e.b0 + bl, a = e.y0 + yl, bb = e.x0 + xl;
+    const bool valid = b < p.B && a < p.Ha && bb < p.Wa;
+    int oy = a, ox = bb;
+    if (p.mode == PG_CONVT) { oy = 2 * a + e.py; ox = 2 * bb + e.px; }
+    const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
+    for (int c = 0; c < p.BN; c += U) {
+      float f[U];
+      const int n = e.n0 + c;
+      epi_load<ACT, U>(p, trow, c, n, f);
+      const int keep = p.ldo - n;     // channels of this chunk that exist in the (possibly trimmed) output row
+      if (valid && keep > 0 && !(p.debug & 4)) {
+        if (p.out_f32 == PG_F32) {
+          float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n);
+#pragma unroll
+          for (int j = 0; j < U / 4; ++j)
+            if (4 * j < keep) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n);
+#pragma unroll
+          for (int j = 0; j < U / 8; ++j)
+            if (8 * j < keep) o[j] = pack8dt(f + 8 * j, p.out_f32);
+          if (p.out2 != nullptr) {
+            uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + opix * p.ldo + n);
+#pragma unroll
+            for (int j = 0; j < U / 8; ++j)
+              if (8 * j < keep) o2[j] = pack8(f + 8 * j);
+          }
+        }
+      }
+    }
+  }
+}
 
 __global__ void __launch_bounds__(TC_THREADS, 4)
 conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB,
@@ -197,6 +371,15 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
   const int py = blockIdx.z >> 1, px = blockIdx.z & 1;
   const int nk = p.nk1 + p.nk2;
   const int ksteps = p.ntaps * nk;
+  if (threadIdx.x == 0) {
+    trace_put(p, 0);
+    if (p.trace != nullptr) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+      p.trace[cta * 8 + 7] = smid;
+    }
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapsA.m[0]);
@@ -215,6 +398,7 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_sh;
+  if (threadIdx.x == 0) trace_put(p, 1);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -262,6 +446,7 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
       for (int ks = 0; ks < ksteps; ++ks) {
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
+        if (ks == 0) trace_put(p, 2);
         const uint64_t adesc = make_smem_desc(a_base + stage * p.a_bytes, p.sbo, p.layout_type);
         const uint64_t bdesc = make_smem_desc(b_base + stage * p.b_bytes, p.sbo, p.layout_type);
         for (int k = 0; k < kk; ++k) {
@@ -278,124 +463,47 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       umma_commit(smem_u32(&acc_bar));
+      trace_put(p, 3);
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;                 // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;            // accumulator row == lattice point inside the tile
-    const int xl = r & (p.TW - 1);
-    const int yl = (r >> p.lgTW) & (p.TH - 1);
-    const int bl = r >> (p.lgTW + p.lgTH);
-    const int b = b0 + bl, a = y0 + yl, bb = x0 + xl;
-    const bool valid = b < p.B && a < p.Ha && bb < p.Wa;
-    int oy = a, ox = bb;
-    if (p.mode == PG_CONVT) { oy = 2 * a + py; ox = 2 * bb + px; }
-    const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
     mbar_wait(smem_u32(&acc_bar), 0);
     tc_fence_after();
-    // 16 accumulator columns of this thread's row -> bias / activation / padding mask
-    auto load16 = [&](int c, float* f) {
-      uint32_t v[16];
-      tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      for (int a = 1; a < p.nacc; ++a) {
-        uint32_t w[16];
-        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * p.BN + c), w);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+    if (threadIdx.x == 64) trace_put(p, 4);
+    const EpiCtx e{smem_base, tmem_acc, x0, y0, b0, n0, py, px};
+    // one uniform dispatch per CTA: the per-element code below is straight-line (4 epilogue warps = one warp per
+    // scheduler, so every branch / dependent-issue bubble of a per-element `switch` was fully exposed: 0.1 us per
+    // accumulator column before this was templated)
+    if (EPI_WIDE && p.BN >= 32) {
+      switch (p.act) {
+        case PG_ACT_RELU: tc_epilogue<PG_ACT_RELU, 32>(p, mapsO, e); break;
+        case PG_ACT_LEAKYRELU: tc_epilogue<PG_ACT_LEAKYRELU, 32>(p, mapsO, e); break;
+        case PG_ACT_TANH: tc_epilogue<PG_ACT_TANH, 32>(p, mapsO, e); break;
+        case PG_ACT_SIGMOID: tc_epilogue<PG_ACT_SIGMOID, 32>(p, mapsO, e); break;
+        default: tc_epilogue<PG_ACT_NONE, 32>(p, mapsO, e); break;
       }
-      const int n = n0 + c;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        float x = __uint_as_float(v[j]);
-        if (p.bias != nullptr && n + j < p.n_valid) x += __ldg(p.bias + n + j);
-        x = act_apply(p.act, x);
-        f[j] = (n + j < p.n_valid) ? x : 0.f;
-      }
-    };
-    if (p.tma_store) {
-      // ---- stage the tile in the (now idle) ring smem with the TMA swizzle, store it with cp.async.bulk.tensor:
-      //      full 128-byte rows instead of 32 scattered 16-byte stores per warp instruction; tails are clipped by TMA
-      const int et = threadIdx.x - 64;                     // 0..127 among the epilogue threads
-      const uint32_t bufbytes = 128u * (uint32_t)p.st_rowbytes;
-      const int sh = p.st_rowbytes == 128 ? 0 : (p.st_rowbytes == 64 ? 1 : 2);
-      const uint32_t xr = (uint32_t)(r >> sh) & (uint32_t)((p.st_rowbytes >> 4) - 1);   // swizzle XOR of this row
-      const int cls = blockIdx.z;
-      const int nch = p.BN / p.st_cw;
-      for (int ch = 0; ch < nch; ++ch) {
-        const int buf = ch % p.st_nbuf;
-        if (ch >= p.st_nbuf) {                              // the buffer's previous store must have been read
-          if (et == 0) { if (p.st_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-          epi_bar_sync();
-        }
-        const uint32_t prim = smem_base + (uint32_t)buf * bufbytes + (uint32_t)r * p.st_rowbytes;
-        const uint32_t twin = smem_base + (uint32_t)(p.st_nbuf + buf) * bufbytes + (uint32_t)r * p.st_rowbytes;
-        for (int sub = 0; sub < p.st_cw; sub += 16) {
-          float f[16];
-          load16(ch * p.st_cw + sub, f);
-          if (p.out_f32 == PG_F32) {
-            const uint32_t u0 = (uint32_t)(sub * 4) >> 4;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 v4 = make_uint4(__float_as_uint(f[4 * j]), __float_as_uint(f[4 * j + 1]), __float_as_uint(f[4 * j + 2]),
-                                    __float_as_uint(f[4 * j + 3]));
-              st_shared_v4(prim + (((u0 + j) ^ xr) << 4), v4);
-            }
-          } else {
-            const uint32_t u0 = (uint32_t)(sub * 2) >> 4;
-            st_shared_v4(prim + ((u0 ^ xr) << 4), pack8dt(f, p.out_f32));
-            st_shared_v4(prim + (((u0 + 1) ^ xr) << 4), pack8dt(f + 8, p.out_f32));
-            if (p.st_twin) {
-              st_shared_v4(twin + ((u0 ^ xr) << 4), pack8(f));
-              st_shared_v4(twin + (((u0 + 1) ^ xr) << 4), pack8(f + 8));
-            }
-          }
-        }
-        fence_proxy_async();
-        epi_bar_sync();
-        if (et == 0 && !(p.debug & 4)) {
-          tma_store_4d(&mapsO.m[cls], smem_base + (uint32_t)buf * bufbytes, n0 + ch * p.st_cw, x0, y0, b0);
-          if (p.st_twin)
-            tma_store_4d(&mapsO.m[4 + cls], smem_base + (uint32_t)(p.st_nbuf + buf) * bufbytes, n0 + ch * p.st_cw, x0, y0, b0);
-          bulk_commit();
-        }
-      }
-      if (et == 0) bulk_wait_read<0>();
     } else {
-      for (int c = 0; c < p.BN; c += 16) {
-        float f[16];
-        load16(c, f);
-        if (valid && !(p.debug & 4)) {
-          const int n = n0 + c;
-          const int keep = p.ldo - n;     // channels of this 16-chunk that exist in the (possibly trimmed) output row
-          if (keep <= 0) {
-          } else if (p.out_f32 == PG_F32) {
-            float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              if (4 * j < keep) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          } else {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n);
-            o[0] = pack8dt(f, p.out_f32);
-            if (keep > 8) o[1] = pack8dt(f + 8, p.out_f32);
-            if (p.out2 != nullptr) {
-              uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + opix * p.ldo + n);
-              o2[0] = pack8(f);
-              if (keep > 8) o2[1] = pack8(f + 8);
-            }
-          }
-        }
+      switch (p.act) {
+        case PG_ACT_RELU: tc_epilogue<PG_ACT_RELU, 16>(p, mapsO, e); break;
+        case PG_ACT_LEAKYRELU: tc_epilogue<PG_ACT_LEAKYRELU, 16>(p, mapsO, e); break;
+        case PG_ACT_TANH: tc_epilogue<PG_ACT_TANH, 16>(p, mapsO, e); break;
+        case PG_ACT_SIGMOID: tc_epilogue<PG_ACT_SIGMOID, 16>(p, mapsO, e); break;
+        default: tc_epilogue<PG_ACT_NONE, 16>(p, mapsO, e); break;
       }
     }
   }
+  if (threadIdx.x == 64) trace_put(p, 5);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, p.tmem_cols);
   }
+  if (threadIdx.x == 0) trace_put(p, 6);
 }
+
+static unsigned long long* g_trace = nullptr;
+void set_tc_trace(void* buf) { g_trace = (unsigned long long*)buf; }
 
 // --------------------------------------------------------------------------------------------
 // host side
@@ -633,6 +741,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   }
   static const int skip = [] { const char* e = getenv("PG_TC_SKIP"); return e ? atoi(e) : 0; }();
   p.debug = skip;
+  p.trace = g_trace;
   static const bool dbg = getenv("PG_TC_DEBUG") != nullptr;
   if (dbg)
     fprintf(stderr, "conv_tc: grid (%u,%u,%u) BN %d BK %d stages %d nacc %d tmem %u smem %zu TW %d TH %d TB %d ksteps %d\n",

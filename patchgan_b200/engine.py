@@ -75,19 +75,76 @@ class Act:
 
     def first(self, nb):
         """The first nb images of the batch (same storage)."""
+        return self.images(0, nb)
+
+    def images(self, b0, nb):
+        """Images b0 .. b0+nb-1 of the batch (same storage)."""
         a = Act(self.t, nb, self.H, self.W, self.C, self.ld, 0, self.dt)
-        a.ptr = self.ptr
+        a.ptr = self.ptr + b0 * self.H * self.W * self.ld * self.esize
         if self.tw is not None:
-            a.tw = self.tw.first(nb)
+            a.tw = self.tw.images(b0, nb)
         return a
+
+
+# ------------------------------------------------------------------------------------------------
+# Streams.  The step is ~140 short launches, most of them far too small to fill 148 SMs, and it contains long
+# independent chains (weight-gradients vs. the data-gradient chain; the discriminator update vs. the generator
+# backward; D(real) vs. the generator forward).  Those chains are issued on side streams that fork from / join
+# into the caller's stream (captured as parallel branches of the step's CUDA graph).  Every buffer allocated
+# during a step is kept alive until the next step begins, so the caching allocator can never hand a block
+# that a side stream is still reading to a later allocation on another stream.
+# ------------------------------------------------------------------------------------------------
+_KEEP = []
+_KEEPING = False
+_SIDE = {}
+
+
+def begin_step():
+    """Drop the previous step's buffers (all streams were joined at its end) and start keeping this step's."""
+    global _KEEPING
+    del _KEEP[:]
+    _KEEPING = True
+
+
+def end_step():
+    """Stop collecting (the collected buffers stay alive until the next begin_step)."""
+    global _KEEPING
+    _KEEPING = False
+
+
+def keep(t):
+    if _KEEPING:
+        _KEEP.append(t)
+    return t
+
+
+def side_streams(device, n=3):
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    if key not in _SIDE:
+        _SIDE[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
+    return _SIDE[key]
+
+
+def fork(side):
+    """`side` continues after everything issued so far on the current stream."""
+    side.wait_stream(torch.cuda.current_stream())
+
+
+def join(side):
+    """The current stream continues after everything issued so far on `side`."""
+    torch.cuda.current_stream().wait_stream(side)
+
+
+def zeros(shape, device, dtype=torch.float32):
+    return keep(torch.zeros(shape, device=device, dtype=dtype))
 
 
 def new_act(B, H, W, C, device, dt=BF16, zero=False, twin=False):
     fn = torch.zeros if zero else torch.empty
-    t = fn((B, H, W, C), device=device, dtype=TORCH_DT[dt])
+    t = keep(fn((B, H, W, C), device=device, dtype=TORCH_DT[dt]))
     a = Act(t, B, H, W, C, dt=dt)
     if twin and dt == F16:
-        a.tw = Act(fn((B, H, W, C), device=device, dtype=torch.bfloat16), B, H, W, C, dt=BF16)
+        a.tw = Act(keep(fn((B, H, W, C), device=device, dtype=torch.bfloat16)), B, H, W, C, dt=BF16)
     return a
 
 
@@ -106,6 +163,8 @@ class Config:
     # tcgen05 rate; fp16's 3 extra mantissa bits keep every layer within the 1e-2 activation tolerance (bf16
     # reaches 1.3-2e-2 at the 2x2 bottleneck).  Gradient tensors are always bf16 (range).
     fwd_dt = {'fp16': L.DT_F16, 'bf16': L.DT_BF16}[os.environ.get('PATCHGAN_B200_FWD_DTYPE', 'fp16')]
+    # independent chains of the step on side streams (0 = everything on the caller's stream)
+    streams = os.environ.get('PATCHGAN_B200_STREAMS', '1') != '0'
 
 
 def conv_flops(desc):
@@ -128,7 +187,13 @@ def run_conv(desc, src1, src2, w, bias, out):
            bias.data_ptr() if bias is not None else None, out.ptr, out.twptr, Config.impl, _stream())
 
 
-def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real):
+def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream=None):
+    """wstream: issue the weight-gradient on that side stream (it forks here, after its operands were produced on
+    the current stream; the caller joins it before the optimizer step)."""
+    if wstream is not None:
+        fork(wstream)
+        with torch.cuda.stream(wstream):
+            return run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real)
     if L.PROFILER is not None:
         L.PROFILER.note(conv_flops(desc), desc_tag(desc))
     L.call('pg_conv_wgrad', ctypes.byref(desc), a.ptr, g.ptr, g.ld, dw_ptr, ld_n, n_real, c_real, Config.impl, _stream())
@@ -266,15 +331,19 @@ def pack_rows(x1, x2, dst, first_image):
            dst.tw.ptr + off if dst.tw is not None else None, B, H, W, dst.ld, dst.dt, _stream())
 
 
-def norm_fwd(x, sums, out, act, drop_p, seed, salt):
+def norm_fwd(x, sums, out, act, drop_p, seed, salt, b0=0):
     HW = x.H * x.W
-    L.call('pg_norm_act_fwd', x.ptr, x.dt, sums.data_ptr() if sums is not None else None, out.ptr, out.dt, out.twptr,
+    L.call('pg_norm_act_fwd', x.ptr, x.dt, sums.data_ptr() + b0 * x.C * 8 if sums is not None else None, out.ptr, out.dt,
+           out.twptr,
            x.B, HW, x.C, x.ld, out.ld, act, drop_p, seed.data_ptr() if seed is not None else None, salt, _stream())
 
 
-def instnorm_stats(x):
-    sums = torch.zeros((x.B, x.C, 2), device=x.t.device, dtype=torch.float32)
-    L.call('pg_instnorm_stats', x.ptr, x.dt, x.B, x.H * x.W, x.C, x.ld, sums.data_ptr(), _stream())
+def instnorm_stats(x, sums=None, b0=0):
+    """(sum, sum of squares) per (image, channel); `sums` (zeroed, for the whole batch) + first image index b0 when
+    x is a batch slice."""
+    if sums is None:
+        sums = zeros((x.B, x.C, 2), x.t.device)
+    L.call('pg_instnorm_stats', x.ptr, x.dt, x.B, x.H * x.W, x.C, x.ld, sums.data_ptr() + b0 * x.C * 8, _stream())
     return sums
 
 
@@ -283,7 +352,7 @@ def norm_bwd(x, sums, dy1, dy2, act, drop_p, seed, salt):
     dev = x.t.device
     HW = x.H * x.W
     dx = new_act(x.B, x.H, x.W, x.C, dev)
-    bsums = torch.zeros((x.B, x.C, 2), device=dev, dtype=torch.float32)
+    bsums = zeros((x.B, x.C, 2), dev)
     sp = seed.data_ptr() if seed is not None else None
     p2, l2 = (dy2.ptr, dy2.ld) if dy2 is not None else (None, 0)
     st = _stream()
@@ -398,9 +467,10 @@ class GeneratorEngine(NetEngine):
             h = out
         return h, ctx
 
-    def backward(self, ctx, d_raw, grads, need_dx=False):
+    def backward(self, ctx, d_raw, grads, need_dx=False, wstream=None):
         """d_raw: bf16 Act, gradient wrt the last ConvTranspose2d's output (pre final activation).
-        grads: dict name -> zero-initialised float32 tensor in the reference layout (accumulated into)."""
+        grads: dict name -> zero-initialised float32 tensor in the reference layout (accumulated into).
+        wstream: side stream for the weight-gradient launches (off the data-gradient critical path)."""
         dev = d_raw.t.device
         B = d_raw.B
         dskip = [None] * 7
@@ -413,11 +483,11 @@ class GeneratorEngine(NetEngine):
             # weight gradient: dW[ci][co][tap] = sum x[ci] * dY[co] -- PG_CONV geometry with A = dY, G = layer input
             wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C, src1.C,
                            out_dt=BF16, in_dt=BF16)
-            run_wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.c1, s.cout)
+            run_wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.c1, s.cout, wstream)
             if src2 is not None:
                 wd2 = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src2.H, src2.W, d_raw.C, 0, d_raw.ld, 0, src2.C,
                                 src2.C, out_dt=BF16, in_dt=BF16)
-                run_wgrad(wd2, d_raw, src2.b16, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout)
+                run_wgrad(wd2, d_raw, src2.b16, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout, wstream)
             # data gradient: stride-2 conv of dY with W'[ci][tap][co]
             din = new_act(B, src1.H, src1.W, s.cinp, dev)
             run_conv(conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
@@ -440,7 +510,7 @@ class GeneratorEngine(NetEngine):
             h, raw, sums, out, dp = ctx['enc'][i]
             d_raw = norm_bwd(raw, sums, dy1, dskip[i] if i < 6 else None, L.ACT[s.act], dp, self.seed, i)
             wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16, in_dt=BF16)
-            run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
+            run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
             if i > 0 or need_dx:
                 din = new_act(B, h.H, h.W, s.cinp, dev)
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, raw.H, raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp, din.ld),
@@ -480,8 +550,14 @@ class DiscriminatorEngine(NetEngine):
 
     def forward(self, xin, save=True):
         """xin: Act (B,H,W,in_cp) bf16 -> (p: f32 Act (B,Ho,Wo,16) with the patch probabilities in channel 0, ctx)."""
+        ctx = self.forward_begin(xin, save)
+        self.forward_part(ctx, 0, xin.B)
+        return ctx[-1][3], (ctx if save else [None] * len(ctx))
+
+    def forward_begin(self, xin, save=True):
+        """Allocate every layer's buffers for the whole batch of xin; no launches except the weight pack.
+        Returns ctx = [(layer input, conv+act output, norm sums or None, layer output)] per layer."""
         self.ensure_packed()
-        ps = self.params()
         dev = xin.t.device
         B = xin.B
         ctx = []
@@ -492,30 +568,44 @@ class DiscriminatorEngine(NetEngine):
             Wo = (h.W + 2 - 4) // s.stride + 1
             if Ho < 1 or Wo < 1:
                 raise RuntimeError(f'Discriminator: input too small at layer {li} ({h.H}x{h.W})')
-            bias = ps[s.bname].detach() if s.bias else None
             if li == last:
                 out = new_act(B, Ho, Wo, 4, dev, dt=F32)                         # one real channel, stride 4
-                run_conv(conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, out.ld,
-                                   n_valid=s.cout, act=L.ACT[s.act], out_dt=F32, has_bias=1, in_dt=h.dt), h, None,
-                         self.packed[li].fwd, bias, out)
-                ctx.append((h, None, None, out) if save else None)
+                ctx.append((h, None, None, out))
             else:
                 t = new_act(B, Ho, Wo, s.np, dev, dt=h.dt, twin=save)
-                run_conv(conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, t.ld,
+                if s.norm:
+                    sums = zeros((B, s.np, 2), dev)
+                    out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt, twin=save)
+                    ctx.append((h, t, sums, out))
+                else:
+                    out = t
+                    ctx.append((h, t, None, out))
+            h = out
+        return ctx
+
+    def forward_part(self, ctx, b0, nb):
+        """Run the layers for images b0 .. b0+nb-1 on the current stream (samples are independent: the only
+        normalisation is per-sample InstanceNorm, disc.py:8)."""
+        ps = self.params()
+        last = len(self.specs) - 1
+        for li, s in enumerate(self.specs):
+            h, t, sums, out = ctx[li]
+            h, out = h.images(b0, nb), out.images(b0, nb)
+            bias = ps[s.bname].detach() if s.bias else None
+            if li == last:
+                run_conv(conv_desc(L.PG_CONV, s.stride, 1, nb, h.H, h.W, out.H, out.W, h.C, 0, h.ld, 0, s.np, out.ld,
+                                   n_valid=s.cout, act=L.ACT[s.act], out_dt=F32, has_bias=1, in_dt=h.dt), h, None,
+                         self.packed[li].fwd, bias, out)
+            else:
+                t = t.images(b0, nb)
+                run_conv(conv_desc(L.PG_CONV, s.stride, 1, nb, h.H, h.W, t.H, t.W, h.C, 0, h.ld, 0, s.np, t.ld,
                                    n_valid=s.cout, act=L.ACT[s.act], out_dt=t.dt, has_bias=int(s.bias), in_dt=h.dt), h,
                          None, self.packed[li].fwd, bias, t)
                 if s.norm:
-                    sums = instnorm_stats(t)
-                    out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt, twin=save)
-                    norm_fwd(t, sums, out, 0, 0.0, None, 0)
-                    ctx.append((h, t, sums, out) if save else None)
-                else:
-                    out = t
-                    ctx.append((h, t, None, out) if save else None)
-            h = out
-        return h, ctx
+                    instnorm_stats(t, sums, b0)
+                    norm_fwd(t, sums, out, 0, 0.0, None, 0, b0)
 
-    def backward(self, ctx, d_raw, grads, need_dx, nb=None):
+    def backward(self, ctx, d_raw, grads, need_dx, nb=None, wstream=None):
         """d_raw: bf16 Act (nb,Ho,Wo,16): gradient wrt the last conv's pre-sigmoid output.
         grads: dict of zero-initialised fp32 tensors to accumulate into, or None to skip weight gradients.
         nb: process only the first nb images of the saved batch."""
@@ -529,10 +619,11 @@ class DiscriminatorEngine(NetEngine):
             if grads is not None:
                 wd = conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, d_raw.H, d_raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
                                in_dt=BF16)
-                run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin)
+                run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
                 if s.bias:
-                    L.call('pg_colsum', d_raw.ptr, B * d_raw.H * d_raw.W, d_raw.ld, s.cout, grads[s.bname].data_ptr(),
-                           _stream())
+                    with torch.cuda.stream(wstream if wstream is not None else torch.cuda.current_stream()):
+                        L.call('pg_colsum', d_raw.ptr, B * d_raw.H * d_raw.W, d_raw.ld, s.cout,
+                               grads[s.bname].data_ptr(), _stream())
             if li > 0 or need_dx:
                 din = new_act(B, h.H, h.W, s.cinp, dev)
                 if s.stride == 2:

@@ -14,6 +14,7 @@ three autograd graphs:
   * with ``torch.distributed`` initialised, each rank steps its own shard and the flat gradient buffers are
     all-reduced over NCCL (generator all-reduce overlapped with the discriminator backward).
 """
+import contextlib
 import glob
 import os
 from collections import defaultdict
@@ -25,6 +26,7 @@ from torch.optim.lr_scheduler import ExponentialLR, ReduceLROnPlateau
 
 from . import _lib as L
 from . import dp
+from . import engine as E
 from .engine import _stream, new_act, pack_rows
 from .optim import FusedAdam
 
@@ -102,8 +104,17 @@ class Trainer:
         dev = x.device
         st = _stream()
         lt = L.LOSS[self.loss_type]
-        losses = torch.zeros(8, device=dev, dtype=torch.float32)
+        E.begin_step()
+        losses = E.zeros(8, dev)
         world = dp.world_size()
+        # Independent chains of the step run on side streams (forked from / joined into the caller's stream):
+        #   s_d: D(real) forward during the generator forward, later the whole discriminator update;
+        #   s_w: the generator's weight-gradients, off its data-gradient chain;  s_dw: the discriminator's.
+        ms = E.Config.streams and L.PROFILER is None
+        s_d, s_w, s_dw = E.side_streams(dev) if ms else (None, None, None)
+
+        def on(stream):
+            return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
 
         # ---- inputs: NCHW float -> NHWC bf16; D input = [fake batch ; real batch] with x in channels 0..cin-1
         xin = G.pack_input(x, twin=train)
@@ -120,7 +131,14 @@ class Trainer:
                 L.call('pg_pack_nchw_f32_to_nhwc_bf16', y.data_ptr(), buf.ptr + half, B, cout, H, W, buf.ld, cin, buf.dt,
                        st)
 
-        # ---- generator forward (trainer.py:63), D(cat(x, G(x))) and D(cat(x, y)) (trainer.py:65-66, 96-97)
+        # ---- D(cat(x, y)) (trainer.py:96-97) does not depend on the generator: side stream, under G's forward
+        dctx = D.forward_begin(dboth, save=train)
+        if ms:
+            E.fork(s_d)
+            with on(s_d):
+                D.forward_part(dctx, B, B)
+
+        # ---- generator forward (trainer.py:63) and D(cat(x, G(x))) (trainer.py:65-66)
         if gm.training and gm.use_dropout:
             G.ensure_packed()
             G.bump_seed()
@@ -128,16 +146,45 @@ class Trainer:
         L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.ptr, dboth.ld, cin, cout, B * H * W, dboth.dt, st)
         if dboth.tw is not None:
             L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.tw.ptr, dboth.ld, cin, cout, B * H * W, 0, st)
-        pd, dctx = D.forward(dboth, save=train)
+        if ms:
+            D.forward_part(dctx, 0, B)
+            E.join(s_d)
+        else:
+            D.forward_part(dctx, 0, 2 * B)
+        pd = dctx[-1][3]
         npatch = B * pd.H * pd.W
         pd_real_ptr = pd.ptr + npatch * pd.ld * 4
 
+        # ---- discriminator losses bce(D(fake),0), bce(D(real),1) (trainer.py:101-103) and update (:105-107):
+        #      independent of the generator update (the reference's second D(fake) forward is bit-identical to the first)
+        dz = new_act(2 * B, pd.H, pd.W, 16, dev) if train else None
+        L.call('pg_bce_const', pd.ptr, pd.ld, 0.0, 0.5, losses.data_ptr(), 3, dz.ptr if train else None, 16, npatch,
+               st)
+        L.call('pg_bce_const', pd_real_ptr, pd.ld, 1.0, 0.5, losses.data_ptr(), 2,
+               dz.ptr + npatch * 16 * 2 if train else None, 16, npatch, st)
+        d_work = None
+        if train:
+            gopt, dopt = self.gen_optimizer, self.disc_optimizer
+            gflat, dflat = gopt.flat(), dopt.flat()
+            gflat['g'].zero_()
+            dflat['g'].zero_()
+            dgrads = {n: q.grad for n, q in dm.named_parameters()}
+            if ms:
+                E.fork(s_d)
+            with on(s_d):
+                D.backward(dctx, dz, dgrads, need_dx=False, wstream=s_dw)
+                if ms:
+                    E.join(s_dw)
+                if world > 1:
+                    d_work = dp.all_reduce_sum_async(dflat['g'])
+                    dopt.grad_scale = 1.0 / world
+
         # ---- segmentation loss (trainer.py:71-82)
-        part = torch.zeros((B, 8), device=dev, dtype=torch.float32)
-        coef = torch.zeros((B, 4), device=dev, dtype=torch.float32)
+        part = E.zeros((B, 8), dev)
+        coef = E.zeros((B, 4), dev)
         chsum = None
         if lt == L.LOSS['weighted_bce']:
-            chsum = torch.zeros((B, cout), device=dev, dtype=torch.float32)
+            chsum = E.zeros((B, cout), dev)
             L.call('pg_target_chsum', y.data_ptr(), chsum.data_ptr(), B, cout, H * W, st)
         chp = chsum.data_ptr() if chsum is not None else None
         L.call('pg_seg_loss_partials', p.ptr, p.ld, y.data_ptr(), chp, part.data_ptr(), B, cout, H * W, lt, st)
@@ -148,41 +195,35 @@ class Trainer:
         dz_g = new_act(B, pd.H, pd.W, 16, dev) if train else None
         L.call('pg_bce_const', pd.ptr, pd.ld, 1.0, 1.0, losses.data_ptr(), 1, dz_g.ptr if train else None, 16,
                npatch, st)
-        g_work = None
         if train:
-            gopt, dopt = self.gen_optimizer, self.disc_optimizer
-            gflat = gopt.flat()
-            gflat['g'].zero_()
             d_dinp = D.backward(dctx, dz_g, None, need_dx=True, nb=B)
+            if ms:
+                # the discriminator's Adam step (on s_d) rewrites the weights this data-gradient chain just read
+                ev_dread = torch.cuda.Event()
+                ev_dread.record()
             d_raw = new_act(B, H, W, G.out_cp, dev)
             L.call('pg_gen_out_bwd', p.ptr, p.ld, y.data_ptr(), chp, coef.data_ptr(), d_dinp.ptr, d_dinp.ld, cin,
                    d_raw.ptr, d_raw.ld, B, cout, H * W, lt, L.ACT[gm.final_act], float(self.tversky_beta), st)
             ggrads = {n: q.grad for n, q in gm.named_parameters()}
-            G.backward(gctx, d_raw, ggrads)
+            G.backward(gctx, d_raw, ggrads, wstream=s_w)
+            if ms:
+                E.join(s_w)
             if world > 1:
                 g_work = dp.all_reduce_sum_async(gflat['g'])
                 gopt.grad_scale = 1.0 / world
-            else:
-                gopt.step(sync_lr=False)
-
-        # ---- discriminator losses (trainer.py:101-103) and update (:105-107)
-        dz = new_act(2 * B, pd.H, pd.W, 16, dev) if train else None
-        L.call('pg_bce_const', pd.ptr, pd.ld, 0.0, 0.5, losses.data_ptr(), 3, dz.ptr if train else None, 16, npatch,
-               st)
-        L.call('pg_bce_const', pd_real_ptr, pd.ld, 1.0, 0.5, losses.data_ptr(), 2,
-               dz.ptr + npatch * 16 * 2 if train else None, 16, npatch, st)
-        if train:
-            dflat = dopt.flat()
-            dflat['g'].zero_()
-            dgrads = {n: q.grad for n, q in dm.named_parameters()}
-            D.backward(dctx, dz, dgrads, need_dx=False)
-            if world > 1:
-                d_work = dp.all_reduce_sum_async(dflat['g'])
-                dopt.grad_scale = 1.0 / world
                 g_work.wait()
-                gopt.step(sync_lr=False)
-                d_work.wait()
-            dopt.step(sync_lr=False)
+            gopt.step(sync_lr=False)
+            with on(s_d):
+                if ms:
+                    s_d.wait_event(ev_dread)
+                if d_work is not None:
+                    d_work.wait()
+                dopt.step(sync_lr=False)
+                D.repack()        # 16-bit operand copies of the new weights, ready for the next step
+            G.repack()
+            if ms:
+                E.join(s_d)
+        E.end_step()
         return losses
 
     def _graph_key(self, x, y, train):
@@ -204,13 +245,14 @@ class Trainer:
             ent['seen'] += 1
             if ent['seen'] <= self.GRAPH_WARMUP:
                 return self.step_device(x, y, train)
-            # capture: static input buffers; every weight pack must be part of the graph
+            # capture: static input buffers.  The packed operand copies of the weights are brought up to date here
+            # (eagerly); inside the graph they are rebuilt right after each optimizer step.
             ent['x'], ent['y'] = x.clone(), y.clone()
-            self.generator._engine().mark_dirty()
-            self.discriminator._engine().mark_dirty()
             if train:
                 self.gen_optimizer.flat()
                 self.disc_optimizer.flat()
+            self.generator._engine().ensure_packed()
+            self.discriminator._engine().ensure_packed()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
@@ -219,11 +261,10 @@ class Trainer:
             # the capture itself executed nothing: fall through to the first replay
         ent['x'].copy_(x, non_blocking=True)
         ent['y'].copy_(y, non_blocking=True)
+        # weights changed from outside (load_state_dict, .to()) since the last step: repack before the replay
+        self.generator._engine().ensure_packed()
+        self.discriminator._engine().ensure_packed()
         ent['graph'].replay()
-        if train:
-            # the captured Adam kernels changed the weights behind torch's back
-            self.generator._engine().mark_dirty()
-            self.discriminator._engine().mark_dirty()
         return ent['losses']
 
     def batch(self, x, y, train=False):
