@@ -346,6 +346,48 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
   }
 }
 
+// --------------------------------------------------------------------------------------------
+// MMA issue loop (one thread).  A single thread retires roughly one dependent instruction every 4-6 cycles, so the
+// instruction count per tcgen05.mma IS the issue rate (tools/mma_probe.cu: 150-190 cycles per MMA with a runtime modulo
+// and descriptor rebuild in the loop, whatever N is).  Everything loop-invariant lives in registers, descriptors advance
+// by adds, the accumulator rotation is a mask, KK = MMAs per k-step is a template parameter.
+// --------------------------------------------------------------------------------------------
+template <int KK>
+__device__ __forceinline__ void mma_issue(const TcParams& p, uint64_t* full_bar, uint64_t* empty_bar, uint64_t* acc_bar,
+                                          uint32_t a_base, uint32_t b_base, uint32_t tmem_acc, int ksteps) {
+  const uint32_t idesc = p.idesc;
+  const uint32_t stages = (uint32_t)p.stages;
+  const uint32_t a_step = p.a_bytes >> 4, b_step = p.b_bytes >> 4;     // descriptor start-address units (16 B)
+  const uint64_t desc_hi = make_smem_desc(0, p.sbo, p.layout_type);     // everything but the start address
+  const uint32_t a_lo0 = (a_base & 0x3FFFF) >> 4, b_lo0 = (b_base & 0x3FFFF) >> 4;
+  const uint32_t acc_wrap = (uint32_t)(p.nacc * p.BN);                  // nacc and BN are powers of two
+  const uint32_t bn = (uint32_t)p.BN;
+  const bool skip = (p.debug & 1) != 0;
+  uint32_t a_lo = a_lo0, b_lo = b_lo0, stage = 0, phase = 0, acc_off = 0;
+  uint32_t fresh = (uint32_t)p.nacc;          // MMAs that still start their accumulator (accumulate = 0)
+  const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  for (int ks = 0; ks < ksteps; ++ks) {
+    mbar_wait(full0 + stage * 8, phase);
+    tc_fence_after();
+    if (ks == 0) trace_put(p, 2);
+    if (!skip) {
+#pragma unroll
+      for (int k = 0; k < KK; ++k) {
+        // +32 bytes (16 elements) along K inside the swizzle row: start-address field += 2
+        const uint32_t accum = fresh == 0 ? 1u : 0u;
+        umma_bf16(tmem_acc + acc_off, desc_hi | (uint64_t)(a_lo + 2 * k), desc_hi | (uint64_t)(b_lo + 2 * k), idesc, accum);
+        fresh -= accum ^ 1u;
+        acc_off += bn;
+        if (acc_off == acc_wrap) acc_off = 0;
+      }
+    }
+    umma_commit(empty0 + stage * 8);
+    a_lo += a_step; b_lo += b_step;
+    if (++stage == stages) { stage = 0; phase ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
+  }
+  umma_commit(smem_u32(acc_bar));
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 4)
 conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB,
                const __grid_constant__ ActMaps mapsO, const TcParams p) {
@@ -440,29 +482,9 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      const int kk = p.BK >> 4;
-      for (int ks = 0; ks < ksteps; ++ks) {
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
-        tc_fence_after();
-        if (ks == 0) trace_put(p, 2);
-        const uint64_t adesc = make_smem_desc(a_base + stage * p.a_bytes, p.sbo, p.layout_type);
-        const uint64_t bdesc = make_smem_desc(b_base + stage * p.b_bytes, p.sbo, p.layout_type);
-        for (int k = 0; k < kk; ++k) {
-          // +32 bytes (16 bf16) along K inside the swizzle row: start-address field += 2.
-          // Successive MMAs go to different accumulators: an MMA that accumulates into the tile of its predecessor
-          // waits for it (~115 ns each), which made small-N tiles latency-bound (0.46 us per k-step).
-          const int idx = ks * kk + k;
-          const int acc = idx % p.nacc;
-          if (p.debug & 1) continue;
-          umma_bf16(tmem_acc + (uint32_t)(acc * p.BN), adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                    idx >= p.nacc ? 1u : 0u);
-        }
-        umma_commit(smem_u32(&empty_bar[stage]));
-        if (++stage == p.stages) { stage = 0; phase ^= 1; }
-      }
-      umma_commit(smem_u32(&acc_bar));
+      if (p.BK == 64) mma_issue<4>(p, full_bar, empty_bar, &acc_bar, a_base, b_base, tmem_acc, ksteps);
+      else if (p.BK == 32) mma_issue<2>(p, full_bar, empty_bar, &acc_bar, a_base, b_base, tmem_acc, ksteps);
+      else mma_issue<1>(p, full_bar, empty_bar, &acc_bar, a_base, b_base, tmem_acc, ksteps);
       trace_put(p, 3);
     }
   } else {
@@ -870,28 +892,36 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
     }
   } else if (warp == 1) {
     if (lane == 0 && ntiles > 0) {
-      int gs = 0, as = 0;
-      uint32_t gph = 0, aph = 0;
+      // lean single-thread issue loop (see mma_issue): loop invariants in registers, descriptors advance by adds
+      const uint32_t idesc = p.idesc, T = (uint32_t)p.T, ct = (uint32_t)p.ct;
+      const uint32_t g_stages = (uint32_t)p.g_stages, a_stages = (uint32_t)p.a_stages;
+      const uint64_t g_hi = make_smem_desc_mn(0, p.g_boxbytes, 8 * p.g_rowbytes, p.g_layout);
+      const uint64_t a_hi = make_smem_desc_mn(0, p.a_boxbytes, 8 * p.a_rowbytes, p.a_layout);
+      const uint32_t g_lo0 = (g_base & 0x3FFFF) >> 4, a_lo0 = (a_base & 0x3FFFF) >> 4;
+      const uint32_t g_step = p.g_stage_bytes >> 4, a_step = p.a_stage_bytes >> 4;
+      const uint32_t gk = (16 * p.g_rowbytes) >> 4, ak = (16 * p.a_rowbytes) >> 4;   // 16 pixels (rows) further along K
+      const uint32_t gfull0 = smem_u32(gfull), gempty0 = smem_u32(gempty), afull0 = smem_u32(afull), aempty0 = smem_u32(aempty);
+      uint32_t gs = 0, as = 0, gph = 0, aph = 0, g_lo = g_lo0, a_lo = a_lo0;
+      uint32_t accum = 0;
       for (int it = 0; it < ntiles; ++it) {
-        mbar_wait(smem_u32(&gfull[gs]), gph);
+        mbar_wait(gfull0 + gs * 8, gph);
         tc_fence_after();
-        const uint64_t gdesc = make_smem_desc_mn(g_base + gs * p.g_stage_bytes, p.g_boxbytes, 8 * p.g_rowbytes, p.g_layout);
-        for (int tl = 0; tl < p.T; ++tl) {
-          mbar_wait(smem_u32(&afull[as]), aph);
+        uint32_t tcol = tmem_acc;
+        for (uint32_t tl = 0; tl < T; ++tl) {
+          mbar_wait(afull0 + as * 8, aph);
           tc_fence_after();
-          const uint64_t adesc =
-              make_smem_desc_mn(a_base + as * p.a_stage_bytes, p.a_boxbytes, 8 * p.a_rowbytes, p.a_layout);
 #pragma unroll
-          for (int k = 0; k < WG_KP / 16; ++k) {
-            // 16 pixels (rows) further along K: 16 * rowbytes
-            umma_bf16(tmem_acc + (uint32_t)(tl * p.ct), gdesc + (uint64_t)((k * 16 * p.g_rowbytes) >> 4),
-                      adesc + (uint64_t)((k * 16 * p.a_rowbytes) >> 4), p.idesc, (it | k) ? 1u : 0u);
-          }
-          umma_commit(smem_u32(&aempty[as]));
-          if (++as == p.a_stages) { as = 0; aph ^= 1; }
+          for (int k = 0; k < WG_KP / 16; ++k)
+            umma_bf16(tcol, g_hi | (uint64_t)(g_lo + k * gk), a_hi | (uint64_t)(a_lo + k * ak), idesc, (accum | k) ? 1u : 0u);
+          umma_commit(aempty0 + as * 8);
+          tcol += ct;
+          a_lo += a_step;
+          if (++as == a_stages) { as = 0; aph ^= 1; a_lo = a_lo0; }
         }
-        umma_commit(smem_u32(&gempty[gs]));
-        if (++gs == p.g_stages) { gs = 0; gph ^= 1; }
+        accum = 1;
+        umma_commit(gempty0 + gs * 8);
+        g_lo += g_step;
+        if (++gs == g_stages) { gs = 0; gph ^= 1; g_lo = g_lo0; }
       }
       umma_commit(smem_u32(&acc_bar));
     }
