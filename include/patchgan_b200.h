@@ -52,13 +52,18 @@ typedef enum PgDType {
 
 typedef enum PgConvMode {
   PG_CONV = 0,            /* nn.Conv2d(k=4, stride, pad)                          */
-  PG_CONVT = 1            /* nn.ConvTranspose2d(k=4, stride=2, pad=1)             */
+  PG_CONVT = 1,           /* nn.ConvTranspose2d(k=4, stride=2, pad=1)             */
+  PG_CONV1X1 = 2          /* pointwise: out[pix][n] = sum_c in[pix][c] * W[n][c]  (W rows at stride ldw).  Used to run the
+                             one-real-channel layers as [pixels x C] x [C x 16 taps] products (see pg_taps_scatter /
+                             pg_taps_gather) */
 } PgConvMode;
 
 typedef enum PgImpl {
   PG_IMPL_AUTO = 0,
   PG_IMPL_SIMT = 1,       /* CUDA-core implicit GEMM (any shape; validation path)  */
-  PG_IMPL_TCGEN05 = 2     /* TMA + tcgen05.mma + TMEM implicit GEMM               */
+  PG_IMPL_TCGEN05 = 2,    /* TMA + tcgen05.mma + TMEM implicit GEMM               */
+  PG_IMPL_SKINNY = 3      /* CUDA-core streaming kernels for layers with one real channel on one side (HBM-bound);
+                             PG_IMPL_AUTO picks them when the shape qualifies */
 } PgImpl;
 
 /* Geometry of one 4x4 convolution-shaped contraction.
@@ -85,6 +90,10 @@ typedef struct PgConvDesc {
   int32_t out_f32;   /* PgDType of the output: PG_BF16, PG_F32 or PG_F16 */
   int32_t has_bias;
   int32_t in_dtype;  /* PgDType of src1/src2 and of the packed weights: PG_BF16 or PG_F16 */
+  int32_t n_first;   /* only output channels [n_first, n_valid) are needed by the caller; channels below n_first may be
+                        left unwritten (0 = all).  Lets the 1-real-channel layers run as streaming kernels. */
+  int32_t c_valid;   /* real (non-padding) input channels of src1 when C2 == 0; 0 = unknown / all C1 */
+  int32_t ldw;       /* PG_CONV1X1: row stride (elements) of the weight matrix W[n][c]; 0 = C1 + C2 */
 } PgConvDesc;
 
 const char* pg_last_error(void);
@@ -95,8 +104,8 @@ int64_t pg_launch_count(void);
 int pg_last_conv_impl(void);
 /* 1 if the library was built with the tcgen05 path and the current device is sm_100. */
 int pg_tcgen05_available(void);
-/* Debug hook (kernel tuning only): when buf != NULL every conv_tc CTA writes 8 uint64 (globaltimer ns at entry, after
- * setup, first operands landed, last MMA issued, accumulator ready, epilogue done, exit; SM id) at buf[cta*8 ...]. */
+/* Debug hook (kernel tuning only): when buf != NULL every conv_tc CTA writes 16 uint64 (globaltimer ns at entry, after
+ * setup, first operands landed, last MMA issued, accumulator ready, epilogue done, exit; SM id) at buf[cta*16 ...]. */
 int pg_debug_set_trace(void* buf);
 
 /* ---- convolutions: replaces aten::convolution behind nn.Conv2d / nn.ConvTranspose2d
@@ -111,11 +120,28 @@ int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const v
  *   dw[n*ld_n + c*16 + tap] += sum_{b,oy,ox} g[b,oy,ox,n] * a[b, oy*s-p+kh, ox*s-p+kw, c]
  * g: [B,Hout,Wout] x N (stride ldg), a: [B,Hin,Win] x C1 (stride ld1).  Only n < n_real, c < c_real are
  * written.  Accumulates atomically into dw (caller zeroes).  For ConvTranspose2d swap the roles:
- * a = dY (2H x 2W), g = layer input.  `ws` = float workspace (>= pg_conv_wgrad_ws_bytes) or NULL. */
+ * a = dY (2H x 2W), g = layer input.
+ * PG_CONV1X1 (pointwise): dw[n*ld_n + c*d->ldw] += sum_pix g[pix,n] * a[pix,c]. */
 int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw,
                   int32_t ld_n, int32_t n_real, int32_t c_real, int impl, void* stream);
 /* (d->in_dtype is the type of `a`; d->out_f32 is reused as the PgDType of `g`: PG_BF16 or PG_F16; the tcgen05
  * implementation needs both to be the same type) */
+
+/* ---- layers with ONE real channel on one side (generator output ConvTranspose2d(2nf -> 1), unet.py:106-107;
+ *      discriminator last Conv2d(8ndf -> 1), disc.py:45; the mask-channel data-gradient of the discriminator's first
+ *      layer, trainer.py:84-89).  They run as pointwise (PG_CONV1X1) products over the 16 taps on the tensor cores:
+ *        forward        P[q][tap] = sum_c in[q][c] W[tap][c];   out[p] = act(bias + sum_tap P[q(p,tap)][tap])   (scatter)
+ *        data-gradient  G[q][tap] = dy[p(q,tap)]  (gather);     dx[q][c] = sum_tap G[q][tap] W[c][tap]
+ *        weight-grad.   dW[c][tap] = sum_q in[q][c] G[q][tap]    (pg_conv_wgrad with PG_CONV1X1, ld_n = 1, ldw = 16)
+ *      q = pixel of the wide tensor (Hq x Wq), p = pixel of the 1-channel tensor (Hp x Wp).  mode / stride / pad are
+ *      the layer's: PG_CONV: q = p*stride - pad + k;  PG_CONVT: p = 2q - 1 + k. ---- */
+/* P: f32 [B,Hq,Wq,ldp] (taps in channels 0..15) -> element `ch` of out [B,Hp,Wp,ldo] (PgDType out_dtype); bias: 1 float or NULL */
+int pg_taps_scatter(int32_t mode, int32_t stride, int32_t pad, int32_t B, int32_t Hq, int32_t Wq, int32_t Hp, int32_t Wp,
+                    const float* P, int32_t ldp, const float* bias, int32_t act, void* out, int32_t out_dtype, int32_t ldo,
+                    int32_t ch, void* stream);
+/* element `ch` of the 16-bit src [B,Hp,Wp,lds] -> G [B,Hq,Wq,16] of the same 16-bit type (zeros where the tap falls outside) */
+int pg_taps_gather(int32_t mode, int32_t stride, int32_t pad, int32_t B, int32_t Hq, int32_t Wq, int32_t Hp, int32_t Wp,
+                   const void* src, int32_t lds, int32_t ch, void* G, void* stream);
 
 /* bias gradient: db[n] += sum_m g[m*ldg + n], n < n_real (disc.py:19,45 biases) */
 int pg_colsum(const void* g, int64_t M, int32_t ldg, int32_t n_real, float* db, void* stream);

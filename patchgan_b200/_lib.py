@@ -9,9 +9,9 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libpatchgan_b200.so')
 
-PG_CONV, PG_CONVT = 0, 1
+PG_CONV, PG_CONVT, PG_CONV1X1 = 0, 1, 2
 ACT = {'none': 0, None: 0, 'relu': 1, 'leakyrelu': 2, 'tanh': 3, 'sigmoid': 4, 'softmax': 5}
-IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05 = 0, 1, 2
+IMPL_AUTO, IMPL_SIMT, IMPL_TCGEN05, IMPL_SKINNY = 0, 1, 2, 3
 DT_BF16, DT_F32, DT_F16 = 0, 1, 2
 LOSS = {'tversky': 0, 'weighted_bce': 1, 'MAE': 2, 'none': 3}
 
@@ -19,7 +19,7 @@ LOSS = {'tversky': 0, 'weighted_bce': 1, 'MAE': 2, 'none': 3}
 class ConvDesc(C.Structure):
     _fields_ = [(n, C.c_int32) for n in (
         'mode', 'stride', 'pad', 'B', 'Hin', 'Win', 'Hout', 'Wout', 'C1', 'C2', 'ld1', 'ld2', 'N', 'ldo',
-        'n_valid', 'act', 'out_f32', 'has_bias', 'in_dtype')]
+        'n_valid', 'act', 'out_f32', 'has_bias', 'in_dtype', 'n_first', 'c_valid', 'ldw')]
 
 
 vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
@@ -34,6 +34,8 @@ _SIGS = {
     'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_wgrad': ([DP, vp, vp, i32, vp, i32, i32, i32, C.c_int, vp], C.c_int),
     'pg_colsum': ([vp, i64, i32, i32, vp, vp], C.c_int),
+    'pg_taps_scatter': ([i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp], C.c_int),
+    'pg_taps_gather': ([i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp], C.c_int),
     'pg_pack_nchw_f32_to_nhwc_bf16': ([vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], C.c_int),
     'pg_unpack_nhwc_to_nchw_f32': ([vp, i32, vp, i32, i32, i32, i32, i32, i32, vp], C.c_int),
     'pg_copy_f32_to_bf16_slice': ([vp, i32, vp, i32, i32, i32, i64, i32, vp], C.c_int),

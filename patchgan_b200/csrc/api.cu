@@ -36,10 +36,19 @@ int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int,
 bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int);
 bool tc_device_ok();
 void set_tc_trace(void*);
+// conv_skinny.cu
+bool conv_fewout_supported(const PgConvDesc*);
+int conv_fewout(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, cudaStream_t);
+bool conv_fewin_supported(const PgConvDesc*);
+int conv_fewin(const PgConvDesc*, const void*, const void*, void*, void*, cudaStream_t);
+int taps_scatter(int, int, int, int, int, int, int, int, const float*, int, const float*, int, void*, int, int, int, cudaStream_t);
+int taps_gather(int, int, int, int, int, int, int, int, const void*, int, int, void*, cudaStream_t);
+bool conv_wgrad1_supported(const PgConvDesc*, int, const float*, int, int, int);
+int conv_wgrad1(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
 
 static int validate(const PgConvDesc* d, const char* who) {
   PG_REQUIRE(d != nullptr, "%s: desc is NULL", who);
-  PG_REQUIRE(d->mode == PG_CONV || d->mode == PG_CONVT, "%s: bad mode %d", who, d->mode);
+  PG_REQUIRE(d->mode == PG_CONV || d->mode == PG_CONVT || d->mode == PG_CONV1X1, "%s: bad mode %d", who, d->mode);
   PG_REQUIRE(d->B > 0 && d->Hin > 0 && d->Win > 0 && d->Hout > 0 && d->Wout > 0, "%s: empty extent", who);
   PG_REQUIRE(d->C1 > 0 && d->C1 % 16 == 0 && d->C2 >= 0 && d->C2 % 16 == 0, "%s: C1=%d C2=%d must be multiples of 16",
              who, d->C1, d->C2);
@@ -51,7 +60,12 @@ static int validate(const PgConvDesc* d, const char* who) {
              "%s: bad output stride %d", who, d->ldo);
   PG_REQUIRE(d->in_dtype == PG_BF16 || d->in_dtype == PG_F16, "%s: in_dtype must be PG_BF16 or PG_F16", who);
   PG_REQUIRE(d->out_f32 >= PG_BF16 && d->out_f32 <= PG_F16, "%s: bad output dtype %d", who, d->out_f32);
-  if (d->mode == PG_CONV) {
+  PG_REQUIRE(d->n_first >= 0 && d->n_first < d->n_valid && d->c_valid >= 0 && d->c_valid <= d->C1,
+             "%s: bad n_first=%d / c_valid=%d", who, d->n_first, d->c_valid);
+  if (d->mode == PG_CONV1X1) {
+    PG_REQUIRE(d->Hout == d->Hin && d->Wout == d->Win && d->ldw >= 0 && d->ldw % 8 == 0,
+               "%s: pointwise needs Hout = Hin, Wout = Win, ldw %% 8 == 0", who);
+  } else if (d->mode == PG_CONV) {
     PG_REQUIRE((d->stride == 1 || d->stride == 2) && (d->pad == 1 || d->pad == 2), "%s: stride/pad unsupported", who);
     PG_REQUIRE(d->Hout == (d->Hin + 2 * d->pad - 4) / d->stride + 1 && d->Wout == (d->Win + 2 * d->pad - 4) / d->stride + 1,
                "%s: Hout/Wout inconsistent with Hin/Win", who);
@@ -81,6 +95,22 @@ extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* sr
   g_last_impl = PG_IMPL_SIMT;
   PG_REQUIRE(out2 == nullptr || d->out_f32 != PG_F32, "pg_conv_fwd: out2 (bf16 twin) needs a 16-bit primary output");
   if (impl == PG_IMPL_SIMT) return conv_fwd_simt(d, src1, src2, w_packed, bias, out, out2, s);
+  if (impl == PG_IMPL_SKINNY) {
+    // CUDA-core kernels for one real channel on one side (kept as a second implementation for validation; the
+    // engine runs these layers as PG_CONV1X1 tap products on the tensor cores, which is faster)
+    if (out2 == nullptr && conv_fewout_supported(d)) {
+      g_last_impl = PG_IMPL_SKINNY;
+      return conv_fewout(d, src1, src2, w_packed, bias, out, s);
+    }
+    if (conv_fewin_supported(d)) {
+      g_last_impl = PG_IMPL_SKINNY;
+      return conv_fewin(d, src1, w_packed, out, out2, s);
+    }
+    if (impl == PG_IMPL_SKINNY) {
+      set_error("pg_conv_fwd: shape does not qualify for the skinny kernels");
+      return PG_ERR_UNSUPPORTED;
+    }
+  }
   const bool ok = conv_fwd_tc_supported(d, src1, src2, w_packed, out);
   if (ok) g_last_impl = PG_IMPL_TCGEN05;
   if (impl == PG_IMPL_TCGEN05) {
@@ -94,15 +124,42 @@ extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* sr
   return conv_fwd_simt(d, src1, src2, w_packed, bias, out, out2, s);
 }
 
+extern "C" int pg_taps_scatter(int32_t mode, int32_t stride, int32_t pad, int32_t B, int32_t Hq, int32_t Wq, int32_t Hp, int32_t Wp,
+                               const float* P, int32_t ldp, const float* bias, int32_t act, void* out, int32_t out_dtype,
+                               int32_t ldo, int32_t ch, void* stream) {
+  PG_REQUIRE(P && out && B > 0 && Hq > 0 && Wq > 0 && Hp > 0 && Wp > 0 && ldp >= 16, "pg_taps_scatter: bad arguments");
+  PG_REQUIRE(mode == PG_CONV || mode == PG_CONVT, "pg_taps_scatter: bad mode %d", mode);
+  return taps_scatter(mode, stride, pad, B, Hq, Wq, Hp, Wp, P, ldp, bias, act, out, out_dtype, ldo, ch, (cudaStream_t)stream);
+}
+
+extern "C" int pg_taps_gather(int32_t mode, int32_t stride, int32_t pad, int32_t B, int32_t Hq, int32_t Wq, int32_t Hp, int32_t Wp,
+                              const void* src, int32_t lds, int32_t ch, void* G, void* stream) {
+  PG_REQUIRE(src && G && B > 0 && Hq > 0 && Wq > 0 && Hp > 0 && Wp > 0, "pg_taps_gather: bad arguments");
+  PG_REQUIRE(mode == PG_CONV || mode == PG_CONVT, "pg_taps_gather: bad mode %d", mode);
+  PG_REQUIRE((((uintptr_t)G) & 15) == 0, "pg_taps_gather: G must be 16-byte aligned");
+  return taps_gather(mode, stride, pad, B, Hq, Wq, Hp, Wp, src, lds, ch, G, (cudaStream_t)stream);
+}
+
 extern "C" int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw, int32_t ld_n,
                              int32_t n_real, int32_t c_real, int impl, void* stream) {
   if (int e = validate(d, "pg_conv_wgrad")) return e;
-  PG_REQUIRE(d->mode == PG_CONV && d->C2 == 0, "pg_conv_wgrad: geometry must be PG_CONV with one source");
+  PG_REQUIRE((d->mode == PG_CONV || d->mode == PG_CONV1X1) && d->C2 == 0,
+             "pg_conv_wgrad: geometry must be PG_CONV / PG_CONV1X1 with one source");
   PG_REQUIRE(a && g && dw && ldg >= d->N && ldg % 8 == 0, "pg_conv_wgrad: bad pointers / ldg");
   PG_REQUIRE(n_real <= d->N && c_real <= d->C1, "pg_conv_wgrad: n_real / c_real exceed padded extents");
   cudaStream_t s = (cudaStream_t)stream;
   g_last_impl = PG_IMPL_SIMT;
   if (impl == PG_IMPL_SIMT) return conv_wgrad_simt(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
+  if (impl == PG_IMPL_SKINNY) {
+    if (conv_wgrad1_supported(d, ldg, dw, ld_n, n_real, c_real)) {
+      g_last_impl = PG_IMPL_SKINNY;
+      return conv_wgrad1(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
+    }
+    if (impl == PG_IMPL_SKINNY) {
+      set_error("pg_conv_wgrad: shape does not qualify for the skinny kernels");
+      return PG_ERR_UNSUPPORTED;
+    }
+  }
   const bool ok = conv_wgrad_tc_supported(d, a, g, ldg);
   if (ok) g_last_impl = PG_IMPL_TCGEN05;
   if (impl == PG_IMPL_TCGEN05) {

@@ -12,6 +12,7 @@ struct ConvK {
   void* out;
   void* out2;
   int mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo, n_valid, act, out_f32, in_dt;
+  long long wrow;   // elements between the weight rows of consecutive n
   int Ha, Wa;  // lattice the tiles walk: PG_CONV -> (Hout, Wout); PG_CONVT -> (Hin, Win) per parity class
   long long M;
 };
@@ -25,7 +26,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvK p) {
   const long long m0 = (long long)blockIdx.x * TM;
   const int n0 = blockIdx.y * TN;
   const int py = blockIdx.z >> 1, px = blockIdx.z & 1;
-  const int ntaps = p.mode == PG_CONVT ? 4 : 16;
+  const int ntaps = p.mode == PG_CONVT ? 4 : (p.mode == PG_CONV1X1 ? 1 : 16);
   const int Ctot = p.C1 + p.C2;
 
   const int lrow = tid >> 2, lkq = tid & 3;
@@ -53,6 +54,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvK p) {
       iy = la + py - j;
       ix = lbb + px - i;
       wtap = kh * 4 + kw;
+    } else if (p.mode == PG_CONV1X1) {
+      iy = la; ix = lbb; wtap = 0;
     } else {
       const int kh = t >> 2, kw = t & 3;
       iy = la * p.stride - p.pad + kh;
@@ -69,7 +72,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvK p) {
         else av = *reinterpret_cast<const uint4*>(p.src2 + pix * p.ld2 + (c - p.C1));
       }
       if (n0 + lrow < p.N && c < Ctot)
-        wv = *reinterpret_cast<const uint4*>(p.w + ((long long)(n0 + lrow) * 16 + wtap) * Ctot + c);
+        wv = *reinterpret_cast<const uint4*>(p.w + (long long)(n0 + lrow) * p.wrow + (long long)wtap * Ctot + c);
       float af[8], wf[8];
       unpack8dt(av, p.in_dt, af);
       unpack8dt(wv, p.in_dt, wf);
@@ -148,6 +151,7 @@ int conv_fwd_simt(const PgConvDesc* d, const void* src1, const void* src2, const
   p.Hout = d->Hout; p.Wout = d->Wout; p.C1 = d->C1; p.C2 = d->C2; p.ld1 = d->ld1; p.ld2 = d->ld2;
   p.N = d->N; p.ldo = d->ldo; p.n_valid = d->n_valid; p.act = d->act; p.out_f32 = d->out_f32;
   p.in_dt = d->in_dtype;
+  p.wrow = d->mode == PG_CONV1X1 ? (d->ldw > 0 ? d->ldw : d->C1 + d->C2) : 16LL * (d->C1 + d->C2);
   if (d->mode == PG_CONVT) { p.Ha = d->Hin; p.Wa = d->Win; } else { p.Ha = d->Hout; p.Wa = d->Wout; }
   p.M = (long long)d->B * p.Ha * p.Wa;
   dim3 grid((unsigned)((p.M + TM - 1) / TM), (unsigned)((d->N + TN - 1) / TN), d->mode == PG_CONVT ? 4 : 1);
@@ -162,7 +166,7 @@ struct WgradK {
   const bf16* a;
   const bf16* g;
   float* dw;
-  int stride, pad, B, Hin, Win, Hout, Wout, C, lda, N, ldg, ld_n, n_real, c_real, a_dt, g_dt;
+  int stride, pad, B, Hin, Win, Hout, Wout, C, lda, N, ldg, ld_n, n_real, c_real, a_dt, g_dt, pointwise, ld_c;
   long long M;
   int chunk;  // pixels per split
   int ctiles;
@@ -199,7 +203,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradK p) {
       const int b = (int)(r / p.Hout);
       const int n = n0 + lq * 8;
       if (n < p.N) gv = *reinterpret_cast<const uint4*>(p.g + m * p.ldg + n);
-      const int iy = oy * p.stride - p.pad + kh, ix = ox * p.stride - p.pad + kw;
+      const int iy = p.pointwise ? oy : oy * p.stride - p.pad + kh, ix = p.pointwise ? ox : ox * p.stride - p.pad + kw;
       const int c = c0 + lq * 8;
       if (c < p.C && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
         av = *reinterpret_cast<const uint4*>(p.a + (((long long)b * p.Hin + iy) * p.Win + ix) * p.lda + c);
@@ -234,7 +238,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradK p) {
     for (int j = 0; j < 4; ++j) {
       const int c = c0 + tx * 4 + j;
       if (c >= p.c_real) continue;
-      atomicAdd(p.dw + (long long)n * p.ld_n + (long long)c * 16 + t, acc[i][j]);
+      atomicAdd(p.dw + (long long)n * p.ld_n + (long long)c * p.ld_c + t, acc[i][j]);
     }
   }
 }
@@ -247,10 +251,13 @@ int conv_wgrad_simt(const PgConvDesc* d, const void* a, const void* g, int ldg, 
   p.Wout = d->Wout; p.C = d->C1; p.lda = d->ld1; p.N = d->N; p.ldg = ldg; p.ld_n = ld_n;
   p.n_real = n_real; p.c_real = c_real;
   p.a_dt = d->in_dtype; p.g_dt = d->out_f32;
+  p.pointwise = d->mode == PG_CONV1X1 ? 1 : 0;
+  p.ld_c = p.pointwise ? (d->ldw > 0 ? d->ldw : 16) : 16;
+  const int taps = p.pointwise ? 1 : 16;
   p.M = (long long)d->B * d->Hout * d->Wout;
   const int ntiles = (d->N + 63) / 64;
   p.ctiles = (d->C1 + 63) / 64;
-  const int base = ntiles * p.ctiles * 16;
+  const int base = ntiles * p.ctiles * taps;
   long long splits = (4LL * num_sms() + base - 1) / base;
   const long long maxsplits = (p.M + 255) / 256;
   if (splits > maxsplits) splits = maxsplits;
@@ -259,7 +266,7 @@ int conv_wgrad_simt(const PgConvDesc* d, const void* a, const void* g, int ldg, 
   chunk = (chunk + WK - 1) / WK * WK;
   splits = (p.M + chunk - 1) / chunk;
   p.chunk = (int)chunk;
-  dim3 grid(ntiles * p.ctiles, 16, (unsigned)splits);
+  dim3 grid(ntiles * p.ctiles, taps, (unsigned)splits);
   wgrad_simt_kernel<<<grid, 256, 0, stream>>>(p);
   return check_launch("wgrad_simt_kernel");
 }

@@ -170,10 +170,22 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+__device__ __forceinline__ void trace_raw(unsigned long long* tr, int slot, unsigned long long v) {
+  if (tr != nullptr) {
+    const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+    tr[cta * 16 + slot] = v;
+  }
+}
+__device__ __forceinline__ void trace_val(const TcParams& p, int slot, unsigned long long v) {
+  if (p.trace != nullptr) {
+    const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
+    p.trace[cta * 16 + slot] = v;
+  }
+}
 __device__ __forceinline__ void trace_put(const TcParams& p, int slot) {
   if (p.trace != nullptr) {
     const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
-    p.trace[cta * 8 + slot] = gtimer();
+    p.trace[cta * 16 + slot] = gtimer();
   }
 }
 
@@ -366,8 +378,16 @@ __device__ __forceinline__ void mma_issue(const TcParams& p, uint64_t* full_bar,
   uint32_t a_lo = a_lo0, b_lo = b_lo0, stage = 0, phase = 0, acc_off = 0;
   uint32_t fresh = (uint32_t)p.nacc;          // MMAs that still start their accumulator (accumulate = 0)
   const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+  const bool tracing = p.trace != nullptr;
+  long long waited = 0;
   for (int ks = 0; ks < ksteps; ++ks) {
-    mbar_wait(full0 + stage * 8, phase);
+    if (tracing) {
+      const long long w0 = clock64();
+      mbar_wait(full0 + stage * 8, phase);
+      if (ks > 0) waited += clock64() - w0;
+    } else {
+      mbar_wait(full0 + stage * 8, phase);
+    }
     tc_fence_after();
     if (ks == 0) trace_put(p, 2);
     if (!skip) {
@@ -386,6 +406,7 @@ __device__ __forceinline__ void mma_issue(const TcParams& p, uint64_t* full_bar,
     if (++stage == stages) { stage = 0; phase ^= 1; a_lo = a_lo0; b_lo = b_lo0; }
   }
   umma_commit(smem_u32(acc_bar));
+  if (tracing) trace_val(p, 8, (unsigned long long)waited);   // cycles the issuer waited for operands (after the first)
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 4)
@@ -419,7 +440,7 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
       unsigned smid;
       asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
       const unsigned long long cta = blockIdx.x + (unsigned long long)gridDim.x * (blockIdx.y + (unsigned long long)gridDim.y * blockIdx.z);
-      p.trace[cta * 8 + 7] = smid;
+      p.trace[cta * 16 + 7] = smid;
     }
   }
 
@@ -447,6 +468,8 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long pwait = 0;
+      const bool tracing = p.trace != nullptr;
       for (int t = 0; t < p.ntaps; ++t) {
         int cx, cy, wtap, ph = 0;
         if (p.mode == PG_CONVT) {
@@ -454,6 +477,8 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
           wtap = ((1 - py) + 2 * j) * 4 + (1 - px) + 2 * i;
           cx = x0 + px - i;
           cy = y0 + py - j;
+        } else if (p.mode == PG_CONV1X1) {
+          wtap = 0; cx = x0; cy = y0;
         } else {
           const int kh = t >> 2, kw = t & 3;
           wtap = t;
@@ -468,7 +493,13 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
           }
         }
         for (int ck = 0; ck < nk; ++ck) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          if (tracing) {
+            const long long w0 = clock64();
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            pwait += clock64() - w0;
+          } else {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          }
           const uint32_t fb = smem_u32(&full_bar[stage]);
           if (p.debug & 2) { mbar_expect_tx(fb, 0); if (++stage == p.stages) { stage = 0; phase ^= 1; } continue; }
           mbar_expect_tx(fb, p.tx_bytes);
@@ -478,6 +509,7 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (tracing) { trace_val(p, 9, (unsigned long long)pwait); trace_put(p, 10); }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -576,6 +608,7 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
   memset(&p, 0, sizeof(p));
   p.mode = d->mode; p.stride = d->stride; p.pad = d->pad; p.B = d->B;
   if (d->mode == PG_CONVT) { p.Ha = d->Hin; p.Wa = d->Win; p.ntaps = 4; }
+  else if (d->mode == PG_CONV1X1) { p.Ha = d->Hout; p.Wa = d->Wout; p.ntaps = 1; }
   else { p.Ha = d->Hout; p.Wa = d->Wout; p.ntaps = 16; }
   p.Hout = d->Hout; p.Wout = d->Wout;
   p.TW = pow2_ceil(p.Wa); if (p.TW > 128) p.TW = 128;
@@ -712,8 +745,9 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
         return e;
   }
   {
-    cuuint64_t dims[2] = {(cuuint64_t)16 * p.Ctot, (cuuint64_t)d->N};
-    cuuint64_t strides[1] = {(cuuint64_t)16 * p.Ctot * 2};
+    const int wtaps = d->mode == PG_CONV1X1 ? 1 : 16;
+    cuuint64_t dims[2] = {(cuuint64_t)wtaps * p.Ctot, (cuuint64_t)d->N};
+    cuuint64_t strides[1] = {(cuuint64_t)(d->mode == PG_CONV1X1 && d->ldw > 0 ? d->ldw : wtaps * p.Ctot) * 2};
     cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)p.BN};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMapSwizzle sw = pl.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -798,6 +832,9 @@ struct WgParams {
   uint32_t tmem_cols;
   float* dw;
   int ld_n, n_real, c_real;
+  int pointwise, ld_c;     // PG_CONV1X1: one tap, no shift, dw[n*ld_n + c*ld_c]
+  int n_atoms_load;        // G boxes that exist (the accumulator rows of the others are never stored)
+  unsigned long long* trace;
 };
 
 constexpr int WG_KP = 64;
@@ -842,6 +879,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
   int tile_end = tile_beg + p.tiles_per_split;
   if (tile_end > p.total_tiles) tile_end = p.total_tiles;
   const int ntiles = tile_end > tile_beg ? tile_end - tile_beg : 0;
+  if (threadIdx.x == 0 && p.trace != nullptr) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace_raw(p.trace, 0, gtimer());
+    trace_raw(p.trace, 7, smid);
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapG);
@@ -857,6 +900,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_sh;
+  if (threadIdx.x == 0 && p.trace != nullptr) trace_raw(p.trace, 1, gtimer());
 
   if (warp == 0) {
     if (lane == 0 && ntiles > 0) {
@@ -868,8 +912,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
         const int b0 = (tile / (p.nx * p.ny)) * p.TB;
         mbar_wait(smem_u32(&gempty[gs]), gph ^ 1);
         const uint32_t gb = smem_u32(&gfull[gs]);
-        mbar_expect_tx(gb, p.n_atoms * p.g_boxbytes);
-        for (int a = 0; a < p.n_atoms; ++a)
+        mbar_expect_tx(gb, p.n_atoms_load * p.g_boxbytes);
+        for (int a = 0; a < p.n_atoms_load; ++a)
           tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, &mapG, gb, n0 + a * p.g_box, x0, y0, b0);
         if (++gs == p.g_stages) { gs = 0; gph ^= 1; }
         for (int tl = 0; tl < p.T; ++tl) {
@@ -878,7 +922,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
           const uint32_t ab = smem_u32(&afull[as]);
           mbar_expect_tx(ab, p.c_atoms * p.a_boxbytes);
           int ph = 0, cx = x0 - p.pad + kw, cy = y0 - p.pad + kh;
-          if (p.stride == 2) {
+          if (p.pointwise) { cx = x0; cy = y0; }
+          else if (p.stride == 2) {
             const int u = kh - p.pad, v = kw - p.pad;
             ph = (u & 1) * 2 + (v & 1);
             cx = x0 + (v >> 1);
@@ -906,6 +951,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
       for (int it = 0; it < ntiles; ++it) {
         mbar_wait(gfull0 + gs * 8, gph);
         tc_fence_after();
+        if (it == 0 && p.trace != nullptr) trace_raw(p.trace, 2, gtimer());
         uint32_t tcol = tmem_acc;
         for (uint32_t tl = 0; tl < T; ++tl) {
           mbar_wait(afull0 + as * 8, aph);
@@ -924,13 +970,28 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
         if (++gs == g_stages) { gs = 0; gph ^= 1; g_lo = g_lo0; }
       }
       umma_commit(smem_u32(&acc_bar));
+      if (p.trace != nullptr) trace_raw(p.trace, 3, gtimer());
     }
   } else if (ntiles > 0) {
     const int q = warp & 3;
     const int n = n0 + q * 32 + lane;
     mbar_wait(smem_u32(&acc_bar), 0);
     tc_fence_after();
-    if (p.T == 2) {
+    if (threadIdx.x == 64 && p.trace != nullptr) trace_raw(p.trace, 4, gtimer());
+    if (p.pointwise) {
+      for (int c16 = 0; c16 < p.ct; c16 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c16, v);
+        tmem_ld_wait();
+        if (n < p.n_real) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const int c = c0 + c16 + i;
+            if (c < p.c_real) atomicAdd(p.dw + (long long)n * p.ld_n + (long long)c * p.ld_c, __uint_as_float(v[i]));
+          }
+        }
+      }
+    } else if (p.T == 2) {
       for (int c16 = 0; c16 < p.ct; c16 += 16) {
         uint32_t v[2][16];
         tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c16, v[0]);
@@ -966,12 +1027,14 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
       }
     }
   }
+  if (threadIdx.x == 64 && p.trace != nullptr) trace_raw(p.trace, 5, gtimer());
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_acc, p.tmem_cols);
   }
+  if (threadIdx.x == 0 && p.trace != nullptr) trace_raw(p.trace, 6, gtimer());
 }
 
 static int box_of(int ch) { return ch >= 64 ? 64 : (ch >= 32 ? 32 : 16); }
@@ -979,8 +1042,9 @@ static uint32_t layout_of(int rowbytes) { return rowbytes == 128 ? 2u : (rowbyte
 
 static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& smem) {
   memset(&p, 0, sizeof(p));
-  if (d->mode != PG_CONV || d->C2 != 0) return false;
-  p.stride = d->stride; p.pad = d->pad; p.B = d->B; p.Hout = d->Hout; p.Wout = d->Wout;
+  if ((d->mode != PG_CONV && d->mode != PG_CONV1X1) || d->C2 != 0) return false;
+  p.pointwise = d->mode == PG_CONV1X1 ? 1 : 0;
+  p.stride = p.pointwise ? 1 : d->stride; p.pad = d->pad; p.B = d->B; p.Hout = d->Hout; p.Wout = d->Wout;
   p.TW = pow2_ceil(d->Wout); if (p.TW > WG_KP) p.TW = WG_KP;
   p.TH = pow2_ceil(d->Hout); if (p.TH > WG_KP / p.TW) p.TH = WG_KP / p.TW;
   p.TB = WG_KP / (p.TW * p.TH);
@@ -991,7 +1055,8 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   p.g_box = box_of(N); p.n_atoms = 128 / p.g_box;
   p.a_box = box_of(C);
   // T taps x ct channels = 256 accumulator columns, so two CTAs fit the 512 TMEM columns of an SM
-  if (C >= 128) { p.ct = 128; p.T = 2; }
+  if (p.pointwise) { p.T = 1; p.ct = C >= 256 ? 256 : (C >= 128 ? 128 : (C >= 64 ? 64 : (C >= 32 ? 32 : 16))); }
+  else if (C >= 128) { p.ct = 128; p.T = 2; }
   else if (C >= 64) { p.ct = 64; p.T = 4; }
   else if (C >= 32) { p.ct = 32; p.T = 8; }
   else { p.ct = 16; p.T = 16; }
@@ -1013,7 +1078,11 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   const uint32_t afmt = d->out_f32 == PG_F16 ? 0u : 1u, bfmt = d->in_dtype == PG_F16 ? 0u : 1u;
   p.idesc = (1u << 4) | (afmt << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.ct >> 3) << 17) |
             ((uint32_t)(128 >> 4) << 24);
-  const int gx = (N + 127) / 128, gy = p.ctiles * (16 / p.T);
+  {
+    const int rows = N < 128 ? N : 128;              // (the last n-tile of a larger N may be partial: load all its boxes)
+    p.n_atoms_load = N <= 128 ? (rows + p.g_box - 1) / p.g_box : p.n_atoms;
+  }
+  const int gx = (N + 127) / 128, gy = p.ctiles * (p.pointwise ? 1 : 16 / p.T);
   // Split-K over pixel tiles: every CTA ends with 128 x 256 fp32 atomics into dW, so a CTA should own enough pixel
   // tiles (>= 8, ~1 us of MMA) to amortise them; beyond that, split until ~2 CTAs per SM exist.
   int splits = (2 * num_sms() + gx * gy - 1) / (gx * gy);
@@ -1044,20 +1113,26 @@ int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, fl
     set_error("conv_wgrad_tc: unsupported shape");
     return PG_ERR_UNSUPPORTED;
   }
-  if ((((uintptr_t)dw) & 15) != 0 || (ld_n % 4) != 0) {
+  if (!p.pointwise && ((((uintptr_t)dw) & 15) != 0 || (ld_n % 4) != 0)) {
     set_error("conv_wgrad_tc: dw must be 16-byte aligned with ld_n %% 4 == 0");
     return PG_ERR_UNSUPPORTED;
   }
-  p.dw = dw; p.ld_n = ld_n; p.n_real = n_real; p.c_real = c_real;
+  p.dw = dw; p.ld_n = ld_n; p.n_real = n_real; p.c_real = c_real; p.ld_c = d->ldw > 0 ? d->ldw : 16;
+  p.trace = g_trace;
+  static const bool wdbg = getenv("PG_TC_DEBUG") != nullptr;
+  if (wdbg)
+    fprintf(stderr, "wgrad_tc: grid (%u,%u,%u) T %d ct %d tiles %d per-split %d g_stages %d a_stages %d smem %zu tmem %u\n", grid.x,
+            grid.y, grid.z, p.T, p.ct, p.total_tiles, p.tiles_per_split, p.g_stages, p.a_stages, smem, p.tmem_cols);
   CUtensorMap mG;
   ActMaps mA;
   memset(&mA, 0, sizeof(mA));
   if (int e = encode_act_map(&mG, g, d->N, ldg, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, -1, p.g_rowbytes,
                              d->out_f32))
     return e;
-  for (int ph = 0; ph < (d->stride == 2 ? 4 : 1); ++ph)
+  const bool phased = !p.pointwise && d->stride == 2;
+  for (int ph = 0; ph < (phased ? 4 : 1); ++ph)
     if (int e = encode_act_map(&mA.m[ph], a, d->C1, d->ld1, d->B, d->Hin, d->Win, p.a_box, p.TW, p.TH, p.TB,
-                               d->stride == 2 ? ph : -1, p.a_rowbytes, d->in_dtype))
+                               phased ? ph : -1, p.a_rowbytes, d->in_dtype))
       return e;
   static bool smem_set = false;
   if (!smem_set) {

@@ -149,9 +149,9 @@ def new_act(B, H, W, C, device, dt=BF16, zero=False, twin=False):
 
 
 def conv_desc(mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo, n_valid=None, act=0, out_dt=BF16,
-              has_bias=0, in_dt=BF16):
+              has_bias=0, in_dt=BF16, n_first=0, c_valid=0, ldw=0):
     return L.ConvDesc(mode, stride, pad, B, Hin, Win, Hout, Wout, C1, C2, ld1, ld2, N, ldo,
-                      N if n_valid is None else n_valid, act, out_dt, has_bias, in_dt)
+                      N if n_valid is None else n_valid, act, out_dt, has_bias, in_dt, n_first, c_valid, ldw)
 
 
 class Config:
@@ -165,26 +165,31 @@ class Config:
     fwd_dt = {'fp16': L.DT_F16, 'bf16': L.DT_BF16}[os.environ.get('PATCHGAN_B200_FWD_DTYPE', 'fp16')]
     # independent chains of the step on side streams (0 = everything on the caller's stream)
     streams = os.environ.get('PATCHGAN_B200_STREAMS', '1') != '0'
+    # one-real-channel layers as pointwise tap products (0 = run them as 16x padded 4x4 implicit GEMMs)
+    taps = os.environ.get('PATCHGAN_B200_TAPS', '1') != '0'
 
 
 def conv_flops(desc):
     """2*MACs of the contraction as launched (padded channel counts)."""
     c = desc.C1 + desc.C2
+    if desc.mode == L.PG_CONV1X1:
+        return 2.0 * desc.B * desc.Hout * desc.Wout * c * desc.N
     if desc.mode == L.PG_CONVT:
         return 2.0 * desc.B * desc.Hin * desc.Win * c * desc.N * 16
     return 2.0 * desc.B * desc.Hout * desc.Wout * c * desc.N * 16
 
 
 def desc_tag(d):
-    return (f"{'convT' if d.mode else 'conv'} s{d.stride}p{d.pad} B{d.B} {d.Hin}x{d.Win}->{d.Hout}x{d.Wout} "
+    return (f"{('conv', 'convT', 'conv1x1')[d.mode]} s{d.stride}p{d.pad} B{d.B} {d.Hin}x{d.Win}->{d.Hout}x{d.Wout} "
             f"C{d.C1}+{d.C2} N{d.N}")
 
 
 def run_conv(desc, src1, src2, w, bias, out):
     if L.PROFILER is not None:
         L.PROFILER.note(conv_flops(desc), desc_tag(desc))
-    L.call('pg_conv_fwd', ctypes.byref(desc), src1.ptr, src2.ptr if src2 is not None else None, w.data_ptr(),
-           bias.data_ptr() if bias is not None else None, out.ptr, out.twptr, Config.impl, _stream())
+    L.call('pg_conv_fwd', ctypes.byref(desc), src1.ptr, src2.ptr if src2 is not None else None,
+           w if isinstance(w, int) else w.data_ptr(), bias.data_ptr() if bias is not None else None, out.ptr, out.twptr,
+           Config.impl, _stream())
 
 
 def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream=None):
@@ -197,6 +202,51 @@ def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream=None):
     if L.PROFILER is not None:
         L.PROFILER.note(conv_flops(desc), desc_tag(desc))
     L.call('pg_conv_wgrad', ctypes.byref(desc), a.ptr, g.ptr, g.ld, dw_ptr, ld_n, n_real, c_real, Config.impl, _stream())
+
+
+# ------------------------------------------------------------------------------------------------
+# Layers with ONE real channel on one side (generator output ConvTranspose2d(2nf -> 1), discriminator last
+# Conv2d(8ndf -> 1), the mask-channel data-gradient of the discriminator's first layer).  As 4x4 convolutions they are
+# GEMMs with N = 1 (16x padding on the tensor cores) and too many FLOPs per byte for the CUDA cores; as pointwise
+# products over the 16 taps they are GEMMs with N = 16 (or K = 16) that read / write the wide tensor exactly once:
+#   forward        P[q][tap] = sum_c in[q][c] W[tap][c]          then scatter: out[p] = act(b + sum_tap P[q(p,tap)][tap])
+#   data-gradient  gather: G[q][tap] = dy[p(q,tap)]              then dx[q][c] = sum_tap G[q][tap] W[c][tap]
+#   weight-grad.   dW[c][tap] = sum_q in[q][c] G[q][tap]
+# (include/patchgan_b200.h: PG_CONV1X1, pg_taps_scatter, pg_taps_gather)
+# ------------------------------------------------------------------------------------------------
+
+def taps_enabled():
+    return Config.impl == L.IMPL_AUTO and Config.taps
+
+
+def taps_forward(mode, stride, pad, src1, src2, w_ptr, bias, act, out, ch):
+    """out[..., ch] = act(bias + 4x4 conv / convT of (src1 | src2) with the 16 x Ctot tap matrix at w_ptr)."""
+    B, Hq, Wq = src1.B, src1.H, src1.W
+    P = new_act(B, Hq, Wq, 16, src1.t.device, dt=F32)
+    c2, ld2 = (src2.C, src2.ld) if src2 is not None else (0, 0)
+    run_conv(conv_desc(L.PG_CONV1X1, 1, 0, B, Hq, Wq, Hq, Wq, src1.C, c2, src1.ld, ld2, 16, 16, out_dt=F32,
+                       in_dt=src1.dt), src1, src2, w_ptr, None, P)
+    L.call('pg_taps_scatter', mode, stride, pad, B, Hq, Wq, out.H, out.W, P.ptr, 16,
+           bias.data_ptr() if bias is not None else None, act, out.ptr, out.dt, out.ld, ch, _stream())
+
+
+def taps_gather(mode, stride, pad, dy, ch, B, Hq, Wq):
+    """G[q][tap] = dy[p(q, tap)][ch] as a bf16 Act (B, Hq, Wq, 16)."""
+    G = new_act(B, Hq, Wq, 16, dy.t.device)
+    L.call('pg_taps_gather', mode, stride, pad, B, Hq, Wq, dy.H, dy.W, dy.ptr, dy.ld, ch, G.ptr, _stream())
+    return G
+
+
+def taps_dgrad(G, w16, out):
+    """out[q][c] = sum_tap G[q][tap] * w16[c][tap]   (w16: bf16 [C][16])"""
+    run_conv(conv_desc(L.PG_CONV1X1, 1, 0, G.B, G.H, G.W, G.H, G.W, 16, 0, 16, 0, out.C, out.ld), G, None, w16, None, out)
+
+
+def taps_wgrad(G, x, dw_ptr, c_real, wstream=None):
+    """dw[c*16 + tap] += sum_q x[q][c] * G[q][tap]"""
+    d = conv_desc(L.PG_CONV1X1, 1, 0, G.B, G.H, G.W, G.H, G.W, x.C, 0, x.ld, 0, 16, 16, out_dt=BF16, in_dt=BF16, ldw=16)
+    run_wgrad(d, x, G, dw_ptr, 1, 16, c_real, wstream)
+
 
 
 class LayerSpec:
@@ -218,6 +268,14 @@ class PackedWeights:
         self.fwd_dt = Config.fwd_dt
         self.fwd = torch.empty((spec.np, 16, spec.cinp), device=device, dtype=TORCH_DT[self.fwd_dt])
         self.bwd = torch.empty((spec.cinp, 16, spec.np), device=device, dtype=torch.bfloat16)
+        # 1-output-channel layers: bf16 copy of the master weight viewed as [Cin][16 taps] (tap-product data-gradient)
+        self.taps_ok = spec.cout == 1 and spec.c1 == spec.c1p and spec.c2 == spec.c2p
+        self.w16 = torch.empty((spec.cinp, 16), device=device, dtype=torch.bfloat16) if self.taps_ok else None
+
+    def pack_w16(self, w):
+        if self.w16 is not None:
+            n = self.spec.cinp
+            L.call('pg_copy_f32_to_bf16_slice', w.data_ptr(), 16, self.w16.data_ptr(), 16, 0, 16, n, BF16, _stream())
 
     def jobs(self, w):
         """The pg_pack_weight calls of `pack` as (src, dst, N, Np, C1, C1p, C2, C2p, sn, sc, flip, dtype) tuples."""
@@ -287,6 +345,8 @@ class NetEngine:
                 self._jobs = (ptrs,) + self._build_jobs(ps, dev)
             _, table, njobs, ntiles = self._jobs
             L.call('pg_pack_weights_multi', table.data_ptr(), njobs, ntiles, _stream())
+            for pw in self.packed:
+                pw.pack_w16(ps[pw.spec.wname].detach())
             self._stamp = stamp
 
     JOB_DT = np.dtype([('src', '<u8'), ('dst', '<u8'), ('sn', '<i8'), ('sc', '<i8'), ('N', '<i4'), ('Np', '<i4'),
@@ -459,8 +519,12 @@ class GeneratorEngine(NetEngine):
             else:
                 out = new_act(B, Ho, Wo, (s.cout + 3) // 4 * 4, dev, dt=F32)   # trimmed stride: real channels only
                 fused = 0 if s.act == 'softmax' else L.ACT[s.act]
-                run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, out.ld,
-                                   n_valid=s.cout, act=fused, out_dt=F32, in_dt=src1.dt), src1, src2, pw.fwd, None, out)
+                if taps_enabled() and pw.taps_ok and s.act != 'softmax':
+                    taps_forward(L.PG_CONVT, 2, 1, src1, src2, pw.fwd.data_ptr(), None, fused, out, 0)
+                else:
+                    run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np,
+                                       out.ld, n_valid=s.cout, act=fused, out_dt=F32, in_dt=src1.dt), src1, src2,
+                             pw.fwd, None, out)
                 if s.act == 'softmax':
                     L.call('pg_softmax_fwd', out.ptr, out.ptr, B * Ho * Wo, s.cout, out.ld, _stream())
                 ctx['dec'].append((src1, src2, None, None, out, 0.0) if save else None)
@@ -480,6 +544,23 @@ class GeneratorEngine(NetEngine):
             src1, src2, raw, sums, out, dp = ctx['dec'][i]
             pw = self.packed[7 + i]
             g = grads[s.wname]
+            if i == 6 and taps_enabled() and pw.taps_ok:
+                # one output channel: tap products (gather dY once, then two pointwise GEMMs)
+                G6 = taps_gather(L.PG_CONVT, 2, 1, d_raw, 0, B, src1.H, src1.W)
+                taps_wgrad(G6, src1.b16, g.data_ptr(), s.c1, wstream)
+                if src2 is not None:
+                    taps_wgrad(G6, src2.b16, g.data_ptr() + s.c1 * 16 * 4, s.c2, wstream)
+                din = new_act(B, src1.H, src1.W, s.cinp, dev)
+                taps_dgrad(G6, pw.w16, din)
+                d_prev = din.slice(0, s.c1p)
+                dskip[0] = din.slice(s.c1p, s.c2p)
+                ps = self.dec[i - 1]
+                _, _, praw, psums, pout, pdp = ctx['dec'][i - 1]
+                if ps.norm:
+                    d_raw = norm_bwd(praw, psums, d_prev, None, L.ACT[ps.act], pdp, self.seed, 16 + i - 1)
+                else:
+                    d_raw = act_bwd_out(pout, d_prev, L.ACT[ps.act])
+                continue
             # weight gradient: dW[ci][co][tap] = sum x[ci] * dY[co] -- PG_CONV geometry with A = dY, G = layer input
             wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C, src1.C,
                            out_dt=BF16, in_dt=BF16)
@@ -491,7 +572,7 @@ class GeneratorEngine(NetEngine):
             # data gradient: stride-2 conv of dY with W'[ci][tap][co]
             din = new_act(B, src1.H, src1.W, s.cinp, dev)
             run_conv(conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
-                               din.ld), d_raw, None, pw.bwd, None, din)
+                               din.ld, c_valid=s.cout), d_raw, None, pw.bwd, None, din)
             if i >= 1:
                 d_prev = din.slice(0, s.c1p)
                 dskip[6 - i] = din.slice(s.c1p, s.c2p)
@@ -592,7 +673,9 @@ class DiscriminatorEngine(NetEngine):
             h, t, sums, out = ctx[li]
             h, out = h.images(b0, nb), out.images(b0, nb)
             bias = ps[s.bname].detach() if s.bias else None
-            if li == last:
+            if li == last and taps_enabled() and self.packed[li].taps_ok:
+                taps_forward(L.PG_CONV, s.stride, 1, h, None, self.packed[li].fwd.data_ptr(), bias, L.ACT[s.act], out, 0)
+            elif li == last:
                 run_conv(conv_desc(L.PG_CONV, s.stride, 1, nb, h.H, h.W, out.H, out.W, h.C, 0, h.ld, 0, s.np, out.ld,
                                    n_valid=s.cout, act=L.ACT[s.act], out_dt=F32, has_bias=1, in_dt=h.dt), h, None,
                          self.packed[li].fwd, bias, out)
@@ -605,10 +688,11 @@ class DiscriminatorEngine(NetEngine):
                     instnorm_stats(t, sums, b0)
                     norm_fwd(t, sums, out, 0, 0.0, None, 0, b0)
 
-    def backward(self, ctx, d_raw, grads, need_dx, nb=None, wstream=None):
+    def backward(self, ctx, d_raw, grads, need_dx, nb=None, wstream=None, dx_channels=None):
         """d_raw: bf16 Act (nb,Ho,Wo,16): gradient wrt the last conv's pre-sigmoid output.
         grads: dict of zero-initialised fp32 tensors to accumulate into, or None to skip weight gradients.
-        nb: process only the first nb images of the saved batch."""
+        nb: process only the first nb images of the saved batch.
+        dx_channels = (first, count): the caller reads only these channels of the returned input gradient."""
         dev = d_raw.t.device
         B = d_raw.B if nb is None else nb
         din = None
@@ -616,23 +700,41 @@ class DiscriminatorEngine(NetEngine):
             s = self.specs[li]
             h, t, sums, out = ctx[li]
             h = h.first(B)
+            pw = self.packed[li]
+            last_taps = li == len(self.specs) - 1 and li > 0 and taps_enabled() and pw.taps_ok
+            Gt = taps_gather(L.PG_CONV, s.stride, 1, d_raw, 0, B, h.H, h.W) if last_taps else None
             if grads is not None:
-                wd = conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, d_raw.H, d_raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
-                               in_dt=BF16)
-                run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
+                if last_taps:
+                    taps_wgrad(Gt, h.b16, grads[s.wname].data_ptr(), s.cin, wstream)
+                else:
+                    wd = conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, d_raw.H, d_raw.W, h.C, 0, h.ld, 0, s.np, s.np,
+                                   out_dt=BF16, in_dt=BF16)
+                    run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
                 if s.bias:
                     with torch.cuda.stream(wstream if wstream is not None else torch.cuda.current_stream()):
                         L.call('pg_colsum', d_raw.ptr, B * d_raw.H * d_raw.W, d_raw.ld, s.cout,
                                grads[s.bname].data_ptr(), _stream())
             if li > 0 or need_dx:
                 din = new_act(B, h.H, h.W, s.cinp, dev)
-                if s.stride == 2:
+                nf, nv = 0, None
+                if li == 0 and dx_channels is not None:
+                    nf, nv = dx_channels[0], dx_channels[0] + dx_channels[1]
+                if last_taps:
+                    taps_dgrad(Gt, pw.w16, din)
+                elif (li == 0 and dx_channels is not None and dx_channels[1] == 1 and s.stride == 2 and taps_enabled()
+                        and s.cout == s.np):
+                    # only the generated-mask channel of the input gradient is read: tap products of dY with the 16 x Cout
+                    # slab W'[c = mask channel] of the data-gradient operand, scattered as a ConvTranspose2d
+                    wslab = pw.bwd.data_ptr() + dx_channels[0] * 16 * s.np * 2
+                    taps_forward(L.PG_CONVT, 2, 1, d_raw, None, wslab, None, 0, din, dx_channels[0])
+                elif s.stride == 2:
                     dd = conv_desc(L.PG_CONVT, 2, 1, B, d_raw.H, d_raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
-                                   din.ld)
+                                   din.ld, n_valid=nv, n_first=nf, c_valid=s.cout)
+                    run_conv(dd, d_raw, None, pw.bwd, None, din)
                 else:
                     dd = conv_desc(L.PG_CONV, 1, 2, B, d_raw.H, d_raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
-                                   din.ld)
-                run_conv(dd, d_raw, None, self.packed[li].bwd, None, din)
+                                   din.ld, n_valid=nv, n_first=nf, c_valid=s.cout)
+                    run_conv(dd, d_raw, None, pw.bwd, None, din)
             if li > 0:
                 ps = self.specs[li - 1]
                 _, pt, psums, pout = ctx[li - 1]

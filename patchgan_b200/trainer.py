@@ -196,7 +196,7 @@ class Trainer:
         L.call('pg_bce_const', pd.ptr, pd.ld, 1.0, 1.0, losses.data_ptr(), 1, dz_g.ptr if train else None, 16,
                npatch, st)
         if train:
-            d_dinp = D.backward(dctx, dz_g, None, need_dx=True, nb=B)
+            d_dinp = D.backward(dctx, dz_g, None, need_dx=True, nb=B, dx_channels=(cin, cout))
             if ms:
                 # the discriminator's Adam step (on s_d) rewrites the weights this data-gradient chain just read
                 ev_dread = torch.cuda.Event()

@@ -40,7 +40,7 @@ def run(mode, stride, pad, B, H, Ci, Co):
     L.lib().pg_debug_set_trace(ctypes.c_void_p(trace.data_ptr()))
     call(); torch.cuda.synchronize()
     L.lib().pg_debug_set_trace(None)
-    t = trace.cpu().numpy().reshape(-1, 8)
+    t = trace.cpu().numpy().reshape(-1, 16)
     t = t[t[:, 0] != 0]
     n = len(t)
     t0 = t[:, 0].min()
@@ -49,7 +49,7 @@ def run(mode, stride, pad, B, H, Ci, Co):
     sm = t[:, 7]
     print(f'{mode} s{stride} B{B} {H}x{H} C{Ci}->N{Co}: ctas {n} sms {len(set(sm.tolist()))} event {us_plain:7.1f}us span {span:7.1f}us {flops/span/1e6:7.1f} TF/s | '
           f'start(med/max) {r(t[:,0]-t0)} setup {r(t[:,1]-t[:,0])} first-full {r(t[:,2]-t[:,1])} mainloop {r(t[:,3]-t[:,2])} '
-          f'acc-wait {r(t[:,4]-t[:,3])} epi {r(t[:,5]-t[:,4])} exit {r(t[:,6]-t[:,5])} cta-life {r(t[:,6]-t[:,0])}')
+          f'mma-waited {np.median(t[:,8])/1.9e3:6.2f} prod-waited {np.median(t[:,9])/1.9e3:6.2f} prod-done {r(t[:,10]-t[:,1])} acc-wait {r(t[:,4]-t[:,3])} epi {r(t[:,5]-t[:,4])} exit {r(t[:,6]-t[:,5])} cta-life {r(t[:,6]-t[:,0])}')
 
 if __name__ == '__main__':
     pass

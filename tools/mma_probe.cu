@@ -3,6 +3,7 @@
 // Prints ns per MMA for N in {16,64,128,256}, with 1/2/4 rotating accumulators, with/without a commit every 4 MMAs,
 // and with 1 or 2 CTAs resident per SM.
 #include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -79,6 +80,65 @@ __global__ void __launch_bounds__(128, 2) probe(int N, int nacc, int commit_ever
   }
 }
 
+
+template <int NACC>
+__global__ void __launch_bounds__(128, 2) probe_lean(int N, int commit_every8, int nmma, long long* out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bar[2];
+  __shared__ uint32_t tmem_base;
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) ((uint32_t*)(smem_raw + (base - smem_u32(smem_raw))))[i] = 0;
+  if (threadIdx.x == 0) { mbar_init(smem_u32(&bar[0]), 1); mbar_init(smem_u32(&bar[1]), 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  const uint32_t cols = NACC * N < 32 ? 32 : NACC * N;
+  if (threadIdx.x < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tm = tmem_base;
+  if (threadIdx.x == 0) {
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint64_t ad = make_desc(base, 128), bd = make_desc(base + 16384, 128);
+    const uint32_t b1 = smem_u32(&bar[1]);
+    long long t0 = clock64();
+    for (int i = 0; i < nmma; i += 8) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        umma(tm + (uint32_t)((j % NACC) * N), ad + 2 * (j & 3), bd + 2 * (j & 3), idesc, 1u);
+      if (commit_every8) commit(b1);
+    }
+    long long t1 = clock64();
+    commit(smem_u32(&bar[0]));
+    while (!mbar_try_wait(smem_u32(&bar[0]), 0)) {}
+    long long t2 = clock64();
+    out[blockIdx.x * 2] = t1 - t0;
+    out[blockIdx.x * 2 + 1] = t2 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm), "r"(cols) : "memory");
+}
+
+template <int NACC>
+void run_lean(long long* out) {
+  cudaFuncSetAttribute(probe_lean<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  for (int ctas : {1, 2})
+    for (int N : {16, 32, 64, 128, 256})
+      for (int ce : {0, 1}) {
+        if (NACC * N * ctas > 512) continue;
+        probe_lean<NACC><<<148 * ctas, 128, ctas == 1 ? 100 * 1024 : 60 * 1024>>>(N, ce, 512, out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); exit(1); }
+        long long h[2];
+        cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
+        printf("lean nacc %d ctas/SM %d N %3d commit/8 %d: issue %6.1f cyc/mma, complete %6.1f cyc/mma (floor %d)\n", NACC, ctas, N, ce,
+               (double)h[0] / 512, (double)h[1] / 512, N / 2);
+      }
+}
+
 int main() {
   long long* out;
   cudaMalloc(&out, 1 << 16);
@@ -86,6 +146,8 @@ int main() {
   int clk = 0;
   cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
   printf("clock %d kHz\n", clk);
+  run_lean<1>(out); run_lean<2>(out); run_lean<4>(out);
+  return 0;
   const int nmma = 256;
   for (int swz : {128, 32})
     for (int form : {0, 1})
