@@ -167,6 +167,13 @@ int pg_pack_weight(const float* src, void* dst, int32_t N, int32_t Np, int32_t C
  * bf16 twin dst2: the whole torch.cat((input, mask), 1) + cast + pad of trainer.py:65,96 in one pass. */
 int pg_pack2_nchw_rows(const float* src1, int32_t C1, const float* src2, int32_t C2, void* dst, void* dst2, int32_t B,
                        int32_t H, int32_t W, int32_t ld, int32_t dst_dtype, void* stream);
+/* Channel-major stride-2 im2col of a FIRST layer's input (Conv2d k4 s2 p1 with 3 / 4 real input channels; unet.py:84,
+ * disc.py:19): dst[o*K + (k_off + c)*16 + kh*4 + kw] = src[b, c, 2oy-1+kh, 2ox-1+kw] for output pixel o = (b,oy,ox), 0 outside.
+ * src element (b,c,y,x) is at src[b*sb + c*sc + y*sy + x*sx] (NCHW planes or channels of an f32 NHWC tensor).  With
+ * k = c*16 + tap the layer is a PG_CONV1X1 product with its (Cout, Cin*16) weight matrix, and pg_conv_wgrad (PG_CONV1X1,
+ * ld_n = Cin*16, ldw = 1) writes the weight-gradient straight into the reference layout.  dst2: optional bf16 twin. */
+int pg_im2col_s2(const float* src, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int32_t C, int32_t B, int32_t H, int32_t W,
+                 void* dst, void* dst2, int32_t K, int32_t k_off, int32_t dst_dtype, void* stream);
 /* Every weight tensor of a network in one launch.  jobs_dev: DEVICE array; each job is one pg_pack_weight call;
  * tile_begin = first 8x32x16 brick of the job in the launch, ctiles = ceil((C1p+C2p)/32). */
 typedef struct PgPackJob {

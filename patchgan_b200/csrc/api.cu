@@ -63,8 +63,7 @@ static int validate(const PgConvDesc* d, const char* who) {
   PG_REQUIRE(d->n_first >= 0 && d->n_first < d->n_valid && d->c_valid >= 0 && d->c_valid <= d->C1,
              "%s: bad n_first=%d / c_valid=%d", who, d->n_first, d->c_valid);
   if (d->mode == PG_CONV1X1) {
-    PG_REQUIRE(d->Hout == d->Hin && d->Wout == d->Win && d->ldw >= 0 && d->ldw % 8 == 0,
-               "%s: pointwise needs Hout = Hin, Wout = Win, ldw %% 8 == 0", who);
+    PG_REQUIRE(d->Hout == d->Hin && d->Wout == d->Win && d->ldw >= 0, "%s: pointwise needs Hout = Hin, Wout = Win", who);
   } else if (d->mode == PG_CONV) {
     PG_REQUIRE((d->stride == 1 || d->stride == 2) && (d->pad == 1 || d->pad == 2), "%s: stride/pad unsupported", who);
     PG_REQUIRE(d->Hout == (d->Hin + 2 * d->pad - 4) / d->stride + 1 && d->Wout == (d->Win + 2 * d->pad - 4) / d->stride + 1,
@@ -91,6 +90,7 @@ extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* sr
   if (int e = validate(d, "pg_conv_fwd")) return e;
   PG_REQUIRE(src1 && w_packed && out && (d->C2 == 0 || src2), "pg_conv_fwd: NULL pointer");
   PG_REQUIRE(!d->has_bias || bias, "pg_conv_fwd: has_bias but bias is NULL");
+  PG_REQUIRE(d->mode != PG_CONV1X1 || d->ldw % 8 == 0, "pg_conv_fwd: pointwise weight rows need ldw %% 8 == 0");
   cudaStream_t s = (cudaStream_t)stream;
   g_last_impl = PG_IMPL_SIMT;
   PG_REQUIRE(out2 == nullptr || d->out_f32 != PG_F32, "pg_conv_fwd: out2 (bf16 twin) needs a 16-bit primary output");

@@ -984,10 +984,17 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
         tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c16, v);
         tmem_ld_wait();
         if (n < p.n_real) {
+          if (p.ld_c == 1 && c0 + c16 + 16 <= p.c_real && (p.ld_n & 3) == 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const int c = c0 + c16 + i;
-            if (c < p.c_real) atomicAdd(p.dw + (long long)n * p.ld_n + (long long)c * p.ld_c, __uint_as_float(v[i]));
+            for (int i = 0; i < 16; i += 4)
+              red_add_v4(p.dw + (long long)n * p.ld_n + c0 + c16 + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]),
+                         __uint_as_float(v[i + 2]), __uint_as_float(v[i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c0 + c16 + i;
+              if (c < p.c_real) atomicAdd(p.dw + (long long)n * p.ld_n + (long long)c * p.ld_c, __uint_as_float(v[i]));
+            }
           }
         }
       }

@@ -113,6 +113,43 @@ __global__ void __launch_bounds__(256) pack2_rows_kernel(const float* __restrict
   }
 }
 
+// Channel-major stride-2 im2col of a first layer's input (Conv2d k4 s2 p1): for every output pixel o = (b, oy, ox) and
+// source channel c:  dst[o*K + (k_off + c)*16 + kh*4 + kw] = src[b, c, 2oy-1+kh, 2ox-1+kw]   (0 outside the image).
+// With k = c*16 + tap the row IS the layer's weight layout (Cout, Cin, 4, 4) flattened, so the first layers of both
+// networks (3 / 4 real input channels: 16x channel padding as implicit GEMMs) run as one dense pointwise GEMM with
+// K = 16*Cin and their weight-gradients land in the reference layout without a transpose.  The source is addressed
+// with explicit element strides, so NCHW planes and a channel of an NHWC tensor both work.
+__global__ void __launch_bounds__(256) im2col_s2_kernel(const float* __restrict__ src, long long sb, long long sc, long long sy,
+                                                       long long sx, int C, int H, int W, int Ho, int Wo,
+                                                       unsigned short* __restrict__ dst, unsigned short* __restrict__ dst2,
+                                                       int K, int k_off, int dt, long long per_c) {
+  // thread = (channel, output pixel), output pixel fastest: coalesced reads, one full 32-byte sector per write
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = blockIdx.y;
+  if (i >= per_c) return;
+  const int ox = (int)(i % Wo);
+  const long long r = i / Wo;
+  const int oy = (int)(r % Ho), b = (int)(r / Ho);
+  const float* plane = src + b * sb + c * sc;
+  float v[16];
+#pragma unroll
+  for (int kh = 0; kh < 4; ++kh) {
+    const int iy = 2 * oy - 1 + kh;
+#pragma unroll
+    for (int kw = 0; kw < 4; ++kw) {
+      const int ix = 2 * ox - 1 + kw;
+      v[kh * 4 + kw] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(plane + iy * sy + ix * sx) : 0.f;
+    }
+  }
+  const long long o = i * K + (long long)(k_off + c) * 16;
+  *reinterpret_cast<uint4*>(dst + o) = pack8dt(v, dt);
+  *reinterpret_cast<uint4*>(dst + o + 8) = pack8dt(v + 8, dt);
+  if (dst2 != nullptr) {
+    *reinterpret_cast<uint4*>(dst2 + o) = pack8(v);
+    *reinterpret_cast<uint4*>(dst2 + o + 8) = pack8(v + 8);
+  }
+}
+
 // All weight tensors of a network in ONE launch: blockIdx.x walks a concatenated list of 8x32x16 bricks.
 struct PackJob {              // mirrors PgPackJob
   const float* src;
@@ -226,6 +263,20 @@ extern "C" int pg_pack2_nchw_rows(const float* src1, int32_t C1, const float* sr
     pack2_rows_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(src1, C1, src2, C2, (unsigned short*)dst,
                                                                  (unsigned short*)dst2, HW, dst_dtype);
   return check_launch("pack2_rows_kernel");
+}
+
+extern "C" int pg_im2col_s2(const float* src, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int32_t C, int32_t B, int32_t H,
+                            int32_t W, void* dst, void* dst2, int32_t K, int32_t k_off, int32_t dst_dtype, void* stream) {
+  PG_REQUIRE(src && dst && C > 0 && B > 0 && H > 1 && W > 1 && (H % 2) == 0 && (W % 2) == 0, "pg_im2col_s2: bad extents");
+  PG_REQUIRE(K % 16 == 0 && k_off >= 0 && (k_off + C) * 16 <= K, "pg_im2col_s2: K=%d k_off=%d C=%d", K, k_off, C);
+  PG_REQUIRE(dst_dtype == PG_BF16 || dst_dtype == PG_F16, "pg_im2col_s2: dst_dtype must be 16-bit");
+  PG_REQUIRE((((uintptr_t)dst | (uintptr_t)dst2) & 15) == 0, "pg_im2col_s2: dst must be 16-byte aligned");
+  const int Ho = H / 2, Wo = W / 2;
+  const long long per_c = (long long)B * Ho * Wo;
+  dim3 grid((unsigned)((per_c + 255) / 256), (unsigned)C);
+  im2col_s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, sb, sc, sy, sx, C, H, W, Ho, Wo, (unsigned short*)dst,
+                                                         (unsigned short*)dst2, K, k_off, dst_dtype, per_c);
+  return check_launch("im2col_s2_kernel");
 }
 
 extern "C" int pg_pack_weights_multi(const PgPackJob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream) {

@@ -41,7 +41,7 @@ TORCH_DT = {BF16: torch.bfloat16, F32: torch.float32, F16: torch.float16}
 
 class Act:
     """A (possibly channel-sliced) NHWC activation: keeps its storage alive, carries ptr / C / pixel stride / dtype."""
-    __slots__ = ('t', 'ptr', 'C', 'ld', 'B', 'H', 'W', 'dt', 'tw')
+    __slots__ = ('t', 'ptr', 'C', 'ld', 'B', 'H', 'W', 'dt', 'tw', 'im2col')
 
     def __init__(self, t, B, H, W, C, ld=None, off=0, dt=BF16):
         self.t, self.B, self.H, self.W, self.C = t, B, H, W, C
@@ -49,6 +49,7 @@ class Act:
         self.dt = dt
         self.ptr = t.data_ptr() + off * self.esize
         self.tw = None      # bf16 twin of an f16 activation (same shape / stride), read by the wgrad GEMMs
+        self.im2col = 0     # > 0: this is the stride-2 im2col A[b, oy, ox, c*16 + tap] of an image with `im2col` channels
 
     @property
     def b16(self):
@@ -81,6 +82,7 @@ class Act:
         """Images b0 .. b0+nb-1 of the batch (same storage)."""
         a = Act(self.t, nb, self.H, self.W, self.C, self.ld, 0, self.dt)
         a.ptr = self.ptr + b0 * self.H * self.W * self.ld * self.esize
+        a.im2col = self.im2col
         if self.tw is not None:
             a.tw = self.tw.images(b0, nb)
         return a
@@ -249,6 +251,42 @@ def taps_wgrad(G, x, dw_ptr, c_real, wstream=None):
 
 
 
+def first_im2col(B, H, W, cin, device, twin):
+    """Empty stride-2 im2col matrix of a first layer's input: Act (B, H/2, W/2, cin*16), k = c*16 + tap."""
+    a = new_act(B, H // 2, W // 2, cin * 16, device, dt=Config.fwd_dt, twin=twin)
+    a.im2col = cin
+    if a.tw is not None:
+        a.tw.im2col = cin
+    return a
+
+
+def im2col_fill(a, b0, src_ptr, strides, C, k_off, B, H, W):
+    """Write channels [k_off, k_off + C) of images [b0, b0 + B) of the im2col matrix `a` from an f32 source with element
+    strides (batch, channel, row, column)."""
+    off = b0 * a.H * a.W * a.ld * 2
+    L.call('pg_im2col_s2', src_ptr, strides[0], strides[1], strides[2], strides[3], C, B, H, W, a.ptr + off,
+           a.tw.ptr + off if a.tw is not None else None, a.ld, k_off, a.dt, _stream())
+
+
+def nchw_strides(t):
+    B, C, H, W = t.shape
+    return (C * H * W, H * W, W, 1)
+
+
+def first_conv(a, w_first, bias, act, out):
+    """First Conv2d(k4, s2, p1) on the im2col matrix: a pointwise product with the (Np, cin*16) weight matrix."""
+    run_conv(conv_desc(L.PG_CONV1X1, 1, 0, a.B, a.H, a.W, a.H, a.W, a.C, 0, a.ld, 0, w_first.shape[0], out.ld,
+                       n_valid=None, act=act, out_dt=out.dt, has_bias=int(bias is not None), in_dt=a.dt), a, None, w_first,
+             bias, out)
+
+
+def first_wgrad(a, g, dw_ptr, n_real, wstream=None):
+    """dW[n][c][tap] += sum_o g[o][n] * A[o][c*16 + tap]: lands in the reference (Cout, Cin, 4, 4) layout."""
+    d = conv_desc(L.PG_CONV1X1, 1, 0, a.B, a.H, a.W, a.H, a.W, a.C, 0, a.ld, 0, g.C, g.C, out_dt=BF16, in_dt=BF16, ldw=1)
+    run_wgrad(d, a.b16, g, dw_ptr, a.C, n_real, a.C, wstream)
+
+
+
 class LayerSpec:
     """One 4x4 convolution layer of either network."""
 
@@ -272,7 +310,14 @@ class PackedWeights:
         self.taps_ok = spec.cout == 1 and spec.c1 == spec.c1p and spec.c2 == spec.c2p
         self.w16 = torch.empty((spec.cinp, 16), device=device, dtype=torch.bfloat16) if self.taps_ok else None
 
+        # first layers (stride-2 conv reading the image): f16/bf16 copy of the master weight as [Np][Cin*16]
+        self.wfirst = None
+
     def pack_w16(self, w):
+        if self.wfirst is not None:
+            K = self.spec.cin * 16
+            L.call('pg_copy_f32_to_bf16_slice', w.data_ptr(), K, self.wfirst.data_ptr(), K, 0, K, self.spec.cout, self.fwd_dt,
+                   _stream())
         if self.w16 is not None:
             n = self.spec.cinp
             L.call('pg_copy_f32_to_bf16_slice', w.data_ptr(), 16, self.w16.data_ptr(), 16, 0, 16, n, BF16, _stream())
@@ -337,6 +382,9 @@ class NetEngine:
         stamp = tuple((ps[s.wname].data_ptr(), ps[s.wname]._version) for s in self.specs)
         if self.packed is None or self.packed[0].fwd.device != dev or self.packed[0].fwd_dt != Config.fwd_dt:
             self.packed = [PackedWeights(s, dev) for s in self.specs]
+            s0 = self.specs[0]
+            if s0.kind == 'conv' and s0.stride == 2 and s0.c2 == 0:
+                self.packed[0].wfirst = torch.zeros((s0.np, s0.cin * 16), device=dev, dtype=TORCH_DT[Config.fwd_dt])
             self.seed = torch.zeros(1, device=dev, dtype=torch.int64)
             self._stamp = None
         if stamp != self._stamp:
@@ -481,14 +529,17 @@ class GeneratorEngine(NetEngine):
         h = xin
         enc_outs = []
         for i, s in enumerate(self.enc):
-            Ho, Wo = h.H // 2, h.W // 2
+            Ho, Wo = (h.H, h.W) if h.im2col else (h.H // 2, h.W // 2)
             if Ho * Wo <= 1 and training:
                 # aten::instance_norm raises for a single spatial element in training mode
                 raise ValueError('Expected more than 1 spatial element when training (input too small for 7 '
                                  'stride-2 stages)')
             raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
-            run_conv(conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, raw.ld, out_dt=F32,
-                               in_dt=h.dt), h, None, self.packed[i].fwd, None, raw)
+            if h.im2col:
+                first_conv(h, self.packed[i].wfirst, None, 0, raw)
+            else:
+                run_conv(conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, raw.ld, out_dt=F32,
+                                   in_dt=h.dt), h, None, self.packed[i].fwd, None, raw)
             sums = instnorm_stats(raw)
             out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt, twin=save)
             dp = DROP_P if (training and s.dropout) else 0.0
@@ -590,11 +641,16 @@ class GeneratorEngine(NetEngine):
             s = self.enc[i]
             h, raw, sums, out, dp = ctx['enc'][i]
             d_raw = norm_bwd(raw, sums, dy1, dskip[i] if i < 6 else None, L.ACT[s.act], dp, self.seed, i)
-            wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16, in_dt=BF16)
-            run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
+            if h.im2col:
+                first_wgrad(h, d_raw, grads[s.wname].data_ptr(), s.cout, wstream)
+            else:
+                wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
+                               in_dt=BF16)
+                run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
             if i > 0 or need_dx:
-                din = new_act(B, h.H, h.W, s.cinp, dev)
-                run_conv(conv_desc(L.PG_CONVT, 2, 1, B, raw.H, raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp, din.ld),
+                Hi, Wi = (2 * h.H, 2 * h.W) if h.im2col else (h.H, h.W)
+                din = new_act(B, Hi, Wi, s.cinp, dev)
+                run_conv(conv_desc(L.PG_CONVT, 2, 1, B, raw.H, raw.W, Hi, Wi, d_raw.C, 0, d_raw.ld, 0, s.cinp, din.ld),
                          d_raw, None, self.packed[i].bwd, None, din)
                 dy1 = din
                 dx = din
@@ -647,6 +703,8 @@ class DiscriminatorEngine(NetEngine):
         for li, s in enumerate(self.specs):
             Ho = (h.H + 2 - 4) // s.stride + 1
             Wo = (h.W + 2 - 4) // s.stride + 1
+            if h.im2col:
+                Ho, Wo = h.H, h.W
             if Ho < 1 or Wo < 1:
                 raise RuntimeError(f'Discriminator: input too small at layer {li} ({h.H}x{h.W})')
             if li == last:
@@ -681,9 +739,12 @@ class DiscriminatorEngine(NetEngine):
                          self.packed[li].fwd, bias, out)
             else:
                 t = t.images(b0, nb)
-                run_conv(conv_desc(L.PG_CONV, s.stride, 1, nb, h.H, h.W, t.H, t.W, h.C, 0, h.ld, 0, s.np, t.ld,
-                                   n_valid=s.cout, act=L.ACT[s.act], out_dt=t.dt, has_bias=int(s.bias), in_dt=h.dt), h,
-                         None, self.packed[li].fwd, bias, t)
+                if h.im2col:
+                    first_conv(h, self.packed[li].wfirst, bias if s.bias else None, L.ACT[s.act], t)
+                else:
+                    run_conv(conv_desc(L.PG_CONV, s.stride, 1, nb, h.H, h.W, t.H, t.W, h.C, 0, h.ld, 0, s.np, t.ld,
+                                       n_valid=s.cout, act=L.ACT[s.act], out_dt=t.dt, has_bias=int(s.bias), in_dt=h.dt),
+                             h, None, self.packed[li].fwd, bias, t)
                 if s.norm:
                     instnorm_stats(t, sums, b0)
                     norm_fwd(t, sums, out, 0, 0.0, None, 0, b0)
@@ -706,6 +767,8 @@ class DiscriminatorEngine(NetEngine):
             if grads is not None:
                 if last_taps:
                     taps_wgrad(Gt, h.b16, grads[s.wname].data_ptr(), s.cin, wstream)
+                elif h.im2col:
+                    first_wgrad(h, d_raw, grads[s.wname].data_ptr(), s.cout, wstream)
                 else:
                     wd = conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, d_raw.H, d_raw.W, h.C, 0, h.ld, 0, s.np, s.np,
                                    out_dt=BF16, in_dt=BF16)
@@ -715,7 +778,8 @@ class DiscriminatorEngine(NetEngine):
                         L.call('pg_colsum', d_raw.ptr, B * d_raw.H * d_raw.W, d_raw.ld, s.cout,
                                grads[s.bname].data_ptr(), _stream())
             if li > 0 or need_dx:
-                din = new_act(B, h.H, h.W, s.cinp, dev)
+                Hi, Wi = (2 * h.H, 2 * h.W) if h.im2col else (h.H, h.W)
+                din = new_act(B, Hi, Wi, s.cinp, dev)
                 nf, nv = 0, None
                 if li == 0 and dx_channels is not None:
                     nf, nv = dx_channels[0], dx_channels[0] + dx_channels[1]
@@ -728,7 +792,7 @@ class DiscriminatorEngine(NetEngine):
                     wslab = pw.bwd.data_ptr() + dx_channels[0] * 16 * s.np * 2
                     taps_forward(L.PG_CONVT, 2, 1, d_raw, None, wslab, None, 0, din, dx_channels[0])
                 elif s.stride == 2:
-                    dd = conv_desc(L.PG_CONVT, 2, 1, B, d_raw.H, d_raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
+                    dd = conv_desc(L.PG_CONVT, 2, 1, B, d_raw.H, d_raw.W, Hi, Wi, d_raw.C, 0, d_raw.ld, 0, s.cinp,
                                    din.ld, n_valid=nv, n_first=nf, c_valid=s.cout)
                     run_conv(dd, d_raw, None, pw.bwd, None, din)
                 else:

@@ -116,9 +116,23 @@ class Trainer:
         def on(stream):
             return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
 
-        # ---- inputs: NCHW float -> NHWC bf16; D input = [fake batch ; real batch] with x in channels 0..cin-1
-        xin = G.pack_input(x, twin=train)
-        if D.in_cp in (16, 32):
+        # ---- inputs.  Both first layers are Conv2d(k4, s2, p1) over 3 / 4 real channels: their inputs are packed
+        #      straight into stride-2 im2col matrices (k = c*16 + tap), so the layers are dense pointwise GEMMs.
+        #      D input = [fake batch ; real batch] = cat(x, G(x)) ; cat(x, y)  (trainer.py:65, 96).
+        im2col = E.taps_enabled() and H % 2 == 0 and W % 2 == 0
+        if im2col:
+            xs = E.nchw_strides(x)
+            xin = E.first_im2col(B, H, W, cin, dev, twin=train)
+            E.im2col_fill(xin, 0, x.data_ptr(), xs, cin, 0, B, H, W)
+            dboth = E.first_im2col(2 * B, H, W, cin + cout, dev, twin=train)
+            E.im2col_fill(dboth, 0, x.data_ptr(), xs, cin, 0, B, H, W)
+            E.im2col_fill(dboth, B, x.data_ptr(), xs, cin, 0, B, H, W)
+            E.im2col_fill(dboth, B, y.data_ptr(), E.nchw_strides(y), cout, cin, B, H, W)
+        else:
+            xin = G.pack_input(x, twin=train)
+        if im2col:
+            pass
+        elif D.in_cp in (16, 32):
             dboth = D.new_input(2 * B, H, W, dev, twin=train, zero=False)
             pack_rows(x, None, dboth, 0)          # fake half: [x | (G(x) copied in below) | 0]
             pack_rows(x, y, dboth, B)             # real half: [x | y | 0]
@@ -143,9 +157,12 @@ class Trainer:
             G.ensure_packed()
             G.bump_seed()
         p, gctx = G.forward(xin, gm.training, save=train)
-        L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.ptr, dboth.ld, cin, cout, B * H * W, dboth.dt, st)
-        if dboth.tw is not None:
-            L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.tw.ptr, dboth.ld, cin, cout, B * H * W, 0, st)
+        if im2col:      # G(x) (f32 NHWC, pixel stride p.ld) -> mask channels of the fake half
+            E.im2col_fill(dboth, 0, p.ptr, (H * W * p.ld, 1, W * p.ld, p.ld), cout, cin, B, H, W)
+        else:
+            L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.ptr, dboth.ld, cin, cout, B * H * W, dboth.dt, st)
+            if dboth.tw is not None:
+                L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.tw.ptr, dboth.ld, cin, cout, B * H * W, 0, st)
         if ms:
             D.forward_part(dctx, 0, B)
             E.join(s_d)
