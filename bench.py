@@ -40,6 +40,22 @@ CLOCK_QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.ac
                'clocks_event_reasons.sw_power_cap')
 
 
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu launch list of one step (profiles/, tools/summarize_ncu.py);
+    None when no capture is committed."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_step_launches.json'))):
+        try:
+            for k in json.load(open(path))['kernels']:
+                if k['kernel'] == kernel:
+                    best = dict(bytes_per_launch=int(k['dram_MB_per_launch'] * 1e6), launches=k['launches'],
+                                src=os.path.relpath(path, ROOT))
+        except Exception:
+            pass
+    return best
+
+
 def peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     if os.path.exists(path):
@@ -142,7 +158,7 @@ class CallProfiler:
 def sample_clocks(dev_index):
     try:
         return subprocess.Popen(['nvidia-smi', f'--id={dev_index}', f'--query-gpu={CLOCK_QUERY}', '--format=csv,noheader,nounits',
-                                 '-lms', '200'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                 '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     except Exception:
         return None
 
@@ -277,10 +293,16 @@ def run_ours(args, cfg):
     conv = [(k, v) for k, v in top if v[2] > 0]
     kname, (cnt, ms, fl) = conv[0]
     achieved_tf = fl / (ms * 1e-3) / 1e12
-    roof = dict(bound='tensor', kernel=kname, achieved=round(achieved_tf, 2), peak=pk['tf_sustained'],
+    cuda_kernel = {'pg_conv_fwd:tcgen05': 'conv_tc_kernel', 'pg_conv_wgrad:tcgen05': 'wgrad_tc_kernel'}.get(kname)
+    tr_info = ncu_traffic(cuda_kernel) if cuda_kernel else None
+    roof = dict(bound='tensor', kernel=kname, cuda_kernel=cuda_kernel, achieved=round(achieved_tf, 2), peak=pk['tf_sustained'],
                 peak_src=pk['src'] + ' (sustained cuBLAS bf16)', unit='TFLOP/s', frac=round(achieved_tf / pk['tf_sustained'], 4),
-                traffic=None, launches_per_step=cnt // nprof, ms_per_step=round(ms / nprof, 4),
-                flops_per_step=fl / nprof)
+                traffic=tr_info['bytes_per_launch'] if tr_info else None,
+                traffic_src=tr_info['src'] if tr_info else None,
+                launches_per_step=cnt // nprof, ms_per_step=round(ms / nprof, 4), flops_per_step=fl / nprof,
+                flops_per_launch=fl / max(cnt, 1),
+                how='CUDA events around every launch of this kernel in a separate eager pass (side streams and graph off); '
+                    'achieved = sum of 2*MACs as launched / sum of durations')
     img_s = world * B * args.steps / (dev_ms * 1e-3)
     step_tf = img_s * cfg['gflop_per_img'] / 1e3
     line = dict(metric='train_img_per_s', value=round(img_s, 2), unit='img/s', n_gpus=world, steps=args.steps,
@@ -291,7 +313,7 @@ def run_ours(args, cfg):
                 config=dict(workload=cfg['workload'], global_batch=world * B, per_gpu_batch=B, image=S,
                             parallelism=f'dp{world}', l2='flushed (256 MB write) between timed steps',
                             conv_impl={0: 'auto', 1: 'simt', 2: 'tcgen05'}[Config.impl],
-                            cuda_graph=bool(tr.use_cuda_graph)),
+                            cuda_graph=bool(tr.use_cuda_graph), side_streams=bool(Config.streams)),
                 clocks=clock_info,
                 e2e=dict(value=round(world * B * args.steps / e2e_s, 2), unit='img/s',
                          h2d_bytes_per_step=int(x_host.numel() * 4 + y_host.numel() * 4), d2h_bytes_per_step=32,

@@ -116,6 +116,13 @@ int pg_debug_set_trace(void* buf);
 int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
                 const float* bias, void* out, void* out2, int impl, void* stream);
 
+/* pg_conv_fwd + the InstanceNorm statistics of its output (unet.py:19-20, 53-55) in one call:
+ *   sums[(b*N + n)*2 + {0,1}] += {sum, sum of squares} of out[b,:,:,n]   (caller zeroes sums; out: all N channels, ldo >= N)
+ * On the tcgen05 path the sums are taken from the fp32 accumulators in the epilogue (no second pass over the output);
+ * tile shapes that cannot fuse run pg_instnorm_stats after the convolution. */
+int pg_conv_fwd_stats(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed, const float* bias,
+                      void* out, float* sums, int impl, void* stream);
+
 /* weight gradient of PG_CONV geometry `d` (autograd wgrad of unet.py:19,53 / disc.py:19-45):
  *   dw[n*ld_n + c*16 + tap] += sum_{b,oy,ox} g[b,oy,ox,n] * a[b, oy*s-p+kh, ox*s-p+kw, c]
  * g: [B,Hout,Wout] x N (stride ldg), a: [B,Hin,Win] x C1 (stride ld1).  Only n < n_real, c < c_real are
@@ -175,7 +182,9 @@ int pg_pack2_nchw_rows(const float* src1, int32_t C1, const float* src2, int32_t
 int pg_im2col_s2(const float* src, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int32_t C, int32_t B, int32_t H, int32_t W,
                  void* dst, void* dst2, int32_t K, int32_t k_off, int32_t dst_dtype, void* stream);
 /* Every weight tensor of a network in one launch.  jobs_dev: DEVICE array; each job is one pg_pack_weight call;
- * tile_begin = first 8x32x16 brick of the job in the launch, ctiles = ceil((C1p+C2p)/32). */
+ * tile_begin = first 8x32x16 brick of the job in the launch, ctiles = ceil((C1p+C2p)/32).
+ * flip == 2: flat job, dst[i] = convert(src[i]) for i < sn, 4096 elements per brick (operand copies that keep the
+ * master layout: first-layer [N][Cin*16], tap-product [Cin][16]). */
 typedef struct PgPackJob {
   const float* src;
   void* dst;

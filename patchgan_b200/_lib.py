@@ -32,6 +32,7 @@ _SIGS = {
     'pg_launch_count': ([], C.c_int64),
     'pg_last_conv_impl': ([], C.c_int),
     'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
+    'pg_conv_fwd_stats': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_wgrad': ([DP, vp, vp, i32, vp, i32, i32, i32, C.c_int, vp], C.c_int),
     'pg_colsum': ([vp, i64, i32, i32, vp, vp], C.c_int),
     'pg_taps_scatter': ([i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp], C.c_int),

@@ -30,7 +30,8 @@ int check_launch(const char* what) {
 int conv_fwd_simt(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, cudaStream_t);
 int conv_wgrad_simt(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
 // conv_tc.cu
-int conv_fwd_tc(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, cudaStream_t);
+int conv_fwd_tc(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, float*, cudaStream_t);
+bool conv_fwd_tc_stats_ok(const PgConvDesc*);
 bool conv_fwd_tc_supported(const PgConvDesc*, const void*, const void*, const void*, const void*);
 int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
 bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int);
@@ -85,8 +86,26 @@ extern "C" int pg_last_conv_impl(void) { return g_last_impl; }
 extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
 extern "C" int pg_debug_set_trace(void* buf) { set_tc_trace(buf); return PG_OK; }
 
+extern "C" int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_t HW, int32_t C, int32_t ld, float* sums,
+                                 void* stream);
+
+static int conv_fwd_any(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed, const float* bias,
+                        void* out, void* out2, float* stats, int impl, void* stream);
+
 extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
                            const float* bias, void* out, void* out2, int impl, void* stream) {
+  return conv_fwd_any(d, src1, src2, w_packed, bias, out, out2, nullptr, impl, stream);
+}
+
+extern "C" int pg_conv_fwd_stats(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
+                                 const float* bias, void* out, float* sums, int impl, void* stream) {
+  PG_REQUIRE(d != nullptr && sums != nullptr, "pg_conv_fwd_stats: NULL argument");
+  PG_REQUIRE(d->ldo >= d->N, "pg_conv_fwd_stats: the output row must hold all N channels");
+  return conv_fwd_any(d, src1, src2, w_packed, bias, out, nullptr, sums, impl, stream);
+}
+
+static int conv_fwd_any(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed, const float* bias,
+                        void* out, void* out2, float* stats, int impl, void* stream) {
   if (int e = validate(d, "pg_conv_fwd")) return e;
   PG_REQUIRE(src1 && w_packed && out && (d->C2 == 0 || src2), "pg_conv_fwd: NULL pointer");
   PG_REQUIRE(!d->has_bias || bias, "pg_conv_fwd: has_bias but bias is NULL");
@@ -98,11 +117,11 @@ extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* sr
   if (impl == PG_IMPL_SKINNY) {
     // CUDA-core kernels for one real channel on one side (kept as a second implementation for validation; the
     // engine runs these layers as PG_CONV1X1 tap products on the tensor cores, which is faster)
-    if (out2 == nullptr && conv_fewout_supported(d)) {
+    if (out2 == nullptr && stats == nullptr && conv_fewout_supported(d)) {
       g_last_impl = PG_IMPL_SKINNY;
       return conv_fewout(d, src1, src2, w_packed, bias, out, s);
     }
-    if (conv_fewin_supported(d)) {
+    if (stats == nullptr && conv_fewin_supported(d)) {
       g_last_impl = PG_IMPL_SKINNY;
       return conv_fewin(d, src1, w_packed, out, out2, s);
     }
@@ -113,15 +132,17 @@ extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* sr
   }
   const bool ok = conv_fwd_tc_supported(d, src1, src2, w_packed, out);
   if (ok) g_last_impl = PG_IMPL_TCGEN05;
-  if (impl == PG_IMPL_TCGEN05) {
-    if (!ok) {
-      set_error("pg_conv_fwd: tcgen05 path does not support this shape / alignment");
-      return PG_ERR_UNSUPPORTED;
-    }
-    return conv_fwd_tc(d, src1, src2, w_packed, bias, out, out2, s);
+  if (impl == PG_IMPL_TCGEN05 && !ok) {
+    set_error("pg_conv_fwd: tcgen05 path does not support this shape / alignment");
+    return PG_ERR_UNSUPPORTED;
   }
-  if (ok) return conv_fwd_tc(d, src1, src2, w_packed, bias, out, out2, s);
-  return conv_fwd_simt(d, src1, src2, w_packed, bias, out, out2, s);
+  // InstanceNorm statistics: fused into the tcgen05 epilogue when the tile geometry allows, else a second launch
+  const bool fuse = stats != nullptr && ok && conv_fwd_tc_stats_ok(d);
+  int e = ok ? conv_fwd_tc(d, src1, src2, w_packed, bias, out, out2, fuse ? stats : nullptr, s)
+             : conv_fwd_simt(d, src1, src2, w_packed, bias, out, out2, s);
+  if (e == PG_OK && stats != nullptr && !fuse)
+    e = pg_instnorm_stats(out, d->out_f32, d->B, (int64_t)d->Hout * d->Wout, d->N, d->ldo, stats, stream);
+  return e;
 }
 
 extern "C" int pg_taps_scatter(int32_t mode, int32_t stride, int32_t pad, int32_t B, int32_t Hq, int32_t Wq, int32_t Hp, int32_t Wp,

@@ -163,6 +163,9 @@ struct TcParams {
   // TMA-store epilogue: the tile is staged in (reused) ring smem as 128 rows x st_rowbytes, swizzled, st_cw columns at a time
   int tma_store, st_rowbytes, st_cw, st_nbuf, st_twin;
   unsigned long long* trace;   // debug: 8 timestamps per CTA (pg_debug_set_trace), else null
+  int splits, kps;             // K-split cluster: `splits` CTAs (cluster dims (1,1,splits)) share one tile, kps k-steps each
+  uint32_t dump_pitch;         // bytes per accumulator row in the split-K exchange buffer
+  float* stats;                // fused InstanceNorm statistics: sums[(b*N + n)*2 + {0,1}] += {x, x^2} over the tile (or null)
 };
 
 __device__ __forceinline__ unsigned long long gtimer() {
@@ -217,26 +220,12 @@ __device__ __forceinline__ float act_fast(float x) {
 
 struct EpiCtx {
   uint32_t smem_base, tmem_acc;
-  int x0, y0, b0, n0, py, px;
+  int x0, y0, b0, n0, py, px, cls;
 };
 
-// U accumulator columns [c, c+U) of this thread's row (summed over the rotating accumulators) -> f[0..U)
+// bias / activation / padding mask on U raw sums v[] of channels [n, n+U) -> f[]
 template <int ACT, int U>
-__device__ __forceinline__ void epi_load(const TcParams& p, uint32_t trow, int c, int n, float* f) {
-  uint32_t v[U];
-#pragma unroll
-  for (int i = 0; i < U; i += 16) tmem_ld16(trow + (uint32_t)(c + i), v + i);
-  tmem_ld_wait();
-  for (int a = 1; a < p.nacc; ++a) {
-#pragma unroll
-    for (int i = 0; i < U; i += 16) {
-      uint32_t w[16];
-      tmem_ld16(trow + (uint32_t)(a * p.BN + c + i), w);
-      tmem_ld_wait();
-#pragma unroll
-      for (int j = 0; j < 16; ++j) v[i + j] = __float_as_uint(__uint_as_float(v[i + j]) + __uint_as_float(w[j]));
-    }
-  }
+__device__ __forceinline__ void epi_finish(const TcParams& p, int n, uint32_t* v, float* f) {
   if (p.bias != nullptr) {
     if (n + U <= p.n_valid) {
 #pragma unroll
@@ -261,12 +250,76 @@ __device__ __forceinline__ void epi_load(const TcParams& p, uint32_t trow, int c
   }
 }
 
+// U accumulator columns [c, c+U) of this thread's row, summed over the rotating accumulators -> raw sums v[]
+template <int U>
+__device__ __forceinline__ void epi_tmem(const TcParams& p, uint32_t trow, int c, uint32_t* v) {
+#pragma unroll
+  for (int i = 0; i < U; i += 16) tmem_ld16(trow + (uint32_t)(c + i), v + i);
+  tmem_ld_wait();
+  for (int a = 1; a < p.nacc; ++a) {
+#pragma unroll
+    for (int i = 0; i < U; i += 16) {
+      uint32_t w[16];
+      tmem_ld16(trow + (uint32_t)(a * p.BN + c + i), w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[i + j] = __float_as_uint(__uint_as_float(v[i + j]) + __uint_as_float(w[j]));
+    }
+  }
+}
+
+template <int ACT, int U>
+__device__ __forceinline__ void epi_load(const TcParams& p, uint32_t trow, int c, int n, float* f) {
+  uint32_t v[U];
+  epi_tmem<U>(p, trow, c, v);
+  epi_finish<ACT, U>(p, n, v, f);
+}
+
+// Fused InstanceNorm statistics (unet.py:20,55): every epilogue thread holds 16 channels of ONE output pixel, the 32
+// lanes of a warp hold 32 pixels of the same image.  A halving butterfly (8+4+2+1+1 shuffles per quantity instead of
+// 16 x 5) leaves each even lane with the warp's sum of one channel, added to sums[(b*N + n)*2 + {0,1}] with red.add.
+__device__ __forceinline__ void stats_add16(const float* f, bool row_valid, float* sums_bn, int lane) {
+  float a[16], q[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { a[j] = row_valid ? f[j] : 0.f; q[j] = a[j] * a[j]; }
+  const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0;
+  float a8[8], q8[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    a8[i] = (h16 ? a[i + 8] : a[i]) + __shfl_xor_sync(0xffffffffu, h16 ? a[i] : a[i + 8], 16);
+    q8[i] = (h16 ? q[i + 8] : q[i]) + __shfl_xor_sync(0xffffffffu, h16 ? q[i] : q[i + 8], 16);
+  }
+  float a4[4], q4[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    a4[i] = (h8 ? a8[i + 4] : a8[i]) + __shfl_xor_sync(0xffffffffu, h8 ? a8[i] : a8[i + 4], 8);
+    q4[i] = (h8 ? q8[i + 4] : q8[i]) + __shfl_xor_sync(0xffffffffu, h8 ? q8[i] : q8[i + 4], 8);
+  }
+  float a2[2], q2[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    a2[i] = (h4 ? a4[i + 2] : a4[i]) + __shfl_xor_sync(0xffffffffu, h4 ? a4[i] : a4[i + 2], 4);
+    q2[i] = (h4 ? q4[i + 2] : q4[i]) + __shfl_xor_sync(0xffffffffu, h4 ? q4[i] : q4[i + 2], 4);
+  }
+  float a1 = (h2 ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? a2[0] : a2[1], 2);
+  float q1 = (h2 ? q2[1] : q2[0]) + __shfl_xor_sync(0xffffffffu, h2 ? q2[0] : q2[1], 2);
+  a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+  q1 += __shfl_xor_sync(0xffffffffu, q1, 1);
+  if ((lane & 1) == 0) {
+    const int col = (h16 ? 8 : 0) + (h8 ? 4 : 0) + (h4 ? 2 : 0) + (h2 ? 1 : 0);
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(sums_bn + col * 2), "f"(a1), "f"(q1) : "memory");
+  }
+}
+
 template <int ACT, int U>
 __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& mapsO, const EpiCtx& e) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3;                 // TMEM lane quarter this warp may access
   const int r = q * 32 + lane;            // accumulator row == lattice point inside the tile
   const uint32_t trow = e.tmem_acc + ((uint32_t)(q * 32) << 16);
+  // fused statistics (U == 16 only): image of this warp's 32 rows, validity of this thread's row
+  const int s_b = e.b0 + (r >> (p.lgTW + p.lgTH));
+  const bool s_valid = s_b < p.B && e.y0 + ((r >> p.lgTW) & (p.TH - 1)) < p.Ha && e.x0 + (r & (p.TW - 1)) < p.Wa;
   if (p.tma_store) {
     // ---- stage the tile in the (now idle) ring smem with the TMA swizzle, store it with cp.async.bulk.tensor:
     //      full 128-byte rows instead of 32 scattered 16-byte stores per warp instruction; tails are clipped by TMA
@@ -274,7 +327,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
     const uint32_t bufbytes = 128u * (uint32_t)p.st_rowbytes;
     const int sh = p.st_rowbytes == 128 ? 0 : (p.st_rowbytes == 64 ? 1 : 2);
     const uint32_t xr = (uint32_t)(r >> sh) & (uint32_t)((p.st_rowbytes >> 4) - 1);   // swizzle XOR of this row
-    const int cls = blockIdx.z;
+    const int cls = e.cls;
     const int nch = p.BN / p.st_cw;
     for (int ch = 0; ch < nch; ++ch) {
       const int buf = ch % p.st_nbuf;
@@ -287,6 +340,8 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
       for (int sub = 0; sub < p.st_cw; sub += U) {
         float f[U];
         epi_load<ACT, U>(p, trow, ch * p.st_cw + sub, e.n0 + ch * p.st_cw + sub, f);
+        if (U == 16 && p.stats != nullptr && s_b < p.B)
+          stats_add16(f, s_valid, p.stats + ((long long)s_b * p.N + e.n0 + ch * p.st_cw + sub) * 2, lane);
         if (p.out_f32 == PG_F32) {
           const uint32_t u0 = (uint32_t)(sub * 4) >> 4;
 #pragma unroll
@@ -334,6 +389,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
       float f[U];
       const int n = e.n0 + c;
       epi_load<ACT, U>(p, trow, c, n, f);
+      if (U == 16 && p.stats != nullptr && s_b < p.B) stats_add16(f, s_valid, p.stats + ((long long)s_b * p.N + n) * 2, lane);
       const int keep = p.ldo - n;     // channels of this chunk that exist in the (possibly trimmed) output row
       if (valid && keep > 0 && !(p.debug & 4)) {
         if (p.out_f32 == PG_F32) {
@@ -355,6 +411,102 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
         }
       }
     }
+  }
+}
+
+// ---- direct (non-TMA) store of 16 finished channels [n, n+16) of output pixel opix
+__device__ __forceinline__ void store16(const TcParams& p, long long opix, int n, const float* f) {
+  const int keep = p.ldo - n;     // channels of this chunk that exist in the (possibly trimmed) output row
+  if (keep <= 0) return;
+  if (p.out_f32 == PG_F32) {
+    float4* o = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + opix * p.ldo + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (4 * j < keep) o[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  } else {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out) + opix * p.ldo + n);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+      if (8 * j < keep) o[j] = pack8dt(f + 8 * j, p.out_f32);
+    if (p.out2 != nullptr) {
+      uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(p.out2) + opix * p.ldo + n);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+        if (8 * j < keep) o2[j] = pack8(f + 8 * j);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// Split-K over a thread-block cluster (the 2x2 .. 16x16 bottleneck layers: a handful of M tiles, K = 4096).
+// The `splits` CTAs of a cluster (1,1,splits) own disjoint k-ranges of ONE output tile.  Each dumps its fp32 partial
+// accumulators to its own shared memory, the cluster synchronises, and CTA r reduces the column slice
+// [r*BN/splits, (r+1)*BN/splits) over all peers through distributed shared memory (ld.shared::cluster) and runs the
+// normal epilogue (bias / activation / statistics / store) on it.  No atomics, no zero-fill, no extra pass.
+// --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+
+__device__ __forceinline__ void split_dump(const TcParams& p, const EpiCtx& e) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, r = q * 32 + lane;
+  const uint32_t trow = e.tmem_acc + ((uint32_t)(q * 32) << 16);
+  const uint32_t row = e.smem_base + (uint32_t)r * p.dump_pitch;
+  for (int c = 0; c < p.BN; c += 16) {
+    uint32_t v[16];
+    epi_tmem<16>(p, trow, c, v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) st_shared_v4(row + (uint32_t)(c + 4 * j) * 4, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ void split_reduce_store(const TcParams& p, const EpiCtx& e, int rank) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, r = q * 32 + lane;
+  const int xl = r & (p.TW - 1);
+  const int yl = (r >> p.lgTW) & (p.TH - 1);
+  const int bl = r >> (p.lgTW + p.lgTH);
+  const int b = e.b0 + bl, a = e.y0 + yl, bb = e.x0 + xl;
+  const bool valid = b < p.B && a < p.Ha && bb < p.Wa;
+  int oy = a, ox = bb;
+  if (p.mode == PG_CONVT) { oy = 2 * a + e.py; ox = 2 * bb + e.px; }
+  const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
+  const int s_b = e.b0 + (r >> (p.lgTW + p.lgTH));
+  const int w = p.BN / p.splits;
+  const uint32_t row = e.smem_base + (uint32_t)r * p.dump_pitch;
+  for (int c = rank * w; c < (rank + 1) * w; c += 16) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+    for (int peer = 0; peer < p.splits; ++peer) {
+      uint32_t remote;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(row + (uint32_t)c * 4), "r"(peer));
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 t;
+        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                     : "r"(remote + 16u * j)
+                     : "memory");
+        acc[4 * j] += t.x; acc[4 * j + 1] += t.y; acc[4 * j + 2] += t.z; acc[4 * j + 3] += t.w;
+      }
+    }
+    uint32_t v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(acc[j]);
+    float f[16];
+    const int n = e.n0 + c;
+    epi_finish<ACT, 16>(p, n, v, f);
+    if (p.stats != nullptr && s_b < p.B) stats_add16(f, valid, p.stats + ((long long)s_b * p.N + n) * 2, lane);
+    if (valid && !(p.debug & 4)) store16(p, opix, n, f);
   }
 }
 
@@ -431,9 +583,11 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
   const int tb_i = tile / (p.nx * p.ny);
   const int x0 = tx_i * p.TW, y0 = ty_i * p.TH, b0 = tb_i * p.TB;
   const int n0 = blockIdx.y * p.BN;
-  const int py = blockIdx.z >> 1, px = blockIdx.z & 1;
+  const int split = p.splits > 1 ? (int)cluster_rank() : 0;        // cluster dims (1,1,splits): rank = blockIdx.z % splits
+  const int cls = p.splits > 1 ? blockIdx.z / p.splits : blockIdx.z;
+  const int py = cls >> 1, px = cls & 1;
   const int nk = p.nk1 + p.nk2;
-  const int ksteps = p.ntaps * nk;
+  const int ks0 = split * p.kps, ks1 = ks0 + p.kps;                 // this CTA's k-steps (all of them without split-K)
   if (threadIdx.x == 0) {
     trace_put(p, 0);
     if (p.trace != nullptr) {
@@ -470,53 +624,61 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
       uint32_t phase = 0;
       long long pwait = 0;
       const bool tracing = p.trace != nullptr;
-      for (int t = 0; t < p.ntaps; ++t) {
-        int cx, cy, wtap, ph = 0;
-        if (p.mode == PG_CONVT) {
-          const int j = t >> 1, i = t & 1;
-          wtap = ((1 - py) + 2 * j) * 4 + (1 - px) + 2 * i;
-          cx = x0 + px - i;
-          cy = y0 + py - j;
-        } else if (p.mode == PG_CONV1X1) {
-          wtap = 0; cx = x0; cy = y0;
-        } else {
-          const int kh = t >> 2, kw = t & 3;
-          wtap = t;
-          if (p.stride == 2) {
-            const int u = kh - p.pad, v = kw - p.pad;       // input row = 2*oy + u
-            ph = (u & 1) * 2 + (v & 1);
-            cx = x0 + (v >> 1);                              // arithmetic shift = floor
-            cy = y0 + (u >> 1);
+      int t = ks0 / nk, ck = ks0 - t * nk;
+      int cx = 0, cy = 0, wtap = 0, ph = 0;
+      bool newtap = true;
+      for (int ks = ks0; ks < ks1; ++ks) {
+        if (newtap) {
+          newtap = false;
+          ph = 0;
+          if (p.mode == PG_CONVT) {
+            const int j = t >> 1, i = t & 1;
+            wtap = ((1 - py) + 2 * j) * 4 + (1 - px) + 2 * i;
+            cx = x0 + px - i;
+            cy = y0 + py - j;
+          } else if (p.mode == PG_CONV1X1) {
+            wtap = 0; cx = x0; cy = y0;
           } else {
-            cx = x0 - p.pad + kw;
-            cy = y0 - p.pad + kh;
+            const int kh = t >> 2, kw = t & 3;
+            wtap = t;
+            if (p.stride == 2) {
+              const int u = kh - p.pad, v = kw - p.pad;       // input row = 2*oy + u
+              ph = (u & 1) * 2 + (v & 1);
+              cx = x0 + (v >> 1);                              // arithmetic shift = floor
+              cy = y0 + (u >> 1);
+            } else {
+              cx = x0 - p.pad + kw;
+              cy = y0 - p.pad + kh;
+            }
           }
         }
-        for (int ck = 0; ck < nk; ++ck) {
-          if (tracing) {
-            const long long w0 = clock64();
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            pwait += clock64() - w0;
-          } else {
-            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          }
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          if (p.debug & 2) { mbar_expect_tx(fb, 0); if (++stage == p.stages) { stage = 0; phase ^= 1; } continue; }
+        if (tracing) {
+          const long long w0 = clock64();
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          pwait += clock64() - w0;
+        } else {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        }
+        const uint32_t fb = smem_u32(&full_bar[stage]);
+        if (p.debug & 2) {
+          mbar_expect_tx(fb, 0);
+        } else {
           mbar_expect_tx(fb, p.tx_bytes);
           if (ck < p.nk1) tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[ph], fb, ck * p.BK, cx, cy, b0);
           else tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[4 + ph], fb, (ck - p.nk1) * p.BK, cx, cy, b0);
           tma_load_2d(b_base + stage * p.b_bytes, &mapB, fb, wtap * p.Ctot + ck * p.BK, n0);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        if (++ck == nk) { ck = 0; ++t; newtap = true; }
       }
       if (tracing) { trace_val(p, 9, (unsigned long long)pwait); trace_put(p, 10); }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      if (p.BK == 64) mma_issue<4>(p, full_bar, empty_bar, &acc_bar, a_base, b_base, tmem_acc, ksteps);
-      else if (p.BK == 32) mma_issue<2>(p, full_bar, empty_bar, &acc_bar, a_base, b_base, tmem_acc, ksteps);
-      else mma_issue<1>(p, full_bar, empty_bar, &acc_bar, a_base, b_base, tmem_acc, ksteps);
+      if (p.BK == 64) mma_issue<4>(p, full_bar, empty_bar, &acc_bar, a_base, b_base, tmem_acc, ks1 - ks0);
+      else if (p.BK == 32) mma_issue<2>(p, full_bar, empty_bar, &acc_bar, a_base, b_base, tmem_acc, ks1 - ks0);
+      else mma_issue<1>(p, full_bar, empty_bar, &acc_bar, a_base, b_base, tmem_acc, ks1 - ks0);
       trace_put(p, 3);
     }
   } else {
@@ -524,7 +686,10 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
     mbar_wait(smem_u32(&acc_bar), 0);
     tc_fence_after();
     if (threadIdx.x == 64) trace_put(p, 4);
-    const EpiCtx e{smem_base, tmem_acc, x0, y0, b0, n0, py, px};
+    const EpiCtx e{smem_base, tmem_acc, x0, y0, b0, n0, py, px, cls};
+    if (p.splits > 1) {
+      split_dump(p, e);       // partial accumulators -> this CTA's shared memory; reduced after the cluster barrier below
+    } else
     // one uniform dispatch per CTA: the per-element code below is straight-line (4 epilogue warps = one warp per
     // scheduler, so every branch / dependent-issue bubble of a per-element `switch` was fully exposed: 0.1 us per
     // accumulator column before this was templated)
@@ -545,6 +710,20 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
         default: tc_epilogue<PG_ACT_NONE, 16>(p, mapsO, e); break;
       }
     }
+  }
+  if (p.splits > 1) {
+    cluster_sync_all();                                   // every peer's partial tile is in its shared memory
+    if (warp >= 2) {
+      const EpiCtx e{smem_base, tmem_acc, x0, y0, b0, n0, py, px, cls};
+      switch (p.act) {
+        case PG_ACT_RELU: split_reduce_store<PG_ACT_RELU>(p, e, split); break;
+        case PG_ACT_LEAKYRELU: split_reduce_store<PG_ACT_LEAKYRELU>(p, e, split); break;
+        case PG_ACT_TANH: split_reduce_store<PG_ACT_TANH>(p, e, split); break;
+        case PG_ACT_SIGMOID: split_reduce_store<PG_ACT_SIGMOID>(p, e, split); break;
+        default: split_reduce_store<PG_ACT_NONE>(p, e, split); break;
+      }
+    }
+    cluster_sync_all();                                   // nobody leaves while a peer still reads its shared memory
   }
   if (threadIdx.x == 64) trace_put(p, 5);
   tc_fence_before();
@@ -626,10 +805,23 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
   while (bn > 16 && (d->N % bn) != 0) bn >>= 1;
   if ((d->N % bn) != 0) return false;
   // Small M grids (the 2x2 .. 16x16 bottleneck layers) would otherwise run on a handful of SMs, each pulling the
-  // whole weight matrix through its own ~80 GB/s L2 port: split N further so the weights stream on more SMs.
+  // whole weight matrix through its own ~80 GB/s L2 port.  First choice: split K over a cluster of CTAs that reduce
+  // through distributed shared memory (tiles stay 128 x 128, every operand byte is fetched once per tile row/column);
+  // otherwise split N further so the weights stream on more SMs.
+  p.splits = 1;
   {
     const long long mtiles = (long long)p.nx * p.ny * nb * (d->mode == PG_CONVT ? 4 : 1);
-    while (bn > 16 && mtiles * (d->N / bn) < num_sms()) bn >>= 1;
+    const int ksteps0 = p.ntaps * (p.nk1 + p.nk2);
+    static const int splitk_env = [] { const char* e = getenv("PG_TC_SPLITK"); return e ? atoi(e) : 1; }();
+    int sbn = bn > 128 ? 128 : bn;
+    if (splitk_env && d->mode != PG_CONV1X1 && mtiles * (d->N / sbn) * 2 <= num_sms() && ksteps0 >= 8) {
+      int S = 8;
+      while (S > 1 && (sbn / S < 16 || (ksteps0 % S) != 0 || ksteps0 / S < 2)) S >>= 1;
+      while (S > 2 && mtiles * (d->N / sbn) * S > 2LL * num_sms()) S >>= 1;
+      if (S > 1) { p.splits = S; bn = sbn; }
+    }
+    if (p.splits == 1)
+      while (bn > 16 && mtiles * (d->N / bn) < num_sms()) bn >>= 1;
   }
   p.BN = bn;
   p.N = d->N; p.ldo = d->ldo; p.n_valid = d->n_valid; p.act = d->act; p.out_f32 = d->out_f32;
@@ -650,13 +842,14 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
   {
     // small grids cannot fill more than one CTA per SM anyway: give them one CTA with a deep ring (latency-bound
     // k-loops need bytes in flight), large grids get co-resident CTAs with shallow rings
-    const long long ctas = (long long)p.nx * p.ny * nb * (d->N / bn) * (d->mode == PG_CONVT ? 4 : 1);
+    const long long ctas = (long long)p.nx * p.ny * nb * (d->N / bn) * (d->mode == PG_CONVT ? 4 : 1) * p.splits;
     const int want = (int)((ctas + num_sms() - 1) / num_sms());
     if (occ > want) occ = want < 1 ? 1 : want;
+    if (p.splits > 1) occ = 1;                 // the exchange buffer lives in the ring: keep the full ring per CTA
   }
   static const int nacc_env = [] { const char* e = getenv("PG_TC_NACC"); return e ? atoi(e) : 4; }();
   {
-    const int total_mma = p.ntaps * (p.nk1 + p.nk2) * (bk / 16);
+    const int total_mma = p.ntaps * (p.nk1 + p.nk2) * (bk / 16) / p.splits;
     int nacc = bn <= 64 ? nacc_env : (bn == 128 ? (nacc_env >= 2 ? 2 : 1) : 1);
     while (nacc > 1 && (nacc * bn > 256 || total_mma < 2 * nacc)) nacc >>= 1;
     p.nacc = nacc < 1 ? 1 : nacc;
@@ -673,12 +866,15 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
     if (st_env > 0 && st_env < stages) stages = st_env;      // experiment knob
   }
   const int ksteps = p.ntaps * (p.nk1 + p.nk2);
-  if (stages > ksteps) stages = ksteps;
+  p.kps = ksteps / p.splits;
+  if (stages > p.kps) stages = p.kps;
   if (stages < 1) return false;
   p.stages = stages;
   p.tmem_cols = (uint32_t)tmem_need;
   pl.smem = (size_t)stages * per_stage + 1024;
-  pl.grid = dim3((unsigned)(p.nx * p.ny * nb), (unsigned)(d->N / bn), d->mode == PG_CONVT ? 4 : 1);
+  p.dump_pitch = (uint32_t)bn * 4u + 16u;      // +16 B: consecutive rows start 4 banks apart
+  if (p.splits > 1 && pl.smem < (size_t)128 * p.dump_pitch + 1024) pl.smem = (size_t)128 * p.dump_pitch + 1024;
+  pl.grid = dim3((unsigned)(p.nx * p.ny * nb), (unsigned)(d->N / bn), (unsigned)((d->mode == PG_CONVT ? 4 : 1) * p.splits));
   // TMA box limits
   if (p.TW > 256 || p.TH > 256 || p.TB > 256) return false;
   return true;
@@ -721,8 +917,15 @@ static int encode_act_map(CUtensorMap* m, const void* base, int C, int ld, int B
   return PG_OK;
 }
 
+// stats fusion needs every warp's 32 rows inside one image and the 16-column epilogue
+bool conv_fwd_tc_stats_ok(const PgConvDesc* d) {
+  TcPlan pl;
+  if (!make_plan(d, pl)) return false;
+  return pl.p.TW * pl.p.TH >= 32 && !(EPI_WIDE && pl.p.BN >= 32);
+}
+
 int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const void* w, const float* bias, void* out,
-                void* out2, cudaStream_t stream) {
+                void* out2, float* stats, cudaStream_t stream) {
   TcPlan pl;
   if (!make_plan(d, pl)) {
     set_error("conv_fwd_tc: unsupported shape");
@@ -732,6 +935,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   p.bias = d->has_bias ? bias : nullptr;
   p.out = out;
   p.out2 = out2;
+  p.stats = stats;
   const bool phased = d->mode == PG_CONV && d->stride == 2;
   ActMaps mA;
   CUtensorMap mB;
@@ -776,7 +980,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     const int twin = out2 != nullptr ? 1 : 0;
     const uint32_t ring = (uint32_t)p.stages * (p.a_bytes + p.b_bytes);
     const uint32_t need1 = 128u * rowbytes * (1 + twin);
-    p.tma_store = tma_st_env && d->ldo >= d->N && rowbytes >= 32 && ring >= need1 && ((uintptr_t)out & 15) == 0 &&
+    p.tma_store = tma_st_env && p.splits == 1 && d->ldo >= d->N && rowbytes >= 32 && ring >= need1 && ((uintptr_t)out & 15) == 0 &&
                   (twin == 0 || ((uintptr_t)out2 & 15) == 0);
     if (p.tma_store) {
       p.st_rowbytes = rowbytes;
@@ -800,10 +1004,27 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   p.trace = g_trace;
   static const bool dbg = getenv("PG_TC_DEBUG") != nullptr;
   if (dbg)
-    fprintf(stderr, "conv_tc: grid (%u,%u,%u) BN %d BK %d stages %d nacc %d tmem %u smem %zu TW %d TH %d TB %d ksteps %d\n",
+    fprintf(stderr, "conv_tc: grid (%u,%u,%u) BN %d BK %d stages %d nacc %d tmem %u smem %zu TW %d TH %d TB %d ksteps %d splits %d\n",
             pl.grid.x, pl.grid.y, pl.grid.z, p.BN, p.BK, p.stages, p.nacc, p.tmem_cols, pl.smem, p.TW, p.TH, p.TB,
-            p.ntaps * (p.nk1 + p.nk2));
-  conv_tc_kernel<<<pl.grid, TC_THREADS, pl.smem, stream>>>(mA, mB, mO, p);
+            p.ntaps * (p.nk1 + p.nk2), p.splits);
+  if (p.splits > 1) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = pl.grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = pl.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = (unsigned)p.splits;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel, mA, mB, mO, p));
+  } else {
+    conv_tc_kernel<<<pl.grid, TC_THREADS, pl.smem, stream>>>(mA, mB, mO, p);
+  }
   return check_launch("conv_tc_kernel");
 }
 

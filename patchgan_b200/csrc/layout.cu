@@ -172,6 +172,14 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const PackJob* _
   }
   __syncthreads();
   const int local = blockIdx.x - job.tile_begin;
+  if (job.flip == 2) {
+    // flat job: dst[i] = convert(src[i]), i < sn (first-layer [N][Cin*16] and tap-product [Cin][16] operand copies,
+    // which ARE the master layout); one block converts 4096 elements
+    const long long base = (long long)local * 4096;
+    for (int e = threadIdx.x; e < 4096; e += 256)
+      if (base + e < job.sn) job.dst[base + e] = to16(job.src[base + e], job.dt);
+    return;
+  }
   const int n0 = (local / job.ctiles) * 8, cp0 = (local % job.ctiles) * 32;
   const int Cp = job.C1p + job.C2p;
   for (int e = threadIdx.x; e < 8 * 32 * 16; e += 256) {

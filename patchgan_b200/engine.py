@@ -186,9 +186,15 @@ def desc_tag(d):
             f"C{d.C1}+{d.C2} N{d.N}")
 
 
-def run_conv(desc, src1, src2, w, bias, out):
+def run_conv(desc, src1, src2, w, bias, out, stats=None):
+    """stats: zeroed float32 (B, N, 2) tensor -> also accumulates the InstanceNorm sums of the output."""
     if L.PROFILER is not None:
         L.PROFILER.note(conv_flops(desc), desc_tag(desc))
+    if stats is not None:
+        L.call('pg_conv_fwd_stats', ctypes.byref(desc), src1.ptr, src2.ptr if src2 is not None else None,
+               w if isinstance(w, int) else w.data_ptr(), bias.data_ptr() if bias is not None else None, out.ptr,
+               stats.data_ptr(), Config.impl, _stream())
+        return
     L.call('pg_conv_fwd', ctypes.byref(desc), src1.ptr, src2.ptr if src2 is not None else None,
            w if isinstance(w, int) else w.data_ptr(), bias.data_ptr() if bias is not None else None, out.ptr, out.twptr,
            Config.impl, _stream())
@@ -273,11 +279,11 @@ def nchw_strides(t):
     return (C * H * W, H * W, W, 1)
 
 
-def first_conv(a, w_first, bias, act, out):
+def first_conv(a, w_first, bias, act, out, stats=None):
     """First Conv2d(k4, s2, p1) on the im2col matrix: a pointwise product with the (Np, cin*16) weight matrix."""
     run_conv(conv_desc(L.PG_CONV1X1, 1, 0, a.B, a.H, a.W, a.H, a.W, a.C, 0, a.ld, 0, w_first.shape[0], out.ld,
                        n_valid=None, act=act, out_dt=out.dt, has_bias=int(bias is not None), in_dt=a.dt), a, None, w_first,
-             bias, out)
+             bias, out, stats)
 
 
 def first_wgrad(a, g, dw_ptr, n_real, wstream=None):
@@ -382,6 +388,7 @@ class NetEngine:
         stamp = tuple((ps[s.wname].data_ptr(), ps[s.wname]._version) for s in self.specs)
         if self.packed is None or self.packed[0].fwd.device != dev or self.packed[0].fwd_dt != Config.fwd_dt:
             self.packed = [PackedWeights(s, dev) for s in self.specs]
+            self._jobs = None
             s0 = self.specs[0]
             if s0.kind == 'conv' and s0.stride == 2 and s0.c2 == 0:
                 self.packed[0].wfirst = torch.zeros((s0.np, s0.cin * 16), device=dev, dtype=TORCH_DT[Config.fwd_dt])
@@ -393,8 +400,6 @@ class NetEngine:
                 self._jobs = (ptrs,) + self._build_jobs(ps, dev)
             _, table, njobs, ntiles = self._jobs
             L.call('pg_pack_weights_multi', table.data_ptr(), njobs, ntiles, _stream())
-            for pw in self.packed:
-                pw.pack_w16(ps[pw.spec.wname].detach())
             self._stamp = stamp
 
     JOB_DT = np.dtype([('src', '<u8'), ('dst', '<u8'), ('sn', '<i8'), ('sc', '<i8'), ('N', '<i4'), ('Np', '<i4'),
@@ -412,6 +417,12 @@ class NetEngine:
                 ctiles = (C1p + C2p + 31) // 32
                 rows.append((src, dst, sn, sc, N, Np, C1, C1p, C2, C2p, flip, dt, tile, ctiles))
                 tile += ctiles * ((Np + 7) // 8)
+            # flat operand copies (flip = 2): first-layer [N][Cin*16] and tap-product [Cin][16] keep the master layout
+            for dst_t, dt in ((pw.wfirst, pw.fwd_dt), (pw.w16, BF16)):
+                if dst_t is not None:
+                    n = w.numel()
+                    rows.append((w.data_ptr(), dst_t.data_ptr(), n, 0, 0, 0, 0, 0, 0, 0, 2, dt, tile, 1))
+                    tile += (n + 4095) // 4096
         arr = np.array(rows, dtype=self.JOB_DT)
         table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
         return table, len(rows), tile
@@ -535,12 +546,12 @@ class GeneratorEngine(NetEngine):
                 raise ValueError('Expected more than 1 spatial element when training (input too small for 7 '
                                  'stride-2 stages)')
             raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
+            sums = zeros((B, s.np, 2), dev)
             if h.im2col:
-                first_conv(h, self.packed[i].wfirst, None, 0, raw)
+                first_conv(h, self.packed[i].wfirst, None, 0, raw, sums)
             else:
                 run_conv(conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, raw.ld, out_dt=F32,
-                                   in_dt=h.dt), h, None, self.packed[i].fwd, None, raw)
-            sums = instnorm_stats(raw)
+                                   in_dt=h.dt), h, None, self.packed[i].fwd, None, raw, sums)
             out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt, twin=save)
             dp = DROP_P if (training and s.dropout) else 0.0
             norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, i)
@@ -555,9 +566,9 @@ class GeneratorEngine(NetEngine):
             c2, ld2 = (src2.C, src2.ld) if src2 is not None else (0, 0)
             if s.norm:
                 raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
+                sums = zeros((B, s.np, 2), dev)
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, raw.ld,
-                                   out_dt=F32, in_dt=src1.dt), src1, src2, pw.fwd, None, raw)
-                sums = instnorm_stats(raw)
+                                   out_dt=F32, in_dt=src1.dt), src1, src2, pw.fwd, None, raw, sums)
                 out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt, twin=save)
                 dp = DROP_P if (training and s.dropout) else 0.0
                 norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, 16 + i)
