@@ -108,6 +108,12 @@ int pg_tcgen05_available(void);
  * setup, first operands landed, last MMA issued, accumulator ready, epilogue done, exit; SM id) at buf[cta*16 ...]. */
 int pg_debug_set_trace(void* buf);
 
+/* Caller-owned device scratch for the split-K convolutions (the 2x2 .. 16x16 bottleneck layers run their K = 16*Cin
+ * reduction on a cluster of CTAs that exchange fp32 partial tiles through this L2-resident buffer).  256-byte aligned;
+ * 64 MB covers every layer of the reference configurations; NULL / 0 disables split-K (N is split instead).  The buffer must
+ * stay alive while convolutions are in flight; successive launches take successive slices. */
+int pg_conv_set_workspace(void* ws, int64_t bytes);
+
 /* ---- convolutions: replaces aten::convolution behind nn.Conv2d / nn.ConvTranspose2d
  *      (unet.py:19, unet.py:53, disc.py:19,27,37,45) and their autograd dgrad ---- */
 /* out2 (nullable): a second, bf16 copy of the output with the same pixel stride.  tcgen05 kind::f16 needs both

@@ -29,6 +29,7 @@ _SIGS = {
     'pg_version': ([], C.c_int),
     'pg_tcgen05_available': ([], C.c_int),
     'pg_debug_set_trace': ([vp], C.c_int),
+    'pg_conv_set_workspace': ([vp, i64], C.c_int),
     'pg_launch_count': ([], C.c_int64),
     'pg_last_conv_impl': ([], C.c_int),
     'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),

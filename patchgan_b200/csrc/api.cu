@@ -37,6 +37,7 @@ int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int,
 bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int);
 bool tc_device_ok();
 void set_tc_trace(void*);
+void set_conv_workspace(void*, size_t);
 // conv_skinny.cu
 bool conv_fewout_supported(const PgConvDesc*);
 int conv_fewout(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, cudaStream_t);
@@ -85,6 +86,11 @@ extern "C" int64_t pg_launch_count(void) { return (int64_t)g_launches; }
 extern "C" int pg_last_conv_impl(void) { return g_last_impl; }
 extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
 extern "C" int pg_debug_set_trace(void* buf) { set_tc_trace(buf); return PG_OK; }
+extern "C" int pg_conv_set_workspace(void* ws, int64_t bytes) {
+  PG_REQUIRE((ws == nullptr) == (bytes == 0) && bytes >= 0 && (((uintptr_t)ws) & 255) == 0, "pg_conv_set_workspace: bad buffer");
+  set_conv_workspace(ws, (size_t)bytes);
+  return PG_OK;
+}
 
 extern "C" int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_t HW, int32_t C, int32_t ld, float* sums,
                                  void* stream);

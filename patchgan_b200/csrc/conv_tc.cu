@@ -164,7 +164,7 @@ struct TcParams {
   int tma_store, st_rowbytes, st_cw, st_nbuf, st_twin;
   unsigned long long* trace;   // debug: 8 timestamps per CTA (pg_debug_set_trace), else null
   int splits, kps;             // K-split cluster: `splits` CTAs (cluster dims (1,1,splits)) share one tile, kps k-steps each
-  uint32_t dump_pitch;         // bytes per accumulator row in the split-K exchange buffer
+  float* ws;                   // split-K exchange buffer in global memory (L2-resident): [tile][rank][128 rows][BN] fp32
   float* stats;                // fused InstanceNorm statistics: sums[(b*N + n)*2 + {0,1}] += {x, x^2} over the tile (or null)
 };
 
@@ -454,21 +454,27 @@ __device__ __forceinline__ uint32_t cluster_rank() {
   return r;
 }
 
-__device__ __forceinline__ void split_dump(const TcParams& p, const EpiCtx& e) {
+// Exchange through L2: every CTA stores its partial tile (64-byte runs per thread) into its slot of a global scratch
+// buffer, the cluster barrier (release / acquire at cluster scope) orders the stores before the owners' loads.
+// (Distributed shared memory was tried first: ld.shared::cluster reached ~8 GB/s per SM and st.shared::cluster ~15 GB/s,
+// 4-8x slower than the same bytes through L2.)
+__device__ __forceinline__ void split_push(const TcParams& p, const EpiCtx& e, int rank, long long tile_id) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3, r = q * 32 + lane;
   const uint32_t trow = e.tmem_acc + ((uint32_t)(q * 32) << 16);
-  const uint32_t row = e.smem_base + (uint32_t)r * p.dump_pitch;
+  float* dst = p.ws + ((tile_id * p.splits + rank) * 128 + r) * p.BN;
   for (int c = 0; c < p.BN; c += 16) {
     uint32_t v[16];
     epi_tmem<16>(p, trow, c, v);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) st_shared_v4(row + (uint32_t)(c + 4 * j) * 4, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+    for (int j = 0; j < 4; ++j)
+      __stcg(reinterpret_cast<float4*>(dst + c) + j, make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                                 __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
   }
 }
 
 template <int ACT>
-__device__ __forceinline__ void split_reduce_store(const TcParams& p, const EpiCtx& e, int rank) {
+__device__ __forceinline__ void split_reduce_store(const TcParams& p, const EpiCtx& e, int rank, long long tile_id) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q = warp & 3, r = q * 32 + lane;
   const int xl = r & (p.TW - 1);
@@ -481,22 +487,22 @@ __device__ __forceinline__ void split_reduce_store(const TcParams& p, const EpiC
   const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
   const int s_b = e.b0 + (r >> (p.lgTW + p.lgTH));
   const int w = p.BN / p.splits;
-  const uint32_t row = e.smem_base + (uint32_t)r * p.dump_pitch;
+  const float* src0 = p.ws + ((tile_id * p.splits) * 128 + r) * p.BN;
   for (int c = rank * w; c < (rank + 1) * w; c += 16) {
     float acc[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = 0.f;
-    for (int peer = 0; peer < p.splits; ++peer) {
-      uint32_t remote;
-      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(row + (uint32_t)c * 4), "r"(peer));
+    for (int src = 0; src < p.splits; src += 2) {
+      float4 t[8];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float4 t;
-        asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
-                     : "r"(remote + 16u * j)
-                     : "memory");
-        acc[4 * j] += t.x; acc[4 * j + 1] += t.y; acc[4 * j + 2] += t.z; acc[4 * j + 3] += t.w;
+        t[j] = __ldcg(reinterpret_cast<const float4*>(src0 + (long long)src * 128 * p.BN + c) + j);
+        t[4 + j] = __ldcg(reinterpret_cast<const float4*>(src0 + (long long)(src + 1) * 128 * p.BN + c) + j);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        acc[4 * j] += t[j].x + t[4 + j].x; acc[4 * j + 1] += t[j].y + t[4 + j].y;
+        acc[4 * j + 2] += t[j].z + t[4 + j].z; acc[4 * j + 3] += t[j].w + t[4 + j].w;
       }
     }
     uint32_t v[16];
@@ -588,6 +594,7 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
   const int py = cls >> 1, px = cls & 1;
   const int nk = p.nk1 + p.nk2;
   const int ks0 = split * p.kps, ks1 = ks0 + p.kps;                 // this CTA's k-steps (all of them without split-K)
+  const long long tile_id = blockIdx.x + (long long)gridDim.x * (blockIdx.y + (long long)gridDim.y * cls);
   if (threadIdx.x == 0) {
     trace_put(p, 0);
     if (p.trace != nullptr) {
@@ -688,7 +695,8 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
     if (threadIdx.x == 64) trace_put(p, 4);
     const EpiCtx e{smem_base, tmem_acc, x0, y0, b0, n0, py, px, cls};
     if (p.splits > 1) {
-      split_dump(p, e);       // partial accumulators -> this CTA's shared memory; reduced after the cluster barrier below
+      split_push(p, e, split, tile_id);   // partial accumulators -> this CTA's slot of the L2 exchange buffer
+      if (threadIdx.x == 64) trace_put(p, 11);
     } else
     // one uniform dispatch per CTA: the per-element code below is straight-line (4 epilogue warps = one warp per
     // scheduler, so every branch / dependent-issue bubble of a per-element `switch` was fully exposed: 0.1 us per
@@ -712,18 +720,19 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
     }
   }
   if (p.splits > 1) {
-    cluster_sync_all();                                   // every peer's partial tile is in its shared memory
+    cluster_sync_all();                                   // every peer's partial tile is visible (release / acquire)
+    if (threadIdx.x == 64) trace_put(p, 12);
     if (warp >= 2) {
       const EpiCtx e{smem_base, tmem_acc, x0, y0, b0, n0, py, px, cls};
       switch (p.act) {
-        case PG_ACT_RELU: split_reduce_store<PG_ACT_RELU>(p, e, split); break;
-        case PG_ACT_LEAKYRELU: split_reduce_store<PG_ACT_LEAKYRELU>(p, e, split); break;
-        case PG_ACT_TANH: split_reduce_store<PG_ACT_TANH>(p, e, split); break;
-        case PG_ACT_SIGMOID: split_reduce_store<PG_ACT_SIGMOID>(p, e, split); break;
-        default: split_reduce_store<PG_ACT_NONE>(p, e, split); break;
+        case PG_ACT_RELU: split_reduce_store<PG_ACT_RELU>(p, e, split, tile_id); break;
+        case PG_ACT_LEAKYRELU: split_reduce_store<PG_ACT_LEAKYRELU>(p, e, split, tile_id); break;
+        case PG_ACT_TANH: split_reduce_store<PG_ACT_TANH>(p, e, split, tile_id); break;
+        case PG_ACT_SIGMOID: split_reduce_store<PG_ACT_SIGMOID>(p, e, split, tile_id); break;
+        default: split_reduce_store<PG_ACT_NONE>(p, e, split, tile_id); break;
       }
+      if (threadIdx.x == 64) trace_put(p, 13);
     }
-    cluster_sync_all();                                   // nobody leaves while a peer still reads its shared memory
   }
   if (threadIdx.x == 64) trace_put(p, 5);
   tc_fence_before();
@@ -775,6 +784,12 @@ bool tc_device_ok() {
 static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
+// Split-K exchange scratch (caller-owned, pg_conv_set_workspace): consecutive split launches take consecutive slices so
+// that launches in flight on different streams never share one.
+static float* g_ws = nullptr;
+static size_t g_ws_bytes = 0, g_ws_next = 0;
+void set_conv_workspace(void* ws, size_t bytes) { g_ws = (float*)ws; g_ws_bytes = bytes; g_ws_next = 0; }
+
 struct TcPlan {
   TcParams p;
   int swz;  // bytes
@@ -813,12 +828,14 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
     const long long mtiles = (long long)p.nx * p.ny * nb * (d->mode == PG_CONVT ? 4 : 1);
     const int ksteps0 = p.ntaps * (p.nk1 + p.nk2);
     static const int splitk_env = [] { const char* e = getenv("PG_TC_SPLITK"); return e ? atoi(e) : 1; }();
-    int sbn = bn > 128 ? 128 : bn;
-    if (splitk_env && d->mode != PG_CONV1X1 && mtiles * (d->N / sbn) * 2 <= num_sms() && ksteps0 >= 8) {
-      int S = 8;
+    // 128 x 64 tiles, clusters of <= 4: the exchanged partial tile is 32 KB, 4-SM clusters pack into every GPC, and
+    // two such CTAs fit one SM
+    int sbn = bn > 64 ? 64 : bn;
+    if (splitk_env && g_ws != nullptr && d->mode != PG_CONV1X1 && mtiles * (d->N / sbn) * 2 <= num_sms() && ksteps0 >= 8) {
+      int S = 4;
       while (S > 1 && (sbn / S < 16 || (ksteps0 % S) != 0 || ksteps0 / S < 2)) S >>= 1;
       while (S > 2 && mtiles * (d->N / sbn) * S > 2LL * num_sms()) S >>= 1;
-      if (S > 1) { p.splits = S; bn = sbn; }
+      if (S > 1 && (size_t)mtiles * (d->N / sbn) * S * 128 * sbn * 4 <= g_ws_bytes) { p.splits = S; bn = sbn; }
     }
     if (p.splits == 1)
       while (bn > 16 && mtiles * (d->N / bn) < num_sms()) bn >>= 1;
@@ -845,7 +862,7 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
     const long long ctas = (long long)p.nx * p.ny * nb * (d->N / bn) * (d->mode == PG_CONVT ? 4 : 1) * p.splits;
     const int want = (int)((ctas + num_sms() - 1) / num_sms());
     if (occ > want) occ = want < 1 ? 1 : want;
-    if (p.splits > 1) occ = 1;                 // the exchange buffer lives in the ring: keep the full ring per CTA
+    if (p.splits > 1 && occ < 2) occ = 2;      // split-K CTAs are short: half a ring each, so two clusters can share SMs
   }
   static const int nacc_env = [] { const char* e = getenv("PG_TC_NACC"); return e ? atoi(e) : 4; }();
   {
@@ -872,8 +889,6 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
   p.stages = stages;
   p.tmem_cols = (uint32_t)tmem_need;
   pl.smem = (size_t)stages * per_stage + 1024;
-  p.dump_pitch = (uint32_t)bn * 4u + 16u;      // +16 B: consecutive rows start 4 banks apart
-  if (p.splits > 1 && pl.smem < (size_t)128 * p.dump_pitch + 1024) pl.smem = (size_t)128 * p.dump_pitch + 1024;
   pl.grid = dim3((unsigned)(p.nx * p.ny * nb), (unsigned)(d->N / bn), (unsigned)((d->mode == PG_CONVT ? 4 : 1) * p.splits));
   // TMA box limits
   if (p.TW > 256 || p.TH > 256 || p.TB > 256) return false;
@@ -1008,6 +1023,10 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
             pl.grid.x, pl.grid.y, pl.grid.z, p.BN, p.BK, p.stages, p.nacc, p.tmem_cols, pl.smem, p.TW, p.TH, p.TB,
             p.ntaps * (p.nk1 + p.nk2), p.splits);
   if (p.splits > 1) {
+    const size_t need = (size_t)pl.grid.x * pl.grid.y * pl.grid.z * 128 * p.BN * 4;
+    if (g_ws_next + need > g_ws_bytes) g_ws_next = 0;
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g_ws) + g_ws_next);
+    g_ws_next += (need + 255) & ~(size_t)255;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = pl.grid;

@@ -105,6 +105,7 @@ def begin_step():
     """Drop the previous step's buffers (all streams were joined at its end) and start keeping this step's."""
     global _KEEPING
     del _KEEP[:]
+    _FORKED.clear()
     _KEEPING = True
 
 
@@ -127,14 +128,20 @@ def side_streams(device, n=3):
     return _SIDE[key]
 
 
+_FORKED = set()
+
+
 def fork(side):
     """`side` continues after everything issued so far on the current stream."""
     side.wait_stream(torch.cuda.current_stream())
+    _FORKED.add(side)
 
 
 def join(side):
-    """The current stream continues after everything issued so far on `side`."""
-    torch.cuda.current_stream().wait_stream(side)
+    """The current stream continues after everything issued so far on `side` (no-op if `side` was never forked in this
+    step: joining a stream that is not part of the graph being captured would be an error)."""
+    if side in _FORKED:
+        torch.cuda.current_stream().wait_stream(side)
 
 
 def zeros(shape, device, dtype=torch.float32):
@@ -186,6 +193,19 @@ def desc_tag(d):
             f"C{d.C1}+{d.C2} N{d.N}")
 
 
+_WS = {}
+
+
+def ensure_workspace(device):
+    """Register the split-K exchange scratch of the library (one 64 MB buffer per device, allocated once)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if _WS.get('cur') != key:
+        if key not in _WS:
+            _WS[key] = torch.empty(64 << 20, device=device, dtype=torch.uint8)
+        L.call('pg_conv_set_workspace', _WS[key].data_ptr(), _WS[key].numel())
+        _WS['cur'] = key
+
+
 def run_conv(desc, src1, src2, w, bias, out, stats=None):
     """stats: zeroed float32 (B, N, 2) tensor -> also accumulates the InstanceNorm sums of the output."""
     if L.PROFILER is not None:
@@ -200,9 +220,14 @@ def run_conv(desc, src1, src2, w, bias, out, stats=None):
            Config.impl, _stream())
 
 
+SKIP = set(filter(None, os.environ.get('PATCHGAN_B200_SKIP', '').split(',')))   # timing experiments only
+
+
 def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream=None):
     """wstream: issue the weight-gradient on that side stream (it forks here, after its operands were produced on
     the current stream; the caller joins it before the optimizer step)."""
+    if 'wgrad' in SKIP:
+        return
     if wstream is not None:
         fork(wstream)
         with torch.cuda.stream(wstream):
@@ -383,6 +408,8 @@ class NetEngine:
     def ensure_packed(self):
         ps = self.params()
         dev = self.device()
+        if dev.type == 'cuda':
+            ensure_workspace(dev)
         if dev.type != 'cuda':
             raise RuntimeError('patchgan_b200: module parameters must live on a CUDA device (no CPU path)')
         stamp = tuple((ps[s.wname].data_ptr(), ps[s.wname]._version) for s in self.specs)

@@ -189,7 +189,8 @@ class Trainer:
             if ms:
                 E.fork(s_d)
             with on(s_d):
-                D.backward(dctx, dz, dgrads, need_dx=False, wstream=s_dw)
+                if 'dstep' not in E.SKIP:
+                    D.backward(dctx, dz, dgrads, need_dx=False, wstream=s_dw)
                 if ms:
                     E.join(s_dw)
                 if world > 1:
@@ -222,22 +223,26 @@ class Trainer:
             L.call('pg_gen_out_bwd', p.ptr, p.ld, y.data_ptr(), chp, coef.data_ptr(), d_dinp.ptr, d_dinp.ld, cin,
                    d_raw.ptr, d_raw.ld, B, cout, H * W, lt, L.ACT[gm.final_act], float(self.tversky_beta), st)
             ggrads = {n: q.grad for n, q in gm.named_parameters()}
-            G.backward(gctx, d_raw, ggrads, wstream=s_w)
+            if 'gbwd' not in E.SKIP:
+                G.backward(gctx, d_raw, ggrads, wstream=s_w)
             if ms:
                 E.join(s_w)
             if world > 1:
                 g_work = dp.all_reduce_sum_async(gflat['g'])
                 gopt.grad_scale = 1.0 / world
                 g_work.wait()
-            gopt.step(sync_lr=False)
+            if 'adam' not in E.SKIP:
+                gopt.step(sync_lr=False)
             with on(s_d):
                 if ms:
                     s_d.wait_event(ev_dread)
                 if d_work is not None:
                     d_work.wait()
-                dopt.step(sync_lr=False)
-                D.repack()        # 16-bit operand copies of the new weights, ready for the next step
-            G.repack()
+                if 'adam' not in E.SKIP:
+                    dopt.step(sync_lr=False)
+                    D.repack()        # 16-bit operand copies of the new weights, ready for the next step
+            if 'adam' not in E.SKIP:
+                G.repack()
             if ms:
                 E.join(s_d)
         E.end_step()

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 from patchgan_b200 import _lib as L
-from patchgan_b200.engine import conv_desc
+from patchgan_b200.engine import conv_desc, ensure_workspace
 
 SHAPES = [  # mode stride pad B H Ci Co outdt
     ('conv', 2, 1, 16, 256, 16, 32), ('conv', 2, 1, 16, 128, 32, 64), ('conv', 2, 1, 16, 64, 64, 128),
@@ -49,9 +49,10 @@ def run(mode, stride, pad, B, H, Ci, Co):
     sm = t[:, 7]
     print(f'{mode} s{stride} B{B} {H}x{H} C{Ci}->N{Co}: ctas {n} sms {len(set(sm.tolist()))} event {us_plain:7.1f}us span {span:7.1f}us {flops/span/1e6:7.1f} TF/s | '
           f'start(med/max) {r(t[:,0]-t0)} setup {r(t[:,1]-t[:,0])} first-full {r(t[:,2]-t[:,1])} mainloop {r(t[:,3]-t[:,2])} '
-          f'mma-waited {np.median(t[:,8])/1.9e3:6.2f} prod-waited {np.median(t[:,9])/1.9e3:6.2f} prod-done {r(t[:,10]-t[:,1])} acc-wait {r(t[:,4]-t[:,3])} epi {r(t[:,5]-t[:,4])} exit {r(t[:,6]-t[:,5])} cta-life {r(t[:,6]-t[:,0])}')
+          f'mma-waited {np.median(t[:,8])/1.9e3:6.2f} prod-waited {np.median(t[:,9])/1.9e3:6.2f} prod-done {r(t[:,10]-t[:,1])} push {r(t[:,11]-t[:,4])} sync {r(t[:,12]-t[:,11])} reduce {r(t[:,13]-t[:,12])} acc-wait {r(t[:,4]-t[:,3])} epi {r(t[:,5]-t[:,4])} exit {r(t[:,6]-t[:,5])} cta-life {r(t[:,6]-t[:,0])}')
 
 if __name__ == '__main__':
+    ensure_workspace(torch.device('cuda', 0))
     pass
     sel = SHAPES if len(sys.argv) < 2 else [s for s in SHAPES if s[3] == 32]
     for s in sel:
