@@ -140,6 +140,21 @@ int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg
 /* (d->in_dtype is the type of `a`; d->out_f32 is reused as the PgDType of `g`: PG_BF16 or PG_F16; the tcgen05
  * implementation needs both to be the same type) */
 
+/* Same contraction accumulated TAP-MAJOR: S[(tap*Ns + n)*Cs + c] += sum g[..,n] * a[..(tap)..,c], n < Ns, c < Cs (fp32, the
+ * caller zeroes S; Cs % 4 == 0).  On the tcgen05 path every [128 n][32 c] accumulator tile of a tap is added with one TMA
+ * bulk reduce (cp.reduce.async.bulk.tensor .add) instead of per-element atomics; pg_grad_finalize_multi then writes the
+ * reference layout (Cout, Cin, 4, 4) of every layer of a network in one launch. */
+int pg_conv_wgrad_tapmajor(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* S, int32_t Ns, int32_t Cs,
+                           int impl, void* stream);
+typedef struct PgGradJob {
+  const float* S;      /* [16][Ns][Cs] */
+  float* dst;          /* dst[n*ld_n + c*16 + tap] = S[tap][n][c], n < N, c < C (overwrites) */
+  int64_t ld_n;
+  int32_t N, C, Ns, Cs;
+  int32_t tile_begin, ctiles;   /* first block of the job in the launch; ctiles = ceil(C/32); the job has N*ctiles blocks */
+} PgGradJob;
+int pg_grad_finalize_multi(const PgGradJob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream);
+
 /* ---- layers with ONE real channel on one side (generator output ConvTranspose2d(2nf -> 1), unet.py:106-107;
  *      discriminator last Conv2d(8ndf -> 1), disc.py:45; the mask-channel data-gradient of the discriminator's first
  *      layer, trainer.py:84-89).  They run as pointwise (PG_CONV1X1) products over the 16 taps on the tensor cores:

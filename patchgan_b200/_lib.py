@@ -35,6 +35,8 @@ _SIGS = {
     'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_fwd_stats': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_wgrad': ([DP, vp, vp, i32, vp, i32, i32, i32, C.c_int, vp], C.c_int),
+    'pg_conv_wgrad_tapmajor': ([DP, vp, vp, i32, vp, i32, i32, C.c_int, vp], C.c_int),
+    'pg_grad_finalize_multi': ([vp, i32, i32, vp], C.c_int),
     'pg_colsum': ([vp, i64, i32, i32, vp, vp], C.c_int),
     'pg_taps_scatter': ([i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp], C.c_int),
     'pg_taps_gather': ([i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp], C.c_int),

@@ -28,12 +28,12 @@ int check_launch(const char* what) {
 }
 
 int conv_fwd_simt(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, cudaStream_t);
-int conv_wgrad_simt(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
+int conv_wgrad_simt(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, int, int, cudaStream_t);
 // conv_tc.cu
 int conv_fwd_tc(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, float*, cudaStream_t);
 bool conv_fwd_tc_stats_ok(const PgConvDesc*);
 bool conv_fwd_tc_supported(const PgConvDesc*, const void*, const void*, const void*, const void*);
-int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
+int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, int, int, cudaStream_t);
 bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int);
 bool tc_device_ok();
 void set_tc_trace(void*);
@@ -167,8 +167,8 @@ extern "C" int pg_taps_gather(int32_t mode, int32_t stride, int32_t pad, int32_t
   return taps_gather(mode, stride, pad, B, Hq, Wq, Hp, Wp, src, lds, ch, G, (cudaStream_t)stream);
 }
 
-extern "C" int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw, int32_t ld_n,
-                             int32_t n_real, int32_t c_real, int impl, void* stream) {
+static int conv_wgrad_any(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw, int32_t ld_n,
+                          int32_t n_real, int32_t c_real, int tap_major, int Cs, int impl, void* stream) {
   if (int e = validate(d, "pg_conv_wgrad")) return e;
   PG_REQUIRE((d->mode == PG_CONV || d->mode == PG_CONV1X1) && d->C2 == 0,
              "pg_conv_wgrad: geometry must be PG_CONV / PG_CONV1X1 with one source");
@@ -176,26 +176,33 @@ extern "C" int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, 
   PG_REQUIRE(n_real <= d->N && c_real <= d->C1, "pg_conv_wgrad: n_real / c_real exceed padded extents");
   cudaStream_t s = (cudaStream_t)stream;
   g_last_impl = PG_IMPL_SIMT;
-  if (impl == PG_IMPL_SIMT) return conv_wgrad_simt(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
-  if (impl == PG_IMPL_SKINNY) {
+  if (impl == PG_IMPL_SIMT) return conv_wgrad_simt(d, a, g, ldg, dw, ld_n, n_real, c_real, tap_major, Cs, s);
+  if (impl == PG_IMPL_SKINNY && !tap_major) {
     if (conv_wgrad1_supported(d, ldg, dw, ld_n, n_real, c_real)) {
       g_last_impl = PG_IMPL_SKINNY;
       return conv_wgrad1(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
     }
-    if (impl == PG_IMPL_SKINNY) {
-      set_error("pg_conv_wgrad: shape does not qualify for the skinny kernels");
-      return PG_ERR_UNSUPPORTED;
-    }
+    set_error("pg_conv_wgrad: shape does not qualify for the skinny kernels");
+    return PG_ERR_UNSUPPORTED;
   }
-  const bool ok = conv_wgrad_tc_supported(d, a, g, ldg);
+  const bool ok = conv_wgrad_tc_supported(d, a, g, ldg) && !(tap_major && (Cs % 4) != 0);
   if (ok) g_last_impl = PG_IMPL_TCGEN05;
-  if (impl == PG_IMPL_TCGEN05) {
-    if (!ok) {
-      set_error("pg_conv_wgrad: tcgen05 path does not support this shape / alignment");
-      return PG_ERR_UNSUPPORTED;
-    }
-    return conv_wgrad_tc(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
+  if (impl == PG_IMPL_TCGEN05 && !ok) {
+    set_error("pg_conv_wgrad: tcgen05 path does not support this shape / alignment");
+    return PG_ERR_UNSUPPORTED;
   }
-  if (ok) return conv_wgrad_tc(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
-  return conv_wgrad_simt(d, a, g, ldg, dw, ld_n, n_real, c_real, s);
+  if (ok) return conv_wgrad_tc(d, a, g, ldg, dw, ld_n, n_real, c_real, tap_major, Cs, s);
+  return conv_wgrad_simt(d, a, g, ldg, dw, ld_n, n_real, c_real, tap_major, Cs, s);
+}
+
+extern "C" int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw, int32_t ld_n,
+                             int32_t n_real, int32_t c_real, int impl, void* stream) {
+  return conv_wgrad_any(d, a, g, ldg, dw, ld_n, n_real, c_real, 0, 0, impl, stream);
+}
+
+extern "C" int pg_conv_wgrad_tapmajor(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* S, int32_t Ns,
+                                      int32_t Cs, int impl, void* stream) {
+  PG_REQUIRE(d != nullptr && d->mode == PG_CONV, "pg_conv_wgrad_tapmajor: geometry must be PG_CONV");
+  PG_REQUIRE(Ns > 0 && Ns <= d->N && Cs > 0 && Cs <= d->C1, "pg_conv_wgrad_tapmajor: Ns / Cs exceed the padded extents");
+  return conv_wgrad_any(d, a, g, ldg, S, Ns, Ns, Cs, 1, Cs, impl, stream);
 }

@@ -167,6 +167,7 @@ struct WgradK {
   const bf16* g;
   float* dw;
   int stride, pad, B, Hin, Win, Hout, Wout, C, lda, N, ldg, ld_n, n_real, c_real, a_dt, g_dt, pointwise, ld_c;
+  long long ld_t;
   long long M;
   int chunk;  // pixels per split
   int ctiles;
@@ -238,13 +239,13 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradK p) {
     for (int j = 0; j < 4; ++j) {
       const int c = c0 + tx * 4 + j;
       if (c >= p.c_real) continue;
-      atomicAdd(p.dw + (long long)n * p.ld_n + (long long)c * p.ld_c + t, acc[i][j]);
+      atomicAdd(p.dw + (long long)n * p.ld_n + (long long)c * p.ld_c + (long long)t * p.ld_t, acc[i][j]);
     }
   }
 }
 
 int conv_wgrad_simt(const PgConvDesc* d, const void* a, const void* g, int ldg, float* dw, int ld_n, int n_real,
-                    int c_real, cudaStream_t stream) {
+                    int c_real, int tap_major, int Cs, cudaStream_t stream) {
   WgradK p;
   p.a = (const bf16*)a; p.g = (const bf16*)g; p.dw = dw;
   p.stride = d->stride; p.pad = d->pad; p.B = d->B; p.Hin = d->Hin; p.Win = d->Win; p.Hout = d->Hout;
@@ -254,6 +255,8 @@ int conv_wgrad_simt(const PgConvDesc* d, const void* a, const void* g, int ldg, 
   p.pointwise = d->mode == PG_CONV1X1 ? 1 : 0;
   p.ld_c = p.pointwise ? (d->ldw > 0 ? d->ldw : 16) : 16;
   const int taps = p.pointwise ? 1 : 16;
+  p.ld_t = 1;
+  if (tap_major) { p.ld_t = (long long)ld_n * Cs; p.ld_n = Cs; p.ld_c = 1; }   // S[tap][Ns = ld_n][Cs]
   p.M = (long long)d->B * d->Hout * d->Wout;
   const int ntiles = (d->N + 63) / 64;
   p.ctiles = (d->C1 + 63) / 64;

@@ -1073,6 +1073,8 @@ struct WgParams {
   float* dw;
   int ld_n, n_real, c_real;
   int pointwise, ld_c;     // PG_CONV1X1: one tap, no shift, dw[n*ld_n + c*ld_c]
+  int tapmajor;            // epilogue = TMA reduce-add of [128 n][ct c] tiles into S[tap][n][c] (mapS)
+  int st_rowbytes;         // bytes per staged row (128, or 64 when ct == 16)
   int n_atoms_load;        // G boxes that exist (the accumulator rows of the others are never stored)
   unsigned long long* trace;
 };
@@ -1098,8 +1100,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(map),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 2)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ ActMaps mapsA, const WgParams p) {
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ ActMaps mapsA,
+                const __grid_constant__ CUtensorMap mapS, const WgParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t gfull[WG_MAX_G], gempty[WG_MAX_G], afull[WG_MAX_A], aempty[WG_MAX_A];
   __shared__ __align__(8) uint64_t acc_bar;
@@ -1218,7 +1227,45 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
     mbar_wait(smem_u32(&acc_bar), 0);
     tc_fence_after();
     if (threadIdx.x == 64 && p.trace != nullptr) trace_raw(p.trace, 4, gtimer());
-    if (p.pointwise) {
+    if (p.tapmajor) {
+      // Tap-major accumulation: the [128 n][ct c] accumulator of tap t is staged in the (idle) operand ring with the
+      // TMA swizzle and added into S[t][n][c] by ONE bulk reduce per 32 columns (full 128-byte lines, tails clipped by
+      // the tensor map) -- instead of 128 x ct scattered 8/16-byte red.global per tap pair, which cost ~9 us per CTA
+      // and serialised on the few addresses of the small layers.
+      const int et = threadIdx.x - 64;
+      const int r = q * 32 + lane;
+      const int cw = p.st_rowbytes >> 2;                       // fp32 columns per staged row: 32 (or 16)
+      const uint32_t bufbytes = 128u * (uint32_t)p.st_rowbytes;
+      const int sh = p.st_rowbytes == 128 ? 0 : 1;
+      const uint32_t xr = (uint32_t)(r >> sh) & (uint32_t)((p.st_rowbytes >> 4) - 1);
+      int idx = 0;
+      for (int tl = 0; tl < p.T; ++tl) {
+        for (int cc = 0; cc < p.ct; cc += cw, ++idx) {
+          const int buf = idx & 1;
+          if (idx >= 2) {
+            if (et == 0) bulk_wait_read<1>();
+            epi_bar_sync();
+          }
+          const uint32_t row = smem_base + (uint32_t)buf * bufbytes + (uint32_t)r * p.st_rowbytes;
+          for (int sub = 0; sub < cw; sub += 16) {
+            uint32_t v[16];
+            tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)(tl * p.ct + cc + sub), v);
+            tmem_ld_wait();
+            const uint32_t u0 = (uint32_t)(sub * 4) >> 4;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              st_shared_v4(row + (((u0 + j) ^ xr) << 4), make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          }
+          fence_proxy_async();
+          epi_bar_sync();
+          if (et == 0) {
+            tma_reduce_add_3d(&mapS, smem_base + (uint32_t)buf * bufbytes, c0 + cc, n0, t0 + tl);
+            bulk_commit();
+          }
+        }
+      }
+      if (et == 0) bulk_wait_read<0>();
+    } else if (p.pointwise) {
       for (int c16 = 0; c16 < p.ct; c16 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)c16, v);
@@ -1353,16 +1400,39 @@ bool conv_wgrad_tc_supported(const PgConvDesc* d, const void* a, const void* g, 
   return make_wg_plan(d, p, grid, smem);
 }
 
+// tap_major != 0: dw is S[16][Ns = ld_n][Cs = c_stride] (fp32, zeroed by the caller); else the reference layout
 int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, float* dw, int ld_n, int n_real,
-                  int c_real, cudaStream_t stream) {
+                  int c_real, int tap_major, int Cs, cudaStream_t stream) {
   WgParams p; dim3 grid; size_t smem;
   if (!make_wg_plan(d, p, grid, smem)) {
     set_error("conv_wgrad_tc: unsupported shape");
     return PG_ERR_UNSUPPORTED;
   }
-  if (!p.pointwise && ((((uintptr_t)dw) & 15) != 0 || (ld_n % 4) != 0)) {
+  if (!p.pointwise && !tap_major && ((((uintptr_t)dw) & 15) != 0 || (ld_n % 4) != 0)) {
     set_error("conv_wgrad_tc: dw must be 16-byte aligned with ld_n %% 4 == 0");
     return PG_ERR_UNSUPPORTED;
+  }
+  CUtensorMap mS;
+  memset(&mS, 0, sizeof(mS));
+  p.tapmajor = 0;
+  if (tap_major) {
+    if (p.pointwise || (((uintptr_t)dw) & 15) != 0 || (Cs % 4) != 0 || Cs < c_real || ld_n < n_real) {
+      set_error("conv_wgrad_tc: bad tap-major scratch (Ns=%d Cs=%d)", ld_n, Cs);
+      return PG_ERR_UNSUPPORTED;
+    }
+    p.tapmajor = 1;
+    p.st_rowbytes = p.ct >= 32 ? 128 : 64;
+    cuuint64_t dims[3] = {(cuuint64_t)Cs, (cuuint64_t)ld_n, 16};
+    cuuint64_t strides[2] = {(cuuint64_t)Cs * 4, (cuuint64_t)Cs * ld_n * 4};
+    cuuint32_t box[3] = {(cuuint32_t)(p.st_rowbytes / 4), 128, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = get_encode()(&mS, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dw, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              p.st_rowbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled(tap-major dW Ns=%d Cs=%d) failed: %d", ld_n, Cs, (int)r);
+      return PG_ERR_CUDA;
+    }
   }
   p.dw = dw; p.ld_n = ld_n; p.n_real = n_real; p.c_real = c_real; p.ld_c = d->ldw > 0 ? d->ldw : 16;
   p.trace = g_trace;
@@ -1386,7 +1456,7 @@ int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, fl
     PG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
     smem_set = true;
   }
-  wgrad_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mG, mA, p);
+  wgrad_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mG, mA, mS, p);
   return check_launch("wgrad_tc_kernel");
 }
 

@@ -150,6 +150,41 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const float* __restrict_
   }
 }
 
+// Tap-major weight-gradient scratch S[tap][Ns][Cs] -> reference layout dst[n*ld_n + c*16 + tap] for every layer of a
+// network in ONE launch (jobs as in pack_weight_multi_kernel; one block = one n, 32 channels, 16 taps).
+struct GradJob {               // mirrors PgGradJob
+  const float* S;
+  float* dst;
+  long long ld_n;
+  int N, C, Ns, Cs;
+  int tile_begin, ctiles;
+};
+
+__global__ void __launch_bounds__(256) grad_finalize_multi_kernel(const GradJob* __restrict__ jobs, int njobs) {
+  __shared__ float tile[16][33];
+  __shared__ GradJob job;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+    }
+    job = jobs[lo];
+  }
+  __syncthreads();
+  const int local = blockIdx.x - job.tile_begin;
+  const int n = local / job.ctiles, c0 = (local % job.ctiles) * 32;
+  for (int e = threadIdx.x; e < 512; e += 256) {
+    const int t = e >> 5, cl = e & 31, c = c0 + cl;
+    tile[t][cl] = c < job.C ? job.S[((long long)t * job.Ns + n) * job.Cs + c] : 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 512; e += 256) {
+    const int cl = e >> 4, t = e & 15, c = c0 + cl;
+    if (c < job.C) job.dst[n * job.ld_n + (long long)c * 16 + t] = tile[t][cl];
+  }
+}
+
 // All weight tensors of a network in ONE launch: blockIdx.x walks a concatenated list of 8x32x16 bricks.
 struct PackJob {              // mirrors PgPackJob
   const float* src;
@@ -285,6 +320,13 @@ extern "C" int pg_im2col_s2(const float* src, int64_t sb, int64_t sc, int64_t sy
   im2col_s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, sb, sc, sy, sx, C, H, W, Ho, Wo, (unsigned short*)dst,
                                                          (unsigned short*)dst2, K, k_off, dst_dtype, per_c);
   return check_launch("im2col_s2_kernel");
+}
+
+extern "C" int pg_grad_finalize_multi(const PgGradJob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream) {
+  static_assert(sizeof(PgGradJob) == sizeof(GradJob), "PgGradJob layout");
+  PG_REQUIRE(jobs_dev != nullptr && njobs > 0 && total_tiles > 0, "pg_grad_finalize_multi: empty job list");
+  grad_finalize_multi_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>((const GradJob*)jobs_dev, njobs);
+  return check_launch("grad_finalize_multi_kernel");
 }
 
 extern "C" int pg_pack_weights_multi(const PgPackJob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream) {

@@ -148,8 +148,15 @@ def zeros(shape, device, dtype=torch.float32):
     return keep(torch.zeros(shape, device=device, dtype=dtype))
 
 
+_POISON = os.environ.get('PATCHGAN_B200_POISON', '0') != '0'    # debug: fill fresh buffers with NaN instead of leaving them
+
+
+def _empty_nan(shape, device, dtype):
+    return torch.full(shape, float('nan'), device=device, dtype=dtype)
+
+
 def new_act(B, H, W, C, device, dt=BF16, zero=False, twin=False):
-    fn = torch.zeros if zero else torch.empty
+    fn = torch.zeros if zero else (_empty_nan if _POISON else torch.empty)
     t = keep(fn((B, H, W, C), device=device, dtype=TORCH_DT[dt]))
     a = Act(t, B, H, W, C, dt=dt)
     if twin and dt == F16:
@@ -304,11 +311,12 @@ def nchw_strides(t):
     return (C * H * W, H * W, W, 1)
 
 
-def first_conv(a, w_first, bias, act, out, stats=None):
-    """First Conv2d(k4, s2, p1) on the im2col matrix: a pointwise product with the (Np, cin*16) weight matrix."""
+def first_conv(a, w_first, bias, act, out, n_valid, stats=None):
+    """First Conv2d(k4, s2, p1) on the im2col matrix: a pointwise product with the (Np, cin*16) weight matrix.
+    n_valid = real output channels (the bias has only that many entries; padded channels are stored as 0)."""
     run_conv(conv_desc(L.PG_CONV1X1, 1, 0, a.B, a.H, a.W, a.H, a.W, a.C, 0, a.ld, 0, w_first.shape[0], out.ld,
-                       n_valid=None, act=act, out_dt=out.dt, has_bias=int(bias is not None), in_dt=a.dt), a, None, w_first,
-             bias, out, stats)
+                       n_valid=n_valid, act=act, out_dt=out.dt, has_bias=int(bias is not None), in_dt=a.dt), a, None,
+             w_first, bias, out, stats)
 
 
 def first_wgrad(a, g, dw_ptr, n_real, wstream=None):
@@ -395,6 +403,8 @@ class NetEngine:
         self._stamp = None
         self._jobs = None
         self.seed = None   # device uint64 dropout counter
+        self._tm_buf = self._tm_table = self._tm_jobs = None
+        self._tm_off = 0
 
     def params(self):
         return dict(self.module.named_parameters())
@@ -453,6 +463,63 @@ class NetEngine:
         arr = np.array(rows, dtype=self.JOB_DT)
         table = torch.from_numpy(arr.view(np.uint8).copy()).to(dev)
         return table, len(rows), tile
+
+    # ---- weight-gradients accumulated tap-major (TMA bulk reduce) and written to the reference layout in one launch
+    GRAD_JOB_DT = np.dtype([('S', '<u8'), ('dst', '<u8'), ('ld_n', '<i8'), ('N', '<i4'), ('C', '<i4'), ('Ns', '<i4'),
+                            ('Cs', '<i4'), ('tile_begin', '<i4'), ('ctiles', '<i4')])
+
+    def begin_backward(self):
+        """Start collecting weight-gradient jobs for this backward pass; zero the tap-major scratch."""
+        self._tm_jobs = []
+        self._tm_off = 0
+        if taps_enabled():
+            if getattr(self, '_tm_buf', None) is None or self._tm_buf.device != self.device():
+                n = sum(p.numel() for p in self.module.parameters())
+                self._tm_buf = torch.empty(n + 64 * len(self.specs) * 4 + 1024, device=self.device(), dtype=torch.float32)
+                self._tm_table = None
+            self._tm_buf.zero_()
+
+    def wgrad(self, desc, a, g, dst_ptr, ld_n, n_real, c_real, wstream=None):
+        """Weight gradient of one (layer, source): dst[n*ld_n + c*16 + tap] (reference layout) receives it -- directly
+        (atomics) or, by default, through the tap-major scratch + finalize_grads()."""
+        jobs = getattr(self, '_tm_jobs', None)
+        if not (taps_enabled() and jobs is not None and desc.mode == L.PG_CONV) or 'wgrad' in SKIP:
+            return run_wgrad(desc, a, g, dst_ptr, ld_n, n_real, c_real, wstream)
+        Ns, Cs = n_real, (c_real + 3) // 4 * 4
+        need = 16 * Ns * Cs
+        off = (self._tm_off + 63) // 64 * 64            # 256-byte aligned slices
+        if off + need > self._tm_buf.numel():
+            return run_wgrad(desc, a, g, dst_ptr, ld_n, n_real, c_real, wstream)
+        self._tm_off = off + need
+        sp = self._tm_buf.data_ptr() + off * 4
+        jobs.append((sp, dst_ptr, ld_n, n_real, c_real, Ns, Cs))
+        if wstream is not None:
+            fork(wstream)
+        with torch.cuda.stream(wstream if wstream is not None else torch.cuda.current_stream()):
+            if L.PROFILER is not None:
+                L.PROFILER.note(conv_flops(desc), desc_tag(desc))
+            L.call('pg_conv_wgrad_tapmajor', ctypes.byref(desc), a.ptr, g.ptr, g.ld, sp, Ns, Cs, Config.impl, _stream())
+
+    def finalize_grads(self):
+        """Write every tap-major weight-gradient of this backward pass to its reference-layout destination (one launch).
+        Call on a stream that is ordered after all weight-gradient launches."""
+        jobs = getattr(self, '_tm_jobs', None)
+        self._tm_jobs = None
+        if not jobs:
+            return
+        key = tuple(jobs)
+        if self._tm_table is None or self._tm_table[0] != key:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError('patchgan_b200: weight-gradient job table changed during CUDA-graph capture')
+            rows, tile = [], 0
+            for (sp, dst, ld_n, N, C, Ns, Cs) in jobs:
+                ctiles = (C + 31) // 32
+                rows.append((sp, dst, ld_n, N, C, Ns, Cs, tile, ctiles))
+                tile += N * ctiles
+            arr = np.array(rows, dtype=self.GRAD_JOB_DT)
+            self._tm_table = (key, torch.from_numpy(arr.view(np.uint8).copy()).to(self.device()), len(rows), tile)
+        _, table, njobs, ntiles = self._tm_table
+        L.call('pg_grad_finalize_multi', table.data_ptr(), njobs, ntiles, _stream())
 
     def repack(self):
         """Unconditional repack (used inside captured graphs right after the optimizer step)."""
@@ -575,7 +642,7 @@ class GeneratorEngine(NetEngine):
             raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
             sums = zeros((B, s.np, 2), dev)
             if h.im2col:
-                first_conv(h, self.packed[i].wfirst, None, 0, raw, sums)
+                first_conv(h, self.packed[i].wfirst, None, 0, raw, s.cout, sums)
             else:
                 run_conv(conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, raw.ld, out_dt=F32,
                                    in_dt=h.dt), h, None, self.packed[i].fwd, None, raw, sums)
@@ -628,6 +695,7 @@ class GeneratorEngine(NetEngine):
         B = d_raw.B
         dskip = [None] * 7
         d_enc6 = None
+        self.begin_backward()
         for i in range(6, -1, -1):
             s = self.dec[i]
             src1, src2, raw, sums, out, dp = ctx['dec'][i]
@@ -653,11 +721,11 @@ class GeneratorEngine(NetEngine):
             # weight gradient: dW[ci][co][tap] = sum x[ci] * dY[co] -- PG_CONV geometry with A = dY, G = layer input
             wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C, src1.C,
                            out_dt=BF16, in_dt=BF16)
-            run_wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.c1, s.cout, wstream)
+            self.wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.c1, s.cout, wstream)
             if src2 is not None:
                 wd2 = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src2.H, src2.W, d_raw.C, 0, d_raw.ld, 0, src2.C,
                                 src2.C, out_dt=BF16, in_dt=BF16)
-                run_wgrad(wd2, d_raw, src2.b16, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout, wstream)
+                self.wgrad(wd2, d_raw, src2.b16, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout, wstream)
             # data gradient: stride-2 conv of dY with W'[ci][tap][co]
             din = new_act(B, src1.H, src1.W, s.cinp, dev)
             run_conv(conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
@@ -684,7 +752,7 @@ class GeneratorEngine(NetEngine):
             else:
                 wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
                                in_dt=BF16)
-                run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
+                self.wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
             if i > 0 or need_dx:
                 Hi, Wi = (2 * h.H, 2 * h.W) if h.im2col else (h.H, h.W)
                 din = new_act(B, Hi, Wi, s.cinp, dev)
@@ -692,6 +760,8 @@ class GeneratorEngine(NetEngine):
                          d_raw, None, self.packed[i].bwd, None, din)
                 dy1 = din
                 dx = din
+        if wstream is None:
+            self.finalize_grads()       # (with a side stream the caller joins it first, then calls finalize_grads)
         return dx if need_dx else None
 
 
@@ -778,7 +848,7 @@ class DiscriminatorEngine(NetEngine):
             else:
                 t = t.images(b0, nb)
                 if h.im2col:
-                    first_conv(h, self.packed[li].wfirst, bias if s.bias else None, L.ACT[s.act], t)
+                    first_conv(h, self.packed[li].wfirst, bias if s.bias else None, L.ACT[s.act], t, s.cout)
                 else:
                     run_conv(conv_desc(L.PG_CONV, s.stride, 1, nb, h.H, h.W, t.H, t.W, h.C, 0, h.ld, 0, s.np, t.ld,
                                        n_valid=s.cout, act=L.ACT[s.act], out_dt=t.dt, has_bias=int(s.bias), in_dt=h.dt),
@@ -795,6 +865,8 @@ class DiscriminatorEngine(NetEngine):
         dev = d_raw.t.device
         B = d_raw.B if nb is None else nb
         din = None
+        if grads is not None:
+            self.begin_backward()
         for li in range(len(self.specs) - 1, -1, -1):
             s = self.specs[li]
             h, t, sums, out = ctx[li]
@@ -810,7 +882,7 @@ class DiscriminatorEngine(NetEngine):
                 else:
                     wd = conv_desc(L.PG_CONV, s.stride, 1, B, h.H, h.W, d_raw.H, d_raw.W, h.C, 0, h.ld, 0, s.np, s.np,
                                    out_dt=BF16, in_dt=BF16)
-                    run_wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
+                    self.wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
                 if s.bias:
                     with torch.cuda.stream(wstream if wstream is not None else torch.cuda.current_stream()):
                         L.call('pg_colsum', d_raw.ptr, B * d_raw.H * d_raw.W, d_raw.ld, s.cout,
@@ -846,4 +918,6 @@ class DiscriminatorEngine(NetEngine):
                     d_raw = act_bwd_out(pt, dt, L.ACT[ps.act])
                 else:
                     d_raw = act_bwd_out(pt, din, L.ACT[ps.act])
+        if grads is not None and wstream is None:
+            self.finalize_grads()
         return din if need_dx else None

@@ -193,6 +193,7 @@ class Trainer:
                     D.backward(dctx, dz, dgrads, need_dx=False, wstream=s_dw)
                 if ms:
                     E.join(s_dw)
+                    D.finalize_grads()
                 if world > 1:
                     d_work = dp.all_reduce_sum_async(dflat['g'])
                     dopt.grad_scale = 1.0 / world
@@ -227,6 +228,7 @@ class Trainer:
                 G.backward(gctx, d_raw, ggrads, wstream=s_w)
             if ms:
                 E.join(s_w)
+                G.finalize_grads()
             if world > 1:
                 g_work = dp.all_reduce_sum_async(gflat['g'])
                 gopt.grad_scale = 1.0 / world
@@ -246,6 +248,14 @@ class Trainer:
             if ms:
                 E.join(s_d)
         E.end_step()
+        if os.environ.get('PATCHGAN_B200_DEBUGNAN') and not torch.cuda.is_current_stream_capturing():
+            torch.cuda.synchronize()
+            print('[debugnan] losses', losses.cpu().numpy(), 'train', train, flush=True)
+            for i, t in enumerate(E._KEEP):
+                tf = t.float()
+                nan = int(torch.isnan(tf).sum())
+                if nan:
+                    print('[debugnan]', i, tuple(t.shape), t.dtype, 'nan', nan, 'of', tf.numel(), flush=True)
         return losses
 
     def _graph_key(self, x, y, train):

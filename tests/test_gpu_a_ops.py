@@ -370,3 +370,31 @@ def test_inference_tiling_bit_exact():
         torch.cuda.synchronize()
         assert np.array_equal(mo[0].cpu().numpy(), orc.build_mask(masks[:, :1], size, (Hh, Ww), 0.5, overlap)
                               .astype(np.float32))
+
+
+@pytest.mark.parametrize('impl', IMPLS, ids=IMPL_IDS)
+@pytest.mark.parametrize('case', [(2, 32, 64, 32, 2), (2, 256, 512, 16, 1), (3, 64, 64, 4, 2), (2, 128, 256, 32, 2),
+                                  (1, 64, 128, 31, 1), (2, 48, 96, 20, 2), (2, 16, 7, 12, 2)], ids=str)
+def test_conv2d_weight_gradient_tap_major_and_finalize(case, impl):
+    """pg_conv_wgrad_tapmajor (TMA bulk-reduce epilogue on the tcgen05 path) + pg_grad_finalize_multi == reference layout."""
+    from patchgan_b200.engine import NetEngine
+    B, Ci, Co, H, s = case
+    r = rng(7)
+    x = bf16_round(r.standard_normal((B, Ci, H, H)))
+    w = r.standard_normal((Co, Ci, 4, 4)).astype(np.float32)
+    Ho = (H + 2 - 4) // s + 1
+    dy = bf16_round(r.standard_normal((B, Co, Ho, Ho)))
+    _, ref, _ = orc.conv2d_bwd(x, w, dy, s, has_bias=True, need_dx=False)
+    Cip, Cop = rup16(Ci), rup16(Co)
+    Cs = (Ci + 3) // 4 * 4
+    S = torch.zeros((16, Co, Cs), device='cuda')
+    d = conv_desc(L.PG_CONV, s, 1, B, H, H, Ho, Ho, Cip, 0, Cip, 0, Cop, Cop, out_dt=L.DT_BF16, in_dt=L.DT_BF16)
+    xd, dyd = to_nhwc(x), to_nhwc(dy)
+    for _ in range(2):       # two accumulating calls: the scratch must hold the sum
+        L.call('pg_conv_wgrad_tapmajor', ctypes.byref(d), xd.data_ptr(), dyd.data_ptr(), Cop, S.data_ptr(), Co, Cs, impl, stream())
+    dw = torch.full((Co, Ci, 4, 4), 7.0, device='cuda')
+    job = np.array([(S.data_ptr(), dw.data_ptr(), Ci * 16, Co, Ci, Co, Cs, 0, (Ci + 31) // 32)], dtype=NetEngine.GRAD_JOB_DT)
+    table = torch.from_numpy(job.view(np.uint8).copy()).cuda()
+    L.call('pg_grad_finalize_multi', table.data_ptr(), 1, Co * ((Ci + 31) // 32), stream())
+    torch.cuda.synchronize()
+    assert relerr(dw.cpu().numpy(), 2 * ref) < 1e-4
