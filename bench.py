@@ -136,9 +136,10 @@ class CallProfiler:
     def end(self, tok):
         e = self.torch.cuda.Event(enable_timing=True)
         e.record()
-        name = tok[0]
+        # same CUDA kernels behind three entry points each: + fused statistics, + TMA bulk-reduce epilogue
+        name = {'pg_conv_fwd_stats': 'pg_conv_fwd', 'pg_conv_wgrad_tapmajor': 'pg_conv_wgrad'}.get(tok[0], tok[0])
         if name in ('pg_conv_fwd', 'pg_conv_wgrad'):
-            name += ':tcgen05' if self.lib.pg_last_conv_impl() == 2 else ':simt'
+            name += {2: ':tcgen05', 3: ':skinny'}.get(self.lib.pg_last_conv_impl(), ':simt')
         self.rec.append((name, tok[1], tok[2], e, tok[3]))
 
     def summary(self):
