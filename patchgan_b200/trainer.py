@@ -87,9 +87,12 @@ class Trainer:
             return torch.as_tensor(a, dtype=torch.float).to(self.device)
         return a.to(self.device, non_blocking=True)
 
-    def step_device(self, x, y, train):
+    def step_device(self, x, y, train, phase='all'):
         """Issue the whole step on the current stream.  x, y: CUDA float NCHW.  Returns the device tensor
-        [seg*alpha, gdisc, discr, discf] (no host sync)."""
+        [seg*alpha, gdisc, discr, discf] (no host sync).
+        phase='grads' stops after both backward passes (gradients complete in the flat buffers, all side streams
+        joined, no all-reduce, no optimizer step): the data-parallel path replays that part and `update_device` as two
+        CUDA graphs with the NCCL all-reduces between them."""
         G, D = self.generator._engine(), self.discriminator._engine()
         gm, dm = self.generator, self.discriminator
         if self.loss_type not in ('tversky', 'weighted_bce', 'MAE'):
@@ -194,7 +197,7 @@ class Trainer:
                 if ms:
                     E.join(s_dw)
                     D.finalize_grads()
-                if world > 1:
+                if world > 1 and phase == 'all':
                     d_work = dp.all_reduce_sum_async(dflat['g'])
                     dopt.grad_scale = 1.0 / world
 
@@ -229,6 +232,11 @@ class Trainer:
             if ms:
                 E.join(s_w)
                 G.finalize_grads()
+            if phase == 'grads':
+                if ms:
+                    E.join(s_d)
+                E.end_step()
+                return losses
             if world > 1:
                 g_work = dp.all_reduce_sum_async(gflat['g'])
                 gopt.grad_scale = 1.0 / world
@@ -258,6 +266,26 @@ class Trainer:
                     print('[debugnan]', i, tuple(t.shape), t.dtype, 'nan', nan, 'of', tf.numel(), flush=True)
         return losses
 
+    def update_device(self):
+        """Second half of a data-parallel step: both Adam updates and operand repacks (the flat gradient buffers already
+        hold the all-reduced sums; 1/world is folded into the Adam kernel)."""
+        G, D = self.generator._engine(), self.discriminator._engine()
+        world = dp.world_size()
+        self.gen_optimizer.grad_scale = self.disc_optimizer.grad_scale = 1.0 / world
+        ms = E.Config.streams and L.PROFILER is None
+        dev = next(self.generator.parameters()).device
+        s_d = E.side_streams(dev)[0] if ms else None
+        if ms:
+            E._FORKED.clear()
+            E.fork(s_d)
+        with (torch.cuda.stream(s_d) if ms else contextlib.nullcontext()):
+            self.disc_optimizer.step(sync_lr=False)
+            D.repack()
+        self.gen_optimizer.step(sync_lr=False)
+        G.repack()
+        if ms:
+            E.join(s_d)
+
     def _graph_key(self, x, y, train):
         return (tuple(x.shape), tuple(y.shape), bool(train), self.loss_type, float(self.seg_alpha),
                 float(self.tversky_beta), float(self.tversky_gamma), self.generator.training,
@@ -269,6 +297,9 @@ class Trainer:
         if not self.use_cuda_graph or L.PROFILER is not None or \
                 (dp.world_size() > 1 and os.environ.get('PATCHGAN_B200_GRAPH_DP', '1') == '0'):
             return self.step_device(x, y, train)
+        # data-parallel: NCCL is kept out of the graphs (capturing the process group's collectives hung on this stack):
+        # graph A = everything up to the finished gradients, eager all-reduces, graph B = Adam + repack of both networks
+        split = dp.world_size() > 1
         key = self._graph_key(x, y, train)
         ent = self._graphs.get(key)
         if ent is None:
@@ -287,9 +318,16 @@ class Trainer:
             self.discriminator._engine().ensure_packed()
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                ent['losses'] = self.step_device(ent['x'], ent['y'], train)
+            # (the process-group watchdog thread may poll events while we capture: check this thread's calls only)
+            mode = 'thread_local' if split else 'global'
+            with torch.cuda.graph(g, capture_error_mode=mode):
+                ent['losses'] = self.step_device(ent['x'], ent['y'], train, phase='grads' if split else 'all')
             ent['graph'] = g
+            if split and train:
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, capture_error_mode=mode):
+                    self.update_device()
+                ent['graph_update'] = g2
             # the capture itself executed nothing: fall through to the first replay
         ent['x'].copy_(x, non_blocking=True)
         ent['y'].copy_(y, non_blocking=True)
@@ -297,6 +335,11 @@ class Trainer:
         self.generator._engine().ensure_packed()
         self.discriminator._engine().ensure_packed()
         ent['graph'].replay()
+        if split and train:
+            import torch.distributed as dist
+            dist.all_reduce(self.gen_optimizer.flat()['g'])
+            dist.all_reduce(self.disc_optimizer.flat()['g'])
+            ent['graph_update'].replay()
         return ent['losses']
 
     def batch(self, x, y, train=False):
