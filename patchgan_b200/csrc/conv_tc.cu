@@ -163,6 +163,8 @@ struct TcParams {
   // TMA-store epilogue: the tile is staged in (reused) ring smem as 128 rows x st_rowbytes, swizzled, st_cw columns at a time
   int tma_store, st_rowbytes, st_cw, st_nbuf, st_twin;
   unsigned long long* trace;   // debug: 8 timestamps per CTA (pg_debug_set_trace), else null
+  int pers_total, pers_mtiles, pers_ntiles;   // persistent variant: work items = (m-tile fastest, n-tile, class)
+  uint32_t pers_stage_off, pers_slot_cols;    // staging buffers behind the ring; TMEM columns per accumulator slot
   int splits, kps;             // K-split cluster: `splits` CTAs (cluster dims (1,1,splits)) share one tile, kps k-steps each
   float* ws;                   // split-K exchange buffer in global memory (L2-resident): [tile][rank][128 rows][BN] fp32
   float* stats;                // fused InstanceNorm statistics: sums[(b*N + n)*2 + {0,1}] += {x, x^2} over the tile (or null)
@@ -744,6 +746,189 @@ conv_tc_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CU
   if (threadIdx.x == 0) trace_put(p, 6);
 }
 
+// --------------------------------------------------------------------------------------------
+// Persistent variant for grids of many short tiles (first layers, 64-channel decoder / data-gradient layers: thousands of
+// CTAs whose life is setup + one TMA round trip + a few MMAs + epilogue + store drain).  One CTA per SM slot walks the
+// tiles; the operand ring runs ahead across tile boundaries, the accumulator is double-buffered in TMEM (tfull / tempty
+// mbarriers), so the epilogue and the store drain of tile i overlap the loads and MMAs of tile i+1, and barrier init /
+// TMEM allocation / descriptor prefetch are paid once.
+// --------------------------------------------------------------------------------------------
+struct MmaState {
+  uint32_t a_lo, b_lo, stage, phase;
+};
+
+template <int KK>
+__device__ __forceinline__ void mma_issue_tile(const TcParams& p, MmaState& st, uint32_t full0, uint32_t empty0, uint32_t done_bar,
+                                               uint32_t a_lo0, uint32_t b_lo0, uint64_t desc_hi, uint32_t tmem_acc, int ksteps) {
+  const uint32_t idesc = p.idesc, stages = (uint32_t)p.stages;
+  const uint32_t a_step = p.a_bytes >> 4, b_step = p.b_bytes >> 4;
+  const uint32_t acc_wrap = (uint32_t)(p.nacc * p.BN), bn = (uint32_t)p.BN;
+  uint32_t acc_off = 0, fresh = (uint32_t)p.nacc;
+  for (int ks = 0; ks < ksteps; ++ks) {
+    mbar_wait(full0 + st.stage * 8, st.phase);
+    tc_fence_after();
+#pragma unroll
+    for (int k = 0; k < KK; ++k) {
+      const uint32_t accum = fresh == 0 ? 1u : 0u;
+      umma_bf16(tmem_acc + acc_off, desc_hi | (uint64_t)(st.a_lo + 2 * k), desc_hi | (uint64_t)(st.b_lo + 2 * k), idesc, accum);
+      fresh -= accum ^ 1u;
+      acc_off += bn;
+      if (acc_off == acc_wrap) acc_off = 0;
+    }
+    umma_commit(empty0 + st.stage * 8);
+    st.a_lo += a_step; st.b_lo += b_step;
+    if (++st.stage == stages) { st.stage = 0; st.phase ^= 1; st.a_lo = a_lo0; st.b_lo = b_lo0; }
+  }
+  umma_commit(done_bar);
+}
+
+struct TileXY {
+  int x0, y0, b0, n0, py, px, cls;
+};
+__device__ __forceinline__ TileXY pers_decode(const TcParams& p, int w) {
+  const int mt = w % p.pers_mtiles;
+  const int r = w / p.pers_mtiles;
+  const int nt = r % p.pers_ntiles;
+  TileXY t;
+  t.cls = r / p.pers_ntiles;
+  t.x0 = (mt % p.nx) * p.TW;
+  t.y0 = ((mt / p.nx) % p.ny) * p.TH;
+  t.b0 = (mt / (p.nx * p.ny)) * p.TB;
+  t.n0 = nt * p.BN;
+  t.py = t.cls >> 1; t.px = t.cls & 1;
+  return t;
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB,
+                    const __grid_constant__ ActMaps mapsO, const TcParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
+  __shared__ __align__(8) uint64_t tfull[2];
+  __shared__ __align__(8) uint64_t tempty[2];
+  __shared__ uint32_t tmem_base_sh;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t a_base = smem_base;
+  const uint32_t b_base = smem_base + p.stages * p.a_bytes;
+  const int nk = p.nk1 + p.nk2;
+  const int ksteps = p.ntaps * nk;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&mapsA.m[0]);
+    if (p.nk2 > 0) prefetch_tmap(&mapsA.m[4]);
+    prefetch_tmap(&mapB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&tfull[s]), 1);
+      mbar_init(smem_u32(&tempty[s]), 128);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_sh), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_sh;
+
+  if (warp == 0) {
+    // ===================== TMA producer: the ring runs ahead across tiles =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int w = blockIdx.x; w < p.pers_total; w += gridDim.x) {
+        const TileXY t = pers_decode(p, w);
+        int tap = 0, ck = 0, cx = 0, cy = 0, wtap = 0, ph = 0;
+        bool newtap = true;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          if (newtap) {
+            newtap = false;
+            ph = 0;
+            if (p.mode == PG_CONVT) {
+              const int j = tap >> 1, i = tap & 1;
+              wtap = ((1 - t.py) + 2 * j) * 4 + (1 - t.px) + 2 * i;
+              cx = t.x0 + t.px - i;
+              cy = t.y0 + t.py - j;
+            } else if (p.mode == PG_CONV1X1) {
+              wtap = 0; cx = t.x0; cy = t.y0;
+            } else {
+              const int kh = tap >> 2, kw = tap & 3;
+              wtap = tap;
+              if (p.stride == 2) {
+                const int u = kh - p.pad, v = kw - p.pad;
+                ph = (u & 1) * 2 + (v & 1);
+                cx = t.x0 + (v >> 1);
+                cy = t.y0 + (u >> 1);
+              } else {
+                cx = t.x0 - p.pad + kw;
+                cy = t.y0 - p.pad + kh;
+              }
+            }
+          }
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t fb = smem_u32(&full_bar[stage]);
+          mbar_expect_tx(fb, p.tx_bytes);
+          if (ck < p.nk1) tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[ph], fb, ck * p.BK, cx, cy, t.b0);
+          else tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[4 + ph], fb, (ck - p.nk1) * p.BK, cx, cy, t.b0);
+          tma_load_2d(b_base + stage * p.b_bytes, &mapB, fb, wtap * p.Ctot + ck * p.BK, t.n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          if (++ck == nk) { ck = 0; ++tap; newtap = true; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer: accumulator slot it & 1 =====================
+    if (lane == 0) {
+      const uint32_t a_lo0 = (a_base & 0x3FFFF) >> 4, b_lo0 = (b_base & 0x3FFFF) >> 4;
+      const uint64_t desc_hi = make_smem_desc(0, p.sbo, p.layout_type);
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      MmaState st{a_lo0, b_lo0, 0u, 0u};
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < p.pers_total; w += gridDim.x, ++it) {
+        const uint32_t slot = it & 1u;
+        mbar_wait(smem_u32(&tempty[slot]), ((it >> 1) & 1u) ^ 1u);      // epilogue has drained this slot
+        tc_fence_after();
+        const uint32_t acc = tmem_base + slot * p.pers_slot_cols;
+        if (p.BK == 64) mma_issue_tile<4>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps);
+        else if (p.BK == 32) mma_issue_tile<2>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps);
+        else mma_issue_tile<1>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    uint32_t it = 0;
+    for (int w = blockIdx.x; w < p.pers_total; w += gridDim.x, ++it) {
+      const TileXY t = pers_decode(p, w);
+      const uint32_t slot = it & 1u;
+      mbar_wait(smem_u32(&tfull[slot]), (it >> 1) & 1u);
+      tc_fence_after();
+      const EpiCtx e{smem_base + p.pers_stage_off, tmem_base + slot * p.pers_slot_cols, t.x0, t.y0, t.b0, t.n0, t.py, t.px, t.cls};
+      switch (p.act) {
+        case PG_ACT_RELU: tc_epilogue<PG_ACT_RELU, 16>(p, mapsO, e); break;
+        case PG_ACT_LEAKYRELU: tc_epilogue<PG_ACT_LEAKYRELU, 16>(p, mapsO, e); break;
+        case PG_ACT_TANH: tc_epilogue<PG_ACT_TANH, 16>(p, mapsO, e); break;
+        case PG_ACT_SIGMOID: tc_epilogue<PG_ACT_SIGMOID, 16>(p, mapsO, e); break;
+        default: tc_epilogue<PG_ACT_NONE, 16>(p, mapsO, e); break;
+      }
+      tc_fence_before();
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[slot])) : "memory");
+      epi_bar_sync();      // the staging buffers are free again (thread 64 has waited for the bulk stores to read them)
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
 static unsigned long long* g_trace = nullptr;
 void set_tc_trace(void* buf) { g_trace = (unsigned long long*)buf; }
 
@@ -985,6 +1170,47 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     PG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
     smem_set = true;
   }
+  // ---- persistent variant: many short tiles (decided first: it has dedicated store-staging buffers behind the ring)
+  bool pers = false;
+  size_t pers_smem = 0;
+  dim3 pers_grid;
+  {
+    static const int pers_env = [] { const char* e = getenv("PG_TC_PERSIST"); return e ? atoi(e) : 1; }();
+    static const int tma_st_env2 = [] { const char* e = getenv("PG_TC_TMA_STORE"); return e ? atoi(e) : 1; }();
+    const int ncls = d->mode == PG_CONVT ? 4 : 1;
+    const long long mtiles = (long long)pl.grid.x, ntn = d->N / p.BN;
+    const long long total = mtiles * ntn * ncls;
+    if (pers_env && g_trace == nullptr && p.splits == 1 && total >= 4LL * num_sms() && total < (1LL << 30)) {
+      int nacc = p.nacc;
+      while (nacc > 1 && 2 * nacc * p.BN > 256) nacc >>= 1;
+      const int cols = 2 * nacc * p.BN;
+      int tcols = 32;
+      while (tcols < cols) tcols <<= 1;
+      const int occ = tcols <= 256 ? 2 : 1;
+      const int esz = d->out_f32 == PG_F32 ? 4 : 2;
+      const int rowbytes = p.BN * esz > 128 ? 128 : p.BN * esz;
+      const int twin = out2 != nullptr ? 1 : 0;
+      const bool tst = tma_st_env2 && d->ldo >= d->N && rowbytes >= 32 && ((uintptr_t)out & 15) == 0 &&
+                       (twin == 0 || ((uintptr_t)out2 & 15) == 0);
+      const uint32_t staging = tst ? 2u * (1 + twin) * 128u * rowbytes : 0u;
+      const uint32_t per_stage = p.a_bytes + p.b_bytes;
+      const uint32_t budget = 220u * 1024u / occ - 2048u;
+      int stages = budget > staging ? (int)((budget - staging) / per_stage) : 0;
+      if (stages > MAX_STAGES) stages = MAX_STAGES;
+      if (tcols <= 512 && stages >= 2) {
+        pers = true;
+        p.nacc = nacc;
+        p.tmem_cols = (uint32_t)tcols;
+        p.pers_slot_cols = (uint32_t)(nacc * p.BN);
+        p.stages = stages;
+        p.pers_stage_off = (uint32_t)stages * per_stage;
+        p.pers_total = (int)total; p.pers_mtiles = (int)mtiles; p.pers_ntiles = (int)ntn;
+        pers_smem = (size_t)stages * per_stage + staging + 1024;
+        const long long slots = (long long)num_sms() * occ;
+        pers_grid = dim3((unsigned)(total < slots ? total : slots));
+      }
+    }
+  }
   // ---- output path: TMA store of a smem-staged tile unless the output row is trimmed / tiny
   ActMaps mO;
   memset(&mO, 0, sizeof(mO));
@@ -995,12 +1221,12 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     const int twin = out2 != nullptr ? 1 : 0;
     const uint32_t ring = (uint32_t)p.stages * (p.a_bytes + p.b_bytes);
     const uint32_t need1 = 128u * rowbytes * (1 + twin);
-    p.tma_store = tma_st_env && p.splits == 1 && d->ldo >= d->N && rowbytes >= 32 && ring >= need1 && ((uintptr_t)out & 15) == 0 &&
-                  (twin == 0 || ((uintptr_t)out2 & 15) == 0);
+    p.tma_store = tma_st_env && p.splits == 1 && d->ldo >= d->N && rowbytes >= 32 && (pers || ring >= need1) &&
+                  ((uintptr_t)out & 15) == 0 && (twin == 0 || ((uintptr_t)out2 & 15) == 0);
     if (p.tma_store) {
       p.st_rowbytes = rowbytes;
       p.st_cw = rowbytes / esz;
-      p.st_nbuf = ring >= 2 * need1 ? 2 : 1;
+      p.st_nbuf = (pers || ring >= 2 * need1) ? 2 : 1;
       p.st_twin = twin;
       const bool cls = d->mode == PG_CONVT;
       for (int ph = 0; ph < (cls ? 4 : 1); ++ph) {
@@ -1022,6 +1248,17 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     fprintf(stderr, "conv_tc: grid (%u,%u,%u) BN %d BK %d stages %d nacc %d tmem %u smem %zu TW %d TH %d TB %d ksteps %d splits %d\n",
             pl.grid.x, pl.grid.y, pl.grid.z, p.BN, p.BK, p.stages, p.nacc, p.tmem_cols, pl.smem, p.TW, p.TH, p.TB,
             p.ntaps * (p.nk1 + p.nk2), p.splits);
+  if (pers) {
+    static bool pers_set = false;
+    if (!pers_set) {
+      PG_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
+      pers_set = true;
+    }
+    if (dbg) fprintf(stderr, "conv_tc: persistent grid %u stages %d nacc %d tmem %u smem %zu work %d\n", pers_grid.x, p.stages, p.nacc,
+                     p.tmem_cols, pers_smem, p.pers_total);
+    conv_tc_pers_kernel<<<pers_grid, TC_THREADS, pers_smem, stream>>>(mA, mB, mO, p);
+    return check_launch("conv_tc_pers_kernel");
+  }
   if (p.splits > 1) {
     const size_t need = (size_t)pl.grid.x * pl.grid.y * pl.grid.z * 128 * p.BN * 4;
     if (g_ws_next + need > g_ws_bytes) g_ws_next = 0;

@@ -17,7 +17,11 @@ SHAPES = [  # mode stride pad B H Ci Co outdt
 
 def run(mode, stride, pad, B, H, Ci, Co):
     dev = 'cuda'
-    if mode == 'conv':
+    if mode == 'conv1x1':
+        Ho = H
+        d = conv_desc(L.PG_CONV1X1, 1, 0, B, H, H, H, H, Ci, 0, Ci, 0, Co, Co, out_dt=L.DT_F16, in_dt=L.DT_F16)
+        flops = 2.0 * B * H * H * Ci * Co
+    elif mode == 'conv':
         Ho = (H + 2 * pad - 4) // stride + 1
         d = conv_desc(L.PG_CONV, stride, pad, B, H, H, Ho, Ho, Ci, 0, Ci, 0, Co, Co, out_dt=L.DT_F32, in_dt=L.DT_F16)
         flops = 2.0 * B * Ho * Ho * Ci * Co * 16
@@ -27,7 +31,7 @@ def run(mode, stride, pad, B, H, Ci, Co):
         flops = 2.0 * B * H * H * Ci * Co * 16
     x = torch.randn((B, H, H, Ci), device=dev, dtype=torch.float16)
     w = torch.randn((Co, 16, Ci), device=dev, dtype=torch.float16)
-    out = torch.empty((B, Ho, Ho, Co), device=dev, dtype=torch.float32)
+    out = torch.empty((B, Ho, Ho, Co), device=dev, dtype=torch.float16 if mode == 'conv1x1' else torch.float32)
     trace = torch.zeros(1 << 20, device=dev, dtype=torch.int64)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     def call():
@@ -54,6 +58,6 @@ def run(mode, stride, pad, B, H, Ci, Co):
 if __name__ == '__main__':
     ensure_workspace(torch.device('cuda', 0))
     pass
-    sel = SHAPES if len(sys.argv) < 2 else [s for s in SHAPES if s[3] == 32]
+    sel = SHAPES if len(sys.argv) < 2 else ([('conv1x1', 1, 0, 32, 128, 64, 64), ('conv1x1', 1, 0, 16, 128, 48, 32), ('conv1x1', 1, 0, 16, 128, 64, 16), ('convT', 2, 1, 32, 64, 128, 64)] if sys.argv[1] == 'p' else [s for s in SHAPES if s[3] == 32])
     for s in sel:
         run(*s)
