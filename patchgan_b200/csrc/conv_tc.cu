@@ -1173,6 +1173,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   // ---- persistent variant: many short tiles (decided first: it has dedicated store-staging buffers behind the ring)
   bool pers = false;
   size_t pers_smem = 0;
+  int pers_nbuf = 2;
   dim3 pers_grid;
   {
     static const int pers_env = [] { const char* e = getenv("PG_TC_PERSIST"); return e ? atoi(e) : 1; }();
@@ -1180,7 +1181,8 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     const int ncls = d->mode == PG_CONVT ? 4 : 1;
     const long long mtiles = (long long)pl.grid.x, ntn = d->N / p.BN;
     const long long total = mtiles * ntn * ncls;
-    if (pers_env && g_trace == nullptr && p.splits == 1 && total >= 4LL * num_sms() && total < (1LL << 30)) {
+    static const int pers_min = [] { const char* e = getenv("PG_TC_PERSIST_MIN"); return e ? atoi(e) : 1; }();
+    if (pers_env && g_trace == nullptr && p.splits == 1 && total >= (long long)pers_min * num_sms() && total < (1LL << 30)) {
       int nacc = p.nacc;
       while (nacc > 1 && 2 * nacc * p.BN > 256) nacc >>= 1;
       const int cols = 2 * nacc * p.BN;
@@ -1192,10 +1194,15 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
       const int twin = out2 != nullptr ? 1 : 0;
       const bool tst = tma_st_env2 && d->ldo >= d->N && rowbytes >= 32 && ((uintptr_t)out & 15) == 0 &&
                        (twin == 0 || ((uintptr_t)out2 & 15) == 0);
-      const uint32_t staging = tst ? 2u * (1 + twin) * 128u * rowbytes : 0u;
+      // staging: double-buffered unless the tile is a single store chunk anyway
+      const int nch = p.BN / (rowbytes / esz);
+      const int nbuf = nch >= 2 ? 2 : 1;
+      const uint32_t staging = tst ? (uint32_t)nbuf * (1 + twin) * 128u * rowbytes : 0u;
       const uint32_t per_stage = p.a_bytes + p.b_bytes;
+      // (one persistent CTA per SM loses to four short-lived ones when the tile is epilogue-bound: keep two per SM)
       const uint32_t budget = 220u * 1024u / occ - 2048u;
       int stages = budget > staging ? (int)((budget - staging) / per_stage) : 0;
+      pers_nbuf = nbuf;
       if (stages > MAX_STAGES) stages = MAX_STAGES;
       if (tcols <= 512 && stages >= 2) {
         pers = true;
@@ -1226,7 +1233,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     if (p.tma_store) {
       p.st_rowbytes = rowbytes;
       p.st_cw = rowbytes / esz;
-      p.st_nbuf = (pers || ring >= 2 * need1) ? 2 : 1;
+      p.st_nbuf = pers ? pers_nbuf : (ring >= 2 * need1 ? 2 : 1);
       p.st_twin = twin;
       const bool cls = d->mode == PG_CONVT;
       for (int ph = 0; ph < (cls ? 4 : 1); ++ph) {
