@@ -129,6 +129,14 @@ int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const v
 int pg_conv_fwd_stats(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed, const float* bias,
                       void* out, float* sums, int impl, void* stream);
 
+/* Data-gradient through a convolution AND the activation in front of it, in one call (autograd of disc.py:19-42):
+ *   dx = conv_dgrad(dy) * act'(y),  act = d->act, y = the activation's saved OUTPUT (16-bit NHWC, pixel stride ldy)
+ * `d` is the data-gradient geometry as for pg_conv_fwd (d->act is NOT applied forward); dx: bf16, all N channels.
+ * On the tcgen05 path the product is taken on the fp32 accumulators in the epilogue; otherwise the plain data-gradient
+ * runs first and pg_act_bwd_from_output follows in place. */
+int pg_conv_dgrad_act(const PgConvDesc* d, const void* dy, const void* w_packed, void* dx, const void* y, int32_t ldy,
+                      int32_t y_dtype, int impl, void* stream);
+
 /* weight gradient of PG_CONV geometry `d` (autograd wgrad of unet.py:19,53 / disc.py:19-45):
  *   dw[n*ld_n + c*16 + tap] += sum_{b,oy,ox} g[b,oy,ox,n] * a[b, oy*s-p+kh, ox*s-p+kw, c]
  * g: [B,Hout,Wout] x N (stride ldg), a: [B,Hin,Win] x C1 (stride ld1).  Only n < n_real, c < c_real are

@@ -34,6 +34,7 @@ _SIGS = {
     'pg_last_conv_impl': ([], C.c_int),
     'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_fwd_stats': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
+    'pg_conv_dgrad_act': ([DP, vp, vp, vp, vp, i32, i32, C.c_int, vp], C.c_int),
     'pg_conv_wgrad': ([DP, vp, vp, i32, vp, i32, i32, i32, C.c_int, vp], C.c_int),
     'pg_conv_wgrad_tapmajor': ([DP, vp, vp, i32, vp, i32, i32, C.c_int, vp], C.c_int),
     'pg_grad_finalize_multi': ([vp, i32, i32, vp], C.c_int),

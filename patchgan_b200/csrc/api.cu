@@ -30,7 +30,8 @@ int check_launch(const char* what) {
 int conv_fwd_simt(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, cudaStream_t);
 int conv_wgrad_simt(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, int, int, cudaStream_t);
 // conv_tc.cu
-int conv_fwd_tc(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, float*, cudaStream_t);
+int conv_fwd_tc(const PgConvDesc*, const void*, const void*, const void*, const float*, void*, void*, float*, const void*, int, int,
+                cudaStream_t);
 bool conv_fwd_tc_stats_ok(const PgConvDesc*);
 bool conv_fwd_tc_supported(const PgConvDesc*, const void*, const void*, const void*, const void*);
 int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, int, int, cudaStream_t);
@@ -96,23 +97,44 @@ extern "C" int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_
                                  void* stream);
 
 static int conv_fwd_any(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed, const float* bias,
-                        void* out, void* out2, float* stats, int impl, void* stream);
+                        void* out, void* out2, float* stats, const void* mul_y, int mul_ld, int mul_dt, int impl, void* stream);
+extern "C" int pg_act_bwd_from_output(const void* y, int32_t y_f32, int32_t ldy, const void* dy, int32_t lddy, void* dx,
+                                      int32_t lddx, int64_t npix, int32_t C, int32_t act, void* stream);
 
 extern "C" int pg_conv_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
                            const float* bias, void* out, void* out2, int impl, void* stream) {
-  return conv_fwd_any(d, src1, src2, w_packed, bias, out, out2, nullptr, impl, stream);
+  return conv_fwd_any(d, src1, src2, w_packed, bias, out, out2, nullptr, nullptr, 0, 0, impl, stream);
 }
 
 extern "C" int pg_conv_fwd_stats(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed,
                                  const float* bias, void* out, float* sums, int impl, void* stream) {
   PG_REQUIRE(d != nullptr && sums != nullptr, "pg_conv_fwd_stats: NULL argument");
   PG_REQUIRE(d->ldo >= d->N, "pg_conv_fwd_stats: the output row must hold all N channels");
-  return conv_fwd_any(d, src1, src2, w_packed, bias, out, nullptr, sums, impl, stream);
+  return conv_fwd_any(d, src1, src2, w_packed, bias, out, nullptr, sums, nullptr, 0, 0, impl, stream);
+}
+
+extern "C" int pg_conv_dgrad_act(const PgConvDesc* d, const void* dy, const void* w_packed, void* dx, const void* y, int32_t ldy,
+                                 int32_t y_dtype, int impl, void* stream) {
+  PG_REQUIRE(d != nullptr && y != nullptr && dx != nullptr, "pg_conv_dgrad_act: NULL argument");
+  PG_REQUIRE(d->out_f32 == PG_BF16 && !d->has_bias && d->C2 == 0 && d->ldo >= d->N && d->n_valid == d->N,
+             "pg_conv_dgrad_act: needs a bf16 output holding all N channels, no bias, one source");
+  PG_REQUIRE((y_dtype == PG_BF16 || y_dtype == PG_F16) && ldy >= d->N && ldy % 8 == 0 && (((uintptr_t)y) & 15) == 0,
+             "pg_conv_dgrad_act: bad y (16-bit, ldy >= N, 16-byte aligned)");
+  return conv_fwd_any(d, dy, nullptr, w_packed, nullptr, dx, nullptr, nullptr, y, ldy, y_dtype, impl, stream);
 }
 
 static int conv_fwd_any(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed, const float* bias,
-                        void* out, void* out2, float* stats, int impl, void* stream) {
+                        void* out, void* out2, float* stats, const void* mul_y, int mul_ld, int mul_dt, int impl, void* stream) {
   if (int e = validate(d, "pg_conv_fwd")) return e;
+  if (mul_y != nullptr && (impl == PG_IMPL_SIMT || impl == PG_IMPL_SKINNY ||
+                           !conv_fwd_tc_supported(d, src1, src2, w_packed, out))) {
+    // no fused epilogue on this path: the plain data-gradient, then the activation backward in place
+    PgConvDesc plain = *d;
+    plain.act = PG_ACT_NONE;
+    if (int e = conv_fwd_any(&plain, src1, src2, w_packed, bias, out, out2, stats, nullptr, 0, 0, impl, stream)) return e;
+    return pg_act_bwd_from_output(mul_y, mul_dt, mul_ld, out, d->ldo, out, d->ldo, (int64_t)d->B * d->Hout * d->Wout, d->N,
+                                  d->act, stream);
+  }
   PG_REQUIRE(src1 && w_packed && out && (d->C2 == 0 || src2), "pg_conv_fwd: NULL pointer");
   PG_REQUIRE(!d->has_bias || bias, "pg_conv_fwd: has_bias but bias is NULL");
   PG_REQUIRE(d->mode != PG_CONV1X1 || d->ldw % 8 == 0, "pg_conv_fwd: pointwise weight rows need ldw %% 8 == 0");
@@ -144,7 +166,7 @@ static int conv_fwd_any(const PgConvDesc* d, const void* src1, const void* src2,
   }
   // InstanceNorm statistics: fused into the tcgen05 epilogue when the tile geometry allows, else a second launch
   const bool fuse = stats != nullptr && ok && conv_fwd_tc_stats_ok(d);
-  int e = ok ? conv_fwd_tc(d, src1, src2, w_packed, bias, out, out2, fuse ? stats : nullptr, s)
+  int e = ok ? conv_fwd_tc(d, src1, src2, w_packed, bias, out, out2, fuse ? stats : nullptr, mul_y, mul_ld, mul_dt, s)
              : conv_fwd_simt(d, src1, src2, w_packed, bias, out, out2, s);
   if (e == PG_OK && stats != nullptr && !fuse)
     e = pg_instnorm_stats(out, d->out_f32, d->B, (int64_t)d->Hout * d->Wout, d->N, d->ldo, stats, stream);

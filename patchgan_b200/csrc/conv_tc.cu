@@ -167,6 +167,8 @@ struct TcParams {
   uint32_t pers_stage_off, pers_slot_cols;    // staging buffers behind the ring; TMEM columns per accumulator slot
   int splits, kps;             // K-split cluster: `splits` CTAs (cluster dims (1,1,splits)) share one tile, kps k-steps each
   float* ws;                   // split-K exchange buffer in global memory (L2-resident): [tile][rank][128 rows][BN] fp32
+  const void* mul_y;           // data-gradient fusion: out = acc * act'(y) with y = saved activation OUTPUT at the same pixel /
+  int mul_ld, mul_dt;          //   channel (pixel stride mul_ld, PgDType mul_dt); the activation is p.act (not applied forward)
   float* stats;                // fused InstanceNorm statistics: sums[(b*N + n)*2 + {0,1}] += {x, x^2} over the tile (or null)
 };
 
@@ -225,6 +227,28 @@ struct EpiCtx {
   int x0, y0, b0, n0, py, px, cls;
 };
 
+template <int ACT>
+__device__ __forceinline__ float act_grad_out_fast(float y) {
+  if (ACT == PG_ACT_RELU) return y > 0.f ? 1.f : 0.f;
+  if (ACT == PG_ACT_LEAKYRELU) return y > 0.f ? 1.f : 0.2f;
+  if (ACT == PG_ACT_TANH) return 1.f - y * y;
+  if (ACT == PG_ACT_SIGMOID) return y * (1.f - y);
+  return 1.f;
+}
+
+// f[0..16) *= act'(y[opix][n .. n+16))   (data-gradient through an activation, from its saved output)
+template <int ACT>
+__device__ __forceinline__ void epi_mul16(const TcParams& p, long long opix, int n, bool row_valid, float* f) {
+  if (!row_valid) return;
+  const unsigned short* yp = reinterpret_cast<const unsigned short*>(p.mul_y) + opix * p.mul_ld + n;
+  const uint4 y0 = __ldg(reinterpret_cast<const uint4*>(yp));
+  const uint4 y1 = __ldg(reinterpret_cast<const uint4*>(yp) + 1);
+  float yf[16];
+  if (p.mul_dt == PG_F16) { unpack8h(y0, yf); unpack8h(y1, yf + 8); } else { unpack8(y0, yf); unpack8(y1, yf + 8); }
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] *= act_grad_out_fast<ACT>(yf[j]);
+}
+
 // bias / activation / padding mask on U raw sums v[] of channels [n, n+U) -> f[]
 template <int ACT, int U>
 __device__ __forceinline__ void epi_finish(const TcParams& p, int n, uint32_t* v, float* f) {
@@ -244,8 +268,13 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, int n, uint32_t* v
         if (n + j < p.n_valid) v[j] = __float_as_uint(__uint_as_float(v[j]) + __ldg(p.bias + n + j));
     }
   }
+  if (p.mul_y != nullptr) {      // (p.act names the activation whose derivative multiplies the result: epi_mul16)
 #pragma unroll
-  for (int j = 0; j < U; ++j) f[j] = act_fast<ACT>(__uint_as_float(v[j]));
+    for (int j = 0; j < U; ++j) f[j] = __uint_as_float(v[j]);
+  } else {
+#pragma unroll
+    for (int j = 0; j < U; ++j) f[j] = act_fast<ACT>(__uint_as_float(v[j]));
+  }
   if (n + U > p.n_valid) {       // zero the padded output channels
 #pragma unroll
     for (int j = 0; j < U; ++j) f[j] = (n + j < p.n_valid) ? f[j] : 0.f;
@@ -322,6 +351,12 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
   // fused statistics (U == 16 only): image of this warp's 32 rows, validity of this thread's row
   const int s_b = e.b0 + (r >> (p.lgTW + p.lgTH));
   const bool s_valid = s_b < p.B && e.y0 + ((r >> p.lgTW) & (p.TH - 1)) < p.Ha && e.x0 + (r & (p.TW - 1)) < p.Wa;
+  long long m_opix = 0;           // output pixel of this thread's row (activation-gradient fusion)
+  if (p.mul_y != nullptr) {
+    int oy = e.y0 + ((r >> p.lgTW) & (p.TH - 1)), ox = e.x0 + (r & (p.TW - 1));
+    if (p.mode == PG_CONVT) { oy = 2 * oy + e.py; ox = 2 * ox + e.px; }
+    m_opix = ((long long)s_b * p.Hout + oy) * p.Wout + ox;
+  }
   if (p.tma_store) {
     // ---- stage the tile in the (now idle) ring smem with the TMA swizzle, store it with cp.async.bulk.tensor:
     //      full 128-byte rows instead of 32 scattered 16-byte stores per warp instruction; tails are clipped by TMA
@@ -342,6 +377,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
       for (int sub = 0; sub < p.st_cw; sub += U) {
         float f[U];
         epi_load<ACT, U>(p, trow, ch * p.st_cw + sub, e.n0 + ch * p.st_cw + sub, f);
+        if (U == 16 && p.mul_y != nullptr) epi_mul16<ACT>(p, m_opix, e.n0 + ch * p.st_cw + sub, s_valid, f);
         if (U == 16 && p.stats != nullptr && s_b < p.B)
           stats_add16(f, s_valid, p.stats + ((long long)s_b * p.N + e.n0 + ch * p.st_cw + sub) * 2, lane);
         if (p.out_f32 == PG_F32) {
@@ -391,6 +427,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
       float f[U];
       const int n = e.n0 + c;
       epi_load<ACT, U>(p, trow, c, n, f);
+      if (U == 16 && p.mul_y != nullptr) epi_mul16<ACT>(p, m_opix, n, s_valid, f);
       if (U == 16 && p.stats != nullptr && s_b < p.B) stats_add16(f, s_valid, p.stats + ((long long)s_b * p.N + n) * 2, lane);
       const int keep = p.ldo - n;     // channels of this chunk that exist in the (possibly trimmed) output row
       if (valid && keep > 0 && !(p.debug & 4)) {
@@ -513,6 +550,7 @@ __device__ __forceinline__ void split_reduce_store(const TcParams& p, const EpiC
     float f[16];
     const int n = e.n0 + c;
     epi_finish<ACT, 16>(p, n, v, f);
+    if (p.mul_y != nullptr) epi_mul16<ACT>(p, opix, n, valid, f);
     if (p.stats != nullptr && s_b < p.B) stats_add16(f, valid, p.stats + ((long long)s_b * p.N + n) * 2, lane);
     if (valid && !(p.debug & 4)) store16(p, opix, n, f);
   }
@@ -1125,7 +1163,7 @@ bool conv_fwd_tc_stats_ok(const PgConvDesc* d) {
 }
 
 int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const void* w, const float* bias, void* out,
-                void* out2, float* stats, cudaStream_t stream) {
+                void* out2, float* stats, const void* mul_y, int mul_ld, int mul_dt, cudaStream_t stream) {
   TcPlan pl;
   if (!make_plan(d, pl)) {
     set_error("conv_fwd_tc: unsupported shape");
@@ -1136,6 +1174,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   p.out = out;
   p.out2 = out2;
   p.stats = stats;
+  p.mul_y = mul_y; p.mul_ld = mul_ld; p.mul_dt = mul_dt;
   const bool phased = d->mode == PG_CONV && d->stride == 2;
   ActMaps mA;
   CUtensorMap mB;

@@ -230,6 +230,14 @@ def run_conv(desc, src1, src2, w, bias, out, stats=None):
 SKIP = set(filter(None, os.environ.get('PATCHGAN_B200_SKIP', '').split(',')))   # timing experiments only
 
 
+def run_conv_dgrad_act(desc, dy, w, out, y):
+    """Data-gradient + backward of the activation in front of it (desc.act, from its saved output y) in one launch."""
+    if L.PROFILER is not None:
+        L.PROFILER.note(conv_flops(desc), desc_tag(desc))
+    L.call('pg_conv_dgrad_act', ctypes.byref(desc), dy.ptr, w if isinstance(w, int) else w.data_ptr(), out.ptr, y.ptr, y.ld,
+           y.dt, Config.impl, _stream())
+
+
 def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream=None):
     """wstream: issue the weight-gradient on that side stream (it forks here, after its operands were produced on
     the current stream; the caller joins it before the optimizer step)."""
@@ -277,9 +285,13 @@ def taps_gather(mode, stride, pad, dy, ch, B, Hq, Wq):
     return G
 
 
-def taps_dgrad(G, w16, out):
-    """out[q][c] = sum_tap G[q][tap] * w16[c][tap]   (w16: bf16 [C][16])"""
-    run_conv(conv_desc(L.PG_CONV1X1, 1, 0, G.B, G.H, G.W, G.H, G.W, 16, 0, 16, 0, out.C, out.ld), G, None, w16, None, out)
+def taps_dgrad(G, w16, out, y=None, act=0):
+    """out[q][c] = sum_tap G[q][tap] * w16[c][tap]   (w16: bf16 [C][16]);  with y: times act'(y) (fused activation backward)"""
+    d = conv_desc(L.PG_CONV1X1, 1, 0, G.B, G.H, G.W, G.H, G.W, 16, 0, 16, 0, out.C, out.ld, act=act if y is not None else 0)
+    if y is not None:
+        run_conv_dgrad_act(d, G, w16, out, y)
+    else:
+        run_conv(d, G, None, w16, None, out)
 
 
 def taps_wgrad(G, x, dw_ptr, c_real, wstream=None):
@@ -893,8 +905,12 @@ class DiscriminatorEngine(NetEngine):
                 nf, nv = 0, None
                 if li == 0 and dx_channels is not None:
                     nf, nv = dx_channels[0], dx_channels[0] + dx_channels[1]
+                # the activation backward of the previous layer (no norm in between) is fused into this data-gradient
+                fuse_act = li > 0 and not self.specs[li - 1].norm and taps_enabled()
+                yprev = ctx[li - 1][1].first(B) if fuse_act else None
+                aprev = L.ACT[self.specs[li - 1].act] if fuse_act else 0
                 if last_taps:
-                    taps_dgrad(Gt, pw.w16, din)
+                    taps_dgrad(Gt, pw.w16, din, yprev, aprev)
                 elif (li == 0 and dx_channels is not None and dx_channels[1] == 1 and s.stride == 2 and taps_enabled()
                         and s.cout == s.np):
                     # only the generated-mask channel of the input gradient is read: tap products of dY with the 16 x Cout
@@ -903,12 +919,18 @@ class DiscriminatorEngine(NetEngine):
                     taps_forward(L.PG_CONVT, 2, 1, d_raw, None, wslab, None, 0, din, dx_channels[0])
                 elif s.stride == 2:
                     dd = conv_desc(L.PG_CONVT, 2, 1, B, d_raw.H, d_raw.W, Hi, Wi, d_raw.C, 0, d_raw.ld, 0, s.cinp,
-                                   din.ld, n_valid=nv, n_first=nf, c_valid=s.cout)
-                    run_conv(dd, d_raw, None, pw.bwd, None, din)
+                                   din.ld, n_valid=nv, n_first=nf, c_valid=s.cout, act=aprev)
+                    if fuse_act:
+                        run_conv_dgrad_act(dd, d_raw, pw.bwd, din, yprev)
+                    else:
+                        run_conv(dd, d_raw, None, pw.bwd, None, din)
                 else:
                     dd = conv_desc(L.PG_CONV, 1, 2, B, d_raw.H, d_raw.W, h.H, h.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
-                                   din.ld, n_valid=nv, n_first=nf, c_valid=s.cout)
-                    run_conv(dd, d_raw, None, pw.bwd, None, din)
+                                   din.ld, n_valid=nv, n_first=nf, c_valid=s.cout, act=aprev)
+                    if fuse_act:
+                        run_conv_dgrad_act(dd, d_raw, pw.bwd, din, yprev)
+                    else:
+                        run_conv(dd, d_raw, None, pw.bwd, None, din)
             if li > 0:
                 ps = self.specs[li - 1]
                 _, pt, psums, pout = ctx[li - 1]
@@ -916,6 +938,8 @@ class DiscriminatorEngine(NetEngine):
                 if ps.norm:
                     dt = norm_bwd(pt, psums, din, None, 0, 0.0, None, 0)
                     d_raw = act_bwd_out(pt, dt, L.ACT[ps.act])
+                elif fuse_act:
+                    d_raw = din                    # already multiplied by act'(previous output) in the epilogue
                 else:
                     d_raw = act_bwd_out(pt, din, L.ACT[ps.act])
         if grads is not None and wstream is None:

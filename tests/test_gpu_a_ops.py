@@ -398,3 +398,33 @@ def test_conv2d_weight_gradient_tap_major_and_finalize(case, impl):
     L.call('pg_grad_finalize_multi', table.data_ptr(), 1, Co * ((Ci + 31) // 32), stream())
     torch.cuda.synchronize()
     assert relerr(dw.cpu().numpy(), 2 * ref) < 1e-4
+
+
+@pytest.mark.parametrize('impl', IMPLS, ids=IMPL_IDS)
+@pytest.mark.parametrize('act', ['tanh', 'leakyrelu'])
+@pytest.mark.parametrize('case', [(2, 32, 64, 32, 2), (2, 256, 512, 32, 1), (3, 64, 128, 16, 2)], ids=str)
+def test_data_gradient_with_fused_activation_backward(case, act, impl):
+    """pg_conv_dgrad_act: dx = dgrad(dy) * act'(y) with y the saved activation output in front of the convolution."""
+    B, Ci, Co, H, s = case
+    r = rng(8)
+    x = r.standard_normal((B, Ci, H, H)).astype(np.float32)
+    w = bf16_round(r.standard_normal((Co, Ci, 4, 4)) / np.sqrt(Co * 16))
+    Ho = (H + 2 - 4) // s + 1
+    dy = bf16_round(r.standard_normal((B, Co, Ho, Ho)))
+    dxc, _, _ = orc.conv2d_bwd(x, w, dy, s)
+    y = bf16_round(orc.act_fwd(act, r.standard_normal((B, Ci, H, H)).astype(np.float32)), L.DT_F16)
+    ref = dxc * orc.act_bwd_from_output(act, y) if hasattr(orc, 'act_bwd_from_output') else None
+    if ref is None:
+        g = {'tanh': 1 - y * y, 'leakyrelu': np.where(y > 0, 1.0, 0.2)}[act]
+        ref = dxc * g
+    wd = pack_weight(w, Ci, Ci, Co, Co, 0, 0, 16, Ci * 16, flip=1 if s == 1 else 0)
+    if s == 2:
+        d = conv_desc(L.PG_CONVT, 2, 1, B, Ho, Ho, H, H, Co, 0, Co, 0, Ci, Ci, out_dt=L.DT_BF16, act=L.ACT[act])
+    else:
+        d = conv_desc(L.PG_CONV, 1, 2, B, Ho, Ho, H, H, Co, 0, Co, 0, Ci, Ci, out_dt=L.DT_BF16, act=L.ACT[act])
+    out = torch.full((B, H, H, Ci), 7.0, device='cuda', dtype=torch.bfloat16)
+    yd = to_nhwc(y, dt=L.DT_F16)
+    L.call('pg_conv_dgrad_act', ctypes.byref(d), to_nhwc(dy).data_ptr(), wd.data_ptr(), out.data_ptr(), yd.data_ptr(), Ci, L.DT_F16,
+           impl, stream())
+    torch.cuda.synchronize()
+    assert relerr(from_nhwc(out, Ci), ref) < 6e-3       # bf16 output (+ one extra bf16 rounding on the unfused path)
