@@ -35,22 +35,25 @@ CONFIGS = {
                  G=dict(input_nc=3, output_nc=1, nf=64, activation='leakyrelu', final_act='sigmoid', use_dropout=False),
                  D=dict(input_nc=4, ndf=64, n_layers=4), loss_type='tversky', B=4, S=1024, gflop_per_img=1175.2),
 }
+CONFIGS['cfg2'] = dict(workload='cfg2: UNet(3->1,nf=32) generator inference-only forward (infer.py path), 256x256, batch 64',
+                       G=CONFIGS['cfg3']['G'], D=None, loss_type=None, B=64, S=256, gflop_per_img=3.020, infer=True)
 CLOCK_QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
                'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
                'clocks_event_reasons.sw_power_cap')
 
 
-def ncu_traffic(kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu launch list of one step (profiles/, tools/summarize_ncu.py);
-    None when no capture is committed."""
+def ncu_traffic(kernels):
+    """DRAM bytes per launch, averaged over the launches of `kernels` (the CUDA kernels behind one C-ABI entry point) in
+    the committed ncu launch list of one step (profiles/, tools/summarize_ncu.py); None when no capture is committed."""
     import glob
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_step_launches.json'))):
         try:
-            for k in json.load(open(path))['kernels']:
-                if k['kernel'] == kernel:
-                    best = dict(bytes_per_launch=int(k['dram_MB_per_launch'] * 1e6), launches=k['launches'],
-                                src=os.path.relpath(path, ROOT))
+            ks = [k for k in json.load(open(path))['kernels'] if k['kernel'] in kernels]
+            n = sum(k['launches'] for k in ks)
+            if n:
+                tot = sum(k['dram_MB_per_launch'] * 1e6 * k['launches'] for k in ks)
+                best = dict(bytes_per_launch=int(tot / n), launches=n, src=os.path.relpath(path, ROOT))
         except Exception:
             pass
     return best
@@ -99,6 +102,9 @@ def run_reference(args, cfg):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
+    if cfg.get('infer'):
+        print(json.dumps(dict(impl='reference', unavailable='the CPU arm times the training step (cfg3/4/5) only')), flush=True)
+        return
     steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
     batch = 4 if cfg['S'] <= 256 else 1
     rate, sec = cpu_step_rate(cfg, steps, warmup, batch)
@@ -137,7 +143,8 @@ class CallProfiler:
         e = self.torch.cuda.Event(enable_timing=True)
         e.record()
         # same CUDA kernels behind three entry points each: + fused statistics, + TMA bulk-reduce epilogue
-        name = {'pg_conv_fwd_stats': 'pg_conv_fwd', 'pg_conv_wgrad_tapmajor': 'pg_conv_wgrad'}.get(tok[0], tok[0])
+        name = {'pg_conv_fwd_stats': 'pg_conv_fwd', 'pg_conv_dgrad_act': 'pg_conv_fwd',
+                'pg_conv_wgrad_tapmajor': 'pg_conv_wgrad'}.get(tok[0], tok[0])
         if name in ('pg_conv_fwd', 'pg_conv_wgrad'):
             name += {2: ':tcgen05', 3: ':skinny'}.get(self.lib.pg_last_conv_impl(), ':simt')
         self.rec.append((name, tok[1], tok[2], e, tok[3]))
@@ -190,6 +197,60 @@ def finish_clocks(proc):
     sm.sort()
     return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons),
                 samples=len(sm))
+
+
+def run_infer(args, cfg):
+    """cfg2: generator forward only, through the module call a user makes (infer.py:155-170: eval(), no_grad)."""
+    import torch
+    import patchgan_b200 as P
+    from patchgan_b200 import _lib as L
+    from patchgan_b200.engine import Config
+    sys.stdout.flush()
+    dev = torch.device('cuda', 0)
+    torch.cuda.set_device(dev)
+    B, S = cfg['B'], cfg['S']
+    torch.manual_seed(0)
+    G = P.UNet(**cfg['G']).to(dev).eval()
+    gen = torch.Generator().manual_seed(1234)
+    x_host = torch.rand((B, 3, S, S), generator=gen).pin_memory()
+    x_dev = x_host.to(dev)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    out_host = torch.empty((B, cfg['G']['output_nc'], S, S), dtype=torch.float32).pin_memory()
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 3)):
+            G(x_dev)
+        torch.cuda.synchronize()
+        clocks = sample_clocks(0)
+        n0 = L.lib().pg_launch_count()
+        evs = []
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); G(x_dev); e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        launches = (L.lib().pg_launch_count() - n0) // args.steps
+        ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out_host.copy_(G(x_host.to(dev, non_blocking=True)), non_blocking=True)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / args.steps
+    pk = peaks()
+    img_s = B / (ms * 1e-3)
+    tf = img_s * cfg['gflop_per_img'] / 1e3
+    line = dict(metric='infer_img_per_s', value=round(img_s, 2), unit='img/s', n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=round(ms, 4), higher_is_better=True, scaling='weak', vs_baseline=None,
+                dtype=('f16' if Config.fwd_dt == L.DT_F16 else 'bf16') + ' operands, f32 accumulate', data='synthetic',
+                config=dict(workload=cfg['workload'], global_batch=B, image=S, l2='flushed (256 MB write) between timed steps',
+                            cuda_graph=False),
+                clocks=finish_clocks(clocks),
+                e2e=dict(value=round(B / e2e_s, 2), unit='img/s', h2d_bytes_per_step=int(x_host.numel() * 4),
+                         d2h_bytes_per_step=int(out_host.numel() * 4), ms_per_step=round(e2e_s * 1e3, 4)),
+                gpu_launches=int(launches),
+                roofline=dict(bound='tensor', kernel='generator forward (all launches)', achieved=round(tf, 2),
+                              peak=pk['tf_sustained'], unit='TFLOP/s', frac=round(tf / pk['tf_sustained'], 4), traffic=None))
+    print(json.dumps(line), flush=True)
 
 
 def run_ours(args, cfg):
@@ -294,7 +355,8 @@ def run_ours(args, cfg):
     conv = [(k, v) for k, v in top if v[2] > 0]
     kname, (cnt, ms, fl) = conv[0]
     achieved_tf = fl / (ms * 1e-3) / 1e12
-    cuda_kernel = {'pg_conv_fwd:tcgen05': 'conv_tc_kernel', 'pg_conv_wgrad:tcgen05': 'wgrad_tc_kernel'}.get(kname)
+    cuda_kernel = {'pg_conv_fwd:tcgen05': ['conv_tc_pers_kernel', 'conv_tc_kernel'],
+                   'pg_conv_wgrad:tcgen05': ['wgrad_tc_kernel']}.get(kname)
     tr_info = ncu_traffic(cuda_kernel) if cuda_kernel else None
     roof = dict(bound='tensor', kernel=kname, cuda_kernel=cuda_kernel, achieved=round(achieved_tf, 2), peak=pk['tf_sustained'],
                 peak_src=pk['src'] + ' (sustained cuBLAS bf16)', unit='TFLOP/s', frac=round(achieved_tf / pk['tf_sustained'], 4),
@@ -344,6 +406,8 @@ def main():
     cfg = CONFIGS[args.config]
     if args.impl == 'reference':
         run_reference(args, cfg)
+    elif cfg.get('infer'):
+        run_infer(args, cfg)
     else:
         run_ours(args, cfg)
 

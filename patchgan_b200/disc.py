@@ -9,6 +9,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
+from . import engine as E
 from .engine import DiscriminatorEngine, _stream, new_act, pack_rows, require_cuda
 from .transfer import Transferable
 from .unet import _Holder
@@ -32,7 +33,10 @@ class _DiscFunction(torch.autograd.Function):
         B, C, H, W = x.shape
         need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
         xs = x.contiguous().float()
-        if eng.in_cp in (16, 32):
+        if E.taps_enabled() and H % 2 == 0 and W % 2 == 0:
+            xin = E.first_im2col(B, H, W, C, x.device, twin=need_grad)
+            E.im2col_fill(xin, 0, xs.data_ptr(), E.nchw_strides(xs), C, 0, B, H, W)
+        elif eng.in_cp in (16, 32):
             xin = eng.new_input(B, H, W, x.device, twin=need_grad, zero=False)
             pack_rows(xs, None, xin, 0)
         else:

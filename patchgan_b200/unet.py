@@ -12,6 +12,7 @@ import torch
 from torch import nn
 
 from . import _lib as L
+from . import engine as E
 from .engine import Act, GeneratorEngine, _stream, new_act, require_cuda
 from .transfer import Transferable
 
@@ -55,7 +56,13 @@ class _UNetFunction(torch.autograd.Function):
         eng = module._engine()
         B, C, H, W = x.shape
         need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
-        xin = eng.pack_input(x.contiguous().float(), twin=need_grad)
+        xs = x.contiguous().float()
+        if E.taps_enabled() and H % 2 == 0 and W % 2 == 0:
+            # first layer as a dense GEMM over the stride-2 im2col of the NCHW input (engine.first_im2col)
+            xin = E.first_im2col(B, H, W, C, x.device, twin=need_grad)
+            E.im2col_fill(xin, 0, xs.data_ptr(), E.nchw_strides(xs), C, 0, B, H, W)
+        else:
+            xin = eng.pack_input(xs, twin=need_grad)
         if module.training and module.use_dropout:
             eng.ensure_packed()
             eng.bump_seed()

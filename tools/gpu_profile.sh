@@ -17,7 +17,7 @@ ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum 
 echo "ncu launches rc=$?"; cat $O/plain_$TAG.log
 # full capture of the dominant kernel at its largest shape (discriminator conv 256 -> 512, stride 1, B32)
 python tools/conv_probe.py conv 1 32 32 256 512 > $O/probe_$TAG.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 2 -c 3 -o $O/prof_$TAG -f \
+ncu --set full --clock-control none --import-source on -k regex:conv_tc -s 2 -c 3 -o $O/prof_$TAG -f \
     python tools/conv_probe.py conv 1 32 32 256 512 > $O/ncu_full_$TAG.log 2>&1
 echo "ncu full rc=$?"; cat $O/probe_$TAG.log
 ncu -i $O/prof_$TAG.ncu-rep --page raw --csv > $O/prof_${TAG}_raw.csv 2>/dev/null

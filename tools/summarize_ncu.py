@@ -64,7 +64,7 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 try:
     rows = list(csv.reader(open(G + f'prof_{tag}_raw.csv')))
     hdr, units = rows[0], rows[1]
-    out = dict(what='ncu --set full --clock-control none of conv_tc_kernel, discriminator conv 256->512 stride 1, B32, 32x32 '
+    out = dict(what='ncu --set full --clock-control none of the conv_tc kernel (persistent variant), discriminator conv 256->512 stride 1, B32, 32x32 '
                     '(tools/conv_probe.py conv 1 32 32 256 512), 3 launches', launches=[])
     for r in rows[2:]:
         d = {}
@@ -75,5 +75,5 @@ try:
     json.dump(out, open(f'profiles/r{rnd}_ncu_full_conv_tc_d3.json', 'w'), indent=0)
     for k, v in out['launches'][-1].items():
         print(k, v)
-except FileNotFoundError:
+except (FileNotFoundError, IndexError):
     print('no full capture')
