@@ -1243,7 +1243,9 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
       int stages = budget > staging ? (int)((budget - staging) / per_stage) : 0;
       pers_nbuf = nbuf;
       if (stages > MAX_STAGES) stages = MAX_STAGES;
-      if (tcols <= 512 && stages >= 2) {
+      // (BN = 256 needs all 512 TMEM columns for two slots -> one CTA per SM, which measured slower than two co-resident
+      //  non-persistent CTAs: 124 vs 109 us on the largest discriminator layer)
+      if (tcols <= 256 && stages >= 2) {
         pers = true;
         p.nacc = nacc;
         p.tmem_cols = (uint32_t)tcols;
