@@ -248,6 +248,12 @@ int pg_norm_act_bwd_apply(const void* x, int32_t x_f32, const float* sums, const
                           const void* dy2, int32_t ld2, const float* bsums, void* dx, int32_t lddx, int32_t B,
                           int64_t HW, int32_t C, int32_t ldx, int32_t act, float drop_p, const uint64_t* seed,
                           uint64_t salt, void* stream);
+/* Both passes in one call.  Maps of up to 1024 pixels (the 2x2 .. 32x32 layers) run as ONE launch (a block owns an image and
+ * 8 channels, keeps dxhat in registers between the reduction and the apply); larger maps run the two kernels above.
+ * bsums: zeroed workspace [B][C][2] (only touched by the two-pass path). */
+int pg_norm_act_bwd(const void* x, int32_t x_f32, const float* sums, const void* dy1, int32_t ld1, const void* dy2,
+                    int32_t ld2, float* bsums, void* dx, int32_t lddx, int32_t B, int64_t HW, int32_t C, int32_t ldx,
+                    int32_t act, float drop_p, const uint64_t* seed, uint64_t salt, void* stream);
 /* *ctr += inc on the device (advances the dropout seed once per step, graph-capturable) */
 int pg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
 /* activation backward from the saved OUTPUT y (layers without norm: unet.py:97-99,106-107; disc.py):

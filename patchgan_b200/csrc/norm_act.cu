@@ -329,6 +329,84 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
   }
 }
 
+// Small maps (HW <= 1024: the 2x2 .. 32x32 layers): reduce and apply in ONE launch.  A block owns (image, 8-channel group):
+// every thread keeps the dxhat / xhat values of its <= 4 pixels in registers, the block reduces the two sums per channel
+// (shuffles + 8 warp partials in shared memory), then the same registers are turned into dx.  No bsums round trip through
+// global atomics, x and dy are read once, one launch instead of two on the generator's backward critical path.
+constexpr int SMALL_PPT = 4;     // pixels per thread
+
+__global__ void __launch_bounds__(NT) norm_act_bwd_small_kernel(const void* x, int x_f32, const float* sums, const void* dy1,
+                                                                int ld1, const void* dy2, int ld2, void* dx, int lddx,
+                                                                int HW, int C, int ldx, int act, float drop_p,
+                                                                const unsigned long long* seed_ptr, unsigned long long salt) {
+  __shared__ float sh_stat[16];            // mean[8], rstd[8]
+  __shared__ float sh_part[NT / 32][16];   // per-warp partial sums
+  __shared__ float sh_tot[16];
+  const int b = blockIdx.y, c0 = blockIdx.x * 8;
+  const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
+  if (threadIdx.x < 8) {
+    float m = 0.f, r = 1.f;
+    if (sums != nullptr) mean_rstd(sums, b, C, c0 + threadIdx.x, HW, m, r);
+    sh_stat[threadIdx.x] = m;
+    sh_stat[8 + threadIdx.x] = r;
+  }
+  __syncthreads();
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { mean[j] = sh_stat[j]; rstd[j] = sh_stat[8 + j]; }
+  const long long base = (long long)b * HW;
+  float g[SMALL_PPT][8], xh[SMALL_PPT][8];
+  float a1[8], a2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
+#pragma unroll
+  for (int u = 0; u < SMALL_PPT; ++u) {
+    const int p = threadIdx.x + u * NT;
+    if (p < HW) {
+      float f[8];
+      load8(x, x_f32, (base + p) * ldx + c0, f);
+      load_dy(dy1, ld1, dy2, ld2, base + p, c0, g[u]);
+      dxhat8(f, g[u], base + p, C, c0, act, drop_p, seed, mean, rstd, xh[u]);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a1[j] += g[u][j];
+        a2[j] = fmaf(g[u][j], xh[u][j], a2[j]);
+      }
+    }
+  }
+  // block reduction of the 16 sums
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    a1[j] = warp_sum(a1[j]);
+    a2[j] = warp_sum(a2[j]);
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sh_part[warp][j] = a1[j]; sh_part[warp][8 + j] = a2[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < NT / 32; ++w) t += sh_part[w][threadIdx.x];
+    sh_tot[threadIdx.x] = sums != nullptr ? t / (float)HW : 0.f;
+  }
+  __syncthreads();
+  float m1[8], m2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { m1[j] = sh_tot[j]; m2[j] = sh_tot[8 + j]; }
+#pragma unroll
+  for (int u = 0; u < SMALL_PPT; ++u) {
+    const int p = threadIdx.x + u * NT;
+    if (p < HW) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[u][j] = rstd[j] * (g[u][j] - m1[j] - xh[u][j] * m2[j]);
+      store8(dx, 0, (base + p) * lddx + c0, g[u]);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(NT) act_bwd_from_output_kernel(const void* y, int y_f32, int ldy, const void* dy,
                                                                  int lddy, void* dx, int lddx, long long npix, int C,
                                                                  int act) {
@@ -423,6 +501,24 @@ extern "C" int pg_norm_act_bwd_apply(const void* x, int32_t x_f32, const float* 
   norm_act_bwd_apply_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, dx,
                                                                   lddx, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb);
   return check_launch("norm_act_bwd_apply_kernel");
+}
+
+// Backward through dropout / activation / InstanceNorm in one call: small maps in one launch, larger ones as reduce + apply
+// (bsums: zeroed float32 workspace [B][C][2], used by the two-pass path only).
+extern "C" int pg_norm_act_bwd(const void* x, int32_t x_f32, const float* sums, const void* dy1, int32_t ld1, const void* dy2,
+                               int32_t ld2, float* bsums, void* dx, int32_t lddx, int32_t B, int64_t HW, int32_t C, int32_t ldx,
+                               int32_t act, float drop_p, const uint64_t* seed, uint64_t salt, void* stream) {
+  if (int e = check_c("pg_norm_act_bwd", C)) return e;
+  if (HW <= (int64_t)SMALL_PPT * NT) {
+    dim3 grid((unsigned)(C / 8), (unsigned)B);
+    norm_act_bwd_small_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(x, x_f32, sums, dy1, ld1, dy2, ld2, dx, lddx, (int)HW, C, ldx,
+                                                                    act, drop_p, (const unsigned long long*)seed, salt);
+    return check_launch("norm_act_bwd_small_kernel");
+  }
+  PG_REQUIRE(bsums != nullptr, "pg_norm_act_bwd: bsums workspace needed for HW > %d", SMALL_PPT * NT);
+  if (int e = pg_norm_act_bwd_reduce(x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, B, HW, C, ldx, act, drop_p, seed, salt, stream))
+    return e;
+  return pg_norm_act_bwd_apply(x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, dx, lddx, B, HW, C, ldx, act, drop_p, seed, salt, stream);
 }
 
 __global__ void counter_add_kernel(unsigned long long* ctr, unsigned long long inc) { *ctr += inc; }

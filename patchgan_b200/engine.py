@@ -581,6 +581,10 @@ def norm_bwd(x, sums, dy1, dy2, act, drop_p, seed, salt):
     sp = seed.data_ptr() if seed is not None else None
     p2, l2 = (dy2.ptr, dy2.ld) if dy2 is not None else (None, 0)
     st = _stream()
+    if taps_enabled():      # one call: small maps are a single launch
+        L.call('pg_norm_act_bwd', x.ptr, x.dt, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), dx.ptr, dx.ld,
+               x.B, HW, x.C, x.ld, act, drop_p, sp, salt, st)
+        return dx
     L.call('pg_norm_act_bwd_reduce', x.ptr, x.dt, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), x.B,
            HW, x.C, x.ld, act, drop_p, sp, salt, st)
     L.call('pg_norm_act_bwd_apply', x.ptr, x.dt, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(),

@@ -219,10 +219,16 @@ def test_instance_norm_act_forward_backward(shape, act):
            bs.data_ptr(), B, H * W, Cp, Cp, L.ACT[act], 0.0, None, 0, st)
     L.call('pg_norm_act_bwd_apply', xd.data_ptr(), 1, sums.data_ptr(), d1.data_ptr(), Cp, d2.data_ptr(), Cp,
            bs.data_ptr(), dx.data_ptr(), Cp, B, H * W, Cp, Cp, L.ACT[act], 0.0, None, 0, st)
+    # the one-call entry point (single launch for maps of up to 1024 pixels, else the two passes above)
+    bs2 = torch.zeros((B, Cp, 2), device='cuda')
+    dx2 = torch.full((B, H, W, Cp), 7.0, device='cuda', dtype=torch.bfloat16)
+    L.call('pg_norm_act_bwd', xd.data_ptr(), 1, sums.data_ptr(), d1.data_ptr(), Cp, d2.data_ptr(), Cp, bs2.data_ptr(),
+           dx2.data_ptr(), Cp, B, H * W, Cp, Cp, L.ACT[act], 0.0, None, 0, st)
     torch.cuda.synchronize()
     assert relerr(from_nhwc(yd, C), y) < 5e-3
     assert torch.equal(yd, y2)                      # bf16 twin
     assert relerr(from_nhwc(dx, C), dx_ref) < 8e-3
+    assert relerr(from_nhwc(dx2, C), dx_ref) < 8e-3
 
 
 def test_dropout_statistics_and_backward_mask_reuse():
