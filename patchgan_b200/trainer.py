@@ -107,7 +107,7 @@ class Trainer:
         dev = x.device
         st = _stream()
         lt = L.LOSS[self.loss_type]
-        E.begin_step()
+        E.begin_step(dev)
         losses = E.zeros(8, dev)
         world = dp.world_size()
         # Independent chains of the step run on side streams (forked from / joined into the caller's stream):
