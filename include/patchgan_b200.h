@@ -210,6 +210,11 @@ int pg_pack2_nchw_rows(const float* src1, int32_t C1, const float* src2, int32_t
  * ld_n = Cin*16, ldw = 1) writes the weight-gradient straight into the reference layout.  dst2: optional bf16 twin. */
 int pg_im2col_s2(const float* src, int64_t sb, int64_t sc, int64_t sy, int64_t sx, int32_t C, int32_t B, int32_t H, int32_t W,
                  void* dst, void* dst2, int32_t K, int32_t k_off, int32_t dst_dtype, void* stream);
+/* The discriminator batch of trainer.py:65,96 in one launch: dst = im2col rows of [cat(x, .) ; cat(x, y)] for 2B images
+ * (x: NCHW (B,Cx,H,W), y: NCHW (B,Cy,H,W)); the mask columns of the first B images are filled later from the generator's
+ * output with pg_im2col_s2 (k_off = Cx). */
+int pg_im2col_s2_pair(const float* x, int32_t Cx, const float* y, int32_t Cy, int32_t B, int32_t H, int32_t W, void* dst,
+                      void* dst2, int32_t K, int32_t dst_dtype, void* stream);
 /* Every weight tensor of a network in one launch.  jobs_dev: DEVICE array; each job is one pg_pack_weight call;
  * tile_begin = first 8x32x16 brick of the job in the launch, ctiles = ceil((C1p+C2p)/32).
  * flip == 2: flat job, dst[i] = convert(src[i]) for i < sn, 4096 elements per brick (operand copies that keep the

@@ -47,6 +47,7 @@ _SIGS = {
     'pg_pack_weight': ([vp, vp, i32, i32, i32, i32, i32, i32, i64, i64, i32, i32, vp], C.c_int),
     'pg_pack2_nchw_rows': ([vp, i32, vp, i32, vp, vp, i32, i32, i32, i32, i32, vp], C.c_int),
     'pg_pack_weights_multi': ([vp, i32, i32, vp], C.c_int),
+    'pg_im2col_s2_pair': ([vp, i32, vp, i32, i32, i32, i32, vp, vp, i32, i32, vp], C.c_int),
     'pg_im2col_s2': ([vp, i64, i64, i64, i64, i32, i32, i32, i32, vp, vp, i32, i32, i32, vp], C.c_int),
     'pg_instnorm_stats': ([vp, i32, i32, i64, i32, i32, vp, vp], C.c_int),
     'pg_norm_act_fwd': ([vp, i32, vp, vp, i32, vp, i32, i64, i32, i32, i32, i32, f32, vp, u64, vp], C.c_int),

@@ -119,10 +119,15 @@ __global__ void __launch_bounds__(256) pack2_rows_kernel(const float* __restrict
 // networks (3 / 4 real input channels: 16x channel padding as implicit GEMMs) run as one dense pointwise GEMM with
 // K = 16*Cin and their weight-gradients land in the reference layout without a transpose.  The source is addressed
 // with explicit element strides, so NCHW planes and a channel of an NHWC tensor both work.
+// (src_b / C_b / dst_b_off: optional second source whose channels follow the first's and are written only to the rows
+//  dst_b_off elements further on, while the first source's channels are written to BOTH places -- the discriminator batch
+//  [cat(x, .) ; cat(x, y)] of trainer.py:65,96 in one launch.)
 __global__ void __launch_bounds__(256) im2col_s2_kernel(const float* __restrict__ src, long long sb, long long sc, long long sy,
                                                        long long sx, int C, int H, int W, int Ho, int Wo,
                                                        unsigned short* __restrict__ dst, unsigned short* __restrict__ dst2,
-                                                       int K, int k_off, int dt, long long per_c) {
+                                                       int K, int k_off, int dt, long long per_c,
+                                                       const float* __restrict__ src_b, long long sb_b, long long sc_b,
+                                                       long long dst_b_off) {
   // thread = (channel, output pixel), output pixel fastest: coalesced reads, one full 32-byte sector per write
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
@@ -130,7 +135,8 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const float* __restrict_
   const int ox = (int)(i % Wo);
   const long long r = i / Wo;
   const int oy = (int)(r % Ho), b = (int)(r / Ho);
-  const float* plane = src + b * sb + c * sc;
+  const bool second = c >= C;
+  const float* plane = second ? src_b + b * sb_b + (c - C) * sc_b : src + b * sb + c * sc;
   float v[16];
 #pragma unroll
   for (int kh = 0; kh < 4; ++kh) {
@@ -142,11 +148,25 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const float* __restrict_
     }
   }
   const long long o = i * K + (long long)(k_off + c) * 16;
-  *reinterpret_cast<uint4*>(dst + o) = pack8dt(v, dt);
-  *reinterpret_cast<uint4*>(dst + o + 8) = pack8dt(v + 8, dt);
+  const uint4 lo = pack8dt(v, dt), hi = pack8dt(v + 8, dt);
+  if (!second) {
+    *reinterpret_cast<uint4*>(dst + o) = lo;
+    *reinterpret_cast<uint4*>(dst + o + 8) = hi;
+  }
+  if (second || dst_b_off != 0) {
+    *reinterpret_cast<uint4*>(dst + dst_b_off + o) = lo;
+    *reinterpret_cast<uint4*>(dst + dst_b_off + o + 8) = hi;
+  }
   if (dst2 != nullptr) {
-    *reinterpret_cast<uint4*>(dst2 + o) = pack8(v);
-    *reinterpret_cast<uint4*>(dst2 + o + 8) = pack8(v + 8);
+    const uint4 lo2 = pack8(v), hi2 = pack8(v + 8);
+    if (!second) {
+      *reinterpret_cast<uint4*>(dst2 + o) = lo2;
+      *reinterpret_cast<uint4*>(dst2 + o + 8) = hi2;
+    }
+    if (second || dst_b_off != 0) {
+      *reinterpret_cast<uint4*>(dst2 + dst_b_off + o) = lo2;
+      *reinterpret_cast<uint4*>(dst2 + dst_b_off + o + 8) = hi2;
+    }
   }
 }
 
@@ -318,7 +338,23 @@ extern "C" int pg_im2col_s2(const float* src, int64_t sb, int64_t sc, int64_t sy
   const long long per_c = (long long)B * Ho * Wo;
   dim3 grid((unsigned)((per_c + 255) / 256), (unsigned)C);
   im2col_s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src, sb, sc, sy, sx, C, H, W, Ho, Wo, (unsigned short*)dst,
-                                                         (unsigned short*)dst2, K, k_off, dst_dtype, per_c);
+                                                         (unsigned short*)dst2, K, k_off, dst_dtype, per_c, nullptr, 0, 0, 0);
+  return check_launch("im2col_s2_kernel");
+}
+
+extern "C" int pg_im2col_s2_pair(const float* x, int32_t Cx, const float* y, int32_t Cy, int32_t B, int32_t H, int32_t W, void* dst,
+                                 void* dst2, int32_t K, int32_t dst_dtype, void* stream) {
+  PG_REQUIRE(x && y && dst && Cx > 0 && Cy > 0 && B > 0 && H > 1 && W > 1 && (H % 2) == 0 && (W % 2) == 0,
+             "pg_im2col_s2_pair: bad extents");
+  PG_REQUIRE(K % 16 == 0 && (Cx + Cy) * 16 <= K, "pg_im2col_s2_pair: K=%d Cx=%d Cy=%d", K, Cx, Cy);
+  PG_REQUIRE(dst_dtype == PG_BF16 || dst_dtype == PG_F16, "pg_im2col_s2_pair: dst_dtype must be 16-bit");
+  PG_REQUIRE((((uintptr_t)dst | (uintptr_t)dst2) & 15) == 0, "pg_im2col_s2_pair: dst must be 16-byte aligned");
+  const int Ho = H / 2, Wo = W / 2;
+  const long long per_c = (long long)B * Ho * Wo, HW = (long long)H * W;
+  dim3 grid((unsigned)((per_c + 255) / 256), (unsigned)(Cx + Cy));
+  im2col_s2_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, Cx * HW, HW, W, 1, Cx, H, W, Ho, Wo, (unsigned short*)dst,
+                                                         (unsigned short*)dst2, K, 0, dst_dtype, per_c, y, Cy * HW, HW,
+                                                         per_c * K);
   return check_launch("im2col_s2_kernel");
 }
 

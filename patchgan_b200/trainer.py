@@ -128,9 +128,8 @@ class Trainer:
             xin = E.first_im2col(B, H, W, cin, dev, twin=train)
             E.im2col_fill(xin, 0, x.data_ptr(), xs, cin, 0, B, H, W)
             dboth = E.first_im2col(2 * B, H, W, cin + cout, dev, twin=train)
-            E.im2col_fill(dboth, 0, x.data_ptr(), xs, cin, 0, B, H, W)
-            E.im2col_fill(dboth, B, x.data_ptr(), xs, cin, 0, B, H, W)
-            E.im2col_fill(dboth, B, y.data_ptr(), E.nchw_strides(y), cout, cin, B, H, W)
+            L.call('pg_im2col_s2_pair', x.data_ptr(), cin, y.data_ptr(), cout, B, H, W, dboth.ptr,
+                   dboth.tw.ptr if dboth.tw is not None else None, dboth.ld, dboth.dt, st)
         else:
             xin = G.pack_input(x, twin=train)
         if im2col:
