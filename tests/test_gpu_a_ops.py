@@ -380,7 +380,8 @@ def test_inference_tiling_bit_exact():
 
 @pytest.mark.parametrize('impl', IMPLS, ids=IMPL_IDS)
 @pytest.mark.parametrize('case', [(2, 32, 64, 32, 2), (2, 256, 512, 16, 1), (3, 64, 64, 4, 2), (2, 128, 256, 32, 2),
-                                  (1, 64, 128, 31, 1), (2, 48, 96, 20, 2), (2, 16, 7, 12, 2)], ids=str)
+                                  (1, 64, 128, 31, 1), (2, 48, 96, 20, 2), (2, 16, 7, 12, 2),
+                                  (8, 128, 256, 32, 2), (3, 256, 512, 24, 1), (4, 128, 384, 20, 1)], ids=str)
 def test_conv2d_weight_gradient_tap_major_and_finalize(case, impl):
     """pg_conv_wgrad_tapmajor (TMA bulk-reduce epilogue on the tcgen05 path) + pg_grad_finalize_multi == reference layout."""
     from patchgan_b200.engine import NetEngine
