@@ -1,11 +1,14 @@
-// CUDA-core kernels for the "skinny" 4x4 convolutions of the path: layers with ONE real channel on one side
+// Layers with ONE real channel on one side
 //   * generator output layer   ConvTranspose2d(2nf -> output_nc=1)      (unet.py:106-107)
 //   * discriminator last layer  Conv2d(8ndf -> 1, stride 1)              (disc.py:45)
 //   * the data-gradient of the discriminator's first layer w.r.t. the generated mask channel (trainer.py:84-89)
-// and their data- / weight-gradients.  As GEMMs these have N = 1 (or K-per-tap = 1): on the tensor cores they would
-// be padded 16x and still move the same bytes, so they are HBM-bound streaming problems and are written that way:
-// every byte of the wide tensor is read (or written) once with 16-byte coalesced vectors, the 1-channel tensor and the
-// weights come from L1 / shared memory, fp32 accumulation.  (conv_tc.cu handles every layer with real GEMM shape.)
+// and their data- / weight-gradients.  As 4x4 convolutions these are GEMMs with N = 1 (or K-per-tap = 1).
+//
+// This file holds (a) the cheap halves of the formulation the engine uses -- pointwise products over the 16 taps on the
+// tensor cores (PG_CONV1X1 in conv_tc.cu) with taps_gather / taps_scatter around them (bottom of the file) -- and (b) a
+// CUDA-core implementation of the same layers (fewout / fewin / wgrad1, PG_IMPL_SKINNY).  (b) was written first as a
+// streaming kernel set; with ~15 FLOP per byte it turned out instruction-bound (~0.5 TB/s) and 1.5-3x slower than (a), and
+// is kept as an independently written second implementation that the GPU tests compare with the oracle.
 #include "common.cuh"
 
 namespace pg {

@@ -1,6 +1,6 @@
 // Implicit-GEMM 4x4 convolutions on the 5th-generation tensor cores (sm_100a):
 //   TMA (cp.async.bulk.tensor, tiled mode, zero OOB fill; stride-2 layers through four phase-split views) -> swizzled smem
-//   -> tcgen05.mma (cta_group::1, kind::f16, bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
+//   -> tcgen05.mma (cta_group::1, kind::f16, f16 x f16 or bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
 //
 // No im2col is ever materialised.  For every (tap, channel-chunk) k-step the A operand is ONE TMA box of
 // the NHWC activation tensor:
@@ -10,13 +10,19 @@
 //              boxes do the same job but the TMA engine walks them at ~3.7 ns per row, 35 GB/s per SM -- measured with
 //              tools/tma_probe.cu -- which made every stride-2 layer TMA-bound.)
 //   PG_CONVT : per output-parity class (py,px) a stride-1 box {BK, TW, TH, TB} at (c, x0+px-i, y0+py-j, b0)
+//   PG_CONV1X1: pointwise, one "tap" (first-layer im2col GEMMs and the tap products of the one-real-channel layers)
 // padding = TMA out-of-bounds zero fill; the skip concat = a second tensor map (K loop walks src1 then src2).
 // The B operand is a 2D box {BK, BN} of the packed weights [N][16*Ctot].
 //
+// Kernels in this file:
+//   conv_tc_kernel       one output tile per CTA, up to 4 CTAs per SM; optional split-K over a CTA cluster
+//   conv_tc_pers_kernel  persistent: two CTAs per SM walk the tiles, double-buffered TMEM accumulators
+//   wgrad_tc_kernel      weight gradient (MN-major operands, split-K over pixel tiles, TMA bulk-reduce epilogue)
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
-// warps 2..5 = epilogue (each owns the TMEM lane quarter warp_id % 4).
+// warps 2..5 = epilogue (each owns the TMEM lane quarter warp_id % 4): bias / activation / activation-gradient /
+// InstanceNorm statistics / TMA store.
 // Reference ops replaced: aten::convolution under nn.Conv2d / nn.ConvTranspose2d (unet.py:19,53; disc.py:19-45)
-// and their dgrad.
+// and their dgrad / wgrad.
 #include <cuda.h>
 #include <stdlib.h>
 
