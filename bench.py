@@ -319,10 +319,26 @@ def run_ours(args, cfg):
     dev_ms = dp.max_over_ranks(dev_ms, dev)
 
     # ---- end to end through the public API: pinned host inputs -> Trainer.batch -> loss dict on the host
+    for _ in range(3):          # untimed: staging slots, pinned loss slots and the copy stream are created on first use
+        tr.batch(x_host, y_host, train=True)
+    #      (a) Trainer.batch: upload, step, loss read-back, strictly one after the other (the reference's calling pattern)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         losses = tr.batch(x_host, y_host, train=True)
+    torch.cuda.synchronize()
+    e2e_sync_s = dp.max_over_ranks(time.perf_counter() - t0, dev)
+    #      (b) Trainer.submit / .result() with one batch of lookahead -- the loop Trainer.train runs: every step still
+    #      uploads its own inputs from pinned host memory and reads its own losses back, all inside the timed region
+    barrier()
+    t0 = time.perf_counter()
+    pending = None
+    for _ in range(args.steps):
+        nxt = tr.submit(x_host, y_host, train=True)
+        if pending is not None:
+            losses = pending.result()
+        pending = nxt
+    losses = pending.result()
     torch.cuda.synchronize()
     e2e_s = dp.max_over_ranks(time.perf_counter() - t0, dev)
     clock_info = finish_clocks(clocks) if rank == 0 else None
@@ -380,7 +396,10 @@ def run_ours(args, cfg):
                 clocks=clock_info,
                 e2e=dict(value=round(world * B * args.steps / e2e_s, 2), unit='img/s',
                          h2d_bytes_per_step=int(x_host.numel() * 4 + y_host.numel() * 4), d2h_bytes_per_step=32,
-                         ms_per_step=round(e2e_s / args.steps * 1e3, 4)),
+                         ms_per_step=round(e2e_s / args.steps * 1e3, 4),
+                         api='Trainer.submit(x_host, y_host).result(), one batch of lookahead (the loop of Trainer.train)',
+                         sync_batch_value=round(world * B * args.steps / e2e_sync_s, 2),
+                         sync_batch_api='Trainer.batch(x_host, y_host): upload, step, read-back in sequence'),
                 gpu_launches=int(launches), roofline=roof,
                 step_tensor=dict(algorithmic_gflop_per_img=cfg['gflop_per_img'], achieved_tflops=round(step_tf, 2),
                                  frac_of_peak=round(step_tf / pk['tf_sustained'], 4)),

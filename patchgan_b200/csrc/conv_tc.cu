@@ -170,6 +170,7 @@ struct TcParams {
   int tma_store, st_rowbytes, st_cw, st_nbuf, st_twin;
   unsigned long long* trace;   // debug: 8 timestamps per CTA (pg_debug_set_trace), else null
   int pers_total, pers_mtiles, pers_ntiles;   // persistent variant: work items = (m-tile fastest, n-tile, class)
+  int pers_defer, pers_nch;                   // deferred store drain across tiles; store chunks per tile
   uint32_t pers_stage_off, pers_slot_cols;    // staging buffers behind the ring; TMEM columns per accumulator slot
   int splits, kps;             // K-split cluster: `splits` CTAs (cluster dims (1,1,splits)) share one tile, kps k-steps each
   float* ws;                   // split-K exchange buffer in global memory (L2-resident): [tile][rank][128 rows][BN] fp32
@@ -231,6 +232,8 @@ __device__ __forceinline__ float act_fast(float x) {
 struct EpiCtx {
   uint32_t smem_base, tmem_acc;
   int x0, y0, b0, n0, py, px, cls;
+  int seq0 = 0;      // store chunks this CTA has issued before this tile (persistent kernel with deferred drain), else 0
+  int defer = 0;     // 1: do not wait for the tile's bulk stores here; the next use of a staging buffer (or the CTA's exit) does
 };
 
 template <int ACT>
@@ -292,6 +295,28 @@ template <int U>
 __device__ __forceinline__ void epi_tmem(const TcParams& p, uint32_t trow, int c, uint32_t* v) {
 #pragma unroll
   for (int i = 0; i < U; i += 16) tmem_ld16(trow + (uint32_t)(c + i), v + i);
+  if (U == 16 && p.nacc == 2) {           // the loads of all rotating accumulators in flight under ONE wait
+    uint32_t w[16];
+    tmem_ld16(trow + (uint32_t)(p.BN + c), w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+    return;
+  }
+  if (U == 16 && p.nacc == 4) {           // two loads per wait (three would not fit the 80-register budget of occupancy 4)
+    uint32_t w[16];
+    tmem_ld16(trow + (uint32_t)(p.BN + c), w);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+    uint32_t w2[16];
+    tmem_ld16(trow + (uint32_t)(2 * p.BN + c), w);
+    tmem_ld16(trow + (uint32_t)(3 * p.BN + c), w2);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + (__uint_as_float(w[j]) + __uint_as_float(w2[j])));
+    return;
+  }
   tmem_ld_wait();
   for (int a = 1; a < p.nacc; ++a) {
 #pragma unroll
@@ -373,8 +398,9 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
     const int cls = e.cls;
     const int nch = p.BN / p.st_cw;
     for (int ch = 0; ch < nch; ++ch) {
-      const int buf = ch % p.st_nbuf;
-      if (ch >= p.st_nbuf) {                              // the buffer's previous store must have been read
+      const int g = e.seq0 + ch;                          // running chunk number: bulk groups complete in this order
+      const int buf = g % p.st_nbuf;
+      if (g >= p.st_nbuf) {                               // the buffer's previous store must have been read
         if (et == 0) { if (p.st_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
         epi_bar_sync();
       }
@@ -419,7 +445,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
         bulk_commit();
       }
     }
-    if (et == 0) bulk_wait_read<0>();
+    if (et == 0 && !e.defer) bulk_wait_read<0>();
   } else {
     const int xl = r & (p.TW - 1);
     const int yl = (r >> p.lgTW) & (p.TH - 1);
@@ -801,15 +827,22 @@ struct MmaState {
   uint32_t a_lo, b_lo, stage, phase;
 };
 
-template <int KK>
+template <int KK, bool TR = false>
 __device__ __forceinline__ void mma_issue_tile(const TcParams& p, MmaState& st, uint32_t full0, uint32_t empty0, uint32_t done_bar,
-                                               uint32_t a_lo0, uint32_t b_lo0, uint64_t desc_hi, uint32_t tmem_acc, int ksteps) {
+                                               uint32_t a_lo0, uint32_t b_lo0, uint64_t desc_hi, uint32_t tmem_acc, int ksteps,
+                                               long long* waited = nullptr) {
   const uint32_t idesc = p.idesc, stages = (uint32_t)p.stages;
   const uint32_t a_step = p.a_bytes >> 4, b_step = p.b_bytes >> 4;
   const uint32_t acc_wrap = (uint32_t)(p.nacc * p.BN), bn = (uint32_t)p.BN;
   uint32_t acc_off = 0, fresh = (uint32_t)p.nacc;
   for (int ks = 0; ks < ksteps; ++ks) {
-    mbar_wait(full0 + st.stage * 8, st.phase);
+    if (TR) {
+      const long long w0 = clock64();
+      mbar_wait(full0 + st.stage * 8, st.phase);
+      *waited += clock64() - w0;
+    } else {
+      mbar_wait(full0 + st.stage * 8, st.phase);
+    }
     tc_fence_after();
 #pragma unroll
     for (int k = 0; k < KK; ++k) {
@@ -843,6 +876,10 @@ __device__ __forceinline__ TileXY pers_decode(const TcParams& p, int w) {
   return t;
 }
 
+// TR = true: the per-CTA trace build (tools/conv_trace.py): slots 0 start, 1 setup done, 2 first accumulator ready, 6 exit
+// (%globaltimer), 7 SM id, 8 producer cycles waiting for ring slots, 9 issuer cycles waiting for operands, 10 issuer cycles
+// waiting for a drained accumulator, 11 epilogue cycles waiting for an accumulator, 12 epilogue busy cycles, 13 tiles, 15 = 1
+template <bool TR>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ ActMaps mapsO, const TcParams p) {
@@ -875,17 +912,26 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
     fence_barrier_init();
     fence_proxy_async();
   }
+  if (TR && threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace_raw(p.trace, 0, gtimer());
+    trace_raw(p.trace, 7, smid);
+    trace_raw(p.trace, 15, 1);
+  }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_sh), p.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
+  if (TR && threadIdx.x == 0) trace_raw(p.trace, 1, gtimer());
 
   if (warp == 0) {
     // ===================== TMA producer: the ring runs ahead across tiles =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      long long pwait = 0;
       for (int w = blockIdx.x; w < p.pers_total; w += gridDim.x) {
         const TileXY t = pers_decode(p, w);
         int tap = 0, ck = 0, cx = 0, cy = 0, wtap = 0, ph = 0;
@@ -915,7 +961,13 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
               }
             }
           }
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          if (TR) {
+            const long long w0 = clock64();
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            pwait += clock64() - w0;
+          } else {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          }
           const uint32_t fb = smem_u32(&full_bar[stage]);
           mbar_expect_tx(fb, p.tx_bytes);
           if (ck < p.nk1) tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[ph], fb, ck * p.BK, cx, cy, t.b0);
@@ -925,6 +977,7 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
           if (++ck == nk) { ck = 0; ++tap; newtap = true; }
         }
       }
+      if (TR) trace_raw(p.trace, 8, (unsigned long long)pwait);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: accumulator slot it & 1 =====================
@@ -934,25 +987,45 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
       MmaState st{a_lo0, b_lo0, 0u, 0u};
       uint32_t it = 0;
+      long long wfull = 0, wempty = 0;
       for (int w = blockIdx.x; w < p.pers_total; w += gridDim.x, ++it) {
         const uint32_t slot = it & 1u;
-        mbar_wait(smem_u32(&tempty[slot]), ((it >> 1) & 1u) ^ 1u);      // epilogue has drained this slot
+        if (TR) {
+          const long long w0 = clock64();
+          mbar_wait(smem_u32(&tempty[slot]), ((it >> 1) & 1u) ^ 1u);
+          wempty += clock64() - w0;
+        } else {
+          mbar_wait(smem_u32(&tempty[slot]), ((it >> 1) & 1u) ^ 1u);      // epilogue has drained this slot
+        }
         tc_fence_after();
         const uint32_t acc = tmem_base + slot * p.pers_slot_cols;
-        if (p.BK == 64) mma_issue_tile<4>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps);
-        else if (p.BK == 32) mma_issue_tile<2>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps);
-        else mma_issue_tile<1>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps);
+        if (p.BK == 64) mma_issue_tile<4, TR>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps, &wfull);
+        else if (p.BK == 32) mma_issue_tile<2, TR>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps, &wfull);
+        else mma_issue_tile<1, TR>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps, &wfull);
       }
+      if (TR) { trace_raw(p.trace, 9, (unsigned long long)wfull); trace_raw(p.trace, 10, (unsigned long long)wempty); }
     }
   } else {
     // ===================== epilogue =====================
     uint32_t it = 0;
+    long long ewait = 0, ebusy = 0, e0 = 0;
     for (int w = blockIdx.x; w < p.pers_total; w += gridDim.x, ++it) {
       const TileXY t = pers_decode(p, w);
       const uint32_t slot = it & 1u;
-      mbar_wait(smem_u32(&tfull[slot]), (it >> 1) & 1u);
+      if (TR) {
+        const long long w0 = clock64();
+        mbar_wait(smem_u32(&tfull[slot]), (it >> 1) & 1u);
+        e0 = clock64();
+        ewait += e0 - w0;
+        if (it == 0 && threadIdx.x == 64) trace_raw(p.trace, 2, gtimer());
+      } else {
+        mbar_wait(smem_u32(&tfull[slot]), (it >> 1) & 1u);
+      }
       tc_fence_after();
-      const EpiCtx e{smem_base + p.pers_stage_off, tmem_base + slot * p.pers_slot_cols, t.x0, t.y0, t.b0, t.n0, t.py, t.px, t.cls};
+      // (deferred drain: the bulk stores of this tile are still reading the staging buffer while the next tile's
+      //  accumulators are read and converted; a buffer is waited for right before it is written again)
+      const EpiCtx e{smem_base + p.pers_stage_off, tmem_base + slot * p.pers_slot_cols, t.x0, t.y0, t.b0, t.n0, t.py, t.px, t.cls,
+                     p.pers_defer ? (int)it * p.pers_nch : 0, p.pers_defer};
       switch (p.act) {
         case PG_ACT_RELU: tc_epilogue<PG_ACT_RELU, 16>(p, mapsO, e); break;
         case PG_ACT_LEAKYRELU: tc_epilogue<PG_ACT_LEAKYRELU, 16>(p, mapsO, e); break;
@@ -962,7 +1035,14 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
       }
       tc_fence_before();
       asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[slot])) : "memory");
-      epi_bar_sync();      // the staging buffers are free again (thread 64 has waited for the bulk stores to read them)
+      if (!p.pers_defer) epi_bar_sync();      // the staging buffers are free again (thread 64 has waited for the bulk stores)
+      if (TR) ebusy += clock64() - e0;
+    }
+    if (p.pers_defer && p.tma_store && threadIdx.x == 64) bulk_wait_read<0>();   // smem must outlive the last stores
+    if (TR && threadIdx.x == 64) {
+      trace_raw(p.trace, 11, (unsigned long long)ewait);
+      trace_raw(p.trace, 12, (unsigned long long)ebusy);
+      trace_raw(p.trace, 13, it);
     }
   }
   tc_fence_before();
@@ -971,6 +1051,7 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (TR && threadIdx.x == 0) trace_raw(p.trace, 6, gtimer());
 }
 
 static unsigned long long* g_trace = nullptr;
@@ -1227,7 +1308,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     const long long mtiles = (long long)pl.grid.x, ntn = d->N / p.BN;
     const long long total = mtiles * ntn * ncls;
     static const int pers_min = [] { const char* e = getenv("PG_TC_PERSIST_MIN"); return e ? atoi(e) : 1; }();
-    if (pers_env && g_trace == nullptr && p.splits == 1 && total >= (long long)pers_min * num_sms() && total < (1LL << 30)) {
+    if (pers_env && p.splits == 1 && total >= (long long)pers_min * num_sms() && total < (1LL << 30)) {
       int nacc = p.nacc;
       while (nacc > 1 && 2 * nacc * p.BN > 256) nacc >>= 1;
       const int cols = 2 * nacc * p.BN;
@@ -1240,13 +1321,18 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
       const bool tst = tma_st_env2 && d->ldo >= d->N && rowbytes >= 32 && ((uintptr_t)out & 15) == 0 &&
                        (twin == 0 || ((uintptr_t)out2 & 15) == 0);
       // staging: double-buffered unless the tile is a single store chunk anyway
+      static const int defer_env = [] { const char* e = getenv("PG_TC_DEFER"); return e ? atoi(e) : 1; }();
       const int nch = p.BN / (rowbytes / esz);
-      const int nbuf = nch >= 2 ? 2 : 1;
-      const uint32_t staging = tst ? (uint32_t)nbuf * (1 + twin) * 128u * rowbytes : 0u;
       const uint32_t per_stage = p.a_bytes + p.b_bytes;
       // (one persistent CTA per SM loses to four short-lived ones when the tile is epilogue-bound: keep two per SM)
       const uint32_t budget = 220u * 1024u / occ - 2048u;
+      // with the deferred drain one-chunk tiles alternate between two staging buffers as well (if the ring keeps 2 stages)
+      int nbuf = (nch >= 2 || (defer_env && tst)) ? 2 : 1;
+      if (nch < 2 && nbuf == 2 && budget < 2u * (1 + twin) * 128u * rowbytes + 2u * per_stage) nbuf = 1;
+      const uint32_t staging = tst ? (uint32_t)nbuf * (1 + twin) * 128u * rowbytes : 0u;
       int stages = budget > staging ? (int)((budget - staging) / per_stage) : 0;
+      p.pers_defer = defer_env && tst ? 1 : 0;
+      p.pers_nch = nch;
       pers_nbuf = nbuf;
       if (stages > MAX_STAGES) stages = MAX_STAGES;
       // (BN = 256 needs all 512 TMEM columns for two slots -> one CTA per SM, which measured slower than two co-resident
@@ -1305,12 +1391,14 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   if (pers) {
     static bool pers_set = false;
     if (!pers_set) {
-      PG_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
+      PG_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
+      PG_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
       pers_set = true;
     }
     if (dbg) fprintf(stderr, "conv_tc: persistent grid %u stages %d nacc %d tmem %u smem %zu work %d\n", pers_grid.x, p.stages, p.nacc,
                      p.tmem_cols, pers_smem, p.pers_total);
-    conv_tc_pers_kernel<<<pers_grid, TC_THREADS, pers_smem, stream>>>(mA, mB, mO, p);
+    if (p.trace != nullptr) conv_tc_pers_kernel<true><<<pers_grid, TC_THREADS, pers_smem, stream>>>(mA, mB, mO, p);
+    else conv_tc_pers_kernel<false><<<pers_grid, TC_THREADS, pers_smem, stream>>>(mA, mB, mO, p);
     return check_launch("conv_tc_pers_kernel");
   }
   if (p.splits > 1) {

@@ -175,19 +175,23 @@ __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f
   float* sh_rstd = sh + C;
   const int b = blockIdx.y;
   const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
+  const Span s = make_span(C, HW, ppb);
+  const long long base = (long long)b * HW;
+  // the first batch of loads does not depend on the statistics: issue it before the (mean, rstd) prologue
+  float f[UNR][8];
+  long long p0 = s.pbeg + s.my_pl;
+  if (s.active) {
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p0 + u * s.pl < s.pend) load8(x, x_f32, (base + p0 + u * s.pl) * ldx + s.my_cg * 8, f[u]);
+  }
   load_stats(sums, b, C, HW, sh_mean, sh_rstd);
-  Span s = make_span(C, HW, ppb);
   if (!s.active) return;
   float mean[8], rstd[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mean[j] = sh_mean[s.my_cg * 8 + j]; rstd[j] = sh_rstd[s.my_cg * 8 + j]; }
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const long long base = (long long)b * HW;
-  for (long long p0 = s.pbeg + s.my_pl; p0 < s.pend; p0 += UNR * s.pl) {
-    float f[UNR][8];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u)
-      if (p0 + u * s.pl < s.pend) load8(x, x_f32, (base + p0 + u * s.pl) * ldx + s.my_cg * 8, f[u]);
+  while (p0 < s.pend) {
 #pragma unroll
     for (int u = 0; u < UNR; ++u) {
       const long long p = p0 + u * s.pl;
@@ -205,6 +209,10 @@ __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f
       store8(y, y_f32, pix * ldy + s.my_cg * 8, f[u]);
       if (y2 != nullptr) store8(y2, PG_BF16, pix * ldy + s.my_cg * 8, f[u]);
     }
+    p0 += UNR * s.pl;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p0 + u * s.pl < s.pend) load8(x, x_f32, (base + p0 + u * s.pl) * ldx + s.my_cg * 8, f[u]);
   }
 }
 
@@ -245,27 +253,31 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_reduce_kernel(const void* x, 
   extern __shared__ float sh[];
   const int b = blockIdx.y;
   const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
+  const Span s = make_span(C, HW, ppb);
+  const long long base = (long long)b * HW;
+  const int c0 = s.my_cg * 8;
+  // first batch of x / dy loads in flight across the (mean, rstd) prologue
+  float f[UNB][8], g[UNB][8];
+  long long p0 = s.pbeg + s.my_pl;
+  if (s.active) {
+#pragma unroll
+    for (int u = 0; u < UNB; ++u)
+      if (p0 + u * s.pl < s.pend) {
+        load8(x, x_f32, (base + p0 + u * s.pl) * ldx + c0, f[u]);
+        load_dy(dy1, ld1, dy2, ld2, base + p0 + u * s.pl, c0, g[u]);
+      }
+  }
   load_stats(sums, b, C, HW, sh, sh + C);
-  Span s = make_span(C, HW, ppb);
   float a1[8], a2[8], mean[8], rstd[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     a1[j] = a2[j] = 0.f;
-    mean[j] = s.active ? sh[s.my_cg * 8 + j] : 0.f;
-    rstd[j] = s.active ? sh[C + s.my_cg * 8 + j] : 1.f;
+    mean[j] = s.active ? sh[c0 + j] : 0.f;
+    rstd[j] = s.active ? sh[C + c0 + j] : 1.f;
   }
   __syncthreads();       // sh is reused by reduce_channels
   if (s.active) {
-    const long long base = (long long)b * HW;
-    const int c0 = s.my_cg * 8;
-    for (long long p0 = s.pbeg + s.my_pl; p0 < s.pend; p0 += UNB * s.pl) {
-      float f[UNB][8], g[UNB][8];
-#pragma unroll
-      for (int u = 0; u < UNB; ++u)
-        if (p0 + u * s.pl < s.pend) {
-          load8(x, x_f32, (base + p0 + u * s.pl) * ldx + c0, f[u]);
-          load_dy(dy1, ld1, dy2, ld2, base + p0 + u * s.pl, c0, g[u]);
-        }
+    while (p0 < s.pend) {
 #pragma unroll
       for (int u = 0; u < UNB; ++u) {
         if (p0 + u * s.pl >= s.pend) break;
@@ -277,6 +289,13 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_reduce_kernel(const void* x, 
           a2[j] = fmaf(g[u][j], xh[j], a2[j]);
         }
       }
+      p0 += UNB * s.pl;
+#pragma unroll
+      for (int u = 0; u < UNB; ++u)
+        if (p0 + u * s.pl < s.pend) {
+          load8(x, x_f32, (base + p0 + u * s.pl) * ldx + c0, f[u]);
+          load_dy(dy1, ld1, dy2, ld2, base + p0 + u * s.pl, c0, g[u]);
+        }
     }
   }
   reduce_channels(a1, a2, s, C, sh, bsums, b);
@@ -291,11 +310,22 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
   extern __shared__ float sh[];
   const int b = blockIdx.y;
   const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
+  const Span s = make_span(C, HW, ppb);
+  const long long base = (long long)b * HW;
+  const int c0 = s.my_cg * 8;
+  float f[UNB][8], g[UNB][8];
+  long long p0 = s.pbeg + s.my_pl;
+  if (s.active) {
+#pragma unroll
+    for (int u = 0; u < UNB; ++u)
+      if (p0 + u * s.pl < s.pend) {
+        load8(x, x_f32, (base + p0 + u * s.pl) * ldx + c0, f[u]);
+        load_dy(dy1, ld1, dy2, ld2, base + p0 + u * s.pl, c0, g[u]);
+      }
+  }
   load_stats(sums, b, C, HW, sh, sh + C);
-  Span s = make_span(C, HW, ppb);
   if (!s.active) return;
   float mean[8], rstd[8], m1[8], m2[8];
-  const int c0 = s.my_cg * 8;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     mean[j] = sh[c0 + j];
@@ -307,15 +337,7 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
       m1[j] = 0.f; m2[j] = 0.f;
     }
   }
-  const long long base = (long long)b * HW;
-  for (long long p0 = s.pbeg + s.my_pl; p0 < s.pend; p0 += UNB * s.pl) {
-    float f[UNB][8], g[UNB][8];
-#pragma unroll
-    for (int u = 0; u < UNB; ++u)
-      if (p0 + u * s.pl < s.pend) {
-        load8(x, x_f32, (base + p0 + u * s.pl) * ldx + c0, f[u]);
-        load_dy(dy1, ld1, dy2, ld2, base + p0 + u * s.pl, c0, g[u]);
-      }
+  while (p0 < s.pend) {
 #pragma unroll
     for (int u = 0; u < UNB; ++u) {
       const long long pix = base + p0 + u * s.pl;
@@ -326,6 +348,13 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
       for (int j = 0; j < 8; ++j) g[u][j] = rstd[j] * (g[u][j] - m1[j] - xh[j] * m2[j]);
       store8(dx, 0, pix * lddx + c0, g[u]);
     }
+    p0 += UNB * s.pl;
+#pragma unroll
+    for (int u = 0; u < UNB; ++u)
+      if (p0 + u * s.pl < s.pend) {
+        load8(x, x_f32, (base + p0 + u * s.pl) * ldx + c0, f[u]);
+        load_dy(dy1, ld1, dy2, ld2, base + p0 + u * s.pl, c0, g[u]);
+      }
   }
 }
 
@@ -344,6 +373,16 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_small_kernel(const void* x, i
   __shared__ float sh_tot[16];
   const int b = blockIdx.y, c0 = blockIdx.x * 8;
   const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
+  const long long base = (long long)b * HW;
+  float g[SMALL_PPT][8], xh[SMALL_PPT][8];      // xh holds the raw x until the statistics are known
+#pragma unroll
+  for (int u = 0; u < SMALL_PPT; ++u) {
+    const int p = threadIdx.x + u * NT;
+    if (p < HW) {
+      load8(x, x_f32, (base + p) * ldx + c0, xh[u]);
+      load_dy(dy1, ld1, dy2, ld2, base + p, c0, g[u]);
+    }
+  }
   if (threadIdx.x < 8) {
     float m = 0.f, r = 1.f;
     if (sums != nullptr) mean_rstd(sums, b, C, c0 + threadIdx.x, HW, m, r);
@@ -354,8 +393,6 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_small_kernel(const void* x, i
   float mean[8], rstd[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mean[j] = sh_stat[j]; rstd[j] = sh_stat[8 + j]; }
-  const long long base = (long long)b * HW;
-  float g[SMALL_PPT][8], xh[SMALL_PPT][8];
   float a1[8], a2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) a1[j] = a2[j] = 0.f;
@@ -363,10 +400,7 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_small_kernel(const void* x, i
   for (int u = 0; u < SMALL_PPT; ++u) {
     const int p = threadIdx.x + u * NT;
     if (p < HW) {
-      float f[8];
-      load8(x, x_f32, (base + p) * ldx + c0, f);
-      load_dy(dy1, ld1, dy2, ld2, base + p, c0, g[u]);
-      dxhat8(f, g[u], base + p, C, c0, act, drop_p, seed, mean, rstd, xh[u]);
+      dxhat8(xh[u], g[u], base + p, C, c0, act, drop_p, seed, mean, rstd, xh[u]);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a1[j] += g[u][j];
@@ -439,9 +473,13 @@ __global__ void softmax_fwd_kernel(const float* x, float* y, long long npix, int
   }
 }
 
-static void span_grid(int B, long long HW, int C, dim3& grid, long long& ppb) {
+// bps: blocks of this kernel that fit one SM (registers).  One full wave of long-lived blocks: the (mean, rstd) prologue is
+// paid once per block and there is no partial last wave.  PG_NORM_BPS=n overrides (8 = the earlier many-short-blocks grid).
+static void span_grid(int B, long long HW, int C, dim3& grid, long long& ppb, int bps) {
+  static const int bps_env = [] { const char* e = getenv("PG_NORM_BPS"); return e ? atoi(e) : 0; }();
+  if (bps_env > 0) bps = bps_env;
   const int pl = NT / (C >> 3);
-  long long per_img = (8LL * num_sms() + B - 1) / B;
+  long long per_img = bps_env > 0 ? ((long long)bps * num_sms() + B - 1) / B : ((long long)bps * num_sms()) / B;
   if (per_img < 1) per_img = 1;
   ppb = (HW + per_img - 1) / per_img;
   if (ppb < 1LL * pl) ppb = 1LL * pl;
@@ -462,7 +500,7 @@ extern "C" int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_
                                  float* sums, void* stream) {
   if (int e = check_c("pg_instnorm_stats", C)) return e;
   dim3 grid; long long ppb;
-  span_grid(B, HW, C, grid, ppb);
+  span_grid(B, HW, C, grid, ppb, 4);
   instnorm_stats_kernel<<<grid, NT, reduce_smem(C), (cudaStream_t)stream>>>(x, x_f32, HW, C, ld, sums, ppb);
   return check_launch("instnorm_stats_kernel");
 }
@@ -472,7 +510,7 @@ extern "C" int pg_norm_act_fwd(const void* x, int32_t x_f32, const float* sums, 
                                const uint64_t* seed, uint64_t salt, void* stream) {
   if (int e = check_c("pg_norm_act_fwd", C)) return e;
   dim3 grid; long long ppb;
-  span_grid(B, HW, C, grid, ppb);
+  span_grid(B, HW, C, grid, ppb, 3);
   norm_act_fwd_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, sums, y, y_f32, y2, HW, C, ldx, ldy, act, drop_p,
                                                             (const unsigned long long*)seed, salt, ppb);
   return check_launch("norm_act_fwd_kernel");
@@ -485,7 +523,7 @@ extern "C" int pg_norm_act_bwd_reduce(const void* x, int32_t x_f32, const float*
   if (int e = check_c("pg_norm_act_bwd_reduce", C)) return e;
   PG_REQUIRE(sums != nullptr, "pg_norm_act_bwd_reduce: sums is NULL");
   dim3 grid; long long ppb;
-  span_grid(B, HW, C, grid, ppb);
+  span_grid(B, HW, C, grid, ppb, 2);
   norm_act_bwd_reduce_kernel<<<grid, NT, reduce_smem(C), (cudaStream_t)stream>>>(
       x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb);
   return check_launch("norm_act_bwd_reduce_kernel");
@@ -497,7 +535,7 @@ extern "C" int pg_norm_act_bwd_apply(const void* x, int32_t x_f32, const float* 
                                      const uint64_t* seed, uint64_t salt, void* stream) {
   if (int e = check_c("pg_norm_act_bwd_apply", C)) return e;
   dim3 grid; long long ppb;
-  span_grid(B, HW, C, grid, ppb);
+  span_grid(B, HW, C, grid, ppb, 2);
   norm_act_bwd_apply_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, dx,
                                                                   lddx, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb);
   return check_launch("norm_act_bwd_apply_kernel");

@@ -39,6 +39,27 @@ def weights_init(net, init_type='normal', scaling=0.02):
     return None
 
 
+class PendingLosses:
+    """Handle returned by ``Trainer.submit``: the step is queued on the device, ``result()`` waits for its four loss
+    scalars and returns the reference's six-entry loss dict (trainer.py:109-113)."""
+
+    def __init__(self, host, event):
+        self._host, self._event, self._value = host, event, None
+
+    def done(self):
+        return self._value is not None or self._event.query()
+
+    def result(self):
+        if self._value is None:
+            self._event.synchronize()
+            seg, gdisc, discr, discf = (float(v) for v in self._host[:4])
+            gen_loss = float(np.float32(seg) + np.float32(gdisc))
+            disc_loss = float((np.float32(discf) + np.float32(discr)) / np.float32(2.))
+            self._value = dict(zip(LOSS_KEYS, [gen_loss, gen_loss, gdisc, discr, discf, disc_loss]))
+            self._host = None
+        return self._value
+
+
 class Trainer:
     '''
         Drives training of a UNet generator against a PatchGAN discriminator
@@ -69,8 +90,11 @@ class Trainer:
         if not os.path.exists(savefolder):
             os.mkdir(savefolder)
         self.start = 1
-        self._host_losses = None
         self._graphs = {}
+        self._copy_stream = None      # host->device staging (submit): two input slots, four loss slots
+        self._stage = {}
+        self._loss_slots = []
+        self._submits = 0
 
     # ------------------------------------------------------------------------------------------
     # one G+D step
@@ -341,16 +365,46 @@ class Trainer:
             ent['graph_update'].replay()
         return ent['losses']
 
-    def batch(self, x, y, train=False):
-        '''
-            Train the generator and discriminator on a single batch
-        '''
-        input_tensor = self._to_device(x)
-        target_tensor = self._to_device(y)
-        if input_tensor.device.type != 'cuda':
-            raise RuntimeError('patchgan_b200.Trainer runs on CUDA (sm_100a) only; there is no CPU path')
-        input_tensor = input_tensor.float().contiguous()
-        target_tensor = target_tensor.float().contiguous()
+    def _stage_inputs(self, x, y):
+        """Pinned host float tensors: copy into one of two device staging slots on the copy stream, so that the upload of
+        batch i+1 runs under the step of batch i (the step's first kernels wait on the slot's event only).  Anything
+        else (device tensors, pageable memory, numpy, other dtypes) takes the plain ``.to(device)`` route of
+        trainer.py:55-56."""
+        def pinned_f32(a):
+            return isinstance(a, torch.Tensor) and a.device.type == 'cpu' and a.dtype == torch.float32 and \
+                a.is_contiguous() and a.is_pinned()
+        if not (pinned_f32(x) and pinned_f32(y)) or torch.device(self.device).type != 'cuda':
+            xd, yd = self._to_device(x), self._to_device(y)
+            if xd.device.type != 'cuda':
+                raise RuntimeError('patchgan_b200.Trainer runs on CUDA (sm_100a) only; there is no CPU path')
+            return xd.float().contiguous(), yd.float().contiguous(), None
+        dev = torch.device(self.device)
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        key = (tuple(x.shape), tuple(y.shape), dev.index)
+        slots = self._stage.get(key)
+        if slots is None:
+            slots = self._stage[key] = [dict(x=torch.empty(x.shape, dtype=torch.float32, device=dev),
+                                             y=torch.empty(y.shape, dtype=torch.float32, device=dev),
+                                             ready=torch.cuda.Event(), free=None) for _ in range(2)]
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        slot = slots[self._submits % 2]
+        cs = self._copy_stream
+        if slot['free'] is not None:
+            cs.wait_event(slot['free'])          # the step that last read this slot
+        with torch.cuda.stream(cs):
+            slot['x'].copy_(x, non_blocking=True)
+            slot['y'].copy_(y, non_blocking=True)
+            slot['ready'].record(cs)
+        torch.cuda.current_stream(dev).wait_event(slot['ready'])
+        return slot['x'], slot['y'], slot
+
+    def submit(self, x, y, train=False):
+        """Queue one ``batch`` without waiting for it: returns a ``PendingLosses`` whose ``result()`` is the loss dict.
+        With pinned host inputs the host->device copies go through a copy stream, so a loop that submits batch i+1
+        before asking for the result of batch i (``_run_epoch`` does) hides both the upload and the loss read-back."""
+        input_tensor, target_tensor, slot = self._stage_inputs(x, y)
         if train:
             if not hasattr(self, 'gen_optimizer'):
                 raise AttributeError("'Trainer' object has no attribute 'gen_optimizer' (call train() or "
@@ -358,15 +412,32 @@ class Trainer:
             self.gen_optimizer.sync_lr()
             self.disc_optimizer.sync_lr()
         losses = self.step(input_tensor, target_tensor, train)
-        # one device->host copy instead of six .item() calls (trainer.py:110-111)
-        if self._host_losses is None:
-            self._host_losses = torch.empty(8, dtype=torch.float32, pin_memory=True)
-        self._host_losses.copy_(losses, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        seg, gdisc, discr, discf = (float(v) for v in self._host_losses[:4])
-        gen_loss = float(np.float32(seg) + np.float32(gdisc))
-        disc_loss = float((np.float32(discf) + np.float32(discr)) / np.float32(2.))
-        return dict(zip(LOSS_KEYS, [gen_loss, gen_loss, gdisc, discr, discf, disc_loss]))
+        main = torch.cuda.current_stream(input_tensor.device)
+        if slot is not None:
+            if slot['free'] is None:
+                slot['free'] = torch.cuda.Event()
+            slot['free'].record(main)
+        # one device->host copy instead of six .item() calls (trainer.py:110-111); a slot is reused only after its
+        # previous owner has been read
+        if not self._loss_slots:
+            self._loss_slots = [dict(host=torch.empty(8, dtype=torch.float32, pin_memory=True), owner=None)
+                                for _ in range(4)]
+        ls = self._loss_slots[self._submits % len(self._loss_slots)]
+        if ls['owner'] is not None:
+            ls['owner'].result()
+        ls['host'].copy_(losses, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        pending = PendingLosses(ls['host'], ev)
+        ls['owner'] = pending
+        self._submits += 1
+        return pending
+
+    def batch(self, x, y, train=False):
+        '''
+            Train the generator and discriminator on a single batch
+        '''
+        return self.submit(x, y, train).result()
 
     # ------------------------------------------------------------------------------------------
     # epoch driver (trainer.py:117-279)
@@ -377,12 +448,25 @@ class Trainer:
             data.shuffle()
         sums = defaultdict(float)
         loss_mean = {}
-        for i, (input_img, target_mask) in enumerate(pbar):
-            batch_loss = self.batch(input_img, target_mask, train=train)
+        done = 0
+
+        def account(batch_loss):
+            nonlocal done
+            done += 1
             for key, value in batch_loss.items():
                 sums[key] += value           # O(1) running mean (the reference re-averages a growing list)
-                loss_mean[key] = sums[key] / (i + 1)
+                loss_mean[key] = sums[key] / done
             pbar.set_postfix_str(" ".join(f"{key}: {value:.2e}" for key, value in loss_mean.items()))
+
+        # one batch of lookahead: batch i+1 is uploaded and queued before the losses of batch i are read
+        pending = None
+        for input_img, target_mask in pbar:
+            nxt = self.submit(input_img, target_mask, train=train)
+            if pending is not None:
+                account(pending.result())
+            pending = nxt
+        if pending is not None:
+            account(pending.result())
         return loss_mean
 
     def train(self, train_data, val_data, epochs, dsc_learning_rate=1.e-3,

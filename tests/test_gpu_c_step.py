@@ -212,3 +212,36 @@ def test_cuda_graph_replay_matches_eager(tmp_path):
         for k in a:
             assert abs(a[k] - b[k]) <= 5e-3 * abs(a[k]), (k, a[k], b[k])
     assert traj[True][0]['gen'] != traj[True][5]['gen']                          # and it really trains
+
+
+def test_submit_lookahead_matches_batch(tmp_path):
+    """Trainer.submit with pinned host inputs (copy-stream upload, deferred loss read -- the loop of Trainer.train)
+    follows the same trajectory as synchronous Trainer.batch calls, with different data in consecutive batches so that
+    a staging-slot race would show."""
+    gk, dk, loss_type, B, steps = CASES['mae']
+    data = []
+    for i in range(6):
+        x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=100 + i)
+        data.append((torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()))
+    tr, _, _ = build(gk, dk, loss_type, tmp_path)
+    sync = [tr.batch(x, y, train=True) for x, y in data]
+    tr2, _, _ = build(gk, dk, loss_type, tmp_path)
+    handles, piped = [], []
+    for x, y in data:
+        handles.append(tr2.submit(x, y, train=True))
+        if len(handles) >= 2:
+            piped.append(handles[-2].result())
+    piped.append(handles[-1].result())
+    assert handles[0].done() and handles[0].result() is piped[0]
+    for a, b in zip(sync, piped):
+        assert list(a) == list(b)
+        for k in a:
+            assert abs(a[k] - b[k]) <= 5e-3 * abs(a[k]), (k, a[k], b[k])
+    assert sync[0]['gen'] != sync[1]['gen']
+    # six outstanding submits never read: the four loss slots are recycled by resolving their previous owners
+    hs = [tr2.submit(x, y, train=False) for x, y in data]
+    vals = [h.result() for h in hs]
+    ev = [tr2.batch(x, y, train=False) for x, y in data]
+    for a, b in zip(vals, ev):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 1e-4 * abs(b[k]) + 1e-7, (k, a[k], b[k])

@@ -48,6 +48,17 @@ def run(mode, stride, pad, B, H, Ci, Co):
     t = t[t[:, 0] != 0]
     n = len(t)
     t0 = t[:, 0].min()
+    if n and t[0, 15] == 1:            # persistent kernel: per-CTA totals (cycles -> us at 1.9 GHz)
+        cyc = lambda a: f'{np.median(a)/1.9e3:6.2f}/{np.max(a)/1.9e3:6.2f}'
+        r = lambda a: f'{np.median(a)/1e3:6.2f}/{np.max(a)/1e3:6.2f}'
+        span = (t[:, 6].max() - t0) / 1e3
+        tiles = t[:, 13]
+        print(f'{mode} s{stride} B{B} {H}x{H} C{Ci}->N{Co} [persistent]: ctas {n} event {us_plain:7.1f}us span {span:7.1f}us '
+              f'{flops/span/1e6:7.1f} TF/s | tiles/cta {np.median(tiles):.0f} start(med/max) {r(t[:,0]-t0)} setup {r(t[:,1]-t[:,0])} '
+              f'first-acc {r(t[:,2]-t[:,1])} life {r(t[:,6]-t[:,0])} | us per CTA: producer-wait-ring {cyc(t[:,8])} issuer-wait-operands {cyc(t[:,9])} '
+              f'issuer-wait-drain {cyc(t[:,10])} epi-wait-acc {cyc(t[:,11])} epi-busy {cyc(t[:,12])} | epi-busy per tile '
+              f'{np.median(t[:,12]/np.maximum(tiles,1))/1.9e3:5.2f} us')
+        return
     span = (t[:, 6].max() - t0) / 1e3
     r = lambda a: f'{np.median(a)/1e3:6.2f}/{np.max(a)/1e3:6.2f}'
     sm = t[:, 7]
@@ -58,6 +69,13 @@ def run(mode, stride, pad, B, H, Ci, Co):
 if __name__ == '__main__':
     ensure_workspace(torch.device('cuda', 0))
     pass
+    if len(sys.argv) >= 2 and sys.argv[1] == 'q':      # persistent-kernel shapes of cfg 3
+        for s in [('conv1x1', 1, 0, 32, 128, 64, 64), ('conv1x1', 1, 0, 16, 128, 48, 32), ('conv1x1', 1, 0, 16, 128, 64, 16),
+                  ('conv', 2, 1, 16, 128, 32, 64), ('conv', 2, 1, 16, 64, 64, 128), ('conv', 2, 1, 32, 128, 64, 128),
+                  ('convT', 2, 1, 16, 32, 256, 64), ('convT', 2, 1, 16, 64, 128, 32), ('convT', 2, 1, 32, 64, 128, 64),
+                  ('convT', 2, 1, 32, 32, 256, 128), ('conv1x1', 1, 0, 32, 31, 16, 512)]:
+            run(*s)
+        sys.exit(0)
     sel = SHAPES if len(sys.argv) < 2 else ([('conv1x1', 1, 0, 32, 128, 64, 64), ('conv1x1', 1, 0, 16, 128, 48, 32), ('conv1x1', 1, 0, 16, 128, 64, 16), ('convT', 2, 1, 32, 64, 128, 64)] if sys.argv[1] == 'p' else [s for s in SHAPES if s[3] == 32])
     for s in sel:
         run(*s)
