@@ -313,8 +313,21 @@ __global__ void __launch_bounds__(256) colsum_vec_kernel(const pg::bf16* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) a[j] += f[j];
     }
+    if ((cg & (cg - 1)) == 0 && cg <= 32) {
+      // lanes that share a channel group sit cg apart: shuffle them together first (256 threads adding to the same 8
+      // shared words, as with cg = 1 for the one-channel bias, serialised for ~20 us)
+      for (int off = cg; off < 32; off <<= 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(&sh[my_cg * 8 + j], a[j]);
+        for (int j = 0; j < 8; ++j) a[j] += __shfl_xor_sync(0xffffffffu, a[j], off);
+      }
+      if ((threadIdx.x & 31) < cg) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&sh[my_cg * 8 + j], a[j]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(&sh[my_cg * 8 + j], a[j]);
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n_real; i += 256) atomicAdd(db + i, sh[i]);

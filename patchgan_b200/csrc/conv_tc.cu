@@ -1758,7 +1758,10 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   const int gx = (N + 127) / 128, gy = p.ctiles * (p.pointwise ? 1 : 16 / p.T);
   // Split-K over pixel tiles: every CTA ends with 128 x 256 fp32 atomics into dW, so a CTA should own enough pixel
   // tiles (>= 8, ~1 us of MMA) to amortise them; beyond that, split until ~2 CTAs per SM exist.
-  int splits = (2 * num_sms() + gx * gy - 1) / (gx * gy);
+  // (rounded DOWN: 2 CTAs fit an SM, and a few CTAs beyond 2 x SMs would run as a second wave on an otherwise idle GPU --
+  //  the largest discriminator layer had 320 CTAs for 296 slots)
+  static const int split_ceil = [] { const char* e = getenv("PG_WG_SPLIT_CEIL"); return e ? atoi(e) : 0; }();
+  int splits = split_ceil ? (2 * num_sms() + gx * gy - 1) / (gx * gy) : (2 * num_sms()) / (gx * gy);
   const int max_splits = p.total_tiles / 8 > 0 ? p.total_tiles / 8 : 1;
   if (splits > max_splits) splits = max_splits;
   if (splits > p.total_tiles) splits = p.total_tiles;

@@ -170,8 +170,26 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const float* __restrict_
   }
 }
 
+// Job lookup of the multi-tensor kernels: the job whose [tile_begin, next tile_begin) holds `tile`.  The first njobs threads
+// each test one job (ONE global round trip; a per-block binary search by thread 0 was four dependent ones and made these
+// short blocks latency-bound), then sizeof(Job)/4 threads copy the descriptor to shared memory.  Ends with __syncthreads().
+template <typename Job>
+__device__ __forceinline__ void find_job(const Job* __restrict__ jobs, int njobs, int tile, Job* sh_job, int* sh_idx) {
+  for (int i = threadIdx.x; i < njobs; i += blockDim.x) {
+    const int tb = jobs[i].tile_begin;
+    const int te = i + 1 < njobs ? jobs[i + 1].tile_begin : 0x7fffffff;
+    if (tb <= tile && tile < te) { sh_idx[0] = i; sh_idx[1] = te; }      // sh_idx[1]: first tile of the next job
+  }
+  __syncthreads();
+  const int idx = sh_idx[0];
+  if (threadIdx.x < sizeof(Job) / 4)
+    reinterpret_cast<int*>(sh_job)[threadIdx.x] = reinterpret_cast<const int*>(jobs + idx)[threadIdx.x];
+  __syncthreads();
+}
+
 // Tap-major weight-gradient scratch S[tap][Ns][Cs] -> reference layout dst[n*ld_n + c*16 + tap] for every layer of a
-// network in ONE launch (jobs as in pack_weight_multi_kernel; one block = one n, 32 channels, 16 taps).
+// network in ONE launch (jobs as in pack_weight_multi_kernel; one tile = one n, 32 channels, 16 taps; a block walks
+// GF_TILES consecutive tiles with all their loads in flight before the first store).
 struct GradJob {               // mirrors PgGradJob
   const float* S;
   float* dst;
@@ -180,28 +198,40 @@ struct GradJob {               // mirrors PgGradJob
   int tile_begin, ctiles;
 };
 
-__global__ void __launch_bounds__(256) grad_finalize_multi_kernel(const GradJob* __restrict__ jobs, int njobs) {
-  __shared__ float tile[16][33];
+constexpr int GF_TILES = 8;
+
+__global__ void __launch_bounds__(256) grad_finalize_multi_kernel(const GradJob* __restrict__ jobs, int njobs, int total_tiles) {
+  __shared__ float tile[GF_TILES][16][33];
   __shared__ GradJob job;
-  if (threadIdx.x == 0) {
-    int lo = 0, hi = njobs - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
+  __shared__ int job_idx[2];
+  const int tile0 = blockIdx.x * GF_TILES;
+  int ntiles = total_tiles - tile0;
+  if (ntiles > GF_TILES) ntiles = GF_TILES;
+  find_job(jobs, njobs, tile0, &job, job_idx);
+  int done = 0;
+  while (done < ntiles) {
+    // tiles [done, upto) of this block belong to the current job
+    const int job_end = job_idx[1];
+    int upto = job_end < total_tiles ? job_end - tile0 : ntiles;
+    if (upto > ntiles) upto = ntiles;
+    for (int e = threadIdx.x; e < (upto - done) * 512; e += 256) {
+      const int k = done + (e >> 9), t = (e >> 5) & 15, cl = e & 31;
+      const int local = tile0 + k - job.tile_begin;
+      const int n = local / job.ctiles, c = (local % job.ctiles) * 32 + cl;
+      tile[k][t][cl] = c < job.C ? job.S[((long long)t * job.Ns + n) * job.Cs + c] : 0.f;
     }
-    job = jobs[lo];
-  }
-  __syncthreads();
-  const int local = blockIdx.x - job.tile_begin;
-  const int n = local / job.ctiles, c0 = (local % job.ctiles) * 32;
-  for (int e = threadIdx.x; e < 512; e += 256) {
-    const int t = e >> 5, cl = e & 31, c = c0 + cl;
-    tile[t][cl] = c < job.C ? job.S[((long long)t * job.Ns + n) * job.Cs + c] : 0.f;
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 512; e += 256) {
-    const int cl = e >> 4, t = e & 15, c = c0 + cl;
-    if (c < job.C) job.dst[n * job.ld_n + (long long)c * 16 + t] = tile[t][cl];
+    __syncthreads();
+    for (int e = threadIdx.x; e < (upto - done) * 512; e += 256) {
+      const int k = done + (e >> 9), cl = (e >> 4) & 31, t = e & 15;
+      const int local = tile0 + k - job.tile_begin;
+      const int n = local / job.ctiles, c = (local % job.ctiles) * 32 + cl;
+      if (c < job.C) job.dst[n * job.ld_n + (long long)c * 16 + t] = tile[k][t][cl];
+    }
+    done = upto;
+    if (done < ntiles) {           // the block straddles two tensors (block-uniform)
+      __syncthreads();
+      find_job(jobs, njobs, tile0 + done, &job, job_idx);
+    }
   }
 }
 
@@ -217,15 +247,8 @@ struct PackJob {              // mirrors PgPackJob
 __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const PackJob* __restrict__ jobs, int njobs) {
   __shared__ float tile[8][32][17];
   __shared__ PackJob job;
-  if (threadIdx.x == 0) {
-    int lo = 0, hi = njobs - 1;              // last job whose tile_begin <= blockIdx.x
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].tile_begin <= (int)blockIdx.x) lo = mid; else hi = mid - 1;
-    }
-    job = jobs[lo];
-  }
-  __syncthreads();
+  __shared__ int job_idx[2];
+  find_job(jobs, njobs, (int)blockIdx.x, &job, job_idx);
   const int local = blockIdx.x - job.tile_begin;
   if (job.flip == 2) {
     // flat job: dst[i] = convert(src[i]), i < sn (first-layer [N][Cin*16] and tap-product [Cin][16] operand copies,
@@ -250,11 +273,15 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const PackJob* _
     tile[nl][cl][t] = v;
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 8 * 32 * 16; e += 256) {
-    const int cl = e & 31, t = (e >> 5) & 15, nl = e >> 9;
+  // two channels (4 bytes) per store; Cp is a multiple of 16, so a pair never straddles the padded row end
+  for (int e = threadIdx.x; e < 8 * 16 * 16; e += 256) {
+    const int cl = (e & 15) * 2, t = (e >> 4) & 15, nl = e >> 8;
     const int n = n0 + nl, cp = cp0 + cl;
-    if (n < job.Np && cp < Cp)
-      job.dst[((long long)n * 16 + t) * Cp + cp] = to16(tile[nl][cl][job.flip ? 15 - t : t], job.dt);
+    if (n < job.Np && cp < Cp) {
+      const int ts = job.flip ? 15 - t : t;
+      const unsigned lo = to16(tile[nl][cl][ts], job.dt), hi = to16(tile[nl][cl + 1][ts], job.dt);
+      *reinterpret_cast<unsigned*>(job.dst + ((long long)n * 16 + t) * Cp + cp) = lo | (hi << 16);
+    }
   }
 }
 
@@ -361,7 +388,8 @@ extern "C" int pg_im2col_s2_pair(const float* x, int32_t Cx, const float* y, int
 extern "C" int pg_grad_finalize_multi(const PgGradJob* jobs_dev, int32_t njobs, int32_t total_tiles, void* stream) {
   static_assert(sizeof(PgGradJob) == sizeof(GradJob), "PgGradJob layout");
   PG_REQUIRE(jobs_dev != nullptr && njobs > 0 && total_tiles > 0, "pg_grad_finalize_multi: empty job list");
-  grad_finalize_multi_kernel<<<(unsigned)total_tiles, 256, 0, (cudaStream_t)stream>>>((const GradJob*)jobs_dev, njobs);
+  grad_finalize_multi_kernel<<<(unsigned)((total_tiles + GF_TILES - 1) / GF_TILES), 256, 0, (cudaStream_t)stream>>>(
+      (const GradJob*)jobs_dev, njobs, total_tiles);
   return check_launch("grad_finalize_multi_kernel");
 }
 

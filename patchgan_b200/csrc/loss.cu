@@ -84,38 +84,43 @@ __global__ void __launch_bounds__(256) seg_loss_partials_kernel(const float* __r
   }
 }
 
+// One warp; lane b owns batch element b (strided for B > 32): the per-sample terms are computed side by side and summed by
+// shuffles (a single thread walking the batch with fp64 divisions took 13 us between the generator's forward and backward).
 __global__ void seg_loss_finalize_kernel(const float* part, float* coef, float* losses, int slot, int B, int C,
                                          long long HW, int loss_type, float beta, float gamma, float seg_alpha) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  if (blockIdx.x != 0) return;
+  const int lane = threadIdx.x;
   const double cnt = (double)B * C * (double)HW;
+  auto warp_sum_d = [](double v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+  };
   if (loss_type == LT_TVERSKY) {
     // losses.py:18-31 with smooth = 1; tp = sum t p, fn = sum t - tp, fp = sum p - tp
     double m = 0;
-    for (int b = 0; b < B; ++b) {
+    for (int b = lane; b < B; b += 32) {
       const double tp = part[b * 8], st = part[b * 8 + 1], sp = part[b * 8 + 2];
       const double num = tp + 1.0, den = tp + beta * (st - tp) + (1.0 - beta) * (sp - tp) + 1.0;
       m += 1.0 - num / den;
     }
-    m /= B;
-    losses[slot] = (float)(seg_alpha * pow(m, (double)gamma));
+    m = warp_sum_d(m) / B;
+    if (lane == 0) losses[slot] = (float)(seg_alpha * pow(m, (double)gamma));
     const double k0 = -seg_alpha * gamma * pow(m, (double)gamma - 1.0) / B;
-    for (int b = 0; b < B; ++b) {
+    for (int b = lane; b < B; b += 32) {
       const double tp = part[b * 8], st = part[b * 8 + 1], sp = part[b * 8 + 2];
       const double num = tp + 1.0, den = tp + beta * (st - tp) + (1.0 - beta) * (sp - tp) + 1.0;
       // dTI/dp = (t*den - num*(1-beta)) / den^2
       coef[b * 4 + 0] = (float)(k0 / den);                          // multiplies t
       coef[b * 4 + 1] = (float)(-k0 * num * (1.0 - beta) / (den * den));  // constant term
     }
-  } else if (loss_type == LT_WBCE) {
-    double s = 0;
-    for (int b = 0; b < B; ++b) s += part[b * 8 + 4];
-    losses[slot] = (float)(seg_alpha * s / cnt);
-    for (int b = 0; b < B; ++b) coef[b * 4] = (float)(seg_alpha / cnt);
   } else {
+    const int col = loss_type == LT_WBCE ? 4 : 3;
     double s = 0;
-    for (int b = 0; b < B; ++b) s += part[b * 8 + 3];
-    losses[slot] = (float)(seg_alpha * s / cnt);
-    for (int b = 0; b < B; ++b) coef[b * 4] = (float)(seg_alpha / cnt);
+    for (int b = lane; b < B; b += 32) s += part[b * 8 + col];
+    s = warp_sum_d(s);
+    if (lane == 0) losses[slot] = (float)(seg_alpha * s / cnt);
+    for (int b = lane; b < B; b += 32) coef[b * 4] = (float)(seg_alpha / cnt);
   }
 }
 
