@@ -107,6 +107,9 @@ int pg_tcgen05_available(void);
 /* Debug hook (kernel tuning only): when buf != NULL every conv_tc CTA writes 16 uint64 (globaltimer ns at entry, after
  * setup, first operands landed, last MMA issued, accumulator ready, epilogue done, exit; SM id) at buf[cta*16 ...]. */
 int pg_debug_set_trace(void* buf);
+/* Diagnostics: a one-thread kernel on `stream` that writes %globaltimer (ns) to *slot when the stream gets there; can be
+ * captured into a CUDA graph (tools/timeline.py builds the in-graph timeline of a step from it).  Not a reference op. */
+int pg_debug_stamp(uint64_t* slot, void* stream);
 
 /* Caller-owned device scratch for the split-K convolutions (the 2x2 .. 16x16 bottleneck layers run their K = 16*Cin
  * reduction on a cluster of CTAs that exchange fp32 partial tiles through this L2-resident buffer).  256-byte aligned;

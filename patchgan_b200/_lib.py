@@ -29,6 +29,7 @@ _SIGS = {
     'pg_version': ([], C.c_int),
     'pg_tcgen05_available': ([], C.c_int),
     'pg_debug_set_trace': ([vp], C.c_int),
+    'pg_debug_stamp': ([vp, vp], C.c_int),
     'pg_conv_set_workspace': ([vp, i64], C.c_int),
     'pg_launch_count': ([], C.c_int64),
     'pg_last_conv_impl': ([], C.c_int),
@@ -110,9 +111,14 @@ def check(status, what=''):
 PROFILER = None      # set to an object with begin(name)/end(token) to time every C-ABI call (bench.py)
 
 
+STAMPER = None       # set to a callable (name, args) invoked after every C-ABI call (tools/timeline.py)
+
+
 def call(name, *args):
     if PROFILER is None:
         check(getattr(lib(), name)(*args), name)
+        if STAMPER is not None:
+            STAMPER(name, args)
     else:
         tok = PROFILER.begin(name)
         check(getattr(lib(), name)(*args), name)

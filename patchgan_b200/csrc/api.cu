@@ -87,6 +87,18 @@ extern "C" int64_t pg_launch_count(void) { return (int64_t)g_launches; }
 extern "C" int pg_last_conv_impl(void) { return g_last_impl; }
 extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
 extern "C" int pg_debug_set_trace(void* buf) { set_tc_trace(buf); return PG_OK; }
+
+// In-stream time stamp (tools/timeline.py): *slot = %globaltimer when the stream reaches this point.  Capturable.
+__global__ void debug_stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+extern "C" int pg_debug_stamp(uint64_t* slot, void* stream) {
+  PG_REQUIRE(slot != nullptr, "pg_debug_stamp: slot is NULL");
+  debug_stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)slot);
+  return check_launch("debug_stamp_kernel");
+}
 extern "C" int pg_conv_set_workspace(void* ws, int64_t bytes) {
   PG_REQUIRE((ws == nullptr) == (bytes == 0) && bytes >= 0 && (((uintptr_t)ws) & 255) == 0, "pg_conv_set_workspace: bad buffer");
   set_conv_workspace(ws, (size_t)bytes);
