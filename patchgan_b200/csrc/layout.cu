@@ -208,24 +208,39 @@ __global__ void __launch_bounds__(256) grad_finalize_multi_kernel(const GradJob*
   int ntiles = total_tiles - tile0;
   if (ntiles > GF_TILES) ntiles = GF_TILES;
   find_job(jobs, njobs, tile0, &job, job_idx);
+  // (the first version decoded tile / tap / channel from a flat element index, with an integer division per 4-byte element:
+  //  ncu showed 72 % issue-slot utilisation at 10 % of the DRAM bandwidth.  Now: lane = channel, warp = taps w and w + 8,
+  //  one division per tile.)
+  const int cl = threadIdx.x & 31, tq = threadIdx.x >> 5;
   int done = 0;
   while (done < ntiles) {
     // tiles [done, upto) of this block belong to the current job
     const int job_end = job_idx[1];
     int upto = job_end < total_tiles ? job_end - tile0 : ntiles;
     if (upto > ntiles) upto = ntiles;
-    for (int e = threadIdx.x; e < (upto - done) * 512; e += 256) {
-      const int k = done + (e >> 9), t = (e >> 5) & 15, cl = e & 31;
-      const int local = tile0 + k - job.tile_begin;
-      const int n = local / job.ctiles, c = (local % job.ctiles) * 32 + cl;
-      tile[k][t][cl] = c < job.C ? job.S[((long long)t * job.Ns + n) * job.Cs + c] : 0.f;
+    const long long tstride = (long long)job.Ns * job.Cs;
+    const int first = tile0 + done - job.tile_begin;
+    int n = first / job.ctiles, ct = first - n * job.ctiles;
+    for (int k = done; k < upto; ++k) {
+      const int c = ct * 32 + cl;
+      const float* sp = job.S + (long long)n * job.Cs + c;
+      const bool ok = c < job.C;
+      tile[k][tq][cl] = ok ? sp[tq * tstride] : 0.f;
+      tile[k][tq + 8][cl] = ok ? sp[(tq + 8) * tstride] : 0.f;
+      if (++ct == job.ctiles) { ct = 0; ++n; }
     }
     __syncthreads();
-    for (int e = threadIdx.x; e < (upto - done) * 512; e += 256) {
-      const int k = done + (e >> 9), cl = (e >> 4) & 31, t = e & 15;
-      const int local = tile0 + k - job.tile_begin;
-      const int n = local / job.ctiles, c = (local % job.ctiles) * 32 + cl;
-      if (c < job.C) job.dst[n * job.ld_n + (long long)c * 16 + t] = tile[k][t][cl];
+    n = first / job.ctiles; ct = first - n * job.ctiles;
+    for (int k = done; k < upto; ++k) {
+      // dst[n][c0 .. c0+32)[16 taps] is 512 contiguous floats: two per thread
+      float* dp = job.dst + (long long)n * job.ld_n + (long long)ct * 32 * 16;
+      const int cmax = job.C - ct * 32;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int i = threadIdx.x + h * 256;
+        if ((i >> 4) < cmax) dp[i] = tile[k][i & 15][i >> 4];
+      }
+      if (++ct == job.ctiles) { ct = 0; ++n; }
     }
     done = upto;
     if (done < ntiles) {           // the block straddles two tensors (block-uniform)
@@ -260,27 +275,50 @@ __global__ void __launch_bounds__(256) pack_weight_multi_kernel(const PackJob* _
   }
   const int n0 = (local / job.ctiles) * 8, cp0 = (local % job.ctiles) * 32;
   const int Cp = job.C1p + job.C2p;
-  for (int e = threadIdx.x; e < 8 * 32 * 16; e += 256) {
-    const int t = e & 15;
-    int nl, cl;
-    if (job.sn == 16) { nl = (e >> 4) & 7; cl = e >> 7; } else { cl = (e >> 4) & 31; nl = e >> 9; }
-    const int n = n0 + nl, cp = cp0 + cl;
-    int c = -1;
-    if (cp < job.C1p) { if (cp < job.C1) c = cp; }
-    else if (cp < Cp) { if (cp - job.C1p < job.C2) c = job.C1 + (cp - job.C1p); }
-    float v = 0.f;
-    if (n < job.N && c >= 0) v = job.src[n * job.sn + c * job.sc + t];
-    tile[nl][cl][t] = v;
+  // Every thread owns ONE tap t and walks (n, c) with loop-invariant decoding (the flat-index version spent 65 % of the
+  // issue slots on index arithmetic at 11 % of the DRAM bandwidth).
+  const int t = threadIdx.x & 15, q = threadIdx.x >> 4;            // q = 0..15
+  auto src_channel = [&](int cp) {                                 // padded channel -> real channel or -1
+    if (cp < job.C1p) return cp < job.C1 ? cp : -1;
+    if (cp < Cp) return cp - job.C1p < job.C2 ? job.C1 + (cp - job.C1p) : -1;
+    return -1;
+  };
+  if (job.sn == 16) {
+    // ConvTranspose2d master layout [Cin][Cout][16]: n fastest after the tap.  nl = q & 7, channels q >> 3 + 2 i
+    const int nl = q & 7, n = n0 + nl;
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int cl = (q >> 3) + 2 * i;
+      const int c = src_channel(cp0 + cl);
+      tile[nl][cl][t] = (n < job.N && c >= 0) ? job.src[(long long)n * 16 + (long long)c * job.sc + t] : 0.f;
+    }
+  } else {
+    // Conv2d master layout [Cout][Cin][16]: c fastest after the tap.  channels q and q + 16, all 8 n
+    const int ca = src_channel(cp0 + q), cb = src_channel(cp0 + q + 16);
+#pragma unroll
+    for (int nl = 0; nl < 8; ++nl) {
+      const int n = n0 + nl;
+      const float* sp = job.src + (long long)n * job.sn + t;
+      tile[nl][q][t] = (n < job.N && ca >= 0) ? sp[(long long)ca * job.sc] : 0.f;
+      tile[nl][q + 16][t] = (n < job.N && cb >= 0) ? sp[(long long)cb * job.sc] : 0.f;
+    }
   }
   __syncthreads();
-  // two channels (4 bytes) per store; Cp is a multiple of 16, so a pair never straddles the padded row end
-  for (int e = threadIdx.x; e < 8 * 16 * 16; e += 256) {
-    const int cl = (e & 15) * 2, t = (e >> 4) & 15, nl = e >> 8;
-    const int n = n0 + nl, cp = cp0 + cl;
-    if (n < job.Np && cp < Cp) {
-      const int ts = job.flip ? 15 - t : t;
-      const unsigned lo = to16(tile[nl][cl][ts], job.dt), hi = to16(tile[nl][cl + 1][ts], job.dt);
-      *reinterpret_cast<unsigned*>(job.dst + ((long long)n * 16 + t) * Cp + cp) = lo | (hi << 16);
+  // two channels (4 bytes) per store; Cp is a multiple of 16, so a pair never straddles the padded row end.
+  // thread = (channel pair t', tap q'), loop over the 8 n
+  {
+    const int cl = (threadIdx.x & 15) * 2, tt = threadIdx.x >> 4;
+    const int cp = cp0 + cl;
+    const int ts = job.flip ? 15 - tt : tt;
+    if (cp < Cp) {
+#pragma unroll
+      for (int nl = 0; nl < 8; ++nl) {
+        const int n = n0 + nl;
+        if (n < job.Np) {
+          const unsigned lo = to16(tile[nl][cl][ts], job.dt), hi = to16(tile[nl][cl + 1][ts], job.dt);
+          *reinterpret_cast<unsigned*>(job.dst + ((long long)n * 16 + tt) * Cp + cp) = lo | (hi << 16);
+        }
+      }
     }
   }
 }
