@@ -112,6 +112,22 @@ __device__ __forceinline__ void unpack8dt(const uint4& v, int dt, float* f) {
   if (dt == PG_F16) unpack8h(v, f); else unpack8(v, f);
 }
 __device__ __forceinline__ uint4 pack8dt(const float* f, int dt) { return dt == PG_F16 ? pack8h(f) : pack8(f); }
+// i -> (x = i % W, y = (i / W) % H, b = i / (W * H)).  32-bit divisions when the index allows (a 64-bit division is ~100
+// instructions, more than the rest of a pixel-per-thread kernel).
+__device__ __forceinline__ void split_xyb(long long i, int W, int H, int& x, int& y, int& b) {
+  if (i < 0x7fffffffLL) {
+    const unsigned u = (unsigned)i, r = u / (unsigned)W;
+    x = (int)(u - r * (unsigned)W);
+    b = (int)(r / (unsigned)H);
+    y = (int)(r - (unsigned)b * (unsigned)H);
+  } else {
+    const long long r = i / W;
+    x = (int)(i - r * W);
+    b = (int)(r / H);
+    y = (int)(r - (long long)b * H);
+  }
+}
+
 __device__ __forceinline__ unsigned short to16(float x, int dt) {
   if (dt == PG_F16) return __half_as_ushort(__float2half_rn(x));
   return __bfloat16_as_ushort(__float2bfloat16(x));

@@ -514,9 +514,8 @@ __device__ __forceinline__ int tap_p_of_q(int mode, int stride, int pad, int q, 
 __global__ void __launch_bounds__(256) taps_scatter_kernel(const TapsP t) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t.n) return;
-  const int px = (int)(i % t.Wp);
-  const long long r = i / t.Wp;
-  const int py = (int)(r % t.Hp), b = (int)(r / t.Hp);
+  int px, py, b;
+  split_xyb(i, t.Wp, t.Hp, px, py, b);
   const float* P = reinterpret_cast<const float*>(t.src);
   float acc = t.bias != nullptr ? __ldg(t.bias) : 0.f;
 #pragma unroll
@@ -540,9 +539,8 @@ __global__ void __launch_bounds__(256) taps_scatter_kernel(const TapsP t) {
 __global__ void __launch_bounds__(256) taps_gather_kernel(const TapsP t) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= t.n) return;
-  const int qx = (int)(i % t.Wq);
-  const long long r = i / t.Wq;
-  const int qy = (int)(r % t.Hq), b = (int)(r / t.Hq);
+  int qx, qy, b;
+  split_xyb(i, t.Wq, t.Hq, qx, qy, b);
   const unsigned short* S = reinterpret_cast<const unsigned short*>(t.src);
   unsigned short v[16];
 #pragma unroll

@@ -132,9 +132,8 @@ __global__ void __launch_bounds__(256) im2col_s2_kernel(const float* __restrict_
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int c = blockIdx.y;
   if (i >= per_c) return;
-  const int ox = (int)(i % Wo);
-  const long long r = i / Wo;
-  const int oy = (int)(r % Ho), b = (int)(r / Ho);
+  int ox, oy, b;
+  split_xyb(i, Wo, Ho, ox, oy, b);
   const bool second = c >= C;
   const float* plane = second ? src_b + b * sb_b + (c - C) * sc_b : src + b * sb + c * sc;
   float v[16];
