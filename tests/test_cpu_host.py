@@ -103,3 +103,32 @@ def test_console_entry_points_importable():
     from patchgan_b200.train import patchgan_train  # noqa: F401
     with pytest.raises(RuntimeError, match='CUDA'):
         n_crop(torch.zeros(3, 300, 300), 128, 0.9)
+
+
+def test_pending_losses_builds_the_reference_loss_dict():
+    """Trainer.submit's handle: waits on its event once, then returns the six-entry dict of trainer.py:109-113
+    (gen = gen_loss = seg*alpha + gdisc in fp32, disc = (discf + discr) / 2)."""
+    import numpy as np
+    from patchgan_b200.trainer import LOSS_KEYS, PendingLosses
+
+    class Ev:
+        def __init__(self):
+            self.waits = 0
+
+        def synchronize(self):
+            self.waits += 1
+
+        def query(self):
+            return False
+
+    host = torch.tensor([55.5, 7.25, 0.5, 0.25, 0, 0, 0, 0], dtype=torch.float32)
+    ev = Ev()
+    h = PendingLosses(host, ev)
+    assert not h.done()
+    d = h.result()
+    assert list(d) == LOSS_KEYS == ['gen', 'gen_loss', 'gdisc', 'discr', 'discf', 'disc']
+    assert d['gen'] == d['gen_loss'] == float(np.float32(55.5) + np.float32(7.25))
+    assert (d['gdisc'], d['discr'], d['discf']) == (7.25, 0.5, 0.25)
+    assert d['disc'] == 0.375
+    host[0] = 1.0                       # the pinned slot is recycled by a later submit: the handle keeps its values
+    assert h.result() is d and h.done() and ev.waits == 1
