@@ -299,6 +299,12 @@ int pg_bce_const(const float* p, int32_t ld, float label, float gscale, float* l
  * hyper (device): [0] = lr.  step (device int32): number of steps taken so far; incremented by the call. ---- */
 int pg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int32_t* step,
                  float beta1, float beta2, float eps, float grad_scale, void* stream);
+/* The same update for a sub-range of the flat buffers (pointers already offset, 16-byte aligned): the parameters of a
+ * network may be updated in several launches of one optimizer step -- e.g. the layers whose gradients are final first,
+ * on a side stream, while the backward pass of the remaining layers still runs.  Every launch of the step uses the step
+ * count as it was before the step; exactly one of them (the last in stream order) passes bump = 1. */
+int pg_adam_step_range(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int32_t* step,
+                       float beta1, float beta2, float eps, float grad_scale, int32_t bump, void* stream);
 
 /* ---- inference tiling (infer.py:14-68), "next" row ---- */
 int pg_ncrop(const float* image, float* crops, int32_t C, int32_t H, int32_t W, int32_t size, int32_t eff,

@@ -64,6 +64,7 @@ _SIGS = {
     'pg_gen_out_bwd': ([vp, i32, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i64, i32, i32, f32, vp], C.c_int),
     'pg_bce_const': ([vp, i32, f32, f32, vp, i32, vp, i32, i64, vp], C.c_int),
     'pg_adam_step': ([vp, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, vp], C.c_int),
+    'pg_adam_step_range': ([vp, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, i32, vp], C.c_int),
     'pg_counter_add': ([vp, u64, vp], C.c_int),
     'pg_ncrop': ([vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], C.c_int),
     'pg_build_mask': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp], C.c_int),

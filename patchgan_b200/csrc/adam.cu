@@ -50,18 +50,32 @@ __global__ void bump_step_kernel(int* step) { *step += 1; }
 }  // namespace pg
 using namespace pg;
 
+static int adam_launch(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int32_t* step,
+                       float beta1, float beta2, float eps, float grad_scale, int bump, void* stream);
+
 extern "C" int pg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int32_t* step,
                             float beta1, float beta2, float eps, float grad_scale, void* stream) {
+  return adam_launch(p, g, m, v, n, hyper, step, beta1, beta2, eps, grad_scale, 1, stream);
+}
+
+extern "C" int pg_adam_step_range(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int32_t* step,
+                                  float beta1, float beta2, float eps, float grad_scale, int32_t bump, void* stream) {
+  return adam_launch(p, g, m, v, n, hyper, step, beta1, beta2, eps, grad_scale, bump, stream);
+}
+
+static int adam_launch(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int32_t* step,
+                       float beta1, float beta2, float eps, float grad_scale, int bump, void* stream) {
   PG_REQUIRE(n >= 0, "pg_adam_step: n < 0");
   PG_REQUIRE((((uintptr_t)p | (uintptr_t)g | (uintptr_t)m | (uintptr_t)v) & 15) == 0,
              "pg_adam_step: buffers must be 16-byte aligned");
-  if (n == 0) return PG_OK;
+  if (n == 0 && !bump) return PG_OK;
   long long nb = ((n >> 2) + 255) / 256;
   const long long cap = 8LL * num_sms();
   if (nb > cap) nb = cap;
   if (nb < 1) nb = 1;
   adam_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, hyper, step, beta1, beta2, eps, grad_scale);
   if (int e = check_launch("adam_kernel")) return e;
+  if (!bump) return PG_OK;
   bump_step_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
   return check_launch("bump_step_kernel");
 }

@@ -476,10 +476,11 @@ class NetEngine:
                        ('C1', '<i4'), ('C1p', '<i4'), ('C2', '<i4'), ('C2p', '<i4'), ('flip', '<i4'), ('dt', '<i4'),
                        ('tile_begin', '<i4'), ('ctiles', '<i4')])
 
-    def _build_jobs(self, ps, dev):
-        """Device table for pg_pack_weights_multi: every layer's forward + dgrad operand packs in one launch."""
+    def _build_jobs(self, ps, dev, layers=None):
+        """Device table for pg_pack_weights_multi: every layer's forward + dgrad operand packs in one launch
+        (layers = (first, last): only those layers)."""
         rows, tile = [], 0
-        for pw in self.packed:
+        for pw in (self.packed if layers is None else self.packed[layers[0]:layers[1]]):
             w = ps[pw.spec.wname].detach()
             if w.dtype != torch.float32 or not w.is_contiguous():
                 raise RuntimeError(f'{pw.spec.wname}: weights must be contiguous float32')
@@ -504,6 +505,7 @@ class NetEngine:
     def begin_backward(self):
         """Start collecting weight-gradient jobs for this backward pass; zero the tap-major scratch."""
         self._tm_jobs = []
+        self._tm_done = 0
         self._tm_off = 0
         if taps_enabled():
             if getattr(self, '_tm_buf', None) is None or self._tm_buf.device != self.device():
@@ -533,31 +535,68 @@ class NetEngine:
                 L.PROFILER.note(conv_flops(desc), desc_tag(desc))
             L.call('pg_conv_wgrad_tapmajor', ctypes.byref(desc), a.ptr, g.ptr, g.ld, sp, Ns, Cs, Config.impl, _stream())
 
-    def finalize_grads(self):
-        """Write every tap-major weight-gradient of this backward pass to its reference-layout destination (one launch).
-        Call on a stream that is ordered after all weight-gradient launches."""
+    def finalize_grads(self, partial=False):
+        """Write the tap-major weight-gradients of this backward pass to their reference-layout destinations (one launch).
+        Call on a stream that is ordered after the weight-gradient launches concerned.
+        partial=True: only the jobs collected so far (and not yet written); the pass goes on collecting -- used to update
+        the layers whose gradients are final while the backward of the remaining ones still runs."""
         jobs = getattr(self, '_tm_jobs', None)
-        self._tm_jobs = None
-        if not jobs:
+        if jobs is None:
             return
-        key = tuple(jobs)
-        if self._tm_table is None or self._tm_table[0] != key:
+        start = getattr(self, '_tm_done', 0)
+        todo = jobs[start:]
+        if partial:
+            self._tm_done = len(jobs)
+        else:
+            self._tm_jobs = None
+            self._tm_done = 0
+        if not todo:
+            return
+        key = (start, tuple(todo))
+        if self._tm_table is None:
+            self._tm_table = {}
+        ent = self._tm_table.get(start)
+        if ent is None or ent[0] != key:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError('patchgan_b200: weight-gradient job table changed during CUDA-graph capture')
             rows, tile = [], 0
-            for (sp, dst, ld_n, N, C, Ns, Cs) in jobs:
+            for (sp, dst, ld_n, N, C, Ns, Cs) in todo:
                 ctiles = (C + 31) // 32
                 rows.append((sp, dst, ld_n, N, C, Ns, Cs, tile, ctiles))
                 tile += N * ctiles
             arr = np.array(rows, dtype=self.GRAD_JOB_DT)
-            self._tm_table = (key, torch.from_numpy(arr.view(np.uint8).copy()).to(self.device()), len(rows), tile)
-        _, table, njobs, ntiles = self._tm_table
+            ent = self._tm_table[start] = (key, torch.from_numpy(arr.view(np.uint8).copy()).to(self.device()), len(rows),
+                                           tile)
+        _, table, njobs, ntiles = ent
         L.call('pg_grad_finalize_multi', table.data_ptr(), njobs, ntiles, _stream())
 
     def repack(self):
         """Unconditional repack (used inside captured graphs right after the optimizer step)."""
         self._stamp = None
         self.ensure_packed()
+
+    def layers_match_parameters(self):
+        """True if parameter i of the module is the weight of layer i (no biases): layer ranges are parameter ranges."""
+        return [n for n, _ in self.module.named_parameters()] == [s.wname for s in self.specs]
+
+    def repack_layers(self, first, last, complete):
+        """Repack the operand copies of layers [first, last) on the current stream (their optimizer update is ordered
+        before on this stream).  complete=True on the call that finishes the set: the copies are then up to date."""
+        ps = self.params()
+        ptrs = tuple(ps[s.wname].data_ptr() for s in self.specs)
+        cache = getattr(self, '_part_jobs', None)
+        if cache is None or cache.get('ptrs') != ptrs:
+            cache = self._part_jobs = {'ptrs': ptrs}
+        ent = cache.get((first, last))
+        if ent is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError('patchgan_b200: weight pack job table built during CUDA-graph capture')
+            ent = cache[(first, last)] = self._build_jobs(ps, self.device(), (first, last))
+        table, njobs, ntiles = ent
+        if njobs:
+            L.call('pg_pack_weights_multi', table.data_ptr(), njobs, ntiles, _stream())
+        if complete:
+            self._stamp = tuple((ps[s.wname].data_ptr(), ps[s.wname]._version) for s in self.specs)
 
     def bump_seed(self):
         L.call('pg_counter_add', self.seed.data_ptr(), 1, _stream())
@@ -724,10 +763,12 @@ class GeneratorEngine(NetEngine):
             h = out
         return h, ctx
 
-    def backward(self, ctx, d_raw, grads, need_dx=False, wstream=None):
+    def backward(self, ctx, d_raw, grads, need_dx=False, wstream=None, early=None):
         """d_raw: bf16 Act, gradient wrt the last ConvTranspose2d's output (pre final activation).
         grads: dict name -> zero-initialised float32 tensor in the reference layout (accumulated into).
-        wstream: side stream for the weight-gradient launches (off the data-gradient critical path)."""
+        wstream: side stream for the weight-gradient launches (off the data-gradient critical path).
+        early = (i, fn): fn() is called once everything that touches the layers other than encoder 0 .. i-1 has been
+        issued (their weight-gradients on wstream, the last reads of their operand copies on the current stream)."""
         dev = d_raw.t.device
         B = d_raw.B
         dskip = [None] * 7
@@ -797,6 +838,8 @@ class GeneratorEngine(NetEngine):
                          d_raw, None, self.packed[i].bwd, None, din)
                 dy1 = din
                 dx = din
+            if early is not None and i == early[0]:
+                early[1]()
         if wstream is None:
             self.finalize_grads()       # (with a side stream the caller joins it first, then calls finalize_grads)
         return dx if need_dx else None

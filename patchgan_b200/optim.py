@@ -99,6 +99,20 @@ class FusedAdam(torch.optim.Optimizer):
             self._on_step()
         return loss
 
+    @torch.no_grad()
+    def step_range(self, first, last, bump):
+        """Adam update of parameters [first, last) of the flat order only (pg_adam_step_range).  One optimizer step may be
+        issued as several ranges on different streams; the caller passes bump=True for exactly one of them, ordered after
+        the others, and repacks the operand copies itself (on_step is not called)."""
+        f = self.flat()
+        offs = f['offs'] + [f['n']]
+        lo, hi = offs[first], offs[last]
+        g = self.param_groups[0]
+        b1, b2 = g['betas']
+        L.call('pg_adam_step_range', f['p'].data_ptr() + lo * 4, f['g'].data_ptr() + lo * 4, f['m'].data_ptr() + lo * 4,
+               f['v'].data_ptr() + lo * 4, hi - lo, f['hyper'].data_ptr(), f['step'].data_ptr(), b1, b2, g['eps'],
+               self.grad_scale, 1 if bump else 0, _stream())
+
     def zero_grad(self, set_to_none=False):
         if self._flat is not None:
             self._flat['g'].zero_()

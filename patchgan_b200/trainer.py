@@ -77,6 +77,9 @@ class Trainer:
     # launches; the host cannot keep a B200 fed).  PATCHGAN_B200_GRAPH=0 keeps eager launches.
     use_cuda_graph = os.environ.get('PATCHGAN_B200_GRAPH', '1') != '0'
     GRAPH_WARMUP = 2
+    # generator layers (first encoder layers) updated at the very end of the step; all others are updated on a side stream
+    # while their backward still runs (single GPU, side streams on).  0 = one update at the end.
+    LATE_LAYERS = int(os.environ.get('PATCHGAN_B200_LATE_LAYERS', '2'))
 
     def __init__(self, generator, discriminator, savefolder, device='cuda'):
         generator.apply(weights_init)
@@ -250,6 +253,38 @@ class Trainer:
             L.call('pg_gen_out_bwd', p.ptr, p.ld, y.data_ptr(), chp, coef.data_ptr(), d_dinp.ptr, d_dinp.ld, cin,
                    d_raw.ptr, d_raw.ld, B, cout, H * W, lt, L.ACT[gm.final_act], float(self.tversky_beta), st)
             ggrads = {n: q.grad for n, q in gm.named_parameters()}
+            K = self.LATE_LAYERS
+            if (ms and world == 1 and phase == 'all' and not E.SKIP and K > 0 and len(G.specs) > K
+                    and G.layers_match_parameters()):
+                # ---- single GPU: the step used to end with a serial tail (last weight-gradient -> finalize -> Adam ->
+                #      repack, one kernel on the GPU at a time).  The gradients of every layer but the first K encoder
+                #      layers are final ~0.15 ms before the backward pass ends: those layers are finalized, updated and
+                #      repacked on s_d underneath the rest of the backward; the tail only handles the K late layers.
+                with on(s_d):       # (the discriminator's update first in issue order, the early update queues behind it)
+                    s_d.wait_event(ev_dread)
+                    dopt.step(sync_lr=False)
+                    D.repack()
+                nl = len(G.specs)
+
+                def early_update():
+                    ev_w, ev_m = torch.cuda.Event(), torch.cuda.Event()
+                    ev_w.record(s_w)                 # the weight-gradients of layers K.. (issued on s_w)
+                    ev_m.record()                    # the last reads of their operand copies (data-gradients, this stream)
+                    s_d.wait_event(ev_w)
+                    s_d.wait_event(ev_m)
+                    with on(s_d):
+                        G.finalize_grads(partial=True)
+                        gopt.step_range(K, nl, bump=False)
+                        G.repack_layers(K, nl, complete=False)
+
+                G.backward(gctx, d_raw, ggrads, wstream=s_w, early=(K, early_update))
+                E.join(s_w)
+                G.finalize_grads()
+                E.join(s_d)                          # (the early update reads the step count that the next launch bumps)
+                gopt.step_range(0, K, bump=True)
+                G.repack_layers(0, K, complete=True)
+                E.end_step()
+                return losses
             if 'gbwd' not in E.SKIP:
                 G.backward(gctx, d_raw, ggrads, wstream=s_w)
             if ms:
