@@ -20,3 +20,11 @@ def summarize(t):
     return np.concatenate([[a.mean(), a.std()], a[idx]])
 
 
+
+
+def rect_batch(B=2, H=128, W=256, seed=4321):
+    """Rectangular batch of the 'rect' fixture: x in [0,1), binary one-channel target."""
+    rng = np.random.default_rng(seed)
+    x = rng.random((B, 3, H, W), dtype=np.float32)
+    y = (rng.random((B, 1, H, W), dtype=np.float32) > 0.5).astype(np.float32)
+    return x, y

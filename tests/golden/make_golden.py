@@ -33,7 +33,7 @@ from oracle import patchgan_oracle as orc  # noqa: E402
 
 ref_trainer.device = 'cpu'
 
-from tests.golden.cases import CASES, NS, summarize  # noqa: E402,F401
+from tests.golden.cases import CASES, NS, rect_batch, summarize  # noqa: E402,F401
 
 
 def run_case(name, gk, dk, loss_type, B, steps):
@@ -95,6 +95,38 @@ def run_case(name, gk, dk, loss_type, B, steps):
     print(name, {k: float(v) for k, v in out.items() if '/loss/' in k and k.startswith('s0')})
 
 
+def rect_case():
+    """A rectangular input (128 x 256: the bottleneck is 1 x 2) through a 5-layer discriminator: one training step.
+    Pins the oracle's geometry handling where H != W (every other case is square)."""
+    gk = dict(input_nc=3, output_nc=1, nf=8, activation='leakyrelu', final_act='sigmoid')
+    dk = dict(input_nc=4, ndf=8, n_layers=5, norm=False)
+    og, od = orc.UNet(**gk, seed=21), orc.Discriminator(**dk, seed=22)
+    G, D = patchgan.UNet(**gk), patchgan.Discriminator(**dk)
+    G.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in og.params.items()})
+    D.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in od.params.items()})
+    import tempfile
+    tr = patchgan.Trainer(G, D, tempfile.mkdtemp(), device='cpu')
+    tr.loss_type = 'tversky'
+    tr.gen_optimizer = optim.Adam(G.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    tr.disc_optimizer = optim.Adam(D.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    G.train()
+    D.train()
+    x, y = rect_batch()
+    out = {}
+    with torch.no_grad():
+        out['gen_img'] = summarize(G(torch.from_numpy(x)).numpy())
+        out['disc_shape'] = np.array(D(torch.cat([torch.from_numpy(x), torch.from_numpy(y)], 1)).shape)
+    losses = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=True)
+    for k, v in losses.items():
+        out[f'loss/{k}'] = np.float64(v)
+    for k, p in G.named_parameters():
+        out[f'ggrad/{k}'] = summarize(p.grad.numpy())
+    for k, p in D.named_parameters():
+        out[f'dgrad/{k}'] = summarize(p.grad.numpy())
+    np.savez_compressed(os.path.join(HERE, 'step_rect.npz'), **out)
+    print('rect', {k: float(v) for k, v in out.items() if k.startswith('loss/')}, out['disc_shape'])
+
+
 def losses_case():
     """Direct calls of losses.py functions (incl. tversky / batch_mean=False)."""
     from patchgan import losses as L
@@ -129,7 +161,13 @@ def infer_case():
 if __name__ == '__main__':
     torch.manual_seed(0)
     torch.set_num_threads(8)
+    only = sys.argv[1:]               # e.g. `make_golden.py rect` regenerates one fixture
     for name, (gk, dk, lt, B, steps) in CASES.items():
-        run_case(name, gk, dk, lt, B, steps)
-    losses_case()
-    infer_case()
+        if not only or name in only:
+            run_case(name, gk, dk, lt, B, steps)
+    if not only or 'rect' in only:
+        rect_case()
+    if not only or 'losses' in only:
+        losses_case()
+    if not only or 'infer' in only:
+        infer_case()

@@ -150,3 +150,25 @@ def test_torch_port_matches_reference(name):
                 weights_close(summarize(p.detach().numpy()), gold[f's0/gw/{k}'], 1e-3, 1, 0.05 if name == 'wbce' else 0.0, k)
             for k, p in st.d.items():
                 relnorm(summarize(p.grad.numpy()), gold[f's0/dgrad/{k}'], 1e-4, k)
+
+
+def test_rectangular_step_matches_reference():
+    """H != W (128 x 256, bottleneck 1 x 2) through a 5-layer discriminator: forward, the six losses and every gradient of
+    one training step against the live reference (tests/golden/step_rect.npz)."""
+    from tests.golden.cases import rect_batch
+    gold = np.load(os.path.join(GOLD, 'step_rect.npz'))
+    gk = dict(input_nc=3, output_nc=1, nf=8, activation='leakyrelu', final_act='sigmoid')
+    dk = dict(input_nc=4, ndf=8, n_layers=5, norm=False)
+    G, D = orc.UNet(**gk, seed=21), orc.Discriminator(**dk, seed=22)
+    x, y = rect_batch()
+    close(summarize(G.forward(x)), gold['gen_img'], 1e-3, 2e-5, 'rect gen_img')
+    assert tuple(D.forward(np.concatenate([x, y], 1)).shape) == tuple(gold['disc_shape']) == (2, 1, 2, 6)
+    tr = orc.Trainer(G, D)
+    tr.loss_type = 'tversky'
+    losses = tr.batch(x, y, train=True)
+    for k, v in losses.items():
+        close(v, gold[f'loss/{k}'], 2e-5, 1e-6, f'rect loss {k}')
+    for k, g in tr.last['gen_grads'].items():
+        relnorm(summarize(g), gold[f'ggrad/{k}'], 1e-4, f'rect ggrad {k}')
+    for k, g in tr.last['disc_grads'].items():
+        relnorm(summarize(g), gold[f'dgrad/{k}'], 1e-4, f'rect dgrad {k}')
