@@ -245,3 +245,32 @@ def test_submit_lookahead_matches_batch(tmp_path):
     for a, b in zip(vals, ev):
         for k in a:
             assert abs(a[k] - b[k]) <= 1e-4 * abs(b[k]) + 1e-7, (k, a[k], b[k])
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.xfail(strict=False, reason="added after this round's GPU minutes were used up: not yet run on a GPU "
+                                        "(the oracle side of the same fixture is pinned in test_oracle_golden.py)")
+def test_rectangular_step_matches_reference_golden(tmp_path):
+    """H != W: one training step on a 128 x 256 batch (bottleneck 1 x 2) through a 5-layer discriminator against the
+    live reference's golden (tests/golden/step_rect.npz): losses to 1e-3, gradients norm-wise on the sampled entries."""
+    from tests.golden.cases import rect_batch, summarize
+    gold = np.load(os.path.join(GOLD, 'step_rect.npz'))
+    gk = dict(input_nc=3, output_nc=1, nf=8, activation='leakyrelu', final_act='sigmoid')
+    dk = dict(input_nc=4, ndf=8, n_layers=5, norm=False)
+    og, od = orc.UNet(**gk, seed=21), orc.Discriminator(**dk, seed=22)
+    G, D = P.UNet(**gk), P.Discriminator(**dk)
+    G.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in og.params.items()})
+    D.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in od.params.items()})
+    G, D = G.cuda().train(), D.cuda().train()
+    tr = P.Trainer(G, D, str(tmp_path / 'ckpt'))
+    tr.loss_type = 'tversky'
+    tr.make_optimizers(1e-3, 1e-3)
+    x, y = rect_batch()
+    got = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=True)
+    for k in got:
+        ref = float(gold[f'loss/{k}'])
+        assert abs(got[k] - ref) <= 1e-3 * abs(ref), (k, got[k], ref)
+    gerr = {k: relerr(summarize(p.grad.cpu().numpy()), gold[f'ggrad/{k}']) for k, p in G.named_parameters()}
+    gerr.update({'D.' + k: relerr(summarize(p.grad.cpu().numpy()), gold[f'dgrad/{k}']) for k, p in D.named_parameters()})
+    print('rect grad err vs reference golden (sampled)', short(gerr))
+    assert max(gerr.values()) < GRAD_TOL_FP32, gerr
