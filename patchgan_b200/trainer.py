@@ -438,7 +438,9 @@ class Trainer:
     def submit(self, x, y, train=False):
         """Queue one ``batch`` without waiting for it: returns a ``PendingLosses`` whose ``result()`` is the loss dict.
         With pinned host inputs the host->device copies go through a copy stream, so a loop that submits batch i+1
-        before asking for the result of batch i (``_run_epoch`` does) hides both the upload and the loss read-back."""
+        before asking for the result of batch i (``_run_epoch`` does) hides both the upload and the loss read-back.
+        Pinned inputs are read asynchronously: leave them unmodified until ``result()`` has returned (a DataLoader with
+        ``pin_memory=True`` hands out a fresh tensor per batch)."""
         input_tensor, target_tensor, slot = self._stage_inputs(x, y)
         if train:
             if not hasattr(self, 'gen_optimizer'):
