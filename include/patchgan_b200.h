@@ -102,6 +102,9 @@ int pg_version(void);
 int64_t pg_launch_count(void);
 /* PgImpl the last pg_conv_fwd / pg_conv_wgrad of this thread dispatched to (profiling aid) */
 int pg_last_conv_impl(void);
+/* number of PG_IMPL_AUTO calls of this process that found no tensor-core plan for their shape and ran on the CUDA-core
+ * kernel (the first one is also reported on stderr).  bench.py and the step tests require it to stay 0. */
+int64_t pg_fallback_count(void);
 /* 1 if the library was built with the tcgen05 path and the current device is sm_100. */
 int pg_tcgen05_available(void);
 /* Debug hook (kernel tuning only): when buf != NULL every conv_tc CTA writes 16 uint64 (globaltimer ns at entry, after
@@ -139,6 +142,47 @@ int pg_conv_fwd_stats(const PgConvDesc* d, const void* src1, const void* src2, c
  * runs first and pg_act_bwd_from_output follows in place. */
 int pg_conv_dgrad_act(const PgConvDesc* d, const void* dy, const void* w_packed, void* dx, const void* y, int32_t ldy,
                       int32_t y_dtype, int impl, void* stream);
+
+/* ---- convolution + InstanceNorm2d + activation (+ Dropout) in ONE launch: DownSampleBlock / UpSampleBlock
+ *      (unet.py:19-28, 53-66) forward, and their autograd backward fused into the data-gradient convolution that
+ *      produces dL/d(block output).  The accumulators of the whole layer stay resident in tensor memory (148 SMs x 512
+ *      columns x 128 lanes = 9.7 M fp32 values) across a grid barrier: phase 1 reduces the per-(image, channel) sums from
+ *      the fp32 accumulators, phase 2 normalises / activates and stores the final 16-bit tensor.  The pre-norm tensor is
+ *      never written.  Layers whose output does not fit tensor memory (or with a 1 x 1 map) are refused
+ *      (pg_conv_norm_supported == 0): run pg_conv_fwd_stats + pg_norm_act_fwd / pg_norm_act_bwd instead.
+ *      One such launch may be in flight per device at a time (it occupies every SM until its grid barrier). ---- */
+typedef enum PgFusedKind { PG_FUSED_FWD = 0, PG_FUSED_BWD = 1 } PgFusedKind;
+typedef struct PgFusedNorm {
+  int32_t kind;        /* PgFusedKind */
+  int32_t act;         /* PgAct of the normalised block (none / relu / leakyrelu / tanh) */
+  int32_t n_norm;      /* BWD: output channels [0, n_norm) are gradients of the normalised block's output; channels
+                          [n_norm, N) (the skip half of a concat input) are stored unchanged.  FWD: ignored (= N) */
+  float drop_p;        /* Dropout probability (0 = none); the mask is uniform(mix(*seed, salt), pixel*C + channel) >= p */
+  const uint64_t* seed;
+  uint64_t salt;
+  float* sums;         /* FWD: zeroed [B][N][2], receives (sum, sum of squares) of the conv output per (image, channel).
+                          BWD: the sums the forward call of the block left, [B][n_norm][2] */
+  float* bsums;        /* BWD: zeroed workspace [B][n_norm][2] */
+  uint32_t* sync;      /* zeroed 32-bit counter (grid barrier) */
+  void* xhat;          /* FWD: optional extra output: the normalised pre-activation, same dtype / layout as out with pixel
+                          stride xhat_ld (needed by BWD for relu / tanh / dropout blocks).  BWD: that tensor, or NULL */
+  int32_t xhat_ld;
+  const void* y;       /* BWD, when xhat == NULL: the block's saved output (invertible activation: leakyrelu / none) */
+  int32_t y_ld;
+  int32_t y_dtype;     /* PgDType of y / xhat */
+  const void* dskip;   /* BWD: bf16 gradient arriving over the skip connection, added before the activation backward */
+  int32_t dskip_ld;
+} PgFusedNorm;
+/* 1 if the fused kernel can run this geometry (d as for pg_conv_fwd), else 0 */
+int pg_conv_norm_supported(const PgConvDesc* d, const PgFusedNorm* fn, int32_t has_twin);
+/* out (+ bf16 twin out2, nullable) = dropout(act(instance_norm(conv(src1 | src2)))); d->out_f32 = PG_F16 / PG_BF16,
+ * no bias (the blocks have none), d->act is ignored (fn->act) */
+int pg_conv_norm_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed, void* out, void* out2,
+                     const PgFusedNorm* fn, void* stream);
+/* dx[.., 0:n_norm] = instance_norm_backward(act_backward(dropout_backward(dgrad(dy) [+ dskip]))),
+ * dx[.., n_norm:N] = dgrad(dy);  d = the data-gradient geometry as for pg_conv_fwd, dx bf16 */
+int pg_conv_dgrad_norm_bwd(const PgConvDesc* d, const void* dy, const void* w_packed, void* dx, const PgFusedNorm* fn,
+                           void* stream);
 
 /* weight gradient of PG_CONV geometry `d` (autograd wgrad of unet.py:19,53 / disc.py:19-45):
  *   dw[n*ld_n + c*16 + tap] += sum_{b,oy,ox} g[b,oy,ox,n] * a[b, oy*s-p+kh, ox*s-p+kw, c]
@@ -233,7 +277,11 @@ int pg_pack_weights_multi(const PgPackJob* jobs_dev, int32_t njobs, int32_t tota
 
 /* ---- InstanceNorm2d(affine=False, eps=1e-5) + activation + Dropout(0.2)
  *      (unet.py:20-28,55-66; disc.py:32,42) ---- */
-/* In this group x_f32 / y_f32 are PgDType values (PG_BF16, PG_F32, PG_F16); dy / dx gradients are bf16. */
+/* In this group x_f32 / y_f32 are PgDType values (PG_BF16, PG_F32, PG_F16); dy / dx gradients are bf16.
+ * The backward calls (pg_norm_act_bwd*) accept one of two flags OR-ed into x_f32, telling what the saved tensor x holds
+ * when the forward was the one-launch kernel (pg_conv_norm_fwd), which never writes the pre-norm tensor: */
+#define PG_X_IS_XHAT 0x100    /* x is the normalised pre-activation xhat itself */
+#define PG_X_IS_OUTPUT 0x200  /* x is the block's output y = act(xhat), act = leakyrelu / none, no dropout (xhat is recovered) */
 /* sums[(b*C + c)*2 + {0,1}] += {sum, sum of squares} over the HW pixels of image b (caller zeroes sums) */
 int pg_instnorm_stats(const void* x, int32_t x_f32, int32_t B, int64_t HW, int32_t C, int32_t ld, float* sums,
                       void* stream);
@@ -294,6 +342,17 @@ int pg_gen_out_bwd(const float* p, int32_t ld, const float* t, const float* chsu
  *   channels of the pixel (1..lddz-1) = 0.   (trainer.py:84,101,102 + disc.py:46 sigmoid backward) */
 int pg_bce_const(const float* p, int32_t ld, float label, float gscale, float* losses, int32_t slot, void* dz,
                  int32_t lddz, int64_t npix, void* stream);
+
+/* The standalone loss API (losses.py:5-39 called by user code on arbitrary tensors; the Trainer step uses the fused
+ * calls above).  nn.BCELoss()(p, t) with a general target (losses.py:39): losses[slot] += mean bce(p, t), log clamped
+ * at -100 like aten::binary_cross_entropy; its gradient dp = *gout * (p - t) / max(p (1 - p), 1e-12) / n (gout: DEVICE
+ * scalar, the upstream gradient autograd hands over -- no host read). */
+int pg_bce_mean(const float* p, const float* t, int64_t n, float* losses, int32_t slot, void* stream);
+int pg_bce_mean_bwd(const float* p, const float* t, int64_t n, const float* gout, float* dp, void* stream);
+/* gradient of the per-sample sums (sum t*p, sum p) behind tversky / fc_tversky(batch_mean=False) (losses.py:5-31) wrt the
+ * prediction, NCHW float: dp[b, i] = g_tp[b] * t[b, i] + g_sp[b], i < chw */
+int pg_sample_sums_bwd(const float* t, const float* g_tp, const float* g_sp, float* dp, int32_t B, int64_t chw,
+                       void* stream);
 
 /* ---- optim.Adam (trainer.py:169-172, 90, 107), one launch for a whole flat parameter buffer.
  * hyper (device): [0] = lr.  step (device int32): number of steps taken so far; incremented by the call. ---- */

@@ -25,6 +25,18 @@ class ConvDesc(C.Structure):
 vp, i32, i64, u64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_uint64, C.c_float
 DP = C.POINTER(ConvDesc)
 
+FUSED_FWD, FUSED_BWD = 0, 1
+
+
+class FusedNorm(C.Structure):
+    """PgFusedNorm (include/patchgan_b200.h): arguments of the conv + InstanceNorm one-launch kernels."""
+    _fields_ = [('kind', i32), ('act', i32), ('n_norm', i32), ('drop_p', f32), ('seed', vp), ('salt', u64),
+                ('sums', vp), ('bsums', vp), ('sync', vp), ('xhat', vp), ('xhat_ld', i32), ('y', vp), ('y_ld', i32),
+                ('y_dtype', i32), ('dskip', vp), ('dskip_ld', i32)]
+
+
+FP = C.POINTER(FusedNorm)
+
 _SIGS = {
     'pg_version': ([], C.c_int),
     'pg_tcgen05_available': ([], C.c_int),
@@ -33,9 +45,13 @@ _SIGS = {
     'pg_conv_set_workspace': ([vp, i64], C.c_int),
     'pg_launch_count': ([], C.c_int64),
     'pg_last_conv_impl': ([], C.c_int),
+    'pg_fallback_count': ([], C.c_int64),
     'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_fwd_stats': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_dgrad_act': ([DP, vp, vp, vp, vp, i32, i32, C.c_int, vp], C.c_int),
+    'pg_conv_norm_supported': ([DP, FP, i32], C.c_int),
+    'pg_conv_norm_fwd': ([DP, vp, vp, vp, vp, vp, FP, vp], C.c_int),
+    'pg_conv_dgrad_norm_bwd': ([DP, vp, vp, vp, FP, vp], C.c_int),
     'pg_conv_wgrad': ([DP, vp, vp, i32, vp, i32, i32, i32, C.c_int, vp], C.c_int),
     'pg_conv_wgrad_tapmajor': ([DP, vp, vp, i32, vp, i32, i32, C.c_int, vp], C.c_int),
     'pg_grad_finalize_multi': ([vp, i32, i32, vp], C.c_int),
@@ -63,6 +79,9 @@ _SIGS = {
     'pg_seg_loss_finalize': ([vp, vp, vp, i32, i32, i32, i64, i32, f32, f32, f32, vp], C.c_int),
     'pg_gen_out_bwd': ([vp, i32, vp, vp, vp, vp, i32, i32, vp, i32, i32, i32, i64, i32, i32, f32, vp], C.c_int),
     'pg_bce_const': ([vp, i32, f32, f32, vp, i32, vp, i32, i64, vp], C.c_int),
+    'pg_bce_mean': ([vp, vp, i64, vp, i32, vp], C.c_int),
+    'pg_bce_mean_bwd': ([vp, vp, i64, vp, vp, vp], C.c_int),
+    'pg_sample_sums_bwd': ([vp, vp, vp, vp, i32, i64, vp], C.c_int),
     'pg_adam_step': ([vp, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, vp], C.c_int),
     'pg_adam_step_range': ([vp, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, i32, vp], C.c_int),
     'pg_counter_add': ([vp, u64, vp], C.c_int),

@@ -15,7 +15,17 @@ void set_error(const char* fmt, ...) {
 }
 
 static unsigned long long g_launches = 0;
+static unsigned long long g_simt_fallbacks = 0;
 static thread_local int g_last_impl = 0;
+
+// PG_IMPL_AUTO found no tensor-core plan for a shape and ran the CUDA-core kernel instead: counted (pg_fallback_count,
+// asserted to stay 0 by bench.py and the step tests) and reported once per process -- a 50x cliff must not be silent.
+static void note_simt_fallback(const char* what, const PgConvDesc* d) {
+  if (g_simt_fallbacks++ == 0)
+    fprintf(stderr, "patchgan_b200: %s mode %d stride %d B %d %dx%d -> %dx%d C %d+%d N %d runs on the CUDA-core kernel (no tcgen05 plan "
+            "for this shape / alignment); further fallbacks are only counted (pg_fallback_count)\n", what, d->mode, d->stride,
+            d->B, d->Hin, d->Win, d->Hout, d->Wout, d->C1, d->C2, d->N);
+}
 
 int check_launch(const char* what) {
   ++g_launches;
@@ -37,6 +47,8 @@ bool conv_fwd_tc_supported(const PgConvDesc*, const void*, const void*, const vo
 int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, int, int, cudaStream_t);
 bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int);
 bool tc_device_ok();
+bool conv_res_supported(const PgConvDesc*, const PgFusedNorm*, bool);
+int conv_res_launch(const PgConvDesc*, const void*, const void*, const void*, void*, void*, const PgFusedNorm*, cudaStream_t);
 void set_tc_trace(void*);
 void set_conv_workspace(void*, size_t);
 // conv_skinny.cu
@@ -85,6 +97,7 @@ extern "C" const char* pg_last_error(void) { return g_err; }
 extern "C" int pg_version(void) { return 100; }
 extern "C" int64_t pg_launch_count(void) { return (int64_t)g_launches; }
 extern "C" int pg_last_conv_impl(void) { return g_last_impl; }
+extern "C" int64_t pg_fallback_count(void) { return (int64_t)g_simt_fallbacks; }
 extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
 extern "C" int pg_debug_set_trace(void* buf) { set_tc_trace(buf); return PG_OK; }
 
@@ -177,12 +190,68 @@ static int conv_fwd_any(const PgConvDesc* d, const void* src1, const void* src2,
     return PG_ERR_UNSUPPORTED;
   }
   // InstanceNorm statistics: fused into the tcgen05 epilogue when the tile geometry allows, else a second launch
+  if (!ok) note_simt_fallback("pg_conv_fwd", d);
   const bool fuse = stats != nullptr && ok && conv_fwd_tc_stats_ok(d);
   int e = ok ? conv_fwd_tc(d, src1, src2, w_packed, bias, out, out2, fuse ? stats : nullptr, mul_y, mul_ld, mul_dt, s)
              : conv_fwd_simt(d, src1, src2, w_packed, bias, out, out2, s);
   if (e == PG_OK && stats != nullptr && !fuse)
     e = pg_instnorm_stats(out, d->out_f32, d->B, (int64_t)d->Hout * d->Wout, d->N, d->ldo, stats, stream);
   return e;
+}
+
+static int validate_fused(const PgConvDesc* d, const PgFusedNorm* fn, const char* who) {
+  if (int e = validate(d, who)) return e;
+  PG_REQUIRE(fn != nullptr, "%s: PgFusedNorm is NULL", who);
+  PG_REQUIRE(fn->kind == PG_FUSED_FWD || fn->kind == PG_FUSED_BWD, "%s: bad kind %d", who, fn->kind);
+  PG_REQUIRE(fn->act == PG_ACT_NONE || fn->act == PG_ACT_RELU || fn->act == PG_ACT_LEAKYRELU || fn->act == PG_ACT_TANH,
+             "%s: activation %d cannot follow an InstanceNorm block", who, fn->act);
+  PG_REQUIRE(fn->drop_p >= 0.f && fn->drop_p < 1.f && (fn->drop_p == 0.f || fn->seed != nullptr), "%s: bad dropout arguments", who);
+  PG_REQUIRE(!d->has_bias && d->ldo >= d->N && (d->out_f32 == PG_BF16 || d->out_f32 == PG_F16),
+             "%s: needs a 16-bit output holding all N channels and no bias", who);
+  if (fn->kind == PG_FUSED_BWD) {
+    PG_REQUIRE(fn->n_norm > 0 && fn->n_norm <= d->N && fn->n_norm % 16 == 0, "%s: bad n_norm %d", who, fn->n_norm);
+    PG_REQUIRE(d->out_f32 == PG_BF16 && d->C2 == 0, "%s: gradients are bf16, one source", who);
+    PG_REQUIRE((fn->xhat != nullptr) != (fn->y != nullptr), "%s: exactly one of xhat / y", who);
+    PG_REQUIRE(fn->y == nullptr || ((fn->act == PG_ACT_NONE || fn->act == PG_ACT_LEAKYRELU) && fn->drop_p == 0.f),
+               "%s: recovering xhat from y needs an invertible activation and no dropout (pass xhat)", who);
+    PG_REQUIRE(fn->y_dtype == PG_BF16 || fn->y_dtype == PG_F16, "%s: bad y_dtype", who);
+    const void* t = fn->xhat != nullptr ? fn->xhat : fn->y;
+    const int ld = fn->xhat != nullptr ? fn->xhat_ld : fn->y_ld;
+    PG_REQUIRE((((uintptr_t)t) & 15) == 0 && ld >= fn->n_norm && ld % 8 == 0, "%s: xhat / y must be 16-byte aligned, ld >= n_norm", who);
+    PG_REQUIRE(fn->dskip == nullptr || ((((uintptr_t)fn->dskip) & 15) == 0 && fn->dskip_ld >= fn->n_norm && fn->dskip_ld % 8 == 0),
+               "%s: bad dskip", who);
+  } else {
+    PG_REQUIRE(fn->xhat == nullptr || ((((uintptr_t)fn->xhat) & 15) == 0 && fn->xhat_ld >= d->N && fn->xhat_ld % 8 == 0),
+               "%s: bad xhat output", who);
+  }
+  return PG_OK;
+}
+
+extern "C" int pg_conv_norm_supported(const PgConvDesc* d, const PgFusedNorm* fn, int32_t has_twin) {
+  if (validate_fused(d, fn, "pg_conv_norm_supported") != PG_OK) return 0;
+  return conv_res_supported(d, fn, has_twin != 0) ? 1 : 0;
+}
+
+extern "C" int pg_conv_norm_fwd(const PgConvDesc* d, const void* src1, const void* src2, const void* w_packed, void* out,
+                                void* out2, const PgFusedNorm* fn, void* stream) {
+  if (int e = validate_fused(d, fn, "pg_conv_norm_fwd")) return e;
+  PG_REQUIRE(fn->kind == PG_FUSED_FWD, "pg_conv_norm_fwd: kind must be PG_FUSED_FWD");
+  PG_REQUIRE(src1 && w_packed && out && (d->C2 == 0 || src2) && fn->sums && fn->sync, "pg_conv_norm_fwd: NULL pointer");
+  PG_REQUIRE(((((uintptr_t)src1) | ((uintptr_t)src2) | ((uintptr_t)w_packed) | ((uintptr_t)out) | ((uintptr_t)out2)) & 15) == 0,
+             "pg_conv_norm_fwd: pointers must be 16-byte aligned");
+  g_last_impl = PG_IMPL_TCGEN05;
+  return conv_res_launch(d, src1, src2, w_packed, out, out2, fn, (cudaStream_t)stream);
+}
+
+extern "C" int pg_conv_dgrad_norm_bwd(const PgConvDesc* d, const void* dy, const void* w_packed, void* dx, const PgFusedNorm* fn,
+                                      void* stream) {
+  if (int e = validate_fused(d, fn, "pg_conv_dgrad_norm_bwd")) return e;
+  PG_REQUIRE(fn->kind == PG_FUSED_BWD, "pg_conv_dgrad_norm_bwd: kind must be PG_FUSED_BWD");
+  PG_REQUIRE(dy && w_packed && dx && fn->sums && fn->bsums && fn->sync, "pg_conv_dgrad_norm_bwd: NULL pointer");
+  PG_REQUIRE(((((uintptr_t)dy) | ((uintptr_t)w_packed) | ((uintptr_t)dx)) & 15) == 0,
+             "pg_conv_dgrad_norm_bwd: pointers must be 16-byte aligned");
+  g_last_impl = PG_IMPL_TCGEN05;
+  return conv_res_launch(d, dy, nullptr, w_packed, dx, nullptr, fn, (cudaStream_t)stream);
 }
 
 extern "C" int pg_taps_scatter(int32_t mode, int32_t stride, int32_t pad, int32_t B, int32_t Hq, int32_t Wq, int32_t Hp, int32_t Wp,
@@ -226,6 +295,7 @@ static int conv_wgrad_any(const PgConvDesc* d, const void* a, const void* g, int
     return PG_ERR_UNSUPPORTED;
   }
   if (ok) return conv_wgrad_tc(d, a, g, ldg, dw, ld_n, n_real, c_real, tap_major, Cs, s);
+  note_simt_fallback("pg_conv_wgrad", d);
   return conv_wgrad_simt(d, a, g, ldg, dw, ld_n, n_real, c_real, tap_major, Cs, s);
 }
 

@@ -147,6 +147,11 @@ __device__ __forceinline__ float uniform01(uint64_t seed, uint64_t idx) {
   return (float)(uint32_t)(z >> 40) * (1.0f / 16777216.0f);
 }
 
+// per-layer dropout stream: the device seed counter mixed with the layer's salt
+__device__ __forceinline__ unsigned long long mix_seed(unsigned long long s, unsigned long long salt) {
+  return s ^ (salt * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull);
+}
+
 inline int num_sms() {
   static int n = 0;
   if (n == 0) {

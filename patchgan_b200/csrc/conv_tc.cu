@@ -1842,4 +1842,6 @@ int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, fl
   return check_launch("wgrad_tc_kernel");
 }
 
+#include "conv_res.cuh"
+
 }  // namespace pg

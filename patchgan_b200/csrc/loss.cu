@@ -206,6 +206,37 @@ __global__ void __launch_bounds__(256) bce_const_kernel(const float* __restrict_
   if (threadIdx.x == 0) atomicAdd(losses + slot, s * inv);
 }
 
+// ---- the standalone loss API (losses.py:5-39 called on arbitrary tensors, outside the Trainer step)
+// nn.BCELoss()(p, t) with a general target: losses[slot] += mean bce
+__global__ void __launch_bounds__(256) bce_mean_kernel(const float* __restrict__ p, const float* __restrict__ t, long long n,
+                                                       float* losses, int slot) {
+  __shared__ float sh[32];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    s += bce_elem(p[i], t[i]);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) atomicAdd(losses + slot, s / (float)n);
+}
+// its gradient (aten::binary_cross_entropy_backward): dp = gout * (p - t) / max(p (1 - p), 1e-12) / n; gout: device scalar
+__global__ void __launch_bounds__(256) bce_mean_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t, long long n,
+                                                           const float* __restrict__ gout, float* __restrict__ dp) {
+  const float g = *gout / (float)n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float q = p[i];
+    dp[i] = g * (q - t[i]) / fmaxf(q * (1.f - q), 1e-12f);
+  }
+}
+// gradient of the per-sample sums (tp, sum p) of tversky / fc_tversky(batch_mean=False) wrt the prediction (NCHW float):
+//   dp[b, c, hw] = g_tp[b] * t[b, c, hw] + g_sp[b]
+__global__ void __launch_bounds__(256) sample_sums_bwd_kernel(const float* __restrict__ t, const float* __restrict__ g_tp,
+                                                              const float* __restrict__ g_sp, float* __restrict__ dp,
+                                                              long long chw) {
+  const int b = blockIdx.y;
+  const float a = g_tp[b], c = g_sp[b];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < chw; i += (long long)gridDim.x * blockDim.x)
+    dp[(long long)b * chw + i] = fmaf(a, t[(long long)b * chw + i], c);
+}
+
 static dim3 img_grid(int B, long long HW) {
   long long per = (4LL * num_sms() + B - 1) / B;
   long long nb = (HW + 255) / 256;
@@ -263,4 +294,31 @@ extern "C" int pg_bce_const(const float* p, int32_t ld, float label, float gscal
   bce_const_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(p, ld, label, gscale, losses, slot, (bf16*)dz, lddz,
                                                                   npix);
   return check_launch("bce_const_kernel");
+}
+
+static unsigned flat_blocks(long long n) {
+  long long nb = (n + 255) / 256;
+  const long long cap = 8LL * num_sms();
+  if (nb > cap) nb = cap;
+  return (unsigned)(nb < 1 ? 1 : nb);
+}
+
+extern "C" int pg_bce_mean(const float* p, const float* t, int64_t n, float* losses, int32_t slot, void* stream) {
+  PG_REQUIRE(p && t && losses && n > 0, "pg_bce_mean: bad arguments");
+  bce_mean_kernel<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, t, n, losses, slot);
+  return check_launch("bce_mean_kernel");
+}
+
+extern "C" int pg_bce_mean_bwd(const float* p, const float* t, int64_t n, const float* gout, float* dp, void* stream) {
+  PG_REQUIRE(p && t && gout && dp && n > 0, "pg_bce_mean_bwd: bad arguments");
+  bce_mean_bwd_kernel<<<flat_blocks(n), 256, 0, (cudaStream_t)stream>>>(p, t, n, gout, dp);
+  return check_launch("bce_mean_bwd_kernel");
+}
+
+extern "C" int pg_sample_sums_bwd(const float* t, const float* g_tp, const float* g_sp, float* dp, int32_t B, int64_t chw,
+                                  void* stream) {
+  PG_REQUIRE(t && g_tp && g_sp && dp && B > 0 && chw > 0, "pg_sample_sums_bwd: bad arguments");
+  dim3 grid(flat_blocks(chw), (unsigned)B);
+  sample_sums_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(t, g_tp, g_sp, dp, chw);
+  return check_launch("sample_sums_bwd_kernel");
 }

@@ -9,10 +9,6 @@ namespace pg {
 constexpr float IN_EPS = 1e-5f;
 constexpr int NT = 256;
 
-__device__ __forceinline__ unsigned long long mix_seed(unsigned long long s, unsigned long long salt) {
-  return s ^ (salt * 0xD6E8FEB86659FD93ull + 0x2545F4914F6CDD1Dull);
-}
-
 // is_f32 is a PgDType: PG_BF16 (0), PG_F32 (1) or PG_F16 (2)
 __device__ __forceinline__ void load8(const void* base, int is_f32, long long off, float* f) {
   if (is_f32 == PG_F32) {
@@ -218,12 +214,15 @@ __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f
 
 // ------------------------------------------------------------------ backward
 // dxhat for 8 channels of one pixel, from already loaded x / dy values
+// xk (PG_X_* >> 8): what the saved tensor x holds -- 0: the pre-norm conv output, 1: xhat itself, 2: the block's OUTPUT
+// y = act(xhat) with an invertible activation (LeakyReLU(0.2) / none; the fused forward kernel stores nothing else)
 __device__ __forceinline__ void dxhat8(const float* f, float* g, long long pix, int C, int c0, int act, float drop_p,
-                                       unsigned long long seed, const float* mean, const float* rstd, float* xhat) {
+                                       unsigned long long seed, const float* mean, const float* rstd, float* xhat, int xk) {
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float xh = (f[j] - mean[j]) * rstd[j];
+    const float xh = xk == 0 ? (f[j] - mean[j]) * rstd[j]
+                             : (xk == 2 && act == PG_ACT_LEAKYRELU && f[j] < 0.f ? 5.f * f[j] : f[j]);
     float d = g[j] * act_grad_from_input(act, xh);
     if (drop_p > 0.f) {
       const float u = uniform01(seed, (unsigned long long)(pix * C + c0 + j));
@@ -250,6 +249,8 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_reduce_kernel(const void* x, 
                                                                  float* bsums, long long HW, int C, int ldx, int act,
                                                                  float drop_p, const unsigned long long* seed_ptr,
                                                                  unsigned long long salt, long long ppb) {
+  const int xk = x_f32 >> 8;
+  x_f32 &= 0xff;
   extern __shared__ float sh[];
   const int b = blockIdx.y;
   const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
@@ -282,7 +283,7 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_reduce_kernel(const void* x, 
       for (int u = 0; u < UNB; ++u) {
         if (p0 + u * s.pl >= s.pend) break;
         float xh[8];
-        dxhat8(f[u], g[u], base + p0 + u * s.pl, C, c0, act, drop_p, seed, mean, rstd, xh);
+        dxhat8(f[u], g[u], base + p0 + u * s.pl, C, c0, act, drop_p, seed, mean, rstd, xh, xk);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           a1[j] += g[u][j];
@@ -307,6 +308,8 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
                                                                 int C, int ldx, int act, float drop_p,
                                                                 const unsigned long long* seed_ptr,
                                                                 unsigned long long salt, long long ppb) {
+  const int xk = x_f32 >> 8;
+  x_f32 &= 0xff;
   extern __shared__ float sh[];
   const int b = blockIdx.y;
   const unsigned long long seed = drop_p > 0.f ? mix_seed(*seed_ptr, salt) : 0ull;
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
       const long long pix = base + p0 + u * s.pl;
       if (p0 + u * s.pl >= s.pend) break;
       float xh[8];
-      dxhat8(f[u], g[u], pix, C, c0, act, drop_p, seed, mean, rstd, xh);
+      dxhat8(f[u], g[u], pix, C, c0, act, drop_p, seed, mean, rstd, xh, xk);
 #pragma unroll
       for (int j = 0; j < 8; ++j) g[u][j] = rstd[j] * (g[u][j] - m1[j] - xh[j] * m2[j]);
       store8(dx, 0, pix * lddx + c0, g[u]);
@@ -368,6 +371,8 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_small_kernel(const void* x, i
                                                                 int ld1, const void* dy2, int ld2, void* dx, int lddx,
                                                                 int HW, int C, int ldx, int act, float drop_p,
                                                                 const unsigned long long* seed_ptr, unsigned long long salt) {
+  const int xk = x_f32 >> 8;
+  x_f32 &= 0xff;
   __shared__ float sh_stat[16];            // mean[8], rstd[8]
   __shared__ float sh_part[NT / 32][16];   // per-warp partial sums
   __shared__ float sh_tot[16];
@@ -400,7 +405,7 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_small_kernel(const void* x, i
   for (int u = 0; u < SMALL_PPT; ++u) {
     const int p = threadIdx.x + u * NT;
     if (p < HW) {
-      dxhat8(xh[u], g[u], base + p, C, c0, act, drop_p, seed, mean, rstd, xh[u]);
+      dxhat8(xh[u], g[u], base + p, C, c0, act, drop_p, seed, mean, rstd, xh[u], xk);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         a1[j] += g[u][j];

@@ -69,6 +69,15 @@ def shard_seed(base_seed):
     return base_seed + rank()
 
 
+def mean_over_ranks(value, device):
+    """Mean of a python float over ranks (epoch metrics that drive a learning-rate scheduler)."""
+    if world_size() == 1:
+        return value
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item()) / world_size()
+
+
 def max_over_ranks(value, device):
     """Max of a python float over ranks (used for timing: the job is as slow as its slowest rank)."""
     if world_size() == 1:

@@ -204,6 +204,10 @@ class Config:
     streams = os.environ.get('PATCHGAN_B200_STREAMS', '1') != '0'
     # one-real-channel layers as pointwise tap products (0 = run them as 16x padded 4x4 implicit GEMMs)
     taps = os.environ.get('PATCHGAN_B200_TAPS', '1') != '0'
+    # conv + InstanceNorm + activation as ONE launch with TMEM-resident accumulators (forward), and the block's backward
+    # fused into the data-gradient convolution that feeds it (0 = separate statistics / apply / backward kernels)
+    fused_fwd = os.environ.get('PATCHGAN_B200_FUSED_FWD', '1') != '0'
+    fused_bwd = os.environ.get('PATCHGAN_B200_FUSED_BWD', '1') != '0'
 
 
 def conv_flops(desc):
@@ -257,6 +261,104 @@ def run_conv_dgrad_act(desc, dy, w, out, y):
         L.PROFILER.note(conv_flops(desc), desc_tag(desc))
     L.call('pg_conv_dgrad_act', ctypes.byref(desc), dy.ptr, w if isinstance(w, int) else w.data_ptr(), out.ptr, y.ptr, y.ld,
            y.dt, Config.impl, _stream())
+
+
+X_IS_XHAT, X_IS_OUTPUT = 0x100, 0x200      # flags of pg_norm_act_bwd's x dtype argument (include/patchgan_b200.h)
+INVERTIBLE = ('leakyrelu', 'none', None)    # activations whose input is recovered from the saved output
+
+
+def fused_conv_norm(desc, src1, src2, w, out, act, drop_p, seed, salt, want_xhat):
+    """conv -> InstanceNorm -> act -> dropout in one launch (pg_conv_norm_fwd).  Returns (sums, xhat Act or None), or None
+    if the geometry does not fit tensor memory (the caller then runs the separate kernels)."""
+    if not (taps_enabled() and Config.fused_fwd):
+        return None
+    fn = L.FusedNorm()
+    fn.kind, fn.act, fn.drop_p, fn.salt = L.FUSED_FWD, act, float(drop_p), salt
+    fn.seed = seed.data_ptr() if drop_p > 0 else None
+    if not L.lib().pg_conv_norm_supported(ctypes.byref(desc), ctypes.byref(fn), int(out.tw is not None)):
+        return None
+    dev = out.t.device
+    sums = zeros((desc.B, desc.N, 2), dev)
+    sync = zeros(16, dev)            # (held until the call is issued: a dropped temporary's block would be handed out again)
+    fn.sums, fn.sync = sums.data_ptr(), sync.data_ptr()
+    xh = None
+    if want_xhat:
+        xh = new_act(out.B, out.H, out.W, out.C, dev, dt=out.dt)
+        fn.xhat, fn.xhat_ld = xh.ptr, xh.ld
+    if L.PROFILER is not None:
+        L.PROFILER.note(conv_flops(desc), desc_tag(desc))
+    L.call('pg_conv_norm_fwd', ctypes.byref(desc), src1.ptr, src2.ptr if src2 is not None else None,
+           w if isinstance(w, int) else w.data_ptr(), out.ptr, out.twptr, ctypes.byref(fn), _stream())
+    return sums, xh
+
+
+class Block:
+    """What the backward of one conv -> [norm] -> act -> [dropout] block needs from its forward."""
+    __slots__ = ('spec', 'raw', 'sums', 'out', 'dp', 'xh', 'salt')
+
+    def __init__(self, spec, raw, sums, out, dp, xh, salt):
+        self.spec, self.raw, self.sums, self.out, self.dp, self.xh, self.salt = spec, raw, sums, out, dp, xh, salt
+
+
+def _shift_desc(desc, n0, n):
+    """desc restricted to output channels [n0, n0 + n) (the pointers are offset by the caller)."""
+    d = L.ConvDesc()
+    ctypes.memmove(ctypes.byref(d), ctypes.byref(desc), ctypes.sizeof(d))
+    d.N = n
+    d.n_valid = n
+    return d
+
+
+def dgrad_block_bwd(desc, dy, w, wrow_bytes, din, n_norm, blk, dskip, seed):
+    """din = data-gradient of a layer (geometry desc: dy -> din, all desc.N channels); its first n_norm channels are the
+    gradient wrt the output of block `blk` and are taken through that block's backward (dropout, activation, InstanceNorm;
+    `dskip` = gradient arriving over the skip connection, added first).  Returns d(conv output of blk) as a bf16 Act.
+    One launch when the fused kernel applies (pg_conv_dgrad_norm_bwd), else data-gradient + pg_norm_act_bwd."""
+    s = blk.spec
+    act = L.ACT[s.act]
+    wp = w if isinstance(w, int) else w.data_ptr()
+    can = blk.xh is not None or (s.act in INVERTIBLE and blk.dp == 0)
+    if s.norm and can and taps_enabled() and Config.fused_bwd:
+        dev = din.t.device
+        fn = L.FusedNorm()
+        fn.kind, fn.act, fn.n_norm, fn.drop_p, fn.salt = L.FUSED_BWD, act, n_norm, float(blk.dp), blk.salt
+        fn.seed = seed.data_ptr() if blk.dp > 0 else None
+        fn.y_dtype = blk.out.dt
+        if blk.xh is not None:
+            fn.xhat, fn.xhat_ld = blk.xh.ptr, blk.xh.ld
+        else:
+            fn.y, fn.y_ld = blk.out.ptr, blk.out.ld
+        if dskip is not None:
+            fn.dskip, fn.dskip_ld = dskip.ptr, dskip.ld
+        fn.sums = blk.sums.data_ptr()
+        plans = [(desc, None)]
+        if n_norm < desc.N:       # the normalised half alone may fit tensor memory when the whole concat gradient does not
+            plans.append((_shift_desc(desc, 0, n_norm), _shift_desc(desc, n_norm, desc.N - n_norm)))
+        for d1, d2 in plans:
+            if not L.lib().pg_conv_norm_supported(ctypes.byref(d1), ctypes.byref(fn), 0):
+                continue
+            # one zeroed workspace: [bsums | barrier counter], alive until the call is issued
+            ws = zeros(desc.B * n_norm * 2 + 16, dev)
+            fn.bsums = ws.data_ptr()
+            fn.sync = ws.data_ptr() + desc.B * n_norm * 2 * 4
+            if L.PROFILER is not None:
+                L.PROFILER.note(conv_flops(d1), desc_tag(d1))
+            L.call('pg_conv_dgrad_norm_bwd', ctypes.byref(d1), dy.ptr, wp, din.ptr, ctypes.byref(fn), _stream())
+            if d2 is not None:
+                rest = din.slice(n_norm, desc.N - n_norm)
+                run_conv(d2, dy, None, wp + n_norm * wrow_bytes, None, rest)
+            return din.slice(0, n_norm)
+    run_conv(desc, dy, None, wp, None, din)
+    d_prev = din.slice(0, n_norm)
+    if not s.norm:
+        return act_bwd_out(blk.out, d_prev, act)
+    if blk.raw is not None:
+        x, kind = blk.raw, 0
+    elif blk.xh is not None:
+        x, kind = blk.xh, X_IS_XHAT
+    else:
+        x, kind = blk.out, X_IS_OUTPUT
+    return norm_bwd(x, blk.sums, d_prev, dskip, act, blk.dp, seed, blk.salt, kind)
 
 
 def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream=None):
@@ -632,8 +734,9 @@ def instnorm_stats(x, sums=None, b0=0):
     return sums
 
 
-def norm_bwd(x, sums, dy1, dy2, act, drop_p, seed, salt):
-    """Backward through dropout/act/InstanceNorm: returns d(raw) as a new bf16 Act."""
+def norm_bwd(x, sums, dy1, dy2, act, drop_p, seed, salt, xkind=0):
+    """Backward through dropout/act/InstanceNorm: returns d(raw) as a new bf16 Act.
+    xkind: 0 = x is the pre-norm conv output, X_IS_XHAT = x is the saved xhat, X_IS_OUTPUT = x is the block's output."""
     dev = x.t.device
     HW = x.H * x.W
     dx = new_act(x.B, x.H, x.W, x.C, dev)
@@ -642,12 +745,12 @@ def norm_bwd(x, sums, dy1, dy2, act, drop_p, seed, salt):
     p2, l2 = (dy2.ptr, dy2.ld) if dy2 is not None else (None, 0)
     st = _stream()
     if taps_enabled():      # one call: small maps are a single launch
-        L.call('pg_norm_act_bwd', x.ptr, x.dt, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), dx.ptr, dx.ld,
-               x.B, HW, x.C, x.ld, act, drop_p, sp, salt, st)
+        L.call('pg_norm_act_bwd', x.ptr, x.dt | xkind, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), dx.ptr,
+               dx.ld, x.B, HW, x.C, x.ld, act, drop_p, sp, salt, st)
         return dx
-    L.call('pg_norm_act_bwd_reduce', x.ptr, x.dt, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), x.B,
+    L.call('pg_norm_act_bwd_reduce', x.ptr, x.dt | xkind, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), x.B,
            HW, x.C, x.ld, act, drop_p, sp, salt, st)
-    L.call('pg_norm_act_bwd_apply', x.ptr, x.dt, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(),
+    L.call('pg_norm_act_bwd_apply', x.ptr, x.dt | xkind, sums.data_ptr(), dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(),
            dx.ptr, dx.ld, x.B, HW, x.C, x.ld, act, drop_p, sp, salt, st)
     return dx
 
@@ -702,30 +805,46 @@ class GeneratorEngine(NetEngine):
         return a
 
     def forward(self, xin, training, save=True):
-        """xin: Act (B,H,W,in_cp) bf16.  Returns (p: f32 Act (B,H,W,out_cp), ctx)."""
+        """xin: Act (B,H,W,in_cp) bf16.  Returns (p: f32 Act (B,H,W,out_cp), ctx).
+        ctx['enc'][i] = (input, pre-norm output or None, sums, output, dropout p, xhat or None);
+        ctx['dec'][i] = (src1, src2, pre-norm output or None, sums or None, output, dropout p, xhat or None)."""
         self.ensure_packed()
         dev = xin.t.device
         B = xin.B
         ctx = {'enc': [], 'dec': [], 'training': training}
         h = xin
         enc_outs = []
+
+        def norm_block(desc, src1, src2, w, s, Ho, Wo, salt):
+            """conv (desc) -> InstanceNorm -> act -> dropout: one launch when the layer fits tensor memory, else three."""
+            out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt, twin=save)
+            dp = DROP_P if (training and s.dropout) else 0.0
+            desc.ldo, desc.out_f32, desc.n_valid = out.ld, out.dt, s.cout
+            fused = fused_conv_norm(desc, src1, src2, w, out, L.ACT[s.act], dp, self.seed, salt,
+                                    save and (dp > 0 or s.act not in INVERTIBLE))
+            if fused is not None:
+                return None, fused[0], out, dp, fused[1]
+            raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
+            sums = zeros((B, s.np, 2), dev)
+            desc.ldo, desc.out_f32, desc.n_valid = raw.ld, F32, s.np
+            run_conv(desc, src1, src2, w, None, raw, sums)
+            norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, salt)
+            return raw, sums, out, dp, None
+
         for i, s in enumerate(self.enc):
             Ho, Wo = (h.H, h.W) if h.im2col else (h.H // 2, h.W // 2)
             if Ho * Wo <= 1 and training:
                 # aten::instance_norm raises for a single spatial element in training mode
                 raise ValueError('Expected more than 1 spatial element when training (input too small for 7 '
                                  'stride-2 stages)')
-            raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
-            sums = zeros((B, s.np, 2), dev)
             if h.im2col:
-                first_conv(h, self.packed[i].wfirst, None, 0, raw, s.cout, sums)
+                w = self.packed[i].wfirst
+                desc = conv_desc(L.PG_CONV1X1, 1, 0, B, h.H, h.W, h.H, h.W, h.C, 0, h.ld, 0, w.shape[0], s.np, in_dt=h.dt)
             else:
-                run_conv(conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, raw.ld, out_dt=F32,
-                                   in_dt=h.dt), h, None, self.packed[i].fwd, None, raw, sums)
-            out = new_act(B, Ho, Wo, s.np, dev, dt=h.dt, twin=save)
-            dp = DROP_P if (training and s.dropout) else 0.0
-            norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, i)
-            ctx['enc'].append((h, raw, sums, out, dp) if save else None)
+                w = self.packed[i].fwd
+                desc = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, Ho, Wo, h.C, 0, h.ld, 0, s.np, s.np, in_dt=h.dt)
+            raw, sums, out, dp, xh = norm_block(desc, h, None, w, s, Ho, Wo, i)
+            ctx['enc'].append((h, raw, sums, out, dp, xh) if save else None)
             enc_outs.append(out)
             h = out
         for i, s in enumerate(self.dec):
@@ -735,19 +854,15 @@ class GeneratorEngine(NetEngine):
             pw = self.packed[7 + i]
             c2, ld2 = (src2.C, src2.ld) if src2 is not None else (0, 0)
             if s.norm:
-                raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
-                sums = zeros((B, s.np, 2), dev)
-                run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, raw.ld,
-                                   out_dt=F32, in_dt=src1.dt), src1, src2, pw.fwd, None, raw, sums)
-                out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt, twin=save)
-                dp = DROP_P if (training and s.dropout) else 0.0
-                norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, 16 + i)
-                ctx['dec'].append((src1, src2, raw, sums, out, dp) if save else None)
+                desc = conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, s.np,
+                                 in_dt=src1.dt)
+                raw, sums, out, dp, xh = norm_block(desc, src1, src2, pw.fwd, s, Ho, Wo, 16 + i)
+                ctx['dec'].append((src1, src2, raw, sums, out, dp, xh) if save else None)
             elif i < 6:
                 out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt, twin=save)
                 run_conv(conv_desc(L.PG_CONVT, 2, 1, B, src1.H, src1.W, Ho, Wo, src1.C, c2, src1.ld, ld2, s.np, out.ld,
                                    act=L.ACT[s.act], out_dt=out.dt, in_dt=src1.dt), src1, src2, pw.fwd, None, out)
-                ctx['dec'].append((src1, src2, None, None, out, 0.0) if save else None)
+                ctx['dec'].append((src1, src2, None, None, out, 0.0, None) if save else None)
             else:
                 out = new_act(B, Ho, Wo, (s.cout + 3) // 4 * 4, dev, dt=F32)   # trimmed stride: real channels only
                 fused = 0 if s.act == 'softmax' else L.ACT[s.act]
@@ -759,7 +874,7 @@ class GeneratorEngine(NetEngine):
                              pw.fwd, None, out)
                 if s.act == 'softmax':
                     L.call('pg_softmax_fwd', out.ptr, out.ptr, B * Ho * Wo, s.cout, out.ld, _stream())
-                ctx['dec'].append((src1, src2, None, None, out, 0.0) if save else None)
+                ctx['dec'].append((src1, src2, None, None, out, 0.0, None) if save else None)
             h = out
         return h, ctx
 
@@ -768,76 +883,75 @@ class GeneratorEngine(NetEngine):
         grads: dict name -> zero-initialised float32 tensor in the reference layout (accumulated into).
         wstream: side stream for the weight-gradient launches (off the data-gradient critical path).
         early = (i, fn): fn() is called once everything that touches the layers other than encoder 0 .. i-1 has been
-        issued (their weight-gradients on wstream, the last reads of their operand copies on the current stream)."""
+        issued (their weight-gradients on wstream, the last reads of their operand copies on the current stream).
+
+        Every data-gradient convolution also runs the backward of the block that produced its input (activation, dropout,
+        InstanceNorm; engine.dgrad_block_bwd), so the chain is one launch per layer."""
         dev = d_raw.t.device
         B = d_raw.B
         dskip = [None] * 7
-        d_enc6 = None
+
+        def block_of_dec(j):
+            _, _, raw, sums, out, dp, xh = ctx['dec'][j]
+            return Block(self.dec[j], raw, sums, out, dp, xh, 16 + j)
+
+        def block_of_enc(j):
+            _, raw, sums, out, dp, xh = ctx['enc'][j]
+            return Block(self.enc[j], raw, sums, out, dp, xh, j)
+
         self.begin_backward()
         for i in range(6, -1, -1):
             s = self.dec[i]
-            src1, src2, raw, sums, out, dp = ctx['dec'][i]
+            src1, src2 = ctx['dec'][i][0], ctx['dec'][i][1]
             pw = self.packed[7 + i]
             g = grads[s.wname]
+            prod = block_of_dec(i - 1) if i >= 1 else block_of_enc(6)
+            din = new_act(B, src1.H, src1.W, s.cinp, dev)
             if i == 6 and taps_enabled() and pw.taps_ok:
-                # one output channel: tap products (gather dY once, then two pointwise GEMMs)
+                # one output channel: tap products (gather dY once, then pointwise GEMMs)
                 G6 = taps_gather(L.PG_CONVT, 2, 1, d_raw, 0, B, src1.H, src1.W)
                 taps_wgrad(G6, src1.b16, g.data_ptr(), s.c1, wstream)
                 if src2 is not None:
                     taps_wgrad(G6, src2.b16, g.data_ptr() + s.c1 * 16 * 4, s.c2, wstream)
-                din = new_act(B, src1.H, src1.W, s.cinp, dev)
-                taps_dgrad(G6, pw.w16, din)
-                d_prev = din.slice(0, s.c1p)
-                dskip[0] = din.slice(s.c1p, s.c2p)
-                ps = self.dec[i - 1]
-                _, _, praw, psums, pout, pdp = ctx['dec'][i - 1]
-                if ps.norm:
-                    d_raw = norm_bwd(praw, psums, d_prev, None, L.ACT[ps.act], pdp, self.seed, 16 + i - 1)
-                else:
-                    d_raw = act_bwd_out(pout, d_prev, L.ACT[ps.act])
-                continue
-            # weight gradient: dW[ci][co][tap] = sum x[ci] * dY[co] -- PG_CONV geometry with A = dY, G = layer input
-            wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C, src1.C,
-                           out_dt=BF16, in_dt=BF16)
-            self.wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.c1, s.cout, wstream)
-            if src2 is not None:
-                wd2 = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src2.H, src2.W, d_raw.C, 0, d_raw.ld, 0, src2.C,
-                                src2.C, out_dt=BF16, in_dt=BF16)
-                self.wgrad(wd2, d_raw, src2.b16, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout, wstream)
-            # data gradient: stride-2 conv of dY with W'[ci][tap][co]
-            din = new_act(B, src1.H, src1.W, s.cinp, dev)
-            run_conv(conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
-                               din.ld, c_valid=s.cout), d_raw, None, pw.bwd, None, din)
-            if i >= 1:
-                d_prev = din.slice(0, s.c1p)
-                dskip[6 - i] = din.slice(s.c1p, s.c2p)
-                ps = self.dec[i - 1]
-                _, _, praw, psums, pout, pdp = ctx['dec'][i - 1]
-                if ps.norm:
-                    d_raw = norm_bwd(praw, psums, d_prev, None, L.ACT[ps.act], pdp, self.seed, 16 + i - 1)
-                else:
-                    d_raw = act_bwd_out(pout, d_prev, L.ACT[ps.act])
+                dd = conv_desc(L.PG_CONV1X1, 1, 0, B, G6.H, G6.W, G6.H, G6.W, 16, 0, 16, 0, s.cinp, din.ld)
+                d_raw = dgrad_block_bwd(dd, G6, pw.w16, 16 * 2, din, s.c1p, prod, None, self.seed)
             else:
-                d_enc6 = din
-        dy1 = d_enc6
+                # weight gradient: dW[ci][co][tap] = sum x[ci] * dY[co] -- PG_CONV geometry with A = dY, G = layer input
+                wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C,
+                               src1.C, out_dt=BF16, in_dt=BF16)
+                self.wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.c1, s.cout, wstream)
+                if src2 is not None:
+                    wd2 = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src2.H, src2.W, d_raw.C, 0, d_raw.ld, 0, src2.C,
+                                    src2.C, out_dt=BF16, in_dt=BF16)
+                    self.wgrad(wd2, d_raw, src2.b16, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout,
+                               wstream)
+                # data gradient: stride-2 conv of dY with W'[ci][tap][co]
+                dd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
+                               din.ld, c_valid=s.cout)
+                d_raw = dgrad_block_bwd(dd, d_raw, pw.bwd, 16 * d_raw.C * 2, din, s.c1p, prod, None, self.seed)
+            if i >= 1:
+                dskip[6 - i] = din.slice(s.c1p, s.c2p)
+        # d_raw is now the gradient wrt encoder 6's convolution output
         dx = None
         for i in range(6, -1, -1):
             s = self.enc[i]
-            h, raw, sums, out, dp = ctx['enc'][i]
-            d_raw = norm_bwd(raw, sums, dy1, dskip[i] if i < 6 else None, L.ACT[s.act], dp, self.seed, i)
+            h, out = ctx['enc'][i][0], ctx['enc'][i][3]
             if h.im2col:
                 first_wgrad(h, d_raw, grads[s.wname].data_ptr(), s.cout, wstream)
             else:
-                wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, raw.H, raw.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
+                wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, out.H, out.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
                                in_dt=BF16)
                 self.wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
             if i > 0 or need_dx:
                 Hi, Wi = (2 * h.H, 2 * h.W) if h.im2col else (h.H, h.W)
                 din = new_act(B, Hi, Wi, s.cinp, dev)
-                run_conv(conv_desc(L.PG_CONVT, 2, 1, B, raw.H, raw.W, Hi, Wi, d_raw.C, 0, d_raw.ld, 0, s.cinp, din.ld),
-                         d_raw, None, self.packed[i].bwd, None, din)
-                dy1 = din
-                dx = din
+                dd = conv_desc(L.PG_CONVT, 2, 1, B, out.H, out.W, Hi, Wi, d_raw.C, 0, d_raw.ld, 0, s.cinp, din.ld)
+                if i > 0:
+                    d_raw = dgrad_block_bwd(dd, d_raw, self.packed[i].bwd, 16 * d_raw.C * 2, din, s.cinp, block_of_enc(i - 1),
+                                            dskip[i - 1], self.seed)
+                else:
+                    run_conv(dd, d_raw, None, self.packed[i].bwd, None, din)
+                    dx = din
             if early is not None and i == early[0]:
                 early[1]()
         if wstream is None:

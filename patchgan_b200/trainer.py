@@ -12,7 +12,8 @@ three autograd graphs:
     and then zeroes the discriminator weight-gradients there (trainer.py:89,94);
   * the six ``.item()`` syncs (trainer.py:110-111) become one 4-float device->host copy;
   * with ``torch.distributed`` initialised, each rank steps its own shard and the flat gradient buffers are
-    all-reduced over NCCL (generator all-reduce overlapped with the discriminator backward).
+    sum-all-reduced over NCCL (1/world folded into the Adam kernel); ``make_optimizers`` broadcasts rank 0's weights so
+    the replicas start (and stay) identical.  See ``dp.py`` for how the two all-reduces are scheduled.
 """
 import contextlib
 import glob
@@ -103,11 +104,31 @@ class Trainer:
     # one G+D step
     # ------------------------------------------------------------------------------------------
     def make_optimizers(self, gen_lr=1e-3, dsc_lr=1e-3):
-        """Adam for both nets exactly as trainer.py:169-172 (lr, betas=(0.9, 0.999))."""
+        """Adam for both nets exactly as trainer.py:169-172 (lr, betas=(0.9, 0.999)).
+        A captured step bakes in the addresses of the optimizers' flat parameter / gradient / moment buffers, so every
+        graph captured with the previous optimizers is dropped here (new FusedAdam = new flat buffers, the old ones are
+        freed).  Data-parallel: every rank adopts rank 0's weights first -- the reference has no notion of ranks, and
+        averaged gradients applied to different initialisations would let the replicas drift apart."""
+        self._graphs.clear()
+        if dp.world_size() > 1:
+            dp.broadcast_parameters(self.generator)
+            dp.broadcast_parameters(self.discriminator)
         self.gen_optimizer = FusedAdam(self.generator.parameters(), lr=gen_lr, betas=(0.9, 0.999),
                                        on_step=self.generator._engine().mark_dirty)
         self.disc_optimizer = FusedAdam(self.discriminator.parameters(), lr=dsc_lr, betas=(0.9, 0.999),
                                         on_step=self.discriminator._engine().mark_dirty)
+
+    def _graph_signature(self, train):
+        """Addresses a captured step depends on beyond its key: the flat optimizer buffers and the parameter storages.
+        If anything moved (a second make_optimizers, module.to(), load of new tensors that re-homed the parameters) the
+        graph must not be replayed -- it would update freed memory and leave the live weights untouched."""
+        sig = [p.data_ptr() for p in self.generator.parameters()] + [p.data_ptr() for p in self.discriminator.parameters()]
+        if train:
+            for opt in (self.gen_optimizer, self.disc_optimizer):
+                f = opt.flat()
+                sig += [id(opt), f['p'].data_ptr(), f['g'].data_ptr(), f['m'].data_ptr(), f['v'].data_ptr(),
+                        f['hyper'].data_ptr(), f['step'].data_ptr()]
+        return tuple(sig)
 
     def _to_device(self, a):
         if not isinstance(a, torch.Tensor):
@@ -360,6 +381,8 @@ class Trainer:
         split = dp.world_size() > 1
         key = self._graph_key(x, y, train)
         ent = self._graphs.get(key)
+        if ent is not None and ent['graph'] is not None and ent['sig'] != self._graph_signature(train):
+            ent = None                      # buffers moved since the capture: recapture (eager steps meanwhile)
         if ent is None:
             ent = self._graphs[key] = dict(seen=0, graph=None)
         if ent['graph'] is None:
@@ -381,6 +404,7 @@ class Trainer:
             with torch.cuda.graph(g, capture_error_mode=mode):
                 ent['losses'] = self.step_device(ent['x'], ent['y'], train, phase='grads' if split else 'all')
             ent['graph'] = g
+            ent['sig'] = self._graph_signature(train)
             if split and train:
                 g2 = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g2, capture_error_mode=mode):
@@ -578,8 +602,9 @@ class Trainer:
                         gen_scheduler.step()
                         dsc_scheduler.step()
                 else:
-                    gen_scheduler.step(loss_mean['gen'])
-                    dsc_scheduler.step(loss_mean['disc'])
+                    # (data-parallel: every rank must see the same metric, or the learning rates diverge)
+                    gen_scheduler.step(dp.mean_over_ranks(loss_mean['gen'], self.device))
+                    dsc_scheduler.step(dp.mean_over_ranks(loss_mean['disc'], self.device))
 
             if epoch % save_freq == 0:
                 self.save(epoch)

@@ -13,6 +13,21 @@ CASES = {
 }
 NS = 256
 
+# The BASELINE.json architectures at (or near) their benchmarked sizes -- goldens from the live reference only (the numpy
+# oracle would take minutes at these sizes; it is pinned by the small cases above):
+#   name: (G kwargs, D kwargs, loss_type, B, S, steps)
+BIG_CASES = {
+    # cfg 1 / 3: UNet(3 -> 1, nf=32) + PatchGAN(ndf=64, L=3) at the benchmarked batch 16 (D runs at 2B = 32)
+    'cfg3_b16': (dict(input_nc=3, output_nc=1, nf=32, activation='leakyrelu', final_act='sigmoid'),
+                 dict(input_nc=4, ndf=64, n_layers=3, norm=False), 'tversky', 16, 256, 2),
+    # cfg 4: train_coco.yaml-shaped (3 -> 7, ReLU, ndf=16, L=5, weighted BCE); dropout off (RNG streams cannot match)
+    'cfg4_b4': (dict(input_nc=3, output_nc=7, nf=32, activation='relu', final_act='sigmoid'),
+                dict(input_nc=10, ndf=16, n_layers=5, norm=False), 'weighted_bce', 4, 256, 2),
+    # cfg 5: wide generator nf=64 + 4-layer PatchGAN at 1024 x 1024, one image
+    'cfg5_b1': (dict(input_nc=3, output_nc=1, nf=64, activation='leakyrelu', final_act='sigmoid'),
+                dict(input_nc=4, ndf=64, n_layers=4, norm=False), 'tversky', 1, 1024, 1),
+}
+
 
 def summarize(t):
     a = np.asarray(t, dtype=np.float64).ravel()

@@ -33,10 +33,10 @@ from oracle import patchgan_oracle as orc  # noqa: E402
 
 ref_trainer.device = 'cpu'
 
-from tests.golden.cases import CASES, NS, rect_batch, summarize  # noqa: E402,F401
+from tests.golden.cases import BIG_CASES, CASES, NS, rect_batch, summarize  # noqa: E402,F401
 
 
-def run_case(name, gk, dk, loss_type, B, steps):
+def run_case(name, gk, dk, loss_type, B, steps, S=256):
     og = orc.UNet(**gk, seed=11)
     od = orc.Discriminator(**dk, seed=12)
     G = patchgan.UNet(**gk)
@@ -67,7 +67,7 @@ def run_case(name, gk, dk, loss_type, B, steps):
     for li, j in enumerate(ends):
         hooks.append(D.model[j].register_forward_hook(grab(f'd{li}')))
     for step in range(steps):
-        x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=1234 + step)
+        x, y = orc.synthetic_batch(B, gk['output_nc'], S, seed=1234 + step)
         losses = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=True)
         for k, v in losses.items():
             out[f's{step}/loss/{k}'] = np.float64(v)
@@ -85,7 +85,7 @@ def run_case(name, gk, dk, loss_type, B, steps):
     # eval-mode forward / train=False batch (trainer.py:239-259)
     G.eval()
     D.eval()
-    x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=99)
+    x, y = orc.synthetic_batch(B, gk['output_nc'], S, seed=99)
     losses = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=False)
     for k, v in losses.items():
         out[f'eval/loss/{k}'] = np.float64(v)
@@ -142,6 +142,17 @@ def losses_case():
         mae=L.MAE_loss(tt, tp).item(),
         bce=L.bce_loss(tp, tt).item(),
     )
+    # gradients wrt the prediction of every function / mode (autograd of the reference); per-sample results are
+    # reduced with the weights (1, 2, 3) so that each sample's gradient is told apart
+    wv = torch.tensor([1., 2., 3.])
+    fns = dict(tversky=lambda q: L.tversky(tt, q, 0.7), tversky_nb=lambda q: (L.tversky(tt, q, 0.7, batch_mean=False) * wv).sum(),
+               fc=lambda q: L.fc_tversky(tt, q, 0.75, 0.75),
+               fc_nb=lambda q: (L.fc_tversky(tt, q, 0.75, 0.75, batch_mean=False) * wv).sum(),
+               mae=lambda q: L.MAE_loss(tt, q), bce=lambda q: L.bce_loss(q, tt))
+    for k, f in fns.items():
+        q = tp.clone().requires_grad_(True)
+        f(q).backward()
+        out['grad_' + k] = q.grad.numpy().copy()
     np.savez_compressed(os.path.join(HERE, 'losses.npz'), **out)
 
 
@@ -165,6 +176,9 @@ if __name__ == '__main__':
     for name, (gk, dk, lt, B, steps) in CASES.items():
         if not only or name in only:
             run_case(name, gk, dk, lt, B, steps)
+    for name, (gk, dk, lt, B, S, steps) in BIG_CASES.items():
+        if not only or name in only:
+            run_case(name, gk, dk, lt, B, steps, S)
     if not only or 'rect' in only:
         rect_case()
     if not only or 'losses' in only:

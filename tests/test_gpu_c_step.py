@@ -248,11 +248,18 @@ def test_submit_lookahead_matches_batch(tmp_path):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.xfail(strict=False, reason="added after this round's GPU minutes were used up: not yet run on a GPU "
-                                        "(the oracle side of the same fixture is pinned in test_oracle_golden.py)")
 def test_rectangular_step_matches_reference_golden(tmp_path):
     """H != W: one training step on a 128 x 256 batch (bottleneck 1 x 2) through a 5-layer discriminator against the
-    live reference's golden (tests/golden/step_rect.npz): losses to 1e-3, gradients norm-wise on the sampled entries."""
+    live reference's golden (tests/golden/step_rect.npz): losses to 1e-3, gradients norm-wise.
+
+    encoder.6 sits behind an InstanceNorm over TWO elements: xhat = +-1 whatever the inputs are, its gradient is
+    ~eps/var times everyone else's (norm 7.6e-3 against 0.1 .. 37 for the other layers) and is made of rounding: the numpy
+    oracle run with 16-bit storage rounding is 0.56 away from the fp32 reference there (0.04-0.06 on the other layers; first
+    measured on a B200 in round 2: CUDA path 0.59).  So (a) every layer is compared with the oracle under the SAME storage
+    rounding at the usual gated-activation bound, and (b) against the fp32 golden each tensor's error is measured
+    relative to max(its own norm, 10 % of the median generator-layer norm).  The ABSOLUTE deviation on the sampled entries
+    is the same for every generator layer (4e-3 .. 6e-3), encoder.6's included -- only its norm is 15-25x smaller -- so
+    with the floor the degenerate layer cannot fail on noise while a wrong layer (error of the order of its norm) does."""
     from tests.golden.cases import rect_batch, summarize
     gold = np.load(os.path.join(GOLD, 'step_rect.npz'))
     gk = dict(input_nc=3, output_nc=1, nf=8, activation='leakyrelu', final_act='sigmoid')
@@ -266,11 +273,35 @@ def test_rectangular_step_matches_reference_golden(tmp_path):
     tr.loss_type = 'tversky'
     tr.make_optimizers(1e-3, 1e-3)
     x, y = rect_batch()
+    oq = orc.Trainer(orc.UNet(**gk, seed=21), orc.Discriminator(**dk, seed=22))
+    oq.loss_type = 'tversky'
+    orc.set_quant(**quant_kwargs())
+    try:
+        oq.batch(x, y, train=True)
+    finally:
+        orc.set_quant()
     got = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=True)
     for k in got:
         ref = float(gold[f'loss/{k}'])
         assert abs(got[k] - ref) <= 1e-3 * abs(ref), (k, got[k], ref)
-    gerr = {k: relerr(summarize(p.grad.cpu().numpy()), gold[f'ggrad/{k}']) for k, p in G.named_parameters()}
-    gerr.update({'D.' + k: relerr(summarize(p.grad.cpu().numpy()), gold[f'dgrad/{k}']) for k, p in D.named_parameters()})
-    print('rect grad err vs reference golden (sampled)', short(gerr))
+    grads = {k: p.grad.cpu().numpy() for k, p in G.named_parameters()}
+    grads.update({'D.' + k: p.grad.cpu().numpy() for k, p in D.named_parameters()})
+    oqg = dict(oq.last['gen_grads'])
+    oqg.update({'D.' + k: v for k, v in oq.last['disc_grads'].items()})
+    # (a) same storage rounding, every layer but the degenerate one -- there BOTH sides are rounding noise (xhat = +-1 to
+    #     within eps / var, far below a 16-bit ulp), so all that can be asked is that it is as small as the reference's
+    gnorm = {k: float(np.linalg.norm(v)) for k, v in oqg.items()}
+    med = float(np.median([v for k, v in gnorm.items() if not k.startswith('D.')]))
+    degenerate = 'encoder.6.model.DownConv6.weight'
+    qerr = {k: float(np.linalg.norm(grads[k] - oqg[k]) / gnorm[k]) for k in grads if k != degenerate}
+    print('rect grad err vs storage-rounding oracle', short(qerr))
+    assert max(qerr.values()) < GRAD_TOL_GATED, qerr
+    assert float(np.linalg.norm(grads[degenerate])) < 0.2 * med, (float(np.linalg.norm(grads[degenerate])), med)
+    # (b) the live reference's golden (sampled entries)
+    gold_g = {k: gold[f'ggrad/{k}'] for k in (n for n, _ in G.named_parameters())}
+    gold_g.update({'D.' + k: gold[f'dgrad/{k}'] for k in (n for n, _ in D.named_parameters())})
+    norms = {k: float(np.linalg.norm(v)) for k, v in gold_g.items()}
+    floor = 0.10 * float(np.median([v for k, v in norms.items() if not k.startswith('D.')]))
+    gerr = {k: float(np.linalg.norm(summarize(grads[k]) - gold_g[k]) / max(norms[k], floor)) for k in grads}
+    print('rect grad err vs reference golden (sampled, floored)', short(gerr))
     assert max(gerr.values()) < GRAD_TOL_FP32, gerr
