@@ -117,7 +117,10 @@ int pg_debug_stamp(uint64_t* slot, void* stream);
 /* Caller-owned device scratch for the split-K convolutions (the 2x2 .. 16x16 bottleneck layers run their K = 16*Cin
  * reduction on a cluster of CTAs that exchange fp32 partial tiles through this L2-resident buffer).  256-byte aligned;
  * 64 MB covers every layer of the reference configurations; NULL / 0 disables split-K (N is split instead).  The buffer must
- * stay alive while convolutions are in flight; successive launches take successive slices. */
+ * stay alive while convolutions are in flight.  State is per device (the current one).  Successive launches take
+ * successive slices, so that launches in flight on different streams never share one, and the slices are never reused
+ * behind the caller's back: calling this again rewinds the cursor -- do it where no convolution is in flight (the Python
+ * engine does at the start of every step) -- and a launch that no longer fits returns PG_ERR_INVALID. */
 int pg_conv_set_workspace(void* ws, int64_t bytes);
 
 /* ---- convolutions: replaces aten::convolution behind nn.Conv2d / nn.ConvTranspose2d
@@ -151,6 +154,10 @@ int pg_conv_dgrad_act(const PgConvDesc* d, const void* dy, const void* w_packed,
  *      never written.  Layers whose output does not fit tensor memory (or with a 1 x 1 map) are refused
  *      (pg_conv_norm_supported == 0): run pg_conv_fwd_stats + pg_norm_act_fwd / pg_norm_act_bwd instead.
  *      One such launch may be in flight per device at a time (it occupies every SM until its grid barrier). ---- */
+/* SMs the one-launch kernels below may occupy (0 = all).  Their CTAs wait for each other on a grid barrier, so they must
+ * not compete for the last SMs with a kernel that itself waits for other GPUs: the data-parallel Trainer overlaps NCCL
+ * all-reduces with the backward pass and keeps 16 SMs out of these kernels' reach. */
+int pg_set_sm_limit(int32_t n);
 typedef enum PgFusedKind { PG_FUSED_FWD = 0, PG_FUSED_BWD = 1 } PgFusedKind;
 typedef struct PgFusedNorm {
   int32_t kind;        /* PgFusedKind */
@@ -163,7 +170,7 @@ typedef struct PgFusedNorm {
   float* sums;         /* FWD: zeroed [B][N][2], receives (sum, sum of squares) of the conv output per (image, channel).
                           BWD: the sums the forward call of the block left, [B][n_norm][2] */
   float* bsums;        /* BWD: zeroed workspace [B][n_norm][2] */
-  uint32_t* sync;      /* zeroed 32-bit counter (grid barrier) */
+  uint32_t* sync;      /* TWO zeroed 32-bit counters (grid barriers) */
   void* xhat;          /* FWD: optional extra output: the normalised pre-activation, same dtype / layout as out with pixel
                           stride xhat_ld (needed by BWD for relu / tanh / dropout blocks).  BWD: that tensor, or NULL */
   int32_t xhat_ld;
@@ -172,6 +179,11 @@ typedef struct PgFusedNorm {
   int32_t y_dtype;     /* PgDType of y / xhat */
   const void* dskip;   /* BWD: bf16 gradient arriving over the skip connection, added before the activation backward */
   int32_t dskip_ld;
+  void* ws;            /* optional scratch (256-byte aligned, need not be zeroed, must not be shared by launches in flight):
+                          with it, layers of a few output tiles and K in the thousands (the 2x2 .. 16x16 maps) split K over
+                          the SMs and exchange fp32 partial tiles through it; 8 MB covers every layer of the reference
+                          configurations.  NULL: such layers split N instead (slower). */
+  int64_t ws_bytes;
 } PgFusedNorm;
 /* 1 if the fused kernel can run this geometry (d as for pg_conv_fwd), else 0 */
 int pg_conv_norm_supported(const PgConvDesc* d, const PgFusedNorm* fn, int32_t has_twin);

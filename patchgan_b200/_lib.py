@@ -32,7 +32,7 @@ class FusedNorm(C.Structure):
     """PgFusedNorm (include/patchgan_b200.h): arguments of the conv + InstanceNorm one-launch kernels."""
     _fields_ = [('kind', i32), ('act', i32), ('n_norm', i32), ('drop_p', f32), ('seed', vp), ('salt', u64),
                 ('sums', vp), ('bsums', vp), ('sync', vp), ('xhat', vp), ('xhat_ld', i32), ('y', vp), ('y_ld', i32),
-                ('y_dtype', i32), ('dskip', vp), ('dskip_ld', i32)]
+                ('y_dtype', i32), ('dskip', vp), ('dskip_ld', i32), ('ws', vp), ('ws_bytes', i64)]
 
 
 FP = C.POINTER(FusedNorm)
@@ -41,6 +41,7 @@ _SIGS = {
     'pg_version': ([], C.c_int),
     'pg_tcgen05_available': ([], C.c_int),
     'pg_debug_set_trace': ([vp], C.c_int),
+    'pg_set_sm_limit': ([i32], C.c_int),
     'pg_debug_stamp': ([vp, vp], C.c_int),
     'pg_conv_set_workspace': ([vp, i64], C.c_int),
     'pg_launch_count': ([], C.c_int64),

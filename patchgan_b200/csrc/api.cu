@@ -50,6 +50,7 @@ bool tc_device_ok();
 bool conv_res_supported(const PgConvDesc*, const PgFusedNorm*, bool);
 int conv_res_launch(const PgConvDesc*, const void*, const void*, const void*, void*, void*, const PgFusedNorm*, cudaStream_t);
 void set_tc_trace(void*);
+void set_sm_limit(int);
 void set_conv_workspace(void*, size_t);
 // conv_skinny.cu
 bool conv_fewout_supported(const PgConvDesc*);
@@ -100,6 +101,11 @@ extern "C" int pg_last_conv_impl(void) { return g_last_impl; }
 extern "C" int64_t pg_fallback_count(void) { return (int64_t)g_simt_fallbacks; }
 extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
 extern "C" int pg_debug_set_trace(void* buf) { set_tc_trace(buf); return PG_OK; }
+extern "C" int pg_set_sm_limit(int32_t n) {
+  PG_REQUIRE(n >= 0, "pg_set_sm_limit: negative limit");
+  set_sm_limit(n);
+  return PG_OK;
+}
 
 // In-stream time stamp (tools/timeline.py): *slot = %globaltimer when the stream reaches this point.  Capturable.
 __global__ void debug_stamp_kernel(unsigned long long* slot) {

@@ -23,7 +23,7 @@ struct ResParams {
   int kind;                     // PG_FUSED_FWD / PG_FUSED_BWD
   int n_norm;                   // bwd: output channels [0, n_norm) belong to the normalised layer; the rest is stored as is
   int cn;                       // channels per image in sums / bsums and in the dropout element index
-  unsigned int* sync;           // zeroed by the caller: grid barrier counter
+  unsigned int* sync;           // two zeroed counters: grid barriers
   float* sums;                  // fwd: zeroed [B][N][2], receives (sum, sum of squares); bwd: the forward sums (read)
   float* bsums;                 // bwd: zeroed [B][n_norm][2], receives (sum g, sum g*xhat)
   float inv_hw;
@@ -36,12 +36,12 @@ struct ResParams {
   int y_ld, y_dt;
   const void* dskip;            // bwd: bf16 gradient of the skip connection, added to the accumulators (or null)
   int dskip_ld;
-  uint32_t table_off;           // byte offset (from the 1024-aligned dynamic smem base) of the coefficient tables
-  int table_entries;            // float4 entries per epilogue group
+  uint32_t table_off;           // byte offset (from the 1024-aligned dynamic smem base) of the coefficient table
+  int splits, kps;              // split-K mode (splits > 1): CTA = (tile, split) owns k-steps [split*kps, (split+1)*kps)
+  float* ws;                    // split-K exchange scratch in global memory (L2-resident): [tile][split][128 rows][BN] fp32
 };
 
 constexpr int RES_MAX_SLOTS = 16;
-constexpr int RES_TABLE_ENTRIES = 1024;       // per epilogue group: float4 per (image of the tile, channel of the store chunk)
 constexpr float RES_IN_EPS = 1e-5f;
 
 __device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int* p) {
@@ -158,206 +158,308 @@ __device__ __forceinline__ void res_bwd_gx(const ResParams& r, const uint32_t* v
 }
 
 // ---- the two-phase epilogue.  One CTA owns an SM, so the epilogue gets SIXTEEN warps (four groups of four; warp w may
-// touch TMEM lanes 32*(w % 4) .. +31, a group covers all 128): with the four warps of the other kernels one SM's 56 K
-// accumulators were walked by 128 threads and both phases were instruction-latency-bound.  Work items ((tile, 16-column
-// chunk) in phase 1, (tile, store chunk) in phase 2) go round-robin to the groups; every group has its own named barrier,
-// coefficient table and store staging buffers.
-constexpr int RES_GROUPS = 4;
+// touch TMEM lanes 32*(w % 4) .. +31, a group covers all 128 rows of a tile).  Work units are (tile, 16-column chunk),
+// handed round-robin to the groups; a unit needs no synchronisation inside its group: statistics are warp shuffles +
+// red.global, the final values are stored straight from registers (32 bytes per pixel and unit).
+// Waiting warps must not spin: the TMA producer and the MMA issuer are single threads that share their schedulers with
+// four epilogue warps each, and sixteen warps polling an mbarrier halved the main loop's k-step rate.  One lane per warp
+// polls with a nanosleep back-off, the others wait in __syncwarp.
+#ifndef RES_GROUPS_N
+#define RES_GROUPS_N 3
+#endif
+constexpr int RES_GROUPS = RES_GROUPS_N;
 constexpr int RES_EPI_THREADS = RES_GROUPS * 128;
 constexpr int RES_THREADS = 128 + RES_EPI_THREADS;         // warps 0..3: TMA producer, MMA issuer, 2 idle; warps 4..19: epilogue
+constexpr int RES_TABLE_MAX = 2048;                        // float4 coefficient entries in shared memory
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int KIND, int ACT>
-__device__ __forceinline__ void res_epilogue(const TcParams& p, const ResParams& r, const ActMaps& mapsO, uint32_t smem_base,
-                                             uint8_t* smem_gen, uint32_t tmem_base, uint64_t* tfull, int my_tiles) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q = warp & 3, row = q * 32 + lane;
-  const int grp = (warp - 4) >> 2;                       // 0 .. RES_GROUPS-1
-  const int gt = (int)threadIdx.x - 128 - grp * 128;     // 0 .. 127 inside the group (== row)
-  const int lgP = p.lgTW + p.lgTH;
-  const int xl = row & (p.TW - 1), yl = (row >> p.lgTW) & (p.TH - 1), bl = row >> lgP;
-  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
-  const unsigned long long seed = r.drop_p > 0.f ? mix_seed(*r.seed, r.salt) : 0ull;
-  const int nchunk = p.BN >> 4;
-
-  // ---------------------------------------------------------------- phase 1: per-(image, channel) sums
-  for (int i = 0; i < my_tiles; ++i) {
-    const TileXY t = pers_decode(p, blockIdx.x + i * gridDim.x);
-    mbar_wait(smem_u32(&tfull[i]), 0);
-    tc_fence_after();
-    if (KIND == PG_FUSED_BWD && t.n0 >= r.n_norm) continue;
-    const int b = t.b0 + bl, a = t.y0 + yl, bb = t.x0 + xl;
-    const bool valid = b < p.B && a < p.Ha && bb < p.Wa;
-    int oy = a, ox = bb;
-    if (p.mode == PG_CONVT) { oy = 2 * a + t.py; ox = 2 * bb + t.px; }
-    const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
-    const uint32_t trow = tmem_base + (uint32_t)(i * p.BN) + lane_off;
-    float* dst0 = (KIND == PG_FUSED_FWD ? r.sums : r.bsums) + ((long long)(b < p.B ? b : 0) * r.cn + t.n0) * 2;
-    for (int c16 = (grp + RES_GROUPS - ((i * nchunk) & (RES_GROUPS - 1))) & (RES_GROUPS - 1); c16 < nchunk; c16 += RES_GROUPS) {
-      const int c = c16 << 4;
-      uint32_t v[16];
-      tmem_ld16(trow + (uint32_t)c, v);
-      tmem_ld_wait();
-      float a1[16], a2[16];
-      if (KIND == PG_FUSED_FWD) {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) { a1[j] = valid ? __uint_as_float(v[j]) : 0.f; a2[j] = a1[j] * a1[j]; }
-      } else {
-        float xh[16];
-        res_bwd_gx<ACT>(r, v, opix, t.n0 + c, valid, seed, a1, xh);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) a2[j] = a1[j] * xh[j];
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int lane) {
+  if (lane == 0 && !mbar_try_wait(bar, parity)) {
+    const long long t0 = clock64();
+    unsigned ns = 32;
+    while (!mbar_try_wait(bar, parity)) {
+      __nanosleep(ns);
+      if (ns < 256) ns <<= 1;
+      if (clock64() - t0 > 4000000000LL) {
+        printf("conv_res: accumulator barrier timeout (block %d thread %d)\n", blockIdx.x, threadIdx.x);
+        __trap();
       }
-      group_add16(a1, a2, lgP, lane, b < p.B, dst0 + c * 2);
     }
   }
+  __syncwarp();
+}
 
-  // ---------------------------------------------------------------- grid barrier (every CTA of the grid is resident)
+// every CTA of the grid is resident (grid <= #SMs, one CTA per SM): a counter in global memory is a grid barrier
+__device__ __forceinline__ void res_grid_barrier(unsigned int* ctr) {
   __threadfence();
   named_bar_sync(6, RES_EPI_THREADS);
   if (threadIdx.x == 128) {
-    red_release_gpu_inc(r.sync);
+    red_release_gpu_inc(ctr);
     const long long t0 = clock64();
-    while (ld_acquire_gpu_u32(r.sync) < gridDim.x) {
+    while (ld_acquire_gpu_u32(ctr) < gridDim.x) {
+      __nanosleep(40);
       if (clock64() - t0 > 2000000000LL) {
-        printf("conv_res: grid barrier timeout (block %d of %d, saw %u)\n", blockIdx.x, gridDim.x, ld_acquire_gpu_u32(r.sync));
+        printf("conv_res: grid barrier timeout (block %d of %d, saw %u)\n", blockIdx.x, gridDim.x, ld_acquire_gpu_u32(ctr));
         __trap();
       }
     }
   }
   named_bar_sync(6, RES_EPI_THREADS);
   __threadfence();
+}
 
-  // ---------------------------------------------------------------- phase 2: normalise, activate, store
-  const bool f16out = p.out_f32 == PG_F16;
-  const uint32_t bufbytes = 128u * (uint32_t)p.st_rowbytes;
-  const int sh = p.st_rowbytes == 128 ? 0 : (p.st_rowbytes == 64 ? 1 : 2);
-  const uint32_t xr = (uint32_t)(row >> sh) & (uint32_t)((p.st_rowbytes >> 4) - 1);
-  const int nch = p.BN / p.st_cw;
-  const int lgCW = 31 - __clz(p.st_cw);
+struct RowPix {
+  bool valid;        // this accumulator row is an output pixel
+  int b;             // image
+  long long opix;    // output pixel index (b * Hout + oy) * Wout + ox
+};
+__device__ __forceinline__ RowPix row_pixel(const TcParams& p, const TileXY& t, int row) {
+  const int lgP = p.lgTW + p.lgTH;
+  const int xl = row & (p.TW - 1), yl = (row >> p.lgTW) & (p.TH - 1), bl = row >> lgP;
+  RowPix rp;
+  rp.b = t.b0 + bl;
+  const int a = t.y0 + yl, bb = t.x0 + xl;
+  rp.valid = rp.b < p.B && a < p.Ha && bb < p.Wa;
+  int oy = a, ox = bb;
+  if (p.mode == PG_CONVT) { oy = 2 * a + t.py; ox = 2 * bb + t.px; }
+  rp.opix = ((long long)rp.b * p.Hout + oy) * p.Wout + ox;
+  return rp;
+}
+
+// coefficients of (image b, channel ch): fwd (mean, rstd), bwd (rstd, mean g, mean g*xhat)
+template <int KIND>
+__device__ __forceinline__ float4 res_coef(const TcParams& p, const ResParams& r, int b, int ch) {
+  if (b >= p.B) return make_float4(0.f, 1.f, 0.f, 0.f);
   const double inv_hw = (double)r.inv_hw;
-  const int bar_id = 1 + grp;
-  // this group's staging buffers (primary, twin) and coefficient table
-  const uint32_t prim = smem_base + (uint32_t)(2 * grp) * bufbytes + (uint32_t)row * p.st_rowbytes;
-  const uint32_t twin = prim + bufbytes;
-  float4* table = reinterpret_cast<float4*>(smem_gen + r.table_off) + grp * r.table_entries;
-  const float4* trow_tab = table + (bl << lgCW);
-  int item = 0;
+  const float* sp = r.sums + ((long long)b * r.cn + ch) * 2;
+  const double m = (double)__ldcg(sp) * inv_hw;
+  double var = (double)__ldcg(sp + 1) * inv_hw - m * m;
+  if (var < 0) var = 0;
+  const float rstd = (float)(1.0 / sqrt(var + (double)RES_IN_EPS));
+  if (KIND == PG_FUSED_FWD) return make_float4((float)m, rstd, 0.f, 0.f);
+  const float* bs = r.bsums + ((long long)b * r.cn + ch) * 2;
+  return make_float4(rstd, __ldcg(bs) * r.inv_hw, __ldcg(bs + 1) * r.inv_hw, 0.f);
+}
+
+// phase-1 quantities of one unit: v = 16 raw sums of this thread's row -> (a1, a2) whose per-(image, channel) sums are wanted
+template <int KIND, int ACT>
+__device__ __forceinline__ void res_stats16(const TcParams& p, const ResParams& r, const uint32_t* v, const RowPix& rp, int n,
+                                            unsigned long long seed, int lane, int lgP) {
+  float a1[16], a2[16];
+  if (KIND == PG_FUSED_FWD) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { a1[j] = rp.valid ? __uint_as_float(v[j]) : 0.f; a2[j] = a1[j] * a1[j]; }
+  } else {
+    float xh[16];
+    res_bwd_gx<ACT>(r, v, rp.opix, n, rp.valid, seed, a1, xh);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) a2[j] = a1[j] * xh[j];
+  }
+  float* dst = (KIND == PG_FUSED_FWD ? r.sums : r.bsums) + ((long long)(rp.b < p.B ? rp.b : 0) * r.cn + n) * 2;
+  group_add16(a1, a2, lgP, lane, rp.b < p.B, dst);
+}
+
+// phase-2 of one unit: v = 16 raw sums, cf = the 16 coefficient entries of this row's image -> final values, stored
+template <int KIND, int ACT>
+__device__ __forceinline__ void res_finish16(const TcParams& p, const ResParams& r, const uint32_t* v, const float4* cf,
+                                             bool norm_tile, const RowPix& rp, int n, unsigned long long seed) {
+  float f[16];
+  if (!norm_tile) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  } else if (KIND == PG_FUSED_FWD) {
+    float xh[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 c4 = cf[j];
+      xh[j] = (__uint_as_float(v[j]) - c4.x) * c4.y;
+      f[j] = act_fast<ACT>(xh[j]);
+    }
+    if (r.drop_p > 0.f) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float u = uniform01(seed, (unsigned long long)(rp.opix * r.cn + n + j));
+        f[j] = u >= r.drop_p ? f[j] * r.keep_scale : 0.f;
+      }
+    }
+    if (n + 16 > p.n_valid) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        if (n + j >= p.n_valid) { f[j] = 0.f; xh[j] = 0.f; }
+      }
+    }
+    if (r.xhat != nullptr && rp.valid) {
+      uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(r.xhat) + rp.opix * r.xhat_ld + n);
+      o[0] = pack8dt(xh, p.out_f32);
+      o[1] = pack8dt(xh + 8, p.out_f32);
+    }
+  } else {
+    float g[16], xh[16];
+    res_bwd_gx<ACT>(r, v, rp.opix, n, rp.valid, seed, g, xh);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 c4 = cf[j];
+      f[j] = c4.x * (g[j] - c4.y - xh[j] * c4.z);
+    }
+  }
+  if (rp.valid && !(p.debug & 4)) {
+    uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(p.out) + rp.opix * p.ldo + n);
+    o[0] = pack8dt(f, p.out_f32);
+    o[1] = pack8dt(f + 8, p.out_f32);
+    if (p.out2 != nullptr) {
+      uint4* o2 = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(p.out2) + rp.opix * p.ldo + n);
+      o2[0] = pack8(f);
+      o2[1] = pack8(f + 8);
+    }
+  }
+}
+
+template <int KIND, int ACT>
+__device__ __forceinline__ void res_epilogue(const TcParams& p, const ResParams& r, uint8_t* smem_gen, uint32_t tmem_base,
+                                             uint64_t* tfull, int my_tiles) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3, row = q * 32 + lane;
+  const int grp = (warp - 4) >> 2;                       // 0 .. RES_GROUPS-1
+  const int et = (int)threadIdx.x - 128;                 // 0 .. 511 among the epilogue threads
+  const int lgP = p.lgTW + p.lgTH, lgTB = 7 - lgP, lgBN = 31 - __clz(p.BN);
+  const int bl = row >> lgP;
+  const uint32_t lane_off = (uint32_t)(q * 32) << 16;
+  const unsigned long long seed = r.drop_p > 0.f ? mix_seed(*r.seed, r.salt) : 0ull;
+  const int nchunk = p.BN >> 4;
+  const bool tracer = p.trace != nullptr && threadIdx.x == 128;
+  float4* table = reinterpret_cast<float4*>(smem_gen + r.table_off);
+
+  if (r.splits > 1) {
+    // =========================== split-K mode: this CTA holds a PARTIAL tile ===========================
+    // (small maps: a handful of output tiles, K = 16 * Cin in the thousands.  splits CTAs share a tile's k-range, dump
+    //  their partial accumulators to an L2-resident scratch, and after a grid barrier every (tile, 16-column chunk) unit is
+    //  summed by one epilogue group somewhere in the grid, which then owns it: statistics, second barrier, final values
+    //  from registers.)
+    const int tile = blockIdx.x / r.splits, split = blockIdx.x - tile * r.splits;
+    mbar_wait_warp(smem_u32(&tfull[0]), 0, lane);
+    tc_fence_after();
+    if (tracer) { trace_raw(p.trace, 2, gtimer()); trace_raw(p.trace, 3, gtimer()); }
+    {
+      float* dst = r.ws + (((long long)tile * r.splits + split) * 128 + row) * p.BN;
+      for (int c16 = grp; c16 < nchunk; c16 += RES_GROUPS) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + lane_off + (uint32_t)(c16 << 4), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          __stcg(reinterpret_cast<float4*>(dst + (c16 << 4)) + j,
+                 make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                             __uint_as_float(v[4 * j + 3])));
+      }
+    }
+    if (tracer) trace_raw(p.trace, 4, gtimer());
+    res_grid_barrier(r.sync);
+    if (tracer) trace_raw(p.trace, 5, gtimer());
+    // ---- this group's unit (at most one: the plan keeps units = tiles * nchunk <= RES_GROUPS * grid)
+    const int unit = (int)blockIdx.x + grp * (int)gridDim.x;
+    const bool have = unit < p.pers_total * nchunk;
+    const int utile = have ? unit / nchunk : 0, c16 = have ? unit - utile * nchunk : 0;
+    const TileXY t = pers_decode(p, utile);
+    const RowPix rp = row_pixel(p, t, row);
+    const int n = t.n0 + (c16 << 4);
+    const bool norm_tile = KIND == PG_FUSED_FWD || t.n0 < r.n_norm;
+    uint32_t v[16];
+    if (have) {
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+      const float* src = r.ws + (((long long)utile * r.splits) * 128 + row) * p.BN + (c16 << 4);
+      for (int sp = 0; sp < r.splits; ++sp) {
+        float4 tq[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) tq[j] = __ldcg(reinterpret_cast<const float4*>(src + (long long)sp * 128 * p.BN) + j);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[4 * j] += tq[j].x; acc[4 * j + 1] += tq[j].y; acc[4 * j + 2] += tq[j].z; acc[4 * j + 3] += tq[j].w; }
+      }
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(acc[j]);
+      if (norm_tile) res_stats16<KIND, ACT>(p, r, v, rp, n, seed, lane, lgP);
+    }
+    res_grid_barrier(r.sync + 1);
+    if (have) {
+      // coefficient table of this group: [image of the tile][16 channels of the unit]
+      float4* gtab = table + grp * (16 << lgTB);
+      if (norm_tile)
+        for (int e = (int)threadIdx.x - 128 - grp * 128; e < (16 << lgTB); e += 128)
+          gtab[e] = res_coef<KIND>(p, r, t.b0 + (e >> 4), n + (e & 15));
+    }
+    named_bar_sync(1 + grp, 128);
+    if (have) res_finish16<KIND, ACT>(p, r, v, table + grp * (16 << lgTB) + (bl << 4), norm_tile, rp, n, seed);
+    if (tracer) { trace_raw(p.trace, 8, gtimer()); trace_raw(p.trace, 9, 1ull); }
+    return;
+  }
+
+  // =========================== resident mode: whole tiles stay in TMEM across the barrier ===========================
+  // ---- phase 1: per-(image, channel) sums
+  int unit = 0;
+  for (int i = 0; i < my_tiles; ++i) {
+    const TileXY t = pers_decode(p, blockIdx.x + i * gridDim.x);
+    mbar_wait_warp(smem_u32(&tfull[i]), 0, lane);
+    tc_fence_after();
+    if (tracer && i == 0) trace_raw(p.trace, 2, gtimer());
+    if (tracer && i == my_tiles - 1) trace_raw(p.trace, 3, gtimer());
+    if (KIND == PG_FUSED_BWD && t.n0 >= r.n_norm) { unit += nchunk; continue; }
+    const RowPix rp = row_pixel(p, t, row);
+    const uint32_t trow = tmem_base + (uint32_t)(i * p.BN) + lane_off;
+    for (int c16 = 0; c16 < nchunk; ++c16, ++unit) {
+      if (unit % RES_GROUPS != grp) continue;
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(c16 << 4), v);
+      tmem_ld_wait();
+      res_stats16<KIND, ACT>(p, r, v, rp, t.n0 + (c16 << 4), seed, lane, lgP);
+    }
+  }
+  if (tracer) trace_raw(p.trace, 4, gtimer());
+  res_grid_barrier(r.sync);
+  if (tracer) trace_raw(p.trace, 5, gtimer());
+
+  // ---- coefficients of all my tiles: entry ((i * TB + image of the tile) * BN + channel)
+  {
+    const int per_tile = p.BN << lgTB;
+    const int total = my_tiles * per_tile;
+    for (int e = et; e < total; e += RES_EPI_THREADS) {
+      const int i = e / per_tile, rem = e - i * per_tile;
+      const TileXY t = pers_decode(p, blockIdx.x + i * gridDim.x);
+      if (KIND == PG_FUSED_BWD && t.n0 >= r.n_norm) continue;
+      table[e] = res_coef<KIND>(p, r, t.b0 + (rem >> lgBN), t.n0 + (rem & (p.BN - 1)));
+    }
+  }
+  named_bar_sync(6, RES_EPI_THREADS);
+
+  // ---- phase 2: normalise, activate, store
+  unit = 0;
   for (int i = 0; i < my_tiles; ++i) {
     const TileXY t = pers_decode(p, blockIdx.x + i * gridDim.x);
     const bool norm_tile = KIND == PG_FUSED_FWD || t.n0 < r.n_norm;
-    const int b = t.b0 + bl, a = t.y0 + yl, bb = t.x0 + xl;
-    const bool valid = b < p.B && a < p.Ha && bb < p.Wa;
-    int oy = a, ox = bb;
-    if (p.mode == PG_CONVT) { oy = 2 * a + t.py; ox = 2 * bb + t.px; }
-    const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
+    const RowPix rp = row_pixel(p, t, row);
     const uint32_t trow = tmem_base + (uint32_t)(i * p.BN) + lane_off;
-    for (int ch = 0; ch < nch; ++ch, ++item) {
-      if ((item & (RES_GROUPS - 1)) != grp) continue;
-      const int cbase = ch * p.st_cw;                 // first column of this store chunk inside the tile
-      named_bar_sync(bar_id, 128);                    // the previous item's table readers are done
-      if (norm_tile) {
-        // coefficients of this chunk: fwd (mean, rstd), bwd (rstd, mean g, mean g*xhat) per (image of the tile, channel)
-        const int ent = (128 >> lgP) << lgCW;
-        for (int e = gt; e < ent; e += 128) {
-          const int tb = e >> lgCW, c = e & (p.st_cw - 1);
-          const int eb = t.b0 + tb;
-          float4 cf = make_float4(0.f, 1.f, 0.f, 0.f);
-          if (eb < p.B) {
-            const float* sp = r.sums + ((long long)eb * r.cn + t.n0 + cbase + c) * 2;
-            const double m = (double)__ldcg(sp) * inv_hw;
-            double var = (double)__ldcg(sp + 1) * inv_hw - m * m;
-            if (var < 0) var = 0;
-            const float rstd = (float)(1.0 / sqrt(var + (double)RES_IN_EPS));
-            if (KIND == PG_FUSED_FWD) {
-              cf = make_float4((float)m, rstd, 0.f, 0.f);
-            } else {
-              const float* bs = r.bsums + ((long long)eb * r.cn + t.n0 + cbase + c) * 2;
-              cf = make_float4(rstd, __ldcg(bs) * r.inv_hw, __ldcg(bs + 1) * r.inv_hw, 0.f);
-            }
-          }
-          table[e] = cf;
-        }
-      }
-      if (gt == 0) bulk_wait_read<0>();               // this group's previous bulk store has read the staging buffers
-      named_bar_sync(bar_id, 128);
-      for (int sub = 0; sub < p.st_cw; sub += 16) {
-        const int c = cbase + sub, n = t.n0 + c;
-        uint32_t v[16];
-        tmem_ld16(trow + (uint32_t)c, v);
-        tmem_ld_wait();
-        float f[16];
-        if (!norm_tile) {
-#pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        } else if (KIND == PG_FUSED_FWD) {
-          float xh[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 cf = trow_tab[sub + j];
-            xh[j] = (__uint_as_float(v[j]) - cf.x) * cf.y;
-            f[j] = act_fast<ACT>(xh[j]);
-          }
-          if (r.drop_p > 0.f) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const float u = uniform01(seed, (unsigned long long)(opix * r.cn + n + j));
-              f[j] = u >= r.drop_p ? f[j] * r.keep_scale : 0.f;
-            }
-          }
-          if (n + 16 > p.n_valid) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              if (n + j >= p.n_valid) { f[j] = 0.f; xh[j] = 0.f; }
-            }
-          }
-          if (r.xhat != nullptr && valid) {
-            uint4* o = reinterpret_cast<uint4*>(reinterpret_cast<unsigned short*>(r.xhat) + opix * r.xhat_ld + n);
-            o[0] = pack8dt(xh, p.out_f32);
-            o[1] = pack8dt(xh + 8, p.out_f32);
-          }
-        } else {
-          float g[16], xh[16];
-          res_bwd_gx<ACT>(r, v, opix, n, valid, seed, g, xh);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float4 cf = trow_tab[sub + j];
-            f[j] = cf.x * (g[j] - cf.y - xh[j] * cf.z);
-          }
-        }
-        const uint32_t u0 = (uint32_t)(sub * 2) >> 4;
-        if (f16out) {
-          st_shared_v4(prim + (((u0) ^ xr) << 4), pack8h(f));
-          st_shared_v4(prim + (((u0 + 1) ^ xr) << 4), pack8h(f + 8));
-        } else {
-          st_shared_v4(prim + (((u0) ^ xr) << 4), pack8(f));
-          st_shared_v4(prim + (((u0 + 1) ^ xr) << 4), pack8(f + 8));
-        }
-        if (p.st_twin) {
-          st_shared_v4(twin + (((u0) ^ xr) << 4), pack8(f));
-          st_shared_v4(twin + (((u0 + 1) ^ xr) << 4), pack8(f + 8));
-        }
-      }
-      fence_proxy_async();
-      named_bar_sync(bar_id, 128);
-      if (gt == 0) {
-        const uint32_t sbuf = smem_base + (uint32_t)(2 * grp) * bufbytes;
-        tma_store_4d(&mapsO.m[t.cls], sbuf, t.n0 + cbase, t.x0, t.y0, t.b0);
-        if (p.st_twin) tma_store_4d(&mapsO.m[4 + t.cls], sbuf + bufbytes, t.n0 + cbase, t.x0, t.y0, t.b0);
-        bulk_commit();
-      }
+    const float4* ctile = table + (((i << lgTB) + bl) << lgBN);
+    for (int c16 = 0; c16 < nchunk; ++c16, ++unit) {
+      if (unit % RES_GROUPS != grp) continue;
+      uint32_t v[16];
+      tmem_ld16(trow + (uint32_t)(c16 << 4), v);
+      tmem_ld_wait();
+      res_finish16<KIND, ACT>(p, r, v, ctile + (c16 << 4), norm_tile, rp, t.n0 + (c16 << 4), seed);
     }
   }
-  if (gt == 0) bulk_wait_read<0>();
+  if (p.trace != nullptr) {
+    named_bar_sync(6, RES_EPI_THREADS);
+    if (tracer) { trace_raw(p.trace, 8, gtimer()); trace_raw(p.trace, 9, (unsigned long long)my_tiles); }
+  }
 }
 
 template <int KIND>
 __global__ void __launch_bounds__(RES_THREADS, 1)
-conv_res_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB,
-                const __grid_constant__ ActMaps mapsO, const TcParams p, const ResParams r) {
+conv_res_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB, const TcParams p,
+                const ResParams r) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[MAX_STAGES];
   __shared__ __align__(8) uint64_t empty_bar[MAX_STAGES];
@@ -370,8 +472,16 @@ conv_res_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ C
   const uint32_t a_base = smem_base;
   const uint32_t b_base = smem_base + p.stages * p.a_bytes;
   const int nk = p.nk1 + p.nk2;
-  const int ksteps = p.ntaps * nk;
-  const int my_tiles = (p.pers_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  // resident mode: this CTA's tiles are blockIdx.x + i * gridDim.x, all k-steps; split-K mode: one (tile, split)
+  const int my_tiles = r.splits > 1 ? 1 : (p.pers_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int ks0 = r.splits > 1 ? ((int)blockIdx.x % r.splits) * r.kps : 0;
+  const int ksteps = r.splits > 1 ? r.kps : p.ntaps * nk;
+  if (p.trace != nullptr && threadIdx.x == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    trace_raw(p.trace, 0, gtimer());
+    trace_raw(p.trace, 7, smid);
+  }
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapsA.m[0]);
@@ -390,6 +500,7 @@ conv_res_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ C
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
+  if (p.trace != nullptr && threadIdx.x == 0) trace_raw(p.trace, 1, gtimer());
 
   if (warp == 0) {
     // ===================== TMA producer: the ring runs ahead across this CTA's tiles =====================
@@ -397,8 +508,8 @@ conv_res_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ C
       int stage = 0;
       uint32_t phase = 0;
       for (int i = 0; i < my_tiles; ++i) {
-        const TileXY t = pers_decode(p, blockIdx.x + i * gridDim.x);
-        int tap = 0, ck = 0, cx = 0, cy = 0, wtap = 0, ph = 0;
+        const TileXY t = pers_decode(p, r.splits > 1 ? (int)blockIdx.x / r.splits : (int)blockIdx.x + i * (int)gridDim.x);
+        int tap = ks0 / nk, ck = ks0 - tap * nk, cx = 0, cy = 0, wtap = 0, ph = 0;
         bool newtap = true;
         for (int ks = 0; ks < ksteps; ++ks) {
           if (newtap) {
@@ -453,10 +564,10 @@ conv_res_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ C
   } else if (warp >= 4) {
     // ===================== two-phase epilogue: 16 warps =====================
     switch (p.act) {
-      case PG_ACT_RELU: res_epilogue<KIND, PG_ACT_RELU>(p, r, mapsO, smem_base, smem_gen, tmem_base, tfull, my_tiles); break;
-      case PG_ACT_LEAKYRELU: res_epilogue<KIND, PG_ACT_LEAKYRELU>(p, r, mapsO, smem_base, smem_gen, tmem_base, tfull, my_tiles); break;
-      case PG_ACT_TANH: res_epilogue<KIND, PG_ACT_TANH>(p, r, mapsO, smem_base, smem_gen, tmem_base, tfull, my_tiles); break;
-      default: res_epilogue<KIND, PG_ACT_NONE>(p, r, mapsO, smem_base, smem_gen, tmem_base, tfull, my_tiles); break;
+      case PG_ACT_RELU: res_epilogue<KIND, PG_ACT_RELU>(p, r, smem_gen, tmem_base, tfull, my_tiles); break;
+      case PG_ACT_LEAKYRELU: res_epilogue<KIND, PG_ACT_LEAKYRELU>(p, r, smem_gen, tmem_base, tfull, my_tiles); break;
+      case PG_ACT_TANH: res_epilogue<KIND, PG_ACT_TANH>(p, r, smem_gen, tmem_base, tfull, my_tiles); break;
+      default: res_epilogue<KIND, PG_ACT_NONE>(p, r, smem_gen, tmem_base, tfull, my_tiles); break;
     }
   }
   tc_fence_before();
@@ -465,20 +576,32 @@ conv_res_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ C
     tc_fence_after();
     tmem_dealloc(tmem_base, p.tmem_cols);
   }
+  if (p.trace != nullptr && threadIdx.x == 0) trace_raw(p.trace, 6, gtimer());
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------------------
+// SMs the resident kernels may occupy (pg_set_sm_limit): every CTA spins on a grid barrier, so while another kernel that
+// waits on PEER GPUs (an NCCL collective on a side stream) shares the device, some SMs must stay out of the grid's reach.
+static int g_sm_limit = 0;
+void set_sm_limit(int n) { g_sm_limit = n; }
+static int res_sms() {
+  const int n = num_sms();
+  return g_sm_limit > 0 && g_sm_limit < n ? g_sm_limit : n;
+}
+
 struct ResPlan {
   TcPlan pl;
-  int grid, slots;
-  size_t smem;
+  int grid, slots, splits, kps;
+  size_t smem, ws_bytes;
   uint32_t table_off;
-  int table_entries;
 };
 
+// Tile width BN and K-split S are chosen by a small cost model (microseconds): a CTA moves (16 KB + BN * 128 B) per k-step
+// from L2 at ~120 GB/s (TMA-latency-bound ring), the whole grid at most ~7 TB/s, and the epilogue costs per unit.
 static bool make_res_plan(const PgConvDesc* d, const PgFusedNorm* fn, bool twin, ResPlan& rp) {
+  (void)twin;
   TcParams& p = rp.pl.p;
   memset(&p, 0, sizeof(p));
   p.mode = d->mode; p.stride = d->stride; p.pad = d->pad; p.B = d->B;
@@ -493,6 +616,8 @@ static bool make_res_plan(const PgConvDesc* d, const PgFusedNorm* fn, bool twin,
   p.nx = (p.Wa + p.TW - 1) / p.TW; p.ny = (p.Ha + p.TH - 1) / p.TH;
   if (p.TW * p.TH < 2) return false;                       // one lattice point per image: nothing to normalise over
   if (p.TW > 256 || p.TH > 256 || p.TB > 256) return false;
+  if (d->out_f32 != PG_F16 && d->out_f32 != PG_BF16) return false;
+  if (d->ldo < d->N) return false;
   const int nb = (p.B + p.TB - 1) / p.TB;
   int bk = 64;
   while (bk > 16 && ((d->C1 % bk) != 0 || (d->C2 % bk) != 0)) bk >>= 1;
@@ -500,67 +625,79 @@ static bool make_res_plan(const PgConvDesc* d, const PgFusedNorm* fn, bool twin,
   p.BK = bk; p.nk1 = d->C1 / bk; p.nk2 = d->C2 / bk; p.Ctot = d->C1 + d->C2;
   const int ncls = d->mode == PG_CONVT ? 4 : 1;
   const long long mt = (long long)p.nx * p.ny * nb * ncls;
-  // BN: a power of two dividing N (and n_norm, so that a tile is either normalised or not), at most 128, small enough
-  // for the coefficient table, as small as needed to give every SM a tile, large enough for the tiles to fit TMEM
-  int bnmax = 128;
-  while (bnmax > 16 && ((d->N % bnmax) != 0 || (fn->kind == PG_FUSED_BWD && (fn->n_norm % bnmax) != 0))) bnmax >>= 1;
-  if ((d->N % bnmax) != 0 || (fn->kind == PG_FUSED_BWD && (fn->n_norm % bnmax) != 0)) return false;
-  while (bnmax > 16 && p.TB * (bnmax > 64 ? 64 : bnmax) > RES_TABLE_ENTRIES) bnmax >>= 1;   // (table: one store chunk <= 64 columns)
-  if (p.TB * (bnmax > 64 ? 64 : bnmax) > RES_TABLE_ENTRIES) return false;
-  const int sms = num_sms();
-  int bn = bnmax;
-  while (bn > 16 && mt * (d->N / bn) < sms) bn >>= 1;
-  int grid = 0, slots = 0;
-  for (;; bn <<= 1) {
-    if (bn > bnmax) return false;
-    const long long total = mt * (d->N / bn);
-    if (total >= (1LL << 30)) return false;
-    grid = (int)(total < sms ? total : sms);
-    slots = (int)((total + grid - 1) / grid);
-    if (slots <= RES_MAX_SLOTS && slots * bn <= 512) break;
+  const int ksteps = p.ntaps * (p.nk1 + p.nk2);
+  const int sms = res_sms();
+  const int swz = bk * 2;
+  const double a_bytes = 128.0 * swz;
+  int best_bn = 0, best_s = 0;
+  double best = 1e30;
+  for (int bn = 128; bn >= 16; bn >>= 1) {
+    if ((d->N % bn) != 0 || (fn->kind == PG_FUSED_BWD && (fn->n_norm % bn) != 0)) continue;
+    const long long tiles = mt * (d->N / bn);
+    if (tiles >= (1LL << 30)) continue;
+    const double step_bytes = a_bytes + (double)bn * swz;
+    for (int S = 1; S <= 32; S <<= 1) {
+      double us;
+      if (S == 1) {
+        const int grid = (int)(tiles < sms ? tiles : sms);
+        const int slots = (int)((tiles + grid - 1) / grid);
+        if (slots > RES_MAX_SLOTS || slots * bn > 512) continue;
+        if ((long long)slots * p.TB * bn > RES_TABLE_MAX) continue;
+        const double cta = slots * ksteps * step_bytes, all = (double)tiles * ksteps * step_bytes;
+        const double load = cta / 120e3 > all / 7e6 ? cta / 120e3 : all / 7e6;      // bytes / (bytes per us)
+        us = load + 0.5 * slots * (bn / 16) / RES_GROUPS + 3.0;
+      } else {
+        if (tiles * S > sms || (ksteps % S) != 0 || ksteps / S < 2 || bn / 16 > RES_GROUPS * S) continue;
+        if (fn->ws == nullptr || (size_t)tiles * S * 128 * bn * 4 > (size_t)fn->ws_bytes) continue;
+        if (RES_GROUPS * 16 * p.TB > RES_TABLE_MAX) continue;
+        const double cta = (double)(ksteps / S) * step_bytes, all = (double)tiles * ksteps * step_bytes;
+        const double load = cta / 120e3 > all / 7e6 ? cta / 120e3 : all / 7e6;
+        us = load + 0.3 * (bn / 16) / RES_GROUPS + 0.05 * S + 7.0;       // dump + S-plane sum + second barrier
+      }
+      if (us < best) { best = us; best_bn = bn; best_s = S; }
+    }
   }
+  if (best_bn == 0) return false;
+  const int bn = best_bn;
+  const long long tiles = mt * (d->N / bn);
+  rp.splits = best_s;
+  rp.kps = ksteps / best_s;
+  int grid, slots;
+  if (best_s == 1) {
+    grid = (int)(tiles < sms ? tiles : sms);
+    slots = (int)((tiles + grid - 1) / grid);
+  } else {
+    grid = (int)tiles * best_s;
+    slots = 1;
+  }
+  rp.ws_bytes = best_s > 1 ? (size_t)tiles * best_s * 128 * bn * 4 : 0;
   p.BN = bn;
   p.N = d->N; p.ldo = d->ldo; p.n_valid = d->n_valid; p.act = fn->act; p.out_f32 = d->out_f32;
   p.splits = 1; p.nacc = 1;
-  rp.pl.swz = bk * 2;
-  p.layout_type = rp.pl.swz == 128 ? 2u : (rp.pl.swz == 64 ? 4u : 6u);
-  p.sbo = 8u * rp.pl.swz;
+  rp.pl.swz = swz;
+  p.layout_type = swz == 128 ? 2u : (swz == 64 ? 4u : 6u);
+  p.sbo = 8u * swz;
   const uint32_t fmt = d->in_dtype == PG_F16 ? 0u : 1u;
   p.idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  p.a_bytes = 128u * rp.pl.swz;
-  p.b_bytes = ((uint32_t)bn * rp.pl.swz + 1023u) & ~1023u;
-  p.tx_bytes = 128u * rp.pl.swz + (uint32_t)bn * rp.pl.swz;
+  p.a_bytes = 128u * swz;
+  p.b_bytes = ((uint32_t)bn * swz + 1023u) & ~1023u;
+  p.tx_bytes = 128u * swz + (uint32_t)bn * swz;
   const uint32_t per_stage = p.a_bytes + p.b_bytes;
-  // output staging (reuses the idle ring in phase 2): two buffers (+ two for the bf16 twin)
-  if (d->out_f32 != PG_F16 && d->out_f32 != PG_BF16) return false;
-  if (d->ldo < d->N) return false;
-  const int rowbytes = bn * 2 > 128 ? 128 : bn * 2;
-  p.tma_store = 1;
-  p.st_rowbytes = rowbytes;
-  p.st_cw = rowbytes / 2;
-  p.st_nbuf = 2;
-  p.st_twin = twin ? 1 : 0;
-  const uint32_t staging = (uint32_t)RES_GROUPS * 2u * 128u * (uint32_t)rowbytes;     // per group: primary + twin
-  rp.table_entries = p.TB * p.st_cw;
-  const uint32_t table = (uint32_t)RES_GROUPS * (uint32_t)rp.table_entries * 16u;
-  const int ksteps = p.ntaps * (p.nk1 + p.nk2);
-  uint32_t budget = 200u * 1024u - table;
-  int stages = (int)(budget / per_stage);
+  const uint32_t table = (uint32_t)RES_TABLE_MAX * 16u;
+  int stages = (int)((200u * 1024u - table) / per_stage);
   if (stages > MAX_STAGES) stages = MAX_STAGES;
-  if (stages > ksteps * slots) stages = ksteps * slots;
+  if (stages > rp.kps * slots) stages = rp.kps * slots;
   if (stages < 1) return false;
   p.stages = stages;
-  p.kps = ksteps;
-  uint32_t region = (uint32_t)stages * per_stage;
-  if (region < staging) region = staging;
-  region = (region + 1023u) & ~1023u;
+  p.kps = rp.kps;
+  uint32_t region = ((uint32_t)stages * per_stage + 1023u) & ~1023u;
   if (region < 120u * 1024u) region = 120u * 1024u;        // > half of the SM's shared memory: ONE CTA per SM, always
   rp.table_off = region;
   rp.smem = (size_t)region + table + 1024;
   int tcols = 32;
   while (tcols < slots * bn) tcols <<= 1;
   p.tmem_cols = (uint32_t)tcols;
-  p.pers_total = (int)(mt * (d->N / bn));
+  p.pers_total = (int)tiles;
   p.pers_mtiles = (int)(mt / ncls);
   p.pers_ntiles = d->N / bn;
   rp.grid = grid; rp.slots = slots;
@@ -582,6 +719,9 @@ int conv_res_launch(const PgConvDesc* d, const void* src1, const void* src2, con
   }
   TcParams& p = rp.pl.p;
   p.out = out; p.out2 = out2;
+  p.trace = g_trace;
+  static const int skip = [] { const char* e = getenv("PG_TC_SKIP"); return e ? atoi(e) : 0; }();
+  p.debug = skip;
   ResParams r;
   memset(&r, 0, sizeof(r));
   r.kind = fn->kind;
@@ -596,12 +736,12 @@ int conv_res_launch(const PgConvDesc* d, const void* src1, const void* src2, con
   r.y = fn->y; r.y_ld = fn->y_ld; r.y_dt = fn->y_dtype;
   r.dskip = fn->dskip; r.dskip_ld = fn->dskip_ld;
   r.table_off = rp.table_off;
-  r.table_entries = rp.table_entries;
+  r.splits = rp.splits; r.kps = rp.kps;
+  r.ws = (float*)fn->ws;
   const bool phased = d->mode == PG_CONV && d->stride == 2;
-  ActMaps mA, mO;
+  ActMaps mA;
   CUtensorMap mB;
   memset(&mA, 0, sizeof(mA));
-  memset(&mO, 0, sizeof(mO));
   for (int src = 0; src < (d->C2 > 0 ? 2 : 1); ++src) {
     const void* base = src ? src2 : src1;
     const int C = src ? d->C2 : d->C1, ld = src ? d->ld2 : d->ld1;
@@ -626,18 +766,6 @@ int conv_res_launch(const PgConvDesc* d, const void* src1, const void* src2, con
       return PG_ERR_CUDA;
     }
   }
-  {
-    const bool cls = d->mode == PG_CONVT;
-    for (int ph = 0; ph < (cls ? 4 : 1); ++ph) {
-      if (int e = encode_act_map(&mO.m[ph], out, d->N, d->ldo, d->B, d->Hout, d->Wout, p.st_cw, p.TW, p.TH, p.TB,
-                                 cls ? ph : -1, p.st_rowbytes, d->out_f32))
-        return e;
-      if (out2 != nullptr)
-        if (int e = encode_act_map(&mO.m[4 + ph], out2, d->N, d->ldo, d->B, d->Hout, d->Wout, p.st_cw, p.TW, p.TH, p.TB,
-                                   cls ? ph : -1, p.st_rowbytes, PG_BF16))
-          return e;
-    }
-  }
   static bool smem_set = false;
   if (!smem_set) {
     PG_CUDA(cudaFuncSetAttribute(conv_res_kernel<PG_FUSED_FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
@@ -646,12 +774,12 @@ int conv_res_launch(const PgConvDesc* d, const void* src1, const void* src2, con
   }
   static const bool dbg = getenv("PG_TC_DEBUG") != nullptr;
   if (dbg)
-    fprintf(stderr, "conv_res: kind %d grid %d slots %d BN %d BK %d stages %d tmem %u smem %zu TW %d TH %d TB %d ksteps %d tiles %d\n",
-            r.kind, rp.grid, rp.slots, p.BN, p.BK, p.stages, p.tmem_cols, rp.smem, p.TW, p.TH, p.TB,
+    fprintf(stderr, "conv_res: kind %d grid %d slots %d splits %d BN %d BK %d stages %d tmem %u smem %zu TW %d TH %d TB %d ksteps %d tiles %d\n",
+            r.kind, rp.grid, rp.slots, rp.splits, p.BN, p.BK, p.stages, p.tmem_cols, rp.smem, p.TW, p.TH, p.TB,
             p.ntaps * (p.nk1 + p.nk2), p.pers_total);
   if (r.kind == PG_FUSED_FWD)
-    conv_res_kernel<PG_FUSED_FWD><<<rp.grid, RES_THREADS, rp.smem, stream>>>(mA, mB, mO, p, r);
+    conv_res_kernel<PG_FUSED_FWD><<<rp.grid, RES_THREADS, rp.smem, stream>>>(mA, mB, p, r);
   else
-    conv_res_kernel<PG_FUSED_BWD><<<rp.grid, RES_THREADS, rp.smem, stream>>>(mA, mB, mO, p, r);
+    conv_res_kernel<PG_FUSED_BWD><<<rp.grid, RES_THREADS, rp.smem, stream>>>(mA, mB, p, r);
   return check_launch("conv_res_kernel");
 }

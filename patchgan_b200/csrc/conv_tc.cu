@@ -1094,11 +1094,23 @@ bool tc_device_ok() {
 static int pow2_ceil(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 static int ilog2(int v) { int l = 0; while ((1 << l) < v) ++l; return l; }
 
-// Split-K exchange scratch (caller-owned, pg_conv_set_workspace): consecutive split launches take consecutive slices so
-// that launches in flight on different streams never share one.
-static float* g_ws = nullptr;
-static size_t g_ws_bytes = 0, g_ws_next = 0;
-void set_conv_workspace(void* ws, size_t bytes) { g_ws = (float*)ws; g_ws_bytes = bytes; g_ws_next = 0; }
+// Split-K exchange scratch (caller-owned, pg_conv_set_workspace), one per device: consecutive split launches take
+// consecutive slices so that launches in flight on different streams never share one.  The cursor never wraps: the caller
+// re-registers the buffer (which rewinds the cursor) at a point where no convolution is in flight -- the engine does so at
+// the beginning of every step -- and a launch that does not fit any more fails loudly instead of reusing a slice that
+// another stream may still be reducing through.
+constexpr int MAX_DEVICES = 16;
+struct WsState { float* ws; size_t bytes, next; };
+static WsState g_wss[MAX_DEVICES];
+static WsState& ws_state() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; }
+  return g_wss[dev >= 0 && dev < MAX_DEVICES ? dev : 0];
+}
+void set_conv_workspace(void* ws, size_t bytes) {
+  WsState& w = ws_state();
+  w.ws = (float*)ws; w.bytes = bytes; w.next = 0;
+}
 
 struct TcPlan {
   TcParams p;
@@ -1141,11 +1153,12 @@ static bool make_plan(const PgConvDesc* d, TcPlan& pl) {
     // 128 x 64 tiles, clusters of <= 4: the exchanged partial tile is 32 KB, 4-SM clusters pack into every GPC, and
     // two such CTAs fit one SM
     int sbn = bn > 64 ? 64 : bn;
-    if (splitk_env && g_ws != nullptr && d->mode != PG_CONV1X1 && mtiles * (d->N / sbn) * 2 <= num_sms() && ksteps0 >= 8) {
+    const WsState& wst = ws_state();
+    if (splitk_env && wst.ws != nullptr && d->mode != PG_CONV1X1 && mtiles * (d->N / sbn) * 2 <= num_sms() && ksteps0 >= 8) {
       int S = 4;
       while (S > 1 && (sbn / S < 16 || (ksteps0 % S) != 0 || ksteps0 / S < 2)) S >>= 1;
       while (S > 2 && mtiles * (d->N / sbn) * S > 2LL * num_sms()) S >>= 1;
-      if (S > 1 && (size_t)mtiles * (d->N / sbn) * S * 128 * sbn * 4 <= g_ws_bytes) { p.splits = S; bn = sbn; }
+      if (S > 1 && (size_t)mtiles * (d->N / sbn) * S * 128 * sbn * 4 <= wst.bytes) { p.splits = S; bn = sbn; }
     }
     if (p.splits == 1)
       while (bn > 16 && mtiles * (d->N / bn) < num_sms()) bn >>= 1;
@@ -1403,9 +1416,14 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   }
   if (p.splits > 1) {
     const size_t need = (size_t)pl.grid.x * pl.grid.y * pl.grid.z * 128 * p.BN * 4;
-    if (g_ws_next + need > g_ws_bytes) g_ws_next = 0;
-    p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(g_ws) + g_ws_next);
-    g_ws_next += (need + 255) & ~(size_t)255;
+    WsState& wsm = ws_state();
+    if (wsm.next + need > wsm.bytes) {
+      set_error("conv_tc: split-K workspace exhausted (%zu of %zu bytes handed out since the last pg_conv_set_workspace): "
+                "re-register it when no convolution is in flight, or make it larger", wsm.next, wsm.bytes);
+      return PG_ERR_INVALID;
+    }
+    p.ws = reinterpret_cast<float*>(reinterpret_cast<char*>(wsm.ws) + wsm.next);
+    wsm.next += (need + 255) & ~(size_t)255;
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = pl.grid;

@@ -5,6 +5,8 @@ normalisation is per-sample InstanceNorm, so the only exchange is one gradient a
 Semantics: each rank runs the reference step on its own shard and the flat gradient buffers are averaged
 ("reference per rank + gradient averaging", i.e. DDP semantics).
 """
+import ctypes
+import glob
 import os
 
 import torch
@@ -46,6 +48,91 @@ def init_from_env(backend=None):
 class _Done:
     def wait(self):
         return True
+
+
+# ------------------------------------------------------------------------------------------------
+# Our own NCCL communicator (the torch-bundled libnccl, bound with ctypes).  The process group's collectives could not be
+# captured into the step's CUDA graph on this stack (the capture hung), raw ncclAllReduce calls on a communicator of our
+# own can: the gradient all-reduces become nodes of the step's graph, on the stream whose work they follow, and overlap
+# the backward kernels of the other network.  torch.distributed still does the rendezvous (it carries the NCCL unique id).
+# ------------------------------------------------------------------------------------------------
+class _UniqueId(ctypes.Structure):
+    _fields_ = [('internal', ctypes.c_byte * 128)]
+
+
+NCCL_FLOAT32, NCCL_SUM = 7, 0
+NCCL_SMS = 16        # SMs left to the NCCL kernels while they overlap the backward pass
+_COMM = {'tried': False, 'lib': None, 'comm': None}
+
+
+def _load_nccl():
+    base = os.path.dirname(os.path.dirname(torch.__file__))
+    cands = glob.glob(os.path.join(base, 'nvidia', 'nccl', 'lib', 'libnccl.so*')) + ['libnccl.so.2']
+    for c in cands:
+        try:
+            lib = ctypes.CDLL(c)
+        except OSError:
+            continue
+        lib.ncclGetUniqueId.argtypes = [ctypes.POINTER(_UniqueId)]
+        lib.ncclCommInitRank.argtypes = [ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, _UniqueId, ctypes.c_int]
+        lib.ncclAllReduce.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p]
+        lib.ncclGetErrorString.restype = ctypes.c_char_p
+        lib.ncclGetErrorString.argtypes = [ctypes.c_int]
+        return lib
+    return None
+
+
+def raw_comm():
+    """The process-wide raw NCCL communicator (created on first use, collectively: every rank must get here), or None when
+    the job is not an NCCL job (single process, gloo) or PATCHGAN_B200_RAW_NCCL=0."""
+    if _COMM['tried']:
+        return _COMM['comm']
+    _COMM['tried'] = True
+    if world_size() == 1 or dist.get_backend() != 'nccl' or os.environ.get('PATCHGAN_B200_RAW_NCCL', '1') == '0':
+        return None
+    lib = _load_nccl()
+    if lib is None:
+        return None
+    # The collectives run beside the backward kernels: cap NCCL's CTAs, and keep as many SMs out of the grid-barrier
+    # kernels' reach (see pg_set_sm_limit), so that neither can starve the other of the SMs it needs to make progress.
+    os.environ.setdefault('NCCL_MAX_CTAS', str(NCCL_SMS))
+    from . import _lib as L
+    nsm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    L.check(L.lib().pg_set_sm_limit(max(nsm - NCCL_SMS, nsm // 2)), 'pg_set_sm_limit')
+    uid = _UniqueId()
+    if rank() == 0:
+        rc = lib.ncclGetUniqueId(ctypes.byref(uid))
+        if rc != 0:
+            raise RuntimeError(f'ncclGetUniqueId: {lib.ncclGetErrorString(rc).decode()}')
+    dev = torch.device('cuda', torch.cuda.current_device())
+    t = torch.tensor(list(bytes(uid)), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0)
+    ctypes.memmove(ctypes.byref(uid), bytes(t.cpu().tolist()), 128)
+    comm = ctypes.c_void_p()
+    rc = lib.ncclCommInitRank(ctypes.byref(comm), world_size(), uid, rank())
+    if rc != 0:
+        raise RuntimeError(f'ncclCommInitRank: {lib.ncclGetErrorString(rc).decode()}')
+    _COMM['lib'], _COMM['comm'] = lib, comm
+    return comm
+
+
+def raw_all_reduce_sum_(flat, first=0, count=None):
+    """In-place fp32 sum-all-reduce of flat[first : first + count] on the CURRENT stream through the raw communicator
+    (graph-capturable; no host synchronisation)."""
+    comm = raw_comm()
+    if comm is None:
+        raise RuntimeError('raw NCCL communicator unavailable')
+    if flat.dtype != torch.float32 or not flat.is_contiguous():
+        raise RuntimeError('raw_all_reduce_sum_: contiguous float32 buffers only')
+    n = flat.numel() - first if count is None else count
+    if n <= 0:
+        return
+    ptr = flat.data_ptr() + first * 4
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = _COMM['lib'].ncclAllReduce(ptr, ptr, n, NCCL_FLOAT32, NCCL_SUM, comm, st)
+    if rc != 0:
+        raise RuntimeError(f'ncclAllReduce: {_COMM["lib"].ncclGetErrorString(rc).decode()}')
 
 
 def all_reduce_sum_async(flat):

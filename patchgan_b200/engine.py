@@ -117,6 +117,7 @@ def begin_step(device=None):
     if device is not None:
         _ZPOOL['buf'] = keep(torch.zeros(ZPOOL_FLOATS, device=device, dtype=torch.float32))
         _ZPOOL['off'] = 0
+        ensure_workspace(torch.device(device), rewind=True)
 
 
 def end_step():
@@ -132,7 +133,7 @@ def keep(t):
     return t
 
 
-def side_streams(device, n=3):
+def side_streams(device, n=6):
     key = (device.index if device.index is not None else torch.cuda.current_device())
     if key not in _SIDE:
         _SIDE[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
@@ -150,7 +151,11 @@ def fork(side):
 
 def join(side):
     """The current stream continues after everything issued so far on `side` (no-op if `side` was never forked in this
-    step: joining a stream that is not part of the graph being captured would be an error)."""
+    step: joining a stream that is not part of the graph being captured would be an error).  `side` may be a list."""
+    if isinstance(side, (list, tuple)):
+        for s_ in side:
+            join(s_)
+        return
     if side in _FORKED:
         torch.cuda.current_stream().wait_stream(side)
 
@@ -228,14 +233,25 @@ def desc_tag(d):
 _WS = {}
 
 
-def ensure_workspace(device):
-    """Register the split-K exchange scratch of the library (one 64 MB buffer per device, allocated once)."""
+def ensure_workspace(device, rewind=False):
+    """Register the split-K exchange scratch of the library (one 64 MB buffer per device, allocated once).
+    rewind=True (start of a step: nothing is in flight) hands the slices out from the beginning again."""
     key = device.index if device.index is not None else torch.cuda.current_device()
-    if _WS.get('cur') != key:
-        if key not in _WS:
-            _WS[key] = torch.empty(64 << 20, device=device, dtype=torch.uint8)
-        L.call('pg_conv_set_workspace', _WS[key].data_ptr(), _WS[key].numel())
-        _WS['cur'] = key
+    if key not in _WS:
+        _WS[key] = torch.empty(64 << 20, device=device, dtype=torch.uint8)
+        _WS[('fused', key)] = torch.empty(8 << 20, device=device, dtype=torch.uint8)
+        rewind = True
+    if rewind:
+        with torch.cuda.device(key):
+            # (not a stream call: bypass the profiler / stamper hooks of L.call)
+            L.check(L.lib().pg_conv_set_workspace(_WS[key].data_ptr(), _WS[key].numel()), 'pg_conv_set_workspace')
+
+
+def fused_workspace(device):
+    """Scratch of the one-launch conv + InstanceNorm kernels' split-K mode (one such launch is in flight at a time)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    ensure_workspace(device)
+    return _WS[('fused', key)]
 
 
 def run_conv(desc, src1, src2, w, bias, out, stats=None):
@@ -275,6 +291,8 @@ def fused_conv_norm(desc, src1, src2, w, out, act, drop_p, seed, salt, want_xhat
     fn = L.FusedNorm()
     fn.kind, fn.act, fn.drop_p, fn.salt = L.FUSED_FWD, act, float(drop_p), salt
     fn.seed = seed.data_ptr() if drop_p > 0 else None
+    ws = fused_workspace(out.t.device)
+    fn.ws, fn.ws_bytes = ws.data_ptr(), ws.numel()
     if not L.lib().pg_conv_norm_supported(ctypes.byref(desc), ctypes.byref(fn), int(out.tw is not None)):
         return None
     dev = out.t.device
@@ -331,6 +349,8 @@ def dgrad_block_bwd(desc, dy, w, wrow_bytes, din, n_norm, blk, dskip, seed):
         if dskip is not None:
             fn.dskip, fn.dskip_ld = dskip.ptr, dskip.ld
         fn.sums = blk.sums.data_ptr()
+        fws = fused_workspace(dev)
+        fn.ws, fn.ws_bytes = fws.data_ptr(), fws.numel()
         plans = [(desc, None)]
         if n_norm < desc.N:       # the normalised half alone may fit tensor memory when the whole concat gradient does not
             plans.append((_shift_desc(desc, 0, n_norm), _shift_desc(desc, n_norm, desc.N - n_norm)))
@@ -361,11 +381,24 @@ def dgrad_block_bwd(desc, dy, w, wrow_bytes, din, n_norm, blk, dskip, seed):
     return norm_bwd(x, blk.sums, d_prev, dskip, act, blk.dp, seed, blk.salt, kind)
 
 
+_WRR = [0]
+
+
+def pick_wstream(wstream):
+    """wstream may be one side stream or a list of them (independent weight-gradients then go round-robin, so that one
+    layer's launch does not wait behind another's for no reason)."""
+    if isinstance(wstream, (list, tuple)):
+        _WRR[0] += 1
+        return wstream[_WRR[0] % len(wstream)]
+    return wstream
+
+
 def run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream=None):
     """wstream: issue the weight-gradient on that side stream (it forks here, after its operands were produced on
     the current stream; the caller joins it before the optimizer step)."""
     if 'wgrad' in SKIP:
         return
+    wstream = pick_wstream(wstream)
     if wstream is not None:
         fork(wstream)
         with torch.cuda.stream(wstream):
@@ -554,7 +587,9 @@ class NetEngine:
         ps = self.params()
         dev = self.device()
         if dev.type == 'cuda':
-            ensure_workspace(dev)
+            # outside a Trainer step (module called on its own, one stream) the split-K slices are handed out from the
+            # start again on every call; inside a step begin_step has done so and side streams are in play
+            ensure_workspace(dev, rewind=not _KEEPING)
         if dev.type != 'cuda':
             raise RuntimeError('patchgan_b200: module parameters must live on a CUDA device (no CPU path)')
         stamp = tuple((ps[s.wname].data_ptr(), ps[s.wname]._version) for s in self.specs)
@@ -630,6 +665,7 @@ class NetEngine:
         self._tm_off = off + need
         sp = self._tm_buf.data_ptr() + off * 4
         jobs.append((sp, dst_ptr, ld_n, n_real, c_real, Ns, Cs))
+        wstream = pick_wstream(wstream)
         if wstream is not None:
             fork(wstream)
         with torch.cuda.stream(wstream if wstream is not None else torch.cuda.current_stream()):
@@ -847,6 +883,7 @@ class GeneratorEngine(NetEngine):
             ctx['enc'].append((h, raw, sums, out, dp, xh) if save else None)
             enc_outs.append(out)
             h = out
+        self.last_bottleneck = h          # encoder output (unet.py:119); UNet.forward(return_hidden=True) reads it
         for i, s in enumerate(self.dec):
             src1 = h
             src2 = enc_outs[6 - i] if i > 0 else None
@@ -878,8 +915,9 @@ class GeneratorEngine(NetEngine):
             h = out
         return h, ctx
 
-    def backward(self, ctx, d_raw, grads, need_dx=False, wstream=None, early=None):
+    def backward(self, ctx, d_raw, grads, need_dx=False, wstream=None, early=None, d_hidden=None):
         """d_raw: bf16 Act, gradient wrt the last ConvTranspose2d's output (pre final activation).
+        d_hidden: optional bf16 Act, gradient wrt the encoder bottleneck returned by forward(return_hidden=True).
         grads: dict name -> zero-initialised float32 tensor in the reference layout (accumulated into).
         wstream: side stream for the weight-gradient launches (off the data-gradient critical path).
         early = (i, fn): fn() is called once everything that touches the layers other than encoder 0 .. i-1 has been
@@ -928,7 +966,8 @@ class GeneratorEngine(NetEngine):
                 # data gradient: stride-2 conv of dY with W'[ci][tap][co]
                 dd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
                                din.ld, c_valid=s.cout)
-                d_raw = dgrad_block_bwd(dd, d_raw, pw.bwd, 16 * d_raw.C * 2, din, s.c1p, prod, None, self.seed)
+                d_raw = dgrad_block_bwd(dd, d_raw, pw.bwd, 16 * d_raw.C * 2, din, s.c1p, prod,
+                                        d_hidden if i == 0 else None, self.seed)
             if i >= 1:
                 dskip[6 - i] = din.slice(s.c1p, s.c2p)
         # d_raw is now the gradient wrt encoder 6's convolution output
@@ -1078,7 +1117,7 @@ class DiscriminatorEngine(NetEngine):
                                    out_dt=BF16, in_dt=BF16)
                     self.wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
                 if s.bias:
-                    with torch.cuda.stream(wstream if wstream is not None else torch.cuda.current_stream()):
+                    with torch.cuda.stream(pick_wstream(wstream) if wstream is not None else torch.cuda.current_stream()):
                         L.call('pg_colsum', d_raw.ptr, B * d_raw.H * d_raw.W, d_raw.ld, s.cout,
                                grads[s.bname].data_ptr(), _stream())
             if li > 0 or need_dx:

@@ -113,6 +113,28 @@ class FusedAdam(torch.optim.Optimizer):
                f['v'].data_ptr() + lo * 4, hi - lo, f['hyper'].data_ptr(), f['step'].data_ptr(), b1, b2, g['eps'],
                self.grad_scale, 1 if bump else 0, _stream())
 
+    # ---- checkpointing: the moments and the step count live in the flat device buffers, not in self.state
+    def state_dict(self):
+        """{'step': int, 'exp_avg': [per-parameter tensors], 'exp_avg_sq': [...], 'lr': float} (CPU tensors, the order of
+        the parameters handed to the constructor = module.parameters())."""
+        f = self.flat()
+        ps = self._params()
+        cut = lambda buf: [buf[o:o + p.numel()].view(p.shape).detach().cpu().clone() for p, o in zip(ps, f['offs'])]
+        return dict(step=int(f['step'].item()), exp_avg=cut(f['m']), exp_avg_sq=cut(f['v']),
+                    lr=float(self.param_groups[0]['lr']))
+
+    def load_state_dict(self, state):
+        f = self.flat()
+        ps = self._params()
+        if len(state['exp_avg']) != len(ps) or any(tuple(a.shape) != tuple(p.shape) for a, p in zip(state['exp_avg'], ps)):
+            raise ValueError('FusedAdam.load_state_dict: the saved moments do not match the parameters')
+        for name, buf in (('exp_avg', f['m']), ('exp_avg_sq', f['v'])):
+            for p, o, a in zip(ps, f['offs'], state[name]):
+                buf[o:o + p.numel()].copy_(a.reshape(-1).to(buf.device, torch.float32))
+        f['step'].fill_(int(state['step']))
+        self.param_groups[0]['lr'] = float(state['lr'])
+        self._lr_on_device = None
+
     def zero_grad(self, set_to_none=False):
         if self._flat is not None:
             self._flat['g'].zero_()

@@ -117,6 +117,13 @@ class Trainer:
                                        on_step=self.generator._engine().mark_dirty)
         self.disc_optimizer = FusedAdam(self.discriminator.parameters(), lr=dsc_lr, betas=(0.9, 0.999),
                                         on_step=self.discriminator._engine().mark_dirty)
+        state = getattr(self, '_resume_optimizer_state', None)
+        if state is not None:       # load_last_checkpoint found an optimizer file: continue with its moments / step count
+            self.gen_optimizer.load_state_dict(state['generator'])
+            self.disc_optimizer.load_state_dict(state['discriminator'])
+            self.gen_optimizer.param_groups[0]['lr'] = gen_lr      # (the learning rate is re-derived by train(), as in
+            self.disc_optimizer.param_groups[0]['lr'] = dsc_lr     #  the reference: trainer.py:155-157)
+            self._resume_optimizer_state = None
 
     def _graph_signature(self, train):
         """Addresses a captured step depends on beyond its key: the flat optimizer buffers and the parameter storages.
@@ -162,7 +169,18 @@ class Trainer:
         #   s_d: D(real) forward during the generator forward, later the whole discriminator update;
         #   s_w: the generator's weight-gradients, off its data-gradient chain;  s_dw: the discriminator's.
         ms = E.Config.streams and L.PROFILER is None
-        s_d, s_w, s_dw = E.side_streams(dev) if ms else (None, None, None)
+        s_d = s_w = s_dw = None
+        if ms:
+            ss = E.side_streams(dev)
+            s_d, s_dw = ss[0], ss[2]
+            # the generator's weight-gradients: independent launches, spread over NWS streams
+            nws = max(1, min(4, int(os.environ.get('PATCHGAN_B200_WSTREAMS', '1'))))
+            s_w = ss[1] if nws == 1 else [ss[1]] + ss[3:3 + nws - 1]
+        # D(cat(x, y)) forward: under the generator's forward on a side stream (default), or -- DREAL_LATE=1 -- batched with
+        # D(cat(x, G(x))) into one 2B-image pass after it (the one-launch conv + InstanceNorm kernels of the generator own
+        # every SM while they run, so a concurrent discriminator pass and they only take turns)
+        dreal_late = os.environ.get('PATCHGAN_B200_DREAL_LATE', '1') != '0'
+        raw_nccl = world > 1 and dp.raw_comm() is not None
 
         def on(stream):
             return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
@@ -197,7 +215,7 @@ class Trainer:
 
         # ---- D(cat(x, y)) (trainer.py:96-97) does not depend on the generator: side stream, under G's forward
         dctx = D.forward_begin(dboth, save=train)
-        if ms:
+        if ms and not dreal_late:
             E.fork(s_d)
             with on(s_d):
                 D.forward_part(dctx, B, B)
@@ -213,7 +231,7 @@ class Trainer:
             L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.ptr, dboth.ld, cin, cout, B * H * W, dboth.dt, st)
             if dboth.tw is not None:
                 L.call('pg_copy_f32_to_bf16_slice', p.ptr, p.ld, dboth.tw.ptr, dboth.ld, cin, cout, B * H * W, 0, st)
-        if ms:
+        if ms and not dreal_late:
             D.forward_part(dctx, 0, B)
             E.join(s_d)
         else:
@@ -245,7 +263,12 @@ class Trainer:
                     E.join(s_dw)
                     D.finalize_grads()
                 if world > 1 and phase == 'all':
-                    d_work = dp.all_reduce_sum_async(dflat['g'])
+                    # the discriminator's gradients are final: their all-reduce runs on this side stream, underneath the
+                    # generator's backward pass (raw NCCL call = a node of the step's graph; else the process group's)
+                    if raw_nccl:
+                        dp.raw_all_reduce_sum_(dflat['g'])
+                    else:
+                        d_work = dp.all_reduce_sum_async(dflat['g'])
                     dopt.grad_scale = 1.0 / world
 
         # ---- segmentation loss (trainer.py:71-82)
@@ -288,10 +311,13 @@ class Trainer:
                 nl = len(G.specs)
 
                 def early_update():
-                    ev_w, ev_m = torch.cuda.Event(), torch.cuda.Event()
-                    ev_w.record(s_w)                 # the weight-gradients of layers K.. (issued on s_w)
+                    ev_m = torch.cuda.Event()
+                    for sw in (s_w if isinstance(s_w, list) else [s_w]):   # the weight-gradients of layers K..
+                        if sw in E._FORKED:
+                            ev_w = torch.cuda.Event()
+                            ev_w.record(sw)
+                            s_d.wait_event(ev_w)
                     ev_m.record()                    # the last reads of their operand copies (data-gradients, this stream)
-                    s_d.wait_event(ev_w)
                     s_d.wait_event(ev_m)
                     with on(s_d):
                         G.finalize_grads(partial=True)
@@ -306,6 +332,41 @@ class Trainer:
                 G.repack_layers(0, K, complete=True)
                 E.end_step()
                 return losses
+            if (ms and raw_nccl and phase == 'all' and K > 0 and len(G.specs) > K and G.layers_match_parameters()):
+                # ---- data-parallel, raw NCCL: the generator's gradient buffer is all-reduced in two buckets.  Everything
+                #      but the first K encoder layers (99 % of the bytes) is final while the backward of those K layers
+                #      still runs: it goes out on s_d, behind the discriminator's all-reduce; the small rest follows on the
+                #      main stream at the end.
+                off_k = gopt.flat()['offs'][K]
+
+                def early_allreduce():
+                    ev_m = torch.cuda.Event()
+                    for sw in (s_w if isinstance(s_w, list) else [s_w]):
+                        if sw in E._FORKED:
+                            ev_w = torch.cuda.Event()
+                            ev_w.record(sw)
+                            s_d.wait_event(ev_w)
+                    ev_m.record()
+                    s_d.wait_event(ev_m)
+                    with on(s_d):
+                        G.finalize_grads(partial=True)
+                        dp.raw_all_reduce_sum_(gflat['g'], off_k)
+
+                G.backward(gctx, d_raw, ggrads, wstream=s_w, early=(K, early_allreduce))
+                E.join(s_w)
+                G.finalize_grads()
+                dp.raw_all_reduce_sum_(gflat['g'], 0, off_k)
+                E.join(s_d)
+                gopt.grad_scale = 1.0 / world
+                E.fork(s_d)
+                with on(s_d):
+                    dopt.step(sync_lr=False)
+                    D.repack()
+                gopt.step(sync_lr=False)
+                G.repack()
+                E.join(s_d)
+                E.end_step()
+                return losses
             if 'gbwd' not in E.SKIP:
                 G.backward(gctx, d_raw, ggrads, wstream=s_w)
             if ms:
@@ -317,9 +378,11 @@ class Trainer:
                 E.end_step()
                 return losses
             if world > 1:
-                g_work = dp.all_reduce_sum_async(gflat['g'])
                 gopt.grad_scale = 1.0 / world
-                g_work.wait()
+                if raw_nccl:
+                    dp.raw_all_reduce_sum_(gflat['g'])
+                else:
+                    dp.all_reduce_sum_async(gflat['g']).wait()
             if 'adam' not in E.SKIP:
                 gopt.step(sync_lr=False)
             with on(s_d):
@@ -376,9 +439,10 @@ class Trainer:
         if not self.use_cuda_graph or L.PROFILER is not None or \
                 (dp.world_size() > 1 and os.environ.get('PATCHGAN_B200_GRAPH_DP', '1') == '0'):
             return self.step_device(x, y, train)
-        # data-parallel: NCCL is kept out of the graphs (capturing the process group's collectives hung on this stack):
-        # graph A = everything up to the finished gradients, eager all-reduces, graph B = Adam + repack of both networks
-        split = dp.world_size() > 1
+        # data-parallel: with our own NCCL communicator (dp.raw_comm) the all-reduces are nodes of the step's ONE graph.
+        # Without it (PATCHGAN_B200_RAW_NCCL=0, gloo) the process group's collectives stay out of the graphs (capturing them
+        # hung on this stack): graph A = everything up to the finished gradients, eager all-reduces, graph B = Adam + repack
+        split = dp.world_size() > 1 and dp.raw_comm() is None
         key = self._graph_key(x, y, train)
         ent = self._graphs.get(key)
         if ent is not None and ent['graph'] is not None and ent['sig'] != self._graph_signature(train):
@@ -400,7 +464,7 @@ class Trainer:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             # (the process-group watchdog thread may poll events while we capture: check this thread's calls only)
-            mode = 'thread_local' if split else 'global'
+            mode = 'thread_local' if dp.world_size() > 1 else 'global'
             with torch.cuda.graph(g, capture_error_mode=mode):
                 ent['losses'] = self.step_device(ent['x'], ent['y'], train, phase='grads' if split else 'all')
             ent['graph'] = g
@@ -621,6 +685,11 @@ class Trainer:
         if dp.rank() == 0:
             torch.save({k: v.detach().clone() for k, v in self.generator.state_dict().items()}, gen_savefile)
             torch.save({k: v.detach().clone() for k, v in self.discriminator.state_dict().items()}, disc_savefile)
+            # not in the reference (it restarts Adam from zero moments on resume, trainer.py:281-287): the optimizer state,
+            # in a third file so that the two reference-format files stay exactly what the reference writes
+            if hasattr(self, 'gen_optimizer'):
+                torch.save(dict(generator=self.gen_optimizer.state_dict(), discriminator=self.disc_optimizer.state_dict()),
+                           f'{self.savefolder}/optimizer_ep_{epoch:03d}.pth')
 
     def load_last_checkpoint(self):
         def epochs_of(prefix):
@@ -633,6 +702,8 @@ class Trainer:
             self.load(f"{self.savefolder}/generator_ep_{start:03d}.pth",
                       f"{self.savefolder}/discriminator_ep_{start:03d}.pth")
             self.start = start + 1
+            opt_file = f"{self.savefolder}/optimizer_ep_{start:03d}.pth"
+            self._resume_optimizer_state = torch.load(opt_file, map_location='cpu') if os.path.exists(opt_file) else None
         except Exception as e:
             print(e)
             print("Checkpoints not loaded")

@@ -52,7 +52,7 @@ class UpSampleBlock(nn.Module):
 
 class _UNetFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, *weights):
+    def forward(ctx, module, x, want_hidden, *weights):
         eng = module._engine()
         B, C, H, W = x.shape
         need_grad = any(ctx.needs_input_grad)      # (grad mode is always off inside Function.forward)
@@ -72,14 +72,28 @@ class _UNetFunction(torch.autograd.Function):
         ctx.module, ctx.saved, ctx.p = module, saved, p
         ctx.x_needs_grad = x.requires_grad
         ctx.shape = (B, C, H, W)
-        return out
+        if not want_hidden:
+            return out
+        # the encoder bottleneck (unet.py:119,131-132), from the SAME forward pass: (B, 8nf, H/128, W/128) NCHW float
+        h6 = saved['enc'][6][3] if need_grad else eng.last_bottleneck
+        hidden = torch.empty((B, module.nf * 8, h6.H, h6.W), device=x.device, dtype=torch.float32)
+        L.call('pg_unpack_nhwc_to_nchw_f32', h6.ptr, h6.dt, hidden.data_ptr(), B, module.nf * 8, h6.H, h6.W, h6.ld, 0,
+               _stream())
+        ctx.hidden_shape = (h6.H, h6.W, h6.C)
+        return out, hidden
 
     @staticmethod
-    def backward(ctx, dout):
+    def backward(ctx, dout, dhidden=None):
         module, eng = ctx.module, ctx.module._engine()
         B, C, H, W = ctx.shape
         p = ctx.p
         dev = dout.device
+        d_hid = None
+        if dhidden is not None:
+            hh, hw, hc = ctx.hidden_shape
+            d_hid = new_act(B, hh, hw, hc, dev, zero=True)
+            L.call('pg_pack_nchw_f32_to_nhwc_bf16', dhidden.contiguous().float().data_ptr(), d_hid.ptr, B, module.nf * 8, hh,
+                   hw, d_hid.ld, 0, d_hid.dt, _stream())
         # dOut (NCHW float) -> NHWC bf16, then through the final activation
         dpk = new_act(B, H, W, eng.out_cp, dev, zero=True)
         L.call('pg_pack_nchw_f32_to_nhwc_bf16', dout.contiguous().data_ptr(), dpk.ptr, B, module.output_nc, H, W, dpk.ld,
@@ -90,12 +104,12 @@ class _UNetFunction(torch.autograd.Function):
         names = [s.wname for s in eng.specs]
         params = eng.params()
         grads = {n: torch.zeros_like(params[n], dtype=torch.float32) for n in names}
-        dx = eng.backward(ctx.saved, d_raw, grads, need_dx=ctx.x_needs_grad)
+        dx = eng.backward(ctx.saved, d_raw, grads, need_dx=ctx.x_needs_grad, d_hidden=d_hid)
         gx = None
         if ctx.x_needs_grad:
             gx = torch.empty((B, C, H, W), device=dev, dtype=torch.float32)
             L.call('pg_unpack_nhwc_to_nchw_f32', dx.ptr, dx.dt, gx.data_ptr(), B, C, H, W, dx.ld, 0, _stream())
-        return (None, gx) + tuple(grads[n] for n in names)
+        return (None, gx, None) + tuple(grads[n] for n in names)
 
 
 class UNet(nn.Module, Transferable):
@@ -147,21 +161,6 @@ class UNet(nn.Module, Transferable):
         require_cuda(x, 'UNet input')
         if x.dim() != 4 or x.shape[1] != self.input_nc:
             raise RuntimeError(f'UNet expects (B, {self.input_nc}, H, W), got {tuple(x.shape)}')
-        out = _UNetFunction.apply(self, x, *self._weights())
-        if return_hidden:
-            return out, self._hidden(x)
-        return out
-
-    def _hidden(self, x):
-        """(B, 8nf, H/128, W/128) encoder bottleneck as NCHW float (unet.py:119,131-132; not differentiable here)."""
-        eng = self._engine()
-        with torch.no_grad():
-            xin = eng.pack_input(x.contiguous().float())
-            # re-run the network so that `forward` does not have to keep the bottleneck alive
-            p, saved = eng.forward(xin, self.training, save=True)
-            h6 = saved['enc'][6][3]
-            B = x.shape[0]
-            out = torch.empty((B, self.nf * 8, h6.H, h6.W), device=x.device, dtype=torch.float32)
-            L.call('pg_unpack_nhwc_to_nchw_f32', h6.ptr, h6.dt, out.data_ptr(), B, self.nf * 8, h6.H, h6.W, h6.ld, 0,
-                   _stream())
-        return out
+        # one autograd node; with return_hidden the bottleneck comes from the same pass and is differentiable like the
+        # reference's (unet.py:131-134)
+        return _UNetFunction.apply(self, x, bool(return_hidden), *self._weights())

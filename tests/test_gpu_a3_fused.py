@@ -87,7 +87,11 @@ def test_conv_instance_norm_act_forward(case, dt):
     xh = torch.full((B, Ho, Wo, Cop), 7.0, device='cuda', dtype=TORCH_DT[dt])
     sums = torch.zeros((B, Cop, 2), device='cuda')
     sync = torch.zeros(4, device='cuda', dtype=torch.int32)
-    fn = fused(L.FUSED_FWD, act, sums=sums.data_ptr(), sync=sync.data_ptr(), xhat=xh.data_ptr(), xhat_ld=Cop)
+    kw = {}
+    if dt == L.DT_BF16:      # with a scratch buffer the small-map cases take the split-K route, without it they split N
+        ws = torch.empty(8 << 20, device='cuda', dtype=torch.uint8)
+        kw = dict(ws=ws.data_ptr(), ws_bytes=ws.numel())
+    fn = fused(L.FUSED_FWD, act, sums=sums.data_ptr(), sync=sync.data_ptr(), xhat=xh.data_ptr(), xhat_ld=Cop, **kw)
     assert supported(d, fn, True)
     L.call('pg_conv_norm_fwd', ctypes.byref(d), x1d.data_ptr(), x2d.data_ptr() if C2 else None, wd.data_ptr(),
            out.data_ptr(), twin.data_ptr(), ctypes.byref(fn), stream())
@@ -151,6 +155,11 @@ def test_fused_forward_dropout_matches_the_separate_kernel_mask():
 # on an H x W input (data-gradient in PG_CONVT form), 'convT' = ConvTranspose2d(Cin + Cskip -> Cout) on an H x W input
 # (data-gradient in PG_CONV form; only the first Cin channels of its input come from the normalised block).
 # via: what the block's forward saved -- 'y' (output, invertible activation) or 'xhat'.
+@pytest.fixture(params=[False, True], ids=['nsplit', 'ksplit'])
+def scratch(request):
+    return torch.empty(8 << 20, device='cuda', dtype=torch.uint8) if request.param else None
+
+
 BWD_CASES = [
     ('conv', 2, 32, 0, 64, 32, 32, 'leakyrelu', True, 'y'),
     ('conv', 3, 64, 0, 64, 8, 8, 'relu', True, 'xhat'),
@@ -165,7 +174,7 @@ BWD_CASES = [
 
 
 @pytest.mark.parametrize('case', BWD_CASES, ids=[str(c) for c in BWD_CASES])
-def test_conv_dgrad_instance_norm_backward(case):
+def test_conv_dgrad_instance_norm_backward(case, scratch):
     form, B, Ci, Cs, Co, H, W, act, with_skip, via = case
     fdt = L.DT_F16
     r = rng(13)
@@ -207,6 +216,8 @@ def test_conv_dgrad_instance_norm_backward(case):
     dsk = to_nhwc(dskip) if with_skip else None
     if with_skip:
         kw.update(dskip=dsk.data_ptr(), dskip_ld=Ci)
+    if scratch is not None:
+        kw.update(ws=scratch.data_ptr(), ws_bytes=scratch.numel())
     fn = fused(L.FUSED_BWD, act, **kw)
     assert supported(d, fn, False)
     dx = torch.full((B, H, W, Cit), 7.0, device='cuda', dtype=torch.bfloat16)

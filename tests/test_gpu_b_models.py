@@ -19,7 +19,8 @@ GRAD_TOL_GATED = 8e-2   # same, LeakyReLU / ReLU generators (gate flips; reasoni
 
 
 def quant_kwargs():
-    return dict(fwd=orc.round_f16 if Config.fwd_dt == L.DT_F16 else orc.round_bf16, grad=orc.round_bf16)
+    return dict(fwd=orc.round_f16 if Config.fwd_dt == L.DT_F16 else orc.round_bf16, grad=orc.round_bf16,
+                fused=Config.fused_fwd and Config.fused_bwd)
 
 
 def load(module, oparams):

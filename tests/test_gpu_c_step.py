@@ -39,7 +39,8 @@ FLIP_FRAC = 0.05
 
 
 def quant_kwargs():
-    return dict(fwd=orc.round_f16 if Config.fwd_dt == L.DT_F16 else orc.round_bf16, grad=orc.round_bf16)
+    return dict(fwd=orc.round_f16 if Config.fwd_dt == L.DT_F16 else orc.round_bf16, grad=orc.round_bf16,
+                fused=Config.fused_fwd and Config.fused_bwd)
 
 
 def build(gk, dk, loss_type, tmp_path, gseed=11, dseed=12):

@@ -31,6 +31,8 @@ lib = L.lib()
 
 def stamper(name, args):
     stream = args[-1]
+    if not isinstance(stream, ctypes.c_void_p):
+        return                      # not a stream call
     sid = stream.value if isinstance(stream, ctypes.c_void_p) else int(stream or 0)
     idx = len(names) % 4096
     d = getattr(args[0], '_obj', None) if args else None
