@@ -213,6 +213,21 @@ int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg
  * reference layout (Cout, Cin, 4, 4) of every layer of a network in one launch. */
 int pg_conv_wgrad_tapmajor(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* S, int32_t Ns, int32_t Cs,
                            int impl, void* stream);
+/* A list of weight gradients in ONE launch (tcgen05 only): the generator's backward has ~20 of them, each too small to
+ * fill the GPU and too short to overlap its own phases.  Every job is one pg_conv_wgrad (tap_major = 0: dw / ld_n as
+ * there) or pg_conv_wgrad_tapmajor (tap_major = 1: dw = S, ld_n = Ns, Cs) call; at most 24 jobs per launch.  All operands
+ * must be ready on `stream`. */
+typedef struct PgWgradJob {
+  PgConvDesc desc;
+  const void* a;
+  const void* g;
+  int32_t ldg;
+  int32_t tap_major;
+  float* dw;
+  int32_t ld_n, n_real, c_real, Cs;
+} PgWgradJob;
+int pg_conv_wgrad_group(const PgWgradJob* jobs, int32_t njobs, void* stream);
+
 typedef struct PgGradJob {
   const float* S;      /* [16][Ns][Cs] */
   float* dst;          /* dst[n*ld_n + c*16 + tap] = S[tap][n][c], n < N, c < C (overwrites) */
@@ -237,6 +252,14 @@ int pg_taps_scatter(int32_t mode, int32_t stride, int32_t pad, int32_t B, int32_
 /* element `ch` of the 16-bit src [B,Hp,Wp,lds] -> G [B,Hq,Wq,16] of the same 16-bit type (zeros where the tap falls outside) */
 int pg_taps_gather(int32_t mode, int32_t stride, int32_t pad, int32_t B, int32_t Hq, int32_t Wq, int32_t Hp, int32_t Wp,
                    const void* src, int32_t lds, int32_t ch, void* G, void* stream);
+
+/* data-gradient of a tap-product layer fused with the backward of the activation in front of it (disc.py:39-46 backward):
+ *   dx[q][c] = (sum_tap G[q][tap] * w16[c][tap]) * act'(y[q][c]),  q < nq, c < C
+ * G: bf16 [nq][16] (pg_taps_gather), w16: bf16 [C][16] (the layer's master weight), y: the activation's saved OUTPUT
+ * (16-bit, pixel stride ldy; NULL: no activation), dx: bf16, pixel stride lddx.  K = 16 per output: HBM-bound on the CUDA
+ * cores (as a tensor-core GEMM it is one MMA per tile in front of a 128 x C epilogue). */
+int pg_taps_dgrad_act(const void* G, const void* w16, void* dx, int32_t lddx, const void* y, int32_t ldy, int32_t y_dtype,
+                      int32_t act, int64_t nq, int32_t C, void* stream);
 
 /* bias gradient: db[n] += sum_m g[m*ldg + n], n < n_real (disc.py:19,45 biases) */
 int pg_colsum(const void* g, int64_t M, int32_t ldg, int32_t n_real, float* db, void* stream);

@@ -37,6 +37,12 @@ class FusedNorm(C.Structure):
 
 FP = C.POINTER(FusedNorm)
 
+
+class WgradJob(C.Structure):
+    """PgWgradJob: one weight gradient of a grouped launch (pg_conv_wgrad_group)."""
+    _fields_ = [('desc', ConvDesc), ('a', vp), ('g', vp), ('ldg', i32), ('tap_major', i32), ('dw', vp), ('ld_n', i32),
+                ('n_real', i32), ('c_real', i32), ('Cs', i32)]
+
 _SIGS = {
     'pg_version': ([], C.c_int),
     'pg_tcgen05_available': ([], C.c_int),
@@ -54,10 +60,12 @@ _SIGS = {
     'pg_conv_norm_fwd': ([DP, vp, vp, vp, vp, vp, FP, vp], C.c_int),
     'pg_conv_dgrad_norm_bwd': ([DP, vp, vp, vp, FP, vp], C.c_int),
     'pg_conv_wgrad': ([DP, vp, vp, i32, vp, i32, i32, i32, C.c_int, vp], C.c_int),
+    'pg_conv_wgrad_group': ([C.POINTER(WgradJob), i32, vp], C.c_int),
     'pg_conv_wgrad_tapmajor': ([DP, vp, vp, i32, vp, i32, i32, C.c_int, vp], C.c_int),
     'pg_grad_finalize_multi': ([vp, i32, i32, vp], C.c_int),
     'pg_colsum': ([vp, i64, i32, i32, vp, vp], C.c_int),
     'pg_taps_scatter': ([i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, vp, i32, vp, i32, i32, i32, vp], C.c_int),
+    'pg_taps_dgrad_act': ([vp, vp, vp, i32, vp, i32, i32, i32, i64, i32, vp], C.c_int),
     'pg_taps_gather': ([i32, i32, i32, i32, i32, i32, i32, i32, vp, i32, i32, vp, vp], C.c_int),
     'pg_pack_nchw_f32_to_nhwc_bf16': ([vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], C.c_int),
     'pg_unpack_nhwc_to_nchw_f32': ([vp, i32, vp, i32, i32, i32, i32, i32, i32, vp], C.c_int),

@@ -46,6 +46,7 @@ bool conv_fwd_tc_stats_ok(const PgConvDesc*);
 bool conv_fwd_tc_supported(const PgConvDesc*, const void*, const void*, const void*, const void*);
 int conv_wgrad_tc(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, int, int, cudaStream_t);
 bool conv_wgrad_tc_supported(const PgConvDesc*, const void*, const void*, int);
+int conv_wgrad_group_tc(const PgWgradJob*, int, cudaStream_t);
 bool tc_device_ok();
 bool conv_res_supported(const PgConvDesc*, const PgFusedNorm*, bool);
 int conv_res_launch(const PgConvDesc*, const void*, const void*, const void*, void*, void*, const PgFusedNorm*, cudaStream_t);
@@ -59,6 +60,7 @@ bool conv_fewin_supported(const PgConvDesc*);
 int conv_fewin(const PgConvDesc*, const void*, const void*, void*, void*, cudaStream_t);
 int taps_scatter(int, int, int, int, int, int, int, int, const float*, int, const float*, int, void*, int, int, int, cudaStream_t);
 int taps_gather(int, int, int, int, int, int, int, int, const void*, int, int, void*, cudaStream_t);
+int taps_dgrad_act(const void*, const void*, void*, int, const void*, int, int, int, long long, int, cudaStream_t);
 bool conv_wgrad1_supported(const PgConvDesc*, int, const float*, int, int, int);
 int conv_wgrad1(const PgConvDesc*, const void*, const void*, int, float*, int, int, int, cudaStream_t);
 
@@ -276,6 +278,16 @@ extern "C" int pg_taps_gather(int32_t mode, int32_t stride, int32_t pad, int32_t
   return taps_gather(mode, stride, pad, B, Hq, Wq, Hp, Wp, src, lds, ch, G, (cudaStream_t)stream);
 }
 
+extern "C" int pg_taps_dgrad_act(const void* G, const void* w16, void* dx, int32_t lddx, const void* y, int32_t ldy, int32_t y_dtype,
+                                 int32_t act, int64_t nq, int32_t C, void* stream) {
+  PG_REQUIRE(G && w16 && dx && nq > 0, "pg_taps_dgrad_act: NULL pointer / empty");
+  PG_REQUIRE(C >= 2 && C % 2 == 0 && C <= 1024 && lddx >= C && lddx % 2 == 0, "pg_taps_dgrad_act: C=%d must be even, <= 1024, lddx >= C", C);
+  PG_REQUIRE((((uintptr_t)G) & 15) == 0 && (((uintptr_t)dx) & 3) == 0, "pg_taps_dgrad_act: G must be 16-byte, dx 4-byte aligned");
+  PG_REQUIRE(y == nullptr || ((y_dtype == PG_BF16 || y_dtype == PG_F16) && ldy >= C && ldy % 2 == 0 && (((uintptr_t)y) & 3) == 0),
+             "pg_taps_dgrad_act: bad y");
+  return taps_dgrad_act(G, w16, dx, lddx, y, ldy, y_dtype, act, nq, C, (cudaStream_t)stream);
+}
+
 static int conv_wgrad_any(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw, int32_t ld_n,
                           int32_t n_real, int32_t c_real, int tap_major, int Cs, int impl, void* stream) {
   if (int e = validate(d, "pg_conv_wgrad")) return e;
@@ -308,6 +320,22 @@ static int conv_wgrad_any(const PgConvDesc* d, const void* a, const void* g, int
 extern "C" int pg_conv_wgrad(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* dw, int32_t ld_n,
                              int32_t n_real, int32_t c_real, int impl, void* stream) {
   return conv_wgrad_any(d, a, g, ldg, dw, ld_n, n_real, c_real, 0, 0, impl, stream);
+}
+
+extern "C" int pg_conv_wgrad_group(const PgWgradJob* jobs, int32_t njobs, void* stream) {
+  PG_REQUIRE(jobs != nullptr && njobs > 0, "pg_conv_wgrad_group: no jobs");
+  for (int j = 0; j < njobs; ++j) {
+    const PgWgradJob& jb = jobs[j];
+    if (int e = validate(&jb.desc, "pg_conv_wgrad_group")) return e;
+    PG_REQUIRE((jb.desc.mode == PG_CONV || jb.desc.mode == PG_CONV1X1) && jb.desc.C2 == 0,
+               "pg_conv_wgrad_group: job %d: geometry must be PG_CONV / PG_CONV1X1 with one source", j);
+    PG_REQUIRE(jb.a && jb.g && jb.dw && jb.ldg >= jb.desc.N && jb.ldg % 8 == 0, "pg_conv_wgrad_group: job %d: bad pointers / ldg", j);
+    PG_REQUIRE(jb.n_real <= jb.desc.N && jb.c_real <= jb.desc.C1, "pg_conv_wgrad_group: job %d: n_real / c_real exceed padded extents", j);
+    PG_REQUIRE(!jb.tap_major || (jb.desc.mode == PG_CONV && jb.Cs % 4 == 0), "pg_conv_wgrad_group: job %d: bad tap-major job", j);
+    PG_REQUIRE(conv_wgrad_tc_supported(&jb.desc, jb.a, jb.g, jb.ldg), "pg_conv_wgrad_group: job %d has no tcgen05 plan", j);
+  }
+  g_last_impl = PG_IMPL_TCGEN05;
+  return conv_wgrad_group_tc(jobs, njobs, (cudaStream_t)stream);
 }
 
 extern "C" int pg_conv_wgrad_tapmajor(const PgConvDesc* d, const void* a, const void* g, int32_t ldg, float* S, int32_t Ns,

@@ -585,4 +585,74 @@ int taps_gather(int mode, int stride, int pad, int B, int Hq, int Wq, int Hp, in
   return check_launch("taps_gather_kernel");
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Data-gradient of a tap-product layer (one real output channel; disc.py:45 backward), fused with the backward of the
+// activation in front of it:   dx[q][c] = (sum_tap G[q][tap] * W[c][tap]) * act'(y[q][c])
+// K = 16 and N = 8*ndf = 512: as a tcgen05 GEMM this is one MMA per tile in front of a 128 x 512 epilogue (60-70 us for
+// cfg 3's 30 k pixels); it is a 16-term dot product per output, HBM-bound on the CUDA cores (read y, write dx).
+// A thread owns TWO adjacent channels (weights in registers) and walks the pixels; the pixel's 16 taps come from shared
+// memory as broadcasts; consecutive threads write consecutive channel pairs (coalesced 4-byte stores).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TD_PX = 32;     // pixels staged per block iteration
+
+__global__ void __launch_bounds__(512) taps_dgrad_act_kernel(const bf16* __restrict__ G, const bf16* __restrict__ w16,
+                                                             const unsigned short* __restrict__ y, int ldy, int y_dt, int act,
+                                                             bf16* __restrict__ dx, int lddx, long long nq, int C) {
+  __shared__ float Gs[TD_PX][16];
+  const int c = 2 * threadIdx.x;
+  const bool live = c < C;
+  float w0[16], w1[16];
+#pragma unroll
+  for (int t = 0; t < 16; ++t) {
+    w0[t] = live ? __bfloat162float(w16[(long long)c * 16 + t]) : 0.f;
+    w1[t] = live ? __bfloat162float(w16[(long long)(c + 1) * 16 + t]) : 0.f;
+  }
+  for (long long q0 = (long long)blockIdx.x * TD_PX; q0 < nq; q0 += (long long)gridDim.x * TD_PX) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < TD_PX * 2; i += blockDim.x) {      // 2 loads per pixel, 8 taps (16 bytes) each
+      const int pxl = i >> 1, half = i & 1;
+      float f[8];
+      if (q0 + pxl < nq) {
+        unpack8(*reinterpret_cast<const uint4*>(G + (q0 + pxl) * 16 + half * 8), f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) Gs[pxl][half * 8 + j] = f[j];
+    }
+    __syncthreads();
+    if (!live) continue;
+    const int npx = nq - q0 < TD_PX ? (int)(nq - q0) : TD_PX;
+    for (int pxl = 0; pxl < npx; ++pxl) {
+      const float4* g4 = reinterpret_cast<const float4*>(Gs[pxl]);
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 gv = g4[j];
+        a0 = fmaf(gv.x, w0[4 * j], a0); a0 = fmaf(gv.y, w0[4 * j + 1], a0); a0 = fmaf(gv.z, w0[4 * j + 2], a0); a0 = fmaf(gv.w, w0[4 * j + 3], a0);
+        a1 = fmaf(gv.x, w1[4 * j], a1); a1 = fmaf(gv.y, w1[4 * j + 1], a1); a1 = fmaf(gv.z, w1[4 * j + 2], a1); a1 = fmaf(gv.w, w1[4 * j + 3], a1);
+      }
+      const long long q = q0 + pxl;
+      if (y != nullptr) {
+        const unsigned yy = *reinterpret_cast<const unsigned*>(y + q * ldy + c);
+        a0 *= act_grad_from_output(act, from16((unsigned short)(yy & 0xffffu), y_dt));
+        a1 *= act_grad_from_output(act, from16((unsigned short)(yy >> 16), y_dt));
+      }
+      *reinterpret_cast<__nv_bfloat162*>(dx + q * lddx + c) = __floats2bfloat162_rn(a0, a1);
+    }
+  }
+}
+
+int taps_dgrad_act(const void* G, const void* w16, void* dx, int lddx, const void* y, int ldy, int y_dt, int act, long long nq, int C,
+                   cudaStream_t stream) {
+  const int threads = ((C / 2 + 31) / 32) * 32;
+  long long blocks = (nq + TD_PX - 1) / TD_PX;
+  const long long cap = 2LL * num_sms();          // two blocks per SM walk the pixels (the weights are loaded once per block)
+  if (blocks > cap) blocks = cap;
+  taps_dgrad_act_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const bf16*)G, (const bf16*)w16, (const unsigned short*)y, ldy,
+                                                                y_dt, act, (bf16*)dx, lddx, nq, C);
+  return check_launch("taps_dgrad_act_kernel");
+}
+
 }  // namespace pg

@@ -1503,9 +1503,10 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
                : "memory");
 }
 
-__global__ void __launch_bounds__(TC_THREADS, 2)
-wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ ActMaps mapsA,
-                const __grid_constant__ CUtensorMap mapS, const WgParams p) {
+// The kernel body: one CTA = (n-tile bx, (channel tile, tap group) by, pixel-tile split bz) of ONE weight gradient.
+// Called by wgrad_tc_kernel (one weight gradient per launch) and wgrad_group_kernel (many per launch).
+__device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtensorMap* mapsA, const CUtensorMap* mapS,
+                                           const WgParams& p, int bx, int by, int bz) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t gfull[WG_MAX_G], gempty[WG_MAX_G], afull[WG_MAX_A], aempty[WG_MAX_A];
   __shared__ __align__(8) uint64_t acc_bar;
@@ -1516,12 +1517,12 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
   const uint32_t g_base = smem_base;
   const uint32_t a_base = smem_base + p.g_stages * p.g_stage_bytes;
 
-  const int n0 = blockIdx.x * 128;
-  const int ctile = blockIdx.y % p.ctiles;
-  const int tgrp = blockIdx.y / p.ctiles;
+  const int n0 = bx * 128;
+  const int ctile = by % p.ctiles;
+  const int tgrp = by / p.ctiles;
   const int c0 = ctile * p.ct;
   const int t0 = tgrp * p.T;
-  const int tile_beg = blockIdx.z * p.tiles_per_split;
+  const int tile_beg = bz * p.tiles_per_split;
   int tile_end = tile_beg + p.tiles_per_split;
   if (tile_end > p.total_tiles) tile_end = p.total_tiles;
   const int ntiles = tile_end > tile_beg ? tile_end - tile_beg : 0;
@@ -1533,8 +1534,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
   }
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&mapG);
-    prefetch_tmap(&mapsA.m[0]);
+    prefetch_tmap(mapG);
+    prefetch_tmap(&mapsA[0]);
     for (int s = 0; s < p.g_stages; ++s) { mbar_init(smem_u32(&gfull[s]), 1); mbar_init(smem_u32(&gempty[s]), 1); }
     for (int s = 0; s < p.a_stages; ++s) { mbar_init(smem_u32(&afull[s]), 1); mbar_init(smem_u32(&aempty[s]), 1); }
     mbar_init(smem_u32(&acc_bar), 1);
@@ -1560,7 +1561,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
         const uint32_t gb = smem_u32(&gfull[gs]);
         mbar_expect_tx(gb, p.n_atoms_load * p.g_boxbytes);
         for (int a = 0; a < p.n_atoms_load; ++a)
-          tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, &mapG, gb, n0 + a * p.g_box, x0, y0, b0);
+          tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, mapG, gb, n0 + a * p.g_box, x0, y0, b0);
         if (++gs == p.g_stages) { gs = 0; gph ^= 1; }
         for (int tl = 0; tl < p.T; ++tl) {
           const int t = t0 + tl, kh = t >> 2, kw = t & 3;
@@ -1576,7 +1577,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
             cy = y0 + (u >> 1);
           }
           for (int a = 0; a < p.c_atoms; ++a)
-            tma_load_4d(a_base + as * p.a_stage_bytes + a * p.a_boxbytes, &mapsA.m[ph], ab, c0 + a * p.a_box, cx, cy, b0);
+            tma_load_4d(a_base + as * p.a_stage_bytes + a * p.a_boxbytes, &mapsA[ph], ab, c0 + a * p.a_box, cx, cy, b0);
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
       }
@@ -1656,7 +1657,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
           fence_proxy_async();
           epi_bar_sync();
           if (et == 0) {
-            tma_reduce_add_3d(&mapS, smem_base + (uint32_t)buf * bufbytes, c0 + cc, n0, t0 + tl);
+            tma_reduce_add_3d(mapS, smem_base + (uint32_t)buf * bufbytes, c0 + cc, n0, t0 + tl);
             bulk_commit();
           }
         }
@@ -1728,10 +1729,45 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
   if (threadIdx.x == 0 && p.trace != nullptr) trace_raw(p.trace, 6, gtimer());
 }
 
+__global__ void __launch_bounds__(TC_THREADS, 2)
+wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ ActMaps mapsA,
+                const __grid_constant__ CUtensorMap mapS, const WgParams p) {
+  wgrad_body(&mapG, mapsA.m, &mapS, p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+
+// Many weight gradients in ONE launch.  The generator's backward has ~20 of them (14 layers, two sources per decoder
+// layer), each a 10-20 us launch of a few hundred short CTAs whose phases (setup, one TMA round trip, a few MMAs, the
+// reduce-add epilogue) barely overlap -- and while the one-CTA-per-SM convolution kernels run nothing else does, so
+// they only took turns with the data-gradient chain.  Here every job keeps its own tensor maps and parameters (the whole
+// table is a kernel parameter, 1 KB per job); CTAs of different jobs share the SMs, so one job's epilogue runs under
+// another's loads.
+constexpr int WG_GROUP_MAX = 24;
+struct __align__(64) WgJobDev {
+  CUtensorMap mapG;
+  CUtensorMap mapA[4];
+  CUtensorMap mapS;
+  WgParams p;
+  int gx, gy, gz, pad0;
+};
+struct __align__(64) WgGroupArgs {
+  int njobs;
+  int cta_begin[WG_GROUP_MAX + 1];
+  WgJobDev jobs[WG_GROUP_MAX];
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2) wgrad_group_kernel(const __grid_constant__ WgGroupArgs g) {
+  int j = 0;
+  while (j + 1 < g.njobs && (int)blockIdx.x >= g.cta_begin[j + 1]) ++j;
+  const WgJobDev& jb = g.jobs[j];
+  const int local = (int)blockIdx.x - g.cta_begin[j];
+  const int bx = local % jb.gx, r = local / jb.gx;
+  wgrad_body(&jb.mapG, jb.mapA, &jb.mapS, jb.p, bx, r % jb.gy, r / jb.gy);
+}
+
 static int box_of(int ch) { return ch >= 64 ? 64 : (ch >= 32 ? 32 : 16); }
 static uint32_t layout_of(int rowbytes) { return rowbytes == 128 ? 2u : (rowbytes == 64 ? 4u : 6u); }
 
-static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& smem) {
+static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& smem, int split_cap = 0) {
   memset(&p, 0, sizeof(p));
   if ((d->mode != PG_CONV && d->mode != PG_CONV1X1) || d->C2 != 0) return false;
   p.pointwise = d->mode == PG_CONV1X1 ? 1 : 0;
@@ -1758,8 +1794,16 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   p.g_boxbytes = WG_KP * p.g_rowbytes; p.a_boxbytes = WG_KP * p.a_rowbytes;
   p.g_stage_bytes = (p.n_atoms * p.g_boxbytes + 1023u) & ~1023u;
   p.a_stage_bytes = (p.c_atoms * p.a_boxbytes + 1023u) & ~1023u;
-  p.g_stages = 2;
-  int as = (int)((110u * 1024u - p.g_stages * p.g_stage_bytes) / p.a_stage_bytes);
+  // Both rings are TMA-latency-bound (a box takes ~2 us to land): the pixel-tile (G) ring is as deep as shared memory allows
+  // while the tap ring keeps at least T + 2 slots (one tile's taps plus a head start on the next), at most 4 / 12 slots.
+  static const int gst_env = [] { const char* e = getenv("PG_WG_GSTAGES"); return e ? atoi(e) : WG_MAX_G; }();
+  int gst = gst_env < 2 ? 2 : (gst_env > WG_MAX_G ? WG_MAX_G : gst_env);
+  int as = 0;
+  for (;; --gst) {
+    as = (int)((110u * 1024u - (uint32_t)gst * p.g_stage_bytes) / p.a_stage_bytes);
+    if (as >= p.T + 2 || gst == 2) break;
+  }
+  p.g_stages = gst;
   if (as > WG_MAX_A) as = WG_MAX_A;
   if (as < 2) return false;
   p.a_stages = as;
@@ -1782,6 +1826,7 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   int splits = split_ceil ? (2 * num_sms() + gx * gy - 1) / (gx * gy) : (2 * num_sms()) / (gx * gy);
   const int max_splits = p.total_tiles / 8 > 0 ? p.total_tiles / 8 : 1;
   if (splits > max_splits) splits = max_splits;
+  if (split_cap > 0 && splits > split_cap) splits = split_cap;
   if (splits > p.total_tiles) splits = p.total_tiles;
   if (splits < 1) splits = 1;
   p.tiles_per_split = (p.total_tiles + splits - 1) / splits;
@@ -1800,11 +1845,20 @@ bool conv_wgrad_tc_supported(const PgConvDesc* d, const void* a, const void* g, 
   return make_wg_plan(d, p, grid, smem);
 }
 
+// Everything a launch of one weight gradient needs: plan, parameters, tensor maps.
+struct WgPrepared {
+  WgParams p;
+  dim3 grid;
+  size_t smem;
+  CUtensorMap mG, mS;
+  ActMaps mA;
+};
+
 // tap_major != 0: dw is S[16][Ns = ld_n][Cs = c_stride] (fp32, zeroed by the caller); else the reference layout
-int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, float* dw, int ld_n, int n_real,
-                  int c_real, int tap_major, int Cs, cudaStream_t stream) {
-  WgParams p; dim3 grid; size_t smem;
-  if (!make_wg_plan(d, p, grid, smem)) {
+static int wg_prepare(const PgConvDesc* d, const void* a, const void* g, int ldg, float* dw, int ld_n, int n_real, int c_real,
+                      int tap_major, int Cs, int split_cap, WgPrepared& w) {
+  WgParams& p = w.p;
+  if (!make_wg_plan(d, p, w.grid, w.smem, split_cap)) {
     set_error("conv_wgrad_tc: unsupported shape");
     return PG_ERR_UNSUPPORTED;
   }
@@ -1812,8 +1866,7 @@ int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, fl
     set_error("conv_wgrad_tc: dw must be 16-byte aligned with ld_n %% 4 == 0");
     return PG_ERR_UNSUPPORTED;
   }
-  CUtensorMap mS;
-  memset(&mS, 0, sizeof(mS));
+  memset(&w.mS, 0, sizeof(w.mS));
   p.tapmajor = 0;
   if (tap_major) {
     if (p.pointwise || (((uintptr_t)dw) & 15) != 0 || (Cs % 4) != 0 || Cs < c_real || ld_n < n_real) {
@@ -1826,7 +1879,7 @@ int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, fl
     cuuint64_t strides[2] = {(cuuint64_t)Cs * 4, (cuuint64_t)Cs * ld_n * 4};
     cuuint32_t box[3] = {(cuuint32_t)(p.st_rowbytes / 4), 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = get_encode()(&mS, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dw, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = get_encode()(&w.mS, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, dw, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                               p.st_rowbytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -1838,26 +1891,78 @@ int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, fl
   p.trace = g_trace;
   static const bool wdbg = getenv("PG_TC_DEBUG") != nullptr;
   if (wdbg)
-    fprintf(stderr, "wgrad_tc: grid (%u,%u,%u) T %d ct %d tiles %d per-split %d g_stages %d a_stages %d smem %zu tmem %u\n", grid.x,
-            grid.y, grid.z, p.T, p.ct, p.total_tiles, p.tiles_per_split, p.g_stages, p.a_stages, smem, p.tmem_cols);
-  CUtensorMap mG;
-  ActMaps mA;
-  memset(&mA, 0, sizeof(mA));
-  if (int e = encode_act_map(&mG, g, d->N, ldg, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, -1, p.g_rowbytes,
+    fprintf(stderr, "wgrad_tc: grid (%u,%u,%u) T %d ct %d tiles %d per-split %d g_stages %d a_stages %d smem %zu tmem %u\n", w.grid.x,
+            w.grid.y, w.grid.z, p.T, p.ct, p.total_tiles, p.tiles_per_split, p.g_stages, p.a_stages, w.smem, p.tmem_cols);
+  memset(&w.mA, 0, sizeof(w.mA));
+  if (int e = encode_act_map(&w.mG, g, d->N, ldg, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, -1, p.g_rowbytes,
                              d->out_f32))
     return e;
   const bool phased = !p.pointwise && d->stride == 2;
   for (int ph = 0; ph < (phased ? 4 : 1); ++ph)
-    if (int e = encode_act_map(&mA.m[ph], a, d->C1, d->ld1, d->B, d->Hin, d->Win, p.a_box, p.TW, p.TH, p.TB,
+    if (int e = encode_act_map(&w.mA.m[ph], a, d->C1, d->ld1, d->B, d->Hin, d->Win, p.a_box, p.TW, p.TH, p.TB,
                                phased ? ph : -1, p.a_rowbytes, d->in_dtype))
       return e;
+  return PG_OK;
+}
+
+int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, float* dw, int ld_n, int n_real,
+                  int c_real, int tap_major, int Cs, cudaStream_t stream) {
+  WgPrepared w;
+  if (int e = wg_prepare(d, a, g, ldg, dw, ld_n, n_real, c_real, tap_major, Cs, 0, w)) return e;
   static bool smem_set = false;
   if (!smem_set) {
     PG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
     smem_set = true;
   }
-  wgrad_tc_kernel<<<grid, TC_THREADS, smem, stream>>>(mG, mA, mS, p);
+  wgrad_tc_kernel<<<w.grid, TC_THREADS, w.smem, stream>>>(w.mG, w.mA, w.mS, w.p);
   return check_launch("wgrad_tc_kernel");
+}
+
+// One launch for a list of weight gradients (see wgrad_group_kernel).  The pixel-tile splits of every job are capped so
+// that the whole group is a few waves of the 2 x #SM resident CTAs: a job no longer has to fill the GPU by itself.
+int conv_wgrad_group_tc(const PgWgradJob* jobs, int njobs, cudaStream_t stream) {
+  if (njobs < 1 || njobs > WG_GROUP_MAX) {
+    set_error("conv_wgrad_group_tc: 1..%d jobs per launch, got %d", WG_GROUP_MAX, njobs);
+    return PG_ERR_INVALID;
+  }
+  static WgGroupArgs args;         // (32 KB: not on the stack; launches are serialised by the caller's thread)
+  static WgPrepared w;
+  const int cap = (3 * 2 * num_sms() + njobs - 1) / njobs;       // ~3 waves in total
+  size_t smem = 0;
+  int total = 0;
+  for (int j = 0; j < njobs; ++j) {
+    const PgWgradJob& jb = jobs[j];
+    // splits such that this job contributes at most `cap` CTAs
+    WgParams probe; dim3 g0; size_t s0;
+    if (!make_wg_plan(&jb.desc, probe, g0, s0, 0)) {
+      set_error("conv_wgrad_group_tc: job %d: unsupported shape", j);
+      return PG_ERR_UNSUPPORTED;
+    }
+    int split_cap = cap / (int)(g0.x * g0.y);
+    if (split_cap < 1) split_cap = 1;
+    if (int e = wg_prepare(&jb.desc, jb.a, jb.g, jb.ldg, jb.dw, jb.ld_n, jb.n_real, jb.c_real, jb.tap_major, jb.Cs, split_cap, w))
+      return e;
+    WgJobDev& dst = args.jobs[j];
+    dst.mapG = w.mG;
+    for (int ph = 0; ph < 4; ++ph) dst.mapA[ph] = w.mA.m[ph];
+    dst.mapS = w.mS;
+    dst.p = w.p;
+    dst.gx = (int)w.grid.x; dst.gy = (int)w.grid.y; dst.gz = (int)w.grid.z;
+    args.cta_begin[j] = total;
+    total += (int)(w.grid.x * w.grid.y * w.grid.z);
+    if (w.smem > smem) smem = w.smem;
+  }
+  args.njobs = njobs;
+  args.cta_begin[njobs] = total;
+  static bool smem_set = false;
+  if (!smem_set) {
+    PG_CUDA(cudaFuncSetAttribute(wgrad_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
+    smem_set = true;
+  }
+  static const bool wdbg = getenv("PG_TC_DEBUG") != nullptr;
+  if (wdbg) fprintf(stderr, "wgrad_group: %d jobs, %d CTAs, smem %zu\n", njobs, total, smem);
+  wgrad_group_kernel<<<total, TC_THREADS, smem, stream>>>(args);
+  return check_launch("wgrad_group_kernel");
 }
 
 #include "conv_res.cuh"

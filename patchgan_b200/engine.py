@@ -213,6 +213,8 @@ class Config:
     # fused into the data-gradient convolution that feeds it (0 = separate statistics / apply / backward kernels)
     fused_fwd = os.environ.get('PATCHGAN_B200_FUSED_FWD', '1') != '0'
     fused_bwd = os.environ.get('PATCHGAN_B200_FUSED_BWD', '1') != '0'
+    # the generator's ~20 weight-gradients as grouped launches (pg_conv_wgrad_group) instead of one launch each
+    group_wgrad = os.environ.get('PATCHGAN_B200_GROUP_WGRAD', '1') != '0'
 
 
 def conv_flops(desc):
@@ -443,6 +445,12 @@ def taps_gather(mode, stride, pad, dy, ch, B, Hq, Wq):
 
 def taps_dgrad(G, w16, out, y=None, act=0):
     """out[q][c] = sum_tap G[q][tap] * w16[c][tap]   (w16: bf16 [C][16]);  with y: times act'(y) (fused activation backward)"""
+    if out.C % 2 == 0 and out.C <= 1024:
+        # 16 FMAs per output: a CUDA-core streaming kernel (as a GEMM it would be K = 16 in front of a C-wide epilogue)
+        L.call('pg_taps_dgrad_act', G.ptr, w16.data_ptr(), out.ptr, out.ld, y.ptr if y is not None else None,
+               y.ld if y is not None else 0, y.dt if y is not None else 0, act if y is not None else 0,
+               G.B * G.H * G.W, out.C, _stream())
+        return
     d = conv_desc(L.PG_CONV1X1, 1, 0, G.B, G.H, G.W, G.H, G.W, 16, 0, 16, 0, out.C, out.ld, act=act if y is not None else 0)
     if y is not None:
         run_conv_dgrad_act(d, G, w16, out, y)
@@ -450,10 +458,10 @@ def taps_dgrad(G, w16, out, y=None, act=0):
         run_conv(d, G, None, w16, None, out)
 
 
-def taps_wgrad(G, x, dw_ptr, c_real, wstream=None):
-    """dw[c*16 + tap] += sum_q x[q][c] * G[q][tap]"""
+def taps_wgrad(G, x, dw_ptr, c_real, wstream=None, eng=None):
+    """dw[c*16 + tap] += sum_q x[q][c] * G[q][tap]   (eng: the network engine, when its weight-gradients are grouped)"""
     d = conv_desc(L.PG_CONV1X1, 1, 0, G.B, G.H, G.W, G.H, G.W, x.C, 0, x.ld, 0, 16, 16, out_dt=BF16, in_dt=BF16, ldw=16)
-    run_wgrad(d, x, G, dw_ptr, 1, 16, c_real, wstream)
+    (eng.wgrad_direct if eng is not None else run_wgrad)(d, x, G, dw_ptr, 1, 16, c_real, wstream)
 
 
 
@@ -487,10 +495,10 @@ def first_conv(a, w_first, bias, act, out, n_valid, stats=None):
              w_first, bias, out, stats)
 
 
-def first_wgrad(a, g, dw_ptr, n_real, wstream=None):
+def first_wgrad(a, g, dw_ptr, n_real, wstream=None, eng=None):
     """dW[n][c][tap] += sum_o g[o][n] * A[o][c*16 + tap]: lands in the reference (Cout, Cin, 4, 4) layout."""
     d = conv_desc(L.PG_CONV1X1, 1, 0, a.B, a.H, a.W, a.H, a.W, a.C, 0, a.ld, 0, g.C, g.C, out_dt=BF16, in_dt=BF16, ldw=1)
-    run_wgrad(d, a.b16, g, dw_ptr, a.C, n_real, a.C, wstream)
+    (eng.wgrad_direct if eng is not None else run_wgrad)(d, a.b16, g, dw_ptr, a.C, n_real, a.C, wstream)
 
 
 
@@ -639,11 +647,13 @@ class NetEngine:
     GRAD_JOB_DT = np.dtype([('S', '<u8'), ('dst', '<u8'), ('ld_n', '<i8'), ('N', '<i4'), ('C', '<i4'), ('Ns', '<i4'),
                             ('Cs', '<i4'), ('tile_begin', '<i4'), ('ctiles', '<i4')])
 
-    def begin_backward(self):
-        """Start collecting weight-gradient jobs for this backward pass; zero the tap-major scratch."""
+    def begin_backward(self, group=False):
+        """Start collecting weight-gradient jobs for this backward pass; zero the tap-major scratch.
+        group=True: the weight-gradients are not launched one by one but collected and issued by flush_wgrads()."""
         self._tm_jobs = []
         self._tm_done = 0
         self._tm_off = 0
+        self._wg_group = [] if (group and taps_enabled() and Config.group_wgrad) else None
         if taps_enabled():
             if getattr(self, '_tm_buf', None) is None or self._tm_buf.device != self.device():
                 n = sum(p.numel() for p in self.module.parameters())
@@ -665,6 +675,9 @@ class NetEngine:
         self._tm_off = off + need
         sp = self._tm_buf.data_ptr() + off * 4
         jobs.append((sp, dst_ptr, ld_n, n_real, c_real, Ns, Cs))
+        if self._wg_group is not None:
+            self._wg_group.append((desc, a, g, g.ld, 1, sp, Ns, Ns, Cs, Cs))    # (the Acts keep their storage alive)
+            return
         wstream = pick_wstream(wstream)
         if wstream is not None:
             fork(wstream)
@@ -672,6 +685,35 @@ class NetEngine:
             if L.PROFILER is not None:
                 L.PROFILER.note(conv_flops(desc), desc_tag(desc))
             L.call('pg_conv_wgrad_tapmajor', ctypes.byref(desc), a.ptr, g.ptr, g.ld, sp, Ns, Cs, Config.impl, _stream())
+
+    def wgrad_direct(self, desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream=None):
+        """A weight gradient accumulated straight into the reference layout (pointwise layers): grouped or launched now."""
+        if getattr(self, '_wg_group', None) is not None and 'wgrad' not in SKIP:
+            self._wg_group.append((desc, a, g, g.ld, 0, dw_ptr, ld_n, n_real, c_real, 0))
+            return
+        run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream)
+
+    def flush_wgrads(self, wstream=None):
+        """Issue the collected weight-gradients as grouped launches (at most 24 jobs each) on `wstream` (forked here) or the
+        current stream.  Their operands must have been produced on the current stream."""
+        pend = getattr(self, '_wg_group', None)
+        if not pend:
+            return
+        self._wg_group = []
+        wstream = pick_wstream(wstream)
+        if wstream is not None:
+            fork(wstream)
+        with torch.cuda.stream(wstream if wstream is not None else torch.cuda.current_stream()):
+            for i in range(0, len(pend), 24):
+                chunk = pend[i:i + 24]
+                arr = (L.WgradJob * len(chunk))()
+                for j, (desc, a, g, ldg, tm, dw, ld_n, n_real, c_real, Cs) in enumerate(chunk):
+                    ctypes.memmove(ctypes.byref(arr[j].desc), ctypes.byref(desc), ctypes.sizeof(L.ConvDesc))
+                    arr[j].a, arr[j].g, arr[j].ldg, arr[j].tap_major, arr[j].dw = a.ptr, g.ptr, ldg, tm, dw
+                    arr[j].ld_n, arr[j].n_real, arr[j].c_real, arr[j].Cs = ld_n, n_real, c_real, Cs
+                    if L.PROFILER is not None:
+                        L.PROFILER.note(conv_flops(desc), 'group')
+                L.call('pg_conv_wgrad_group', arr, len(chunk), _stream())
 
     def finalize_grads(self, partial=False):
         """Write the tap-major weight-gradients of this backward pass to their reference-layout destinations (one launch).
@@ -937,7 +979,7 @@ class GeneratorEngine(NetEngine):
             _, raw, sums, out, dp, xh = ctx['enc'][j]
             return Block(self.enc[j], raw, sums, out, dp, xh, j)
 
-        self.begin_backward()
+        self.begin_backward(group=True)
         for i in range(6, -1, -1):
             s = self.dec[i]
             src1, src2 = ctx['dec'][i][0], ctx['dec'][i][1]
@@ -948,9 +990,9 @@ class GeneratorEngine(NetEngine):
             if i == 6 and taps_enabled() and pw.taps_ok:
                 # one output channel: tap products (gather dY once, then pointwise GEMMs)
                 G6 = taps_gather(L.PG_CONVT, 2, 1, d_raw, 0, B, src1.H, src1.W)
-                taps_wgrad(G6, src1.b16, g.data_ptr(), s.c1, wstream)
+                taps_wgrad(G6, src1.b16, g.data_ptr(), s.c1, wstream, self)
                 if src2 is not None:
-                    taps_wgrad(G6, src2.b16, g.data_ptr() + s.c1 * 16 * 4, s.c2, wstream)
+                    taps_wgrad(G6, src2.b16, g.data_ptr() + s.c1 * 16 * 4, s.c2, wstream, self)
                 dd = conv_desc(L.PG_CONV1X1, 1, 0, B, G6.H, G6.W, G6.H, G6.W, 16, 0, 16, 0, s.cinp, din.ld)
                 d_raw = dgrad_block_bwd(dd, G6, pw.w16, 16 * 2, din, s.c1p, prod, None, self.seed)
             else:
@@ -976,7 +1018,7 @@ class GeneratorEngine(NetEngine):
             s = self.enc[i]
             h, out = ctx['enc'][i][0], ctx['enc'][i][3]
             if h.im2col:
-                first_wgrad(h, d_raw, grads[s.wname].data_ptr(), s.cout, wstream)
+                first_wgrad(h, d_raw, grads[s.wname].data_ptr(), s.cout, wstream, self)
             else:
                 wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, out.H, out.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
                                in_dt=BF16)
@@ -992,7 +1034,9 @@ class GeneratorEngine(NetEngine):
                     run_conv(dd, d_raw, None, self.packed[i].bwd, None, din)
                     dx = din
             if early is not None and i == early[0]:
+                self.flush_wgrads(wstream)      # the weight-gradients of every layer but encoder 0 .. i-1: one grouped launch
                 early[1]()
+        self.flush_wgrads(wstream)              # the rest (everything, without `early`)
         if wstream is None:
             self.finalize_grads()       # (with a side stream the caller joins it first, then calls finalize_grads)
         return dx if need_dx else None
