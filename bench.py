@@ -49,7 +49,8 @@ def ncu_traffic(kernels):
     best = None
     for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_step_launches.json'))):
         try:
-            ks = [k for k in json.load(open(path))['kernels'] if k['kernel'] in kernels]
+            # (kernel names in the profile keep their template arguments: conv_tc_pers_kernel<0>, conv_res_kernel<1>)
+            ks = [k for k in json.load(open(path))['kernels'] if k['kernel'].split('<')[0] in kernels]
             n = sum(k['launches'] for k in ks)
             if n:
                 tot = sum(k['dram_MB_per_launch'] * 1e6 * k['launches'] for k in ks)
@@ -98,6 +99,12 @@ def cpu_step_rate(cfg, steps, warmup, batch=4):
     return batch / sec, sec
 
 
+def cpu_batch(cfg):
+    """Batch of one CPU step: the configuration's own per-GPU batch at 256 x 256 (a step is well under a second per image on
+    the host), one image at 1024 x 1024 (bounded sample; the workload string of that line says so)."""
+    return cfg['B'] if cfg['S'] <= 256 else 1
+
+
 def run_reference(args, cfg):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -106,13 +113,17 @@ def run_reference(args, cfg):
         print(json.dumps(dict(impl='reference', unavailable='the CPU arm times the training step (cfg3/4/5) only')), flush=True)
         return
     steps, warmup = max(1, min(args.steps, 10)), max(1, min(args.warmup, 2))
-    batch = 4 if cfg['S'] <= 256 else 1
+    batch = cpu_batch(cfg)
+    if cfg['S'] > 256:
+        steps, warmup = min(steps, 3), 1          # a 1024 x 1024 step takes tens of seconds on the host
     rate, sec = cpu_step_rate(cfg, steps, warmup, batch)
     cores = os.cpu_count()
     sample = f'{CPU_SAMPLE}; {warmup} warm-up + {steps} timed step(s) of batch {batch} at {cfg["S"]}x{cfg["S"]}, median'
     line = dict(metric='train_img_per_s', value=round(rate, 3), unit='img/s', n_gpus=args.gpus, steps=steps, warmup=warmup,
                 ms_per_step=round(sec * 1e3, 2), higher_is_better=True, scaling='weak', vs_baseline=None, dtype='f32',
-                data='synthetic', impl='reference', config=dict(workload=cfg['workload'], cpu_batch=batch),
+                data='synthetic', impl='reference',
+                config=dict(workload=cfg['workload'] + ('' if batch == cfg['B'] else f' [CPU sample: batch {batch}]'),
+                            cpu_batch=batch, same_config=batch == cfg['B']),
                 cpu_baseline=dict(value=round(rate, 3), unit='img/s', cores=cores, kind='port', sample=sample),
                 e2e=dict(value=round(rate, 3), unit='img/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
@@ -200,7 +211,12 @@ def finish_clocks(proc):
 
 
 def run_infer(args, cfg):
-    """cfg2: generator forward only, through the module call a user makes (infer.py:155-170: eval(), no_grad)."""
+    print(json.dumps(infer_numbers(args, cfg, full=True)), flush=True)
+
+
+def infer_numbers(args, cfg, full=False):
+    """cfg2: generator forward only, through the module call a user makes (infer.py:155-170: eval(), no_grad).
+    full=False: the compact form embedded as `infer` in the training line."""
     import torch
     import patchgan_b200 as P
     from patchgan_b200 import _lib as L
@@ -250,7 +266,11 @@ def run_infer(args, cfg):
                 gpu_launches=int(launches),
                 roofline=dict(bound='tensor', kernel='generator forward (all launches)', achieved=round(tf, 2),
                               peak=pk['tf_sustained'], unit='TFLOP/s', frac=round(tf / pk['tf_sustained'], 4), traffic=None))
-    print(json.dumps(line), flush=True)
+    if full:
+        return line
+    return dict(metric=line['metric'], workload=cfg['workload'], value=line['value'], unit='img/s', steps=line['steps'],
+                ms_per_step=line['ms_per_step'], e2e=line['e2e'], gpu_launches=line['gpu_launches'],
+                roofline_frac=line['roofline']['frac'])
 
 
 def run_ours(args, cfg):
@@ -281,15 +301,15 @@ def run_ours(args, cfg):
     tr.loss_type = cfg['loss_type']
     tr.make_optimizers(1e-3, 1e-3)
 
+    # synthetic RAW batch, the form a decoded COCO-stuff sample has (io.py:42-43): uint8 RGB image + uint8 label map; the
+    # device pipeline (patchgan_b200/io.py, pg_prep_batch_u8) turns it into the float image and the per-label masks
+    from patchgan_b200.io import prepare_batch
     gen = torch.Generator().manual_seed(dp.shard_seed(1234))
     cout = cfg['G']['output_nc']
-    x_host = torch.rand((B, 3, S, S), generator=gen).pin_memory()
-    if cout == 1:
-        y_host = (torch.rand((B, 1, S, S), generator=gen) > 0.5).float().pin_memory()
-    else:
-        lab = torch.randint(0, cout + 1, (B, S, S), generator=gen)
-        y_host = torch.stack([(lab == i + 1) for i in range(cout)], 1).float().pin_memory()
-    x_dev, y_dev = x_host.to(dev), y_host.to(dev)
+    x_host = torch.randint(0, 256, (B, 3, S, S), generator=gen, dtype=torch.uint8).pin_memory()
+    y_host = torch.randint(0, cout + 1, (B, S, S), generator=gen, dtype=torch.uint8).pin_memory()      # raw label map
+    tr.labels = list(range(2, cout + 2))         # mask i = (label map + 1 == i + 2) = (label map == i + 1), some pixels unlabelled
+    x_dev, y_dev = prepare_batch(x_host.to(dev), y_host.to(dev), tr.labels, (S, S))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
     def barrier():
@@ -352,6 +372,9 @@ def run_ours(args, cfg):
         tr.step_device(x_dev, y_dev, True)
     launches = (lib.pg_launch_count() - n0) // nprof      # kernels of this library per step (graph replays launch the same)
     L.PROFILER = None
+    fallbacks = lib.pg_fallback_count()
+    if fallbacks:
+        raise SystemExit(f'{fallbacks} convolution call(s) of this run had no tcgen05 plan and ran on the CUDA-core kernel')
     agg = prof.summary()
     if world > 1:
         torch.distributed.barrier()
@@ -372,7 +395,8 @@ def run_ours(args, cfg):
     kname, (cnt, ms, fl) = conv[0]
     achieved_tf = fl / (ms * 1e-3) / 1e12
     cuda_kernel = {'pg_conv_fwd:tcgen05': ['conv_tc_pers_kernel', 'conv_tc_kernel'],
-                   'pg_conv_wgrad:tcgen05': ['wgrad_tc_kernel']}.get(kname)
+                   'pg_conv_wgrad:tcgen05': ['wgrad_tc_kernel'], 'pg_conv_wgrad_group': ['wgrad_group_kernel'],
+                   'pg_conv_norm_fwd': ['conv_res_kernel'], 'pg_conv_dgrad_norm_bwd': ['conv_res_kernel']}.get(kname)
     tr_info = ncu_traffic(cuda_kernel) if cuda_kernel else None
     roof = dict(bound='tensor', kernel=kname, cuda_kernel=cuda_kernel, achieved=round(achieved_tf, 2), peak=pk['tf_sustained'],
                 peak_src=pk['src'] + ' (sustained cuBLAS bf16)', unit='TFLOP/s', frac=round(achieved_tf / pk['tf_sustained'], 4),
@@ -383,7 +407,7 @@ def run_ours(args, cfg):
                 how='CUDA events around every launch of this kernel in a separate eager pass (side streams and graph off); '
                     'achieved = sum of 2*MACs as launched / sum of durations')
     img_s = world * B * args.steps / (dev_ms * 1e-3)
-    step_tf = img_s * cfg['gflop_per_img'] / 1e3
+    step_tf = img_s * cfg['gflop_per_img'] / 1e3 / world          # per GPU: the peak below is one GPU's
     line = dict(metric='train_img_per_s', value=round(img_s, 2), unit='img/s', n_gpus=world, steps=args.steps,
                 warmup=max(args.warmup, 3), ms_per_step=round(dev_ms / args.steps, 4), higher_is_better=True,
                 scaling='weak', vs_baseline=None,
@@ -395,20 +419,26 @@ def run_ours(args, cfg):
                             cuda_graph=bool(tr.use_cuda_graph), side_streams=bool(Config.streams)),
                 clocks=clock_info,
                 e2e=dict(value=round(world * B * args.steps / e2e_s, 2), unit='img/s',
-                         h2d_bytes_per_step=int(x_host.numel() * 4 + y_host.numel() * 4), d2h_bytes_per_step=32,
+                         h2d_bytes_per_step=int(x_host.numel() + y_host.numel()), d2h_bytes_per_step=32,
                          ms_per_step=round(e2e_s / args.steps * 1e3, 4),
-                         api='Trainer.submit(x_host, y_host).result(), one batch of lookahead (the loop of Trainer.train)',
+                         api='Trainer.submit(x_u8_host, labelmap_u8_host).result(): raw uint8 upload, float image + masks built on the '
+                             'device (pg_prep_batch_u8), one batch of lookahead (the loop of Trainer.train)',
                          sync_batch_value=round(world * B * args.steps / e2e_sync_s, 2),
-                         sync_batch_api='Trainer.batch(x_host, y_host): upload, step, read-back in sequence'),
+                         sync_batch_api='Trainer.batch(x_u8_host, labelmap_u8_host): upload, step, read-back in sequence'),
                 gpu_launches=int(launches), roofline=roof,
-                step_tensor=dict(algorithmic_gflop_per_img=cfg['gflop_per_img'], achieved_tflops=round(step_tf, 2),
+                step_tensor=dict(algorithmic_gflop_per_img=cfg['gflop_per_img'], achieved_tflops_per_gpu=round(step_tf, 2),
                                  frac_of_peak=round(step_tf / pk['tf_sustained'], 4)),
+                cuda_core_fallbacks=int(fallbacks),
                 kernel_time_shares=shares, last_losses={k: round(v, 5) for k, v in losses.items()})
     if world == 1 and not args.no_cpu_baseline:
-        cb = 4 if S <= 256 else 1
-        rate, sec = cpu_step_rate(cfg, 5, 2, cb)
+        cb = cpu_batch(cfg)
+        nst = 5 if S <= 256 else 2
+        rate, sec = cpu_step_rate(cfg, nst, 1, cb)
         line['cpu_baseline'] = dict(value=round(rate, 3), unit='img/s', cores=os.cpu_count(), kind='port',
-                                    sample=f'{CPU_SAMPLE}; 2 warm-up + 5 timed steps of batch {cb}, median')
+                                    sample=f'{CPU_SAMPLE}; 1 warm-up + {nst} timed steps of batch {cb}, median')
+    if world == 1 and not args.no_infer and args.config == 'cfg3':
+        # BASELINE.json configs[1] (generator inference forward, batch 64) inside the same driver-run line
+        line['infer'] = infer_numbers(args, CONFIGS['cfg2'])
     print(json.dumps(line), flush=True)
 
 
@@ -420,6 +450,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--config', default='cfg3', choices=list(CONFIGS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-infer', action='store_true', help='skip the cfg2 inference numbers added to the cfg3 line')
     ap.add_argument('--detail', default=None, help='write the per-launch timing of one profiled step to this JSON file')
     args = ap.parse_args()
     cfg = CONFIGS[args.config]

@@ -225,6 +225,10 @@ typedef struct PgWgradJob {
   int32_t tap_major;
   float* dw;
   int32_t ld_n, n_real, c_real, Cs;
+  const void* g2;      /* optional: g is the virtual concat [g (n_split channels) | g2 (desc.N - n_split)] -- the two sources of
+                          a decoder layer's input (unet.py:127) in one job, so that the tap-shifted operand `a` is read once
+                          for both; n_split and desc.N - n_split must be multiples of min(64, ...) channel boxes */
+  int32_t ldg2, n_split;
 } PgWgradJob;
 int pg_conv_wgrad_group(const PgWgradJob* jobs, int32_t njobs, void* stream);
 
@@ -399,6 +403,16 @@ int pg_adam_step(float* p, const float* g, float* m, float* v, int64_t n, const 
  * count as it was before the step; exactly one of them (the last in stream order) passes bump = 1. */
 int pg_adam_step_range(float* p, const float* g, float* m, float* v, int64_t n, const float* hyper, int32_t* step,
                        float beta1, float beta2, float eps, float grad_scale, int32_t bump, void* stream);
+
+/* ---- device input pipeline: COCOStuffDataset.__getitem__ (io.py:38-58) from RAW uint8 data, "next" row f3 ----
+ * img: uint8 [B][3][Hs][Ws] (decoded RGB), lab: uint8 [B][Hs][Ws] (decoded label map), both on the device;
+ * x[b] = resize(img / 255), labels' = resize(uint8(lab + 1)) (the reference adds 1 in uint8, 255 wraps to 0),
+ * y[b][l] = (labels' == labels[l]) as 0 / 1 float; resize = torchvision Resize((Ho, Wo)) on a float tensor (bilinear,
+ * align_corners = False, no antialias; identity when the sizes match); flips[b] (device, nullable): bit 0 horizontal, bit 1
+ * vertical flip after the resize (RandomHorizontalFlip / RandomVerticalFlip; the caller draws them).  `labels` is a HOST
+ * array of nlabels <= 16 values.  x: float [B][3][Ho][Wo], y: float [B][nlabels][Ho][Wo]. */
+int pg_prep_batch_u8(const uint8_t* img, const uint8_t* lab, const int32_t* labels, int32_t nlabels, int32_t B, int32_t Hs,
+                     int32_t Ws, int32_t Ho, int32_t Wo, const uint8_t* flips, float* x, float* y, void* stream);
 
 /* ---- inference tiling (infer.py:14-68), "next" row ---- */
 int pg_ncrop(const float* image, float* crops, int32_t C, int32_t H, int32_t W, int32_t size, int32_t eff,

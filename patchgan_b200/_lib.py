@@ -41,7 +41,7 @@ FP = C.POINTER(FusedNorm)
 class WgradJob(C.Structure):
     """PgWgradJob: one weight gradient of a grouped launch (pg_conv_wgrad_group)."""
     _fields_ = [('desc', ConvDesc), ('a', vp), ('g', vp), ('ldg', i32), ('tap_major', i32), ('dw', vp), ('ld_n', i32),
-                ('n_real', i32), ('c_real', i32), ('Cs', i32)]
+                ('n_real', i32), ('c_real', i32), ('Cs', i32), ('g2', vp), ('ldg2', i32), ('n_split', i32)]
 
 _SIGS = {
     'pg_version': ([], C.c_int),
@@ -94,6 +94,7 @@ _SIGS = {
     'pg_adam_step': ([vp, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, vp], C.c_int),
     'pg_adam_step_range': ([vp, vp, vp, vp, i64, vp, vp, f32, f32, f32, f32, i32, vp], C.c_int),
     'pg_counter_add': ([vp, u64, vp], C.c_int),
+    'pg_prep_batch_u8': ([vp, vp, C.POINTER(i32), i32, i32, i32, i32, i32, i32, vp, vp, vp, vp], C.c_int),
     'pg_ncrop': ([vp, vp, i32, i32, i32, i32, i32, i32, i32, vp], C.c_int),
     'pg_build_mask': ([vp, vp, vp, i32, i32, i32, i32, i32, i32, i32, f32, vp], C.c_int),
 }

@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(HERE, 'libpatchgan_b200.so')
-SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_skinny.cu', 'norm_act.cu', 'layout.cu', 'loss.cu', 'adam.cu', 'tiling.cu']
+SOURCES = ['api.cu', 'conv_simt.cu', 'conv_tc.cu', 'conv_skinny.cu', 'norm_act.cu', 'layout.cu', 'loss.cu', 'adam.cu', 'tiling.cu', 'input.cu']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--expt-relaxed-constexpr', '-Xcompiler', '-fPIC']
 

@@ -329,7 +329,10 @@ extern "C" int pg_conv_wgrad_group(const PgWgradJob* jobs, int32_t njobs, void* 
     if (int e = validate(&jb.desc, "pg_conv_wgrad_group")) return e;
     PG_REQUIRE((jb.desc.mode == PG_CONV || jb.desc.mode == PG_CONV1X1) && jb.desc.C2 == 0,
                "pg_conv_wgrad_group: job %d: geometry must be PG_CONV / PG_CONV1X1 with one source", j);
-    PG_REQUIRE(jb.a && jb.g && jb.dw && jb.ldg >= jb.desc.N && jb.ldg % 8 == 0, "pg_conv_wgrad_group: job %d: bad pointers / ldg", j);
+    PG_REQUIRE(jb.a && jb.g && jb.dw && jb.ldg % 8 == 0 && jb.ldg >= (jb.g2 ? jb.n_split : jb.desc.N),
+               "pg_conv_wgrad_group: job %d: bad pointers / ldg", j);
+    PG_REQUIRE(jb.g2 == nullptr || (jb.n_split > 0 && jb.n_split < jb.desc.N && jb.ldg2 >= jb.desc.N - jb.n_split),
+               "pg_conv_wgrad_group: job %d: bad second source", j);
     PG_REQUIRE(jb.n_real <= jb.desc.N && jb.c_real <= jb.desc.C1, "pg_conv_wgrad_group: job %d: n_real / c_real exceed padded extents", j);
     PG_REQUIRE(!jb.tap_major || (jb.desc.mode == PG_CONV && jb.Cs % 4 == 0), "pg_conv_wgrad_group: job %d: bad tap-major job", j);
     PG_REQUIRE(conv_wgrad_tc_supported(&jb.desc, jb.a, jb.g, jb.ldg), "pg_conv_wgrad_group: job %d has no tcgen05 plan", j);

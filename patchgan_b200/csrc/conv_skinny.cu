@@ -624,22 +624,29 @@ __global__ void __launch_bounds__(512) taps_dgrad_act_kernel(const bf16* __restr
     __syncthreads();
     if (!live) continue;
     const int npx = nq - q0 < TD_PX ? (int)(nq - q0) : TD_PX;
-    for (int pxl = 0; pxl < npx; ++pxl) {
-      const float4* g4 = reinterpret_cast<const float4*>(Gs[pxl]);
-      float a0 = 0.f, a1 = 0.f;
+    // eight pixels at a time: their y loads are issued together (a serial walk paid one DRAM latency per pixel)
+    for (int p0 = 0; p0 < npx; p0 += 8) {
+      unsigned yy[8];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 gv = g4[j];
-        a0 = fmaf(gv.x, w0[4 * j], a0); a0 = fmaf(gv.y, w0[4 * j + 1], a0); a0 = fmaf(gv.z, w0[4 * j + 2], a0); a0 = fmaf(gv.w, w0[4 * j + 3], a0);
-        a1 = fmaf(gv.x, w1[4 * j], a1); a1 = fmaf(gv.y, w1[4 * j + 1], a1); a1 = fmaf(gv.z, w1[4 * j + 2], a1); a1 = fmaf(gv.w, w1[4 * j + 3], a1);
+      for (int u = 0; u < 8; ++u)
+        yy[u] = (y != nullptr && p0 + u < npx) ? __ldg(reinterpret_cast<const unsigned*>(y + (q0 + p0 + u) * ldy + c)) : 0u;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (p0 + u >= npx) break;
+        const float4* g4 = reinterpret_cast<const float4*>(Gs[p0 + u]);
+        float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 gv = g4[j];
+          a0 = fmaf(gv.x, w0[4 * j], a0); a0 = fmaf(gv.y, w0[4 * j + 1], a0); a0 = fmaf(gv.z, w0[4 * j + 2], a0); a0 = fmaf(gv.w, w0[4 * j + 3], a0);
+          a1 = fmaf(gv.x, w1[4 * j], a1); a1 = fmaf(gv.y, w1[4 * j + 1], a1); a1 = fmaf(gv.z, w1[4 * j + 2], a1); a1 = fmaf(gv.w, w1[4 * j + 3], a1);
+        }
+        if (y != nullptr) {
+          a0 *= act_grad_from_output(act, from16((unsigned short)(yy[u] & 0xffffu), y_dt));
+          a1 *= act_grad_from_output(act, from16((unsigned short)(yy[u] >> 16), y_dt));
+        }
+        *reinterpret_cast<__nv_bfloat162*>(dx + (q0 + p0 + u) * lddx + c) = __floats2bfloat162_rn(a0, a1);
       }
-      const long long q = q0 + pxl;
-      if (y != nullptr) {
-        const unsigned yy = *reinterpret_cast<const unsigned*>(y + q * ldy + c);
-        a0 *= act_grad_from_output(act, from16((unsigned short)(yy & 0xffffu), y_dt));
-        a1 *= act_grad_from_output(act, from16((unsigned short)(yy >> 16), y_dt));
-      }
-      *reinterpret_cast<__nv_bfloat162*>(dx + q * lddx + c) = __floats2bfloat162_rn(a0, a1);
     }
   }
 }
@@ -648,7 +655,7 @@ int taps_dgrad_act(const void* G, const void* w16, void* dx, int lddx, const voi
                    cudaStream_t stream) {
   const int threads = ((C / 2 + 31) / 32) * 32;
   long long blocks = (nq + TD_PX - 1) / TD_PX;
-  const long long cap = 2LL * num_sms();          // two blocks per SM walk the pixels (the weights are loaded once per block)
+  const long long cap = 6LL * num_sms();          // (the weights are loaded once per block: 64 bytes per thread, from L2)
   if (blocks > cap) blocks = cap;
   taps_dgrad_act_kernel<<<(unsigned)blocks, threads, 0, stream>>>((const bf16*)G, (const bf16*)w16, (const unsigned short*)y, ldy,
                                                                 y_dt, act, (bf16*)dx, lddx, nq, C);

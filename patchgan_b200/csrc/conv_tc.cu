@@ -1473,6 +1473,7 @@ struct WgParams {
   int tapmajor;            // epilogue = TMA reduce-add of [128 n][ct c] tiles into S[tap][n][c] (mapS)
   int st_rowbytes;         // bytes per staged row (128, or 64 when ct == 16)
   int n_atoms_load;        // G boxes that exist (the accumulator rows of the others are never stored)
+  int n_split;             // > 0: the G operand is the virtual concat of two tensors: channels [0, n_split) | [n_split, N)
   unsigned long long* trace;
 };
 
@@ -1505,8 +1506,8 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
 
 // The kernel body: one CTA = (n-tile bx, (channel tile, tap group) by, pixel-tile split bz) of ONE weight gradient.
 // Called by wgrad_tc_kernel (one weight gradient per launch) and wgrad_group_kernel (many per launch).
-__device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtensorMap* mapsA, const CUtensorMap* mapS,
-                                           const WgParams& p, int bx, int by, int bz) {
+__device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtensorMap* mapG2, const CUtensorMap* mapsA,
+                                           const CUtensorMap* mapS, const WgParams& p, int bx, int by, int bz) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t gfull[WG_MAX_G], gempty[WG_MAX_G], afull[WG_MAX_A], aempty[WG_MAX_A];
   __shared__ __align__(8) uint64_t acc_bar;
@@ -1560,8 +1561,13 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtens
         mbar_wait(smem_u32(&gempty[gs]), gph ^ 1);
         const uint32_t gb = smem_u32(&gfull[gs]);
         mbar_expect_tx(gb, p.n_atoms_load * p.g_boxbytes);
-        for (int a = 0; a < p.n_atoms_load; ++a)
-          tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, mapG, gb, n0 + a * p.g_box, x0, y0, b0);
+        for (int a = 0; a < p.n_atoms_load; ++a) {
+          const int ch = n0 + a * p.g_box;          // (a box never straddles the two sources: n_split % g_box == 0)
+          if (p.n_split > 0 && ch >= p.n_split)
+            tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, mapG2, gb, ch - p.n_split, x0, y0, b0);
+          else
+            tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, mapG, gb, ch, x0, y0, b0);
+        }
         if (++gs == p.g_stages) { gs = 0; gph ^= 1; }
         for (int tl = 0; tl < p.T; ++tl) {
           const int t = t0 + tl, kh = t >> 2, kw = t & 3;
@@ -1732,7 +1738,7 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtens
 __global__ void __launch_bounds__(TC_THREADS, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ ActMaps mapsA,
                 const __grid_constant__ CUtensorMap mapS, const WgParams p) {
-  wgrad_body(&mapG, mapsA.m, &mapS, p, blockIdx.x, blockIdx.y, blockIdx.z);
+  wgrad_body(&mapG, &mapG, mapsA.m, &mapS, p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // Many weight gradients in ONE launch.  The generator's backward has ~20 of them (14 layers, two sources per decoder
@@ -1744,6 +1750,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant_
 constexpr int WG_GROUP_MAX = 24;
 struct __align__(64) WgJobDev {
   CUtensorMap mapG;
+  CUtensorMap mapG2;       // second source of the G operand (virtual concat), else a copy of mapG
   CUtensorMap mapA[4];
   CUtensorMap mapS;
   WgParams p;
@@ -1761,7 +1768,7 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_group_kernel(const __grid
   const WgJobDev& jb = g.jobs[j];
   const int local = (int)blockIdx.x - g.cta_begin[j];
   const int bx = local % jb.gx, r = local / jb.gx;
-  wgrad_body(&jb.mapG, jb.mapA, &jb.mapS, jb.p, bx, r % jb.gy, r / jb.gy);
+  wgrad_body(&jb.mapG, &jb.mapG2, jb.mapA, &jb.mapS, jb.p, bx, r % jb.gy, r / jb.gy);
 }
 
 static int box_of(int ch) { return ch >= 64 ? 64 : (ch >= 32 ? 32 : 16); }
@@ -1850,13 +1857,14 @@ struct WgPrepared {
   WgParams p;
   dim3 grid;
   size_t smem;
-  CUtensorMap mG, mS;
+  CUtensorMap mG, mG2, mS;
   ActMaps mA;
 };
 
 // tap_major != 0: dw is S[16][Ns = ld_n][Cs = c_stride] (fp32, zeroed by the caller); else the reference layout
 static int wg_prepare(const PgConvDesc* d, const void* a, const void* g, int ldg, float* dw, int ld_n, int n_real, int c_real,
-                      int tap_major, int Cs, int split_cap, WgPrepared& w) {
+                      int tap_major, int Cs, int split_cap, WgPrepared& w, const void* g2 = nullptr, int ldg2 = 0,
+                      int n_split = 0) {
   WgParams& p = w.p;
   if (!make_wg_plan(d, p, w.grid, w.smem, split_cap)) {
     set_error("conv_wgrad_tc: unsupported shape");
@@ -1894,9 +1902,27 @@ static int wg_prepare(const PgConvDesc* d, const void* a, const void* g, int ldg
     fprintf(stderr, "wgrad_tc: grid (%u,%u,%u) T %d ct %d tiles %d per-split %d g_stages %d a_stages %d smem %zu tmem %u\n", w.grid.x,
             w.grid.y, w.grid.z, p.T, p.ct, p.total_tiles, p.tiles_per_split, p.g_stages, p.a_stages, w.smem, p.tmem_cols);
   memset(&w.mA, 0, sizeof(w.mA));
-  if (int e = encode_act_map(&w.mG, g, d->N, ldg, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, -1, p.g_rowbytes,
-                             d->out_f32))
-    return e;
+  p.n_split = 0;
+  if (g2 != nullptr) {
+    // G = [g (n_split channels) | g2 (N - n_split channels)]: two tensor maps, every box inside one of them
+    if (n_split <= 0 || n_split >= d->N || (n_split % p.g_box) != 0 || ((d->N - n_split) % p.g_box) != 0 || (ldg2 % 8) != 0 ||
+        (((uintptr_t)g2) & 15) != 0) {
+      set_error("conv_wgrad_tc: bad two-source G operand (n_split=%d of N=%d, box %d)", n_split, d->N, p.g_box);
+      return PG_ERR_UNSUPPORTED;
+    }
+    p.n_split = n_split;
+    if (int e = encode_act_map(&w.mG, g, n_split, ldg, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, -1, p.g_rowbytes,
+                               d->out_f32))
+      return e;
+    if (int e = encode_act_map(&w.mG2, g2, d->N - n_split, ldg2, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, -1,
+                               p.g_rowbytes, d->out_f32))
+      return e;
+  } else {
+    if (int e = encode_act_map(&w.mG, g, d->N, ldg, d->B, d->Hout, d->Wout, p.g_box, p.TW, p.TH, p.TB, -1, p.g_rowbytes,
+                               d->out_f32))
+      return e;
+    w.mG2 = w.mG;
+  }
   const bool phased = !p.pointwise && d->stride == 2;
   for (int ph = 0; ph < (phased ? 4 : 1); ++ph)
     if (int e = encode_act_map(&w.mA.m[ph], a, d->C1, d->ld1, d->B, d->Hin, d->Win, p.a_box, p.TW, p.TH, p.TB,
@@ -1940,10 +1966,12 @@ int conv_wgrad_group_tc(const PgWgradJob* jobs, int njobs, cudaStream_t stream) 
     }
     int split_cap = cap / (int)(g0.x * g0.y);
     if (split_cap < 1) split_cap = 1;
-    if (int e = wg_prepare(&jb.desc, jb.a, jb.g, jb.ldg, jb.dw, jb.ld_n, jb.n_real, jb.c_real, jb.tap_major, jb.Cs, split_cap, w))
+    if (int e = wg_prepare(&jb.desc, jb.a, jb.g, jb.ldg, jb.dw, jb.ld_n, jb.n_real, jb.c_real, jb.tap_major, jb.Cs, split_cap, w,
+                           jb.g2, jb.ldg2, jb.n_split))
       return e;
     WgJobDev& dst = args.jobs[j];
     dst.mapG = w.mG;
+    dst.mapG2 = w.mG2;
     for (int ph = 0; ph < 4; ++ph) dst.mapA[ph] = w.mA.m[ph];
     dst.mapS = w.mS;
     dst.p = w.p;

@@ -661,9 +661,10 @@ class NetEngine:
                 self._tm_table = None
             self._tm_buf.zero_()
 
-    def wgrad(self, desc, a, g, dst_ptr, ld_n, n_real, c_real, wstream=None):
+    def wgrad(self, desc, a, g, dst_ptr, ld_n, n_real, c_real, wstream=None, g2=None, n_split=0):
         """Weight gradient of one (layer, source): dst[n*ld_n + c*16 + tap] (reference layout) receives it -- directly
-        (atomics) or, by default, through the tap-major scratch + finalize_grads()."""
+        (atomics) or, by default, through the tap-major scratch + finalize_grads().
+        g2 / n_split (grouped launches only): g is the virtual concat [g | g2] of a decoder layer's two sources."""
         jobs = getattr(self, '_tm_jobs', None)
         if not (taps_enabled() and jobs is not None and desc.mode == L.PG_CONV) or 'wgrad' in SKIP:
             return run_wgrad(desc, a, g, dst_ptr, ld_n, n_real, c_real, wstream)
@@ -676,7 +677,7 @@ class NetEngine:
         sp = self._tm_buf.data_ptr() + off * 4
         jobs.append((sp, dst_ptr, ld_n, n_real, c_real, Ns, Cs))
         if self._wg_group is not None:
-            self._wg_group.append((desc, a, g, g.ld, 1, sp, Ns, Ns, Cs, Cs))    # (the Acts keep their storage alive)
+            self._wg_group.append((desc, a, g, g.ld, 1, sp, Ns, Ns, Cs, Cs, g2, n_split))    # (the Acts keep their storage alive)
             return
         wstream = pick_wstream(wstream)
         if wstream is not None:
@@ -689,7 +690,7 @@ class NetEngine:
     def wgrad_direct(self, desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream=None):
         """A weight gradient accumulated straight into the reference layout (pointwise layers): grouped or launched now."""
         if getattr(self, '_wg_group', None) is not None and 'wgrad' not in SKIP:
-            self._wg_group.append((desc, a, g, g.ld, 0, dw_ptr, ld_n, n_real, c_real, 0))
+            self._wg_group.append((desc, a, g, g.ld, 0, dw_ptr, ld_n, n_real, c_real, 0, None, 0))
             return
         run_wgrad(desc, a, g, dw_ptr, ld_n, n_real, c_real, wstream)
 
@@ -707,9 +708,11 @@ class NetEngine:
             for i in range(0, len(pend), 24):
                 chunk = pend[i:i + 24]
                 arr = (L.WgradJob * len(chunk))()
-                for j, (desc, a, g, ldg, tm, dw, ld_n, n_real, c_real, Cs) in enumerate(chunk):
+                for j, (desc, a, g, ldg, tm, dw, ld_n, n_real, c_real, Cs, g2, n_split) in enumerate(chunk):
                     ctypes.memmove(ctypes.byref(arr[j].desc), ctypes.byref(desc), ctypes.sizeof(L.ConvDesc))
                     arr[j].a, arr[j].g, arr[j].ldg, arr[j].tap_major, arr[j].dw = a.ptr, g.ptr, ldg, tm, dw
+                    if g2 is not None:
+                        arr[j].g2, arr[j].ldg2, arr[j].n_split = g2.ptr, g2.ld, n_split
                     arr[j].ld_n, arr[j].n_real, arr[j].c_real, arr[j].Cs = ld_n, n_real, c_real, Cs
                     if L.PROFILER is not None:
                         L.PROFILER.note(conv_flops(desc), 'group')
@@ -997,10 +1000,19 @@ class GeneratorEngine(NetEngine):
                 d_raw = dgrad_block_bwd(dd, G6, pw.w16, 16 * 2, din, s.c1p, prod, None, self.seed)
             else:
                 # weight gradient: dW[ci][co][tap] = sum x[ci] * dY[co] -- PG_CONV geometry with A = dY, G = layer input
-                wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C,
-                               src1.C, out_dt=BF16, in_dt=BF16)
-                self.wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.c1, s.cout, wstream)
-                if src2 is not None:
+                merged = (self._wg_group is not None and src2 is not None and s.c1 == s.c1p and s.c2 == s.c2p and
+                          s.c1p % 64 == 0 and s.c2p % 64 == 0)
+                if merged:
+                    # both sources of the concat in ONE job: the tap-shifted operand (dY, 16 taps) is read once, not twice
+                    wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, s.cinp,
+                                   s.cinp, out_dt=BF16, in_dt=BF16)
+                    self.wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.cin, s.cout, wstream, g2=src2.b16,
+                               n_split=s.c1p)
+                else:
+                    wd = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src1.H, src1.W, d_raw.C, 0, d_raw.ld, 0, src1.C,
+                                   src1.C, out_dt=BF16, in_dt=BF16)
+                    self.wgrad(wd, d_raw, src1.b16, g.data_ptr(), s.cout * 16, s.c1, s.cout, wstream)
+                if src2 is not None and not merged:
                     wd2 = conv_desc(L.PG_CONV, 2, 1, B, d_raw.H, d_raw.W, src2.H, src2.W, d_raw.C, 0, d_raw.ld, 0, src2.C,
                                     src2.C, out_dt=BF16, in_dt=BF16)
                     self.wgrad(wd2, d_raw, src2.b16, g.data_ptr() + s.c1 * s.cout * 16 * 4, s.cout * 16, s.c2, s.cout,

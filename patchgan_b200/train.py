@@ -49,9 +49,15 @@ def patchgan_train():
         full = Dataset(train_paths['images'], train_paths['masks'], size=size, augmentation=augmentation, **ds_kwargs)
         train_set, val_set = random_split(full, split)
 
-    loader_kwargs = dict(num_workers=args.dataloader_workers, persistent_workers=True) if args.dataloader_workers > 0 else {}
-    train_data = DataLoader(train_set, batch_size=args.batch_size, shuffle=True, pin_memory=True, **loader_kwargs)
-    val_data = DataLoader(val_set, batch_size=args.batch_size, shuffle=True, pin_memory=True, **loader_kwargs)
+    from .io import COCOStuffDataset, DeviceBatches
+    if Dataset is COCOStuffDataset:
+        # raw uint8 samples from the workers; /255, label shift, resize, flips and masks on the GPU (patchgan_b200/io.py)
+        train_data = DeviceBatches(train_set, args.batch_size, True, args.dataloader_workers, device)
+        val_data = DeviceBatches(val_set, args.batch_size, True, args.dataloader_workers, device)
+    else:
+        loader_kwargs = dict(num_workers=args.dataloader_workers, persistent_workers=True) if args.dataloader_workers > 0 else {}
+        train_data = DataLoader(train_set, batch_size=args.batch_size, shuffle=True, pin_memory=True, **loader_kwargs)
+        val_data = DataLoader(val_set, batch_size=args.batch_size, shuffle=True, pin_memory=True, **loader_kwargs)
 
     generator, discriminator = build_models(config, in_channels, out_channels, device)
     if args.summary:

@@ -73,6 +73,9 @@ class Trainer:
     tversky_gamma = 0.75
 
     neptune_config = None
+    # label ids of the masks (io.py:17,54-56).  When set, batch / submit also take a RAW batch -- x: uint8 (B,3,H,W) image,
+    # y: uint8 (B,H,W) label map -- and build the float tensors of io.py:42-56 on the device (patchgan_b200.io.prepare_batch)
+    labels = None
 
     # Replay the step as ONE CUDA graph once a (shape, mode) has been seen GRAPH_WARMUP times (the step is ~140 short
     # launches; the host cannot keep a B200 fed).  PATCHGAN_B200_GRAPH=0 keeps eager launches.
@@ -496,6 +499,8 @@ class Trainer:
         def pinned_f32(a):
             return isinstance(a, torch.Tensor) and a.device.type == 'cpu' and a.dtype == torch.float32 and \
                 a.is_contiguous() and a.is_pinned()
+        if isinstance(x, torch.Tensor) and x.dtype == torch.uint8 and isinstance(y, torch.Tensor) and y.dtype == torch.uint8:
+            return self._stage_raw(x, y)
         if not (pinned_f32(x) and pinned_f32(y)) or torch.device(self.device).type != 'cuda':
             xd, yd = self._to_device(x), self._to_device(y)
             if xd.device.type != 'cuda':
@@ -519,6 +524,39 @@ class Trainer:
         with torch.cuda.stream(cs):
             slot['x'].copy_(x, non_blocking=True)
             slot['y'].copy_(y, non_blocking=True)
+            slot['ready'].record(cs)
+        torch.cuda.current_stream(dev).wait_event(slot['ready'])
+        return slot['x'], slot['y'], slot
+
+    def _stage_raw(self, x, y):
+        """Raw uint8 batch (image (B,3,H,W), label map (B,H,W)): upload the bytes (copy stream, two staging slots, like
+        _stage_inputs) and turn them into the float image / per-label masks on the device."""
+        from .io import prepare_batch
+        if self.labels is None:
+            raise RuntimeError('Trainer.labels (the label ids of the masks) must be set to train from raw uint8 batches')
+        dev = torch.device(self.device)
+        if dev.index is None:
+            dev = torch.device('cuda', torch.cuda.current_device())
+        nl = len(self.labels)
+        B, _, H, W = x.shape
+        key = ('u8', tuple(x.shape), nl, dev.index)
+        slots = self._stage.get(key)
+        if slots is None:
+            slots = self._stage[key] = [dict(xu=torch.empty(x.shape, dtype=torch.uint8, device=dev),
+                                             yu=torch.empty(y.shape, dtype=torch.uint8, device=dev),
+                                             x=torch.empty((B, 3, H, W), dtype=torch.float32, device=dev),
+                                             y=torch.empty((B, nl, H, W), dtype=torch.float32, device=dev),
+                                             ready=torch.cuda.Event(), free=None) for _ in range(2)]
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+        slot = slots[self._submits % 2]
+        cs = self._copy_stream
+        if slot['free'] is not None:
+            cs.wait_event(slot['free'])
+        with torch.cuda.stream(cs):
+            slot['xu'].copy_(x, non_blocking=True)
+            slot['yu'].copy_(y, non_blocking=True)
+            prepare_batch(slot['xu'], slot['yu'], self.labels, (H, W), out=(slot['x'], slot['y']))
             slot['ready'].record(cs)
         torch.cuda.current_stream(dev).wait_event(slot['ready'])
         return slot['x'], slot['y'], slot

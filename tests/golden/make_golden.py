@@ -156,6 +156,55 @@ def losses_case():
     np.savez_compressed(os.path.join(HERE, 'losses.npz'), **out)
 
 
+def io_case():
+    """COCOStuffDataset.__getitem__ (io.py:38-58) on synthetic jpg / png files.  The decoded uint8 arrays are stored with the
+    outputs, so the tests need neither an image decoder nor the files; flip codes are detected from the output."""
+    import tempfile
+    from torchvision.io import ImageReadMode, read_image, write_jpeg, write_png
+    from patchgan.io import COCOStuffDataset
+    rng = np.random.default_rng(17)
+    d = tempfile.mkdtemp()
+    os.makedirs(d + '/img'); os.makedirs(d + '/msk')
+    sizes = [(75, 100), (64, 64), (130, 97)]
+    for i, (h, w) in enumerate(sizes):
+        # smooth-ish image, blocky label map with values that include 254 / 255 (uint8 wrap of the +1 shift)
+        img = (rng.random((3, h // 4 + 1, w // 4 + 1)) * 255).astype(np.uint8).repeat(4, 1).repeat(4, 2)[:, :h, :w]
+        img = (img.astype(np.int32) + rng.integers(-8, 9, img.shape)).clip(0, 255).astype(np.uint8)
+        lab = rng.choice(np.array([0, 1, 2, 6, 254, 255], dtype=np.uint8), size=(h // 8 + 1, w // 8 + 1)).repeat(8, 0).repeat(8, 1)[:h, :w]
+        write_jpeg(torch.from_numpy(np.ascontiguousarray(img)), f'{d}/img/{i:03d}.jpg', quality=95)
+        write_png(torch.from_numpy(np.ascontiguousarray(lab[None])), f'{d}/msk/{i:03d}.png')
+    labels = [7, 1, 3, 0]                      # unsorted on purpose (io.py:17 sorts); 0 = wrapped 255
+    S = 64
+    out = dict(labels=np.array(labels), size=np.array([S, S]))
+    ds = COCOStuffDataset(d + '/img', d + '/msk', labels=labels, size=S, augmentation='randomcrop')
+    for i in range(len(sizes)):
+        out[f'img_u8/{i}'] = read_image(ds.images[i], ImageReadMode.RGB).numpy()
+        out[f'lab_u8/{i}'] = read_image(ds.masks[i], ImageReadMode.GRAY).numpy()[0]
+        img, mask = ds[i]
+        out[f'img/{i}'] = img.numpy()
+        out[f'mask/{i}'] = mask.numpy().astype(np.uint8)
+    # flips: run the flipping dataset under several seeds, keep one sample per flip code that occurred
+    dsf = COCOStuffDataset(d + '/img', d + '/msk', labels=labels, size=S, augmentation='randomcrop+flip')
+    seen = {}
+    for seed in range(200):
+        torch.manual_seed(seed)
+        img, mask = dsf[0]
+        base = out['img/0']
+        for code in (1, 2, 3):
+            ref = base[:, :, ::-1] if code & 1 else base
+            ref = ref[:, ::-1, :] if code & 2 else ref
+            if code not in seen and np.array_equal(img.numpy(), ref):
+                seen[code] = (img.numpy(), mask.numpy().astype(np.uint8))
+        if len(seen) == 3:
+            break
+    for code, (img, mask) in seen.items():
+        out[f'flip{code}/img'] = img
+        out[f'flip{code}/mask'] = mask
+    out['flip_codes'] = np.array(sorted(seen))
+    np.savez_compressed(os.path.join(HERE, 'io.npz'), **out)
+    print('io', {k: v.shape for k, v in out.items() if k.startswith('img/')}, 'flip codes', sorted(seen))
+
+
 def infer_case():
     """n_crop / build_mask (infer.py:14-68) on a small non-trivial image."""
     from patchgan import infer as I
@@ -185,3 +234,5 @@ if __name__ == '__main__':
         losses_case()
     if not only or 'infer' in only:
         infer_case()
+    if not only or 'io' in only:
+        io_case()

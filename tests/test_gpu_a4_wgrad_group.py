@@ -43,6 +43,22 @@ def test_grouped_weight_gradients_match_oracle_and_single_launches():
         outs.append((dw, tap_major))
     L.call('pg_conv_wgrad_group', jobs, len(cases), stream())
     torch.cuda.synchronize()
+    # one more launch: a job whose gradient-side operand is the virtual concat of two tensors (64 | 64 channels)
+    B, Ci, Co, H = 2, 32, 128, 16
+    x = bf16_round(r.standard_normal((B, Ci, H, H)))
+    dy = bf16_round(r.standard_normal((B, Co, H // 2, H // 2)))
+    _, dw_ref, _ = orc.conv2d_bwd(x, np.zeros((Co, Ci, 4, 4), np.float32), dy, 2, need_dx=False)
+    xd, d1, d2 = to_nhwc(x), to_nhwc(dy[:, :64]), to_nhwc(dy[:, 64:])
+    cat = (L.WgradJob * 1)()
+    d = conv_desc(L.PG_CONV, 2, 1, B, H, H, H // 2, H // 2, Ci, 0, Ci, 0, Co, Co, out_dt=L.DT_BF16, in_dt=L.DT_BF16)
+    ctypes.memmove(ctypes.byref(cat[0].desc), ctypes.byref(d), ctypes.sizeof(L.ConvDesc))
+    S = torch.zeros((16, Co, Ci), device='cuda')
+    cat[0].a, cat[0].g, cat[0].ldg, cat[0].tap_major, cat[0].dw = xd.data_ptr(), d1.data_ptr(), 64, 1, S.data_ptr()
+    cat[0].ld_n, cat[0].n_real, cat[0].c_real, cat[0].Cs = Co, Co, Ci, Ci
+    cat[0].g2, cat[0].ldg2, cat[0].n_split = d2.data_ptr(), 64, 64
+    L.call('pg_conv_wgrad_group', cat, 1, stream())
+    torch.cuda.synchronize()
+    assert relerr(S.cpu().numpy().transpose(1, 2, 0).reshape(dw_ref.shape), dw_ref) < 1e-4
     for (dw, tm), ref in zip(outs, refs):
         got = dw.cpu().numpy()
         if tm:

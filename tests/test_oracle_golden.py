@@ -172,3 +172,22 @@ def test_rectangular_step_matches_reference():
         relnorm(summarize(g), gold[f'ggrad/{k}'], 1e-4, f'rect ggrad {k}')
     for k, g in tr.last['disc_grads'].items():
         relnorm(summarize(g), gold[f'dgrad/{k}'], 1e-4, f'rect dgrad {k}')
+
+
+def test_input_pipeline_matches_reference():
+    """oracle/io_oracle.py against COCOStuffDataset.__getitem__ of the live reference (tests/golden/io.npz): per-label
+    masks bit-exact (incl. the uint8 wrap 255 + 1 -> 0 and labels interpolated by the bilinear Resize), image to 1 ulp,
+    all four flip combinations."""
+    from oracle import io_oracle as io
+    gold = np.load(os.path.join(GOLD, 'io.npz'))
+    labels, size = gold['labels'], tuple(gold['size'])
+    for i in range(3):
+        img, mask = io.prepare_sample(gold[f'img_u8/{i}'], gold[f'lab_u8/{i}'], labels, size)
+        assert np.array_equal(mask.astype(np.uint8), gold[f'mask/{i}'])
+        assert np.abs(img - gold[f'img/{i}']).max() <= 1.2e-7
+        assert gold[f'mask/{i}'].sum() > 0
+    assert sorted(gold['flip_codes'].tolist()) == [1, 2, 3]
+    for code in gold['flip_codes']:
+        img, mask = io.prepare_sample(gold['img_u8/0'], gold['lab_u8/0'], labels, size, flip=int(code))
+        assert np.array_equal(mask.astype(np.uint8), gold[f'flip{code}/mask'])
+        assert np.abs(img - gold[f'flip{code}/img']).max() <= 1.2e-7
