@@ -631,12 +631,17 @@ static bool make_res_plan(const PgConvDesc* d, const PgFusedNorm* fn, bool twin,
   const double a_bytes = 128.0 * swz;
   int best_bn = 0, best_s = 0;
   double best = 1e30;
+  // (experiment knobs: PG_RES_BN / PG_RES_S restrict the candidates)
+  static const int force_bn = [] { const char* e = getenv("PG_RES_BN"); return e ? atoi(e) : 0; }();
+  static const int force_s = [] { const char* e = getenv("PG_RES_S"); return e ? atoi(e) : 0; }();
   for (int bn = 128; bn >= 16; bn >>= 1) {
+    if (force_bn > 0 && bn != force_bn && (d->N % force_bn) == 0) continue;
     if ((d->N % bn) != 0 || (fn->kind == PG_FUSED_BWD && (fn->n_norm % bn) != 0)) continue;
     const long long tiles = mt * (d->N / bn);
     if (tiles >= (1LL << 30)) continue;
     const double step_bytes = a_bytes + (double)bn * swz;
     for (int S = 1; S <= 32; S <<= 1) {
+      if (force_s > 0 && S != force_s) continue;
       double us;
       if (S == 1) {
         const int grid = (int)(tiles < sms ? tiles : sms);
