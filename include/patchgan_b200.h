@@ -105,6 +105,13 @@ int pg_last_conv_impl(void);
 /* number of PG_IMPL_AUTO calls of this process that found no tensor-core plan for their shape and ran on the CUDA-core
  * kernel (the first one is also reported on stderr).  bench.py and the step tests require it to stay 0. */
 int64_t pg_fallback_count(void);
+/* CTA-pair variant of the persistent convolution kernel (tcgen05.mma.cta_group::2 on clusters of two CTAs: a 256-pixel x BN
+ * tile per pair, each CTA fetching half of the weight tile).  Eligible: tile width 128 or 256 output channels, an even number
+ * of >= 148 pixel tiles, no split-K.  mode 0 = never, 1 = only where it measured faster than two co-resident single CTAs
+ * (128-wide tiles, >= 4 tile pairs per cluster), 2 = every eligible shape (parity tests, A/B runs), -1 = back to the default
+ * (environment variable PG_TC_PAIR, else 1).  pg_pair_launch_count: convolutions of this process that took the variant. */
+int pg_set_pair_mode(int32_t mode);
+int64_t pg_pair_launch_count(void);
 /* 1 if the library was built with the tcgen05 path and the current device is sm_100. */
 int pg_tcgen05_available(void);
 /* Debug hook (kernel tuning only): when buf != NULL every conv_tc CTA writes 16 uint64 (globaltimer ns at entry, after

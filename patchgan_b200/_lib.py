@@ -53,6 +53,8 @@ _SIGS = {
     'pg_launch_count': ([], C.c_int64),
     'pg_last_conv_impl': ([], C.c_int),
     'pg_fallback_count': ([], C.c_int64),
+    'pg_pair_launch_count': ([], C.c_int64),
+    'pg_set_pair_mode': ([i32], C.c_int),
     'pg_conv_fwd': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_fwd_stats': ([DP, vp, vp, vp, vp, vp, vp, C.c_int, vp], C.c_int),
     'pg_conv_dgrad_act': ([DP, vp, vp, vp, vp, i32, i32, C.c_int, vp], C.c_int),

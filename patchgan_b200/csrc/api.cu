@@ -51,6 +51,8 @@ bool tc_device_ok();
 bool conv_res_supported(const PgConvDesc*, const PgFusedNorm*, bool);
 int conv_res_launch(const PgConvDesc*, const void*, const void*, const void*, void*, void*, const PgFusedNorm*, cudaStream_t);
 void set_tc_trace(void*);
+unsigned long long pair_launch_count();
+void set_pair_mode(int);
 void set_sm_limit(int);
 void set_conv_workspace(void*, size_t);
 // conv_skinny.cu
@@ -101,6 +103,8 @@ extern "C" int pg_version(void) { return 100; }
 extern "C" int64_t pg_launch_count(void) { return (int64_t)g_launches; }
 extern "C" int pg_last_conv_impl(void) { return g_last_impl; }
 extern "C" int64_t pg_fallback_count(void) { return (int64_t)g_simt_fallbacks; }
+extern "C" int64_t pg_pair_launch_count(void) { return (int64_t)pair_launch_count(); }
+extern "C" int pg_set_pair_mode(int32_t mode) { set_pair_mode(mode); return PG_OK; }
 extern "C" int pg_tcgen05_available(void) { return tc_device_ok() ? 1 : 0; }
 extern "C" int pg_debug_set_trace(void* buf) { set_tc_trace(buf); return PG_OK; }
 extern "C" int pg_set_sm_limit(int32_t n) {

@@ -372,10 +372,25 @@ __device__ __forceinline__ void res_epilogue(const TcParams& p, const ResParams&
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = 0.f;
       const float* src = r.ws + (((long long)utile * r.splits) * 128 + row) * p.BN + (c16 << 4);
-      for (int sp = 0; sp < r.splits; ++sp) {
+      const long long sstride = 128LL * p.BN;
+      // (the partials of four splits are requested before any is added: one L2 round trip per four splits instead of one
+      //  per split -- the loop used to cost ~0.5 us per split on the layer's critical path)
+      int sp = 0;
+      for (; sp + 4 <= r.splits; sp += 4) {
+        float4 tq[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tq[u][j] = __ldcg(reinterpret_cast<const float4*>(src + (sp + u) * sstride) + j);
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { acc[4 * j] += tq[u][j].x; acc[4 * j + 1] += tq[u][j].y; acc[4 * j + 2] += tq[u][j].z; acc[4 * j + 3] += tq[u][j].w; }
+      }
+      for (; sp < r.splits; ++sp) {
         float4 tq[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) tq[j] = __ldcg(reinterpret_cast<const float4*>(src + (long long)sp * 128 * p.BN) + j);
+        for (int j = 0; j < 4; ++j) tq[j] = __ldcg(reinterpret_cast<const float4*>(src + sp * sstride) + j);
 #pragma unroll
         for (int j = 0; j < 4; ++j) { acc[4 * j] += tq[j].x; acc[4 * j + 1] += tq[j].y; acc[4 * j + 2] += tq[j].z; acc[4 * j + 3] += tq[j].w; }
       }
@@ -383,7 +398,9 @@ __device__ __forceinline__ void res_epilogue(const TcParams& p, const ResParams&
       for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(acc[j]);
       if (norm_tile) res_stats16<KIND, ACT>(p, r, v, rp, n, seed, lane, lgP);
     }
+    if (tracer) trace_raw(p.trace, 10, gtimer());
     res_grid_barrier(r.sync + 1);
+    if (tracer) trace_raw(p.trace, 11, gtimer());
     if (have) {
       // coefficient table of this group: [image of the tile][16 channels of the unit]
       float4* gtab = table + grp * (16 << lgTB);
@@ -657,7 +674,7 @@ static bool make_res_plan(const PgConvDesc* d, const PgFusedNorm* fn, bool twin,
         if (RES_GROUPS * 16 * p.TB > RES_TABLE_MAX) continue;
         const double cta = (double)(ksteps / S) * step_bytes, all = (double)tiles * ksteps * step_bytes;
         const double load = cta / 120e3 > all / 7e6 ? cta / 120e3 : all / 7e6;
-        us = load + 0.3 * (bn / 16) / RES_GROUPS + 0.05 * S + 7.0;       // dump + S-plane sum + second barrier
+        us = load + 0.3 * (bn / 16) / RES_GROUPS + 0.15 * S + 7.0;       // dump + S-plane sum + second barrier
       }
       if (us < best) { best = us; best_bn = bn; best_s = S; }
     }

@@ -84,6 +84,32 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// CTA-pair (cta_group::2) forms: the destination is this CTA's shared memory, the mbarrier may live in the peer CTA
+// (the pair's leader collects the bytes of both halves of a stage)
+__device__ __forceinline__ void tma_load_4d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], "
+      "[%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+// shared::cluster address of `addr` (an address in this CTA's shared memory) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
                "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -93,6 +119,7 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 template <int N>
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync_grp(int grp) { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
@@ -108,6 +135,14 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -119,6 +154,23 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// CTA pair: D[256 x N] over the two SMs' tensor cores; each CTA's shared memory holds its 128 rows of A and N/2 rows of B
+// at the SAME offsets, each CTA's TMEM its 128 rows of D.  Issued by the leader CTA only.
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_c),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// ... and the completion of the pair's MMAs arrives on the barrier at the same offset in both CTAs
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
 }
 // arrives on the mbarrier when all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -234,6 +286,8 @@ struct EpiCtx {
   int x0, y0, b0, n0, py, px, cls;
   int seq0 = 0;      // store chunks this CTA has issued before this tile (persistent kernel with deferred drain), else 0
   int defer = 0;     // 1: do not wait for the tile's bulk stores here; the next use of a staging buffer (or the CTA's exit) does
+  int grp = 0, ngrp = 1;   // epilogue warp groups (4 warps each; CTA-pair kernel: 2): group g takes the store chunks
+                           // ch = g (mod ngrp) of every tile, owns staging buffer g and named barrier 1 + g
 };
 
 template <int ACT>
@@ -391,18 +445,29 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
   if (p.tma_store) {
     // ---- stage the tile in the (now idle) ring smem with the TMA swizzle, store it with cp.async.bulk.tensor:
     //      full 128-byte rows instead of 32 scattered 16-byte stores per warp instruction; tails are clipped by TMA
-    const int et = threadIdx.x - 64;                     // 0..127 among the epilogue threads
+    const int et = (threadIdx.x - 64) & 127;             // 0..127 among the epilogue threads of this group
     const uint32_t bufbytes = 128u * (uint32_t)p.st_rowbytes;
     const int sh = p.st_rowbytes == 128 ? 0 : (p.st_rowbytes == 64 ? 1 : 2);
     const uint32_t xr = (uint32_t)(r >> sh) & (uint32_t)((p.st_rowbytes >> 4) - 1);   // swizzle XOR of this row
     const int cls = e.cls;
     const int nch = p.BN / p.st_cw;
-    for (int ch = 0; ch < nch; ++ch) {
-      const int g = e.seq0 + ch;                          // running chunk number: bulk groups complete in this order
-      const int buf = g % p.st_nbuf;
-      if (g >= p.st_nbuf) {                               // the buffer's previous store must have been read
-        if (et == 0) { if (p.st_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
-        epi_bar_sync();
+    for (int ch = e.grp; ch < nch; ch += e.ngrp) {
+      int buf;
+      if (e.ngrp > 1) {
+        // one staging buffer per group (st_nbuf == ngrp): its previous store (this group's previous chunk, possibly of the
+        // previous tile: seq0 = tiles done) must have been read; the other group keeps working meanwhile
+        buf = e.grp;
+        if (e.seq0 > 0 || ch >= e.ngrp) {
+          if (et == 0) bulk_wait_read<0>();
+          epi_bar_sync_grp(e.grp);
+        }
+      } else {
+        const int g = e.seq0 + ch;                        // running chunk number: bulk groups complete in this order
+        buf = g % p.st_nbuf;
+        if (g >= p.st_nbuf) {                             // the buffer's previous store must have been read
+          if (et == 0) { if (p.st_nbuf == 2) bulk_wait_read<1>(); else bulk_wait_read<0>(); }
+          epi_bar_sync();
+        }
       }
       const uint32_t prim = e.smem_base + (uint32_t)buf * bufbytes + (uint32_t)r * p.st_rowbytes;
       const uint32_t twin = e.smem_base + (uint32_t)(p.st_nbuf + buf) * bufbytes + (uint32_t)r * p.st_rowbytes;
@@ -436,7 +501,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
         }
       }
       fence_proxy_async();
-      epi_bar_sync();
+      if (e.ngrp > 1) epi_bar_sync_grp(e.grp); else epi_bar_sync();
       if (et == 0 && !(p.debug & 4)) {
         tma_store_4d(&mapsO.m[cls], e.smem_base + (uint32_t)buf * bufbytes, e.n0 + ch * p.st_cw, e.x0, e.y0, e.b0);
         if (p.st_twin)
@@ -455,7 +520,7 @@ __device__ __forceinline__ void tc_epilogue(const TcParams& p, const ActMaps& ma
     int oy = a, ox = bb;
     if (p.mode == PG_CONVT) { oy = 2 * a + e.py; ox = 2 * bb + e.px; }
     const long long opix = ((long long)b * p.Hout + oy) * p.Wout + ox;
-    for (int c = 0; c < p.BN; c += U) {
+    for (int c = e.grp * U; c < p.BN; c += U * e.ngrp) {
       float f[U];
       const int n = e.n0 + c;
       epi_load<ACT, U>(p, trow, c, n, f);
@@ -827,7 +892,7 @@ struct MmaState {
   uint32_t a_lo, b_lo, stage, phase;
 };
 
-template <int KK, bool TR = false>
+template <int KK, bool TR = false, bool PAIR = false>
 __device__ __forceinline__ void mma_issue_tile(const TcParams& p, MmaState& st, uint32_t full0, uint32_t empty0, uint32_t done_bar,
                                                uint32_t a_lo0, uint32_t b_lo0, uint64_t desc_hi, uint32_t tmem_acc, int ksteps,
                                                long long* waited = nullptr) {
@@ -847,23 +912,25 @@ __device__ __forceinline__ void mma_issue_tile(const TcParams& p, MmaState& st, 
 #pragma unroll
     for (int k = 0; k < KK; ++k) {
       const uint32_t accum = fresh == 0 ? 1u : 0u;
-      umma_bf16(tmem_acc + acc_off, desc_hi | (uint64_t)(st.a_lo + 2 * k), desc_hi | (uint64_t)(st.b_lo + 2 * k), idesc, accum);
+      if (PAIR) umma_bf16_pair(tmem_acc + acc_off, desc_hi | (uint64_t)(st.a_lo + 2 * k), desc_hi | (uint64_t)(st.b_lo + 2 * k), idesc, accum);
+      else umma_bf16(tmem_acc + acc_off, desc_hi | (uint64_t)(st.a_lo + 2 * k), desc_hi | (uint64_t)(st.b_lo + 2 * k), idesc, accum);
       fresh -= accum ^ 1u;
       acc_off += bn;
       if (acc_off == acc_wrap) acc_off = 0;
     }
-    umma_commit(empty0 + st.stage * 8);
+    if (PAIR) umma_commit_pair(empty0 + st.stage * 8); else umma_commit(empty0 + st.stage * 8);
     st.a_lo += a_step; st.b_lo += b_step;
     if (++st.stage == stages) { st.stage = 0; st.phase ^= 1; st.a_lo = a_lo0; st.b_lo = b_lo0; }
   }
-  umma_commit(done_bar);
+  if (PAIR) umma_commit_pair(done_bar); else umma_commit(done_bar);
 }
 
 struct TileXY {
   int x0, y0, b0, n0, py, px, cls;
 };
-__device__ __forceinline__ TileXY pers_decode(const TcParams& p, int w) {
-  const int mt = w % p.pers_mtiles;
+// (CTA pair: pers_mtiles counts PAIRS of adjacent m-tiles, the CTA of rank r owns the r-th of its pair)
+__device__ __forceinline__ TileXY pers_decode(const TcParams& p, int w, int pair = 0, int rank = 0) {
+  const int mt = pair ? 2 * (w % p.pers_mtiles) + rank : w % p.pers_mtiles;
   const int r = w / p.pers_mtiles;
   const int nt = r % p.pers_ntiles;
   TileXY t;
@@ -879,8 +946,15 @@ __device__ __forceinline__ TileXY pers_decode(const TcParams& p, int w) {
 // TR = true: the per-CTA trace build (tools/conv_trace.py): slots 0 start, 1 setup done, 2 first accumulator ready, 6 exit
 // (%globaltimer), 7 SM id, 8 producer cycles waiting for ring slots, 9 issuer cycles waiting for operands, 10 issuer cycles
 // waiting for a drained accumulator, 11 epilogue cycles waiting for an accumulator, 12 epilogue busy cycles, 13 tiles, 15 = 1
-template <bool TR>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+// PAIR = true: launched as clusters of two CTAs (one TPC); the pair accumulates a 256-row x BN tile with
+// tcgen05.mma.cta_group::2 -- each CTA loads its own 128 rows of A and HALF of the B tile (the weights), which is what
+// lowers the L2 -> SM bytes per flop of these L2-throughput-bound loops by 25..33 % -- the leader's full barriers collect the
+// bytes of both CTAs, the leader issues the MMAs, and its commits release the ring slots / publish the accumulators in
+// both CTAs.  Each CTA runs the ordinary epilogue on its own 128 TMEM lanes.
+constexpr int PAIR_EPI_GROUPS = 2;                      // one CTA per SM: 8 epilogue warps, like two co-resident single CTAs
+constexpr int PAIR_THREADS = 64 + 128 * PAIR_EPI_GROUPS;
+template <bool TR, bool PAIR = false>
+__global__ void __launch_bounds__(PAIR ? PAIR_THREADS : TC_THREADS, PAIR ? 1 : 2)
 conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant__ CUtensorMap mapB,
                     const __grid_constant__ ActMaps mapsO, const TcParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -896,6 +970,8 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
   const uint32_t b_base = smem_base + p.stages * p.a_bytes;
   const int nk = p.nk1 + p.nk2;
   const int ksteps = p.ntaps * nk;
+  const int rank = PAIR ? (int)cluster_rank() : 0;
+  const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, w_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&mapsA.m[0]);
@@ -907,7 +983,7 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&tfull[s]), 1);
-      mbar_init(smem_u32(&tempty[s]), 128);
+      mbar_init(smem_u32(&tempty[s]), PAIR ? 256 * PAIR_EPI_GROUPS : 128);   // pair: the epilogue threads of both CTAs release the leader's slot
     }
     fence_barrier_init();
     fence_proxy_async();
@@ -919,9 +995,12 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
     trace_raw(p.trace, 7, smid);
     trace_raw(p.trace, 15, 1);
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_sh), p.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(smem_u32(&tmem_base_sh), p.tmem_cols);
+    else tmem_alloc(smem_u32(&tmem_base_sh), p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();      // (pair: the peer's barriers exist before anything signals them)
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_sh;
   if (TR && threadIdx.x == 0) trace_raw(p.trace, 1, gtimer());
@@ -932,8 +1011,9 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       long long pwait = 0;
-      for (int w = blockIdx.x; w < p.pers_total; w += gridDim.x) {
-        const TileXY t = pers_decode(p, w);
+      const int b_row0 = PAIR ? rank * (p.BN >> 1) : 0;      // pair: this CTA's half of the weight tile
+      for (int w = w_first; w < p.pers_total; w += w_step) {
+        const TileXY t = pers_decode(p, w, PAIR, rank);
         int tap = 0, ck = 0, cx = 0, cy = 0, wtap = 0, ph = 0;
         bool newtap = true;
         for (int ks = 0; ks < ksteps; ++ks) {
@@ -968,27 +1048,43 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
           } else {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
           }
-          const uint32_t fb = smem_u32(&full_bar[stage]);
-          mbar_expect_tx(fb, p.tx_bytes);
-          if (ck < p.nk1) tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[ph], fb, ck * p.BK, cx, cy, t.b0);
-          else tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[4 + ph], fb, (ck - p.nk1) * p.BK, cx, cy, t.b0);
-          tma_load_2d(b_base + stage * p.b_bytes, &mapB, fb, wtap * p.Ctot + ck * p.BK, t.n0);
+          if (PAIR) {
+            // both CTAs' bytes complete on the LEADER's barrier (tx_bytes counts both); only the leader arrives on it
+            if (rank == 0) mbar_expect_tx(smem_u32(&full_bar[stage]), p.tx_bytes);
+            const uint32_t fb = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (ck < p.nk1) tma_load_4d_pair(a_base + stage * p.a_bytes, &mapsA.m[ph], fb, ck * p.BK, cx, cy, t.b0);
+            else tma_load_4d_pair(a_base + stage * p.a_bytes, &mapsA.m[4 + ph], fb, (ck - p.nk1) * p.BK, cx, cy, t.b0);
+            tma_load_2d_pair(b_base + stage * p.b_bytes, &mapB, fb, wtap * p.Ctot + ck * p.BK, t.n0 + b_row0);
+          } else {
+            const uint32_t fb = smem_u32(&full_bar[stage]);
+            mbar_expect_tx(fb, p.tx_bytes);
+            if (ck < p.nk1) tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[ph], fb, ck * p.BK, cx, cy, t.b0);
+            else tma_load_4d(a_base + stage * p.a_bytes, &mapsA.m[4 + ph], fb, (ck - p.nk1) * p.BK, cx, cy, t.b0);
+            tma_load_2d(b_base + stage * p.b_bytes, &mapB, fb, wtap * p.Ctot + ck * p.BK, t.n0);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
           if (++ck == nk) { ck = 0; ++tap; newtap = true; }
+        }
+      }
+      if (PAIR) {
+        // the leader's last commits still arrive on this CTA's ring barriers: see them land before the CTA may exit
+        for (int s = 0; s < p.stages; ++s) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
       if (TR) trace_raw(p.trace, 8, (unsigned long long)pwait);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer: accumulator slot it & 1 =====================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       const uint32_t a_lo0 = (a_base & 0x3FFFF) >> 4, b_lo0 = (b_base & 0x3FFFF) >> 4;
       const uint64_t desc_hi = make_smem_desc(0, p.sbo, p.layout_type);
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
       MmaState st{a_lo0, b_lo0, 0u, 0u};
       uint32_t it = 0;
       long long wfull = 0, wempty = 0;
-      for (int w = blockIdx.x; w < p.pers_total; w += gridDim.x, ++it) {
+      for (int w = w_first; w < p.pers_total; w += w_step, ++it) {
         const uint32_t slot = it & 1u;
         if (TR) {
           const long long w0 = clock64();
@@ -999,9 +1095,9 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
         }
         tc_fence_after();
         const uint32_t acc = tmem_base + slot * p.pers_slot_cols;
-        if (p.BK == 64) mma_issue_tile<4, TR>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps, &wfull);
-        else if (p.BK == 32) mma_issue_tile<2, TR>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps, &wfull);
-        else mma_issue_tile<1, TR>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps, &wfull);
+        if (p.BK == 64) mma_issue_tile<4, TR, PAIR>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps, &wfull);
+        else if (p.BK == 32) mma_issue_tile<2, TR, PAIR>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps, &wfull);
+        else mma_issue_tile<1, TR, PAIR>(p, st, full0, empty0, smem_u32(&tfull[slot]), a_lo0, b_lo0, desc_hi, acc, ksteps, &wfull);
       }
       if (TR) { trace_raw(p.trace, 9, (unsigned long long)wfull); trace_raw(p.trace, 10, (unsigned long long)wempty); }
     }
@@ -1009,8 +1105,8 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
     // ===================== epilogue =====================
     uint32_t it = 0;
     long long ewait = 0, ebusy = 0, e0 = 0;
-    for (int w = blockIdx.x; w < p.pers_total; w += gridDim.x, ++it) {
-      const TileXY t = pers_decode(p, w);
+    for (int w = w_first; w < p.pers_total; w += w_step, ++it) {
+      const TileXY t = pers_decode(p, w, PAIR, rank);
       const uint32_t slot = it & 1u;
       if (TR) {
         const long long w0 = clock64();
@@ -1025,7 +1121,8 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
       // (deferred drain: the bulk stores of this tile are still reading the staging buffer while the next tile's
       //  accumulators are read and converted; a buffer is waited for right before it is written again)
       const EpiCtx e{smem_base + p.pers_stage_off, tmem_base + slot * p.pers_slot_cols, t.x0, t.y0, t.b0, t.n0, t.py, t.px, t.cls,
-                     p.pers_defer ? (int)it * p.pers_nch : 0, p.pers_defer};
+                     PAIR ? (int)it : (p.pers_defer ? (int)it * p.pers_nch : 0), PAIR ? 1 : p.pers_defer,
+                     PAIR ? (warp - 2) >> 2 : 0, PAIR ? PAIR_EPI_GROUPS : 1};
       switch (p.act) {
         case PG_ACT_RELU: tc_epilogue<PG_ACT_RELU, 16>(p, mapsO, e); break;
         case PG_ACT_LEAKYRELU: tc_epilogue<PG_ACT_LEAKYRELU, 16>(p, mapsO, e); break;
@@ -1034,11 +1131,12 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
         default: tc_epilogue<PG_ACT_NONE, 16>(p, mapsO, e); break;
       }
       tc_fence_before();
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[slot])) : "memory");
-      if (!p.pers_defer) epi_bar_sync();      // the staging buffers are free again (thread 64 has waited for the bulk stores)
+      if (PAIR) mbar_arrive_cluster(mapa_u32(smem_u32(&tempty[slot]), 0));
+      else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[slot])) : "memory");
+      if (!PAIR && !p.pers_defer) epi_bar_sync();      // the staging buffers are free again (thread 64 has waited for the bulk stores)
       if (TR) ebusy += clock64() - e0;
     }
-    if (p.pers_defer && p.tma_store && threadIdx.x == 64) bulk_wait_read<0>();   // smem must outlive the last stores
+    if ((PAIR || p.pers_defer) && p.tma_store && ((threadIdx.x - 64) & 127) == 0) bulk_wait_read<0>();   // smem must outlive the last stores
     if (TR && threadIdx.x == 64) {
       trace_raw(p.trace, 11, (unsigned long long)ewait);
       trace_raw(p.trace, 12, (unsigned long long)ebusy);
@@ -1046,16 +1144,25 @@ conv_tc_pers_kernel(const __grid_constant__ ActMaps mapsA, const __grid_constant
     }
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, p.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_base, p.tmem_cols);
+    else tmem_dealloc(tmem_base, p.tmem_cols);
   }
   if (TR && threadIdx.x == 0) trace_raw(p.trace, 6, gtimer());
 }
 
 static unsigned long long* g_trace = nullptr;
 void set_tc_trace(void* buf) { g_trace = (unsigned long long*)buf; }
+static unsigned long long g_pair_launches = 0;
+static int g_pair_mode = -1;     // 0 never, 1 where it measured faster, 2 every eligible shape; default from PG_TC_PAIR (1)
+static int pair_mode() {
+  if (g_pair_mode < 0) { const char* e = getenv("PG_TC_PAIR"); g_pair_mode = e ? atoi(e) : 1; }
+  return g_pair_mode;
+}
+void set_pair_mode(int m) { g_pair_mode = m < 0 ? -1 : (m > 2 ? 2 : m); }
+unsigned long long pair_launch_count() { return g_pair_launches; }
 
 // --------------------------------------------------------------------------------------------
 // host side
@@ -1276,6 +1383,29 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
   p.stats = stats;
   p.mul_y = mul_y; p.mul_ld = mul_ld; p.mul_dt = mul_dt;
   const bool phased = d->mode == PG_CONV && d->stride == 2;
+  // ---- CTA-pair variant (cta_group::2) of the persistent kernel: wide tiles of the big layers, whose main loops run at
+  //      the chip's L2 -> SM throughput; the pair shares one weight tile, so each CTA fetches half of it
+  bool pair = false;
+  {
+    const int pair_env = pair_mode();
+    static const int pair_min_bn = [] { const char* e = getenv("PG_TC_PAIR_MINBN"); return e ? atoi(e) : 128; }();
+    const int ncls = d->mode == PG_CONVT ? 4 : 1;
+    const long long mtiles = (long long)pl.grid.x, ntn = d->N / p.BN;
+    const int sms = num_sms() & ~1;
+    const long long npairs = (mtiles / 2) * ntn * ncls;
+    pair = pair_env && p.splits == 1 && (mtiles & 1) == 0 && p.BN >= pair_min_bn && p.BN <= 256 && stats == nullptr &&
+           npairs >= sms / 2 && npairs < (1LL << 30);
+    // Measured on B200 (tools/conv_trace.py d, PG_TC_PAIR=2 vs 0): the pair wins 5..8 % on 128-wide tiles walked >= 4 per
+    // cluster (d1 forward, d2 data-gradient) and loses to two co-resident single CTAs on the 256-wide layers, whose main
+    // loops already run at 78..98 % of the sustained tensor rate and whose tile counts quantise worse over 74 clusters
+    // than over 296 CTA slots.  PG_TC_PAIR=2 takes every eligible shape (A/B runs, the parity tests), 0 none.
+    if (pair && pair_env == 1 && !(p.BN == 128 && npairs >= 4LL * (sms / 2))) pair = false;
+    if (pair) {
+      p.b_bytes = ((uint32_t)(p.BN / 2) * pl.swz + 1023u) & ~1023u;
+      p.tx_bytes = 2u * (128u * pl.swz + (uint32_t)(p.BN / 2) * pl.swz);
+      p.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(256 >> 4) << 24);
+    }
+  }
   ActMaps mA;
   CUtensorMap mB;
   memset(&mA, 0, sizeof(mA));
@@ -1291,7 +1421,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     const int wtaps = d->mode == PG_CONV1X1 ? 1 : 16;
     cuuint64_t dims[2] = {(cuuint64_t)wtaps * p.Ctot, (cuuint64_t)d->N};
     cuuint64_t strides[1] = {(cuuint64_t)(d->mode == PG_CONV1X1 && d->ldw > 0 ? d->ldw : wtaps * p.Ctot) * 2};
-    cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)p.BN};
+    cuuint32_t box[2] = {(cuuint32_t)p.BK, (cuuint32_t)(pair ? p.BN / 2 : p.BN)};
     cuuint32_t estr[2] = {1, 1};
     CUtensorMapSwizzle sw = pl.swz == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                           : (pl.swz == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -1321,13 +1451,13 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     const long long mtiles = (long long)pl.grid.x, ntn = d->N / p.BN;
     const long long total = mtiles * ntn * ncls;
     static const int pers_min = [] { const char* e = getenv("PG_TC_PERSIST_MIN"); return e ? atoi(e) : 1; }();
-    if (pers_env && p.splits == 1 && total >= (long long)pers_min * num_sms() && total < (1LL << 30)) {
+    if (pair || (pers_env && p.splits == 1 && total >= (long long)pers_min * num_sms() && total < (1LL << 30))) {
       int nacc = p.nacc;
-      while (nacc > 1 && 2 * nacc * p.BN > 256) nacc >>= 1;
+      while (nacc > 1 && 2 * nacc * p.BN > (pair ? 512 : 256)) nacc >>= 1;
       const int cols = 2 * nacc * p.BN;
       int tcols = 32;
       while (tcols < cols) tcols <<= 1;
-      const int occ = tcols <= 256 ? 2 : 1;
+      const int occ = (tcols <= 256 && !pair) ? 2 : 1;      // a CTA pair owns its two SMs
       const int esz = d->out_f32 == PG_F32 ? 4 : 2;
       const int rowbytes = p.BN * esz > 128 ? 128 : p.BN * esz;
       const int twin = out2 != nullptr ? 1 : 0;
@@ -1350,7 +1480,7 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
       if (stages > MAX_STAGES) stages = MAX_STAGES;
       // (BN = 256 needs all 512 TMEM columns for two slots -> one CTA per SM, which measured slower than two co-resident
       //  non-persistent CTAs: 124 vs 109 us on the largest discriminator layer)
-      if (tcols <= 256 && stages >= 2) {
+      if ((tcols <= 256 || pair) && stages >= 2) {
         pers = true;
         p.nacc = nacc;
         p.tmem_cols = (uint32_t)tcols;
@@ -1361,6 +1491,15 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
         pers_smem = (size_t)stages * per_stage + staging + 1024;
         const long long slots = (long long)num_sms() * occ;
         pers_grid = dim3((unsigned)(total < slots ? total : slots));
+        if (pair) {          // work items are pairs of m-tiles; one cluster of two CTAs per TPC
+          p.pers_mtiles = (int)(mtiles / 2);
+          p.pers_total = (int)(total / 2);
+          const long long cl = (long long)(num_sms() / 2);
+          pers_grid = dim3((unsigned)(2 * (p.pers_total < cl ? p.pers_total : cl)));
+        }
+      } else if (pair) {
+        set_error("conv_tc: CTA-pair plan does not fit (BN %d stages %d)", p.BN, stages);
+        return PG_ERR_UNSUPPORTED;
       }
     }
   }
@@ -1410,6 +1549,31 @@ int conv_fwd_tc(const PgConvDesc* d, const void* src1, const void* src2, const v
     }
     if (dbg) fprintf(stderr, "conv_tc: persistent grid %u stages %d nacc %d tmem %u smem %zu work %d\n", pers_grid.x, p.stages, p.nacc,
                      p.tmem_cols, pers_smem, p.pers_total);
+    if (pair) {
+      static bool pair_set = false;
+      if (!pair_set) {
+        PG_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
+        PG_CUDA(cudaFuncSetAttribute(conv_tc_pers_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
+        pair_set = true;
+      }
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.gridDim = pers_grid;
+      cfg.blockDim = dim3(PAIR_THREADS);
+      cfg.dynamicSmemBytes = pers_smem;
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      if (p.trace != nullptr) PG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_pers_kernel<true, true>, mA, mB, mO, p));
+      else PG_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_pers_kernel<false, true>, mA, mB, mO, p));
+      ++g_pair_launches;
+      return check_launch("conv_tc_pers_kernel<pair>");
+    }
     if (p.trace != nullptr) conv_tc_pers_kernel<true><<<pers_grid, TC_THREADS, pers_smem, stream>>>(mA, mB, mO, p);
     else conv_tc_pers_kernel<false><<<pers_grid, TC_THREADS, pers_smem, stream>>>(mA, mB, mO, p);
     return check_launch("conv_tc_pers_kernel");

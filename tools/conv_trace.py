@@ -15,6 +15,9 @@ SHAPES = [  # mode stride pad B H Ci Co outdt
     ('conv', 1, 1, 32, 32, 256, 512), ('conv', 1, 1, 32, 31, 512, 16),
 ]
 
+OUT16 = os.environ.get('PROBE_OUT', 'f32') == 'f16'     # 16-bit output + bf16 twin like the discriminator layers
+
+
 def run(mode, stride, pad, B, H, Ci, Co):
     dev = 'cuda'
     if mode == 'conv1x1':
@@ -23,19 +26,20 @@ def run(mode, stride, pad, B, H, Ci, Co):
         flops = 2.0 * B * H * H * Ci * Co
     elif mode == 'conv':
         Ho = (H + 2 * pad - 4) // stride + 1
-        d = conv_desc(L.PG_CONV, stride, pad, B, H, H, Ho, Ho, Ci, 0, Ci, 0, Co, Co, out_dt=L.DT_F32, in_dt=L.DT_F16)
+        d = conv_desc(L.PG_CONV, stride, pad, B, H, H, Ho, Ho, Ci, 0, Ci, 0, Co, Co, out_dt=L.DT_F16 if OUT16 else L.DT_F32, in_dt=L.DT_F16, act=2 if OUT16 else 0)
         flops = 2.0 * B * Ho * Ho * Ci * Co * 16
     else:
         Ho = 2 * H
-        d = conv_desc(L.PG_CONVT, 2, 1, B, H, H, Ho, Ho, Ci, 0, Ci, 0, Co, Co, out_dt=L.DT_F32, in_dt=L.DT_F16)
+        d = conv_desc(L.PG_CONVT, 2, 1, B, H, H, Ho, Ho, Ci, 0, Ci, 0, Co, Co, out_dt=L.DT_F16 if OUT16 else L.DT_F32, in_dt=L.DT_F16, act=2 if OUT16 else 0)
         flops = 2.0 * B * H * H * Ci * Co * 16
     x = torch.randn((B, H, H, Ci), device=dev, dtype=torch.float16)
     w = torch.randn((Co, 16, Ci), device=dev, dtype=torch.float16)
-    out = torch.empty((B, Ho, Ho, Co), device=dev, dtype=torch.float16 if mode == 'conv1x1' else torch.float32)
+    out = torch.empty((B, Ho, Ho, Co), device=dev, dtype=torch.float16 if (mode == 'conv1x1' or OUT16) else torch.float32)
+    twin = torch.empty((B, Ho, Ho, Co), device=dev, dtype=torch.bfloat16) if OUT16 else None
     trace = torch.zeros(1 << 20, device=dev, dtype=torch.int64)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     def call():
-        L.call('pg_conv_fwd', ctypes.byref(d), x.data_ptr(), None, w.data_ptr(), None, out.data_ptr(), None, L.IMPL_TCGEN05, st)
+        L.call('pg_conv_fwd', ctypes.byref(d), x.data_ptr(), None, w.data_ptr(), None, out.data_ptr(), twin.data_ptr() if OUT16 else None, L.IMPL_TCGEN05, st)
     for _ in range(3): call()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -74,6 +78,11 @@ if __name__ == '__main__':
                   ('conv', 2, 1, 16, 128, 32, 64), ('conv', 2, 1, 16, 64, 64, 128), ('conv', 2, 1, 32, 128, 64, 128),
                   ('convT', 2, 1, 16, 32, 256, 64), ('convT', 2, 1, 16, 64, 128, 32), ('convT', 2, 1, 32, 64, 128, 64),
                   ('convT', 2, 1, 32, 32, 256, 128), ('conv1x1', 1, 0, 32, 31, 16, 512)]:
+            run(*s)
+        sys.exit(0)
+    if len(sys.argv) >= 2 and sys.argv[1] == 'd':      # the discriminator's wide layers (CTA-pair candidates)
+        for s in [('conv', 2, 1, 32, 128, 64, 128), ('conv', 2, 1, 32, 64, 128, 256), ('conv', 1, 1, 32, 32, 256, 512),
+                  ('convT', 2, 1, 32, 32, 256, 128), ('convT', 2, 1, 32, 64, 128, 64), ('conv', 1, 2, 32, 31, 512, 256)]:
             run(*s)
         sys.exit(0)
     sel = SHAPES if len(sys.argv) < 2 else ([('conv1x1', 1, 0, 32, 128, 64, 64), ('conv1x1', 1, 0, 16, 128, 48, 32), ('conv1x1', 1, 0, 16, 128, 64, 16), ('convT', 2, 1, 32, 64, 128, 64)] if sys.argv[1] == 'p' else [s for s in SHAPES if s[3] == 32])

@@ -2,7 +2,7 @@
    python tools/res_trace.py
 For every shape: CUDA-event time of a warm launch, then one traced launch (pg_debug_set_trace): %globaltimer stamps per CTA
   0 start, 1 setup done, 2 first tile accumulated, 3 last tile accumulated, 4 phase 1 done, 5 grid barrier passed,
-  8 phase 2 done, 6 exit.  PG_TC_DEBUG=1 prints the plan (tile width, K-split) of every launch."""
+  8 phase 2 done, 6 exit; split-K launches also 10 partial sums + statistics done, 11 second grid barrier passed.  PG_TC_DEBUG=1 prints the plan (tile width, K-split) of every launch."""
 import ctypes
 import os
 import sys
@@ -49,8 +49,9 @@ def report(tag, launch, flops):
     span = (t[:, 6].max() - t0) / 1e3
     print(f'{tag:44s} ctas {len(t):3d} tiles/cta {int(t[:, 9].max()):2d} event {us:6.1f}us span {span:6.1f}us {flops / span / 1e6:7.1f} TF/s | '
           f'start {r(t[:, 0] - t0)} setup {r(t[:, 1] - t[:, 0])} first-tile {r(t[:, 2] - t[:, 1])} mainloop {r(t[:, 3] - t[:, 2])} '
-          f'phase1-tail {r(t[:, 4] - t[:, 3])} barrier {r(t[:, 5] - t[:, 4])} phase2 {r(t[:, 8] - t[:, 5])} exit {r(t[:, 6] - t[:, 8])}',
-          flush=True)
+          f'phase1-tail {r(t[:, 4] - t[:, 3])} barrier {r(t[:, 5] - t[:, 4])} phase2 {r(t[:, 8] - t[:, 5])} exit {r(t[:, 6] - t[:, 8])}'
+          + (f' | split-K: sum+stats {r(t[:, 10] - t[:, 5])} barrier2 {r(t[:, 11] - t[:, 10])} finish {r(t[:, 8] - t[:, 11])}'
+             if t[:, 10].max() > 0 else ''), flush=True)
 
 
 def run_fwd(mode, H, C1, C2, N):
