@@ -2,8 +2,10 @@
 //   TMA (cp.async.bulk.tensor, tiled mode, zero OOB fill; stride-2 layers through four phase-split views) -> swizzled smem
 //   -> tcgen05.mma (cta_group::1, kind::f16, f16 x f16 or bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
 //
-// No im2col is ever materialised.  For every (tap, channel-chunk) k-step the A operand is ONE TMA box of
-// the NHWC activation tensor:
+// No im2col of an NHWC activation is ever materialised: for every (tap, channel-chunk) k-step the A operand is ONE TMA box
+// of the activation tensor.  (The only im2col in the package is layout.cu's pg_im2col_s2 over the 3 / 4-channel NCHW float
+// IMAGES in front of the two first layers: it doubles as the NCHW -> operand-layout conversion that is needed anyway, see
+// DESIGN.md section 4.4 for the byte count.)
 //   PG_CONV  : stride 1: box {BK ch, TW, TH, TB} at (c, ox0-pad+kw, oy0-pad+kh, b0).  Stride 2: the input is viewed as
 //              four phase tensors X[b][2y'+ry][2x'+rx][c] (one tensor map each); tap (kh,kw) with u = kh-pad, v = kw-pad
 //              is the STRIDE-1 box at (c, ox0+floor(v/2), oy0+floor(u/2), b0) of phase (u&1, v&1).  (Element-strided
@@ -16,7 +18,8 @@
 //
 // Kernels in this file:
 //   conv_tc_kernel       one output tile per CTA, up to 4 CTAs per SM; optional split-K over a CTA cluster
-//   conv_tc_pers_kernel  persistent: two CTAs per SM walk the tiles, double-buffered TMEM accumulators
+//   conv_tc_pers_kernel  persistent: two CTAs per SM walk the tiles, double-buffered TMEM accumulators; <.., PAIR = true>:
+//                        clusters of two CTAs, tcgen05.mma.cta_group::2 on 256-pixel tiles, 8 epilogue warps
 //   wgrad_tc_kernel      weight gradient (MN-major operands, split-K over pixel tiles, TMA bulk-reduce epilogue)
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one lane),
 // warps 2..5 = epilogue (each owns the TMEM lane quarter warp_id % 4): bias / activation / activation-gradient /

@@ -965,8 +965,11 @@ class GeneratorEngine(NetEngine):
         d_hidden: optional bf16 Act, gradient wrt the encoder bottleneck returned by forward(return_hidden=True).
         grads: dict name -> zero-initialised float32 tensor in the reference layout (accumulated into).
         wstream: side stream for the weight-gradient launches (off the data-gradient critical path).
-        early = (i, fn): fn() is called once everything that touches the layers other than encoder 0 .. i-1 has been
-        issued (their weight-gradients on wstream, the last reads of their operand copies on the current stream).
+        early = (i, fn[, pull]): fn() is called once the data-gradient of encoder i has been issued.  At that point the
+        weight-gradients of every layer but encoder 0 .. i-1 are on wstream and the operand copies of those layers have
+        been read for the last time on the current stream.  pull=True also queues encoder i-1's weight-gradient before the
+        grouped launch (its dY exists by then; its operand copies are still read by its own data-gradient afterwards) --
+        measured slower on one GPU (the heavier group stretches the last one-launch kernel it runs beside), off by default.
 
         Every data-gradient convolution also runs the backward of the block that produced its input (activation, dropout,
         InstanceNorm; engine.dgrad_block_bwd), so the chain is one launch per layer."""
@@ -1026,15 +1029,23 @@ class GeneratorEngine(NetEngine):
                 dskip[6 - i] = din.slice(s.c1p, s.c2p)
         # d_raw is now the gradient wrt encoder 6's convolution output
         dx = None
-        for i in range(6, -1, -1):
+        pulled = -1                 # encoder layer whose weight-gradient was queued ahead of its turn (see `early`)
+
+        def enc_wgrad(i, dy):
             s = self.enc[i]
             h, out = ctx['enc'][i][0], ctx['enc'][i][3]
             if h.im2col:
-                first_wgrad(h, d_raw, grads[s.wname].data_ptr(), s.cout, wstream, self)
+                first_wgrad(h, dy, grads[s.wname].data_ptr(), s.cout, wstream, self)
             else:
                 wd = conv_desc(L.PG_CONV, 2, 1, B, h.H, h.W, out.H, out.W, h.C, 0, h.ld, 0, s.np, s.np, out_dt=BF16,
                                in_dt=BF16)
-                self.wgrad(wd, h.b16, d_raw, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
+                self.wgrad(wd, h.b16, dy, grads[s.wname].data_ptr(), s.cin * 16, s.cout, s.cin, wstream)
+
+        for i in range(6, -1, -1):
+            s = self.enc[i]
+            h, out = ctx['enc'][i][0], ctx['enc'][i][3]
+            if i != pulled:
+                enc_wgrad(i, d_raw)
             if i > 0 or need_dx:
                 Hi, Wi = (2 * h.H, 2 * h.W) if h.im2col else (h.H, h.W)
                 din = new_act(B, Hi, Wi, s.cinp, dev)
@@ -1046,7 +1057,12 @@ class GeneratorEngine(NetEngine):
                     run_conv(dd, d_raw, None, self.packed[i].bwd, None, din)
                     dx = din
             if early is not None and i == early[0]:
-                self.flush_wgrads(wstream)      # the weight-gradients of every layer but encoder 0 .. i-1: one grouped launch
+                # d_raw is now dL/d(output of encoder i-1): that layer's weight-gradient joins this group, so that only the
+                # layers below it are still open (self.early_late_layers of them)
+                if len(early) > 2 and early[2] and i >= 2 and not ctx['enc'][i - 1][0].im2col:
+                    enc_wgrad(i - 1, d_raw)
+                    pulled = i - 1
+                self.flush_wgrads(wstream)      # the weight-gradients of every layer still open: one grouped launch
                 early[1]()
         self.flush_wgrads(wstream)              # the rest (everything, without `early`)
         if wstream is None:

@@ -20,6 +20,8 @@ import glob
 import os
 from collections import defaultdict
 
+import warnings
+
 import numpy as np
 import torch
 import tqdm
@@ -40,6 +42,21 @@ def weights_init(net, init_type='normal', scaling=0.02):
     return None
 
 
+_WARNED_NON_FINITE = False
+
+
+def _warn_non_finite():
+    """Forward activations are stored as fp16 by default: |x| > 65504 becomes inf.  InstanceNorm keeps the
+    generator's activations O(1); a discriminator without normalisation loaded from a checkpoint with very large weights
+    can exceed that range, where the reference (fp32) would not."""
+    global _WARNED_NON_FINITE
+    if not _WARNED_NON_FINITE:
+        _WARNED_NON_FINITE = True
+        warnings.warn('patchgan_b200: a loss of this step is not finite.  If the fp32 reference trains this model, an '
+                      'activation probably left the fp16 range (65504): set PATCHGAN_B200_FWD_DTYPE=bf16 to store forward '
+                      'activations as bfloat16 (fp32 range, 3 fewer mantissa bits).', RuntimeWarning, stacklevel=3)
+
+
 class PendingLosses:
     """Handle returned by ``Trainer.submit``: the step is queued on the device, ``result()`` waits for its four loss
     scalars and returns the reference's six-entry loss dict (trainer.py:109-113)."""
@@ -54,6 +71,8 @@ class PendingLosses:
         if self._value is None:
             self._event.synchronize()
             seg, gdisc, discr, discf = (float(v) for v in self._host[:4])
+            if not all(np.isfinite(v) for v in (seg, gdisc, discr, discf)):
+                _warn_non_finite()
             gen_loss = float(np.float32(seg) + np.float32(gdisc))
             disc_loss = float((np.float32(discf) + np.float32(discr)) / np.float32(2.))
             self._value = dict(zip(LOSS_KEYS, [gen_loss, gen_loss, gdisc, discr, discf, disc_loss]))
@@ -313,34 +332,50 @@ class Trainer:
                     D.repack()
                 nl = len(G.specs)
 
+                KL = K      # (first layer whose gradient is final at the early point; see GeneratorEngine.backward `early`)
+
                 def early_update():
                     ev_m = torch.cuda.Event()
-                    for sw in (s_w if isinstance(s_w, list) else [s_w]):   # the weight-gradients of layers K..
+                    for sw in (s_w if isinstance(s_w, list) else [s_w]):   # the weight-gradients of layers KL..
                         if sw in E._FORKED:
                             ev_w = torch.cuda.Event()
                             ev_w.record(sw)
                             s_d.wait_event(ev_w)
-                    ev_m.record()                    # the last reads of their operand copies (data-gradients, this stream)
+                    ev_m.record()                    # the last reads of the operand copies of layers K.. (this stream)
                     s_d.wait_event(ev_m)
                     with on(s_d):
                         G.finalize_grads(partial=True)
-                        gopt.step_range(K, nl, bump=False)
-                        G.repack_layers(K, nl, complete=False)
+                        gopt.step_range(KL, nl, bump=False)
+                        G.repack_layers(K, nl, complete=False)     # (layer K-1's copies are still read by its data-gradient)
 
                 G.backward(gctx, d_raw, ggrads, wstream=s_w, early=(K, early_update))
                 E.join(s_w)
                 G.finalize_grads()
                 E.join(s_d)                          # (the early update reads the step count that the next launch bumps)
-                gopt.step_range(0, K, bump=True)
+                gopt.step_range(0, KL, bump=True)
                 G.repack_layers(0, K, complete=True)
                 E.end_step()
                 return losses
             if (ms and raw_nccl and phase == 'all' and K > 0 and len(G.specs) > K and G.layers_match_parameters()):
                 # ---- data-parallel, raw NCCL: the generator's gradient buffer is all-reduced in two buckets.  Everything
-                #      but the first K encoder layers (99 % of the bytes) is final while the backward of those K layers
-                #      still runs: it goes out on s_d, behind the discriminator's all-reduce; the small rest follows on the
-                #      main stream at the end.
-                off_k = gopt.flat()['offs'][K]
+                #      but the first K encoder layers (99 % of the bytes) is final while the backward of those K layers is
+                #      still to run: it goes out on s_d (behind the discriminator's all-reduce, update and repack) and is
+                #      followed there by the Adam update and the repack of those layers; the small rest is reduced, updated
+                #      and repacked on the main stream at the end.
+                #      The main stream WAITS until the bucket's gradients are finalized (ev_fin) before it launches the
+                #      remaining one-launch conv + InstanceNorm kernels: those occupy every SM they run on (512 threads x
+                #      128 registers), and the finalize kernel and the collective queued behind them used to start only
+                #      when the backward pass was over -- no overlap at all (in-graph timeline, tools/timeline.py under
+                #      torchrun).  Started first, the collective runs on the SMs pg_set_sm_limit keeps free.
+                KL = K      # (first layer whose gradient is final at the early point; see GeneratorEngine.backward `early`)
+                off_k = gopt.flat()['offs'][KL]
+                nl = len(G.specs)
+                gopt.grad_scale = 1.0 / world
+                with on(s_d):
+                    s_d.wait_event(ev_dread)
+                    dopt.step(sync_lr=False)
+                    D.repack()
+                ev_adam = torch.cuda.Event()
 
                 def early_allreduce():
                     ev_m = torch.cuda.Event()
@@ -351,22 +386,24 @@ class Trainer:
                             s_d.wait_event(ev_w)
                     ev_m.record()
                     s_d.wait_event(ev_m)
+                    ev_fin = torch.cuda.Event()
                     with on(s_d):
                         G.finalize_grads(partial=True)
+                        ev_fin.record()
                         dp.raw_all_reduce_sum_(gflat['g'], off_k)
+                        gopt.step_range(KL, nl, bump=False)
+                        ev_adam.record()
+                        G.repack_layers(K, nl, complete=False)     # (layer K-1's copies are still read by its data-gradient)
+                    if os.environ.get('PATCHGAN_B200_DP_HOLD', '1') != '0':
+                        torch.cuda.current_stream().wait_event(ev_fin)
 
                 G.backward(gctx, d_raw, ggrads, wstream=s_w, early=(K, early_allreduce))
                 E.join(s_w)
                 G.finalize_grads()
                 dp.raw_all_reduce_sum_(gflat['g'], 0, off_k)
-                E.join(s_d)
-                gopt.grad_scale = 1.0 / world
-                E.fork(s_d)
-                with on(s_d):
-                    dopt.step(sync_lr=False)
-                    D.repack()
-                gopt.step(sync_lr=False)
-                G.repack()
+                torch.cuda.current_stream().wait_event(ev_adam)      # (the early update reads the step count bumped next)
+                gopt.step_range(0, KL, bump=True)
+                G.repack_layers(0, K, complete=True)
                 E.join(s_d)
                 E.end_step()
                 return losses

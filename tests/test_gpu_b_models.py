@@ -94,6 +94,43 @@ def test_discriminator_forward(name):
     assert max(errs.values()) < ACT_TOL, errs
 
 
+def test_discriminator_activations_beyond_fp16_range():
+    """Range of the forward storage type.  Forward activations are fp16 by default; a discriminator
+    without normalisation whose (e.g. checkpoint) weights push activations past 65504 overflows there, where the fp32
+    reference does not.  PATCHGAN_B200_FWD_DTYPE=bf16 (Config.fwd_dt) stores them as bfloat16: same range as fp32, parity
+    with the oracle at the bf16 tolerance.  Both behaviours are pinned here."""
+    import ctypes
+    dk = D_CASES['L3']
+    od = orc.Discriminator(**dk, seed=4)
+    od.params['model.0.weight'] = od.params['model.0.weight'] * np.float32(4.0e5)       # d0 activations ~ 1e5 .. 1e6
+    x = np.random.default_rng(6).random((2, dk['input_nc'], 256, 256), dtype=np.float32)
+    od.forward(x)
+    assert float(np.abs(od.acts['d0']).max()) > 65504.0
+    xt = torch.from_numpy(x).cuda()
+    old = Config.fwd_dt
+    try:
+        for dt in (L.DT_BF16, L.DT_F16):
+            Config.fwd_dt = dt
+            D = load(P.Discriminator(**dk), od.params)
+            eng = D._engine()
+            xin = eng.new_input(2, 256, 256, 'cuda')
+            L.call('pg_pack_nchw_f32_to_nhwc_bf16', xt.data_ptr(), xin.ptr, 2, dk['input_nc'], 256, 256, xin.ld, 0, xin.dt,
+                   ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+            p, ctx = eng.forward(xin, save=True)
+            torch.cuda.synchronize()
+            d0 = ctx[0][3].t.float()
+            if dt == L.DT_BF16:
+                assert bool(torch.isfinite(d0).all())
+                assert relerr(from_nhwc(ctx[0][3].t, eng.specs[0].cout), od.acts['d0']) < 1e-2
+                # (the later layers are tanh units driven far into saturation: finite, but their sign pattern is not a
+                #  meaningful parity target)
+                assert all(bool(torch.isfinite(ctx[li][3].t.float()).all()) for li in range(1, len(eng.specs)))
+            else:
+                assert not bool(torch.isfinite(d0).all()), 'fp16 storage was expected to overflow at |x| > 65504'
+    finally:
+        Config.fwd_dt = old
+
+
 @pytest.mark.parametrize('name', ['nf8-leaky-sigmoid', 'nf16-relu-softmax', 'nf32-tanh-tanh'])
 def test_unet_autograd_gradients(name):
     gk = G_CASES[name]

@@ -1,10 +1,9 @@
 #!/bin/bash
-# CTA-pair kernel: parity tests, then A/B of the discriminator layer shapes with PG_TC_PAIR=1/0
+# CTA-pair (cta_group::2) kernel: parity tests, then the per-CTA role trace of the discriminator's wide layers with the
+# pair kernel on every eligible shape (PG_TC_PAIR=2) and off (0).   gpurun -- 'bash tools/gpu_pair.sh'
 mkdir -p gpurun_out
-timeout 900 python -m pytest -q -x -p no:cacheprovider tests/test_gpu_a5_pair.py > gpurun_out/pair_tests.log 2>&1; echo "pair tests rc=$?"; tail -n 5 gpurun_out/pair_tests.log
-for pr in 1 0; do
+timeout 900 python -m pytest -q -x -p no:cacheprovider tests/test_gpu_a5_pair.py > gpurun_out/pair_tests.log 2>&1; echo "pair tests rc=$?"; tail -n 3 gpurun_out/pair_tests.log
+for pr in 2 0; do
   echo "== PG_TC_PAIR=$pr"
-  for sh in "conv 2 32 128 64 128" "conv 2 32 64 128 256" "conv 1 32 32 256 512" "convT 2 32 32 256 128" "convT 2 32 64 128 64" "convT 2 16 32 256 128"; do
-    PROBE_OUT=f16 PROBE_ACT=2 PG_TC_PAIR=$pr timeout 120 python tools/conv_probe.py $sh 2>&1 | tail -n 1
-  done
+  PROBE_OUT=f16 PG_TC_PAIR=$pr timeout 300 python tools/conv_trace.py d 2>&1 | tail -n 8 | cut -c1-420
 done

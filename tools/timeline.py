@@ -1,7 +1,9 @@
 """In-graph timeline of one training step (cfg3): a %globaltimer stamp after every C-ABI call, on the call's stream, captured
 into the step's CUDA graph together with the kernels.  Prints, per call in completion order: stream, end time, and the time
 since the previous stamp on the same stream (= the call's duration plus whatever it waited for).
-   python tools/timeline.py [out.json]"""
+   python tools/timeline.py [out.json]
+Data-parallel: run it under torch.distributed.run (N ranks); rank 0 prints its timeline, with a stamp after every raw-NCCL
+all-reduce (`ncclAllReduce <MB>`) on the stream it was issued on."""
 import ctypes, json, os, sys, tempfile
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -10,12 +12,16 @@ import patchgan_b200 as P
 from patchgan_b200 import _lib as L
 import bench
 
+from patchgan_b200 import dp
+
 cfg = bench.CONFIGS[os.environ.get('BENCH_CONFIG', 'cfg3')]
-dev = torch.device('cuda', 0)
+rank, world, _local = dp.init_from_env()
+dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', '0')))
+torch.cuda.set_device(dev)
 torch.manual_seed(0)
 G = P.UNet(**cfg['G']).to(dev).train()
 D = P.Discriminator(**cfg['D']).to(dev).train()
-tr = P.Trainer(G, D, tempfile.mkdtemp(prefix='pgtl'), device='cuda:0')
+tr = P.Trainer(G, D, tempfile.mkdtemp(prefix='pgtl'), device=str(dev))
 tr.loss_type = cfg['loss_type']
 tr.make_optimizers(1e-3, 1e-3)
 B, S = cfg['B'], cfg['S']
@@ -41,6 +47,18 @@ def stamper(name, args):
     names.append((name, sid or 0))
     lib.pg_debug_stamp(ctypes.c_void_p(buf.data_ptr() + 8 * idx), ctypes.c_void_p(sid))
 
+
+_raw_ar = dp.raw_all_reduce_sum_
+
+
+def stamped_all_reduce(flat, first=0, count=None):
+    _raw_ar(flat, first, count)
+    if L.STAMPER is not None:
+        n = flat.numel() - first if count is None else count
+        L.STAMPER(f'ncclAllReduce {n * 4 / 1e6:.1f} MB', [ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)])
+
+
+dp.raw_all_reduce_sum_ = stamped_all_reduce
 
 for _ in range(tr.GRAPH_WARMUP):
     tr.step(x, y, True)
@@ -70,7 +88,9 @@ for i in range(n):                      # issue order gives the per-stream prede
     rows.append(dict(i=i, call=name, stream=streams[sid], end_us=(t[i] - t0) / 1e3,
                      since_prev_on_stream_us=None if prev is None else (t[i] - t[prev]) / 1e3))
     last[sid] = i
-print(f'{n} calls, span {(t.max() - t0) / 1e3:.1f} us, streams {len(streams)}')
+if rank != 0:
+    sys.exit(0)
+print(f'{n} calls, span {(t.max() - t0) / 1e3:.1f} us, streams {len(streams)}, world {world}')
 for i in order:
     r = rows[i]
     d = r['since_prev_on_stream_us']
