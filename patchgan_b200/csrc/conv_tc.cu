@@ -1641,6 +1641,7 @@ struct WgParams {
   int st_rowbytes;         // bytes per staged row (128, or 64 when ct == 16)
   int n_atoms_load;        // G boxes that exist (the accumulator rows of the others are never stored)
   int n_split;             // > 0: the G operand is the virtual concat of two tensors: channels [0, n_split) | [n_split, N)
+  int pair;                // CTA pair (cta_group::2): two n-tiles share the activation tiles, each CTA loads half of them
   unsigned long long* trace;
 };
 
@@ -1673,6 +1674,11 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* map, uint32
 
 // The kernel body: one CTA = (n-tile bx, (channel tile, tap group) by, pixel-tile split bz) of ONE weight gradient.
 // Called by wgrad_tc_kernel (one weight gradient per launch) and wgrad_group_kernel (many per launch).
+// PAIR = true (wgrad_tc_pair_kernel, clusters of two CTAs along bx): the two n-tiles of a pair accumulate [256 n][ct c] per
+// tap with tcgen05.mma.cta_group::2.  Each CTA loads its own G tile and HALF of every activation tile (the MMA's N
+// operand is split over the pair), so a pixel tile costs a CTA 32 KB instead of 48 KB through its L2 port; barriers as in
+// conv_tc_pers_kernel<.., PAIR>: the leader's full barriers collect both CTAs' bytes, its commits are multicast.
+template <bool PAIR>
 __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtensorMap* mapG2, const CUtensorMap* mapsA,
                                            const CUtensorMap* mapS, const WgParams& p, int bx, int by, int bz) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -1694,6 +1700,8 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtens
   int tile_end = tile_beg + p.tiles_per_split;
   if (tile_end > p.total_tiles) tile_end = p.total_tiles;
   const int ntiles = tile_end > tile_beg ? tile_end - tile_beg : 0;
+  const int rank = PAIR ? (int)cluster_rank() : 0;
+  const int a_first = PAIR ? rank * (p.c_atoms >> 1) : 0, a_count = PAIR ? (p.c_atoms >> 1) : p.c_atoms;
   if (threadIdx.x == 0 && p.trace != nullptr) {
     unsigned smid;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -1710,9 +1718,12 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtens
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_sh), p.tmem_cols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_pair(smem_u32(&tmem_base_sh), p.tmem_cols);
+    else tmem_alloc(smem_u32(&tmem_base_sh), p.tmem_cols);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_acc = tmem_base_sh;
   if (threadIdx.x == 0 && p.trace != nullptr) trace_raw(p.trace, 1, gtimer());
@@ -1726,21 +1737,33 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtens
         const int y0 = ((tile / p.nx) % p.ny) * p.TH;
         const int b0 = (tile / (p.nx * p.ny)) * p.TB;
         mbar_wait(smem_u32(&gempty[gs]), gph ^ 1);
-        const uint32_t gb = smem_u32(&gfull[gs]);
-        mbar_expect_tx(gb, p.n_atoms_load * p.g_boxbytes);
-        for (int a = 0; a < p.n_atoms_load; ++a) {
-          const int ch = n0 + a * p.g_box;          // (a box never straddles the two sources: n_split % g_box == 0)
-          if (p.n_split > 0 && ch >= p.n_split)
-            tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, mapG2, gb, ch - p.n_split, x0, y0, b0);
-          else
-            tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, mapG, gb, ch, x0, y0, b0);
+        if (PAIR) {
+          if (rank == 0) mbar_expect_tx(smem_u32(&gfull[gs]), 2u * p.n_atoms_load * p.g_boxbytes);
+          const uint32_t gb = mapa_u32(smem_u32(&gfull[gs]), 0);
+          for (int a = 0; a < p.n_atoms_load; ++a)
+            tma_load_4d_pair(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, mapG, gb, n0 + a * p.g_box, x0, y0, b0);
+        } else {
+          const uint32_t gb = smem_u32(&gfull[gs]);
+          mbar_expect_tx(gb, p.n_atoms_load * p.g_boxbytes);
+          for (int a = 0; a < p.n_atoms_load; ++a) {
+            const int ch = n0 + a * p.g_box;          // (a box never straddles the two sources: n_split % g_box == 0)
+            if (p.n_split > 0 && ch >= p.n_split)
+              tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, mapG2, gb, ch - p.n_split, x0, y0, b0);
+            else
+              tma_load_4d(g_base + gs * p.g_stage_bytes + a * p.g_boxbytes, mapG, gb, ch, x0, y0, b0);
+          }
         }
         if (++gs == p.g_stages) { gs = 0; gph ^= 1; }
         for (int tl = 0; tl < p.T; ++tl) {
           const int t = t0 + tl, kh = t >> 2, kw = t & 3;
           mbar_wait(smem_u32(&aempty[as]), aph ^ 1);
-          const uint32_t ab = smem_u32(&afull[as]);
-          mbar_expect_tx(ab, p.c_atoms * p.a_boxbytes);
+          uint32_t ab = smem_u32(&afull[as]);
+          if (PAIR) {
+            if (rank == 0) mbar_expect_tx(ab, p.c_atoms * p.a_boxbytes);      // both halves complete on the leader's barrier
+            ab = mapa_u32(ab, 0);
+          } else {
+            mbar_expect_tx(ab, p.c_atoms * p.a_boxbytes);
+          }
           int ph = 0, cx = x0 - p.pad + kw, cy = y0 - p.pad + kh;
           if (p.pointwise) { cx = x0; cy = y0; }
           else if (p.stride == 2) {
@@ -1749,14 +1772,21 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtens
             cx = x0 + (v >> 1);
             cy = y0 + (u >> 1);
           }
-          for (int a = 0; a < p.c_atoms; ++a)
-            tma_load_4d(a_base + as * p.a_stage_bytes + a * p.a_boxbytes, &mapsA[ph], ab, c0 + a * p.a_box, cx, cy, b0);
+          for (int a = 0; a < a_count; ++a) {
+            if (PAIR) tma_load_4d_pair(a_base + as * p.a_stage_bytes + a * p.a_boxbytes, &mapsA[ph], ab,
+                                       c0 + (a_first + a) * p.a_box, cx, cy, b0);
+            else tma_load_4d(a_base + as * p.a_stage_bytes + a * p.a_boxbytes, &mapsA[ph], ab, c0 + a * p.a_box, cx, cy, b0);
+          }
           if (++as == p.a_stages) { as = 0; aph ^= 1; }
         }
       }
+      if (PAIR) {      // the leader's last commits still arrive on this CTA's ring barriers
+        for (int s = 0; s < p.g_stages; ++s) { mbar_wait(smem_u32(&gempty[gs]), gph ^ 1); if (++gs == p.g_stages) { gs = 0; gph ^= 1; } }
+        for (int s = 0; s < p.a_stages; ++s) { mbar_wait(smem_u32(&aempty[as]), aph ^ 1); if (++as == p.a_stages) { as = 0; aph ^= 1; } }
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0 && ntiles > 0) {
+    if (lane == 0 && ntiles > 0 && rank == 0) {
       // lean single-thread issue loop (see mma_issue): loop invariants in registers, descriptors advance by adds
       const uint32_t idesc = p.idesc, T = (uint32_t)p.T, ct = (uint32_t)p.ct;
       const uint32_t g_stages = (uint32_t)p.g_stages, a_stages = (uint32_t)p.a_stages;
@@ -1777,19 +1807,21 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtens
           mbar_wait(afull0 + as * 8, aph);
           tc_fence_after();
 #pragma unroll
-          for (int k = 0; k < WG_KP / 16; ++k)
-            umma_bf16(tcol, g_hi | (uint64_t)(g_lo + k * gk), a_hi | (uint64_t)(a_lo + k * ak), idesc, (accum | k) ? 1u : 0u);
-          umma_commit(aempty0 + as * 8);
+          for (int k = 0; k < WG_KP / 16; ++k) {
+            if (PAIR) umma_bf16_pair(tcol, g_hi | (uint64_t)(g_lo + k * gk), a_hi | (uint64_t)(a_lo + k * ak), idesc, (accum | k) ? 1u : 0u);
+            else umma_bf16(tcol, g_hi | (uint64_t)(g_lo + k * gk), a_hi | (uint64_t)(a_lo + k * ak), idesc, (accum | k) ? 1u : 0u);
+          }
+          if (PAIR) umma_commit_pair(aempty0 + as * 8); else umma_commit(aempty0 + as * 8);
           tcol += ct;
           a_lo += a_step;
           if (++as == a_stages) { as = 0; aph ^= 1; a_lo = a_lo0; }
         }
         accum = 1;
-        umma_commit(gempty0 + gs * 8);
+        if (PAIR) umma_commit_pair(gempty0 + gs * 8); else umma_commit(gempty0 + gs * 8);
         g_lo += g_step;
         if (++gs == g_stages) { gs = 0; gph ^= 1; g_lo = g_lo0; }
       }
-      umma_commit(smem_u32(&acc_bar));
+      if (PAIR) umma_commit_pair(smem_u32(&acc_bar)); else umma_commit(smem_u32(&acc_bar));
       if (p.trace != nullptr) trace_raw(p.trace, 3, gtimer());
     }
   } else if (ntiles > 0) {
@@ -1894,10 +1926,11 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtens
   }
   if (threadIdx.x == 64 && p.trace != nullptr) trace_raw(p.trace, 5, gtimer());
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_acc, p.tmem_cols);
+    if (PAIR) tmem_dealloc_pair(tmem_acc, p.tmem_cols);
+    else tmem_dealloc(tmem_acc, p.tmem_cols);
   }
   if (threadIdx.x == 0 && p.trace != nullptr) trace_raw(p.trace, 6, gtimer());
 }
@@ -1905,7 +1938,13 @@ __device__ __forceinline__ void wgrad_body(const CUtensorMap* mapG, const CUtens
 __global__ void __launch_bounds__(TC_THREADS, 2)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ ActMaps mapsA,
                 const __grid_constant__ CUtensorMap mapS, const WgParams p) {
-  wgrad_body(&mapG, &mapG, mapsA.m, &mapS, p, blockIdx.x, blockIdx.y, blockIdx.z);
+  wgrad_body<false>(&mapG, &mapG, mapsA.m, &mapS, p, blockIdx.x, blockIdx.y, blockIdx.z);
+}
+// clusters of two CTAs along x (n-tiles 2i, 2i+1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
+wgrad_tc_pair_kernel(const __grid_constant__ CUtensorMap mapG, const __grid_constant__ ActMaps mapsA,
+                     const __grid_constant__ CUtensorMap mapS, const WgParams p) {
+  wgrad_body<true>(&mapG, &mapG, mapsA.m, &mapS, p, blockIdx.x, blockIdx.y, blockIdx.z);
 }
 
 // Many weight gradients in ONE launch.  The generator's backward has ~20 of them (14 layers, two sources per decoder
@@ -1935,13 +1974,13 @@ __global__ void __launch_bounds__(TC_THREADS, 2) wgrad_group_kernel(const __grid
   const WgJobDev& jb = g.jobs[j];
   const int local = (int)blockIdx.x - g.cta_begin[j];
   const int bx = local % jb.gx, r = local / jb.gx;
-  wgrad_body(&jb.mapG, &jb.mapG2, jb.mapA, &jb.mapS, jb.p, bx, r % jb.gy, r / jb.gy);
+  wgrad_body<false>(&jb.mapG, &jb.mapG2, jb.mapA, &jb.mapS, jb.p, bx, r % jb.gy, r / jb.gy);
 }
 
 static int box_of(int ch) { return ch >= 64 ? 64 : (ch >= 32 ? 32 : 16); }
 static uint32_t layout_of(int rowbytes) { return rowbytes == 128 ? 2u : (rowbytes == 64 ? 4u : 6u); }
 
-static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& smem, int split_cap = 0) {
+static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& smem, int split_cap = 0, bool want_pair = false) {
   memset(&p, 0, sizeof(p));
   if ((d->mode != PG_CONV && d->mode != PG_CONV1X1) || d->C2 != 0) return false;
   p.pointwise = d->mode == PG_CONV1X1 ? 1 : 0;
@@ -1966,8 +2005,10 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   p.g_rowbytes = p.g_box * 2; p.a_rowbytes = p.a_box * 2;
   p.g_layout = layout_of(p.g_rowbytes); p.a_layout = layout_of(p.a_rowbytes);
   p.g_boxbytes = WG_KP * p.g_rowbytes; p.a_boxbytes = WG_KP * p.a_rowbytes;
+  // CTA pair: two full n-tiles, an even number of activation boxes per tap to split between the CTAs
+  p.pair = want_pair && !p.pointwise && (N % 256) == 0 && p.c_atoms >= 2 && (p.c_atoms & 1) == 0 ? 1 : 0;
   p.g_stage_bytes = (p.n_atoms * p.g_boxbytes + 1023u) & ~1023u;
-  p.a_stage_bytes = (p.c_atoms * p.a_boxbytes + 1023u) & ~1023u;
+  p.a_stage_bytes = ((p.pair ? p.c_atoms / 2 : p.c_atoms) * p.a_boxbytes + 1023u) & ~1023u;
   // Both rings are TMA-latency-bound (a box takes ~2 us to land): the pixel-tile (G) ring is as deep as shared memory allows
   // while the tap ring keeps at least T + 2 slots (one tile's taps plus a head start on the next), at most 4 / 12 slots.
   static const int gst_env = [] { const char* e = getenv("PG_WG_GSTAGES"); return e ? atoi(e) : WG_MAX_G; }();
@@ -1986,7 +2027,7 @@ static bool make_wg_plan(const PgConvDesc* d, WgParams& p, dim3& grid, size_t& s
   // A operand = G (grad side, d->out_f32 holds its dtype), B operand = activations (d->in_dtype); both MN-major
   const uint32_t afmt = d->out_f32 == PG_F16 ? 0u : 1u, bfmt = d->in_dtype == PG_F16 ? 0u : 1u;
   p.idesc = (1u << 4) | (afmt << 7) | (bfmt << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.ct >> 3) << 17) |
-            ((uint32_t)(128 >> 4) << 24);
+            ((uint32_t)((p.pair ? 256 : 128) >> 4) << 24);
   {
     const int rows = N < 128 ? N : 128;              // (the last n-tile of a larger N may be partial: load all its boxes)
     p.n_atoms_load = N <= 128 ? (rows + p.g_box - 1) / p.g_box : p.n_atoms;
@@ -2031,9 +2072,9 @@ struct WgPrepared {
 // tap_major != 0: dw is S[16][Ns = ld_n][Cs = c_stride] (fp32, zeroed by the caller); else the reference layout
 static int wg_prepare(const PgConvDesc* d, const void* a, const void* g, int ldg, float* dw, int ld_n, int n_real, int c_real,
                       int tap_major, int Cs, int split_cap, WgPrepared& w, const void* g2 = nullptr, int ldg2 = 0,
-                      int n_split = 0) {
+                      int n_split = 0, bool want_pair = false) {
   WgParams& p = w.p;
-  if (!make_wg_plan(d, p, w.grid, w.smem, split_cap)) {
+  if (!make_wg_plan(d, p, w.grid, w.smem, split_cap, want_pair && g2 == nullptr)) {
     set_error("conv_wgrad_tc: unsupported shape");
     return PG_ERR_UNSUPPORTED;
   }
@@ -2101,11 +2142,34 @@ static int wg_prepare(const PgConvDesc* d, const void* a, const void* g, int ldg
 int conv_wgrad_tc(const PgConvDesc* d, const void* a, const void* g, int ldg, float* dw, int ld_n, int n_real,
                   int c_real, int tap_major, int Cs, cudaStream_t stream) {
   WgPrepared w;
-  if (int e = wg_prepare(d, a, g, ldg, dw, ld_n, n_real, c_real, tap_major, Cs, 0, w)) return e;
+  // (CTA pairs: default on for every eligible weight gradient -- PG_WG_PAIR=0 or pg_set_pair_mode(0) turn them off)
+  static const int wg_pair_env = [] { const char* e = getenv("PG_WG_PAIR"); return e ? atoi(e) : 1; }();
+  if (int e = wg_prepare(d, a, g, ldg, dw, ld_n, n_real, c_real, tap_major, Cs, 0, w, nullptr, 0, 0,
+                         wg_pair_env != 0 && pair_mode() != 0))
+    return e;
   static bool smem_set = false;
   if (!smem_set) {
     PG_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
+    PG_CUDA(cudaFuncSetAttribute(wgrad_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_MAX_DYN_SMEM));
     smem_set = true;
+  }
+  if (w.p.pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = w.grid;
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = w.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    PG_CUDA(cudaLaunchKernelEx(&cfg, wgrad_tc_pair_kernel, w.mG, w.mA, w.mS, w.p));
+    ++g_pair_launches;
+    return check_launch("wgrad_tc_pair_kernel");
   }
   wgrad_tc_kernel<<<w.grid, TC_THREADS, w.smem, stream>>>(w.mG, w.mA, w.mS, w.p);
   return check_launch("wgrad_tc_kernel");

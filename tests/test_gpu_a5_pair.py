@@ -101,3 +101,30 @@ def test_data_gradient_with_activation_backward_pair(case):
     torch.cuda.synchronize()
     assert pair_count() == n0 + 1, 'the CTA-pair kernel was not chosen for this shape'
     assert relerr(from_nhwc(out, Ci), ref) < 6e-3
+
+
+@pytest.mark.parametrize('tap_major', [0, 1], ids=['direct', 'tapmajor'])
+@pytest.mark.parametrize('case', [(2, 256, 512, 16, 1), (4, 128, 256, 32, 2), (3, 256, 256, 25, 1)], ids=str)
+def test_weight_gradient_pair(case, tap_major):
+    """wgrad_tc_pair_kernel: two n-tiles per cluster, each CTA loads half of every activation tile (N % 256 == 0, C >= 128)."""
+    B, Ci, Co, H, s = case
+    r = np.random.default_rng(14)
+    x = bf16_round(r.standard_normal((B, Ci, H, H)))
+    Ho = (H + 2 - 4) // s + 1
+    dy = bf16_round(r.standard_normal((B, Co, Ho, Ho)))
+    _, ref, _ = orc.conv2d_bwd(x, np.zeros((Co, Ci, 4, 4), np.float32), dy, s, has_bias=True, need_dx=False)
+    d = conv_desc(L.PG_CONV, s, 1, B, H, H, Ho, Ho, Ci, 0, Ci, 0, Co, Co, out_dt=L.DT_BF16, in_dt=L.DT_BF16)
+    xd, dyd = to_nhwc(x), to_nhwc(dy)
+    n0 = pair_count()
+    if tap_major:
+        S = torch.zeros((16, Co, Ci), device='cuda')
+        L.call('pg_conv_wgrad_tapmajor', ctypes.byref(d), xd.data_ptr(), dyd.data_ptr(), Co, S.data_ptr(), Co, Ci, TC, stream())
+        torch.cuda.synchronize()
+        got = S.cpu().numpy().reshape(4, 4, Co, Ci).transpose(2, 3, 0, 1)
+    else:
+        dw = torch.zeros((Co, Ci, 4, 4), device='cuda')
+        L.call('pg_conv_wgrad', ctypes.byref(d), xd.data_ptr(), dyd.data_ptr(), Co, dw.data_ptr(), Ci * 16, Co, Ci, TC, stream())
+        torch.cuda.synchronize()
+        got = dw.cpu().numpy()
+    assert pair_count() == n0 + 1, 'the CTA-pair weight-gradient kernel was not chosen for this shape'
+    assert relerr(got, ref) < 1e-4
