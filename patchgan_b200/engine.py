@@ -133,7 +133,7 @@ def keep(t):
     return t
 
 
-def side_streams(device, n=6):
+def side_streams(device, n=7):
     key = (device.index if device.index is not None else torch.cuda.current_device())
     if key not in _SIDE:
         _SIDE[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
