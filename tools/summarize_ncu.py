@@ -1,5 +1,5 @@
 """Turn the ncu CSVs of tools/gpu_profile.sh into the small summaries committed under profiles/.
-   python tools/summarize_ncu.py TAG ROUND      (reads gpurun_out/launches_TAG.csv, prof_TAG_raw.csv, bench_TAG.json)"""
+   python tools/summarize_ncu.py TAG ROUND      (reads gpurun_out/launches_TAG.csv, full_TAG_raw.csv, prof_TAG_raw.csv)"""
 import collections, csv, json, re, sys
 
 tag, rnd = sys.argv[1], sys.argv[2]
@@ -77,3 +77,48 @@ try:
         print(k, v)
 except (FileNotFoundError, IndexError):
     print('no full capture')
+
+
+# ---- ncu --set full of the step's main kernels (tools/gpu_profile.sh: full_TAG_raw.csv): one line per launch
+HBM_PEAK_GBS = 6558.0        # MEASURED_PEAKS.json hbm_gbs of this pool (copy bandwidth)
+try:
+    rows = list(csv.reader(open(G + f'full_{tag}_raw.csv')))
+    hdr, units = rows[0], rows[1]
+    col = {h: i for i, h in enumerate(hdr)}
+
+    def val(r, name, to=None):
+        i = col.get(name)
+        if i is None or r[i] in ('', 'n/a'):
+            return None
+        v = float(r[i].replace(',', ''))
+        if to == 'MB':
+            v *= {'byte': 1e-6, 'Kbyte': 1e-3, 'Mbyte': 1.0, 'Gbyte': 1e3}[units[i]]
+        elif to == 'us':
+            v *= {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'nsecond': 1e-3, 'usecond': 1.0, 'msecond': 1e3}[units[i]]
+        elif to == 'KB':
+            v *= {'byte': 1 / 1024, 'Kbyte': 1.0, 'Mbyte': 1024.0}[units[i].split('/')[0]]
+        return v
+
+    out = dict(what='ncu --set full --clock-control none --import-source on over the first eager G+D step of tools/step_once.py '
+                    '(cfg3, graphs and side streams off), the launches of the step\'s main kernel families; hbm_frac = DRAM '
+                    f'bytes / duration / {HBM_PEAK_GBS:.0f} GB/s (measured copy bandwidth)',
+               made_by=f'tools/gpu_profile.sh (gpurun_out/full_{tag}_raw.csv) + tools/summarize_ncu.py', launches=[])
+    for r in rows[2:]:
+        us = val(r, 'gpu__time_duration.sum', 'us')
+        rd_, wr_ = val(r, 'dram__bytes_read.sum', 'MB') or 0.0, val(r, 'dram__bytes_write.sum', 'MB') or 0.0
+        gbps = (rd_ + wr_) / us * 1e3 if us else None
+        rnd2 = lambda v, n=1: None if v is None else round(v, n)
+        out['launches'].append(dict(
+            kernel=re.sub(r'\(.*', '', r[col['Kernel Name']]).replace('void ', '').replace('pg::', ''),
+            grid=r[col['Grid Size']], block=r[col['Block Size']], us=rnd2(us, 2), dram_read_MB=rnd2(rd_, 2),
+            dram_write_MB=rnd2(wr_, 2), dram_GBps=rnd2(gbps), hbm_frac=rnd2(gbps / HBM_PEAK_GBS if gbps else None, 3),
+            tensor_pipe_pct=rnd2(val(r, 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active')),
+            warps_active_pct=rnd2(val(r, 'sm__warps_active.avg.pct_of_peak_sustained_active')),
+            regs=rnd2(val(r, 'launch__registers_per_thread'), 0),
+            dyn_smem_KB=rnd2(val(r, 'launch__shared_mem_per_block_dynamic', 'KB')),
+            l2_hit_pct=rnd2(val(r, 'lts__t_sector_hit_rate.pct')),
+            xbar2l1_read_MB=rnd2(val(r, 'l1tex__m_xbar2l1tex_read_bytes.sum', 'MB'), 2)))
+    json.dump(out, open(f'profiles/r{rnd}_ncu_full_step_kernels.json', 'w'), indent=0)
+    print('full capture:', len(out['launches']), 'launches')
+except FileNotFoundError:
+    print('no full capture of the step kernels')
