@@ -356,6 +356,34 @@ int pg_norm_act_bwd_apply(const void* x, int32_t x_f32, const float* sums, const
 int pg_norm_act_bwd(const void* x, int32_t x_f32, const float* sums, const void* dy1, int32_t ld1, const void* dy2,
                     int32_t ld2, float* bsums, void* dx, int32_t lddx, int32_t B, int64_t HW, int32_t C, int32_t ldx,
                     int32_t act, float drop_p, const uint64_t* seed, uint64_t salt, void* stream);
+/* ---- norm_layer = nn.BatchNorm2d (unet.py:77: the blocks call norm_layer(output_filt) -> BatchNorm2d(C): affine weight /
+ *      bias, running statistics, momentum 0.1, eps 1e-5).  The kernels above normalise image b with sums[b][c]; BatchNorm2d
+ *      uses one mean / variance per channel over the whole batch:
+ *      pg_bn_fold_fwd replaces every image's (sum, sum of squares) pair by the batch mean of the pairs, so the same kernels
+ *      then normalise with batch statistics.  training != 0: also running_mean / running_var <- (1 - momentum) * running +
+ *      momentum * (batch mean / unbiased batch variance), as aten::batch_norm; training == 0 (eval): the pairs are filled
+ *      from the running statistics instead.  Channels >= c_real (zero padding) are left out of the running buffers.
+ *      The *_affine_* variants insert z = gamma * xhat + beta (BatchNorm2d.weight / .bias, c_real entries; padded channels
+ *      use (1, 0)) between the normalisation and the activation, forward and backward.
+ *      pg_bn_fold_bwd: after pg_norm_affine_act_bwd_reduce left bsums[b][c] = (sum g, sum g*xhat) per image (g = dL/dz):
+ *      dbeta[c] += sum_b sum g, dgamma[c] += sum_b sum g*xhat, and the pairs are replaced by their batch mean (training) or
+ *      zero (eval: constant statistics), so pg_norm_affine_act_bwd_apply writes
+ *      dx = gamma * rstd * (g - mean(g) - xhat * mean(g*xhat)) with batch-wide means. ---- */
+int pg_bn_fold_fwd(float* sums, int32_t B, int32_t C, int64_t HW, float* running_mean, float* running_var, int32_t c_real,
+                   float momentum, int32_t training, void* stream);
+int pg_bn_fold_bwd(float* bsums, int32_t B, int32_t C, float* dgamma, float* dbeta, int32_t c_real, int32_t training,
+                   void* stream);
+int pg_norm_affine_act_fwd(const void* x, int32_t x_f32, const float* sums, const float* gamma, const float* beta,
+                           int32_t c_real, void* y, int32_t y_f32, void* y2, int32_t B, int64_t HW, int32_t C, int32_t ldx,
+                           int32_t ldy, int32_t act, float drop_p, const uint64_t* seed, uint64_t salt, void* stream);
+int pg_norm_affine_act_bwd_reduce(const void* x, int32_t x_f32, const float* sums, const float* gamma, const float* beta,
+                                  int32_t c_real, const void* dy1, int32_t ld1, const void* dy2, int32_t ld2, float* bsums,
+                                  int32_t B, int64_t HW, int32_t C, int32_t ldx, int32_t act, float drop_p,
+                                  const uint64_t* seed, uint64_t salt, void* stream);
+int pg_norm_affine_act_bwd_apply(const void* x, int32_t x_f32, const float* sums, const float* gamma, const float* beta,
+                                 int32_t c_real, const void* dy1, int32_t ld1, const void* dy2, int32_t ld2,
+                                 const float* bsums, void* dx, int32_t lddx, int32_t B, int64_t HW, int32_t C, int32_t ldx,
+                                 int32_t act, float drop_p, const uint64_t* seed, uint64_t salt, void* stream);
 /* *ctr += inc on the device (advances the dropout seed once per step, graph-capturable) */
 int pg_counter_add(uint64_t* ctr, uint64_t inc, void* stream);
 /* activation backward from the saved OUTPUT y (layers without norm: unet.py:97-99,106-107; disc.py):

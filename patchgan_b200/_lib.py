@@ -83,6 +83,13 @@ _SIGS = {
     'pg_norm_act_bwd_apply': ([vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, f32, vp, u64, vp],
                               C.c_int),
     'pg_norm_act_bwd': ([vp, i32, vp, vp, i32, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, f32, vp, u64, vp], C.c_int),
+    'pg_bn_fold_fwd': ([vp, i32, i32, i64, vp, vp, i32, f32, i32, vp], C.c_int),
+    'pg_bn_fold_bwd': ([vp, i32, i32, vp, vp, i32, i32, vp], C.c_int),
+    'pg_norm_affine_act_fwd': ([vp, i32, vp, vp, vp, i32, vp, i32, vp, i32, i64, i32, i32, i32, i32, f32, vp, u64, vp], C.c_int),
+    'pg_norm_affine_act_bwd_reduce': ([vp, i32, vp, vp, vp, i32, vp, i32, vp, i32, vp, i32, i64, i32, i32, i32, f32, vp, u64, vp],
+                                      C.c_int),
+    'pg_norm_affine_act_bwd_apply': ([vp, i32, vp, vp, vp, i32, vp, i32, vp, i32, vp, vp, i32, i32, i64, i32, i32, i32, f32, vp,
+                                      u64, vp], C.c_int),
     'pg_act_bwd_from_output': ([vp, i32, i32, vp, i32, vp, i32, i64, i32, i32, vp], C.c_int),
     'pg_softmax_fwd': ([vp, vp, i64, i32, i32, vp], C.c_int),
     'pg_target_chsum': ([vp, vp, i32, i32, i64, vp], C.c_int),

@@ -122,6 +122,23 @@ static inline size_t reduce_smem(int C) {
   return (size_t)(pow2 ? (NT / 32) * C * 2 : 2 * C) * sizeof(float);
 }
 
+// Optional per-channel affine transform between the normalisation and the activation (BatchNorm2d's weight / bias,
+// unet.py:20,55 with norm_layer = nn.BatchNorm2d): z = gamma * xhat + beta.  gamma == nullptr: identity (InstanceNorm2d,
+// affine=False).  Channels >= c_real (zero padding) use (1, 0).
+struct Affine {
+  const float* gamma;
+  const float* beta;
+  int c_real;
+};
+__device__ __forceinline__ void load_affine(const Affine& af, int c0, float* ga, float* be) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const bool on = af.gamma != nullptr && c0 + j < af.c_real;
+    ga[j] = on ? af.gamma[c0 + j] : 1.f;
+    be[j] = on ? af.beta[c0 + j] : 0.f;
+  }
+}
+
 constexpr int UNR = 4;   // independent 16/32-byte loads in flight per thread
 
 // ------------------------------------------------------------------ statistics
@@ -165,7 +182,7 @@ __global__ void __launch_bounds__(NT) instnorm_stats_kernel(const void* x, int x
 __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f32, const float* sums, void* y,
                                                           int y_f32, void* y2, long long HW, int C, int ldx, int ldy, int act,
                                                           float drop_p, const unsigned long long* seed_ptr, unsigned long long salt,
-                                                          long long ppb) {
+                                                          long long ppb, Affine af) {
   extern __shared__ float sh[];
   float* sh_mean = sh;
   float* sh_rstd = sh + C;
@@ -183,9 +200,10 @@ __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f
   }
   load_stats(sums, b, C, HW, sh_mean, sh_rstd);
   if (!s.active) return;
-  float mean[8], rstd[8];
+  float mean[8], rstd[8], ga[8], be[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { mean[j] = sh_mean[s.my_cg * 8 + j]; rstd[j] = sh_rstd[s.my_cg * 8 + j]; }
+  load_affine(af, s.my_cg * 8, ga, be);
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   while (p0 < s.pend) {
 #pragma unroll
@@ -195,7 +213,7 @@ __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f
       const long long pix = base + p;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float v = act_apply(act, (f[u][j] - mean[j]) * rstd[j]);
+        float v = act_apply(act, fmaf((f[u][j] - mean[j]) * rstd[j], ga[j], be[j]));
         if (drop_p > 0.f) {
           const float r = uniform01(seed, (unsigned long long)(pix * C + s.my_cg * 8 + j));
           v = r >= drop_p ? v * keep_scale : 0.f;
@@ -217,13 +235,15 @@ __global__ void __launch_bounds__(NT) norm_act_fwd_kernel(const void* x, int x_f
 // xk (PG_X_* >> 8): what the saved tensor x holds -- 0: the pre-norm conv output, 1: xhat itself, 2: the block's OUTPUT
 // y = act(xhat) with an invertible activation (LeakyReLU(0.2) / none; the fused forward kernel stores nothing else)
 __device__ __forceinline__ void dxhat8(const float* f, float* g, long long pix, int C, int c0, int act, float drop_p,
-                                       unsigned long long seed, const float* mean, const float* rstd, float* xhat, int xk) {
+                                       unsigned long long seed, const float* mean, const float* rstd, float* xhat, int xk,
+                                       const float* ga = nullptr, const float* be = nullptr) {
   const float keep_scale = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const float xh = xk == 0 ? (f[j] - mean[j]) * rstd[j]
                              : (xk == 2 && act == PG_ACT_LEAKYRELU && f[j] < 0.f ? 5.f * f[j] : f[j]);
-    float d = g[j] * act_grad_from_input(act, xh);
+    // (with an affine transform the activation sees z = gamma * xhat + beta; g stays d/dz, gamma is applied by the caller)
+    float d = g[j] * act_grad_from_input(act, ga != nullptr ? fmaf(xh, ga[j], be[j]) : xh);
     if (drop_p > 0.f) {
       const float u = uniform01(seed, (unsigned long long)(pix * C + c0 + j));
       d = u >= drop_p ? d * keep_scale : 0.f;
@@ -248,7 +268,7 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_reduce_kernel(const void* x, 
                                                                  const void* dy1, int ld1, const void* dy2, int ld2,
                                                                  float* bsums, long long HW, int C, int ldx, int act,
                                                                  float drop_p, const unsigned long long* seed_ptr,
-                                                                 unsigned long long salt, long long ppb) {
+                                                                 unsigned long long salt, long long ppb, Affine af) {
   const int xk = x_f32 >> 8;
   x_f32 &= 0xff;
   extern __shared__ float sh[];
@@ -257,6 +277,8 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_reduce_kernel(const void* x, 
   const Span s = make_span(C, HW, ppb);
   const long long base = (long long)b * HW;
   const int c0 = s.my_cg * 8;
+  float ga[8], be[8];
+  load_affine(af, c0, ga, be);
   // first batch of x / dy loads in flight across the (mean, rstd) prologue
   float f[UNB][8], g[UNB][8];
   long long p0 = s.pbeg + s.my_pl;
@@ -283,7 +305,7 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_reduce_kernel(const void* x, 
       for (int u = 0; u < UNB; ++u) {
         if (p0 + u * s.pl >= s.pend) break;
         float xh[8];
-        dxhat8(f[u], g[u], base + p0 + u * s.pl, C, c0, act, drop_p, seed, mean, rstd, xh, xk);
+        dxhat8(f[u], g[u], base + p0 + u * s.pl, C, c0, act, drop_p, seed, mean, rstd, xh, xk, ga, be);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           a1[j] += g[u][j];
@@ -307,7 +329,7 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
                                                                 const float* bsums, void* dx, int lddx, long long HW,
                                                                 int C, int ldx, int act, float drop_p,
                                                                 const unsigned long long* seed_ptr,
-                                                                unsigned long long salt, long long ppb) {
+                                                                unsigned long long salt, long long ppb, Affine af) {
   const int xk = x_f32 >> 8;
   x_f32 &= 0xff;
   extern __shared__ float sh[];
@@ -316,6 +338,8 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
   const Span s = make_span(C, HW, ppb);
   const long long base = (long long)b * HW;
   const int c0 = s.my_cg * 8;
+  float ga[8], be[8];
+  load_affine(af, c0, ga, be);
   float f[UNB][8], g[UNB][8];
   long long p0 = s.pbeg + s.my_pl;
   if (s.active) {
@@ -346,9 +370,9 @@ __global__ void __launch_bounds__(NT) norm_act_bwd_apply_kernel(const void* x, i
       const long long pix = base + p0 + u * s.pl;
       if (p0 + u * s.pl >= s.pend) break;
       float xh[8];
-      dxhat8(f[u], g[u], pix, C, c0, act, drop_p, seed, mean, rstd, xh, xk);
+      dxhat8(f[u], g[u], pix, C, c0, act, drop_p, seed, mean, rstd, xh, xk, ga, be);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) g[u][j] = rstd[j] * (g[u][j] - m1[j] - xh[j] * m2[j]);
+      for (int j = 0; j < 8; ++j) g[u][j] = ga[j] * rstd[j] * (g[u][j] - m1[j] - xh[j] * m2[j]);
       store8(dx, 0, pix * lddx + c0, g[u]);
     }
     p0 += UNB * s.pl;
@@ -480,6 +504,61 @@ __global__ void softmax_fwd_kernel(const float* x, float* y, long long npix, int
 
 // bps: blocks of this kernel that fit one SM (registers).  One full wave of long-lived blocks: the (mean, rstd) prologue is
 // paid once per block and there is no partial last wave.  PG_NORM_BPS=n overrides (8 = the earlier many-short-blocks grid).
+// ------------------------------------------------------------------ BatchNorm2d on top of the per-image kernels
+// The kernels above normalise image b with (sums[b][c] / HW).  BatchNorm2d (unet.py:20,55 with norm_layer = nn.BatchNorm2d)
+// uses ONE mean / variance per channel over the whole batch: fold the per-image pairs into their batch mean and write it
+// back into every image's slot, and the same kernels produce BatchNorm.  training != 0 also updates running_mean /
+// running_var the way aten::batch_norm does (momentum, unbiased variance); training == 0 fills the slots from the running
+// statistics instead (eval mode).  One thread per channel, fp64.
+__global__ void bn_fold_fwd_kernel(float* sums, int B, int C, long long HW, float* running_mean, float* running_var, int c_real,
+                                   float momentum, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, ss = 0.0;
+  if (training) {
+    for (int b = 0; b < B; ++b) {
+      s += (double)sums[((long long)b * C + c) * 2];
+      ss += (double)sums[((long long)b * C + c) * 2 + 1];
+    }
+    const double M = (double)B * (double)HW, mean = s / M;
+    double var = ss / M - mean * mean;
+    if (var < 0) var = 0;
+    if (c < c_real && running_mean != nullptr) {
+      running_mean[c] = (float)((1.0 - momentum) * running_mean[c] + momentum * mean);
+      running_var[c] = (float)((1.0 - momentum) * running_var[c] + momentum * (M > 1 ? var * M / (M - 1) : var));
+    }
+    s /= B; ss /= B;
+  } else {
+    const double m = c < c_real ? (double)running_mean[c] : 0.0, v = c < c_real ? (double)running_var[c] : 1.0;
+    s = m * (double)HW;
+    ss = (v + m * m) * (double)HW;
+  }
+  for (int b = 0; b < B; ++b) {
+    sums[((long long)b * C + c) * 2] = (float)s;
+    sums[((long long)b * C + c) * 2 + 1] = (float)ss;
+  }
+}
+// Backward: bsums[b][c] = (sum g, sum g * xhat) of image b.  dbeta[c] += sum_b sum g, dgamma[c] += sum_b sum g * xhat, and the
+// slots are replaced by their batch mean (training) or by zero (eval mode: the statistics are constants, no mean terms).
+__global__ void bn_fold_bwd_kernel(float* bsums, int B, int C, float* dgamma, float* dbeta, int c_real, int training) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double a1 = 0.0, a2 = 0.0;
+  for (int b = 0; b < B; ++b) {
+    a1 += (double)bsums[((long long)b * C + c) * 2];
+    a2 += (double)bsums[((long long)b * C + c) * 2 + 1];
+  }
+  if (c < c_real && dgamma != nullptr) {
+    dbeta[c] += (float)a1;
+    dgamma[c] += (float)a2;
+  }
+  const float m1 = training ? (float)(a1 / B) : 0.f, m2 = training ? (float)(a2 / B) : 0.f;
+  for (int b = 0; b < B; ++b) {
+    bsums[((long long)b * C + c) * 2] = m1;
+    bsums[((long long)b * C + c) * 2 + 1] = m2;
+  }
+}
+
 static void span_grid(int B, long long HW, int C, dim3& grid, long long& ppb, int bps) {
   static const int bps_env = [] { const char* e = getenv("PG_NORM_BPS"); return e ? atoi(e) : 0; }();
   if (bps_env > 0) bps = bps_env;
@@ -517,8 +596,39 @@ extern "C" int pg_norm_act_fwd(const void* x, int32_t x_f32, const float* sums, 
   dim3 grid; long long ppb;
   span_grid(B, HW, C, grid, ppb, 3);
   norm_act_fwd_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, sums, y, y_f32, y2, HW, C, ldx, ldy, act, drop_p,
-                                                            (const unsigned long long*)seed, salt, ppb);
+                                                            (const unsigned long long*)seed, salt, ppb, Affine{nullptr, nullptr, 0});
   return check_launch("norm_act_fwd_kernel");
+}
+
+extern "C" int pg_norm_affine_act_fwd(const void* x, int32_t x_f32, const float* sums, const float* gamma, const float* beta,
+                                      int32_t c_real, void* y, int32_t y_f32, void* y2, int32_t B, int64_t HW, int32_t C,
+                                      int32_t ldx, int32_t ldy, int32_t act, float drop_p, const uint64_t* seed, uint64_t salt,
+                                      void* stream) {
+  if (int e = check_c("pg_norm_affine_act_fwd", C)) return e;
+  PG_REQUIRE(gamma != nullptr && beta != nullptr && c_real > 0 && c_real <= C, "pg_norm_affine_act_fwd: gamma / beta / c_real");
+  dim3 grid; long long ppb;
+  span_grid(B, HW, C, grid, ppb, 3);
+  norm_act_fwd_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, sums, y, y_f32, y2, HW, C, ldx, ldy, act, drop_p,
+                                                            (const unsigned long long*)seed, salt, ppb, Affine{gamma, beta, c_real});
+  return check_launch("norm_act_fwd_kernel");
+}
+
+extern "C" int pg_bn_fold_fwd(float* sums, int32_t B, int32_t C, int64_t HW, float* running_mean, float* running_var, int32_t c_real,
+                              float momentum, int32_t training, void* stream) {
+  PG_REQUIRE(sums != nullptr && B > 0 && C > 0 && HW > 0 && c_real >= 0 && c_real <= C, "pg_bn_fold_fwd: bad extents");
+  PG_REQUIRE(training || (running_mean != nullptr && running_var != nullptr), "pg_bn_fold_fwd: eval mode needs the running statistics");
+  PG_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "pg_bn_fold_fwd: running_mean / running_var go together");
+  bn_fold_fwd_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(sums, B, C, HW, running_mean, running_var, c_real, momentum,
+                                                                       training);
+  return check_launch("bn_fold_fwd_kernel");
+}
+
+extern "C" int pg_bn_fold_bwd(float* bsums, int32_t B, int32_t C, float* dgamma, float* dbeta, int32_t c_real, int32_t training,
+                              void* stream) {
+  PG_REQUIRE(bsums != nullptr && B > 0 && C > 0 && c_real >= 0 && c_real <= C, "pg_bn_fold_bwd: bad extents");
+  PG_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "pg_bn_fold_bwd: dgamma / dbeta go together");
+  bn_fold_bwd_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bsums, B, C, dgamma, dbeta, c_real, training);
+  return check_launch("bn_fold_bwd_kernel");
 }
 
 extern "C" int pg_norm_act_bwd_reduce(const void* x, int32_t x_f32, const float* sums, const void* dy1, int32_t ld1,
@@ -530,7 +640,23 @@ extern "C" int pg_norm_act_bwd_reduce(const void* x, int32_t x_f32, const float*
   dim3 grid; long long ppb;
   span_grid(B, HW, C, grid, ppb, 2);
   norm_act_bwd_reduce_kernel<<<grid, NT, reduce_smem(C), (cudaStream_t)stream>>>(
-      x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb);
+      x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb,
+      Affine{nullptr, nullptr, 0});
+  return check_launch("norm_act_bwd_reduce_kernel");
+}
+
+extern "C" int pg_norm_affine_act_bwd_reduce(const void* x, int32_t x_f32, const float* sums, const float* gamma, const float* beta,
+                                             int32_t c_real, const void* dy1, int32_t ld1, const void* dy2, int32_t ld2,
+                                             float* bsums, int32_t B, int64_t HW, int32_t C, int32_t ldx, int32_t act, float drop_p,
+                                             const uint64_t* seed, uint64_t salt, void* stream) {
+  if (int e = check_c("pg_norm_affine_act_bwd_reduce", C)) return e;
+  PG_REQUIRE(sums != nullptr && gamma != nullptr && beta != nullptr && c_real > 0 && c_real <= C,
+             "pg_norm_affine_act_bwd_reduce: sums / gamma / beta / c_real");
+  dim3 grid; long long ppb;
+  span_grid(B, HW, C, grid, ppb, 2);
+  norm_act_bwd_reduce_kernel<<<grid, NT, reduce_smem(C), (cudaStream_t)stream>>>(
+      x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb,
+      Affine{gamma, beta, c_real});
   return check_launch("norm_act_bwd_reduce_kernel");
 }
 
@@ -542,7 +668,24 @@ extern "C" int pg_norm_act_bwd_apply(const void* x, int32_t x_f32, const float* 
   dim3 grid; long long ppb;
   span_grid(B, HW, C, grid, ppb, 2);
   norm_act_bwd_apply_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, dx,
-                                                                  lddx, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb);
+                                                                  lddx, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb,
+                                                                  Affine{nullptr, nullptr, 0});
+  return check_launch("norm_act_bwd_apply_kernel");
+}
+
+extern "C" int pg_norm_affine_act_bwd_apply(const void* x, int32_t x_f32, const float* sums, const float* gamma, const float* beta,
+                                            int32_t c_real, const void* dy1, int32_t ld1, const void* dy2, int32_t ld2,
+                                            const float* bsums, void* dx, int32_t lddx, int32_t B, int64_t HW, int32_t C,
+                                            int32_t ldx, int32_t act, float drop_p, const uint64_t* seed, uint64_t salt,
+                                            void* stream) {
+  if (int e = check_c("pg_norm_affine_act_bwd_apply", C)) return e;
+  PG_REQUIRE(sums != nullptr && gamma != nullptr && beta != nullptr && c_real > 0 && c_real <= C,
+             "pg_norm_affine_act_bwd_apply: sums / gamma / beta / c_real");
+  dim3 grid; long long ppb;
+  span_grid(B, HW, C, grid, ppb, 2);
+  norm_act_bwd_apply_kernel<<<grid, NT, 2 * C * sizeof(float), (cudaStream_t)stream>>>(x, x_f32, sums, dy1, ld1, dy2, ld2, bsums, dx,
+                                                                  lddx, HW, C, ldx, act, drop_p, (const unsigned long long*)seed, salt, ppb,
+                                                                  Affine{gamma, beta, c_real});
   return check_launch("norm_act_bwd_apply_kernel");
 }
 

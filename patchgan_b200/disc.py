@@ -85,8 +85,13 @@ class Discriminator(nn.Module, Transferable):
 
     def __init__(self, input_nc, ndf=64, n_layers=3, norm=False, norm_layer=nn.InstanceNorm2d):
         super(Discriminator, self).__init__()
-        if norm_layer is not nn.InstanceNorm2d:
-            raise NotImplementedError('patchgan_b200.Discriminator implements norm_layer=nn.InstanceNorm2d only')
+        # (norm_layer is only instantiated when norm=True, disc.py:31-32,41-42: with the default norm=False any value is inert)
+        if norm and norm_layer is not nn.InstanceNorm2d:
+            raise NotImplementedError(
+                'patchgan_b200.Discriminator(norm=True) implements norm_layer=nn.InstanceNorm2d only.  A BatchNorm2d '
+                'discriminator couples the images of a call, and Trainer.batch calls the reference discriminator three times '
+                'per step (fake, real, fake again: trainer.py:65,96,98) with separate batch statistics and three running-'
+                'statistics updates, which the batched [fake ; real] discriminator pass of this package does not reproduce.')
         self.input_nc, self.ndf, self.n_layers, self.norm = input_nc, ndf, n_layers, norm
         sequence = [_Holder((ndf, input_nc, 4, 4), input_nc * 16, bias_n=ndf), _Slot('LeakyReLU(0.2)')]
         nf_mult = 1

@@ -314,10 +314,11 @@ def fused_conv_norm(desc, src1, src2, w, out, act, drop_p, seed, salt, want_xhat
 
 class Block:
     """What the backward of one conv -> [norm] -> act -> [dropout] block needs from its forward."""
-    __slots__ = ('spec', 'raw', 'sums', 'out', 'dp', 'xh', 'salt')
+    __slots__ = ('spec', 'raw', 'sums', 'out', 'dp', 'xh', 'salt', 'bn')
 
-    def __init__(self, spec, raw, sums, out, dp, xh, salt):
+    def __init__(self, spec, raw, sums, out, dp, xh, salt, bn=None):
         self.spec, self.raw, self.sums, self.out, self.dp, self.xh, self.salt = spec, raw, sums, out, dp, xh, salt
+        self.bn = bn      # BatchNorm2d blocks: (gamma, beta, dgamma, dbeta, training) tensors / flag, else None
 
 
 def _shift_desc(desc, n0, n):
@@ -338,7 +339,7 @@ def dgrad_block_bwd(desc, dy, w, wrow_bytes, din, n_norm, blk, dskip, seed):
     act = L.ACT[s.act]
     wp = w if isinstance(w, int) else w.data_ptr()
     can = blk.xh is not None or (s.act in INVERTIBLE and blk.dp == 0)
-    if s.norm and can and taps_enabled() and Config.fused_bwd:
+    if s.norm and can and taps_enabled() and Config.fused_bwd and blk.bn is None:
         dev = din.t.device
         fn = L.FusedNorm()
         fn.kind, fn.act, fn.n_norm, fn.drop_p, fn.salt = L.FUSED_BWD, act, n_norm, float(blk.dp), blk.salt
@@ -374,6 +375,8 @@ def dgrad_block_bwd(desc, dy, w, wrow_bytes, din, n_norm, blk, dskip, seed):
     d_prev = din.slice(0, n_norm)
     if not s.norm:
         return act_bwd_out(blk.out, d_prev, act)
+    if blk.bn is not None:
+        return batchnorm_bwd(blk.raw, blk.sums, blk.bn, s.cout, d_prev, dskip, act, blk.dp, seed, blk.salt)
     if blk.raw is not None:
         x, kind = blk.raw, 0
     elif blk.xh is not None:
@@ -505,7 +508,9 @@ def first_wgrad(a, g, dw_ptr, n_real, wstream=None, eng=None):
 class LayerSpec:
     """One 4x4 convolution layer of either network."""
 
-    def __init__(self, kind, stride, c1, c2, cout, bias, act, norm, dropout, wname, bname=None, norm_after_act=False):
+    def __init__(self, kind, stride, c1, c2, cout, bias, act, norm, dropout, wname, bname=None, norm_after_act=False,
+                 bn=None):
+        self.bn = bn          # norm_layer = nn.BatchNorm2d: state_dict prefix of the layer's BatchNorm2d module, else None
         self.kind, self.stride, self.c1, self.c2, self.cout = kind, stride, c1, c2, cout
         self.bias, self.act, self.norm, self.dropout = bias, act, norm, dropout
         self.wname, self.bname, self.norm_after_act = wname, bname, norm_after_act
@@ -836,6 +841,44 @@ def norm_bwd(x, sums, dy1, dy2, act, drop_p, seed, salt, xkind=0):
     return dx
 
 
+BN_MOMENTUM = 0.1     # nn.BatchNorm2d default (unet.py:20,55 call norm_layer(output_filt) with defaults)
+
+
+def batchnorm_fwd(raw, sums, bn, c_real, out, act, drop_p, seed, salt, training):
+    """raw (fp32 conv output) + its per-(image, channel) sums -> out = dropout(act(BatchNorm2d(raw))).
+    bn = (gamma, beta, running_mean, running_var, num_batches_tracked) tensors of the layer's BatchNorm2d module.
+    `sums` is folded to batch statistics in place (kept for the backward)."""
+    gamma, beta, rmean, rvar, nbt = bn
+    st = _stream()
+    L.call('pg_bn_fold_fwd', sums.data_ptr(), raw.B, raw.C, raw.H * raw.W, rmean.data_ptr(), rvar.data_ptr(), c_real,
+           BN_MOMENTUM, 1 if training else 0, st)
+    if training and nbt is not None:
+        L.call('pg_counter_add', nbt.data_ptr(), 1, st)
+    L.call('pg_norm_affine_act_fwd', raw.ptr, raw.dt, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), c_real, out.ptr,
+           out.dt, out.twptr, raw.B, raw.H * raw.W, raw.C, raw.ld, out.ld, act, drop_p,
+           seed.data_ptr() if seed is not None else None, salt, st)
+
+
+def batchnorm_bwd(raw, sums, bn, c_real, dy1, dy2, act, drop_p, seed, salt):
+    """Backward of dropout / act / BatchNorm2d: returns d(raw) as a new bf16 Act and accumulates dgamma / dbeta.
+    bn = (gamma, beta, dgamma, dbeta, training)."""
+    gamma, beta, dgamma, dbeta, training = bn
+    dev = raw.t.device
+    HW = raw.H * raw.W
+    dx = new_act(raw.B, raw.H, raw.W, raw.C, dev)
+    bsums = zeros((raw.B, raw.C, 2), dev)
+    sp = seed.data_ptr() if seed is not None else None
+    p2, l2 = (dy2.ptr, dy2.ld) if dy2 is not None else (None, 0)
+    st = _stream()
+    L.call('pg_norm_affine_act_bwd_reduce', raw.ptr, raw.dt, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), c_real,
+           dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), raw.B, HW, raw.C, raw.ld, act, drop_p, sp, salt, st)
+    L.call('pg_bn_fold_bwd', bsums.data_ptr(), raw.B, raw.C, dgamma.data_ptr() if dgamma is not None else None,
+           dbeta.data_ptr() if dbeta is not None else None, c_real, 1 if training else 0, st)
+    L.call('pg_norm_affine_act_bwd_apply', raw.ptr, raw.dt, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), c_real,
+           dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), dx.ptr, dx.ld, raw.B, HW, raw.C, raw.ld, act, drop_p, sp, salt, st)
+    return dx
+
+
 def act_bwd_out(y, dy, act):
     dx = new_act(y.B, y.H, y.W, y.C, y.t.device)
     L.call('pg_act_bwd_from_output', y.ptr, y.dt, y.ld, dy.ptr, dy.ld, dx.ptr, dx.ld, y.B * y.H * y.W, y.C, act,
@@ -852,9 +895,11 @@ class GeneratorEngine(NetEngine):
         nf, inc, outc = module.nf, module.input_nc, module.output_nc
         filts = [nf, nf * 2, nf * 4, nf * 8, nf * 8, nf * 8, nf * 8]
         specs, prev = [], inc
+        bn = bool(getattr(module, 'batchnorm', False))
         for i, f in enumerate(filts):
             specs.append(LayerSpec('conv', 2, prev, 0, f, False, module.activation, True, module.use_dropout,
-                                   f'encoder.{i}.model.DownConv{i}.weight'))
+                                   f'encoder.{i}.model.DownConv{i}.weight',
+                                   bn=f'encoder.{i}.model.DownNorm{i}' if bn else None))
             prev = f
         enc_out = filts
         for i, f in enumerate(filts[:-1][::-1]):
@@ -863,7 +908,8 @@ class GeneratorEngine(NetEngine):
                                        f'decoder.{i}.model.UpConv{i}.weight'))
             else:
                 specs.append(LayerSpec('convT', 2, prev, enc_out[6 - i], f, False, module.activation, True,
-                                       module.use_dropout, f'decoder.{i}.model.UpConv{i}.weight'))
+                                       module.use_dropout, f'decoder.{i}.model.UpConv{i}.weight',
+                                       bn=f'decoder.{i}.model.UpNorm{i}' if bn else None))
             prev = f
         specs.append(LayerSpec('convT', 2, prev, enc_out[0], outc, False, module.final_act, False, False,
                                'decoder.6.model.UpConv6.weight'))
@@ -871,6 +917,16 @@ class GeneratorEngine(NetEngine):
         self.enc, self.dec = specs[:7], specs[7:]
         self.in_cp = rup16(inc)
         self.out_cp = rup16(outc)
+
+    def bn_tensors(self, s):
+        """(weight, bias, running_mean, running_var, num_batches_tracked) of layer s's BatchNorm2d module."""
+        ps, bs = self.params(), dict(self.module.named_buffers())
+        return (ps[s.bn + '.weight'], ps[s.bn + '.bias'], bs[s.bn + '.running_mean'], bs[s.bn + '.running_var'],
+                bs.get(s.bn + '.num_batches_tracked'))
+
+    def bn_names(self):
+        """names of the BatchNorm2d affine parameters, in layer order (empty for InstanceNorm2d)"""
+        return [s.bn + sfx for s in self.specs if s.bn is not None for sfx in ('.weight', '.bias')]
 
     def pack_input(self, x, twin=False):
         """NCHW float -> NHWC bf16 with channels zero-padded to 16."""
@@ -901,15 +957,21 @@ class GeneratorEngine(NetEngine):
             out = new_act(B, Ho, Wo, s.np, dev, dt=src1.dt, twin=save)
             dp = DROP_P if (training and s.dropout) else 0.0
             desc.ldo, desc.out_f32, desc.n_valid = out.ld, out.dt, s.cout
-            fused = fused_conv_norm(desc, src1, src2, w, out, L.ACT[s.act], dp, self.seed, salt,
-                                    save and (dp > 0 or s.act not in INVERTIBLE))
+            fused = None
+            if s.bn is None:
+                fused = fused_conv_norm(desc, src1, src2, w, out, L.ACT[s.act], dp, self.seed, salt,
+                                        save and (dp > 0 or s.act not in INVERTIBLE))
             if fused is not None:
                 return None, fused[0], out, dp, fused[1]
             raw = new_act(B, Ho, Wo, s.np, dev, dt=F32)
             sums = zeros((B, s.np, 2), dev)
             desc.ldo, desc.out_f32, desc.n_valid = raw.ld, F32, s.np
             run_conv(desc, src1, src2, w, None, raw, sums)
-            norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, salt)
+            if s.bn is not None:
+                # norm_layer = nn.BatchNorm2d: batch statistics (running ones in eval mode) + affine, three launches
+                batchnorm_fwd(raw, sums, self.bn_tensors(s), s.cout, out, L.ACT[s.act], dp, self.seed, salt, training)
+            else:
+                norm_fwd(raw, sums, out, L.ACT[s.act], dp, self.seed, salt)
             return raw, sums, out, dp, None
 
         for i, s in enumerate(self.enc):
@@ -977,13 +1039,21 @@ class GeneratorEngine(NetEngine):
         B = d_raw.B
         dskip = [None] * 7
 
+        ps = self.params()
+
+        def bn_of(s):
+            if s.bn is None:
+                return None
+            gw, gb = grads.get(s.bn + '.weight'), grads.get(s.bn + '.bias')
+            return (ps[s.bn + '.weight'], ps[s.bn + '.bias'], gw, gb, bool(ctx.get('training', True)))
+
         def block_of_dec(j):
             _, _, raw, sums, out, dp, xh = ctx['dec'][j]
-            return Block(self.dec[j], raw, sums, out, dp, xh, 16 + j)
+            return Block(self.dec[j], raw, sums, out, dp, xh, 16 + j, bn_of(self.dec[j]))
 
         def block_of_enc(j):
             _, raw, sums, out, dp, xh = ctx['enc'][j]
-            return Block(self.enc[j], raw, sums, out, dp, xh, j)
+            return Block(self.enc[j], raw, sums, out, dp, xh, j, bn_of(self.enc[j]))
 
         self.begin_backward(group=True)
         for i in range(6, -1, -1):

@@ -35,8 +35,10 @@ class DownSampleBlock(nn.Module):
 
     def __init__(self, input_filt, output_filt, activation, norm_layer, layer, use_dropout=False, **kwargs):
         super().__init__()
-        self.model = nn.Sequential(OrderedDict([
-            (f'DownConv{layer}', _Holder((output_filt, input_filt, 4, 4), input_filt * 16))]))
+        mods = [(f'DownConv{layer}', _Holder((output_filt, input_filt, 4, 4), input_filt * 16))]
+        if norm_layer is nn.BatchNorm2d:      # parameter / buffer holder, same state_dict keys as the reference's module
+            mods.append((f'DownNorm{layer}', nn.BatchNorm2d(output_filt)))
+        self.model = nn.Sequential(OrderedDict(mods))
 
 
 class UpSampleBlock(nn.Module):
@@ -46,8 +48,10 @@ class UpSampleBlock(nn.Module):
                  **kwargs):
         super().__init__()
         # torch computes fan_in of a ConvTranspose2d weight (Cin, Cout, 4, 4) from dim 1
-        self.model = nn.Sequential(OrderedDict([
-            (f'UpConv{layer}', _Holder((input_filt, output_filt, 4, 4), output_filt * 16))]))
+        mods = [(f'UpConv{layer}', _Holder((input_filt, output_filt, 4, 4), output_filt * 16))]
+        if batch_norm and norm_layer is nn.BatchNorm2d:
+            mods.append((f'UpNorm{layer}', nn.BatchNorm2d(output_filt)))
+        self.model = nn.Sequential(OrderedDict(mods))
 
 
 class _UNetFunction(torch.autograd.Function):
@@ -101,7 +105,7 @@ class _UNetFunction(torch.autograd.Function):
         d_raw = new_act(B, H, W, eng.out_cp, dev)
         L.call('pg_gen_out_bwd', p.ptr, p.ld, None, None, None, dpk.ptr, dpk.ld, 0, d_raw.ptr, d_raw.ld, B,
                module.output_nc, H * W, L.LOSS['none'], L.ACT[module.final_act], 0.0, _stream())
-        names = [s.wname for s in eng.specs]
+        names = [s.wname for s in eng.specs] + eng.bn_names()
         params = eng.params()
         grads = {n: torch.zeros_like(params[n], dtype=torch.float32) for n in names}
         dx = eng.backward(ctx.saved, d_raw, grads, need_dx=ctx.x_needs_grad, d_hidden=d_hid)
@@ -116,9 +120,13 @@ class UNet(nn.Module, Transferable):
     def __init__(self, input_nc, output_nc, nf=64, norm_layer=nn.InstanceNorm2d, use_dropout=False,
                  activation='tanh', final_act='softmax'):
         super(UNet, self).__init__()
-        if norm_layer is not nn.InstanceNorm2d:
-            raise NotImplementedError('patchgan_b200.UNet implements the reference default norm_layer=nn.InstanceNorm2d '
-                                      '(affine=False) only')
+        if norm_layer not in (nn.InstanceNorm2d, nn.BatchNorm2d):
+            raise NotImplementedError('patchgan_b200.UNet implements norm_layer=nn.InstanceNorm2d (the reference default) '
+                                      'and nn.BatchNorm2d')
+        # BatchNorm2d: batch statistics + affine weight / bias + running buffers; runs the un-fused kernels (conv with the
+        # statistics in its epilogue, pg_bn_fold_*, pg_norm_affine_act_*) -- the one-launch conv + norm kernels are
+        # InstanceNorm-only
+        self.batchnorm = norm_layer is nn.BatchNorm2d
         if activation not in ('tanh', 'relu', 'leakyrelu'):
             raise ValueError(f'activation must be tanh / relu / leakyrelu, got {activation!r}')
         if final_act not in _ACTS:
@@ -155,7 +163,8 @@ class UNet(nn.Module, Transferable):
 
     def _weights(self):
         ps = dict(self.named_parameters())
-        return [ps[s.wname] for s in self._engine().specs]
+        eng = self._engine()
+        return [ps[s.wname] for s in eng.specs] + [ps[n] for n in eng.bn_names()]
 
     def forward(self, x, return_hidden=False):
         require_cuda(x, 'UNet input')

@@ -13,6 +13,13 @@ CASES = {
 }
 NS = 256
 
+# norm_layer = nn.BatchNorm2d in the generator (unet.py:77; the discriminator keeps its default norm=False).  'norm': 'batch' is
+# the oracle's spelling; make_golden.py / the GPU tests translate it to norm_layer=nn.BatchNorm2d.  Fixture: step_bn.npz
+BN_CASES = {
+    'bn': (dict(input_nc=3, output_nc=1, nf=8, activation='leakyrelu', final_act='sigmoid', norm='batch'),
+           dict(input_nc=4, ndf=8, n_layers=3, norm=False), 'tversky', 2, 2),
+}
+
 # The BASELINE.json architectures at (or near) their benchmarked sizes -- goldens from the live reference only (the numpy
 # oracle would take minutes at these sizes; it is pinned by the small cases above):
 #   name: (G kwargs, D kwargs, loss_type, B, S, steps)

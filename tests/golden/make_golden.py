@@ -33,15 +33,20 @@ from oracle import patchgan_oracle as orc  # noqa: E402
 
 ref_trainer.device = 'cpu'
 
-from tests.golden.cases import BIG_CASES, CASES, NS, rect_batch, summarize  # noqa: E402,F401
+from tests.golden.cases import BIG_CASES, BN_CASES, CASES, NS, rect_batch, summarize  # noqa: E402,F401
 
 
 def run_case(name, gk, dk, loss_type, B, steps, S=256):
     og = orc.UNet(**gk, seed=11)
     od = orc.Discriminator(**dk, seed=12)
-    G = patchgan.UNet(**gk)
+    ref_gk = dict(gk)
+    if ref_gk.pop('norm', 'instance') == 'batch':
+        ref_gk['norm_layer'] = torch.nn.BatchNorm2d
+    G = patchgan.UNet(**ref_gk)
     D = patchgan.Discriminator(**dk)
-    G.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in og.params.items()})
+    # (strict=False: BatchNorm's running buffers keep their defaults, which are the oracle's too)
+    missing = G.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in og.params.items()}, strict=False)
+    assert not missing.unexpected_keys and all('running_' in k or 'num_batches' in k for k in missing.missing_keys), missing
     D.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in od.params.items()})
     import tempfile
     tr = patchgan.Trainer(G, D, tempfile.mkdtemp(), device='cpu')
@@ -82,6 +87,9 @@ def run_case(name, gk, dk, loss_type, B, steps, S=256):
         for k, p in D.named_parameters():
             out[f's{step}/dgrad/{k}'] = summarize(p.grad.numpy())
             out[f's{step}/dw/{k}'] = summarize(p.detach().numpy())
+        for k, b in G.named_buffers():
+            if 'running_' in k:
+                out[f's{step}/gbuf/{k}'] = summarize(b.numpy())
     # eval-mode forward / train=False batch (trainer.py:239-259)
     G.eval()
     D.eval()
@@ -228,6 +236,9 @@ if __name__ == '__main__':
     for name, (gk, dk, lt, B, S, steps) in BIG_CASES.items():
         if not only or name in only:
             run_case(name, gk, dk, lt, B, steps, S)
+    for name, (gk, dk, lt, B, steps) in BN_CASES.items():
+        if not only or name in only:
+            run_case(name, gk, dk, lt, B, steps)
     if not only or 'rect' in only:
         rect_case()
     if not only or 'losses' in only:

@@ -1,0 +1,150 @@
+"""norm_layer = nn.BatchNorm2d in the generator (unet.py:77 takes the layer class as an argument; DownSampleBlock /
+UpSampleBlock call norm_layer(output_filt), unet.py:20,55): batch statistics, affine weight / bias, running buffers,
+train and eval mode.  Checked against the numpy oracle (oracle.UNet(norm='batch'), itself pinned to the live reference's
+tests/golden/step_bn.npz) and against that fixture directly.  Tolerances as for the InstanceNorm generator
+(tests/test_gpu_b_models.py, tests/test_gpu_c_step.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+import patchgan_b200 as P
+from oracle import patchgan_oracle as orc
+from patchgan_b200 import _lib as L
+from patchgan_b200.engine import Config
+from tests.golden.cases import BN_CASES
+from tests.gpu_util import relerr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), 'golden')
+ACT_TOL = 1e-2
+GRAD_TOL_GATED = 8e-2
+
+
+def ref_kwargs(gk):
+    k = dict(gk)
+    if k.pop('norm', 'instance') == 'batch':
+        k['norm_layer'] = nn.BatchNorm2d
+    return k
+
+
+def load(module, og):
+    sd = {k: torch.from_numpy(v.copy()) for k, v in og.params.items()}
+    sd.update({k: torch.from_numpy(v.copy()) for k, v in og.buffers.items()})
+    missing = module.load_state_dict(sd, strict=False)
+    assert not missing.unexpected_keys and all('num_batches_tracked' in k for k in missing.missing_keys), missing
+    return module.cuda()
+
+
+def quant_kwargs():
+    return dict(fwd=orc.round_f16 if Config.fwd_dt == L.DT_F16 else orc.round_bf16, grad=orc.round_bf16, fused=False)
+
+
+def test_state_dict_keys_match_the_reference_layout():
+    g = P.UNet(3, 1, 8, norm_layer=nn.BatchNorm2d)
+    keys = list(g.state_dict().keys())
+    assert 'encoder.0.model.DownNorm0.running_var' in keys and 'decoder.5.model.UpNorm5.weight' in keys
+    assert not any(k.startswith('decoder.0.model.UpNorm') or k.startswith('decoder.6.model.UpNorm') for k in keys)
+    assert len(keys) == 14 + 12 * 5                       # 14 convolutions, 12 BatchNorm2d modules x 5 entries
+    # (a discriminator without norm layers never instantiates norm_layer: any class is accepted there)
+    P.Discriminator(4, 8, n_layers=3, norm=False, norm_layer=nn.BatchNorm2d)
+    with pytest.raises(NotImplementedError):
+        P.Discriminator(4, 8, n_layers=3, norm=True, norm_layer=nn.BatchNorm2d)
+
+
+@pytest.mark.parametrize('act', ['leakyrelu', 'tanh'])
+def test_batchnorm_unet_forward_backward_train_and_eval(act):
+    gk = dict(input_nc=3, output_nc=2, nf=8, activation=act, final_act='sigmoid', norm='batch')
+    og = orc.UNet(**gk, seed=5)
+    rng = np.random.default_rng(8)
+    for k in og.params:                                   # non-trivial affine parameters
+        if 'Norm' in k and k.endswith('.weight'):
+            og.params[k] = (0.5 + rng.random(og.params[k].shape)).astype(np.float32)
+        elif 'Norm' in k and k.endswith('.bias'):
+            og.params[k] = (0.2 * rng.standard_normal(og.params[k].shape)).astype(np.float32)
+    G = load(P.UNet(**ref_kwargs(gk)), og).train()
+    x = rng.random((3, 3, 256, 256), dtype=np.float32)
+    dout = rng.standard_normal((3, 2, 256, 256)).astype(np.float32)
+    # ---- training mode: batch statistics, running buffers updated
+    orc.set_quant(**quant_kwargs())
+    try:
+        ref = og.forward(x, keep=True)
+        rg = og.backward(dout)                            # dout = gradient wrt the (post-sigmoid) output
+    finally:
+        orc.set_quant()
+    xt = torch.from_numpy(x).cuda()
+    out = G(xt)
+    out.backward(torch.from_numpy(dout).cuda())
+    torch.cuda.synchronize()
+    assert relerr(out.detach().cpu().numpy(), ref) < ACT_TOL
+    errs = {k: relerr(p.grad.cpu().numpy(), rg[k]) for k, p in G.named_parameters()}
+    print(act, 'grad err', {k.split('.model.')[-1]: f'{v:.1e}' for k, v in errs.items()})
+    # (smooth activation: 2e-2 for the convolution weights as in test_gpu_b_models.py; the BatchNorm bias gradients are plain
+    #  sums of dL/dz over B x H x W with heavy cancellation, where bf16 gradient storage + atomic summation order show: 3e-2)
+    tol = {k: (GRAD_TOL_GATED if act == 'leakyrelu' else (3e-2 if 'Norm' in k else 2e-2)) for k in errs}
+    assert all(errs[k] < tol[k] for k in errs), errs
+    for k, b in G.named_buffers():
+        if 'running_' in k:
+            assert np.allclose(b.cpu().numpy(), og.buffers[k], rtol=2e-3, atol=2e-4), k
+        elif 'num_batches_tracked' in k:
+            assert int(b) == 1
+    # ---- eval mode: running statistics, buffers untouched
+    og.training = False
+    G.eval()
+    before = {k: b.clone() for k, b in G.named_buffers()}
+    with torch.no_grad():
+        out_e = G(xt)
+    torch.cuda.synchronize()
+    assert relerr(out_e.cpu().numpy(), og.forward(x)) < 2e-2
+    for k, b in G.named_buffers():
+        assert torch.equal(b, before[k]), k
+
+
+def test_trainer_step_with_batchnorm_generator_matches_oracle_and_reference_golden(tmp_path):
+    gk, dk, loss_type, B, steps = BN_CASES['bn']
+    gold = np.load(os.path.join(GOLD, 'step_bn.npz'))
+    og, od = orc.UNet(**gk, seed=11), orc.Discriminator(**dk, seed=12)
+    G = load(P.UNet(**ref_kwargs(gk)), og).train()
+    D = P.Discriminator(**dk)
+    D.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in od.params.items()})
+    tr = P.Trainer(G, D.cuda().train(), str(tmp_path / 'ckpt'))
+    tr.loss_type = loss_type
+    tr.make_optimizers(1e-3, 1e-3)
+    oq = orc.Trainer(og, od)
+    oq.loss_type = loss_type
+    lr = 1e-3
+    for step in range(steps):
+        x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=1234 + step)
+        orc.set_quant(**quant_kwargs())
+        try:
+            ref = oq.batch(x, y, train=True)
+        finally:
+            orc.set_quant()
+        got = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=True)
+        print('bn step', step, {k: (f'{got[k]:.6g}', f'{ref[k]:.6g}', f"{float(gold[f's{step}/loss/{k}']):.6g}") for k in got})
+        for k in got:
+            g = float(gold[f's{step}/loss/{k}'])
+            assert abs(got[k] - g) <= (1e-3 if step == 0 else 5e-3) * abs(g), (step, k, got[k], g)
+        if step == 0:
+            gerr = {k: relerr(p.grad.cpu().numpy(), oq.last['gen_grads'][k]) for k, p in G.named_parameters()}
+            print('bn grad err', {k.split('.model.')[-1]: f'{v:.1e}' for k, v in gerr.items()})
+            assert max(gerr.values()) < GRAD_TOL_GATED, gerr
+            for k, p in G.named_parameters():
+                assert np.abs(p.detach().cpu().numpy() - og.params[k]).max() <= 2.05 * lr, k
+        # (after the first Adam step the two weight sets differ by up to 2 lr per element -- sign flips of near-zero
+        #  gradients, tests/test_gpu_c_step.py -- so the second step's statistics of the 2 x 2 .. 8 x 8 maps, a few dozen
+        #  samples per channel, agree to a few 1e-3 only)
+        for k, b in G.named_buffers():
+            if 'running_' in k:
+                tol = dict(rtol=5e-3, atol=5e-4) if step == 0 else dict(rtol=3e-2, atol=5e-3)
+                assert np.allclose(b.cpu().numpy(), og.buffers[k], **tol), (step, k)
+    # eval-mode batch: running statistics
+    og.training = False
+    G.eval()
+    x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=99)
+    got = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=False)
+    for k in got:
+        g = float(gold[f'eval/loss/{k}'])
+        assert abs(got[k] - g) <= 2e-2 * abs(g) + 1e-4, (k, got[k], g)

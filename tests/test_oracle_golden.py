@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import patchgan_oracle as orc
-from tests.golden.cases import CASES, summarize
+from tests.golden.cases import BN_CASES, CASES, summarize
 
 GOLD = os.path.join(os.path.dirname(__file__), 'golden')
 
@@ -72,6 +72,38 @@ def test_step_matches_reference(name):
     for k, v in losses.items():
         close(v, gold[f'eval/loss/{k}'], 5e-3, 1e-5, f'{name} eval loss {k}')
     close(summarize(G.forward(x)), gold['eval/gen_img'], 5e-2, 5e-3, f'{name} eval gen_img')
+
+
+def test_batchnorm_generator_step_matches_reference():
+    """norm_layer = nn.BatchNorm2d in the generator (unet.py:77): losses, activations, gradients incl. the affine weight / bias,
+    post-step weights, running statistics after each step and the eval-mode forward (running statistics) of two steps."""
+    gk, dk, loss_type, B, steps = BN_CASES['bn']
+    gold = np.load(os.path.join(GOLD, 'step_bn.npz'))
+    G = orc.UNet(**gk, seed=11)
+    D = orc.Discriminator(**dk, seed=12)
+    tr = orc.Trainer(G, D)
+    tr.loss_type = loss_type
+    for step in range(steps):
+        x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=1234 + step)
+        losses = tr.batch(x, y, train=True)
+        for k, v in losses.items():
+            close(v, gold[f's{step}/loss/{k}'], 2e-5 if step == 0 else 2e-3, 1e-6, f'bn s{step} loss {k}')
+        if step == 0:
+            for k, v in G.acts.items():
+                close(summarize(v), gold[f's0/act/{k}'], 1e-3, 2e-5, f'bn act {k}')
+        gtol = 1e-4 if step == 0 else 0.1
+        for k, g in tr.last['gen_grads'].items():
+            relnorm(summarize(g), gold[f's{step}/ggrad/{k}'], gtol, f'bn s{step} ggrad {k}')
+        for k, p in G.params.items():
+            weights_close(summarize(p), gold[f's{step}/gw/{k}'], 1e-3, step + 1, 0.0 if step == 0 else 1.0, f'bn s{step} gw {k}')
+        for k, b in G.buffers.items():
+            close(summarize(b), gold[f's{step}/gbuf/{k}'], 1e-4 if step == 0 else 5e-3, 1e-6, f'bn s{step} buffer {k}')
+    G.training = False
+    x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=99)
+    losses = tr.batch(x, y, train=False)
+    for k, v in losses.items():
+        close(v, gold[f'eval/loss/{k}'], 5e-3, 1e-5, f'bn eval loss {k}')
+    close(summarize(G.forward(x)), gold['eval/gen_img'], 5e-2, 5e-3, 'bn eval gen_img')
 
 
 def test_d_activations_match_reference():
