@@ -70,6 +70,7 @@ class _DiscFunction(torch.autograd.Function):
             names.append(s.wname)
             if s.bias:
                 names.append(s.bname)
+        names += eng.bn_names()
         params = eng.params()
         grads = {n: torch.zeros_like(params[n], dtype=torch.float32) for n in names}
         dx = eng.backward(ctx.saved, d_raw, grads, need_dx=ctx.x_needs_grad)
@@ -86,24 +87,28 @@ class Discriminator(nn.Module, Transferable):
     def __init__(self, input_nc, ndf=64, n_layers=3, norm=False, norm_layer=nn.InstanceNorm2d):
         super(Discriminator, self).__init__()
         # (norm_layer is only instantiated when norm=True, disc.py:31-32,41-42: with the default norm=False any value is inert)
-        if norm and norm_layer is not nn.InstanceNorm2d:
-            raise NotImplementedError(
-                'patchgan_b200.Discriminator(norm=True) implements norm_layer=nn.InstanceNorm2d only.  A BatchNorm2d '
-                'discriminator couples the images of a call, and Trainer.batch calls the reference discriminator three times '
-                'per step (fake, real, fake again: trainer.py:65,96,98) with separate batch statistics and three running-'
-                'statistics updates, which the batched [fake ; real] discriminator pass of this package does not reproduce.')
+        if norm and norm_layer not in (nn.InstanceNorm2d, nn.BatchNorm2d):
+            raise NotImplementedError('patchgan_b200.Discriminator(norm=True) implements norm_layer=nn.InstanceNorm2d '
+                                      '(the reference default) and nn.BatchNorm2d')
         self.input_nc, self.ndf, self.n_layers, self.norm = input_nc, ndf, n_layers, norm
+        # BatchNorm2d couples the images of ONE call: the Trainer then runs D(fake) and D(real) as separate groups of the
+        # batched pass and repeats the running-statistics update of the reference's second D(fake) call (trainer.py:98-99)
+        self.batchnorm = bool(norm) and norm_layer is nn.BatchNorm2d
+
+        def norm_slot(c):
+            return nn.BatchNorm2d(c) if self.batchnorm else _Slot('InstanceNorm2d')
+
         sequence = [_Holder((ndf, input_nc, 4, 4), input_nc * 16, bias_n=ndf), _Slot('LeakyReLU(0.2)')]
         nf_mult = 1
         for n in range(1, n_layers):
             nf_mult_prev, nf_mult = nf_mult, min(2 ** n, 8)
             sequence += [_Holder((ndf * nf_mult, ndf * nf_mult_prev, 4, 4), ndf * nf_mult_prev * 16), _Slot('Tanh')]
             if norm:
-                sequence += [_Slot('InstanceNorm2d')]
+                sequence += [norm_slot(ndf * nf_mult)]
         nf_mult_prev, nf_mult = nf_mult, min(2 ** n_layers, 8)
         sequence += [_Holder((ndf * nf_mult, ndf * nf_mult_prev, 4, 4), ndf * nf_mult_prev * 16), _Slot('Tanh')]
         if norm:
-            sequence += [_Slot('InstanceNorm2d')]
+            sequence += [norm_slot(ndf * nf_mult)]
         sequence += [_Holder((1, ndf * nf_mult, 4, 4), ndf * nf_mult * 16, bias_n=1), _Slot('Sigmoid')]
         self.model = nn.Sequential(*sequence)
         self.__dict__['_eng'] = None
@@ -120,7 +125,7 @@ class Discriminator(nn.Module, Transferable):
             out.append(ps[s.wname])
             if s.bias:
                 out.append(ps[s.bname])
-        return out
+        return out + [ps[n] for n in self._engine().bn_names()]
 
     def forward(self, input):
         """Standard forward."""

@@ -859,9 +859,10 @@ def batchnorm_fwd(raw, sums, bn, c_real, out, act, drop_p, seed, salt, training)
            seed.data_ptr() if seed is not None else None, salt, st)
 
 
-def batchnorm_bwd(raw, sums, bn, c_real, dy1, dy2, act, drop_p, seed, salt):
+def batchnorm_bwd(raw, sums, bn, c_real, dy1, dy2, act, drop_p, seed, salt, parts=None):
     """Backward of dropout / act / BatchNorm2d: returns d(raw) as a new bf16 Act and accumulates dgamma / dbeta.
-    bn = (gamma, beta, dgamma, dbeta, training)."""
+    bn = (gamma, beta, dgamma, dbeta, training).  parts = [(first image, images)]: groups of images that were normalised
+    together (separate discriminator calls batched into one pass); default: the whole batch."""
     gamma, beta, dgamma, dbeta, training = bn
     dev = raw.t.device
     HW = raw.H * raw.W
@@ -872,8 +873,9 @@ def batchnorm_bwd(raw, sums, bn, c_real, dy1, dy2, act, drop_p, seed, salt):
     st = _stream()
     L.call('pg_norm_affine_act_bwd_reduce', raw.ptr, raw.dt, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), c_real,
            dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), raw.B, HW, raw.C, raw.ld, act, drop_p, sp, salt, st)
-    L.call('pg_bn_fold_bwd', bsums.data_ptr(), raw.B, raw.C, dgamma.data_ptr() if dgamma is not None else None,
-           dbeta.data_ptr() if dbeta is not None else None, c_real, 1 if training else 0, st)
+    for b0, nb in (parts or [(0, raw.B)]):
+        L.call('pg_bn_fold_bwd', bsums.data_ptr() + b0 * raw.C * 8, nb, raw.C, dgamma.data_ptr() if dgamma is not None else None,
+               dbeta.data_ptr() if dbeta is not None else None, c_real, 1 if training else 0, st)
     L.call('pg_norm_affine_act_bwd_apply', raw.ptr, raw.dt, sums.data_ptr(), gamma.data_ptr(), beta.data_ptr(), c_real,
            dy1.ptr, dy1.ld, p2, l2, bsums.data_ptr(), dx.ptr, dx.ld, raw.B, HW, raw.C, raw.ld, act, drop_p, sp, salt, st)
     return dx
@@ -1147,6 +1149,7 @@ class GeneratorEngine(NetEngine):
 class DiscriminatorEngine(NetEngine):
     def __init__(self, module):
         inc, ndf, nl, norm = module.input_nc, module.ndf, module.n_layers, module.norm
+        bn = bool(norm) and bool(getattr(module, 'batchnorm', False))
         idx = 0
         specs = [LayerSpec('conv', 2, inc, 0, ndf, True, 'leakyrelu', False, False, 'model.0.weight', 'model.0.bias')]
         idx += 2
@@ -1154,16 +1157,41 @@ class DiscriminatorEngine(NetEngine):
         for n in range(1, nl):
             prev, mult = mult, min(2 ** n, 8)
             specs.append(LayerSpec('conv', 2, ndf * prev, 0, ndf * mult, False, 'tanh', norm, False,
-                                   f'model.{idx}.weight', norm_after_act=True))
+                                   f'model.{idx}.weight', norm_after_act=True, bn=f'model.{idx + 2}' if bn else None))
             idx += 3 if norm else 2
         prev, mult = mult, min(2 ** nl, 8)
         specs.append(LayerSpec('conv', 1, ndf * prev, 0, ndf * mult, False, 'tanh', norm, False, f'model.{idx}.weight',
-                               norm_after_act=True))
+                               norm_after_act=True, bn=f'model.{idx + 2}' if bn else None))
         idx += 3 if norm else 2
         specs.append(LayerSpec('conv', 1, ndf * mult, 0, 1, True, 'sigmoid', False, False, f'model.{idx}.weight',
                                f'model.{idx}.bias'))
         super().__init__(module, specs)
         self.in_cp = rup16(inc)
+
+    def bn_tensors(self, s):
+        ps, bs = self.params(), dict(self.module.named_buffers())
+        return (ps[s.bn + '.weight'], ps[s.bn + '.bias'], bs[s.bn + '.running_mean'], bs[s.bn + '.running_var'],
+                bs.get(s.bn + '.num_batches_tracked'))
+
+    def bn_names(self):
+        return [s.bn + sfx for s in self.specs if s.bn is not None for sfx in ('.weight', '.bias')]
+
+    def bn_repeat_update(self, ctx, b0, nb):
+        """Running-statistics update of a REPEATED forward call over images b0 .. b0+nb-1 (trainer.py:98-99 runs D(fake) a
+        second time: identical outputs, but BatchNorm2d in train mode updates its running buffers again).  The fold is
+        idempotent on the already folded pairs."""
+        if not self.module.training:
+            return
+        for li, s in enumerate(self.specs):
+            if s.bn is None:
+                continue
+            h, t, sums, out = ctx[li]
+            g, b, rm, rv, nbt = self.bn_tensors(s)
+            st = _stream()
+            L.call('pg_bn_fold_fwd', sums.data_ptr() + b0 * t.C * 8, nb, t.C, t.H * t.W, rm.data_ptr(), rv.data_ptr(), s.cout,
+                   BN_MOMENTUM, 1, st)
+            if nbt is not None:
+                L.call('pg_counter_add', nbt.data_ptr(), 1, st)
 
     def new_input(self, B, H, W, device, twin=False, zero=True):
         return new_act(B, H, W, self.in_cp, device, dt=Config.fwd_dt, zero=zero, twin=twin)
@@ -1181,6 +1209,7 @@ class DiscriminatorEngine(NetEngine):
         dev = xin.t.device
         B = xin.B
         ctx = []
+        self._parts = []          # groups of images normalised together (BatchNorm2d): one per forward_part call
         h = xin
         last = len(self.specs) - 1
         for li, s in enumerate(self.specs):
@@ -1210,6 +1239,7 @@ class DiscriminatorEngine(NetEngine):
         normalisation is per-sample InstanceNorm, disc.py:8)."""
         ps = self.params()
         last = len(self.specs) - 1
+        self._parts.append((b0, nb))
         for li, s in enumerate(self.specs):
             h, t, sums, out = ctx[li]
             h, out = h.images(b0, nb), out.images(b0, nb)
@@ -1228,7 +1258,19 @@ class DiscriminatorEngine(NetEngine):
                     run_conv(conv_desc(L.PG_CONV, s.stride, 1, nb, h.H, h.W, t.H, t.W, h.C, 0, h.ld, 0, s.np, t.ld,
                                        n_valid=s.cout, act=L.ACT[s.act], out_dt=t.dt, has_bias=int(s.bias), in_dt=h.dt),
                              h, None, self.packed[li].fwd, bias, t)
-                if s.norm:
+                if s.norm and s.bn is not None:
+                    # BatchNorm2d after the Tanh (disc.py:29-32): statistics over the images of THIS call
+                    instnorm_stats(t, sums, b0)
+                    gam, bet, rm, rv, nbt = self.bn_tensors(s)
+                    st = _stream()
+                    training = self.module.training
+                    L.call('pg_bn_fold_fwd', sums.data_ptr() + b0 * t.C * 8, nb, t.C, t.H * t.W, rm.data_ptr(), rv.data_ptr(),
+                           s.cout, BN_MOMENTUM, 1 if training else 0, st)
+                    if training and nbt is not None:
+                        L.call('pg_counter_add', nbt.data_ptr(), 1, st)
+                    L.call('pg_norm_affine_act_fwd', t.ptr, t.dt, sums.data_ptr() + b0 * t.C * 8, gam.data_ptr(), bet.data_ptr(),
+                           s.cout, out.ptr, out.dt, out.twptr, nb, t.H * t.W, t.C, t.ld, out.ld, 0, 0.0, None, 0, st)
+                elif s.norm:
                     instnorm_stats(t, sums, b0)
                     norm_fwd(t, sums, out, 0, 0.0, None, 0, b0)
 
@@ -1298,7 +1340,15 @@ class DiscriminatorEngine(NetEngine):
                 ps = self.specs[li - 1]
                 _, pt, psums, pout = ctx[li - 1]
                 pt = pt.first(B)
-                if ps.norm:
+                if ps.norm and ps.bn is not None:
+                    pp = self.params()
+                    gw = grads.get(ps.bn + '.weight') if grads is not None else None
+                    gb = grads.get(ps.bn + '.bias') if grads is not None else None
+                    parts = [(b0, nb_) for (b0, nb_) in getattr(self, '_parts', []) if b0 + nb_ <= B] or [(0, B)]
+                    dt = batchnorm_bwd(pt, psums, (pp[ps.bn + '.weight'], pp[ps.bn + '.bias'], gw, gb, self.module.training),
+                                       ps.cout, din, None, 0, 0.0, None, 0, parts)
+                    d_raw = act_bwd_out(pt, dt, L.ACT[ps.act])
+                elif ps.norm:
                     dt = norm_bwd(pt, psums, din, None, 0, 0.0, None, 0)
                     d_raw = act_bwd_out(pt, dt, L.ACT[ps.act])
                 elif fuse_act:

@@ -203,7 +203,7 @@ class Trainer:
         # D(cat(x, y)) forward: under the generator's forward on a side stream (default), or -- DREAL_LATE=1 -- batched with
         # D(cat(x, G(x))) into one 2B-image pass after it (the one-launch conv + InstanceNorm kernels of the generator own
         # every SM while they run, so a concurrent discriminator pass and they only take turns)
-        dreal_late = os.environ.get('PATCHGAN_B200_DREAL_LATE', '1') != '0'
+        dreal_late = os.environ.get('PATCHGAN_B200_DREAL_LATE', '1') != '0' or bool(getattr(dm, 'batchnorm', False))
         raw_nccl = world > 1 and dp.raw_comm() is not None
 
         def on(stream):
@@ -258,6 +258,12 @@ class Trainer:
         if ms and not dreal_late:
             D.forward_part(dctx, 0, B)
             E.join(s_d)
+        elif getattr(dm, 'batchnorm', False):
+            # a BatchNorm2d discriminator normalises over the images of one call: D(fake) and D(real) stay separate groups,
+            # and the reference's second D(fake) call (trainer.py:98-99) repeats the running-statistics update
+            D.forward_part(dctx, 0, B)
+            D.forward_part(dctx, B, B)
+            D.bn_repeat_update(dctx, 0, B)
         else:
             D.forward_part(dctx, 0, 2 * B)
         pd = dctx[-1][3]

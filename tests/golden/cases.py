@@ -18,6 +18,10 @@ NS = 256
 BN_CASES = {
     'bn': (dict(input_nc=3, output_nc=1, nf=8, activation='leakyrelu', final_act='sigmoid', norm='batch'),
            dict(input_nc=4, ndf=8, n_layers=3, norm=False), 'tversky', 2, 2),
+    # BatchNorm2d in BOTH networks: the discriminator's three calls per step (fake, real, fake again: trainer.py:65,96,98)
+    # use separate batch statistics and update its running buffers three times.  Fixture: step_bnd.npz
+    'bnd': (dict(input_nc=3, output_nc=1, nf=8, activation='tanh', final_act='sigmoid', norm='batch'),
+            dict(input_nc=4, ndf=8, n_layers=3, norm=True, norm_layer='batch'), 'MAE', 2, 2),
 }
 
 # The BASELINE.json architectures at (or near) their benchmarked sizes -- goldens from the live reference only (the numpy

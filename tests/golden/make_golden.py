@@ -43,11 +43,15 @@ def run_case(name, gk, dk, loss_type, B, steps, S=256):
     if ref_gk.pop('norm', 'instance') == 'batch':
         ref_gk['norm_layer'] = torch.nn.BatchNorm2d
     G = patchgan.UNet(**ref_gk)
-    D = patchgan.Discriminator(**dk)
+    ref_dk = dict(dk)
+    if ref_dk.get('norm_layer') == 'batch':
+        ref_dk['norm_layer'] = torch.nn.BatchNorm2d
+    D = patchgan.Discriminator(**ref_dk)
     # (strict=False: BatchNorm's running buffers keep their defaults, which are the oracle's too)
     missing = G.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in og.params.items()}, strict=False)
     assert not missing.unexpected_keys and all('running_' in k or 'num_batches' in k for k in missing.missing_keys), missing
-    D.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in od.params.items()})
+    dmiss = D.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in od.params.items()}, strict=False)
+    assert not dmiss.unexpected_keys and all('running_' in k or 'num_batches' in k for k in dmiss.missing_keys), dmiss
     import tempfile
     tr = patchgan.Trainer(G, D, tempfile.mkdtemp(), device='cpu')
     tr.loss_type = loss_type
@@ -90,6 +94,9 @@ def run_case(name, gk, dk, loss_type, B, steps, S=256):
         for k, b in G.named_buffers():
             if 'running_' in k:
                 out[f's{step}/gbuf/{k}'] = summarize(b.numpy())
+        for k, b in D.named_buffers():
+            if 'running_' in k:
+                out[f's{step}/dbuf/{k}'] = summarize(b.numpy())
     # eval-mode forward / train=False batch (trainer.py:239-259)
     G.eval()
     D.eval()

@@ -50,8 +50,11 @@ def test_state_dict_keys_match_the_reference_layout():
     assert len(keys) == 14 + 12 * 5                       # 14 convolutions, 12 BatchNorm2d modules x 5 entries
     # (a discriminator without norm layers never instantiates norm_layer: any class is accepted there)
     P.Discriminator(4, 8, n_layers=3, norm=False, norm_layer=nn.BatchNorm2d)
+    d = P.Discriminator(4, 8, n_layers=3, norm=True, norm_layer=nn.BatchNorm2d)
+    dkeys = list(d.state_dict().keys())
+    assert 'model.4.running_mean' in dkeys and 'model.10.weight' in dkeys and 'model.11.bias' in dkeys
     with pytest.raises(NotImplementedError):
-        P.Discriminator(4, 8, n_layers=3, norm=True, norm_layer=nn.BatchNorm2d)
+        P.Discriminator(4, 8, n_layers=3, norm=True, norm_layer=nn.GroupNorm)
 
 
 @pytest.mark.parametrize('act', ['leakyrelu', 'tanh'])
@@ -102,14 +105,46 @@ def test_batchnorm_unet_forward_backward_train_and_eval(act):
         assert torch.equal(b, before[k]), k
 
 
-def test_trainer_step_with_batchnorm_generator_matches_oracle_and_reference_golden(tmp_path):
-    gk, dk, loss_type, B, steps = BN_CASES['bn']
-    gold = np.load(os.path.join(GOLD, 'step_bn.npz'))
+def test_batchnorm_discriminator_forward_backward():
+    """Discriminator(norm=True, norm_layer=nn.BatchNorm2d): conv -> Tanh -> BatchNorm2d (disc.py:27-32), module level."""
+    dk = dict(input_nc=4, ndf=8, n_layers=3, norm=True, norm_layer='batch')
+    od = orc.Discriminator(**dk, seed=4)
+    rng = np.random.default_rng(9)
+    for k in od.buffers:
+        od.params[k.replace('running_mean', 'weight').replace('running_var', 'weight')] = \
+            (0.5 + rng.random(od.buffers[k].shape)).astype(np.float32)
+    D = load(P.Discriminator(**{**dk, 'norm_layer': nn.BatchNorm2d}), od).train()
+    x = rng.random((3, 4, 256, 256), dtype=np.float32)
+    orc.set_quant(**quant_kwargs())
+    try:
+        ref = od.forward(x, keep=True)
+        m = rng.standard_normal(ref.shape).astype(np.float32)
+        rdx, rg = od.backward(m, need_dx=True)                        # m = gradient wrt the (post-sigmoid) output
+    finally:
+        orc.set_quant()
+    xt = torch.from_numpy(x).cuda().requires_grad_(True)
+    out = D(xt)
+    (out * torch.from_numpy(m).cuda()).sum().backward()
+    torch.cuda.synchronize()
+    assert relerr(out.detach().cpu().numpy(), ref) < ACT_TOL
+    errs = {k: relerr(p.grad.cpu().numpy(), rg[k]) for k, p in D.named_parameters()}
+    print('D-bn grad err', {k: f'{v:.1e}' for k, v in errs.items()})
+    assert max(errs.values()) < 3e-2, errs
+    assert relerr(xt.grad.cpu().numpy(), rdx) < 3e-2
+    for k, b in D.named_buffers():
+        if 'running_' in k:
+            assert np.allclose(b.cpu().numpy(), od.buffers[k], rtol=2e-3, atol=2e-4), k
+
+
+@pytest.mark.parametrize('case', ['bn', 'bnd'])
+def test_trainer_step_with_batchnorm_matches_oracle_and_reference_golden(case, tmp_path):
+    gk, dk, loss_type, B, steps = BN_CASES[case]
+    gold = np.load(os.path.join(GOLD, f'step_{case}.npz'))
     og, od = orc.UNet(**gk, seed=11), orc.Discriminator(**dk, seed=12)
     G = load(P.UNet(**ref_kwargs(gk)), og).train()
-    D = P.Discriminator(**dk)
-    D.load_state_dict({k: torch.from_numpy(v.copy()) for k, v in od.params.items()})
-    tr = P.Trainer(G, D.cuda().train(), str(tmp_path / 'ckpt'))
+    ref_dk = {**dk, 'norm_layer': nn.BatchNorm2d} if dk.get('norm_layer') == 'batch' else dk
+    D = load(P.Discriminator(**ref_dk), od)
+    tr = P.Trainer(G, D.train(), str(tmp_path / 'ckpt'))
     tr.loss_type = loss_type
     tr.make_optimizers(1e-3, 1e-3)
     oq = orc.Trainer(og, od)
@@ -129,6 +164,7 @@ def test_trainer_step_with_batchnorm_generator_matches_oracle_and_reference_gold
             assert abs(got[k] - g) <= (1e-3 if step == 0 else 5e-3) * abs(g), (step, k, got[k], g)
         if step == 0:
             gerr = {k: relerr(p.grad.cpu().numpy(), oq.last['gen_grads'][k]) for k, p in G.named_parameters()}
+            gerr.update({'D.' + k: relerr(p.grad.cpu().numpy(), oq.last['disc_grads'][k]) for k, p in D.named_parameters()})
             print('bn grad err', {k.split('.model.')[-1]: f'{v:.1e}' for k, v in gerr.items()})
             assert max(gerr.values()) < GRAD_TOL_GATED, gerr
             for k, p in G.named_parameters():
@@ -136,13 +172,17 @@ def test_trainer_step_with_batchnorm_generator_matches_oracle_and_reference_gold
         # (after the first Adam step the two weight sets differ by up to 2 lr per element -- sign flips of near-zero
         #  gradients, tests/test_gpu_c_step.py -- so the second step's statistics of the 2 x 2 .. 8 x 8 maps, a few dozen
         #  samples per channel, agree to a few 1e-3 only)
-        for k, b in G.named_buffers():
-            if 'running_' in k:
-                tol = dict(rtol=5e-3, atol=5e-4) if step == 0 else dict(rtol=3e-2, atol=5e-3)
-                assert np.allclose(b.cpu().numpy(), og.buffers[k], **tol), (step, k)
+        for mod, ob in ((G, og), (D, od)):
+            for k, b in mod.named_buffers():
+                if 'running_' in k:
+                    tol = dict(rtol=5e-3, atol=5e-4) if step == 0 else dict(rtol=3e-2, atol=5e-3)
+                    assert np.allclose(b.cpu().numpy(), ob.buffers[k], **tol), (step, k)
+                elif 'num_batches_tracked' in k:
+                    assert int(b) == (step + 1) * (3 if mod is D else 1), (k, int(b))     # D: three calls per step
     # eval-mode batch: running statistics
-    og.training = False
+    og.training = od.training = False
     G.eval()
+    D.eval()
     x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=99)
     got = tr.batch(torch.from_numpy(x), torch.from_numpy(y), train=False)
     for k in got:

@@ -74,11 +74,13 @@ def test_step_matches_reference(name):
     close(summarize(G.forward(x)), gold['eval/gen_img'], 5e-2, 5e-3, f'{name} eval gen_img')
 
 
-def test_batchnorm_generator_step_matches_reference():
-    """norm_layer = nn.BatchNorm2d in the generator (unet.py:77): losses, activations, gradients incl. the affine weight / bias,
-    post-step weights, running statistics after each step and the eval-mode forward (running statistics) of two steps."""
-    gk, dk, loss_type, B, steps = BN_CASES['bn']
-    gold = np.load(os.path.join(GOLD, 'step_bn.npz'))
+@pytest.mark.parametrize('case', ['bn', 'bnd'])
+def test_batchnorm_step_matches_reference(case):
+    """norm_layer = nn.BatchNorm2d in the generator ('bn', unet.py:77) and in both networks ('bnd', disc.py:8 with norm=True):
+    losses, activations, gradients incl. the affine weight / bias, post-step weights, running statistics after each step
+    (the discriminator's are updated three times per step: trainer.py:65,96,98) and the eval-mode forward of two steps."""
+    gk, dk, loss_type, B, steps = BN_CASES[case]
+    gold = np.load(os.path.join(GOLD, f'step_{case}.npz'))
     G = orc.UNet(**gk, seed=11)
     D = orc.Discriminator(**dk, seed=12)
     tr = orc.Trainer(G, D)
@@ -98,7 +100,11 @@ def test_batchnorm_generator_step_matches_reference():
             weights_close(summarize(p), gold[f's{step}/gw/{k}'], 1e-3, step + 1, 0.0 if step == 0 else 1.0, f'bn s{step} gw {k}')
         for k, b in G.buffers.items():
             close(summarize(b), gold[f's{step}/gbuf/{k}'], 1e-4 if step == 0 else 5e-3, 1e-6, f'bn s{step} buffer {k}')
-    G.training = False
+        for k, g in tr.last['disc_grads'].items():
+            relnorm(summarize(g), gold[f's{step}/dgrad/{k}'], gtol, f'bn s{step} dgrad {k}')
+        for k, b in D.buffers.items():
+            close(summarize(b), gold[f's{step}/dbuf/{k}'], 1e-4 if step == 0 else 5e-3, 1e-6, f'bn s{step} D buffer {k}')
+    G.training = D.training = False
     x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=99)
     losses = tr.batch(x, y, train=False)
     for k, v in losses.items():
