@@ -61,7 +61,7 @@ class _UniqueId(ctypes.Structure):
 
 
 NCCL_FLOAT32, NCCL_SUM = 7, 0
-NCCL_SMS = 16        # SMs left to the NCCL kernels while they overlap the backward pass
+NCCL_SMS = int(os.environ.get('PATCHGAN_B200_NCCL_SMS', '16'))   # SMs left to the NCCL kernels while they overlap the backward
 _COMM = {'tried': False, 'lib': None, 'comm': None}
 
 
@@ -100,6 +100,7 @@ def raw_comm():
     from . import _lib as L
     nsm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
     L.check(L.lib().pg_set_sm_limit(max(nsm - NCCL_SMS, nsm // 2)), 'pg_set_sm_limit')
+    _COMM['nsm'] = nsm
     uid = _UniqueId()
     if rank() == 0:
         rc = lib.ncclGetUniqueId(ctypes.byref(uid))
@@ -115,6 +116,17 @@ def raw_comm():
         raise RuntimeError(f'ncclCommInitRank: {lib.ncclGetErrorString(rc).decode()}')
     _COMM['lib'], _COMM['comm'] = lib, comm
     return comm
+
+
+def reserve_sms(on):
+    """Keep NCCL_SMS SMs out of the reach of the one-launch conv + InstanceNorm kernels planned from now on (on=True: a raw
+    all-reduce may be in flight beside them) or give them the whole GPU (on=False: the caller guarantees that none is).
+    The limit is host-side planning state: it is baked into the launches captured after the call."""
+    if _COMM.get('comm') is None:
+        return
+    from . import _lib as L
+    nsm = _COMM['nsm']
+    L.check(L.lib().pg_set_sm_limit(max(nsm - NCCL_SMS, nsm // 2) if on else 0), 'pg_set_sm_limit')
 
 
 def raw_all_reduce_sum_(flat, first=0, count=None):

@@ -1024,7 +1024,7 @@ class GeneratorEngine(NetEngine):
             h = out
         return h, ctx
 
-    def backward(self, ctx, d_raw, grads, need_dx=False, wstream=None, early=None, d_hidden=None):
+    def backward(self, ctx, d_raw, grads, need_dx=False, wstream=None, early=None, d_hidden=None, hooks=None):
         """d_raw: bf16 Act, gradient wrt the last ConvTranspose2d's output (pre final activation).
         d_hidden: optional bf16 Act, gradient wrt the encoder bottleneck returned by forward(return_hidden=True).
         grads: dict name -> zero-initialised float32 tensor in the reference layout (accumulated into).
@@ -1035,8 +1035,12 @@ class GeneratorEngine(NetEngine):
         grouped launch (its dY exists by then; its operand copies are still read by its own data-gradient afterwards) --
         measured slower on one GPU (the heavier group stretches the last one-launch kernel it runs beside), off by default.
 
+        hooks: optional {('after_dec', j): fn, ('before_enc', i): fn}: fn() is called right after decoder j's / right before
+        encoder i's data-gradient is issued (the data-parallel trainer places its all-reduces and SM reservations there).
+
         Every data-gradient convolution also runs the backward of the block that produced its input (activation, dropout,
         InstanceNorm; engine.dgrad_block_bwd), so the chain is one launch per layer."""
+        hooks = hooks or {}
         dev = d_raw.t.device
         B = d_raw.B
         dskip = [None] * 7
@@ -1099,6 +1103,8 @@ class GeneratorEngine(NetEngine):
                                         d_hidden if i == 0 else None, self.seed)
             if i >= 1:
                 dskip[6 - i] = din.slice(s.c1p, s.c2p)
+            if ('after_dec', i) in hooks:
+                hooks[('after_dec', i)]()
         # d_raw is now the gradient wrt encoder 6's convolution output
         dx = None
         pulled = -1                 # encoder layer whose weight-gradient was queued ahead of its turn (see `early`)
@@ -1118,6 +1124,8 @@ class GeneratorEngine(NetEngine):
             h, out = ctx['enc'][i][0], ctx['enc'][i][3]
             if i != pulled:
                 enc_wgrad(i, d_raw)
+            if ('before_enc', i) in hooks:
+                hooks[('before_enc', i)]()
             if i > 0 or need_dx:
                 Hi, Wi = (2 * h.H, 2 * h.W) if h.im2col else (h.H, h.W)
                 din = new_act(B, Hi, Wi, s.cinp, dev)

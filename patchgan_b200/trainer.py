@@ -205,6 +205,13 @@ class Trainer:
         # every SM while they run, so a concurrent discriminator pass and they only take turns)
         dreal_late = os.environ.get('PATCHGAN_B200_DREAL_LATE', '1') != '0' or bool(getattr(dm, 'batchnorm', False))
         raw_nccl = world > 1 and dp.raw_comm() is not None
+        # raw NCCL + side streams: the one-launch conv + norm kernels only leave SMs to NCCL while a collective can actually
+        # be in flight beside them (dp.reserve_sms); everywhere else they get the whole GPU
+        sm_toggle = (raw_nccl and ms and phase == 'all' and train and self.LATE_LAYERS > 0
+                     and os.environ.get('PATCHGAN_B200_DP_SMTOGGLE', '1') != '0' and G.layers_match_parameters()
+                     and len(G.specs) > self.LATE_LAYERS)
+        if raw_nccl:
+            dp.reserve_sms(not sm_toggle)
 
         def on(stream):
             return torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
@@ -295,7 +302,9 @@ class Trainer:
                 if world > 1 and phase == 'all':
                     # the discriminator's gradients are final: their all-reduce runs on this side stream, underneath the
                     # generator's backward pass (raw NCCL call = a node of the step's graph; else the process group's)
-                    if raw_nccl:
+                    if raw_nccl and sm_toggle:
+                        pass                         # issued from inside the generator's backward (see `d_exchange` below)
+                    elif raw_nccl:
                         dp.raw_all_reduce_sum_(dflat['g'])
                     else:
                         d_work = dp.all_reduce_sum_async(dflat['g'])
@@ -379,10 +388,35 @@ class Trainer:
                 off_k = gopt.flat()['offs'][KL]
                 nl = len(G.specs)
                 gopt.grad_scale = 1.0 / world
-                with on(s_d):
-                    s_d.wait_event(ev_dread)
-                    dopt.step(sync_lr=False)
-                    D.repack()
+                hooks = None
+                if sm_toggle:
+                    # No collective is in flight during the generator's forward and the first (largest) kernels of its
+                    # backward: they were planned for the whole GPU.  The discriminator's all-reduce is released once the
+                    # decoder's three big data-gradients are done (ev_big), runs beside the small layers (64 .. 128 CTAs
+                    # whatever the limit), and has to be over (ev_dar) before the next full-grid kernel is launched.
+                    ev_big, ev_dar = torch.cuda.Event(), torch.cuda.Event()
+
+                    def d_exchange():
+                        ev_big.record()
+                        dp.reserve_sms(True)
+                        with on(s_d):
+                            s_d.wait_event(ev_big)
+                            dp.raw_all_reduce_sum_(dflat['g'])
+                            ev_dar.record()
+                            s_d.wait_event(ev_dread)
+                            dopt.step(sync_lr=False)
+                            D.repack()
+
+                    def d_exchange_done():
+                        torch.cuda.current_stream().wait_event(ev_dar)
+                        dp.reserve_sms(False)
+
+                    hooks = {('after_dec', 4): d_exchange, ('before_enc', K): d_exchange_done}
+                else:
+                    with on(s_d):
+                        s_d.wait_event(ev_dread)
+                        dopt.step(sync_lr=False)
+                        D.repack()
                 ev_adam = torch.cuda.Event()
 
                 def early_allreduce():
@@ -395,6 +429,7 @@ class Trainer:
                     ev_m.record()
                     s_d.wait_event(ev_m)
                     ev_fin = torch.cuda.Event()
+                    dp.reserve_sms(True)             # the generator's bucket is about to be in flight beside the last layers
                     # the bucket goes out in NB pieces of about equal bytes: Adam and the operand repack of piece i run on
                     # s_e underneath the all-reduce of piece i+1 (the collective runs on the SMs pg_set_sm_limit keeps free)
                     offs = gopt.flat()['offs'] + [gopt.flat()['n']]
@@ -422,7 +457,7 @@ class Trainer:
                     if os.environ.get('PATCHGAN_B200_DP_HOLD', '1') != '0':
                         torch.cuda.current_stream().wait_event(ev_fin)
 
-                G.backward(gctx, d_raw, ggrads, wstream=s_w, early=(K, early_allreduce))
+                G.backward(gctx, d_raw, ggrads, wstream=s_w, early=(K, early_allreduce), hooks=hooks)
                 E.join(s_w)
                 G.finalize_grads()
                 dp.raw_all_reduce_sum_(gflat['g'], 0, off_k)
