@@ -61,7 +61,10 @@ class _UniqueId(ctypes.Structure):
 
 
 NCCL_FLOAT32, NCCL_SUM = 7, 0
-NCCL_SMS = int(os.environ.get('PATCHGAN_B200_NCCL_SMS', '16'))   # SMs left to the NCCL kernels while they overlap the backward
+# SMs left to the NCCL kernels while they overlap the backward (= NCCL_MAX_CTAS).  Measured on B200 (cfg 3, ms/step): 16 vs 32 SMs
+# at 2 GPUs 2.54 / 2.60, at 4 GPUs 2.60 / 2.63, at 8 GPUs 2.68 / 2.63 -- the 42 MB all-reduce takes 176 us at 2 GPUs and 259 us
+# at 8 with 16 CTAs, so only the 8-GPU ring is worth more SMs.  PATCHGAN_B200_NCCL_SMS overrides.
+NCCL_SMS = 16
 _COMM = {'tried': False, 'lib': None, 'comm': None}
 
 
@@ -96,6 +99,8 @@ def raw_comm():
         return None
     # The collectives run beside the backward kernels: cap NCCL's CTAs, and keep as many SMs out of the grid-barrier
     # kernels' reach (see pg_set_sm_limit), so that neither can starve the other of the SMs it needs to make progress.
+    global NCCL_SMS
+    NCCL_SMS = int(os.environ.get('PATCHGAN_B200_NCCL_SMS', '32' if world_size() >= 8 else '16'))
     os.environ.setdefault('NCCL_MAX_CTAS', str(NCCL_SMS))
     from . import _lib as L
     nsm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count

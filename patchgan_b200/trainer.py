@@ -392,9 +392,10 @@ class Trainer:
                 if sm_toggle:
                     # No collective is in flight during the generator's forward and the first (largest) kernels of its
                     # backward: they were planned for the whole GPU.  The discriminator's all-reduce is released once the
-                    # decoder's three big data-gradients are done (ev_big), runs beside the small layers (64 .. 128 CTAs
-                    # whatever the limit), and has to be over (ev_dar) before the next full-grid kernel is launched.
-                    ev_big, ev_dar = torch.cuda.Event(), torch.cuda.Event()
+                    # decoder's three big data-gradients are done (ev_big) and runs beside the small layers (64 .. 128 CTAs
+                    # whatever the limit); from there on the reservation stays (the main stream never waits for the
+                    # collective: with a heavy discriminator -- cfg 5 -- its backward can still be running by then).
+                    ev_big = torch.cuda.Event()
 
                     def d_exchange():
                         ev_big.record()
@@ -402,16 +403,11 @@ class Trainer:
                         with on(s_d):
                             s_d.wait_event(ev_big)
                             dp.raw_all_reduce_sum_(dflat['g'])
-                            ev_dar.record()
                             s_d.wait_event(ev_dread)
                             dopt.step(sync_lr=False)
                             D.repack()
 
-                    def d_exchange_done():
-                        torch.cuda.current_stream().wait_event(ev_dar)
-                        dp.reserve_sms(False)
-
-                    hooks = {('after_dec', 4): d_exchange, ('before_enc', K): d_exchange_done}
+                    hooks = {('after_dec', 4): d_exchange}
                 else:
                     with on(s_d):
                         s_d.wait_event(ev_dread)
