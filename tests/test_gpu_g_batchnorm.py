@@ -188,3 +188,33 @@ def test_trainer_step_with_batchnorm_matches_oracle_and_reference_golden(case, t
     for k in got:
         g = float(gold[f'eval/loss/{k}'])
         assert abs(got[k] - g) <= 2e-2 * abs(g) + 1e-4, (k, got[k], g)
+
+
+def test_batchnorm_cuda_graph_replay_matches_eager(tmp_path):
+    """BatchNorm in both networks through the captured-graph step (replays from step 3 on) vs. eager launches: same
+    trajectory, same running statistics, num_batches_tracked advanced by the replays too."""
+    gk, dk, loss_type, B, steps = BN_CASES['bnd']
+    x, y = orc.synthetic_batch(B, gk['output_nc'], 256, seed=1234)
+    xt, yt = torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda()
+    traj, bufs = {}, {}
+    for mode in (False, True):
+        og, od = orc.UNet(**gk, seed=11), orc.Discriminator(**dk, seed=12)
+        G = load(P.UNet(**ref_kwargs(gk)), og).train()
+        D = load(P.Discriminator(**{**dk, 'norm_layer': nn.BatchNorm2d}), od).train()
+        tr = P.Trainer(G, D, str(tmp_path / f'ckpt{int(mode)}'))
+        tr.loss_type = loss_type
+        tr.make_optimizers(1e-3, 1e-3)
+        tr.use_cuda_graph = mode
+        traj[mode] = [tr.batch(xt, yt, train=True) for _ in range(6)]
+        if mode:
+            assert any(e['graph'] is not None for e in tr._graphs.values())
+        bufs[mode] = {('G.' if m is G else 'D.') + k: b.detach().float().cpu().numpy().copy()
+                      for m in (G, D) for k, b in m.named_buffers()}
+    for a, b in zip(traj[False], traj[True]):
+        for k in a:
+            assert abs(a[k] - b[k]) <= 5e-3 * abs(a[k]), (k, a[k], b[k])
+    for k, v in bufs[False].items():
+        if 'num_batches_tracked' in k:
+            assert int(v) == int(bufs[True][k]) == 6 * (3 if k.startswith('D.') else 1), (k, v, bufs[True][k])
+        else:
+            assert np.allclose(v, bufs[True][k], rtol=3e-2, atol=5e-3), k
