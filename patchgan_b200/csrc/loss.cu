@@ -179,6 +179,9 @@ __global__ void __launch_bounds__(256) gen_out_bwd_kernel(const float* __restric
     if (lddx == 16) {          // the usual case: one 32-byte row
       *reinterpret_cast<uint4*>(dx + pix * 16) = pack8(outv);
       *reinterpret_cast<uint4*>(dx + pix * 16 + 8) = pack8(outv + 8);
+    } else if (lddx == 4) {    // trimmed row (one real channel, consumed by the tap gather): one 8-byte store
+      const uint4 v = pack8(outv);
+      *reinterpret_cast<uint2*>(dx + pix * 4) = make_uint2(v.x, v.y);
     } else {
       for (int c = 0; c < lddx; ++c) dx[pix * lddx + c] = __float2bfloat16(c < 16 ? outv[c] : 0.f);
     }

@@ -1327,7 +1327,10 @@ class DiscriminatorEngine(NetEngine):
                 elif (li == 0 and dx_channels is not None and dx_channels[1] == 1 and s.stride == 2 and taps_enabled()
                         and s.cout == s.np):
                     # only the generated-mask channel of the input gradient is read: tap products of dY with the 16 x Cout
-                    # slab W'[c = mask channel] of the data-gradient operand, scattered as a ConvTranspose2d
+                    # slab W'[c = mask channel] of the data-gradient operand, scattered as a ConvTranspose2d.  The result
+                    # gets a TRIMMED pixel stride (the channels up to the mask's, rounded to 4: 8 bytes per pixel instead
+                    # of 32), which is 4x fewer sectors for the scatter here and for the reader (pg_gen_out_bwd)
+                    din = new_act(B, Hi, Wi, (nv + 3) // 4 * 4, dev)
                     wslab = pw.bwd.data_ptr() + dx_channels[0] * 16 * s.np * 2
                     taps_forward(L.PG_CONVT, 2, 1, d_raw, None, wslab, None, 0, din, dx_channels[0])
                 elif s.stride == 2:

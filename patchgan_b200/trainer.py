@@ -332,7 +332,9 @@ class Trainer:
                 # the discriminator's Adam step (on s_d) rewrites the weights this data-gradient chain just read
                 ev_dread = torch.cuda.Event()
                 ev_dread.record()
-            d_raw = new_act(B, H, W, G.out_cp, dev)
+            # (one output channel: the generator's backward starts with a tap gather of channel 0 only -- trimmed 8-byte rows)
+            trim = cout == 1 and E.taps_enabled() and G.packed[-1].taps_ok
+            d_raw = new_act(B, H, W, 4 if trim else G.out_cp, dev)
             L.call('pg_gen_out_bwd', p.ptr, p.ld, y.data_ptr(), chp, coef.data_ptr(), d_dinp.ptr, d_dinp.ld, cin,
                    d_raw.ptr, d_raw.ld, B, cout, H * W, lt, L.ACT[gm.final_act], float(self.tversky_beta), st)
             ggrads = {n: q.grad for n, q in gm.named_parameters()}
