@@ -132,3 +132,22 @@ def test_pending_losses_builds_the_reference_loss_dict():
     assert d['disc'] == 0.375
     host[0] = 1.0                       # the pinned slot is recycled by a later submit: the handle keeps its values
     assert h.result() is d and h.done() and ev.waits == 1
+
+
+def test_integration_stub_structs_match_the_binding():
+    """The ctypes structures shown in INTEGRATION.md (what a maintainer of the reference would paste) have the layout of the
+    ones this package binds with (patchgan_b200/_lib.py), which the C side checks with static_asserts."""
+    import ctypes as C
+    import re
+    from patchgan_b200 import _lib as L
+    text = open(os.path.join(ROOT, 'INTEGRATION.md')).read()
+    blocks = re.findall(r'^class (Pg\w+)\(C\.Structure\):.*?(?=^\S|\Z)', text, flags=re.S | re.M)
+    assert set(blocks) >= {'PgConvDesc', 'PgFusedNorm'}, blocks
+    ns = {'C': C}
+    for name in ('PgConvDesc', 'PgFusedNorm'):
+        src = re.search(rf'^class {name}\(C\.Structure\):.*?(?=^\S)', text, flags=re.S | re.M).group(0)
+        exec(src, ns)
+    for stub, ours in ((ns['PgConvDesc'], L.ConvDesc), (ns['PgFusedNorm'], L.FusedNorm)):
+        assert C.sizeof(stub) == C.sizeof(ours), (stub, C.sizeof(stub), C.sizeof(ours))
+        assert [(n, getattr(stub, n).offset) for n, _ in stub._fields_] == \
+               [(n, getattr(ours, n).offset) for n, _ in ours._fields_], stub
