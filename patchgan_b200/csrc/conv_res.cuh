@@ -399,7 +399,16 @@ __device__ __forceinline__ void res_epilogue(const TcParams& p, const ResParams&
       if (norm_tile) res_stats16<KIND, ACT>(p, r, v, rp, n, seed, lane, lgP);
     }
     if (tracer) trace_raw(p.trace, 10, gtimer());
-    res_grid_barrier(r.sync + 1);
+    // The statistics of a unit's images are complete when every unit holding pixels of those images has added its sums.
+    // A conv-form tile that covers the whole map (maps up to 8 x 8: nx = ny = 1) holds ALL pixels of its images, and a unit
+    // = (tile, 16 channels) belongs to this group alone: the group's own fence + barrier is enough, no grid-wide wait for
+    // the slowest CTA.  (ConvTranspose2d-form tiles hold one output-parity class of an image: they need the grid.)
+    if (p.nx == 1 && p.ny == 1 && p.mode != PG_CONVT) {
+      __threadfence();
+      named_bar_sync(1 + grp, 128);
+    } else {
+      res_grid_barrier(r.sync + 1);
+    }
     if (tracer) trace_raw(p.trace, 11, gtimer());
     if (have) {
       // coefficient table of this group: [image of the tile][16 channels of the unit]
